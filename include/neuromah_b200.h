@@ -1,0 +1,193 @@
+/*
+ * neuromah_b200.h -- C ABI of libneuromah_b200.so (sm_100a).
+ *
+ * This is the drop-in boundary for Neuromah's training hot path.  Every entry
+ * point is `extern "C"`, takes plain device/host pointers and sizes, launches
+ * asynchronously on the caller's CUDA stream (a `cudaStream_t` passed as
+ * `void*`, NULL = legacy default stream) and returns an int status
+ * (0 = NM_OK, negative = error; text via nm_last_error()).  No torch types,
+ * no exceptions, never exit().
+ *
+ * Reference interfaces replaced (paths relative to the Neuromah repository):
+ *   - pybind11 module _Conv2DBackend_cpp   (src/layers/CPU_kernels/Conv2D.cpp:242-245,
+ *     call site src/layers/Conv_wrapepr.py:91)
+ *   - pybind11 module _MaxPooling2DBackend_cpp (CPU_kernels/maxpooling_backend.cpp:240-247,
+ *     call sites src/layers/MaxPooling2D.py:53-58, :73-80)
+ *   - the NumPy bodies of Layer_Dense.forward/backward (src/layers/Dense.py:64-108),
+ *     Activation_ReLU (src/activations/Relu.py:7-14), Activation_Softmax
+ *     (src/activations/Softmax.py:7-22), Loss_CategoricalCrossentropy.forward
+ *     (src/losses/categorical_crossentropy.py:8-25), the fused softmax-CE gradient
+ *     (src/losses/Activation_Softmax_Loss_CategoricalCrossentropy.py:4-19),
+ *     Optimizer_Adam.update_params (src/optimizers/Adam.py:49-100),
+ *     Optimizer_SGD.update_params (src/optimizers/SGD.py:55-97) and
+ *     federated_average (Federated/utils.py:20-23).
+ *
+ * Layouts: FP32 tensors are exactly the reference's (NCHW activations, OIHW conv
+ * weights, (in,out) Dense weights, row-major).  The bf16 tensor-core path
+ * (nm_tc_*) uses its own NHWC-padded activation layout, documented per call.
+ */
+#ifndef NEUROMAH_B200_H
+#define NEUROMAH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------- */
+#define NM_OK               0
+#define NM_ERR_BAD_ARG     -1   /* Python wrapper re-raises ValueError            */
+#define NM_ERR_CUDA        -2   /* RuntimeError (reference: std::runtime_error)   */
+#define NM_ERR_NCCL        -3
+#define NM_ERR_OOM         -4   /* MemoryError                                    */
+#define NM_ERR_UNSUPPORTED -5
+
+const char* nm_last_error(void);          /* thread-local, never NULL */
+int nm_version(void);                     /* ABI version of this header: 1 */
+
+/* ---- device, memory, streams, events, graphs ---------------------------- */
+int nm_device_count(int* count);
+int nm_init(int device);                  /* cudaSetDevice + context warm-up */
+int nm_device_props(int device, int* sm_count, int* cc_major, int* cc_minor,
+                    size_t* total_mem);
+int nm_malloc(void** dptr, size_t bytes);
+int nm_free(void* dptr);
+int nm_host_alloc(void** hptr, size_t bytes);       /* pinned host memory */
+int nm_host_free(void* hptr);
+int nm_memset(void* dptr, int byte, size_t bytes, void* stream);
+int nm_h2d(void* dst, const void* src, size_t bytes, void* stream);
+int nm_d2h(void* dst, const void* src, size_t bytes, void* stream);
+int nm_d2d(void* dst, const void* src, size_t bytes, void* stream);
+int nm_stream_create(void** stream);
+int nm_stream_destroy(void* stream);
+int nm_stream_sync(void* stream);
+int nm_device_sync(void);
+int nm_event_create(void** event);
+int nm_event_destroy(void* event);
+int nm_event_record(void* event, void* stream);
+int nm_event_sync(void* event);
+int nm_event_elapsed_ms(void* start, void* stop, float* ms);
+int nm_stream_wait_event(void* stream, void* event);
+int nm_graph_begin(void* stream);                        /* stream capture (thread-local mode) */
+int nm_graph_end(void* stream, void** graph_exec);
+int nm_graph_launch(void* graph_exec, void* stream);
+int nm_graph_destroy(void* graph_exec);
+/* number of kernels this library launched since process start (bench "gpu_launches") */
+int nm_launch_count(unsigned long long* count);
+
+/* ---- FP32-exact path (CUDA-core FMA, reference layouts) ------------------ */
+
+/* conv2d_cpu replacement (Conv2D.cpp:83-146) + the np.pad of Conv_wrapepr.py:78-84
+ * folded in as pad_* (zeros), + optional bias (NULL = reference behaviour, Q4)
+ * + optional ReLU epilogue (Conv_wrapepr.py:96-98).
+ * x[N,C,H,W], w[OC,C,kH,kW], y[N,OC,OH,OW], OH = H+pad_t+pad_b-kH+1, stride 1. */
+int nm_conv2d_fprop_f32(const float* x, const float* w, const float* bias, float* y,
+                        int N, int C, int H, int W, int OC, int kH, int kW,
+                        int pad_t, int pad_b, int pad_l, int pad_r, int relu, void* stream);
+/* dgrad of the above (conv2d_backward_cpu, Conv2D.cpp:218-222 + col2im :48-74),
+ * returned already cropped to the un-padded input: dx[N,C,H,W]. */
+int nm_conv2d_dgrad_f32(const float* dy, const float* w, float* dx,
+                        int N, int C, int H, int W, int OC, int kH, int kW,
+                        int pad_t, int pad_b, int pad_l, int pad_r, void* stream);
+/* wgrad (Conv2D.cpp:207-216: sum over batch, no normalisation) + bias gradient
+ * (Conv_wrapepr.py:107-109: sum over n,h,w -> [OC]).  dbias may be NULL.
+ * workspace: device scratch of nm_conv2d_wgrad_f32_workspace() bytes; the
+ * split-K partials are reduced in a fixed order (deterministic). */
+size_t nm_conv2d_wgrad_f32_workspace(int N, int C, int H, int W, int OC, int kH, int kW,
+                                     int pad_t, int pad_b, int pad_l, int pad_r);
+int nm_conv2d_wgrad_f32(const float* x, const float* dy, float* dw, float* dbias,
+                        void* workspace, size_t workspace_bytes,
+                        int N, int C, int H, int W, int OC, int kH, int kW,
+                        int pad_t, int pad_b, int pad_l, int pad_r, void* stream);
+
+/* Activation_ReLU forward / backward (Relu.py:7-14).  `ref` is the tensor the mask
+ * is taken from: ref <= 0 -> 0 (pre-activation and post-activation are equivalent). */
+int nm_relu_fwd_f32(const float* x, float* y, size_t n, void* stream);
+int nm_relu_bwd_f32(const float* dy, const float* ref, float* dx, size_t n, void* stream);
+
+/* maxpool2d_forward_cpu / maxpool2d_backward_cpu (maxpooling_backend.cpp:24-133, :145-238).
+ * idx[N,C,OH,OW,2] int32 = (row, col) of the max in PADDED coordinates; zero padding
+ * participates in the max; ties keep the first element of the row-major window scan. */
+int nm_maxpool2d_fwd_f32(const float* x, float* y, int32_t* idx,
+                         int N, int C, int H, int W, int ph, int pw, int sh, int sw,
+                         int pad_t, int pad_l, int OH, int OW, void* stream);
+int nm_maxpool2d_bwd_f32(const float* dy, const int32_t* idx, float* dx,
+                         int N, int C, int H, int W, int ph, int pw, int sh, int sw,
+                         int pad_t, int pad_l, int OH, int OW, void* stream);
+
+/* Layer_Dense.forward: y = x @ w + b (+ReLU)  (Dense.py:79-85). x[B,in] w[in,out] b[out] */
+int nm_dense_fprop_f32(const float* x, const float* w, const float* b, float* y,
+                       int B, int n_in, int n_out, int relu, void* stream);
+/* dinputs = dy @ w^T (Dense.py:108) */
+int nm_dense_dgrad_f32(const float* dy, const float* w, float* dx,
+                       int B, int n_in, int n_out, void* stream);
+/* dweights = x^T dy * scale + l1*sign(w) + 2*l2*w ; dbiases = sum dy * scale
+ * (Dense.py:96-105; scale = 1/batch -- the GLOBAL batch under data parallelism). */
+size_t nm_dense_wgrad_f32_workspace(int B, int n_in, int n_out);
+int nm_dense_wgrad_f32(const float* x, const float* dy, const float* w,
+                       float* dw, float* db, void* workspace, size_t workspace_bytes,
+                       int B, int n_in, int n_out, float scale, float l1, float l2,
+                       void* stream);
+
+/* Activation_Softmax.forward (Softmax.py:7-11): row softmax with max subtraction. */
+int nm_softmax_fwd_f32(const float* logits, float* probs, int B, int n, void* stream);
+/* Jacobian backward (Softmax.py:13-18), closed form s*(d - <s,d>). */
+int nm_softmax_bwd_f32(const float* probs, const float* dy, float* dx, int B, int n, void* stream);
+/* Loss_CategoricalCrossentropy.forward per-sample losses with clip [1e-7, 1-1e-7]
+ * (categorical_crossentropy.py:8-25), argmax==label flags (Accuracy_Categorical),
+ * and -- if dlogits != NULL -- the fused gradient (p - onehot)*inv_batch
+ * (Activation_Softmax_Loss_CategoricalCrossentropy.py:4-19).  labels = class ids.
+ * accum (may be NULL): double[2] device accumulators {sum of losses, #correct},
+ * updated by a single thread block in a fixed order (deterministic). */
+int nm_softmax_ce_f32(const float* probs, const int32_t* labels, float* dlogits,
+                      float* sample_loss, int32_t* correct, double* accum,
+                      int B, int n, float inv_batch, void* stream);
+/* Loss_CategoricalCrossentropy.backward: -onehot/p * inv_batch (:27-38) */
+int nm_cce_bwd_f32(const float* probs, const int32_t* labels, float* dx,
+                   int B, int n, float inv_batch, void* stream);
+
+/* ---- optimizers over a flat FP32 slab ------------------------------------ */
+/* Optimizer_Adam.update_params (Adam.py:86-100) applied n_apply times in registers
+ * with the same t (Model registers every trainable layer twice: Model.py:56-59,:82-83).
+ * bc1 = 1-beta1^(t+1), bc2 = 1-beta2^(t+1) computed by the host in double.
+ * One coalesced 128-bit pass: 28 B/param regardless of n_apply. */
+int nm_adam_step_f32(float* param, const float* grad, float* m, float* v, size_t n,
+                     float lr, float beta1, float beta2, float eps, float bc1, float bc2,
+                     int n_apply, void* stream);
+/* Graph-capturable variant: hyper-parameters live in a device struct that
+ * nm_adam_advance_f32 refreshes on the device each step (no host round trip). */
+typedef struct nm_adam_state {
+    float lr, beta1, beta2, eps;
+    float bc1, bc2, base_lr, decay;
+    long long iterations;
+    double beta1_pow, beta2_pow;      /* beta^(iterations+1) */
+} nm_adam_state;
+int nm_adam_state_init(nm_adam_state* dev_state, float lr, float decay, float beta1,
+                       float beta2, float eps, long long iterations, void* stream);
+int nm_adam_step_dev_f32(float* param, const float* grad, float* m, float* v, size_t n,
+                         const nm_adam_state* dev_state, int n_apply, void* stream);
+int nm_adam_advance_f32(nm_adam_state* dev_state, void* stream);   /* post_update_params */
+/* Optimizer_SGD.update_params (SGD.py:85-97); mom may be NULL when momentum == 0.
+ * nonfinite (may be NULL): device int set to 1 if any gradient is NaN/Inf (SGD.py:80-83). */
+int nm_sgd_step_f32(float* param, const float* grad, float* mom, size_t n,
+                    float lr, float momentum, int n_apply, int32_t* nonfinite, void* stream);
+/* y = a*x (+ y if accumulate): FedAvg pre-scale n_i/N (Federated/utils.py:21-22). */
+int nm_scale_f32(float* y, const float* x, size_t n, float a, int accumulate, void* stream);
+
+/* ---- bf16 tensor-core path (tcgen05 + TMA), see DESIGN.md ---------------- */
+/* Declared in the tensor-core section at the end of this header once built. */
+
+/* ---- data-parallel communication (NCCL over NVLink) ---------------------- */
+int nm_comm_load(const char* libnccl_path);                 /* dlopen libnccl.so.2 */
+int nm_comm_unique_id(void* id128);                          /* rank 0: 128-byte ncclUniqueId */
+int nm_comm_init(void** comm, const void* id128, int rank, int world);
+int nm_comm_destroy(void* comm);
+int nm_comm_allreduce_sum_f32(void* comm, float* buf, size_t n, void* stream);  /* in place */
+int nm_comm_broadcast_f32(void* comm, float* buf, size_t n, int root, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEUROMAH_B200_H */

@@ -1,0 +1,146 @@
+"""ctypes binding of libneuromah_b200.so (C ABI: include/neuromah_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a call
+fails, an exception is raised.  Error mapping follows SURVEY.md 8(b): bad
+arguments -> ValueError, CUDA failures -> RuntimeError (the reference's C++
+raised std::runtime_error -> RuntimeError), out of memory -> MemoryError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libneuromah_b200.so")
+
+NM_OK, NM_ERR_BAD_ARG, NM_ERR_CUDA, NM_ERR_NCCL, NM_ERR_OOM, NM_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+
+_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_pvp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); every int-returning function is status-checked.
+_SIGS = {
+    "nm_last_error": (C.c_char_p, []),
+    "nm_version": (_i, []),
+    "nm_device_count": (_i, [C.POINTER(_i)]),
+    "nm_init": (_i, [_i]),
+    "nm_device_props": (_i, [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz)]),
+    "nm_malloc": (_i, [_pvp, _sz]),
+    "nm_free": (_i, [_vp]),
+    "nm_host_alloc": (_i, [_pvp, _sz]),
+    "nm_host_free": (_i, [_vp]),
+    "nm_memset": (_i, [_vp, _i, _sz, _vp]),
+    "nm_h2d": (_i, [_vp, _vp, _sz, _vp]),
+    "nm_d2h": (_i, [_vp, _vp, _sz, _vp]),
+    "nm_d2d": (_i, [_vp, _vp, _sz, _vp]),
+    "nm_stream_create": (_i, [_pvp]),
+    "nm_stream_destroy": (_i, [_vp]),
+    "nm_stream_sync": (_i, [_vp]),
+    "nm_device_sync": (_i, []),
+    "nm_event_create": (_i, [_pvp]),
+    "nm_event_destroy": (_i, [_vp]),
+    "nm_event_record": (_i, [_vp, _vp]),
+    "nm_event_sync": (_i, [_vp]),
+    "nm_event_elapsed_ms": (_i, [_vp, _vp, C.POINTER(_f)]),
+    "nm_stream_wait_event": (_i, [_vp, _vp]),
+    "nm_graph_begin": (_i, [_vp]),
+    "nm_graph_end": (_i, [_vp, _pvp]),
+    "nm_graph_launch": (_i, [_vp, _vp]),
+    "nm_graph_destroy": (_i, [_vp]),
+    "nm_launch_count": (_i, [C.POINTER(C.c_ulonglong)]),
+    "nm_conv2d_fprop_f32": (_i, [_vp, _vp, _vp, _vp] + [_i] * 12 + [_vp]),
+    "nm_conv2d_dgrad_f32": (_i, [_vp, _vp, _vp] + [_i] * 11 + [_vp]),
+    "nm_conv2d_wgrad_f32_workspace": (_sz, [_i] * 11),
+    "nm_conv2d_wgrad_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _sz] + [_i] * 11 + [_vp]),
+    "nm_relu_fwd_f32": (_i, [_vp, _vp, _sz, _vp]),
+    "nm_relu_bwd_f32": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "nm_maxpool2d_fwd_f32": (_i, [_vp, _vp, _vp] + [_i] * 12 + [_vp]),
+    "nm_maxpool2d_bwd_f32": (_i, [_vp, _vp, _vp] + [_i] * 12 + [_vp]),
+    "nm_dense_fprop_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "nm_dense_dgrad_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "nm_dense_wgrad_f32_workspace": (_sz, [_i, _i, _i]),
+    "nm_dense_wgrad_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _f, _f, _vp]),
+    "nm_softmax_fwd_f32": (_i, [_vp, _vp, _i, _i, _vp]),
+    "nm_softmax_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "nm_softmax_ce_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "nm_cce_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp]),
+    "nm_adam_step_f32": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _f, _i, _vp]),
+    "nm_adam_state_init": (_i, [_vp, _f, _f, _f, _f, _f, C.c_longlong, _vp]),
+    "nm_adam_step_dev_f32": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
+    "nm_adam_advance_f32": (_i, [_vp, _vp]),
+    "nm_sgd_step_f32": (_i, [_vp, _vp, _vp, _sz, _f, _f, _i, _vp, _vp]),
+    "nm_scale_f32": (_i, [_vp, _vp, _sz, _f, _i, _vp]),
+    "nm_comm_load": (_i, [C.c_char_p]),
+    "nm_comm_unique_id": (_i, [_vp]),
+    "nm_comm_init": (_i, [_pvp, _vp, _i, _i]),
+    "nm_comm_destroy": (_i, [_vp]),
+    "nm_comm_allreduce_sum_f32": (_i, [_vp, _vp, _sz, _vp]),
+    "nm_comm_broadcast_f32": (_i, [_vp, _vp, _sz, _i, _vp]),
+}
+
+_UNCHECKED = {"nm_last_error", "nm_version", "nm_conv2d_wgrad_f32_workspace", "nm_dense_wgrad_f32_workspace"}
+
+
+class NeuromahB200Error(RuntimeError):
+    pass
+
+
+def _raise(name: str, rc: int, dll):
+    msg = dll.nm_last_error().decode("utf-8", "replace")
+    text = f"{name} failed ({rc}): {msg}"
+    if rc == NM_ERR_BAD_ARG:
+        raise ValueError(text)
+    if rc == NM_ERR_OOM:
+        raise MemoryError(text)
+    raise NeuromahB200Error(text)
+
+
+class _Lib:
+    """Lazily loaded library; attribute access returns status-checked callables."""
+
+    def __init__(self):
+        self._dll = None
+
+    def load(self):
+        if self._dll is not None:
+            return self._dll
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(neuromah_b200 has no CPU fallback)")
+        dll = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(dll, name)          # AttributeError if the .so is stale
+            fn.restype, fn.argtypes = res, args
+        self._dll = dll
+        return dll
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        dll = self.load()
+        fn = getattr(dll, name)
+        if name in _UNCHECKED:
+            return fn
+
+        def checked(*a, _fn=fn, _name=name):
+            rc = _fn(*a)
+            if rc != 0:
+                _raise(_name, rc, dll)
+            return rc
+        checked.__name__ = name
+        setattr(self, name, checked)
+        return checked
+
+
+lib = _Lib()
+
+
+def declared_symbols(header_path: str | None = None):
+    """Names of every function declared in include/neuromah_b200.h (for the ABI test)."""
+    import re
+    if header_path is None:
+        header_path = os.path.join(os.path.dirname(_HERE), "include", "neuromah_b200.h")
+    text = open(header_path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nm_[a-z0-9_]+)\s*\(", text)))

@@ -1,0 +1,288 @@
+"""Device memory for the hot path: a small array type over the C ABI.
+
+``DeviceArray`` is what the layers' ``output`` / ``dinputs`` / ``weights`` /
+gradient attributes hold.  It quacks enough like ``numpy.ndarray`` for the
+reference's scripts (``shape``, ``dtype``, ``len``, leading-axis slicing,
+``np.asarray(x)`` via ``__array__``) while the data stays in HBM.  PyTorch is
+not involved; memory comes from ``nm_malloc`` and every launch goes to one
+process-wide non-blocking stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._lib import lib
+
+_state = {"device": None, "stream": None}
+
+
+def init(device: int | None = None):
+    """Select the GPU (default: LOCAL_RANK or 0) and create the library stream."""
+    if _state["device"] is not None and (device is None or device == _state["device"]):
+        return _state["device"]
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    n = C.c_int(0)
+    lib.nm_device_count(C.byref(n))
+    if n.value <= 0:
+        raise RuntimeError("neuromah_b200: no CUDA device visible (there is no CPU fallback)")
+    lib.nm_init(device % n.value)
+    s = C.c_void_p()
+    lib.nm_stream_create(C.byref(s))
+    _state["device"], _state["stream"] = device % n.value, s
+    return _state["device"]
+
+
+def stream():
+    if _state["stream"] is None:
+        init()
+    return _state["stream"]
+
+
+def synchronize():
+    lib.nm_stream_sync(stream())
+
+
+def launch_count() -> int:
+    n = C.c_ulonglong(0)
+    lib.nm_launch_count(C.byref(n))
+    return int(n.value)
+
+
+class _Block:
+    """Owner of one cudaMalloc'd block."""
+    __slots__ = ("ptr", "nbytes")
+
+    def __init__(self, nbytes: int):
+        init()
+        p = C.c_void_p()
+        lib.nm_malloc(C.byref(p), max(int(nbytes), 16))
+        self.ptr, self.nbytes = p.value, int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib.nm_free(C.c_void_p(self.ptr))
+                self.ptr = None
+        except Exception:
+            pass
+
+
+_pinned_ranges = []      # (start, end) of live page-locked host blocks
+
+
+def pinned_address(arr) -> int | None:
+    """Host address of ``arr`` if it is a C-contiguous NumPy view into page-locked memory."""
+    if not isinstance(arr, np.ndarray) or not arr.flags["C_CONTIGUOUS"]:
+        return None
+    a = arr.ctypes.data
+    for lo, hi in _pinned_ranges:
+        if lo <= a and a + arr.nbytes <= hi:
+            return a
+    return None
+
+
+def new_stream():
+    s = C.c_void_p()
+    lib.nm_stream_create(C.byref(s))
+    return s
+
+
+def new_event():
+    e = C.c_void_p()
+    lib.nm_event_create(C.byref(e))
+    return e
+
+
+class PinnedBuffer:
+    """Page-locked host buffer exposed as a NumPy array (for async H2D / D2H)."""
+
+    def __init__(self, shape, dtype=np.float32):
+        init()
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        count = int(np.prod(self.shape))
+        self.nbytes = count * self.dtype.itemsize
+        p = C.c_void_p()
+        lib.nm_host_alloc(C.byref(p), max(self.nbytes, 16))
+        self.ptr = p.value
+        _pinned_ranges.append((self.ptr, self.ptr + max(self.nbytes, 16)))
+        buf = (C.c_byte * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=count).reshape(self.shape)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.array = None
+                _pinned_ranges[:] = [r for r in _pinned_ranges if r[0] != self.ptr]
+                lib.nm_host_free(C.c_void_p(self.ptr))
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class DeviceArray:
+    """Contiguous row-major tensor in HBM (float32 / int32 / uint8 / uint16=bf16 bits / float64)."""
+
+    __array_priority__ = 100
+
+    def __init__(self, shape, dtype=np.float32, *, block: _Block | None = None, offset: int = 0):
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.size = int(np.prod(self.shape)) if len(self.shape) else 1
+        self.nbytes = self.size * self.dtype.itemsize
+        self._block = block if block is not None else _Block(self.nbytes)
+        self._offset = int(offset)
+        if self._offset + self.nbytes > max(self._block.nbytes, 16):
+            raise ValueError("DeviceArray view exceeds its block")
+
+    # -- basic properties -----------------------------------------------------
+    @property
+    def ptr(self) -> int:
+        return self._block.ptr + self._offset
+
+    @property
+    def p(self):
+        return C.c_void_p(self.ptr)
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __repr__(self):
+        return f"DeviceArray(shape={self.shape}, dtype={self.dtype}, ptr=0x{self.ptr:x})"
+
+    # -- construction -----------------------------------------------------------
+    @classmethod
+    def from_numpy(cls, arr, dtype=None):
+        a = np.ascontiguousarray(arr, dtype=dtype)
+        out = cls(a.shape, a.dtype)
+        out.copy_from(a)
+        return out
+
+    @classmethod
+    def zeros(cls, shape, dtype=np.float32):
+        out = cls(shape, dtype)
+        out.fill_zero()
+        return out
+
+    # -- data movement ------------------------------------------------------------
+    def copy_from(self, arr):
+        """Host (or device) -> this array.  Pageable host sources are synchronous."""
+        if isinstance(arr, DeviceArray):
+            if arr.nbytes != self.nbytes:
+                raise ValueError("size mismatch")
+            lib.nm_d2d(self.p, arr.p, self.nbytes, stream())
+            return self
+        a = np.ascontiguousarray(arr, dtype=self.dtype)
+        if a.size != self.size:
+            raise ValueError(f"cannot copy array of shape {a.shape} into DeviceArray of shape {self.shape}")
+        lib.nm_h2d(self.p, a.ctypes.data_as(C.c_void_p), self.nbytes, stream())
+        synchronize()          # pageable source: keep `a` alive until the copy has landed
+        return self
+
+    def copy_from_pinned(self, pinned: PinnedBuffer, nbytes: int | None = None):
+        """Asynchronous host -> device from page-locked memory (no sync)."""
+        lib.nm_h2d(self.p, C.c_void_p(pinned.ptr), self.nbytes if nbytes is None else nbytes, stream())
+        return self
+
+    def numpy(self) -> np.ndarray:
+        out = np.empty(self.shape, dtype=self.dtype)
+        if self.nbytes:
+            lib.nm_d2h(out.ctypes.data_as(C.c_void_p), self.p, self.nbytes, stream())
+            synchronize()
+        return out
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def fill_zero(self):
+        lib.nm_memset(self.p, 0, self.nbytes, stream())
+        return self
+
+    def copy(self):
+        out = DeviceArray(self.shape, self.dtype)
+        lib.nm_d2d(out.p, self.p, self.nbytes, stream())
+        return out
+
+    # -- views ------------------------------------------------------------------
+    def reshape(self, *shape):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        shape = list(shape)
+        if -1 in shape:
+            known = int(np.prod([s for s in shape if s != -1])) or 1
+            shape[shape.index(-1)] = self.size // known
+        if int(np.prod(shape)) != self.size:
+            raise ValueError(f"cannot reshape {self.shape} into {tuple(shape)}")
+        return DeviceArray(shape, self.dtype, block=self._block, offset=self._offset)
+
+    def __getitem__(self, key):
+        # contiguous leading-axis slices stay on the device (batch slicing, Model.py:150-151)
+        if isinstance(key, slice) and self.ndim >= 1:
+            start, stop, step = key.indices(self.shape[0])
+            if step == 1:
+                rows = max(stop - start, 0)
+                row_bytes = (self.nbytes // self.shape[0]) if self.shape[0] else 0
+                return DeviceArray((rows,) + self.shape[1:], self.dtype, block=self._block,
+                                   offset=self._offset + start * row_bytes)
+        return self.numpy()[key]
+
+    @property
+    def T(self):
+        return self.numpy().T
+
+    def astype(self, dtype, copy=True):
+        return self.numpy().astype(dtype)
+
+    def tolist(self):
+        return self.numpy().tolist()
+
+
+def as_device(x, dtype=np.float32) -> DeviceArray:
+    """NumPy (or anything array-like) -> DeviceArray of ``dtype``; DeviceArray passes through."""
+    if isinstance(x, DeviceArray):
+        if x.dtype != np.dtype(dtype):
+            raise TypeError(f"expected a {np.dtype(dtype)} DeviceArray, got {x.dtype}")
+        return x
+    return DeviceArray.from_numpy(np.asarray(x), dtype=dtype)
+
+
+def is_array(x) -> bool:
+    return isinstance(x, (np.ndarray, DeviceArray))
+
+
+def labels_to_device(y) -> DeviceArray:
+    """Class ids (int32) on the device from sparse labels or one-hot rows.
+
+    One-hot rows are reduced with argmax exactly as the reference's fused
+    gradient does (Activation_Softmax_Loss_CategoricalCrossentropy.py:11-12).
+    """
+    if isinstance(y, DeviceArray):
+        if y.dtype == np.int32 and y.ndim == 1:
+            return y
+        y = y.numpy()
+    y = np.asarray(y)
+    if y.ndim == 2:
+        y = np.argmax(y, axis=1)
+    elif y.ndim != 1:
+        raise ValueError("y_true must be either sparse labels or one-hot encoded")
+    return DeviceArray.from_numpy(y, dtype=np.int32)
+
+
+class Scratch:
+    """Grow-only device scratch buffer (split-K partials, loss staging)."""
+
+    def __init__(self):
+        self._buf = None
+
+    def get(self, nbytes: int) -> DeviceArray:
+        if self._buf is None or self._buf.nbytes < nbytes:
+            self._buf = DeviceArray((max(int(nbytes), 16),), np.uint8)
+        return self._buf

@@ -1,0 +1,112 @@
+"""Data-parallel plumbing: one process per GPU, NCCL all-reduce of the gradient slab.
+
+Sharding: rank r owns rows [r*b, (r+1)*b) of every global batch.  The
+softmax-CE gradient and the Dense parameter gradients are divided by the GLOBAL batch
+(``set_global_batch``), conv gradients are unnormalised sums of already-scaled dvalues, so
+a plain SUM all-reduce of the gradient slab reproduces the single-GPU batch-B step exactly.
+
+Bootstrap uses torch.distributed (whatever backend the launcher initialised; gloo works)
+only to ship the 128-byte NCCL unique id; the data path is our own communicator on our
+own stream (nm_comm_*).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+
+from ._lib import lib
+from .device import stream
+
+
+def shard_bounds(n: int, rank: int, world: int):
+    """Contiguous shard [lo, hi) of n rows for ``rank``; n must divide evenly."""
+    if n % world:
+        raise ValueError(f"global batch {n} is not divisible by world size {world}")
+    b = n // world
+    return rank * b, (rank + 1) * b
+
+
+def set_global_batch(model, global_batch: int | None):
+    """Make every batch-normalised gradient divide by the global batch (None = local)."""
+    from .src.layers.Dense import Layer_Dense
+    for layer in model.layers:
+        if isinstance(layer, Layer_Dense):
+            layer.grad_batch = global_batch
+    if model.softmax_classifier_output is not None:
+        model.softmax_classifier_output.grad_batch = global_batch
+
+
+def find_libnccl() -> str:
+    """Prefer the NCCL wheel next to torch (2.28.x), fall back to the system library."""
+    try:
+        import nvidia.nccl as _n      # type: ignore
+        for root in list(getattr(_n, "__path__", [])):
+            hits = glob.glob(os.path.join(root, "lib", "libnccl.so*"))
+            if hits:
+                return sorted(hits)[0]
+    except Exception:
+        pass
+    return "libnccl.so.2"
+
+
+class Communicator:
+    """NCCL communicator owned by libneuromah_b200 (one per process)."""
+
+    def __init__(self, rank: int, world: int, unique_id: bytes | None = None):
+        self.rank, self.world = rank, world
+        self.handle = None
+        if world == 1:
+            return
+        lib.nm_comm_load(find_libnccl().encode())
+        if unique_id is None:
+            unique_id = self._exchange_id()
+        h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, 128)
+        lib.nm_comm_init(C.byref(h), buf, rank, world)
+        self.handle = h
+
+    def _exchange_id(self) -> bytes:
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised to bootstrap the NCCL id")
+        t = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = C.create_string_buffer(128)
+            lib.nm_comm_unique_id(buf)
+            t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=0)
+        return bytes(t.cpu().numpy().tobytes())
+
+    def allreduce(self, arr, count=None):
+        if self.world == 1:
+            return
+        lib.nm_comm_allreduce_sum_f32(self.handle, arr.p, arr.size if count is None else count, stream())
+
+    def allreduce_grads(self, arena):
+        self.allreduce(arena.grads, arena.total)
+
+    def broadcast(self, arr, root=0, count=None):
+        if self.world == 1:
+            return
+        lib.nm_comm_broadcast_f32(self.handle, arr.p, arr.size if count is None else count, root, stream())
+
+    def close(self):
+        if self.handle is not None:
+            lib.nm_comm_destroy(self.handle)
+            self.handle = None
+
+
+def attach(model, comm: Communicator, global_batch: int):
+    """Turn ``model`` into one data-parallel replica: global-batch normalisation + grad all-reduce,
+    and identical initial weights on every rank (broadcast from rank 0)."""
+    model.comm = comm if comm.world > 1 else None
+    set_global_batch(model, global_batch)
+    if comm.world > 1:
+        comm.broadcast(model.arena.params, 0, model.arena.total)
+    return model

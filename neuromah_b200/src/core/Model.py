@@ -1,0 +1,416 @@
+"""Model: the Keras-like driver, GPU resident (reference: src/core/Model.py:11-417).
+
+add / set / finalize / train / evaluate / predict / forward / backward /
+get_parameters / set_parameters / save(_parameters) / load(_parameters) keep the
+reference's signatures and step order (Model.py:154-174).  Differences, all to keep
+the host out of the hot loop:
+  * the data set and labels are staged in HBM once per train() call (or streamed
+    through pinned double buffers when ``stream_batches=True``); batch slicing
+    (Model.py:150-151) is a pointer offset
+  * the running loss / accuracy sums live in a device accumulator and are read
+    back once per epoch
+  * finalize() adopts all parameters into a flat arena (neuromah_b200/arena.py) so
+    the optimizer is one launch and the gradient slab is the all-reduce buffer
+  * the end-of-epoch "forward over the entire X" (Model.py:199) runs in batches.
+finalize() registers every trainable layer twice exactly as the reference does
+(Model.py:56-59 and :82-83) unless config.duplicate_trainable_registration
+is cleared.
+"""
+import copy
+import pickle
+import time
+
+import numpy as np
+
+from ... import config, ops
+from ...arena import ParamArena
+import ctypes as C
+
+from ..._lib import lib
+from ...device import (DeviceArray, PinnedBuffer, as_device, labels_to_device, new_event, new_stream,
+                       pinned_address, stream, synchronize)
+from ..layers.Input import Layer_Input
+from ..layers.Conv_wrapepr import Layer_Conv2D
+
+
+class Model:
+    xp = np
+
+    def __init__(self, device=None):
+        self.layers = []
+        self.softmax_classifier_output = None
+        self.loss = None
+        self.accuracy = None
+        self.optimizer = None
+        self.tensorMonitor = None
+        self.arena = None
+        self.comm = None                   # data-parallel communicator (neuromah_b200.parallel)
+        self.epoch_end_accuracy = True     # Model.py:199-201: forward over the whole X after each epoch
+        self.device = device
+
+    def add(self, layer):
+        layer.xp = Model.xp
+        layer.model = self
+        self.layers.append(layer)
+
+    def set(self, *, loss=None, optimizer=None, accuracy=None, tensorMonitor=None):
+        if loss is None:
+            raise ValueError("A loss object needs to be passed to the set contructor")
+        if optimizer is None:
+            raise ValueError("An optimizer object needs to be passed to the set contructor")
+        if accuracy is None:
+            raise ValueError("A metrics object needs to be passed to the set contructor")
+        self.loss, self.optimizer, self.accuracy = loss, optimizer, accuracy
+        self.tensorMonitor = tensorMonitor
+
+    def finalize(self, xp=np):
+        from ..activations import Activation_Softmax
+        from ..losses import Loss_CategoricalCrossentropy
+        from ..losses.Activation_Softmax_Loss_CategoricalCrossentropy import \
+            Activation_Softmax_Loss_CategoricalCrossentropy
+
+        self.input_layer = Layer_Input()
+        n = len(self.layers)
+        if n < 2:
+            raise IndexError("Model.finalize needs at least two layers")     # Model.py:67 indexes layers[i+1]
+        unique = [l for l in self.layers if hasattr(l, "weights")]
+        self.trainable_layers = list(unique) if config.duplicate_trainable_registration else []
+        for i, layer in enumerate(self.layers):
+            layer.prev = self.input_layer if i == 0 else self.layers[i - 1]
+            if i < n - 1:
+                layer.next = self.layers[i + 1]
+            else:
+                layer.next = self.loss
+                self.output_layer_activation = layer
+            if hasattr(layer, "weights"):
+                self.trainable_layers.append(layer)
+        if isinstance(self.loss, type):
+            self.loss = self.loss(model=self)
+        if isinstance(self.accuracy, type):
+            self.accuracy = self.accuracy(model=self)
+        if isinstance(self.layers[-1], Activation_Softmax) and isinstance(self.loss, Loss_CategoricalCrossentropy):
+            self.softmax_classifier_output = Activation_Softmax_Loss_CategoricalCrossentropy()
+        # no consumer for the first layer's input gradient: skip the first conv dgrad
+        if isinstance(self.layers[0], Layer_Conv2D):
+            self.layers[0].compute_dinputs = False
+        # flat arena + optimizer state slabs
+        self.arena = ParamArena(unique)
+        self._n_apply = {id(l): sum(1 for t in self.trainable_layers if t is l) for l in unique}
+        if hasattr(self.optimizer, "bind_arena"):
+            self.optimizer.bind_arena(self.arena)
+        self._accum = DeviceArray.zeros((2,), np.float64)        # {sum of losses, #correct}
+        if self.tensorMonitor:
+            self.tensorMonitor.start_run(self)
+
+    # ------------------------------------------------------------------ steps ----
+    def _steps(self, n, batch_size):
+        if batch_size is None:
+            return 1
+        steps = n // batch_size
+        return steps + 1 if steps * batch_size < n else steps
+
+    def _optimizer_step(self):
+        """pre_update / update_params x layers / post_update (Model.py:171-174)."""
+        opt = self.optimizer
+        opt.pre_update_params()
+        counts = set(self._n_apply.values())
+        if hasattr(opt, "update_arena") and len(counts) == 1:
+            opt.update_arena(self.arena, n_apply=counts.pop())
+        else:
+            for layer in self.trainable_layers:
+                opt.update_params(layer)
+        opt.post_update_params()
+
+    def _device_loss_acc(self, output, labels):
+        """Accumulate sum of CCE losses and #correct for this batch on the device."""
+        ops.softmax_ce(output, labels, want_grad=False, accum=self._accum, holder=self)
+
+    def train_step(self, batch_X, batch_y):
+        """One step of Model.train's loop body with device-side loss/accuracy sums."""
+        output = self.forward(batch_X, training=True)
+        labels = labels_to_device(batch_y)
+        self._device_loss_acc(output, labels)
+        self.backward(output, labels)
+        if self.comm is not None:
+            self.comm.allreduce_grads(self.arena)
+        self._optimizer_step()
+        return output
+
+    def _fast_path_ok(self):
+        from ..losses import Loss_CategoricalCrossentropy
+        return self.softmax_classifier_output is not None and isinstance(self.loss, Loss_CategoricalCrossentropy)
+
+    def _read_accum(self, reset=True):
+        s = self._accum.numpy()
+        if reset:
+            self._accum.fill_zero()
+        return float(s[0]), float(s[1])
+
+    def train(self, X, y, *, epochs=1, batch_size=None, verbose=1, validation_data=None, xp=np,
+              stream_batches=False):
+        self.accuracy.init(y)
+        n = len(X)
+        train_steps = self._steps(n, batch_size)
+        bs = n if batch_size is None else batch_size
+        if not self._fast_path_ok():
+            return self._train_generic(X, y, epochs=epochs, batch_size=batch_size, verbose=verbose,
+                                       validation_data=validation_data)
+        feeder = _BatchFeeder(X, _host_labels(y), bs, stream_batches)
+        self.h2d_bytes = self.d2h_bytes = 0
+        ring = PinnedBuffer((64, 2), np.float64) if feeder.stream else None
+        for epoch in range(1, epochs + 1):
+            start_time = time.time()
+            self.loss.new_pass()
+            self.accuracy.new_pass()
+            self._accum.fill_zero()
+            if self.tensorMonitor:
+                self.tensorMonitor.start_epoch(epoch)
+            feeder.rewind() if feeder.stream else None
+            for step in range(train_steps):
+                self.train_step(*feeder.batch(step))
+                feeder.release(step, train_steps)
+                if ring is not None:      # streamed mode: the step's running loss/accuracy sums go back to the host
+                    lib.nm_d2h(C.c_void_p(ring.ptr + 16 * (step % 64)), self._accum.p, 16, stream())
+                    self.d2h_bytes += 16
+            loss_sum, _ = self._read_accum()
+            self.h2d_bytes = feeder.h2d_bytes
+            epoch_time = time.time() - start_time
+            self.loss.accumulated_sum, self.loss.accumulated_count = loss_sum, n
+            epoch_losses = self.loss.calculate_accumulated(include_regularization=True)
+            epoch_data_loss = epoch_losses["data_loss"]
+            epoch_regularization_loss = epoch_losses.get("regularization_loss", 0)
+            epoch_loss = epoch_data_loss + epoch_regularization_loss
+            # accuracy of the post-epoch weights over the whole training set (Model.py:199-201), batched
+            if self.epoch_end_accuracy:
+                feeder.rewind() if feeder.stream else None
+                for step in range(train_steps):
+                    xb, lb = feeder.batch(step)
+                    self._device_loss_acc(self.forward(xb, training=False), lb)
+                    feeder.release(step, train_steps)
+                _, correct = self._read_accum()
+            else:
+                correct = float("nan")
+            epoch_accuracy = correct / n
+            self.accuracy.accumulated_sum += correct
+            self.accuracy.accumulated_count += n
+            if self.tensorMonitor:
+                self.tensorMonitor.log_scalar("loss/epoch_training", epoch_loss)
+                self.tensorMonitor.log_scalar("accuracy/epoch_training", epoch_accuracy)
+                for layer in self.trainable_layers:
+                    self.tensorMonitor.log_layer_parameters(layer)
+                self.tensorMonitor.end_epoch()
+            if verbose:
+                print(f"time: {epoch_time:.2f}s, acc: {epoch_accuracy:.3f}, loss: {epoch_loss:.3f} ("
+                      f"data_loss: {epoch_data_loss:.3f}, reg_loss: {epoch_regularization_loss:.3f}), "
+                      f"lr: {self.optimizer.current_learning_rate:.7f}")
+            self.last_epoch = {"time": epoch_time, "acc": epoch_accuracy, "loss": epoch_loss,
+                               "data_loss": epoch_data_loss}
+            if validation_data is not None:
+                self.evaluate(*validation_data, batch_size=batch_size, verbose=verbose)
+        if self.tensorMonitor:
+            self.tensorMonitor.save_logs()
+
+    def _train_generic(self, X, y, *, epochs, batch_size, verbose, validation_data):
+        """The reference's loop verbatim in structure (any loss / last layer); host-side sums."""
+        train_steps = self._steps(len(X), batch_size)
+        for epoch in range(1, epochs + 1):
+            start_time = time.time()
+            self.loss.new_pass()
+            self.accuracy.new_pass()
+            for step in range(train_steps):
+                sl = slice(None) if batch_size is None else slice(step * batch_size, (step + 1) * batch_size)
+                batch_X, batch_y = X[sl], y[sl]
+                output = self.forward(batch_X, training=True)
+                self.loss.calculate(output, batch_y, include_regularization=True)
+                predictions = self.output_layer_activation.predictions(output)
+                self.accuracy.calculate(predictions, batch_y)
+                self.backward(output, batch_y)
+                if self.comm is not None:
+                    self.comm.allreduce_grads(self.arena)
+                self._optimizer_step()
+            epoch_time = time.time() - start_time
+            losses = self.loss.calculate_accumulated(include_regularization=True)
+            output = self.forward(X, training=False)
+            acc = self.accuracy.calculate(self.output_layer_activation.predictions(output), y)
+            if verbose:
+                print(f"time: {epoch_time:.2f}s, acc: {acc:.3f}, loss: "
+                      f"{losses['data_loss'] + losses.get('regularization_loss', 0):.3f} ("
+                      f"data_loss: {losses['data_loss']:.3f}, reg_loss: {losses.get('regularization_loss', 0):.3f}), "
+                      f"lr: {self.optimizer.current_learning_rate:.7f}")
+            if validation_data is not None:
+                self.evaluate(*validation_data, batch_size=batch_size, verbose=verbose)
+
+    def evaluate(self, X_val, y_val, *, batch_size=None, verbose=1):
+        n = len(X_val)
+        steps = self._steps(n, batch_size)
+        bs = n if batch_size is None else batch_size
+        self.loss.new_pass()
+        self.accuracy.new_pass()
+        if self._fast_path_ok():
+            feeder = _BatchFeeder(X_val, _host_labels(y_val), bs, False)
+            self._accum.fill_zero()
+            for step in range(steps):
+                xb, lb = feeder.batch(step)
+                self._device_loss_acc(self.forward(xb, training=False), lb)
+            loss_sum, correct = self._read_accum()
+            self.loss.accumulated_sum, self.loss.accumulated_count = loss_sum, n
+            self.accuracy.accumulated_sum, self.accuracy.accumulated_count = correct, n
+        else:
+            for step in range(steps):
+                sl = slice(None) if batch_size is None else slice(step * batch_size, (step + 1) * batch_size)
+                output = self.forward(X_val[sl], training=False)
+                self.loss.calculate(output, y_val[sl])
+                self.accuracy.calculate(self.output_layer_activation.predictions(output), y_val[sl])
+        validation_data_loss = self.loss.calculate_accumulated()["data_loss"]
+        validation_accuracy = self.accuracy.calculate_accumulated()
+        if verbose:
+            print(f"validation, acc: {validation_accuracy:.3f}, loss: {validation_data_loss:.3f}")
+        return {"acc": float(validation_accuracy), "loss": float(validation_data_loss)}
+
+    def predict(self, X, *, batch_size=None):
+        steps = self._steps(len(X), batch_size)
+        output = []
+        for step in range(steps):
+            batch_X = X if batch_size is None else X[step * batch_size:(step + 1) * batch_size]
+            output.append(np.asarray(self.forward(batch_X, training=False)))
+        return np.vstack(output)
+
+    # --------------------------------------------------- forward / backward ----
+    def forward(self, X, training):
+        self.input_layer.forward(X, training)
+        for layer in self.layers:
+            layer.forward(layer.prev.output, training)
+        return layer.output
+
+    def backward(self, output, y):
+        if self.softmax_classifier_output is not None:
+            self.softmax_classifier_output.backward(output, y)
+            self.layers[-1].dinputs = self.softmax_classifier_output.dinputs
+            for layer in reversed(self.layers[:-1]):
+                layer.backward(layer.next.dinputs)
+            return
+        self.loss.backward(output, y)
+        for layer in reversed(self.layers):
+            layer.backward(layer.next.dinputs)
+
+    # ------------------------------------------------------------ parameters ----
+    def get_parameters(self):
+        return [layer.get_parameters() for layer in self.trainable_layers]
+
+    def set_parameters(self, parameters):
+        """Accepts the reference's list of {"weights": (W, dW), "biases": (b, db)} dicts
+        (the reference's own ``layer.set_parameters(*parameter_set)`` unpacks the dict KEYS,
+        Model.py:380-381, and cannot load what save_parameters wrote; we read the values)."""
+        for parameter_set, layer in zip(parameters, self.trainable_layers):
+            if isinstance(parameter_set, dict):
+                w, b = parameter_set["weights"], parameter_set["biases"]
+                w = w[0] if isinstance(w, tuple) else w
+                b = b[0] if isinstance(b, tuple) else b
+                layer.set_parameters(np.asarray(w), np.asarray(b))
+            else:
+                layer.set_parameters(*parameter_set)
+
+    def save_parameters(self, path):
+        host = [{k: (np.asarray(p), np.asarray(g)) for k, (p, g) in d.items()} for d in self.get_parameters()]
+        with open(path, "wb") as f:
+            pickle.dump(host, f)
+
+    def load_parameters(self, path):
+        with open(path, "rb") as f:
+            self.set_parameters(pickle.load(f))
+
+
+def _host_labels(y):
+    """Class ids from sparse labels or one-hot rows (argmax, as the reference's fused gradient does)."""
+    if isinstance(y, DeviceArray):
+        return y if (y.dtype == np.int32 and y.ndim == 1) else _host_labels(y.numpy())
+    y = np.asarray(y)
+    if y.ndim == 2:
+        return np.argmax(y, axis=1).astype(np.int32)
+    if y.ndim != 1:
+        raise ValueError("y_true must be either sparse labels or one-hot encoded")
+    return y.astype(np.int32)
+
+
+class _BatchFeeder:
+    """Supplies batch ``step`` as (X DeviceArray, labels DeviceArray).
+
+    staged   (default)       : the whole data set and the labels are uploaded once; a batch is a
+                               pointer offset (Model.py:150-151 becomes free).
+    streamed (stream_batches): every step's inputs are copied host->device inside the step, on a
+                               separate copy stream, double-buffered so the upload of step k+1
+                               overlaps the compute of step k.  Page-locked sources
+                               (device.PinnedBuffer.array) are DMA'd in place; pageable sources are
+                               staged through two pinned buffers first.
+    """
+
+    def __init__(self, X, labels_host, bs, stream_batches):
+        self.bs, self.n = bs, len(X)
+        self.stream = bool(stream_batches) and not isinstance(X, DeviceArray)
+        self.h2d_bytes = 0
+        if not self.stream:
+            self.X = as_device(X)
+            self.labels = labels_to_device(labels_host)
+            return
+        self.X = np.asarray(X)
+        if self.X.dtype != np.float32:
+            self.X = self.X.astype(np.float32)
+        self.labels_host = np.ascontiguousarray(labels_host, dtype=np.int32)
+        shape = (bs,) + self.X.shape[1:]
+        self.dev = [DeviceArray(shape, np.float32) for _ in range(2)]
+        self.dev_lab = [DeviceArray((bs,), np.int32) for _ in range(2)]
+        self.pin_lab = [PinnedBuffer((bs,), np.int32) for _ in range(2)]
+        self.pin_x = None
+        self.copy_stream = new_stream()
+        self.uploaded = [new_event() for _ in range(2)]
+        self.consumed = [new_event() for _ in range(2)]
+        self.issued = -1          # last step (of the current pass) whose upload has been enqueued
+        self.uploads = 0          # uploads ever enqueued; slot = uploads & 1
+        self.slot_of = {}
+
+    def rewind(self):
+        """Start a new pass over the data (new epoch / evaluation sweep)."""
+        self.issued = -1
+
+    def _upload(self, step):
+        slot = self.uploads & 1
+        lo, hi = step * self.bs, min((step + 1) * self.bs, self.n)
+        rows = hi - lo
+        if self.uploads >= 2:
+            lib.nm_stream_wait_event(self.copy_stream, self.consumed[slot])   # device slot consumed by step-2
+            lib.nm_event_sync(self.uploaded[slot])                            # pinned staging slot drained
+        src = self.X[lo:hi]
+        addr = pinned_address(src)
+        if addr is None:                              # pageable: stage through pinned memory
+            if self.pin_x is None:
+                self.pin_x = [PinnedBuffer((self.bs,) + self.X.shape[1:], np.float32) for _ in range(2)]
+            self.pin_x[slot].array[:rows] = src
+            addr = self.pin_x[slot].ptr
+        xb = self.dev[slot][0:rows]
+        lib.nm_h2d(xb.p, C.c_void_p(addr), xb.nbytes, self.copy_stream)
+        self.pin_lab[slot].array[:rows] = self.labels_host[lo:hi]
+        lb = self.dev_lab[slot][0:rows]
+        lib.nm_h2d(lb.p, C.c_void_p(self.pin_lab[slot].ptr), lb.nbytes, self.copy_stream)
+        lib.nm_event_record(self.uploaded[slot], self.copy_stream)
+        self.h2d_bytes += xb.nbytes + lb.nbytes
+        self.issued = step
+        self.uploads += 1
+        self.slot_of[step] = slot
+
+    def batch(self, step):
+        lo, hi = step * self.bs, min((step + 1) * self.bs, self.n)
+        if not self.stream:
+            return self.X[lo:hi], self.labels[lo:hi]
+        if self.issued < step:
+            self._upload(step)
+        slot = self.slot_of[step]
+        lib.nm_stream_wait_event(stream(), self.uploaded[slot])
+        return self.dev[slot][0:hi - lo], self.dev_lab[slot][0:hi - lo]
+
+    def release(self, step, n_steps):
+        """Call after step's kernels are enqueued: marks its slot reusable and prefetches step+1."""
+        if not self.stream:
+            return
+        lib.nm_event_record(self.consumed[self.slot_of[step]], stream())
+        if step + 1 < n_steps and self.issued < step + 1:
+            self._upload(step + 1)

@@ -1,0 +1,7 @@
+from .Conv_wrapepr import Layer_Conv2D
+from .Dense import Layer_Dense
+from .Input import Layer_Input
+from .Flatten import Layer_Flatten
+from .MaxPooling2D import Layer_MaxPooling2D
+
+__all__ = ["Layer_Dense", "Layer_Input", "Layer_Conv2D", "Layer_Flatten", "Layer_MaxPooling2D"]

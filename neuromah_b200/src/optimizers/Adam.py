@@ -1,0 +1,85 @@
+"""Optimizer_Adam on the device (reference: src/optimizers/Adam.py:4-119).
+
+Same attributes and the same pre/update/post call triple.  ``update_params(layer)``
+launches nm_adam_step_f32 per parameter tensor; ``update_arena`` covers the whole
+model in ONE 128-bit-vectorised launch over the flat parameter slab, applying the
+update ``n_apply`` times in registers (Model registers each layer twice).
+"""
+import numpy as np
+
+from ... import ops
+from ...device import DeviceArray
+
+
+class Optimizer_Adam:
+    def __init__(self, learning_rate=0.001, decay=0., epsilon=1e-7, beta_1=0.9, beta_2=0.999, xp=np):
+        if not (0 <= beta_1 < 1) or not (0 <= beta_2 < 1):
+            raise ValueError("beta values must be in the interval [0 , 1)")
+        self.learning_rate = learning_rate
+        self.current_learning_rate = learning_rate
+        self.decay = decay
+        self.iterations = 0
+        self.epsilon = epsilon
+        self.beta_1 = beta_1
+        self.beta_2 = beta_2
+        self.momentums = {}
+        self.caches = {}
+        if xp is None:
+            raise AttributeError("The Adam Optimizer expects a numpy or cupy object")
+        self.xp = np
+
+    def pre_update_params(self):
+        if self.decay:
+            self.current_learning_rate = self.learning_rate * (1. / (1. + self.decay * self.iterations))
+
+    def _hp(self):
+        return dict(lr=self.current_learning_rate, beta_1=self.beta_1, beta_2=self.beta_2,
+                    eps=self.epsilon, t=self.iterations)
+
+    def update_params(self, layer):
+        if not hasattr(layer, "get_parameters") or not callable(getattr(layer, "get_parameters")):
+            raise AttributeError("Layer must have a get_parameters method")
+        parameters = layer.get_parameters()
+        if not isinstance(parameters, dict):
+            raise TypeError("The get_parameters method must return a dictionary")
+        for original_name, values in parameters.items():
+            key = f"{id(layer)}_{original_name}"
+            if not isinstance(values, tuple) or len(values) != 2:
+                raise ValueError("The parameter values must be in tuples")
+            param, grad = values
+            if not isinstance(param, DeviceArray) or not isinstance(grad, DeviceArray):
+                raise ValueError("The parameters and gradients must be device arrays")
+            if param.shape != grad.shape:
+                raise ValueError("The parameter and gradient must have the same shape")
+            if key not in self.momentums:
+                self.momentums[key] = DeviceArray.zeros(param.shape)
+                self.caches[key] = DeviceArray.zeros(param.shape)
+            ops.adam_step(param, grad, self.momentums[key], self.caches[key], n_apply=1, **self._hp())
+
+    def bind_arena(self, arena):
+        """Point momentums/caches at two zeroed slabs laid out like the parameter arena."""
+        arena.ensure_state(2)
+        for (layer, name, view_of) in arena.entries():
+            key = f"{id(layer)}_{name}"
+            self.momentums[key] = view_of(arena.state[0])
+            self.caches[key] = view_of(arena.state[1])
+
+    def update_arena(self, arena, n_apply=1):
+        ops.adam_step(arena.params, arena.grads, arena.state[0], arena.state[1], n_apply=n_apply, **self._hp())
+
+    def post_update_params(self):
+        self.iterations += 1
+
+    def get_state(self):
+        return {"momentums": {k: np.asarray(v) for k, v in self.momentums.items()},
+                "caches": {k: np.asarray(v) for k, v in self.caches.items()},
+                "iterations": self.iterations}
+
+    def load_state(self, state):
+        for k, v in state["momentums"].items():
+            self.momentums[k].copy_from(v) if k in self.momentums else self.momentums.__setitem__(k, DeviceArray.from_numpy(v, np.float32))
+        for k, v in state["caches"].items():
+            self.caches[k].copy_from(v) if k in self.caches else self.caches.__setitem__(k, DeviceArray.from_numpy(v, np.float32))
+        self.iterations = state["iterations"]
+
+    laod_state = load_state          # the reference's spelling (Adam.py:117)

@@ -1,0 +1,32 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def synth(seed, n, shape, classes=10):
+    """Synthetic MNIST-shaped data exactly as tests/golden/make_golden.py draws it."""
+    rng = np.random.default_rng(seed)
+    x = rng.random((n,) + tuple(shape), dtype=np.float32)
+    y = np.eye(classes)[rng.integers(0, classes, n)]
+    return x, y
+
+
+@pytest.fixture(scope="session")
+def have_reference():
+    return os.path.isdir("/root/reference/src")

@@ -1,0 +1,162 @@
+"""Generate golden vectors by running the UNMODIFIED reference (authoring container only).
+
+    python tests/golden/make_golden.py
+
+Imports /root/reference through oracle/ref_shim.py (Dense, ReLU, Softmax, CCE, fused
+gradient, Adam, SGD, Model and the compiled max-pool are the reference's own code; conv
+goes through the oracle restatement because Conv2D.cpp needs Eigen -- see DESIGN.md) and
+writes small .npz fixtures next to this file.  Inputs are regenerated from seeds by the
+tests, so only outputs are stored.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_net, ref_shim  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def data(seed, n, shape, classes=10):
+    rng = np.random.default_rng(seed)
+    x = rng.random((n,) + shape, dtype=np.float32)
+    y = np.eye(classes)[rng.integers(0, classes, n)]
+    return x, y
+
+
+def trainable(model):
+    seen, out = set(), []
+    for l in model.trainable_layers:
+        if id(l) not in seen:
+            seen.add(id(l))
+            out.append(l)
+    return out
+
+
+def flat_params(model):
+    return np.concatenate([np.concatenate([l.weights.ravel(), l.biases.ravel()]) for l in trainable(model)])
+
+
+def mlp_200():
+    """BASELINE.json configs[0]: 784-128-10, batch 128, Adam lr 1e-3, 200 steps."""
+    spec = ref_net.mlp_spec()
+    params = ref_net.init_params(spec, np.random.RandomState(0))
+    model = ref_shim.build_model(spec, params, optimizer="adam", lr=0.001)
+    x, y = data(1, 128 * 200, (784,))
+    losses, accs = [], []
+    for s in range(200):
+        r = ref_shim.train_step(model, x[s * 128:(s + 1) * 128], y[s * 128:(s + 1) * 128])
+        losses.append(r["loss"]); accs.append(r["acc"])
+    np.savez_compressed(os.path.join(HERE, "mlp_200steps.npz"), losses=np.array(losses), accs=np.array(accs),
+                        final_params=flat_params(model).astype(np.float32))
+
+
+def mlp_sgd():
+    spec = ref_net.mlp_spec(64, 32, 10)
+    params = ref_net.init_params(spec, np.random.RandomState(5))
+    model = ref_shim.build_model(spec, params, optimizer="sgd", lr=0.5, decay=0.01)
+    x, y = data(6, 32 * 20, (64,))
+    losses = []
+    for s in range(20):
+        losses.append(ref_shim.train_step(model, x[s * 32:(s + 1) * 32], y[s * 32:(s + 1) * 32])["loss"])
+    np.savez_compressed(os.path.join(HERE, "mlp_sgd_20steps.npz"), losses=np.array(losses),
+                        final_params=flat_params(model).astype(np.float32))
+
+
+def cnn_small():
+    """MNIST CNN of examples/test_Conv2D_MNIST.py:47-53, batch 4, 3 Adam steps, wired conv backward."""
+    spec = ref_net.mnist_cnn_spec()
+    params = ref_net.init_params(spec, np.random.RandomState(2))
+    model = ref_shim.build_model(spec, params, optimizer="adam", lr=0.001, conv_backward="wired")
+    x, y = data(3, 4 * 3, (1, 28, 28))
+    out = {}
+    for s in range(3):
+        r = ref_shim.train_step(model, x[s * 4:(s + 1) * 4], y[s * 4:(s + 1) * 4])
+        out[f"loss{s}"] = r["loss"]
+        if s == 0:
+            for i, l in enumerate(model.layers):
+                out[f"out{i}"] = np.asarray(l.output, dtype=np.float32)
+                if i < len(model.layers) - 1 and l.dinputs is not None:
+                    out[f"din{i}"] = np.asarray(l.dinputs, dtype=np.float32)
+            g = []
+            for l in trainable(model):
+                p = l.get_parameters()
+                g += [np.ravel(p["weights"][1]), np.ravel(p["biases"][1])]
+            out["grads0"] = np.concatenate(g).astype(np.float64)
+        out[f"params{s}"] = flat_params(model).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "cnn_small_3steps.npz"), **out)
+
+
+def cnn_stub():
+    """Same net with the reference's SHIPPED stub conv backward, 2 steps."""
+    spec = ref_net.mnist_cnn_spec()
+    params = ref_net.init_params(spec, np.random.RandomState(2))
+    model = ref_shim.build_model(spec, params, optimizer="adam", lr=0.001, conv_backward="stub")
+    x, y = data(3, 4 * 2, (1, 28, 28))
+    out = {}
+    for s in range(2):
+        out[f"loss{s}"] = ref_shim.train_step(model, x[s * 4:(s + 1) * 4], y[s * 4:(s + 1) * 4])["loss"]
+    out["final_params"] = flat_params(model).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "cnn_stub_2steps.npz"), **out)
+
+
+def ops():
+    """Op-level vectors straight from the reference classes."""
+    ref_shim.load()
+    from NeuromahRef.src.layers import Layer_Dense, Layer_MaxPooling2D
+    from NeuromahRef.src.activations import Activation_ReLU, Activation_Softmax
+    from NeuromahRef.src.losses import Loss_CategoricalCrossentropy
+    from NeuromahRef.src.losses.Activation_Softmax_Loss_CategoricalCrossentropy import \
+        Activation_Softmax_Loss_CategoricalCrossentropy
+    from NeuromahRef.src.optimizers import Optimizer_Adam
+    rng = np.random.default_rng(11)
+    out = {}
+    # Dense fwd/bwd with ReLU + L1/L2
+    np.random.seed(7)
+    d = Layer_Dense(20, 12, activation=Activation_ReLU(), weight_regularizer_l1=0.01, weight_regularizer_l2=0.02)
+    x = rng.standard_normal((9, 20)).astype(np.float32); dv = rng.standard_normal((9, 12))
+    d.forward(x, True); d.backward(dv)
+    out.update(dense_w=d.weights, dense_x=x, dense_dv=dv, dense_out=d.output, dense_dw=d.dweights,
+               dense_db=d.dbiases, dense_dx=d.dinputs)
+    # Softmax + CCE + fused gradient
+    z = rng.standard_normal((7, 10)) * 3
+    sm = Activation_Softmax(); sm.forward(z)
+    yy = rng.integers(0, 10, 7)
+    loss = Loss_CategoricalCrossentropy(model=None)
+    out.update(sm_in=z, sm_out=sm.output, cce=loss.forward(sm.output, yy), cce_onehot=loss.forward(sm.output, np.eye(10)[yy]),
+               labels=yy)
+    f = Activation_Softmax_Loss_CategoricalCrossentropy(); f.backward(sm.output, np.eye(10)[yy])
+    out["fused_grad"] = f.dinputs
+    loss.backward(sm.output, yy); out["cce_bwd"] = loss.dinputs
+    sm.backward(dvs := rng.standard_normal((7, 10))); out.update(sm_dv=dvs, sm_bwd=sm.dinputs)
+    # max pool: 'same' padding, overlapping windows, ties
+    xp = np.round(rng.standard_normal((2, 3, 7, 9)) * 2).astype(np.float32)       # many ties
+    for tag, (ps, st, pad) in {"a": (2, 2, "valid"), "b": (3, 2, "same"), "c": ((2, 3), (1, 2), "same")}.items():
+        p = Layer_MaxPooling2D(ps, strides=st, padding=pad); p.forward(xp)
+        dvp = rng.standard_normal(p.output.shape).astype(np.float32); p.backward(dvp)
+        out.update({f"pool_{tag}_out": p.output, f"pool_{tag}_idx": p.max_indices, f"pool_{tag}_dv": dvp,
+                    f"pool_{tag}_dx": p.dinputs})
+    out["pool_x"] = xp
+    # Adam: 3 iterations on one mock layer, decay on
+    class L:
+        def __init__(s): s.w = rng.standard_normal((5, 4)); s.g = None
+        def get_parameters(s): return {"weights": (s.w, s.g)}
+    lay = L(); out["adam_w0"] = lay.w.copy()
+    opt = Optimizer_Adam(learning_rate=0.01, decay=0.1)
+    gs = []
+    for it in range(3):
+        lay.g = rng.standard_normal((5, 4)) * (10.0 ** -it); gs.append(lay.g.copy())
+        opt.pre_update_params(); opt.update_params(lay); opt.update_params(lay); opt.post_update_params()
+        out[f"adam_w{it + 1}"] = lay.w.copy()
+    out["adam_g"] = np.stack(gs)
+    np.savez_compressed(os.path.join(HERE, "ops.npz"), **out)
+
+
+if __name__ == "__main__":
+    mlp_200(); mlp_sgd(); cnn_small(); cnn_stub(); ops()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -1,0 +1,120 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/neuromah_b200.h declares
+(no compute calls without a GPU), plus the host-side logic of the mirror API."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import neuromah_b200
+from neuromah_b200 import ops, parallel
+from neuromah_b200._lib import LIB_PATH, _SIGS, declared_symbols, lib
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(LIB_PATH), "build the library first: python -c 'import __graft_entry__ as g; g.build()'"
+    dll = ctypes.CDLL(LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 50
+    missing = [n for n in names if not hasattr(dll, n)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    assert set(names) == set(_SIGS), "ctypes signature table out of sync with the header"
+
+
+def test_version_and_error_string_without_gpu():
+    dll = lib.load()
+    assert dll.nm_version() == 1
+    assert isinstance(dll.nm_last_error(), bytes)
+
+
+def test_no_cpu_fallback_exists():
+    """The product package must not import the oracle (or fall back to NumPy compute)."""
+    root = os.path.dirname(neuromah_b200.__file__)
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_same_padding_rule():
+    assert ops.same_padding(3) == (1, 1) and ops.same_padding(5) == (2, 2)
+    assert ops.same_padding(2) == (0, 1) and ops.same_padding(4) == (1, 2)      # Conv_wrapepr.py:134-137
+    assert ops.same_padding(1) == (0, 0)
+
+
+def test_pool_geometry_matches_reference_rule():
+    assert ops.pool_geometry(28, 28, 2, 2, 2, 2, "valid") == (14, 14, 0, 0)
+    assert ops.pool_geometry(7, 9, 3, 3, 2, 2, "same") == (4, 5, 1, 1)
+    assert ops.pool_geometry(7, 9, 2, 3, 1, 2, "same") == (7, 5, 0, 1)
+
+
+def test_shard_bounds():
+    assert [parallel.shard_bounds(4096, r, 8) for r in (0, 7)] == [(0, 512), (3584, 4096)]
+    with pytest.raises(ValueError):
+        parallel.shard_bounds(10, 0, 4)
+
+
+def test_constructor_validation_matches_reference_errors():
+    """tests/layers/test_Conv2dBackend.py:64-81 and tests/optimizers/test_Adam.py:13-35 (no device needed)."""
+    from neuromah_b200.src.layers import Layer_Conv2D, Layer_Dense, Layer_MaxPooling2D
+    from neuromah_b200.src.optimizers import Optimizer_Adam, Optimizer_SGD
+    with pytest.raises(ValueError):
+        Layer_Conv2D(in_channels=3, out_channels=2, kernel_size=3, padding="invalid")
+    with pytest.raises(ValueError):
+        Layer_Conv2D(in_channels=3, out_channels=2, kernel_size=(3, -1))
+    with pytest.raises(ValueError):
+        Layer_Conv2D(in_channels=3, out_channels=2, kernel_size=3, stride=(1, -1))
+    with pytest.raises(ValueError):
+        Layer_Conv2D(in_channels=-1, out_channels=2, kernel_size=3)
+    with pytest.raises(ValueError):
+        Layer_Conv2D(in_channels=3, out_channels=-2, kernel_size=3)
+    with pytest.raises(ValueError):
+        Layer_Dense(0, 3)
+    with pytest.raises(ValueError):
+        Layer_MaxPooling2D((1, 2, 3))
+    opt = Optimizer_Adam()
+    assert (opt.learning_rate, opt.decay, opt.beta_1, opt.beta_2, opt.epsilon, opt.iterations) == \
+           (0.001, 0.0, 0.9, 0.999, 1e-7, 0)
+    opt = Optimizer_Adam(learning_rate=0.2, epsilon=1e-5, beta_1=0.8, beta_2=0.888, decay=0.5)
+    assert (opt.learning_rate, opt.beta_1, opt.beta_2, opt.epsilon, opt.decay) == (0.2, 0.8, 0.888, 1e-5, 0.5)
+    with pytest.raises(ValueError):
+        Optimizer_Adam(beta_1=1.2, beta_2=0.5)
+    with pytest.raises(ValueError):
+        Optimizer_Adam(beta_1=0.8, beta_2=-0.5)
+    with pytest.raises(ValueError):
+        Optimizer_SGD(learning_rate=-1)
+    with pytest.raises(TypeError):
+        Optimizer_SGD(learning_rate="x")
+
+
+def test_initializers_draw_like_the_reference():
+    from neuromah_b200.src.initializers import HeInitializer, RandomNormalInitializer, XavierInitializer
+    np.random.seed(0)
+    a = RandomNormalInitializer().initialize((3, 4))
+    np.random.seed(0)
+    np.testing.assert_array_equal(a, np.random.randn(3, 4) * 0.01)          # Initializer.py:96
+    np.random.seed(1)
+    b = HeInitializer().initialize((8, 3, 3, 3))
+    np.random.seed(1)
+    np.testing.assert_array_equal(b, np.random.normal(0, np.sqrt(2.0 / 27), size=(8, 3, 3, 3)))
+    np.random.seed(2)
+    c = XavierInitializer().initialize((6, 5))
+    lim = np.sqrt(6.0 / 11)
+    assert np.all(np.abs(c) <= lim)
+
+
+def test_alias_makes_reference_imports_resolve():
+    neuromah_b200.install_alias()
+    from Neuromah.src.layers import Layer_Conv2D, Layer_MaxPooling2D, Layer_Dense, Layer_Flatten   # noqa: F401
+    from Neuromah.src.optimizers import Optimizer_Adam          # noqa: F401
+    from Neuromah.src.losses import Loss_CategoricalCrossentropy  # noqa: F401
+    from Neuromah.src.core import Model                         # noqa: F401
+    from Neuromah.src.activations import Activation_ReLU, Activation_Softmax   # noqa: F401
+    from Neuromah.src.metrics import Accuracy_Categorical       # noqa: F401
+
+
+def test_federated_average_host_mirror():
+    from neuromah_b200.Federated import federated_average
+    out = federated_average([[1.0, 2.0], [3.0, 6.0]], [100, 300])
+    assert out == [2.5, 5.0]
