@@ -176,8 +176,30 @@ int nm_sgd_step_f32(float* param, const float* grad, float* mom, size_t n,
 /* y = a*x (+ y if accumulate): FedAvg pre-scale n_i/N (Federated/utils.py:21-22). */
 int nm_scale_f32(float* y, const float* x, size_t n, float a, int accumulate, void* stream);
 
-/* ---- bf16 tensor-core path (tcgen05 + TMA), see DESIGN.md ---------------- */
-/* Declared in the tensor-core section at the end of this header once built. */
+/* ---- bf16 tensor-core path (tcgen05 + TMA + TMEM), see DESIGN.md --------- */
+/* Activations: bf16 NHWC with a one-pixel zero halo, [N, H+2, W+2, C] ("padded grid"); the halo is
+ * written once (zeros) and never touched again.  Parameters and parameter gradients stay FP32 in the
+ * reference layouts (arena); the MMAs read packed bf16 copies refreshed after every optimizer step.
+ * Pool arg-max: one nibble per pooled element = window position (dy*2+dx, first max in the reference's
+ * row-major scan, maxpooling_backend.cpp:94-108) | (value > 0) << 2  (the ReLU mask, Relu.py:12-14). */
+
+/* OIHW f32 -> bf16 [OC][tap][C] (fprop B operand) and bf16 [C][8-tap][OC] (dgrad B operand); either may be NULL */
+int nm_tc_pack_conv_weights_bf16(const float* w_oihw, void* w_fprop, void* w_dgrad, int OC, int C, void* stream);
+/* Layer_Conv2D.forward (3x3, 'same', ReLU, no bias: Conv_wrapepr.py:73-98) fused with the following
+ * Layer_MaxPooling2D(2, 2) forward.  x_pad bf16 [N,H+2,W+2,C]; y bf16 [N,H/2,W/2,OC] (out_padded = 0)
+ * or [N,H/2+2,W/2+2,OC] written at (+1,+1) (out_padded = 1); idx nibbles [N,H/2,W/2,OC/2] bytes.
+ * tcgen05 implicit GEMM; instantiated for C=32, OC=64, H=W=14 (NM_ERR_UNSUPPORTED otherwise). */
+int nm_tc_conv3x3_fprop_pool_bf16(const void* x_pad, const void* w_packed, void* y, void* idx,
+                                  int N, int H, int W, int C, int OC, int out_padded, void* stream);
+/* dgrad (Conv2D.cpp:218-222 + col2im): dy_pad bf16 [N,H+2,W+2,OC] (zero halo) -> dx bf16 on the un-shifted
+ * grid [N,H+2,W+2,C] (pixel (y,x) at row y*(W+2)+x; rows/cols >= H/W hold don't-care values). */
+int nm_tc_conv3x3_dgrad_bf16(const void* dy_pad, const void* w_packed_dgrad, void* dx_grid,
+                             int N, int H, int W, int C, int OC, void* stream);
+/* wgrad (Conv2D.cpp:207-216, summed over the batch, no normalisation) -> dw f32 OIHW; split over the
+ * pixel range across one CTA per SM, partials reduced in a fixed order (deterministic). */
+size_t nm_tc_conv3x3_wgrad_workspace(int C, int OC);
+int nm_tc_conv3x3_wgrad_bf16(const void* x_pad, const void* dy_pad, float* dw, void* workspace, size_t workspace_bytes,
+                             int N, int H, int W, int C, int OC, void* stream);
 
 /* ---- data-parallel communication (NCCL over NVLink) ---------------------- */
 int nm_comm_load(const char* libnccl_path);                 /* dlopen libnccl.so.2 */

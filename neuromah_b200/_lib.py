@@ -70,6 +70,11 @@ _SIGS = {
     "nm_adam_advance_f32": (_i, [_vp, _vp]),
     "nm_sgd_step_f32": (_i, [_vp, _vp, _vp, _sz, _f, _f, _i, _vp, _vp]),
     "nm_scale_f32": (_i, [_vp, _vp, _sz, _f, _i, _vp]),
+    "nm_tc_pack_conv_weights_bf16": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "nm_tc_conv3x3_fprop_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "nm_tc_conv3x3_dgrad_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "nm_tc_conv3x3_wgrad_workspace": (_sz, [_i, _i]),
+    "nm_tc_conv3x3_wgrad_bf16": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "nm_comm_load": (_i, [C.c_char_p]),
     "nm_comm_unique_id": (_i, [_vp]),
     "nm_comm_init": (_i, [_pvp, _vp, _i, _i]),
@@ -78,7 +83,8 @@ _SIGS = {
     "nm_comm_broadcast_f32": (_i, [_vp, _vp, _sz, _i, _vp]),
 }
 
-_UNCHECKED = {"nm_last_error", "nm_version", "nm_conv2d_wgrad_f32_workspace", "nm_dense_wgrad_f32_workspace"}
+_UNCHECKED = {"nm_last_error", "nm_version", "nm_conv2d_wgrad_f32_workspace", "nm_dense_wgrad_f32_workspace",
+              "nm_tc_conv3x3_wgrad_workspace"}
 
 
 class NeuromahB200Error(RuntimeError):

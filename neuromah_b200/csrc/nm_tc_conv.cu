@@ -1,0 +1,488 @@
+// bf16 tensor-core 3x3 'same' convolution for sm_100a: fprop (+ReLU +2x2 max-pool epilogue), dgrad, wgrad.
+//
+// Implicit GEMM with NO im2col anywhere -- not in HBM, not in shared memory, not in the TMA:
+// activations live in HBM as zero-haloed NHWC bf16 [N, Hp=H+2, Wp=W+2, C].  For an M-tile of 128
+// consecutive pixels of that flattened grid, ONE TMA box of 128 + 2*Wp + 2 pixel rows is loaded into
+// shared memory, and the nine filter taps are nine tcgen05.mma issues whose A-descriptor start address
+// is shifted by (r*Wp + s) rows inside that tile (descriptor row shifts validated in
+// profiles/r01_tcgen05_probe.txt).  Accumulators live in TMEM (double-buffered), the epilogue warps
+// read them with tcgen05.ld while the next tile's MMAs run.
+//
+// Replaces: conv2d_cpu / conv2d_backward_cpu (src/layers/CPU_kernels/Conv2D.cpp:83-146, :150-240),
+// the np.pad in Layer_Conv2D.forward (Conv_wrapepr.py:78-84), the embedded ReLU (:96-98) and the
+// following Layer_MaxPooling2D 2x2/2 (maxpooling_backend.cpp:24-133) for the tensor-core mode.
+#include "nm_common.cuh"
+#include "nm_tc_common.cuh"
+#include <mutex>
+
+namespace {
+
+using namespace tc;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encoder(EncodeTiledFn* out) {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        cudaDriverEntryPointQueryResult q;
+        void* p = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiledFn)p;
+    });
+    if (!fn) return nm::fail(NM_ERR_CUDA, "%s%s", "cuTensorMapEncodeTiled not available from the driver");
+    *out = fn;
+    return NM_OK;
+}
+
+// 2-D bf16 tensor map: rows x inner, row pitch in bytes, box (box_inner x box_rows), OOB reads as zero
+int make_map_2d(CUtensorMap* m, const void* gptr, uint64_t inner, uint64_t rows, uint64_t pitch_bytes,
+                uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle sw) {
+    EncodeTiledFn enc;
+    int rc = get_encoder(&enc);
+    if (rc) return rc;
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {pitch_bytes};
+    cuuint32_t box[2] = {box_inner, box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return nm::fail(NM_ERR_CUDA, "%s%s", "cuTensorMapEncodeTiled failed");
+    return NM_OK;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
+    return n;
+}
+
+constexpr int TILE_M = 128;
+
+struct ConvTcParams {
+    int num_tiles, rows_total;         // M tiles / rows of the flattened padded grid N*Hp*Wp
+    int Hp, Wp, H, W;
+    int a_rows;                        // 128 + 2*Wp + 2
+    uint32_t a_stage_bytes;            // a_rows * row bytes, rounded up to 1024
+    int n_stages;
+    void* out;                         // EPI 0: bf16 [rows_total][NOUT];  EPI 1: pooled bf16 NHWC
+    uint8_t* idx;                      // EPI 1: one nibble per pooled element: argmax (2 bits) | (value>0) << 2
+    int oHp, oWp, ooff;                // EPI 1: pooled output geometry (padded for a following conv, or dense)
+};
+
+// ---------------------------------------------------------------------------------------------
+// fprop / dgrad:  D[128 pixels, NOUT] = sum_{tap} A[pixel + shift(tap), 0:CIN] * B[tap][NOUT, CIN]^T
+// ---------------------------------------------------------------------------------------------
+template <int CIN, int NOUT, int EPI>
+__global__ void __launch_bounds__(256, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvTcParams p) {
+    constexpr int ROWB = CIN * 2;                                   // bytes per pixel row: 64 (SW64) or 128 (SW128)
+    static_assert(ROWB == 64 || ROWB == 128, "CIN must be 32 or 64");
+    constexpr uint32_t LAYOUT = ROWB == 128 ? LAYOUT_SW128 : LAYOUT_SW64;
+    constexpr uint64_t TMPL = desc_template(16, 8 * ROWB, LAYOUT);  // K-major: SBO = 8 rows
+    constexpr int KSTEPS = CIN / 16;
+    constexpr int B_TAP_BYTES = NOUT * ROWB;
+    constexpr int B_BYTES = 9 * B_TAP_BYTES;
+    static_assert(B_BYTES % 1024 == 0, "weight block must keep the A stages 1024-aligned");
+    constexpr uint32_t TMEM_COLS = 2 * NOUT < 32 ? 32 : 2 * NOUT;   // two accumulators; 64 or 128: powers of two
+    constexpr uint32_t IDESC = idesc_bf16(TILE_M, NOUT, 0, 0);
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* b_smem = smem;
+    uint8_t* a_smem = smem + B_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + (size_t)p.n_stages * p.a_stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + p.n_stages;
+    uint64_t* tfull = empty + p.n_stages;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* bfull = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        mbar_init(bfull, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            mbar_expect_tx(bfull, B_BYTES);
+            for (int tap = 0; tap < 9; ++tap) tma_load_2d(b_smem + tap * B_TAP_BYTES, &map_b, tap * CIN, 0, bfull);
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_expect_tx(&full[stage], (uint32_t)p.a_rows * ROWB);
+                tma_load_2d(a_smem + (size_t)stage * p.a_stage_bytes, &map_a, 0, tile * TILE_M, &full[stage]);
+                if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ================================
+        if (lane == 0) {
+            mbar_wait(bfull, 0);
+            const uint32_t b_base = smem_u32(b_smem);
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                mbar_wait(&full[stage], phase);
+                fence_after_sync();
+                const uint32_t a_base = smem_u32(a_smem + (size_t)stage * p.a_stage_bytes);
+                const uint32_t d_addr = tmem_base + acc * NOUT;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const uint32_t shift = (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * ROWB;
+#pragma unroll
+                    for (int kk = 0; kk < KSTEPS; ++kk)
+                        mma_bf16(d_addr, desc_at(TMPL, a_base + shift + kk * 32),
+                                 desc_at(TMPL, b_base + tap * B_TAP_BYTES + kk * 32), IDESC, (tap | kk) != 0);
+                }
+                mma_commit(&empty[stage]);          // A stage reusable once these MMAs have read it
+                mma_commit(&tfull[acc]);            // accumulator ready for the epilogue
+                if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                acc ^= 1; if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ============================== epilogue (4 warps) ========================
+        const int q = warp & 3;                       // TMEM sub-partition = lanes [32q, 32q+32)
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            mbar_wait(&tfull[acc], acc_phase);
+            fence_after_sync();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NOUT;
+            uint32_t raw[NOUT];
+#pragma unroll
+            for (int c = 0; c < NOUT; c += 16) tmem_ld_x16(taddr + c, raw + c);
+            tmem_ld_wait();
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator drained: MMA may overwrite it
+            acc ^= 1; if (acc == 0) acc_phase ^= 1;
+
+            if constexpr (EPI == 0) {
+                // plain bf16 store of the [pixel][NOUT] row (dgrad)
+                const long long row = (long long)tile * TILE_M + q * 32 + lane;
+                if (row < p.rows_total) {
+                    uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row * NOUT);
+#pragma unroll
+                    for (int c = 0; c < NOUT; c += 8) {
+                        uint4 o;
+                        o.x = pack_bf16x2(__uint_as_float(raw[c + 0]), __uint_as_float(raw[c + 1]));
+                        o.y = pack_bf16x2(__uint_as_float(raw[c + 2]), __uint_as_float(raw[c + 3]));
+                        o.z = pack_bf16x2(__uint_as_float(raw[c + 4]), __uint_as_float(raw[c + 5]));
+                        o.w = pack_bf16x2(__uint_as_float(raw[c + 6]), __uint_as_float(raw[c + 7]));
+                        dst[c / 8] = o;
+                    }
+                }
+            } else {
+                // ReLU + 2x2/2 max-pool + arg-max nibble.  Wp == 16: a warp holds grid rows (2q, 2q+1) of the
+                // tile, lane = 16*dy + x, so a pool window is lanes {l, l^1, l^16, l^17}.  Two exchange stages
+                // leave lane (dy,dx) owning channels [ (NOUT/2)*dx + (NOUT/4)*dy, +NOUT/4 ) of its window.
+                static_assert(EPI == 0 || NOUT % 4 == 0, "pool epilogue needs NOUT % 4 == 0");
+                constexpr int HALF = NOUT / 2, QUART = NOUT / 4;
+                const int dx = lane & 1, dy = (lane >> 4) & 1;
+                float h[HALF];
+                uint32_t hsel = 0;
+#pragma unroll
+                for (int j = 0; j < HALF; ++j) {
+                    float lo = fmaxf(__uint_as_float(raw[j]), 0.f), hi = fmaxf(__uint_as_float(raw[HALF + j]), 0.f);
+                    float mine = dx ? hi : lo, send = dx ? lo : hi;
+                    float r = __shfl_xor_sync(0xffffffffu, send, 1);
+                    float left = dx ? r : mine, right = dx ? mine : r;     // scan order: (.,0) then (.,1)
+                    bool s = right > left;                                 // strict '>' keeps the first max
+                    h[j] = s ? right : left;
+                    hsel |= (uint32_t)s << j;
+                }
+                const uint32_t osel = __shfl_xor_sync(0xffffffffu, hsel, 16);
+                const uint32_t mysel = dy ? (hsel >> QUART) : hsel, othsel = dy ? (osel >> QUART) : osel;
+                float best[QUART];
+                uint32_t nib[QUART];
+#pragma unroll
+                for (int j = 0; j < QUART; ++j) {
+                    float mine = dy ? h[QUART + j] : h[j], send = dy ? h[j] : h[QUART + j];
+                    float r = __shfl_xor_sync(0xffffffffu, send, 16);
+                    float top = dy ? r : mine, bot = dy ? mine : r;        // scan order: row 0 then row 1
+                    uint32_t tsel = ((dy ? othsel : mysel) >> j) & 1u, bsel = ((dy ? mysel : othsel) >> j) & 1u;
+                    bool s = bot > top;
+                    best[j] = s ? bot : top;
+                    nib[j] = (s ? (2u | bsel) : tsel) | (best[j] > 0.f ? 4u : 0u);
+                }
+                const int tiles_per_img = (p.Hp * p.Wp) / TILE_M;
+                const int n = tile / tiles_per_img;
+                const int py = ((tile % tiles_per_img) * (TILE_M / 16)) / 2 + q, px = (lane & 15) >> 1;
+                if (py < p.H / 2 && px < p.W / 2) {
+                    const int cbase = HALF * dx + QUART * dy;
+                    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) +
+                        (((size_t)n * p.oHp + py + p.ooff) * p.oWp + px + p.ooff) * NOUT + cbase;
+                    uint32_t packed[QUART / 2];
+#pragma unroll
+                    for (int j = 0; j < QUART; j += 2) packed[j / 2] = pack_bf16x2(best[j], best[j + 1]);
+#pragma unroll
+                    for (int j = 0; j < QUART / 2; j += 4)
+                        *reinterpret_cast<uint4*>(o + 2 * j) = make_uint4(packed[j], packed[j + 1], packed[j + 2], packed[j + 3]);
+                    uint8_t* ip = p.idx + (((size_t)n * (p.H / 2) + py) * (p.W / 2) + px) * (NOUT / 2) + cbase / 2;
+                    uint32_t w[QUART / 8];
+#pragma unroll
+                    for (int j = 0; j < QUART; j += 8) {
+                        uint32_t x = 0;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) x |= nib[j + k] << (4 * k);
+                        w[j / 8] = x;
+                    }
+                    if constexpr (QUART == 16) *reinterpret_cast<uint2*>(ip) = make_uint2(w[0], w[1]);
+                    else *reinterpret_cast<uint32_t*>(ip) = w[0];
+                }
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad:  dW[oc, tap, c] = sum_pixels dY[pixel, oc] * X[pixel + shift(tap), c]   (both operands MN-major)
+// Each CTA accumulates its share of the pixel range in nine [COUT x CIN] TMEM accumulators and writes one
+// FP32 partial; a second kernel sums the partials in a fixed order (deterministic) into OIHW.
+// ---------------------------------------------------------------------------------------------
+struct WgradTcParams {
+    int num_kblocks, rows_total, Wp;
+    int x_rows;                          // 128 + 2*Wp + 2
+    uint32_t x_stage_bytes;              // rounded to 1024
+    int n_stages;
+    float* partial;                      // [gridDim.x][COUT][9*CIN]
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256, 1)
+conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, WgradTcParams p) {
+    static_assert(COUT == 64 && CIN == 32, "instantiated for the MNIST conv2 shape");
+    constexpr int A_ROWB = COUT * 2, B_ROWB = CIN * 2;              // 128 B (SW128), 64 B (SW64)
+    constexpr uint64_t TMPL_A = desc_template(16, 8 * A_ROWB, LAYOUT_SW128);   // MN-major: SBO = 8 k-rows
+    constexpr uint64_t TMPL_B = desc_template(16, 8 * B_ROWB, LAYOUT_SW64);
+    constexpr uint32_t IDESC = idesc_bf16(COUT, CIN, 1, 1);        // M = 64, N = 32, both MN-major
+    constexpr int A_BYTES = TILE_M * A_ROWB;                        // 16 KB
+    constexpr uint32_t TMEM_COLS = 512;                             // 9 * 32 = 288 columns used
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t stage_bytes = A_BYTES + p.x_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + p.n_stages;
+    uint64_t* done = empty + p.n_stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_dy); tma_prefetch_desc(&map_x); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = blockIdx.x; kb < p.num_kblocks; kb += gridDim.x) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* st = smem + (size_t)stage * stage_bytes;
+                mbar_expect_tx(&full[stage], A_BYTES + (uint32_t)p.x_rows * B_ROWB);
+                tma_load_2d(st, &map_dy, 0, kb * TILE_M, &full[stage]);
+                tma_load_2d(st + A_BYTES, &map_x, 0, kb * TILE_M - (p.Wp + 1), &full[stage]);   // OOB rows read as 0
+                if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0; uint32_t first = 1;
+            for (int kb = blockIdx.x; kb < p.num_kblocks; kb += gridDim.x) {
+                mbar_wait(&full[stage], phase);
+                fence_after_sync();
+                const uint32_t a_base = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t x_base = a_base + A_BYTES;
+#pragma unroll 1
+                for (int ks = 0; ks < TILE_M / 16; ++ks) {
+                    const uint64_t adesc = desc_at(TMPL_A, a_base + ks * 16 * A_ROWB);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t shift = (uint32_t)((tap / 3) * p.Wp + (tap % 3) + ks * 16) * B_ROWB;
+                        mma_bf16(tmem_base + tap * CIN, adesc, desc_at(TMPL_B, x_base + shift), IDESC, !(first && ks == 0));
+                    }
+                }
+                first = 0;
+                mma_commit(&empty[stage]);
+                if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+            }
+            mma_commit(done);
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const bool has_work = (int)blockIdx.x < p.num_kblocks;
+        if (has_work) { mbar_wait(done, 0); fence_after_sync(); }
+        // M = 64 accumulator rows sit in lanes (m%16) + 32*(m/16): lanes 0..15 of each sub-partition
+        float* dst = p.partial + ((size_t)blockIdx.x * COUT + 16 * q + lane) * (9 * CIN);
+        for (int c = 0; c < 9 * CIN; c += 16) {
+            uint32_t raw[16];
+            if (has_work) { tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + c, raw); tmem_ld_wait(); }
+            if (lane < 16) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(dst + c + j) = has_work
+                        ? make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// dw[oc][c][r][s] = sum_cta partial[cta][oc][(r*3+s)*CIN + c]      (fixed order => deterministic)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int n_cta, int COUT, int CIN) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = COUT * 9 * CIN;
+    if (i >= total) return;
+    int oc = i / (9 * CIN), rem = i - oc * 9 * CIN, tap = rem / CIN, c = rem - tap * CIN;
+    float s = 0.f;
+    for (int k = 0; k < n_cta; ++k) s += partial[(size_t)k * total + i];
+    dw[((size_t)oc * CIN + c) * 9 + tap] = s;
+}
+
+// OIHW f32 -> bf16 [OC][tap][C] (fprop B operand) and [C][tap'][OC] with tap' = 8 - tap (dgrad B operand)
+__global__ void pack_conv_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                         __nv_bfloat16* __restrict__ wd, int OC, int C) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= OC * C * 9) return;
+    int oc = i / (C * 9), rem = i - oc * C * 9, c = rem / 9, tap = rem - c * 9;
+    __nv_bfloat16 v = __float2bfloat16(w[i]);
+    if (wf) wf[((size_t)oc * 9 + tap) * C + c] = v;
+    if (wd) wd[((size_t)c * 9 + (8 - tap)) * OC + oc] = v;
+}
+
+template <int CIN, int NOUT, int EPI>
+int launch_conv(const void* a, const void* b, ConvTcParams p, int N, cudaStream_t st) {
+    constexpr int ROWB = CIN * 2;
+    CUtensorMap ma, mb;
+    const CUtensorMapSwizzle sw = ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    int rc = make_map_2d(&ma, a, CIN, (uint64_t)p.rows_total, ROWB, CIN, (uint32_t)p.a_rows, sw);
+    if (rc) return rc;
+    rc = make_map_2d(&mb, b, 9 * CIN, NOUT, 9 * ROWB, CIN, NOUT, sw);
+    if (rc) return rc;
+    p.a_stage_bytes = ((uint32_t)p.a_rows * ROWB + 1023u) & ~1023u;
+    p.n_stages = 6;
+    size_t smem = 9 * NOUT * ROWB + (size_t)p.n_stages * p.a_stage_bytes + 256;
+    auto kern = conv3x3_tc_kernel<CIN, NOUT, EPI>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        NM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    kern<<<grid, 256, smem, st>>>(ma, mb, p);
+    return nm::launched("conv3x3_tc");
+}
+
+}  // namespace
+
+extern "C" {
+
+int nm_tc_pack_conv_weights_bf16(const float* w_oihw, void* w_fprop, void* w_dgrad, int OC, int C, void* stream) {
+    NM_REQUIRE(w_oihw && (w_fprop || w_dgrad), "null pointer");
+    NM_REQUIRE(OC > 0 && C > 0, "bad dimensions");
+    int total = OC * C * 9;
+    pack_conv_weights_kernel<<<nm_cdiv(total, 256), 256, 0, nm::S(stream)>>>(
+        w_oihw, static_cast<__nv_bfloat16*>(w_fprop), static_cast<__nv_bfloat16*>(w_dgrad), OC, C);
+    return nm::launched("pack_conv_weights");
+}
+
+int nm_tc_conv3x3_fprop_pool_bf16(const void* x_pad, const void* w_packed, void* y, void* idx,
+                                  int N, int H, int W, int C, int OC, int out_padded, void* stream) {
+    NM_REQUIRE(x_pad && w_packed && y && idx, "null pointer");
+    NM_REQUIRE(N > 0, "bad batch");
+    if (!(C == 32 && OC == 64 && H == 14 && W == 14))
+        return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv3x3_fprop_pool_bf16: only C=32, OC=64, 14x14 is instantiated");
+    ConvTcParams p{};
+    p.Hp = H + 2; p.Wp = W + 2; p.H = H; p.W = W;
+    p.rows_total = N * p.Hp * p.Wp;
+    p.num_tiles = (p.rows_total + TILE_M - 1) / TILE_M;
+    p.a_rows = TILE_M + 2 * p.Wp + 2;
+    p.out = y; p.idx = static_cast<uint8_t*>(idx);
+    p.oHp = out_padded ? H / 2 + 2 : H / 2; p.oWp = out_padded ? W / 2 + 2 : W / 2; p.ooff = out_padded ? 1 : 0;
+    return launch_conv<32, 64, 1>(x_pad, w_packed, p, N, nm::S(stream));
+}
+
+int nm_tc_conv3x3_dgrad_bf16(const void* dy_pad, const void* w_packed_dgrad, void* dx_grid,
+                             int N, int H, int W, int C, int OC, void* stream) {
+    NM_REQUIRE(dy_pad && w_packed_dgrad && dx_grid, "null pointer");
+    NM_REQUIRE(N > 0, "bad batch");
+    if (!(C == 32 && OC == 64))
+        return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv3x3_dgrad_bf16: only C=32, OC=64 is instantiated");
+    ConvTcParams p{};
+    p.Hp = H + 2; p.Wp = W + 2; p.H = H; p.W = W;
+    NM_REQUIRE(p.Wp <= 60, "image too wide for one TMA box");
+    p.rows_total = N * p.Hp * p.Wp;
+    p.num_tiles = (p.rows_total + TILE_M - 1) / TILE_M;
+    p.a_rows = TILE_M + 2 * p.Wp + 2;
+    p.out = dx_grid;
+    return launch_conv<64, 32, 0>(dy_pad, w_packed_dgrad, p, N, nm::S(stream));
+}
+
+size_t nm_tc_conv3x3_wgrad_workspace(int C, int OC) {
+    return (size_t)sm_count() * OC * 9 * C * sizeof(float);
+}
+
+int nm_tc_conv3x3_wgrad_bf16(const void* x_pad, const void* dy_pad, float* dw, void* workspace, size_t workspace_bytes,
+                             int N, int H, int W, int C, int OC, void* stream) {
+    NM_REQUIRE(x_pad && dy_pad && dw && workspace, "null pointer");
+    NM_REQUIRE(N > 0, "bad batch");
+    if (!(C == 32 && OC == 64))
+        return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv3x3_wgrad_bf16: only C=32, OC=64 is instantiated");
+    WgradTcParams p{};
+    p.Wp = W + 2;
+    NM_REQUIRE(p.Wp <= 60, "image too wide for one TMA box");
+    p.rows_total = N * (H + 2) * p.Wp;
+    p.num_kblocks = (p.rows_total + TILE_M - 1) / TILE_M;
+    p.x_rows = TILE_M + 2 * p.Wp + 2;
+    p.x_stage_bytes = ((uint32_t)p.x_rows * 64 + 1023u) & ~1023u;
+    p.n_stages = 4;
+    int grid = p.num_kblocks < sm_count() ? p.num_kblocks : sm_count();
+    NM_REQUIRE(workspace_bytes >= (size_t)grid * OC * 9 * C * sizeof(float), "workspace too small");
+    p.partial = static_cast<float*>(workspace);
+    CUtensorMap mdy, mx;
+    int rc = make_map_2d(&mdy, dy_pad, 64, (uint64_t)p.rows_total, 128, 64, TILE_M, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map_2d(&mx, x_pad, 32, (uint64_t)p.rows_total, 64, 32, (uint32_t)p.x_rows, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    size_t smem = (size_t)p.n_stages * (TILE_M * 128 + p.x_stage_bytes) + 256;
+    auto kern = conv3x3_wgrad_tc_kernel<32, 64>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        NM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    kern<<<grid, 256, smem, nm::S(stream)>>>(mdy, mx, p);
+    rc = nm::launched("conv3x3_wgrad_tc");
+    if (rc) return rc;
+    int total = OC * 9 * C;
+    wgrad_reduce_kernel<<<nm_cdiv(total, 256), 256, 0, nm::S(stream)>>>(p.partial, dw, grid, OC, C);
+    return nm::launched("wgrad_reduce");
+}
+
+}  // extern "C"
