@@ -201,6 +201,34 @@ size_t nm_tc_conv3x3_wgrad_workspace(int C, int OC);
 int nm_tc_conv3x3_wgrad_bf16(const void* x_pad, const void* dy_pad, float* dw, void* workspace, size_t workspace_bytes,
                              int N, int H, int W, int C, int OC, void* stream);
 
+/* First conv of the net (C_in = 1, K = 9: streaming CUDA-core kernel) + ReLU + MaxPooling2D(2,2), forward:
+ * x f32 [N,1,H,W], w f32 [OC,1,3,3] -> y_pad bf16 [N,H/2+2,W/2+2,OC] (interior), idx nibbles [N,H/2,W/2,OC/2]. */
+int nm_tc_conv1_fwd_pool_bf16(const float* x, const float* w, void* y_pad, void* idx, int N, int H, int W, int OC, void* stream);
+/* ... and backward: pool backward + ReLU backward (the nibble) + wgrad + bias gradient in one pass.
+ * dp_grid = gradient of the pooled output, bf16 on the un-shifted grid [N,H/2+2,W/2+2,OC] (nm_tc_conv3x3_dgrad_bf16). */
+size_t nm_tc_conv1_bwd_workspace(int OC);
+int nm_tc_conv1_bwd_bf16(const float* x, const void* dp_grid, const void* idx, float* dw, float* db,
+                         void* workspace, size_t workspace_bytes, int N, int H, int W, int OC, void* stream);
+/* Dense weights in the reference layout [(c,h,w) rows][n_out] -> packed f32 [n_out][K] with K in (h,w,c) order */
+int nm_tc_pack_dense_weights(const float* w, float* w_packed, int K, int n_out, int HW, int C, void* stream);
+/* Layer_Dense.forward + Activation_Softmax + CCE losses + accuracy flags + fused gradient (p-onehot)*inv_batch
+ * (Dense.py:79-80, Softmax.py:7-11, categorical_crossentropy.py:8-25, Activation_Softmax_Loss_...py:4-19).
+ * x bf16 [B,K]; accum (may be NULL) = double[2] device accumulators {loss sum, #correct}. n_out <= 16. */
+int nm_tc_dense_softmax_ce_bf16(const void* x, const float* w_packed, const float* bias, const int32_t* labels,
+                                float* probs, float* dlogits, float* sample_loss, int32_t* correct, double* accum,
+                                int B, int K, int n_out, float inv_batch, void* stream);
+/* Dense dinputs (Dense.py:108) + MaxPooling2D backward (maxpooling_backend.cpp:145-238) + ReLU backward
+ * (Relu.py:12-14) -> the last conv's dY, bf16 [B,2PH+2,2PW+2,C] (interior); dbias[C] = sum of dY
+ * (Conv_wrapepr.py:107-109).  workspace: B*C floats. */
+int nm_tc_dense_bwd_unpool_bf16(const float* dlogits, const float* w_packed, const void* idx, void* dy_pad,
+                                float* dbias, void* workspace, size_t workspace_bytes,
+                                int B, int PH, int PW, int C, int n_out, void* stream);
+/* Dense dweights / dbiases (Dense.py:96-105) from bf16 inputs, written in the reference row order. */
+size_t nm_tc_dense_wgrad_workspace(int B, int K);
+int nm_tc_dense_wgrad_bf16(const void* x, const float* dlogits, const float* w, float* dw, float* db,
+                           void* workspace, size_t workspace_bytes, int B, int K, int n_out, int HW, int C,
+                           float scale, float l1, float l2, void* stream);
+
 /* ---- data-parallel communication (NCCL over NVLink) ---------------------- */
 int nm_comm_load(const char* libnccl_path);                 /* dlopen libnccl.so.2 */
 int nm_comm_unique_id(void* id128);                          /* rank 0: 128-byte ncclUniqueId */

@@ -75,6 +75,14 @@ _SIGS = {
     "nm_tc_conv3x3_dgrad_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_conv3x3_wgrad_workspace": (_sz, [_i, _i]),
     "nm_tc_conv3x3_wgrad_bf16": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
+    "nm_tc_conv1_fwd_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "nm_tc_conv1_bwd_workspace": (_sz, [_i]),
+    "nm_tc_conv1_bwd_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp]),
+    "nm_tc_pack_dense_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "nm_tc_dense_softmax_ce_bf16": (_i, [_vp] * 9 + [_i, _i, _i, _f, _vp]),
+    "nm_tc_dense_bwd_unpool_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
+    "nm_tc_dense_wgrad_workspace": (_sz, [_i, _i]),
+    "nm_tc_dense_wgrad_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _f, _f, _f, _vp]),
     "nm_comm_load": (_i, [C.c_char_p]),
     "nm_comm_unique_id": (_i, [_vp]),
     "nm_comm_init": (_i, [_pvp, _vp, _i, _i]),
@@ -84,7 +92,7 @@ _SIGS = {
 }
 
 _UNCHECKED = {"nm_last_error", "nm_version", "nm_conv2d_wgrad_f32_workspace", "nm_dense_wgrad_f32_workspace",
-              "nm_tc_conv3x3_wgrad_workspace"}
+              "nm_tc_conv3x3_wgrad_workspace", "nm_tc_conv1_bwd_workspace", "nm_tc_dense_wgrad_workspace"}
 
 
 class NeuromahB200Error(RuntimeError):

@@ -63,7 +63,9 @@ class Model:
         self.loss, self.optimizer, self.accuracy = loss, optimizer, accuracy
         self.tensorMonitor = tensorMonitor
 
-    def finalize(self, xp=np):
+    def finalize(self, xp=np, mode=None):
+        """``mode``: None / "fp32" = FP32-exact CUDA-core kernels (per-layer launches, reference layouts);
+        "bf16" = fused tensor-core plan (neuromah_b200/tc_plan.py) for the supported layer pattern."""
         from ..activations import Activation_Softmax
         from ..losses import Loss_CategoricalCrossentropy
         from ..losses.Activation_Softmax_Loss_CategoricalCrossentropy import \
@@ -99,6 +101,13 @@ class Model:
         if hasattr(self.optimizer, "bind_arena"):
             self.optimizer.bind_arena(self.arena)
         self._accum = DeviceArray.zeros((2,), np.float64)        # {sum of losses, #correct}
+        self.mode = mode or "fp32"
+        self.plan = None
+        if self.mode == "bf16":
+            from ...tc_plan import TcCnnPlan
+            self.plan = TcCnnPlan(self)
+        elif self.mode != "fp32":
+            raise ValueError("mode must be None, 'fp32' or 'bf16'")
         if self.tensorMonitor:
             self.tensorMonitor.start_run(self)
 
@@ -127,10 +136,16 @@ class Model:
 
     def train_step(self, batch_X, batch_y):
         """One step of Model.train's loop body with device-side loss/accuracy sums."""
-        output = self.forward(batch_X, training=True)
         labels = labels_to_device(batch_y)
-        self._device_loss_acc(output, labels)
-        self.backward(output, labels)
+        if self.plan is not None:
+            gb = self.softmax_classifier_output.grad_batch
+            output = self.plan.forward(as_device(batch_X), labels, accum=self._accum,
+                                       inv_batch=None if gb is None else 1.0 / gb)
+            self.plan.backward(gb)
+        else:
+            output = self.forward(batch_X, training=True)
+            self._device_loss_acc(output, labels)
+            self.backward(output, labels)
         if self.comm is not None:
             self.comm.allreduce_grads(self.arena)
         self._optimizer_step()
@@ -278,11 +293,21 @@ class Model:
     # --------------------------------------------------- forward / backward ----
     def forward(self, X, training):
         self.input_layer.forward(X, training)
+        if self.plan is not None:
+            return self.plan.forward(self.input_layer.output)
         for layer in self.layers:
             layer.forward(layer.prev.output, training)
         return layer.output
 
     def backward(self, output, y):
+        if self.plan is not None:
+            # public-API backward after a label-free forward: fused (p - onehot)/B, then the plan's backward
+            gb = self.softmax_classifier_output.grad_batch
+            self.softmax_classifier_output.backward(output, y)
+            bsz = output.shape[0]
+            self.plan.dlogits[0:bsz].copy_from(self.softmax_classifier_output.dinputs)
+            self.plan.backward(gb)
+            return
         if self.softmax_classifier_output is not None:
             self.softmax_classifier_output.backward(output, y)
             self.layers[-1].dinputs = self.softmax_classifier_output.dinputs

@@ -1,0 +1,167 @@
+"""bf16 tensor-core execution plan for the Conv-Pool-Conv-Pool-Flatten-Dense-Softmax net.
+
+``Model.finalize(mode="bf16")`` recognises the layer pattern of examples/test_Conv2D_MNIST.py:47-53 and
+replaces the per-layer FP32 launches with nine fused launches per training step:
+
+  forward   conv1+ReLU+pool (CUDA cores, C_in=1)  ->  conv2+ReLU+pool (tcgen05 implicit GEMM)
+            ->  Dense+softmax+CE+grad (+ loss/accuracy sums)
+  backward  Dense wgrad  |  Dense dgrad+unpool+ReLU' -> dY2 (+conv2 bias grad)  |  conv2 wgrad (tcgen05)
+            |  conv2 dgrad (tcgen05)  |  conv1 unpool+ReLU'+wgrad+bias grad
+  update    one Adam/SGD launch over the arena  +  re-pack of the bf16 operand copies
+
+Activations are bf16 NHWC with a zero halo; parameters, gradients and optimizer state stay FP32 in the
+arena in the reference's layouts, so optimizers, all-reduce, FedAvg, save/load are shared with the FP32 path.
+Numerics: bf16 operands, FP32 accumulation (stated tolerance in tests/test_gpu_tc_model.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._lib import lib
+from .device import DeviceArray, Scratch, stream
+
+
+def bf16_bits_to_f32(bits: np.ndarray) -> np.ndarray:
+    return (bits.astype(np.uint32) << 16).view(np.float32)
+
+
+class Bf16Activation:
+    """Host-convertible view of an internal bf16 NHWC (optionally haloed) activation: np.asarray(view)
+    yields the reference's float32 NCHW tensor."""
+
+    def __init__(self, buf: DeviceArray, n, halo):
+        self.buf, self.n, self.halo = buf, n, halo
+        _, hp, wp, c = buf.shape
+        self.shape = (n, c, hp - 2 * halo, wp - 2 * halo)
+        self.dtype = np.dtype(np.float32)
+        self.ndim = 4
+
+    def __len__(self):
+        return self.n
+
+    def numpy(self):
+        a = bf16_bits_to_f32(self.buf.numpy()[:self.n])
+        if self.halo:
+            a = a[:, self.halo:-self.halo, self.halo:-self.halo, :]
+        return np.ascontiguousarray(a.transpose(0, 3, 1, 2))
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+
+class TcCnnPlan:
+    PATTERN = "Conv2D(1->32,3x3,same,ReLU) Pool(2,2) Conv2D(32->64,3x3,same,ReLU) Pool(2,2) Flatten Dense(->n<=16) Softmax"
+
+    @staticmethod
+    def match(model):
+        from .src.layers import Layer_Conv2D, Layer_MaxPooling2D, Layer_Dense, Layer_Flatten
+        from .src.activations import Activation_ReLU, Activation_Softmax
+        L = model.layers
+        if len(L) != 7:
+            return False
+        c1, p1, c2, p2, fl, de, sm = L
+        ok = (isinstance(c1, Layer_Conv2D) and isinstance(c2, Layer_Conv2D) and isinstance(p1, Layer_MaxPooling2D)
+              and isinstance(p2, Layer_MaxPooling2D) and isinstance(fl, Layer_Flatten) and isinstance(de, Layer_Dense)
+              and isinstance(sm, Activation_Softmax))
+        if not ok:
+            return False
+        for c, shape in ((c1, (32, 1, 3, 3)), (c2, (64, 32, 3, 3))):
+            if c.weights.shape != shape or c.padding != "same" or type(c.activation) is not Activation_ReLU:
+                return False
+        for p in (p1, p2):
+            if p.pool_size != (2, 2) or p.strides != (2, 2) or p.padding != "valid":
+                return False
+        return de.activation is None and de.weights.shape[1] <= 16 and de.weights.shape[0] % 64 == 0
+
+    def __init__(self, model):
+        if not self.match(model):
+            raise ValueError(f"mode='bf16' supports the layer pattern: {self.PATTERN}")
+        if model.softmax_classifier_output is None:
+            raise ValueError("mode='bf16' needs Loss_CategoricalCrossentropy with a final Activation_Softmax")
+        from . import config
+        if config.conv_backward != "wired" or config.conv_bias_in_forward:
+            raise ValueError("mode='bf16' implements the default quirk settings only")
+        self.model = model
+        self.c1, self.p1, self.c2, self.p2, self.fl, self.de, self.sm = model.layers
+        self.n_out = self.de.weights.shape[1]
+        self.B = 0
+        self.scratch = Scratch()
+        self.w2f = DeviceArray((64, 9, 32), np.uint16)
+        self.w2d = DeviceArray((32, 9, 64), np.uint16)
+        self.w3p = None
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------ buffers ----
+    def _ensure(self, B, H, W):
+        if B <= self.B and (H, W) == getattr(self, "hw", None):
+            return
+        if (H, W) != (28, 28):
+            raise ValueError("mode='bf16' is instantiated for 28x28 inputs")
+        self.hw, self.B = (H, W), B
+        K = 7 * 7 * 64
+        if self.de.weights.shape[0] != K:
+            raise ValueError(f"Dense expects {self.de.weights.shape[0]} inputs, the conv stack produces {K}")
+        self.K = K
+        z = DeviceArray.zeros
+        self.act1_pad = z((B, 16, 16, 32), np.uint16)       # conv2 input, zero halo kept forever
+        self.idx1 = z((B, 14, 14, 16), np.uint8)
+        self.act2 = z((B, 7, 7, 64), np.uint16)
+        self.idx2 = z((B, 7, 7, 32), np.uint8)
+        self.probs = z((B, self.n_out))
+        self.dlogits = z((B, self.n_out))
+        self.losses = z((B,))
+        self.correct = z((B,), np.int32)
+        self.dy2_pad = z((B, 16, 16, 64), np.uint16)      # zero halo kept forever
+        self.dp1 = z((B, 16, 16, 32), np.uint16)
+        self.dummy_labels = z((B,), np.int32)
+        self.w3p = DeviceArray((self.n_out, K), np.float32)
+        ws = max(lib.nm_tc_conv3x3_wgrad_workspace(32, 64), lib.nm_tc_conv1_bwd_workspace(32),
+                 lib.nm_tc_dense_wgrad_workspace(B, K), B * 64 * 4)
+        self.ws = DeviceArray((ws,), np.uint8)
+
+    def pack_weights(self):
+        """Refresh the bf16 / permuted operand copies from the FP32 master weights in the arena."""
+        s = stream()
+        lib.nm_tc_pack_conv_weights_bf16(self.c2.weights.p, self.w2f.p, self.w2d.p, 64, 32, s)
+        if self.w3p is not None:
+            lib.nm_tc_pack_dense_weights(self.de.weights.p, self.w3p.p, self.K, self.n_out, 49, 64, s)
+
+    # ------------------------------------------------------------------ passes ----
+    def forward(self, x: DeviceArray, labels=None, accum=None, inv_batch=None):
+        B = x.shape[0]
+        if x.ndim != 4 or x.shape[1] != 1:
+            raise RuntimeError("Input and kernel must be 4D tensors")
+        self._ensure(B, x.shape[2], x.shape[3])
+        s = stream()
+        self.x = x
+        self.pack_weights()          # master weights may have changed (optimizer, set_parameters, FedAvg)
+        lib.nm_tc_conv1_fwd_pool_bf16(x.p, self.c1.weights.p, self.act1_pad.p, self.idx1.p, B, 28, 28, 32, s)
+        lib.nm_tc_conv3x3_fprop_pool_bf16(self.act1_pad.p, self.w2f.p, self.act2.p, self.idx2.p, B, 14, 14, 32, 64, 0, s)
+        lab = labels if labels is not None else self.dummy_labels
+        lib.nm_tc_dense_softmax_ce_bf16(self.act2.p, self.w3p.p, self.de.biases.p, lab.p, self.probs.p, self.dlogits.p,
+                                        self.losses.p, self.correct.p, accum.p if accum is not None else None,
+                                        B, self.K, self.n_out, float(1.0 / B if inv_batch is None else inv_batch), s)
+        out = self.probs[0:B]
+        # reference-style attribute views (host conversion on demand)
+        self.p1.output = Bf16Activation(self.act1_pad, B, 1)
+        self.p2.output = Bf16Activation(self.act2, B, 0)
+        self.fl.output = self.p2.output
+        self.sm.output = out
+        self.model.softmax_classifier_output.dinputs = self.dlogits[0:B]
+        return out
+
+    def backward(self, grad_batch=None):
+        B = self.x.shape[0]
+        s = stream()
+        scale = 1.0 / (B if grad_batch is None else grad_batch)
+        lib.nm_tc_dense_wgrad_bf16(self.act2.p, self.dlogits.p, self.de.weights.p, self.de.dweights.p, self.de.dbiases.p,
+                                   self.ws.p, self.ws.nbytes, B, self.K, self.n_out, 49, 64, float(scale),
+                                   float(self.de.weight_regularizer_l1), float(self.de.weight_regularizer_l2), s)
+        lib.nm_tc_dense_bwd_unpool_bf16(self.dlogits.p, self.w3p.p, self.idx2.p, self.dy2_pad.p,
+                                        self.c2.bias_gradients.p, self.ws.p, self.ws.nbytes, B, 7, 7, 64, self.n_out, s)
+        lib.nm_tc_conv3x3_wgrad_bf16(self.act1_pad.p, self.dy2_pad.p, self.c2.weight_gradients.p, self.ws.p, self.ws.nbytes,
+                                     B, 14, 14, 32, 64, s)
+        lib.nm_tc_conv3x3_dgrad_bf16(self.dy2_pad.p, self.w2d.p, self.dp1.p, B, 14, 14, 32, 64, s)
+        lib.nm_tc_conv1_bwd_bf16(self.x.p, self.dp1.p, self.idx1.p, self.c1.weight_gradients.p, self.c1.bias_gradients.p,
+                                 self.ws.p, self.ws.nbytes, B, 28, 28, 32, s)

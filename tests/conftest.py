@@ -27,6 +27,16 @@ def synth(seed, n, shape, classes=10):
     return x, y
 
 
+def synth_learnable(seed, n, classes=10):
+    """MNIST-shaped inputs = uniform noise + a fixed binary 28x28 template per class, so a loss curve
+    actually falls within 200 steps (random labels would pin it at ln 10)."""
+    rng = np.random.default_rng(seed)
+    lab = rng.integers(0, classes, n)
+    t = (np.random.default_rng(12345).random((classes, 1, 28, 28), dtype=np.float32) > 0.7).astype(np.float32)
+    x = 0.6 * rng.random((n, 1, 28, 28), dtype=np.float32) + 0.4 * t[lab]
+    return x.astype(np.float32), np.eye(classes)[lab]
+
+
 @pytest.fixture(scope="session")
 def have_reference():
     return os.path.isdir("/root/reference/src")

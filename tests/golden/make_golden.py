@@ -103,6 +103,22 @@ def cnn_stub():
     np.savez_compressed(os.path.join(HERE, "cnn_stub_2steps.npz"), **out)
 
 
+def cnn_200():
+    """MNIST CNN, batch 64, Adam 1e-3, 200 steps on LEARNABLE synthetic data: the loss curve the
+    north star asks to match (FP32-exact and bf16 modes)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import synth_learnable
+    spec = ref_net.mnist_cnn_spec()
+    params = ref_net.init_params(spec, np.random.RandomState(8))
+    model = ref_shim.build_model(spec, params, optimizer="adam", lr=0.001, conv_backward="wired")
+    x, y = synth_learnable(9, 64 * 200)
+    losses, accs = [], []
+    for s in range(200):
+        r = ref_shim.train_step(model, x[s * 64:(s + 1) * 64], y[s * 64:(s + 1) * 64])
+        losses.append(r["loss"]); accs.append(r["acc"])
+    np.savez_compressed(os.path.join(HERE, "cnn_200steps.npz"), losses=np.array(losses), accs=np.array(accs))
+
+
 def ops():
     """Op-level vectors straight from the reference classes."""
     ref_shim.load()
@@ -156,7 +172,10 @@ def ops():
 
 
 if __name__ == "__main__":
-    mlp_200(); mlp_sgd(); cnn_small(); cnn_stub(); ops()
+    only = sys.argv[1:]
+    for fn in (mlp_200, mlp_sgd, cnn_small, cnn_stub, cnn_200, ops):
+        if not only or fn.__name__ in only:
+            fn()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-4, 1e-5
 
 
-def build(spec, params, optimizer="adam", **opt_kw):
+def build(spec, params, optimizer="adam", mode=None, **opt_kw):
     """Build a neuromah_b200 Model from an oracle spec with the given initial parameters."""
     from neuromah_b200.src.core import Model
     from neuromah_b200.src.layers import Layer_Conv2D, Layer_MaxPooling2D, Layer_Dense, Layer_Flatten
@@ -39,7 +39,7 @@ def build(spec, params, optimizer="adam", **opt_kw):
         model.add(layer)
     opt = Optimizer_Adam(**opt_kw) if optimizer == "adam" else Optimizer_SGD(**opt_kw)
     model.set(loss=Loss_CategoricalCrossentropy, optimizer=opt, accuracy=Accuracy_Categorical)
-    model.finalize()
+    model.finalize(mode=mode)
     return model
 
 
