@@ -46,23 +46,31 @@ conv1_fwd_pool_kernel(const float* __restrict__ x, const float* __restrict__ w, 
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) patch[a][b] = img[(2 * py + a) * Wp + 2 * px + b];
+        float s[4][8];                                   // conv value at the 4 window positions x 8 channels
+#pragma unroll
+        for (int pos = 0; pos < 4; ++pos)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) s[pos][c] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wt + t * OC + g * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(wt + t * OC + g * 8 + 4);
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int pos = 0; pos < 4; ++pos) {
+                const float xv = patch[(pos >> 1) + t / 3][(pos & 1) + t % 3];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) s[pos][c] = fmaf(xv, wv[c], s[pos][c]);
+            }
+        }
         float best[8]; uint32_t nibs = 0;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            float wv[9];
-#pragma unroll
-            for (int t = 0; t < 9; ++t) wv[t] = wt[t * OC + g * 8 + c];
             float bv = -1.f; uint32_t bi = 0;
 #pragma unroll
             for (int pos = 0; pos < 4; ++pos) {                    // reference scan order (0,0),(0,1),(1,0),(1,1)
-                const int dy = pos >> 1, dx = pos & 1;
-                float s = 0.f;
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) s = fmaf(patch[dy + r][dx + q], wv[r * 3 + q], s);
-                s = fmaxf(s, 0.f);
-                if (s > bv) { bv = s; bi = pos; }                  // strict '>': first max wins
+                const float v = fmaxf(s[pos][c], 0.f);
+                if (v > bv) { bv = v; bi = pos; }                  // strict '>': first max wins
             }
             best[c] = bv;
             nibs |= (bi | (bv > 0.f ? 4u : 0u)) << (4 * c);
@@ -77,48 +85,93 @@ conv1_fwd_pool_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 // conv1 backward: dW1[oc][tap], db1[oc] from the gradient of the POOLED output (bf16, un-shifted grid
 // [N, PH+2, PW+2, OC]), the arg-max nibbles and the input image.  Pool backward + ReLU backward are the
 // nibble; nothing of the 28x28x32 activation gradient is ever materialised.
-// threads = 8 pixel lanes x OC channels; per-CTA partials, reduced in a fixed order by a second kernel.
+// Per image the CTA stages x, dP and the nibbles in shared memory with 16-byte loads (all in flight at
+// once -- the first version chased idx -> dP -> x per thread and was latency-bound at 3% of HBM), then a
+// work item = (pooled pixel, 8 channels) accumulates 8 x (9 taps + bias) sums in registers.
+// Partials per CTA, reduced in a fixed order by a second kernel (deterministic).
 // ------------------------------------------------------------------------------------------------
 template <int OC>
-__global__ void __launch_bounds__(8 * OC)
+__global__ void __launch_bounds__(256, 2)
 conv1_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dp_grid, const uint8_t* __restrict__ idx,
                  float* __restrict__ partial, int N, int H, int W) {
-    extern __shared__ float sm[];
-    const int Wp = W + 2, PH = H / 2, PW = W / 2, GW = PW + 2;
-    float* img = sm;
-    float* red = sm + (H + 2) * Wp;           // [8][OC][10]
-    const int oc = threadIdx.x % OC, pl = threadIdx.x / OC;
-    float acc[10];
+    static_assert(OC == 32, "thread mapping assumes 4 groups of 8 channels");
+    extern __shared__ __align__(16) uint8_t smraw[];
+    const int Wp = W + 2, PH = H / 2, PW = W / 2, GW = PW + 2, NPIX = PH * PW;
+    float* img = reinterpret_cast<float*>(smraw);                              // (H+2) x (W+2), zero halo
+    uint4* dps = reinterpret_cast<uint4*>(img + (((H + 2) * Wp + 3) & ~3));    // [NPIX][4] x 16 B (8 bf16)
+    uint32_t* ids = reinterpret_cast<uint32_t*>(dps + NPIX * 4);               // [NPIX][4] x 4 B (8 nibbles)
+    float* red = reinterpret_cast<float*>(ids + NPIX * 4);                     // [8 warps][4 groups][80]
+    constexpr int G = OC / 8;
+    const int g = threadIdx.x % G;
+    float acc[8][10];
 #pragma unroll
-    for (int t = 0; t < 10; ++t) acc[t] = 0.f;
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int t = 0; t < 10; ++t) acc[c][t] = 0.f;
+
     for (int n = blockIdx.x; n < N; n += gridDim.x) {
         __syncthreads();
         for (int i = threadIdx.x; i < (H + 2) * Wp; i += blockDim.x) {
             int yy = i / Wp - 1, xx = i % Wp - 1;
-            img[i] = ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) ? x[((size_t)n * H + yy) * W + xx] : 0.f;
+            img[i] = ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) ? __ldg(x + ((size_t)n * H + yy) * W + xx) : 0.f;
+        }
+        for (int i = threadIdx.x; i < NPIX * G; i += blockDim.x) {
+            const int pix = i / G, ch = i % G, py = pix / PW, px = pix % PW;
+            dps[i] = __ldg(reinterpret_cast<const uint4*>(dp_grid + (((size_t)n * (PH + 2) + py) * GW + px) * OC) + ch);
+            ids[i] = __ldg(reinterpret_cast<const uint32_t*>(idx + ((size_t)n * NPIX + pix) * (OC / 2)) + ch);
         }
         __syncthreads();
-        for (int pix = pl; pix < PH * PW; pix += 8) {
-            const int py = pix / PW, px = pix % PW;
-            const uint32_t nib = (idx[(((size_t)n * PH + py) * PW + px) * (OC / 2) + oc / 2] >> (4 * (oc & 1))) & 0xF;
-            if (!(nib & 4)) continue;                                        // ReLU mask (Relu.py:12-14)
-            const float g = __bfloat162float(dp_grid[(((size_t)n * (PH + 2) + py) * GW + px) * OC + oc]);
-            const int Y = 2 * py + ((nib >> 1) & 1), X = 2 * px + (nib & 1);  // arg-max position (pool backward)
+        for (int item = threadIdx.x; item < NPIX * G; item += blockDim.x) {
+            const int pix = item / G, py = pix / PW, px = pix % PW;
+            const uint32_t nibs = ids[item];
+            if ((nibs & 0x44444444u) == 0) continue;                      // all 8 channels ReLU-dead
+            const uint4 d = dps[item];
+            const float gv[8] = {bf_lo(d.x), bf_hi(d.x), bf_lo(d.y), bf_hi(d.y), bf_lo(d.z), bf_hi(d.z), bf_lo(d.w), bf_hi(d.w)};
+            float patch[4][4];
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
+            for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int q = 0; q < 3; ++q) acc[r * 3 + q] = fmaf(g, img[(Y + r) * Wp + X + q], acc[r * 3 + q]);
-            acc[9] += g;
+                for (int b = 0; b < 4; ++b) patch[a][b] = img[(2 * py + a) * Wp + 2 * px + b];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t nb = (nibs >> (4 * c)) & 0xF;
+                const float gc = (nb & 4) ? gv[c] : 0.f;                   // ReLU mask (Relu.py:12-14)
+                acc[c][9] += gc;
+#pragma unroll
+                for (int pos = 0; pos < 4; ++pos) {                        // arg-max routing (pool backward)
+                    const float gp = ((nb & 3) == (uint32_t)pos) ? gc : 0.f;
+#pragma unroll
+                    for (int t = 0; t < 9; ++t)
+                        acc[c][t] = fmaf(gp, patch[(pos >> 1) + t / 3][(pos & 1) + t % 3], acc[c][t]);
+                }
+            }
         }
     }
-    __syncthreads();
+    // fixed-order reduction: lanes with equal (lane % 4) share a channel group -> xor 4, 8, 16; then warps
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int t = 0; t < 10; ++t) red[(pl * OC + oc) * 10 + t] = acc[t];
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int t = 0; t < 10; ++t) {
+            float v = acc[c][t];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            acc[c][t] = v;
+        }
     __syncthreads();
-    for (int i = threadIdx.x; i < OC * 10; i += blockDim.x) {
-        float s = 0.f;
-        for (int l = 0; l < 8; ++l) s += red[l * OC * 10 + i];
-        partial[(size_t)blockIdx.x * OC * 10 + i] = s;
+    if (lane < G) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int t = 0; t < 10; ++t) red[(warp * G + g) * 80 + c * 10 + t] = acc[c][t];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < OC * 10; i += blockDim.x) {              // i = (g*8 + c)*10 + t
+        const int gg = i / 80, rem = i % 80;
+        float sum = 0.f;
+        for (int w8 = 0; w8 < 8; ++w8) sum += red[(w8 * G + gg) * 80 + rem];
+        partial[(size_t)blockIdx.x * OC * 10 + i] = sum;
     }
 }
 
@@ -368,7 +421,8 @@ int nm_tc_conv1_bwd_bf16(const float* x, const void* dp_grid, const void* idx, f
     if (OC != 32) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_bwd_bf16: only OC=32 is instantiated");
     int blocks = N < 296 ? N : 296;
     NM_REQUIRE(workspace_bytes >= (size_t)blocks * OC * 10 * sizeof(float), "workspace too small");
-    size_t smem = ((size_t)(H + 2) * (W + 2) + 8 * OC * 10) * sizeof(float);
+    const int npix = (H / 2) * (W / 2);
+    size_t smem = ((((size_t)(H + 2) * (W + 2) + 3) & ~(size_t)3) + 8 * 4 * 80) * sizeof(float) + (size_t)npix * 4 * (16 + 4);
     conv1_bwd_kernel<32><<<blocks, 256, smem, nm::S(stream)>>>(x, static_cast<const __nv_bfloat16*>(dp_grid),
                                                               static_cast<const uint8_t*>(idx),
                                                               static_cast<float*>(workspace), N, H, W);

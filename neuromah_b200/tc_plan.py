@@ -17,8 +17,15 @@ from __future__ import annotations
 
 import numpy as np
 
+from . import ops
 from ._lib import lib
 from .device import DeviceArray, Scratch, stream
+
+
+def _timed(name, fn, *a):
+    tok = ops._tic(name)
+    fn(*a)
+    ops._toc(tok)
 
 
 def bf16_bits_to_f32(bits: np.ndarray) -> np.ndarray:
@@ -136,10 +143,10 @@ class TcCnnPlan:
         s = stream()
         self.x = x
         self.pack_weights()          # master weights may have changed (optimizer, set_parameters, FedAvg)
-        lib.nm_tc_conv1_fwd_pool_bf16(x.p, self.c1.weights.p, self.act1_pad.p, self.idx1.p, B, 28, 28, 32, s)
-        lib.nm_tc_conv3x3_fprop_pool_bf16(self.act1_pad.p, self.w2f.p, self.act2.p, self.idx2.p, B, 14, 14, 32, 64, 0, s)
+        _timed('tc_conv1_fwd_pool', lib.nm_tc_conv1_fwd_pool_bf16, x.p, self.c1.weights.p, self.act1_pad.p, self.idx1.p, B, 28, 28, 32, s)
+        _timed('tc_conv2_fprop_pool', lib.nm_tc_conv3x3_fprop_pool_bf16, self.act1_pad.p, self.w2f.p, self.act2.p, self.idx2.p, B, 14, 14, 32, 64, 0, s)
         lab = labels if labels is not None else self.dummy_labels
-        lib.nm_tc_dense_softmax_ce_bf16(self.act2.p, self.w3p.p, self.de.biases.p, lab.p, self.probs.p, self.dlogits.p,
+        _timed('tc_dense_softmax_ce', lib.nm_tc_dense_softmax_ce_bf16, self.act2.p, self.w3p.p, self.de.biases.p, lab.p, self.probs.p, self.dlogits.p,
                                         self.losses.p, self.correct.p, accum.p if accum is not None else None,
                                         B, self.K, self.n_out, float(1.0 / B if inv_batch is None else inv_batch), s)
         out = self.probs[0:B]
@@ -155,13 +162,13 @@ class TcCnnPlan:
         B = self.x.shape[0]
         s = stream()
         scale = 1.0 / (B if grad_batch is None else grad_batch)
-        lib.nm_tc_dense_wgrad_bf16(self.act2.p, self.dlogits.p, self.de.weights.p, self.de.dweights.p, self.de.dbiases.p,
+        _timed('tc_dense_wgrad', lib.nm_tc_dense_wgrad_bf16, self.act2.p, self.dlogits.p, self.de.weights.p, self.de.dweights.p, self.de.dbiases.p,
                                    self.ws.p, self.ws.nbytes, B, self.K, self.n_out, 49, 64, float(scale),
                                    float(self.de.weight_regularizer_l1), float(self.de.weight_regularizer_l2), s)
-        lib.nm_tc_dense_bwd_unpool_bf16(self.dlogits.p, self.w3p.p, self.idx2.p, self.dy2_pad.p,
+        _timed('tc_dense_bwd_unpool', lib.nm_tc_dense_bwd_unpool_bf16, self.dlogits.p, self.w3p.p, self.idx2.p, self.dy2_pad.p,
                                         self.c2.bias_gradients.p, self.ws.p, self.ws.nbytes, B, 7, 7, 64, self.n_out, s)
-        lib.nm_tc_conv3x3_wgrad_bf16(self.act1_pad.p, self.dy2_pad.p, self.c2.weight_gradients.p, self.ws.p, self.ws.nbytes,
+        _timed('tc_conv2_wgrad', lib.nm_tc_conv3x3_wgrad_bf16, self.act1_pad.p, self.dy2_pad.p, self.c2.weight_gradients.p, self.ws.p, self.ws.nbytes,
                                      B, 14, 14, 32, 64, s)
-        lib.nm_tc_conv3x3_dgrad_bf16(self.dy2_pad.p, self.w2d.p, self.dp1.p, B, 14, 14, 32, 64, s)
-        lib.nm_tc_conv1_bwd_bf16(self.x.p, self.dp1.p, self.idx1.p, self.c1.weight_gradients.p, self.c1.bias_gradients.p,
+        _timed('tc_conv2_dgrad', lib.nm_tc_conv3x3_dgrad_bf16, self.dy2_pad.p, self.w2d.p, self.dp1.p, B, 14, 14, 32, 64, s)
+        _timed('tc_conv1_bwd', lib.nm_tc_conv1_bwd_bf16, self.x.p, self.dp1.p, self.idx1.p, self.c1.weight_gradients.p, self.c1.bias_gradients.p,
                                  self.ws.p, self.ws.nbytes, B, 28, 28, 32, s)
