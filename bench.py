@@ -111,50 +111,63 @@ def build_model(spec, params, lr=0.001, mode=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md).
+
+    The sampler is started at program start (nvidia-smi needs a second or two to come up on a fresh box) and
+    every line carries a timestamp; ``stop(t0, t1)`` keeps the samples that fall inside the timed window
+    (widened by ``slack`` seconds when the window is shorter than the sampling period)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.gpu, self.proc, self.path = gpu_index, None, f"/tmp/nm_clocks_{os.getpid()}.csv"
+    def __init__(self, gpu_index, period_ms=50):
+        self.gpu, self.proc, self.path, self.period_ms = gpu_index, None, f"/tmp/nm_clocks_{os.getpid()}.csv", period_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0, t1):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(2.5 * self.period_ms / 1e3)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in open(self.path):
             f = [t.strip() for t in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[2]), float(f[3]), float(f[4]) if f[4] not in ("", "[N/A]") else 0.0,
+                             [n for n, v in zip(names, f[6:10]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
         try:
             os.remove(self.path)
         except OSError:
             pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        window = "timed region"
+        inside = [r for r in rows if t0 <= r[0] <= t1]
+        if len(inside) < 2:
+            slack = 4 * self.period_ms / 1e3
+            inside = [r for r in rows if t0 - slack <= r[0] <= t1 + slack]
+            window = f"timed region +/- {slack:.2f} s (region shorter than the sampling period)"
+        reasons = sorted({n for r in inside for n in r[4]})
+        return {"sm_mhz": statistics.median([r[1] for r in inside]) if inside else None,
+                "sm_max_mhz": max([r[2] for r in inside]) if inside else (max([r[2] for r in rows]) if rows else None),
+                "power_w_max": max([r[3] for r in inside]) if inside else None,
+                "samples": len(inside), "window": window, "reasons": reasons}
 
 
 def cpu_arm(steps, warmup, sample):
@@ -197,8 +210,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"],
@@ -221,6 +234,8 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    clocks = ClockSampler(local_rank)
+    clocks.start()                      # early: nvidia-smi takes a while to produce its first sample
     device.init(local_rank)
     W, K, B = max(args.warmup, 3), args.steps, args.batch
 
@@ -245,34 +260,33 @@ def main():
     parallel.attach(model, comm, B * world)
     model.epoch_end_accuracy = False     # time the K training steps only (no Model.py:199 sweep)
 
-    # synthetic data: K+W distinct host batches per rank in page-locked memory
-    n_batches = K + W
+    # synthetic data: up to 32 distinct host batches per rank in page-locked memory (cycled when K > 32)
+    n_host = min(max(K, 1), 32)
     rng = np.random.default_rng(100 + rank)
-    host_x = device.PinnedBuffer((n_batches * B, 1, 28, 28), np.float32)
+    host_x = device.PinnedBuffer((n_host * B, 1, 28, 28), np.float32)
     rng.random(out=host_x.array, dtype=np.float32)
-    labels = rng.integers(0, 10, n_batches * B).astype(np.int32)
+    labels = rng.integers(0, 10, n_host * B).astype(np.int32)
 
     # ---------------- device-resident leg: inputs already in HBM --------------------------------
-    n_dev = min(n_batches, 8)
+    n_dev = min(n_host, 8)
     x_dev = device.DeviceArray.from_numpy(host_x.array[:n_dev * B])
     y_dev = device.DeviceArray.from_numpy(labels[:n_dev * B])
     for s in range(W):
         model.train_step(x_dev[(s % n_dev) * B:(s % n_dev + 1) * B], y_dev[(s % n_dev) * B:(s % n_dev + 1) * B])
     ops.timers = ops.KernelTimers()
-    clocks = ClockSampler(local_rank)
     e0, e1 = device.new_event(), device.new_event()
     barrier()
-    clocks.start()
     launches0 = device.launch_count()
+    t_wall0 = time.time()
     lib.nm_event_record(e0, device.stream())
     for s in range(K):
         i = s % n_dev
         model.train_step(x_dev[i * B:(i + 1) * B], y_dev[i * B:(i + 1) * B])
     lib.nm_event_record(e1, device.stream())
     device.synchronize()
+    t_wall1 = time.time()
     barrier()
     launches = device.launch_count() - launches0
-    clock_info = clocks.stop()
     ms = C.c_float()
     lib.nm_event_elapsed_ms(e0, e1, C.byref(ms))
     elapsed_ms = max_over_ranks(ms.value)
@@ -281,18 +295,29 @@ def main():
     value = K * B * world / (elapsed_ms / 1e3)
 
     # ---------------- end-to-end leg: Model.train from pinned host memory ------------------------
-    model.train(host_x.array[:W * B], labels[:W * B], epochs=1, batch_size=B, verbose=0, stream_batches=True)
+    # K steps = (K // n_host) epochs over the n_host pinned batches + one partial pass; every step copies its
+    # batch host->device and reads the running loss/accuracy sums back (16 bytes)
+    n_warm = min(W, n_host)
+    model.train(host_x.array[:n_warm * B], labels[:n_warm * B], epochs=1, batch_size=B, verbose=0, stream_batches=True)
+    full, rem = divmod(K, n_host)
+    h2d = d2h = 0
     barrier()
     lib.nm_event_record(e0, device.stream())
-    model.train(host_x.array[W * B:], labels[W * B:], epochs=1, batch_size=B, verbose=0, stream_batches=True)
+    if full:
+        model.train(host_x.array, labels, epochs=full, batch_size=B, verbose=0, stream_batches=True)
+        h2d += model.h2d_bytes; d2h += model.d2h_bytes
+    if rem:
+        model.train(host_x.array[:rem * B], labels[:rem * B], epochs=1, batch_size=B, verbose=0, stream_batches=True)
+        h2d += model.h2d_bytes; d2h += model.d2h_bytes
     lib.nm_event_record(e1, device.stream())
     device.synchronize()
     barrier()
     lib.nm_event_elapsed_ms(e0, e1, C.byref(ms))
     e2e_ms = max_over_ranks(ms.value)
     e2e = {"value": K * B * world / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms / K,
-           "h2d_bytes_per_step": model.h2d_bytes // K, "d2h_bytes_per_step": model.d2h_bytes // K,
-           "api": "Model.train(X_pinned_host, y, batch_size=4096, stream_batches=True)"}
+           "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
+           "api": f"Model.train(X_pinned_host, y, batch_size={B}, stream_batches=True)"}
+    clock_info = clocks.stop(t_wall0, t_wall1)
 
     if rank != 0:
         return

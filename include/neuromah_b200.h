@@ -74,6 +74,9 @@ int nm_graph_begin(void* stream);                        /* stream capture (thre
 int nm_graph_end(void* stream, void** graph_exec);
 int nm_graph_launch(void* graph_exec, void* stream);
 int nm_graph_destroy(void* graph_exec);
+/* cudaProfilerStart/Stop: bracket the region `ncu --profile-from-start off` captures (profiles/prof_step.py) */
+int nm_profiler_start(void);
+int nm_profiler_stop(void);
 /* number of kernels this library launched since process start (bench "gpu_launches") */
 int nm_launch_count(unsigned long long* count);
 
@@ -209,23 +212,36 @@ int nm_tc_conv1_fwd_pool_bf16(const float* x, const float* w, void* y_pad, void*
 size_t nm_tc_conv1_bwd_workspace(int OC);
 int nm_tc_conv1_bwd_bf16(const float* x, const void* dp_grid, const void* idx, float* dw, float* db,
                          void* workspace, size_t workspace_bytes, int N, int H, int W, int OC, void* stream);
-/* Dense weights in the reference layout [(c,h,w) rows][n_out] -> packed f32 [n_out][K] with K in (h,w,c) order */
-int nm_tc_pack_dense_weights(const float* w, float* w_packed, int K, int n_out, int HW, int C, void* stream);
+/* Dense weights in the reference layout [(c,h,w) rows][n_out] f32 ->
+ *   w_packed f32 [n_out][K] with K in the kernels' (h,w,c) order (CUDA-core dgrad; may be NULL)
+ *   w_hilo  bf16 [32][K]: rows [0,16) = bf16(w), rows [16,32) = bf16(w - bf16(w)), classes >= n_out zero
+ *           (tcgen05 B operand; the hi/lo pair keeps ~16 mantissa bits of the weights; may be NULL) */
+int nm_tc_pack_dense_weights(const float* w, float* w_packed, void* w_hilo, int K, int n_out, int HW, int C, void* stream);
+/* f32 dlogits [B][n_out] -> bf16 hi/lo [B][32] (only needed when dlogits did not come from nm_tc_dense_softmax_ce_bf16) */
+int nm_tc_pack_dlogits_bf16(const float* dlogits, void* dl_hilo, int B, int n_out, void* stream);
 /* Layer_Dense.forward + Activation_Softmax + CCE losses + accuracy flags + fused gradient (p-onehot)*inv_batch
  * (Dense.py:79-80, Softmax.py:7-11, categorical_crossentropy.py:8-25, Activation_Softmax_Loss_...py:4-19).
- * x bf16 [B,K]; accum (may be NULL) = double[2] device accumulators {loss sum, #correct}. n_out <= 16. */
-int nm_tc_dense_softmax_ce_bf16(const void* x, const float* w_packed, const float* bias, const int32_t* labels,
-                                float* probs, float* dlogits, float* sample_loss, int32_t* correct, double* accum,
+ * TMA-fed tcgen05 tiles (M = 128 rows, N = 32 = hi+lo classes), split-K over CTAs, one finalize kernel.
+ * x bf16 [B,K] (K % 8 == 0); dl_hilo (may be NULL) receives the gradient as bf16 hi/lo [B][32] for
+ * nm_tc_dense_wgrad_bf16; accum (may be NULL) = double[2] device accumulators {loss sum, #correct}, updated
+ * in a fixed order.  workspace: nm_tc_dense_softmax_ce_workspace() bytes, ZERO-FILLED once before first use
+ * (it holds a ticket counter that every call leaves at zero).  n_out <= 16. */
+size_t nm_tc_dense_softmax_ce_workspace(int B, int K);
+int nm_tc_dense_softmax_ce_bf16(const void* x, const void* w_hilo, const float* bias, const int32_t* labels,
+                                float* probs, float* dlogits, void* dl_hilo, float* sample_loss, int32_t* correct,
+                                double* accum, void* workspace, size_t workspace_bytes,
                                 int B, int K, int n_out, float inv_batch, void* stream);
 /* Dense dinputs (Dense.py:108) + MaxPooling2D backward (maxpooling_backend.cpp:145-238) + ReLU backward
  * (Relu.py:12-14) -> the last conv's dY, bf16 [B,2PH+2,2PW+2,C] (interior); dbias[C] = sum of dY
- * (Conv_wrapepr.py:107-109).  workspace: B*C floats. */
+ * (Conv_wrapepr.py:107-109).  One thread per (pooled pixel, 8 channels): PH*PW*C/8 <= 416. */
+size_t nm_tc_dense_bwd_unpool_workspace(int C);
 int nm_tc_dense_bwd_unpool_bf16(const float* dlogits, const float* w_packed, const void* idx, void* dy_pad,
                                 float* dbias, void* workspace, size_t workspace_bytes,
                                 int B, int PH, int PW, int C, int n_out, void* stream);
-/* Dense dweights / dbiases (Dense.py:96-105) from bf16 inputs, written in the reference row order. */
+/* Dense dweights / dbiases (Dense.py:96-105): tcgen05 tiles over X^T (M = 64 features) x dlogits hi/lo (N = 32),
+ * split over the batch rows, fixed-order reduction, written in the reference row order (+ L1/L2 terms). */
 size_t nm_tc_dense_wgrad_workspace(int B, int K);
-int nm_tc_dense_wgrad_bf16(const void* x, const float* dlogits, const float* w, float* dw, float* db,
+int nm_tc_dense_wgrad_bf16(const void* x, const void* dl_hilo, const float* dlogits, const float* w, float* dw, float* db,
                            void* workspace, size_t workspace_bytes, int B, int K, int n_out, int HW, int C,
                            float scale, float l1, float l2, void* stream);
 

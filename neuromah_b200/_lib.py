@@ -47,6 +47,8 @@ _SIGS = {
     "nm_graph_end": (_i, [_vp, _pvp]),
     "nm_graph_launch": (_i, [_vp, _vp]),
     "nm_graph_destroy": (_i, [_vp]),
+    "nm_profiler_start": (_i, []),
+    "nm_profiler_stop": (_i, []),
     "nm_launch_count": (_i, [C.POINTER(C.c_ulonglong)]),
     "nm_conv2d_fprop_f32": (_i, [_vp, _vp, _vp, _vp] + [_i] * 12 + [_vp]),
     "nm_conv2d_dgrad_f32": (_i, [_vp, _vp, _vp] + [_i] * 11 + [_vp]),
@@ -78,11 +80,14 @@ _SIGS = {
     "nm_tc_conv1_fwd_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "nm_tc_conv1_bwd_workspace": (_sz, [_i]),
     "nm_tc_conv1_bwd_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp]),
-    "nm_tc_pack_dense_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    "nm_tc_dense_softmax_ce_bf16": (_i, [_vp] * 9 + [_i, _i, _i, _f, _vp]),
+    "nm_tc_pack_dense_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "nm_tc_pack_dlogits_bf16": (_i, [_vp, _vp, _i, _i, _vp]),
+    "nm_tc_dense_softmax_ce_workspace": (_sz, [_i, _i]),
+    "nm_tc_dense_softmax_ce_bf16": (_i, [_vp] * 11 + [_sz, _i, _i, _i, _f, _vp]),
+    "nm_tc_dense_bwd_unpool_workspace": (_sz, [_i]),
     "nm_tc_dense_bwd_unpool_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_dense_wgrad_workspace": (_sz, [_i, _i]),
-    "nm_tc_dense_wgrad_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _f, _f, _f, _vp]),
+    "nm_tc_dense_wgrad_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _f, _f, _f, _vp]),
     "nm_comm_load": (_i, [C.c_char_p]),
     "nm_comm_unique_id": (_i, [_vp]),
     "nm_comm_init": (_i, [_pvp, _vp, _i, _i]),
@@ -92,7 +97,8 @@ _SIGS = {
 }
 
 _UNCHECKED = {"nm_last_error", "nm_version", "nm_conv2d_wgrad_f32_workspace", "nm_dense_wgrad_f32_workspace",
-              "nm_tc_conv3x3_wgrad_workspace", "nm_tc_conv1_bwd_workspace", "nm_tc_dense_wgrad_workspace"}
+              "nm_tc_conv3x3_wgrad_workspace", "nm_tc_conv1_bwd_workspace", "nm_tc_dense_wgrad_workspace",
+              "nm_tc_dense_softmax_ce_workspace", "nm_tc_dense_bwd_unpool_workspace"}
 
 
 class NeuromahB200Error(RuntimeError):

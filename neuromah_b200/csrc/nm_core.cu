@@ -1,5 +1,6 @@
 // Device / memory / stream / event / graph plumbing of the C ABI (include/neuromah_b200.h).
 #include "nm_common.cuh"
+#include <cuda_profiler_api.h>
 
 namespace nm {
 thread_local char g_err[512] = "";
@@ -119,6 +120,9 @@ int nm_graph_destroy(void* graph_exec) {
     if (graph_exec) NM_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
     return NM_OK;
 }
+
+int nm_profiler_start(void) { NM_CUDA(cudaProfilerStart()); return NM_OK; }
+int nm_profiler_stop(void) { NM_CUDA(cudaProfilerStop()); return NM_OK; }
 
 int nm_launch_count(unsigned long long* count) {
     NM_REQUIRE(count, "count is NULL");

@@ -13,51 +13,11 @@
 // following Layer_MaxPooling2D 2x2/2 (maxpooling_backend.cpp:24-133) for the tensor-core mode.
 #include "nm_common.cuh"
 #include "nm_tc_common.cuh"
-#include <mutex>
+#include "nm_tc_host.cuh"
 
 namespace {
 
 using namespace tc;
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int get_encoder(EncodeTiledFn* out) {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        cudaDriverEntryPointQueryResult q;
-        void* p = nullptr;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiledFn)p;
-    });
-    if (!fn) return nm::fail(NM_ERR_CUDA, "%s%s", "cuTensorMapEncodeTiled not available from the driver");
-    *out = fn;
-    return NM_OK;
-}
-
-// 2-D bf16 tensor map: rows x inner, row pitch in bytes, box (box_inner x box_rows), OOB reads as zero
-int make_map_2d(CUtensorMap* m, const void* gptr, uint64_t inner, uint64_t rows, uint64_t pitch_bytes,
-                uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle sw) {
-    EncodeTiledFn enc;
-    int rc = get_encoder(&enc);
-    if (rc) return rc;
-    cuuint64_t dims[2] = {inner, rows};
-    cuuint64_t strides[1] = {pitch_bytes};
-    cuuint32_t box[2] = {box_inner, box_rows};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return nm::fail(NM_ERR_CUDA, "%s%s", "cuTensorMapEncodeTiled failed");
-    return NM_OK;
-}
-
-int sm_count() {
-    static int n = 0;
-    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
-    return n;
-}
 
 constexpr int TILE_M = 128;
 
@@ -129,14 +89,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
     } else if (warp == 1) {
         // ============================== MMA issuer ================================
-        if (lane == 0) {
-            mbar_wait(bfull, 0);
-            const uint32_t b_base = smem_u32(b_smem);
-            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
-                mbar_wait(&full[stage], phase);
-                fence_after_sync();
+        // The whole warp runs the loop converged and ONE elected lane issues: under `if (lane == 0)` the
+        // compiler wraps every UTCHMMA in an ELECT/BRA.U.ANY retry loop fed by R2UR moves (~50 cycles per MMA,
+        // measured with scratch/mma_rate.cu); converged + elect.sync issues one every few cycles.
+        mbar_wait(bfull, 0);
+        const uint32_t b_base = smem_u32(b_smem);
+        int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            mbar_wait(&full[stage], phase);
+            fence_after_sync();
+            if (elect_one()) {
                 const uint32_t a_base = smem_u32(a_smem + (size_t)stage * p.a_stage_bytes);
                 const uint32_t d_addr = tmem_base + acc * NOUT;
 #pragma unroll
@@ -149,9 +112,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
                 mma_commit(&empty[stage]);          // A stage reusable once these MMAs have read it
                 mma_commit(&tfull[acc]);            // accumulator ready for the epilogue
-                if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
-                acc ^= 1; if (acc == 0) acc_phase ^= 1;
             }
+            __syncwarp();
+            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+            acc ^= 1; if (acc == 0) acc_phase ^= 1;
         }
     } else if (warp >= 4) {
         // ============================== epilogue (4 warps) ========================
@@ -309,14 +273,15 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0; uint32_t first = 1;
-            for (int kb = blockIdx.x; kb < p.num_kblocks; kb += gridDim.x) {
-                mbar_wait(&full[stage], phase);
-                fence_after_sync();
+        // converged warp, one elected lane issues (see conv3x3_tc_kernel)
+        int stage = 0; uint32_t phase = 0; uint32_t first = 1;
+        for (int kb = blockIdx.x; kb < p.num_kblocks; kb += gridDim.x) {
+            mbar_wait(&full[stage], phase);
+            fence_after_sync();
+            if (elect_one()) {
                 const uint32_t a_base = smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint32_t x_base = a_base + A_BYTES;
-#pragma unroll 1
+#pragma unroll
                 for (int ks = 0; ks < TILE_M / 16; ++ks) {
                     const uint64_t adesc = desc_at(TMPL_A, a_base + ks * 16 * A_ROWB);
 #pragma unroll
@@ -325,12 +290,14 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
                         mma_bf16(tmem_base + tap * CIN, adesc, desc_at(TMPL_B, x_base + shift), IDESC, !(first && ks == 0));
                     }
                 }
-                first = 0;
                 mma_commit(&empty[stage]);
-                if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
             }
-            mma_commit(done);
+            __syncwarp();
+            first = 0;
+            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         }
+        if (elect_one()) mma_commit(done);
+        __syncwarp();
     } else if (warp >= 4) {
         const int q = warp & 3;
         const bool has_work = (int)blockIdx.x < p.num_kblocks;
@@ -355,14 +322,32 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
 }
 
 // dw[oc][c][r][s] = sum_cta partial[cta][oc][(r*3+s)*CIN + c]      (fixed order => deterministic)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int n_cta, int COUT, int CIN) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int total = COUT * 9 * CIN;
-    if (i >= total) return;
-    int oc = i / (9 * CIN), rem = i - oc * 9 * CIN, tap = rem / CIN, c = rem - tap * CIN;
-    float s = 0.f;
-    for (int k = 0; k < n_cta; ++k) s += partial[(size_t)k * total + i];
-    dw[((size_t)oc * CIN + c) * 9 + tap] = s;
+// 64 consecutive outputs per block (coalesced 256-byte rows), 4 slices of the CTA range per output, combined in
+// a fixed order through shared memory.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                                           int n_cta, int COUT, int CIN) {
+    __shared__ float red[4][64];
+    const int total = COUT * 9 * CIN;
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63), slice = threadIdx.x >> 6;
+    const int per = (n_cta + 3) / 4, k0 = slice * per, k1 = min(n_cta, k0 + per);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (i < total) {
+        int k = k0;
+        for (; k + 4 <= k1; k += 4) {
+            s0 += __ldg(partial + (size_t)k * total + i);
+            s1 += __ldg(partial + (size_t)(k + 1) * total + i);
+            s2 += __ldg(partial + (size_t)(k + 2) * total + i);
+            s3 += __ldg(partial + (size_t)(k + 3) * total + i);
+        }
+        for (; k < k1; ++k) s0 += __ldg(partial + (size_t)k * total + i);
+    }
+    red[slice][threadIdx.x & 63] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (slice == 0 && i < total) {
+        const float s = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+        const int oc = i / (9 * CIN), rem = i - oc * 9 * CIN, tap = rem / CIN, c = rem - tap * CIN;
+        dw[((size_t)oc * CIN + c) * 9 + tap] = s;
+    }
 }
 
 // OIHW f32 -> bf16 [OC][tap][C] (fprop B operand) and [C][tap'][OC] with tap' = 8 - tap (dgrad B operand)
@@ -481,7 +466,7 @@ int nm_tc_conv3x3_wgrad_bf16(const void* x_pad, const void* dy_pad, float* dw, v
     rc = nm::launched("conv3x3_wgrad_tc");
     if (rc) return rc;
     int total = OC * 9 * C;
-    wgrad_reduce_kernel<<<nm_cdiv(total, 256), 256, 0, nm::S(stream)>>>(p.partial, dw, grid, OC, C);
+    wgrad_reduce_kernel<<<nm_cdiv(total, 64), 256, 0, nm::S(stream)>>>(p.partial, dw, grid, OC, C);
     return nm::launched("wgrad_reduce");
 }
 

@@ -175,110 +175,87 @@ conv1_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ 
     }
 }
 
-__global__ void conv1_bwd_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db,
-                                        int n_blocks, int OC) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= OC * 10) return;
-    float s = 0.f;
-    for (int b = 0; b < n_blocks; ++b) s += partial[(size_t)b * OC * 10 + i];
-    int oc = i / 10, t = i % 10;
-    if (t < 9) dw[oc * 9 + t] = s; else db[oc] = s;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Dense head + softmax + CCE + fused gradient.  x bf16 [B,K], wp f32 [NO][K] (packed, K in the kernel's
-// (h,w,c) order), one warp per row, the whole weight matrix staged in shared memory once per CTA.
-// ------------------------------------------------------------------------------------------------
-template <int NO>
-__global__ void __launch_bounds__(256)
-dense_softmax_ce_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ bias,
-                        const int32_t* __restrict__ labels, float* __restrict__ probs, float* __restrict__ dlogits,
-                        float* __restrict__ sample_loss, int32_t* __restrict__ correct, int B, int K, int n_out,
-                        float inv_batch) {
-    extern __shared__ float wsm[];                  // [n_out][K]
-    for (int i = threadIdx.x * 4; i < n_out * K; i += blockDim.x * 4)
-        *reinterpret_cast<float4*>(wsm + i) = *reinterpret_cast<const float4*>(wp + i);
+// 32 outputs x 8 slices of the block range per CTA; slices combined in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) conv1_bwd_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                                               float* __restrict__ db, int n_blocks, int OC) {
+    __shared__ float red[8][32];
+    const int total = OC * 10;
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+    const int per = (n_blocks + 7) / 8, b0 = slice * per, b1 = min(n_blocks, b0 + per);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (i < total) {
+        int b = b0;
+        for (; b + 4 <= b1; b += 4) {
+            s0 += __ldg(partial + (size_t)b * total + i);
+            s1 += __ldg(partial + (size_t)(b + 1) * total + i);
+            s2 += __ldg(partial + (size_t)(b + 2) * total + i);
+            s3 += __ldg(partial + (size_t)(b + 3) * total + i);
+        }
+        for (; b < b1; ++b) s0 += __ldg(partial + (size_t)b * total + i);
+    }
+    red[slice][threadIdx.x & 31] = (s0 + s1) + (s2 + s3);
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int row = blockIdx.x * nwarps + warp; row < B; row += gridDim.x * nwarps) {
-        float acc[NO];
+    if (slice == 0 && i < total) {
+        float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < NO; ++j) acc[j] = 0.f;
-        const uint2* xr = reinterpret_cast<const uint2*>(x + (size_t)row * K);
-        for (int k4 = lane; k4 < K / 4; k4 += 32) {
-            const uint2 u = __ldg(xr + k4);
-            const float x0 = bf_lo(u.x), x1 = bf_hi(u.x), x2 = bf_lo(u.y), x3 = bf_hi(u.y);
-#pragma unroll
-            for (int j = 0; j < NO; ++j) {
-                if (j < n_out) {
-                    const float4 wv = *reinterpret_cast<const float4*>(wsm + j * K + k4 * 4);
-                    acc[j] = fmaf(x0, wv.x, fmaf(x1, wv.y, fmaf(x2, wv.z, fmaf(x3, wv.w, acc[j]))));
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < NO; ++j)
-#pragma unroll
-            for (int o = 16; o; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-        if (lane == 0) {
-            float z[NO], mx = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < NO; ++j) if (j < n_out) { z[j] = acc[j] + bias[j]; mx = fmaxf(mx, z[j]); }
-            float s = 0.f;
-#pragma unroll
-            for (int j = 0; j < NO; ++j) if (j < n_out) { z[j] = expf(z[j] - mx); s += z[j]; }
-            const int yv = labels[row];
-            float best = -1.f; int bj = 0; float py = 1e-7f;
-#pragma unroll
-            for (int j = 0; j < NO; ++j) if (j < n_out) {
-                const float pj = z[j] / s;
-                probs[(size_t)row * n_out + j] = pj;
-                dlogits[(size_t)row * n_out + j] = (pj - (j == yv ? 1.f : 0.f)) * inv_batch;
-                if (pj > best) { best = pj; bj = j; }
-                if (j == yv) py = pj;
-            }
-            py = fminf(fmaxf(py, 1e-7f), 1.f - 1e-7f);
-            sample_loss[row] = -logf(py);
-            correct[row] = (bj == yv) ? 1 : 0;
-        }
+        for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+        const int oc = i / 10, t = i % 10;
+        if (t < 9) dw[oc * 9 + t] = s; else db[oc] = s;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Dense dgrad + pool backward + ReLU backward: dY of the last conv, straight into its zero-haloed bf16
-// layout [B, 2PH+2, 2PW+2, C].  Also the conv bias gradient (sum of the routed values) per image.
+// layout [B, 2PH+2, 2PW+2, C].  Also the conv bias gradient (sum of the routed values), one partial per CTA.
+// A thread owns ONE (pooled pixel, 8-channel group) for every image its CTA processes and keeps that
+// [n_out x 8] slice of the Dense weights in registers: the weights are read once per CTA instead of once
+// per image (the per-image version re-read 125 KB x 4096 images from L2 and sat at 10% of HBM).
+// The next image's nibbles are prefetched while the current one is routed and stored.
 // ------------------------------------------------------------------------------------------------
 template <int NO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(416, 1)
 dense_bwd_unpool_kernel(const float* __restrict__ dlogits, const float* __restrict__ wp, const uint8_t* __restrict__ idx,
-                        __nv_bfloat16* __restrict__ dy_pad, float* __restrict__ dbias_img, int PH, int PW, int C,
+                        __nv_bfloat16* __restrict__ dy_pad, float* __restrict__ dbias_cta, int B, int PH, int PW, int C,
                         int n_out) {
-    __shared__ float dl[NO];
-    __shared__ float red[256 * 8];
-    const int n = blockIdx.x, K = PH * PW * C, G = C / 8;
-    if (threadIdx.x < NO) dl[threadIdx.x] = threadIdx.x < n_out ? dlogits[(size_t)n * n_out + threadIdx.x] : 0.f;
-    __syncthreads();
+    extern __shared__ float red[];                       // [items][8] for the bias-gradient reduction
+    const int K = PH * PW * C, G = C / 8, items = PH * PW * G;
+    const int item = threadIdx.x;
+    const bool active = item < items;
+    const int g = item % G, pix = item / G, py = pix / PW, px = pix % PW;
     const int H2 = 2 * PH + 2, W2 = 2 * PW + 2;
+    float wv[NO][8];
+#pragma unroll
+    for (int j = 0; j < NO; ++j) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (active && j < n_out) {
+            a = __ldg(reinterpret_cast<const float4*>(wp + (size_t)j * K + pix * C + g * 8));
+            b = __ldg(reinterpret_cast<const float4*>(wp + (size_t)j * K + pix * C + g * 8 + 4));
+        }
+        wv[j][0] = a.x; wv[j][1] = a.y; wv[j][2] = a.z; wv[j][3] = a.w;
+        wv[j][4] = b.x; wv[j][5] = b.y; wv[j][6] = b.z; wv[j][7] = b.w;
+    }
     float bsum[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) bsum[c] = 0.f;
-    for (int item = threadIdx.x; item < PH * PW * G; item += blockDim.x) {
-        const int g = item % G, pix = item / G, py = pix / PW, px = pix % PW;
-        const int k0 = pix * C + g * 8;
+    const uint32_t* idx32 = reinterpret_cast<const uint32_t*>(idx);
+    int n = blockIdx.x;
+    uint32_t nibs_next = (active && n < B) ? __ldg(idx32 + (size_t)n * items + item) : 0u;
+    for (; n < B; n += gridDim.x) {
+        const uint32_t nibs = nibs_next;
+        const int nn = n + gridDim.x;
+        if (active && nn < B) nibs_next = __ldg(idx32 + (size_t)nn * items + item);
+        if (!active) continue;
         float d[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) d[c] = 0.f;
 #pragma unroll
         for (int j = 0; j < NO; ++j) {
             if (j < n_out) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(wp + (size_t)j * K + k0));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(wp + (size_t)j * K + k0 + 4));
-                const float s = dl[j];
-                d[0] = fmaf(s, a.x, d[0]); d[1] = fmaf(s, a.y, d[1]); d[2] = fmaf(s, a.z, d[2]); d[3] = fmaf(s, a.w, d[3]);
-                d[4] = fmaf(s, b.x, d[4]); d[5] = fmaf(s, b.y, d[5]); d[6] = fmaf(s, b.z, d[6]); d[7] = fmaf(s, b.w, d[7]);
+                const float sdl = __ldg(dlogits + (size_t)n * n_out + j);     // same address for the whole CTA: broadcast
+#pragma unroll
+                for (int c = 0; c < 8; ++c) d[c] = fmaf(sdl, wv[j][c], d[c]);
             }
         }
-        const uint32_t nibs = *reinterpret_cast<const uint32_t*>(idx + (((size_t)n * PH + py) * PW + px) * (C / 2) + g * 4);
         float v[4][8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -296,15 +273,17 @@ dense_bwd_unpool_kernel(const float* __restrict__ dlogits, const float* __restri
             *reinterpret_cast<uint4*>(dy_pad + (((size_t)n * H2 + Y) * W2 + X) * C + g * 8) = o;
         }
     }
-    // fixed-order block reduction of the bias-gradient partials: thread t always owns channel group t % G
+    // fixed-order reduction over the pooled pixels of each channel
+    if (active) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) red[threadIdx.x * 8 + c] = bsum[c];
+        for (int c = 0; c < 8; ++c) red[item * 8 + c] = bsum[c];
+    }
     __syncthreads();
-    if (threadIdx.x < C) {
-        const int g = threadIdx.x / 8, c = threadIdx.x % 8;
+    if ((int)threadIdx.x < C) {
+        const int gg = threadIdx.x / 8, c = threadIdx.x % 8;
         float s = 0.f;
-        for (int t = g; t < 256; t += G) s += red[t * 8 + c];
-        dbias_img[(size_t)n * C + threadIdx.x] = s;
+        for (int p2 = 0; p2 < PH * PW; ++p2) s += red[(p2 * G + gg) * 8 + c];
+        dbias_cta[(size_t)blockIdx.x * C + threadIdx.x] = s;
     }
 }
 
@@ -318,82 +297,6 @@ __global__ void column_sum_kernel(const float* __restrict__ in, float* __restric
     __syncthreads();
     for (int o = 128; o; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
     if (threadIdx.x == 0) out[c] = red[0];
-}
-
-// ------------------------------------------------------------------------------------------------
-// Dense wgrad: partial[chunk][k][j] = sum_{rows in chunk} x[row][k] * dlogits[row][j]
-// ------------------------------------------------------------------------------------------------
-template <int NO>
-__global__ void __launch_bounds__(256)
-dense_wgrad_partial_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dlogits,
-                           float* __restrict__ partial, int B, int K, int n_out, int rows_per_chunk) {
-    extern __shared__ float dls[];             // [rows_per_chunk][NO]
-    const int chunk = blockIdx.y, r0 = chunk * rows_per_chunk, r1 = min(B, r0 + rows_per_chunk);
-    for (int i = threadIdx.x; i < (r1 - r0) * NO; i += blockDim.x) {
-        int r = i / NO, j = i % NO;
-        dls[i] = j < n_out ? dlogits[(size_t)(r0 + r) * n_out + j] : 0.f;
-    }
-    __syncthreads();
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k > K) return;                               // k == K is a virtual all-ones feature: the bias gradient
-    float acc[NO];
-#pragma unroll
-    for (int j = 0; j < NO; ++j) acc[j] = 0.f;
-    for (int r = r0; r < r1; ++r) {
-        const float xv = k < K ? __bfloat162float(x[(size_t)r * K + k]) : 1.f;
-#pragma unroll
-        for (int j = 0; j < NO; ++j) acc[j] = fmaf(xv, dls[(r - r0) * NO + j], acc[j]);
-    }
-    float* dst = partial + ((size_t)chunk * (K + 1) + k) * NO;
-#pragma unroll
-    for (int j = 0; j < NO; ++j) dst[j] = acc[j];
-}
-
-// dw[perm(k)][j] = scale * sum_chunks partial + l1*sign(w) + 2*l2*w ;  db[j] = scale * sum_rows dlogits
-template <int NO>
-__global__ void dense_wgrad_reduce_kernel(const float* __restrict__ partial,
-                                          const float* __restrict__ w, float* __restrict__ dw, float* __restrict__ db,
-                                          int n_chunks, int B, int K, int n_out, int HW, int C, float scale, float l1, float l2) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < K * n_out) {
-        const int k = i / n_out, j = i % n_out;
-        float s = 0.f;
-        for (int c = 0; c < n_chunks; ++c) s += partial[((size_t)c * (K + 1) + k) * NO + j];
-        const int hw = k / C, ch = k % C, kr = ch * HW + hw;     // kernel (h,w,c) order -> reference (c,h,w) row
-        s *= scale;
-        const float wv = w[(size_t)kr * n_out + j];
-        if (l1 > 0.f) s += l1 * (wv > 0.f ? 1.f : (wv < 0.f ? -1.f : 0.f));
-        if (l2 > 0.f) s += 2.f * l2 * wv;
-        dw[(size_t)kr * n_out + j] = s;
-    } else if (i < K * n_out + n_out) {
-        const int j = i - K * n_out;
-        float s = 0.f;
-        for (int c = 0; c < n_chunks; ++c) s += partial[((size_t)c * (K + 1) + K) * NO + j];
-        db[j] = s * scale;
-    }
-}
-
-// reference (c,h,w)-row Dense weights [K][n_out] -> packed [n_out][K] with K in (h,w,c) order
-__global__ void pack_dense_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int K, int n_out, int HW, int C) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= K * n_out) return;
-    const int j = i / K, k = i % K, hw = k / C, ch = k % C;
-    wp[i] = w[(size_t)(ch * HW + hw) * n_out + j];
-}
-
-// single block, fixed order -> deterministic accumulation into double[2] {sum of losses, #correct}
-__global__ void tc_loss_acc_reduce_kernel(const float* __restrict__ sample_loss, const int32_t* __restrict__ correct,
-                                          double* __restrict__ accum, int B) {
-    __shared__ double sl[256]; __shared__ double sc[256];
-    double l = 0.0, c = 0.0;
-    for (int i = threadIdx.x; i < B; i += blockDim.x) { l += (double)sample_loss[i]; c += (double)correct[i]; }
-    sl[threadIdx.x] = l; sc[threadIdx.x] = c;
-    __syncthreads();
-    for (int o = 128; o; o >>= 1) {
-        if (threadIdx.x < o) { sl[threadIdx.x] += sl[threadIdx.x + o]; sc[threadIdx.x] += sc[threadIdx.x + o]; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) { accum[0] += sl[0]; accum[1] += sc[0]; }
 }
 
 constexpr int kNO = 16;
@@ -428,72 +331,34 @@ int nm_tc_conv1_bwd_bf16(const float* x, const void* dp_grid, const void* idx, f
                                                               static_cast<float*>(workspace), N, H, W);
     int rc = nm::launched("conv1_bwd");
     if (rc) return rc;
-    conv1_bwd_reduce_kernel<<<nm_cdiv(OC * 10, 128), 128, 0, nm::S(stream)>>>(static_cast<const float*>(workspace), dw, db, blocks, OC);
+    conv1_bwd_reduce_kernel<<<nm_cdiv(OC * 10, 32), 256, 0, nm::S(stream)>>>(static_cast<const float*>(workspace), dw, db, blocks, OC);
     return nm::launched("conv1_bwd_reduce");
 }
 
-int nm_tc_pack_dense_weights(const float* w, float* w_packed, int K, int n_out, int HW, int C, void* stream) {
-    NM_REQUIRE(w && w_packed, "null pointer");
-    NM_REQUIRE(K > 0 && n_out > 0 && HW > 0 && C > 0 && HW * C == K, "bad dimensions");
-    pack_dense_weights_kernel<<<nm_cdiv((size_t)K * n_out, 256), 256, 0, nm::S(stream)>>>(w, w_packed, K, n_out, HW, C);
-    return nm::launched("pack_dense_weights");
-}
-
-int nm_tc_dense_softmax_ce_bf16(const void* x, const float* w_packed, const float* bias, const int32_t* labels,
-                                float* probs, float* dlogits, float* sample_loss, int32_t* correct, double* accum,
-                                int B, int K, int n_out, float inv_batch, void* stream) {
-    NM_REQUIRE(x && w_packed && bias && labels && probs && dlogits && sample_loss && correct, "null pointer");
-    NM_REQUIRE(B > 0 && K > 0 && K % 4 == 0 && n_out > 0, "bad dimensions");
-    if (n_out > kNO || (size_t)n_out * K * sizeof(float) > 220 * 1024)
-        return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_dense_softmax_ce_bf16: needs n_out <= 16 and n_out*K floats of shared memory");
-    auto kern = dense_softmax_ce_kernel<kNO>;
-    size_t smem = (size_t)n_out * K * sizeof(float);
-    static bool attr = false;
-    if (!attr) { NM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
-    int grid = (B + 7) / 8 < 148 ? (B + 7) / 8 : 148;
-    kern<<<grid, 256, smem, nm::S(stream)>>>(static_cast<const __nv_bfloat16*>(x), w_packed, bias, labels, probs, dlogits,
-                                            sample_loss, correct, B, K, n_out, inv_batch);
-    int rc = nm::launched("dense_softmax_ce");
-    if (rc || !accum) return rc;
-    tc_loss_acc_reduce_kernel<<<1, 256, 0, nm::S(stream)>>>(sample_loss, correct, accum, B);
-    return nm::launched("tc_loss_acc_reduce");
-}
+size_t nm_tc_dense_bwd_unpool_workspace(int C) { return (size_t)148 * 2 * C * sizeof(float); }
 
 int nm_tc_dense_bwd_unpool_bf16(const float* dlogits, const float* w_packed, const void* idx, void* dy_pad,
                                 float* dbias, void* workspace, size_t workspace_bytes,
                                 int B, int PH, int PW, int C, int n_out, void* stream) {
     NM_REQUIRE(dlogits && w_packed && idx && dy_pad && dbias && workspace, "null pointer");
-    NM_REQUIRE(B > 0 && PH > 0 && PW > 0 && C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0 && n_out > 0 && n_out <= kNO, "bad dimensions");
-    NM_REQUIRE(workspace_bytes >= (size_t)B * C * sizeof(float), "workspace too small");
-    dense_bwd_unpool_kernel<kNO><<<B, 256, 0, nm::S(stream)>>>(dlogits, w_packed, static_cast<const uint8_t*>(idx),
-                                                             static_cast<__nv_bfloat16*>(dy_pad),
-                                                             static_cast<float*>(workspace), PH, PW, C, n_out);
+    NM_REQUIRE(B > 0 && PH > 0 && PW > 0 && C % 8 == 0 && n_out > 0 && n_out <= kNO, "bad dimensions");
+    const int items = PH * PW * (C / 8);
+    if (items > 416 || C > 416)
+        return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_dense_bwd_unpool_bf16: needs PH*PW*C/8 <= 416 (one thread per item)");
+    int grid = B < 148 ? B : 148;
+    NM_REQUIRE(workspace_bytes >= (size_t)grid * C * sizeof(float), "workspace too small");
+    const size_t smem = (size_t)items * 8 * sizeof(float);
+    const uint8_t* ip = static_cast<const uint8_t*>(idx);
+    __nv_bfloat16* dyp = static_cast<__nv_bfloat16*>(dy_pad);
+    float* part = static_cast<float*>(workspace);
+    if (n_out <= 10)     // the [n_out x 8] weight slice lives in registers: instantiate the common head width exactly
+        dense_bwd_unpool_kernel<10><<<grid, 416, smem, nm::S(stream)>>>(dlogits, w_packed, ip, dyp, part, B, PH, PW, C, n_out);
+    else
+        dense_bwd_unpool_kernel<kNO><<<grid, 416, smem, nm::S(stream)>>>(dlogits, w_packed, ip, dyp, part, B, PH, PW, C, n_out);
     int rc = nm::launched("dense_bwd_unpool");
     if (rc) return rc;
-    column_sum_kernel<<<C, 256, 0, nm::S(stream)>>>(static_cast<const float*>(workspace), dbias, B, C);
+    column_sum_kernel<<<C, 256, 0, nm::S(stream)>>>(static_cast<const float*>(workspace), dbias, grid, C);
     return nm::launched("column_sum");
-}
-
-size_t nm_tc_dense_wgrad_workspace(int B, int K) {
-    int rows = 64, chunks = (B + rows - 1) / rows;
-    return (size_t)chunks * (K + 1) * kNO * sizeof(float);
-}
-
-int nm_tc_dense_wgrad_bf16(const void* x, const float* dlogits, const float* w, float* dw, float* db,
-                           void* workspace, size_t workspace_bytes, int B, int K, int n_out, int HW, int C,
-                           float scale, float l1, float l2, void* stream) {
-    NM_REQUIRE(x && dlogits && w && dw && db && workspace, "null pointer");
-    NM_REQUIRE(B > 0 && K > 0 && n_out > 0 && n_out <= kNO && HW * C == K, "bad dimensions");
-    const int rows = 64, chunks = (B + rows - 1) / rows;
-    NM_REQUIRE(workspace_bytes >= (size_t)chunks * (K + 1) * kNO * sizeof(float), "workspace too small");
-    dim3 grid(nm_cdiv(K + 1, 256), chunks);
-    dense_wgrad_partial_kernel<kNO><<<grid, 256, rows * kNO * sizeof(float), nm::S(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), dlogits, static_cast<float*>(workspace), B, K, n_out, rows);
-    int rc = nm::launched("dense_wgrad_partial");
-    if (rc) return rc;
-    dense_wgrad_reduce_kernel<kNO><<<nm_cdiv((size_t)K * n_out + n_out, 256), 256, 0, nm::S(stream)>>>(
-        static_cast<const float*>(workspace), w, dw, db, chunks, B, K, n_out, HW, C, scale, l1, l2);
-    return nm::launched("dense_wgrad_reduce");
 }
 
 }  // extern "C"

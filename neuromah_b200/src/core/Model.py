@@ -306,6 +306,7 @@ class Model:
             self.softmax_classifier_output.backward(output, y)
             bsz = output.shape[0]
             self.plan.dlogits[0:bsz].copy_from(self.softmax_classifier_output.dinputs)
+            self.plan.dl_hilo_valid = False          # the bf16 hi/lo copy must be rebuilt from these dlogits
             self.plan.backward(gb)
             return
         if self.softmax_classifier_output is not None:

@@ -122,17 +122,20 @@ class TcCnnPlan:
         self.dy2_pad = z((B, 16, 16, 64), np.uint16)      # zero halo kept forever
         self.dp1 = z((B, 16, 16, 32), np.uint16)
         self.dummy_labels = z((B,), np.int32)
+        self.dl_hilo = z((B, 32), np.uint16)                 # dlogits as bf16 hi | lo (tcgen05 Dense wgrad operand)
         self.w3p = DeviceArray((self.n_out, K), np.float32)
+        self.w3hl = z((32, K), np.uint16)                    # Dense weights as bf16 hi | lo rows (tcgen05 Dense fprop operand)
         ws = max(lib.nm_tc_conv3x3_wgrad_workspace(32, 64), lib.nm_tc_conv1_bwd_workspace(32),
-                 lib.nm_tc_dense_wgrad_workspace(B, K), B * 64 * 4)
+                 lib.nm_tc_dense_wgrad_workspace(B, K), lib.nm_tc_dense_bwd_unpool_workspace(64))
         self.ws = DeviceArray((ws,), np.uint8)
+        self.ws_head = z((lib.nm_tc_dense_softmax_ce_workspace(B, K),), np.uint8)   # zero-filled once (ticket counter)
 
     def pack_weights(self):
         """Refresh the bf16 / permuted operand copies from the FP32 master weights in the arena."""
         s = stream()
         lib.nm_tc_pack_conv_weights_bf16(self.c2.weights.p, self.w2f.p, self.w2d.p, 64, 32, s)
         if self.w3p is not None:
-            lib.nm_tc_pack_dense_weights(self.de.weights.p, self.w3p.p, self.K, self.n_out, 49, 64, s)
+            lib.nm_tc_pack_dense_weights(self.de.weights.p, self.w3p.p, self.w3hl.p, self.K, self.n_out, 49, 64, s)
 
     # ------------------------------------------------------------------ passes ----
     def forward(self, x: DeviceArray, labels=None, accum=None, inv_batch=None):
@@ -146,9 +149,11 @@ class TcCnnPlan:
         _timed('tc_conv1_fwd_pool', lib.nm_tc_conv1_fwd_pool_bf16, x.p, self.c1.weights.p, self.act1_pad.p, self.idx1.p, B, 28, 28, 32, s)
         _timed('tc_conv2_fprop_pool', lib.nm_tc_conv3x3_fprop_pool_bf16, self.act1_pad.p, self.w2f.p, self.act2.p, self.idx2.p, B, 14, 14, 32, 64, 0, s)
         lab = labels if labels is not None else self.dummy_labels
-        _timed('tc_dense_softmax_ce', lib.nm_tc_dense_softmax_ce_bf16, self.act2.p, self.w3p.p, self.de.biases.p, lab.p, self.probs.p, self.dlogits.p,
-                                        self.losses.p, self.correct.p, accum.p if accum is not None else None,
-                                        B, self.K, self.n_out, float(1.0 / B if inv_batch is None else inv_batch), s)
+        _timed('tc_dense_softmax_ce', lib.nm_tc_dense_softmax_ce_bf16, self.act2.p, self.w3hl.p, self.de.biases.p, lab.p,
+               self.probs.p, self.dlogits.p, self.dl_hilo.p, self.losses.p, self.correct.p,
+               accum.p if accum is not None else None, self.ws_head.p, self.ws_head.nbytes,
+               B, self.K, self.n_out, float(1.0 / B if inv_batch is None else inv_batch), s)
+        self.dl_hilo_valid = labels is not None
         out = self.probs[0:B]
         # reference-style attribute views (host conversion on demand)
         self.p1.output = Bf16Activation(self.act1_pad, B, 1)
@@ -162,7 +167,9 @@ class TcCnnPlan:
         B = self.x.shape[0]
         s = stream()
         scale = 1.0 / (B if grad_batch is None else grad_batch)
-        _timed('tc_dense_wgrad', lib.nm_tc_dense_wgrad_bf16, self.act2.p, self.dlogits.p, self.de.weights.p, self.de.dweights.p, self.de.dbiases.p,
+        if not getattr(self, "dl_hilo_valid", False):      # dlogits were written by the public-API backward
+            lib.nm_tc_pack_dlogits_bf16(self.dlogits.p, self.dl_hilo.p, B, self.n_out, s)
+        _timed('tc_dense_wgrad', lib.nm_tc_dense_wgrad_bf16, self.act2.p, self.dl_hilo.p, self.dlogits.p, self.de.weights.p, self.de.dweights.p, self.de.dbiases.p,
                                    self.ws.p, self.ws.nbytes, B, self.K, self.n_out, 49, 64, float(scale),
                                    float(self.de.weight_regularizer_l1), float(self.de.weight_regularizer_l2), s)
         _timed('tc_dense_bwd_unpool', lib.nm_tc_dense_bwd_unpool_bf16, self.dlogits.p, self.w3p.p, self.idx2.p, self.dy2_pad.p,

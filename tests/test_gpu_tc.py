@@ -126,3 +126,121 @@ def test_tc_conv_wgrad(n, integer):
     dw2 = DeviceArray.zeros((64, 32, 3, 3))                        # deterministic: bitwise repeatable
     lib.nm_tc_conv3x3_wgrad_bf16(xp.p, dyp.p, dw2.p, ws.p, ws.nbytes, n, 14, 14, 32, 64, stream())
     np.testing.assert_array_equal(dw.numpy(), dw2.numpy())
+
+
+# ------------------------------------------------------------------ tcgen05 Dense head ----
+def _dense_case(B, K, n_out, hw, c, seed, integer):
+    rng = np.random.default_rng(seed)
+    if integer:
+        x = rng.integers(0, 3, (B, K)).astype(np.float32)                      # bf16-exact activations
+        w = (rng.integers(-4, 5, (K, n_out)) / 64.0).astype(np.float32)        # exact in bf16 -> lo half is zero
+    else:
+        x = bf16_round(np.abs(rng.standard_normal((B, K))).astype(np.float32))
+        w = (rng.standard_normal((K, n_out)) * 0.02).astype(np.float32)        # full FP32 weights: exercises hi + lo
+    b = (rng.standard_normal((1, n_out)) * 0.1).astype(np.float32)
+    y = rng.integers(0, n_out, B).astype(np.int32)
+    return rng, x, w, b, y
+
+
+def _hwc_from_chw(a_chw_cols, hw, c):
+    """[.., K] with K in the reference (c,h,w) order -> the kernels' (h,w,c) order."""
+    lead = a_chw_cols.shape[:-1]
+    return np.ascontiguousarray(a_chw_cols.reshape(lead + (c, hw)).swapaxes(-1, -2).reshape(lead + (hw * c,)))
+
+
+@pytest.mark.parametrize("B,K,n_out,hw,c,integer", [(4096, 3136, 10, 49, 64, False), (300, 3136, 10, 49, 64, True),
+                                                    (129, 512, 16, 8, 64, False), (7, 64, 3, 1, 64, True)])
+def test_tc_dense_head_forward_and_wgrad(B, K, n_out, hw, c, integer):
+    """Dense.py:79-80 + Softmax.py:7-11 + categorical_crossentropy.py:8-25 + fused gradient, then Dense.py:96-105."""
+    from neuromah_b200._lib import lib
+    from neuromah_b200.device import DeviceArray, stream
+    rng, x_ref, w, b, y = _dense_case(B, K, n_out, hw, c, 50 + B, integer)
+    s = stream()
+    x_k = _hwc_from_chw(x_ref, hw, c)                          # what the conv stack hands over: (h,w,c) order
+    xd = DeviceArray.from_numpy(to_bf16_bits(x_k))
+    wd, bd, yd = DeviceArray.from_numpy(w), DeviceArray.from_numpy(b), DeviceArray.from_numpy(y)
+    wp = DeviceArray.zeros((n_out, K))
+    whl = DeviceArray.zeros((32, K), np.uint16)
+    lib.nm_tc_pack_dense_weights(wd.p, wp.p, whl.p, K, n_out, hw, c, s)
+    np.testing.assert_array_equal(wp.numpy(), _hwc_from_chw(w.T.copy(), hw, c))
+    hl = from_bf16_bits(whl.numpy())
+    np.testing.assert_allclose(hl[:n_out] + hl[16:16 + n_out], wp.numpy(), rtol=2 ** -15, atol=1e-30)
+    assert not hl[n_out:16].any() and not hl[16 + n_out:].any()
+    probs, dl = DeviceArray.zeros((B, n_out)), DeviceArray.zeros((B, n_out))
+    dlh = DeviceArray.zeros((B, 32), np.uint16)
+    losses, correct = DeviceArray.zeros((B,)), DeviceArray.zeros((B,), np.int32)
+    accum = DeviceArray.zeros((2,), np.float64)
+    ws = DeviceArray.zeros((lib.nm_tc_dense_softmax_ce_workspace(B, K),), np.uint8)
+    for _ in range(2):                                         # twice: the ticket counter must be left at zero
+        lib.nm_tc_dense_softmax_ce_bf16(xd.p, whl.p, bd.p, yd.p, probs.p, dl.p, dlh.p, losses.p, correct.p, accum.p,
+                                        ws.p, ws.nbytes, B, K, n_out, 1.0 / B, s)
+    z = x_ref.astype(np.float64) @ w.astype(np.float64) + b
+    p_ref = R.softmax_forward(z)
+    tol = dict(rtol=1e-5, atol=1e-6) if integer else dict(rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose(probs.numpy(), p_ref, **tol)
+    loss_ref = R.cce_forward(p_ref, y)
+    np.testing.assert_allclose(losses.numpy(), loss_ref, rtol=1e-4, atol=1e-5)
+    d_ref = R.softmax_cce_backward(p_ref, y)
+    np.testing.assert_allclose(dl.numpy(), d_ref, rtol=1e-4, atol=1e-5 / B)
+    pred = np.argmax(probs.numpy(), axis=1)
+    np.testing.assert_array_equal(correct.numpy(), (pred == y).astype(np.int32))
+    acc = accum.numpy()
+    np.testing.assert_allclose(acc[0], 2 * losses.numpy().astype(np.float64).sum(), rtol=1e-9)
+    assert acc[1] == 2 * correct.numpy().sum()
+    dh = from_bf16_bits(dlh.numpy())
+    np.testing.assert_allclose(dh[:, :n_out] + dh[:, 16:16 + n_out], dl.numpy(), rtol=2 ** -15, atol=1e-30)
+
+    # wgrad from the same tensors
+    dw, db = DeviceArray.zeros((K, n_out)), DeviceArray.zeros((1, n_out))
+    ws2 = DeviceArray.zeros((lib.nm_tc_dense_wgrad_workspace(B, K),), np.uint8)
+    lib.nm_tc_dense_wgrad_bf16(xd.p, dlh.p, dl.p, wd.p, dw.p, db.p, ws2.p, ws2.nbytes, B, K, n_out, hw, c,
+                               1.0 / B, 0.0, 0.0, s)
+    dlr = dl.numpy().astype(np.float64)
+    dw_ref = x_ref.astype(np.float64).T @ dlr / B
+    db_ref = dlr.sum(axis=0, keepdims=True) / B
+    np.testing.assert_allclose(dw.numpy(), dw_ref, rtol=1e-4, atol=1e-5 * np.abs(dw_ref).max())
+    np.testing.assert_allclose(db.numpy(), db_ref, rtol=1e-4, atol=1e-5 * np.abs(db_ref).max())
+    dw2 = DeviceArray.zeros((K, n_out))                        # deterministic
+    lib.nm_tc_dense_wgrad_bf16(xd.p, dlh.p, dl.p, wd.p, dw2.p, db.p, ws2.p, ws2.nbytes, B, K, n_out, hw, c,
+                               1.0 / B, 0.0, 0.0, s)
+    np.testing.assert_array_equal(dw.numpy(), dw2.numpy())
+    # a dlogits tensor that did not come from the fused kernel: pack it, L1/L2 terms on
+    lib.nm_tc_pack_dlogits_bf16(dl.p, dlh.p, B, n_out, s)
+    lib.nm_tc_dense_wgrad_bf16(xd.p, dlh.p, dl.p, wd.p, dw2.p, db.p, ws2.p, ws2.nbytes, B, K, n_out, hw, c,
+                               1.0 / B, 0.01, 0.02, s)
+    reg = 0.01 * np.sign(w) + 2 * 0.02 * w
+    np.testing.assert_allclose(dw2.numpy(), dw_ref + reg, rtol=1e-4, atol=1e-5 * np.abs(dw_ref + reg).max())
+
+
+@pytest.mark.parametrize("B", [5, 700])
+def test_tc_dense_bwd_unpool(B):
+    """Dense.py:108 + maxpooling_backend.cpp:145-238 + Relu.py:12-14 fused into the last conv's dY."""
+    from neuromah_b200._lib import lib
+    from neuromah_b200.device import DeviceArray, stream
+    rng = np.random.default_rng(70 + B)
+    n_out, PH, PW, Cc = 10, 7, 7, 64
+    K = PH * PW * Cc
+    w = (rng.standard_normal((K, n_out)) * 0.05).astype(np.float32)          # reference (c,h,w) rows
+    dl = (rng.standard_normal((B, n_out)) / B).astype(np.float32)
+    nib = rng.integers(0, 8, (B, PH, PW, Cc)).astype(np.uint8)               # position | relu-bit << 2
+    idx = (nib[..., 0::2] | (nib[..., 1::2] << 4)).astype(np.uint8)
+    s = stream()
+    wd = DeviceArray.from_numpy(w)
+    wp = DeviceArray.zeros((n_out, K))
+    lib.nm_tc_pack_dense_weights(wd.p, wp.p, None, K, n_out, PH * PW, Cc, s)
+    dy = DeviceArray.zeros((B, 2 * PH + 2, 2 * PW + 2, Cc), np.uint16)
+    dbias = DeviceArray.zeros((Cc,))
+    ws = DeviceArray.zeros((lib.nm_tc_dense_bwd_unpool_workspace(Cc),), np.uint8)
+    lib.nm_tc_dense_bwd_unpool_bf16(DeviceArray.from_numpy(dl).p, wp.p, DeviceArray.from_numpy(idx).p, dy.p, dbias.p,
+                                    ws.p, ws.nbytes, B, PH, PW, Cc, n_out, s)
+    dflat = dl.astype(np.float64) @ w.astype(np.float64).T                    # (B, K) in (c,h,w) order
+    dpool = dflat.reshape(B, Cc, PH, PW).transpose(0, 2, 3, 1)                # -> (B, PH, PW, C)
+    live = (nib >> 2).astype(bool)
+    ref = np.zeros((B, 2 * PH + 2, 2 * PW + 2, Cc))
+    for pos in range(4):
+        sel = live & ((nib & 3) == pos)
+        ref[:, 1 + (pos >> 1):1 + 2 * PH:2, 1 + (pos & 1):1 + 2 * PW:2, :] = np.where(sel, dpool, 0.0)
+    got = from_bf16_bits(dy.numpy())
+    np.testing.assert_allclose(got, ref, rtol=2 ** -7, atol=1e-12)
+    assert not got[:, 0].any() and not got[:, -1].any() and not got[:, :, 0].any() and not got[:, :, -1].any()
+    np.testing.assert_allclose(dbias.numpy(), np.where(live, dpool, 0.0).sum(axis=(0, 1, 2)), rtol=1e-4, atol=1e-6)
