@@ -204,10 +204,16 @@ size_t nm_tc_conv3x3_wgrad_workspace(int C, int OC);
 int nm_tc_conv3x3_wgrad_bf16(const void* x_pad, const void* dy_pad, float* dw, void* workspace, size_t workspace_bytes,
                              int N, int H, int W, int C, int OC, void* stream);
 
-/* First conv of the net (C_in = 1, K = 9: streaming CUDA-core kernel) + ReLU + MaxPooling2D(2,2), forward:
- * x f32 [N,1,H,W], w f32 [OC,1,3,3] -> y_pad bf16 [N,H/2+2,W/2+2,OC] (interior), idx nibbles [N,H/2,W/2,OC/2]. */
-int nm_tc_conv1_fwd_pool_bf16(const float* x, const float* w, void* y_pad, void* idx, int N, int H, int W, int OC, void* stream);
-/* ... and backward: pool backward + ReLU backward (the nibble) + wgrad + bias gradient in one pass.
+/* First conv of the net (C_in = 1, 3x3 'same', ReLU, no bias) + MaxPooling2D(2,2) on tcgen05: the 4x4 input patch of a
+ * pool window is the K = 16 dimension and the weights are expanded to Wext[(window position, oc)][4x4] (zero outside the
+ * 3x3 support), so one MMA yields all four conv values of a window per TMEM lane and the pool needs no cross-lane traffic.
+ * w f32 [OC,1,3,3] -> w_ext bf16 [4*OC][16]. */
+int nm_tc_pack_conv1_weights_bf16(const float* w, void* w_ext, int OC, void* stream);
+/* x f32 [N,1,H,W] (rounded to bf16 as the MMA operand) -> y_pad bf16 [N,H/2+2,W/2+2,OC] (interior; the zero halo is
+ * never written), idx nibbles [N,H/2,W/2,OC/2].  OC = 32. */
+int nm_tc_conv1_fwd_pool_bf16(const float* x, const void* w_ext, void* y_pad, void* idx, int N, int H, int W, int OC, void* stream);
+/* ... and backward: pool backward + ReLU backward (the nibble) + wgrad + bias gradient in one tcgen05 pass
+ * (E[(pos,oc)][4x4 patch] accumulated in TMEM, one FP32 partial per CTA, fixed-order reduction).
  * dp_grid = gradient of the pooled output, bf16 on the un-shifted grid [N,H/2+2,W/2+2,OC] (nm_tc_conv3x3_dgrad_bf16). */
 size_t nm_tc_conv1_bwd_workspace(int OC);
 int nm_tc_conv1_bwd_bf16(const float* x, const void* dp_grid, const void* idx, float* dw, float* db,

@@ -77,6 +77,7 @@ _SIGS = {
     "nm_tc_conv3x3_dgrad_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_conv3x3_wgrad_workspace": (_sz, [_i, _i]),
     "nm_tc_conv3x3_wgrad_bf16": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
+    "nm_tc_pack_conv1_weights_bf16": (_i, [_vp, _vp, _i, _vp]),
     "nm_tc_conv1_fwd_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "nm_tc_conv1_bwd_workspace": (_sz, [_i]),
     "nm_tc_conv1_bwd_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp]),

@@ -1,0 +1,446 @@
+// First convolution of the net (C_in = 1, 3x3 'same', ReLU, no bias) fused with the following 2x2/2 max-pool,
+// forward and backward, on the tcgen05 tensor cores.
+//
+// With one input channel the GEMM K dimension is only 9, so instead of nine shifted taps the kernels use the
+// 4x4 INPUT PATCH of a pool window as the K = 16 dimension:
+//
+//   forward   D[window, (pos, oc)] = sum_{a,b} patch[window][a][b] * Wext[(pos, oc)][a][b]
+//             Wext[(dy,dx,oc)][a][b] = W[oc][a-dy][b-dx] (zero outside the 3x3 support)
+//             -> ONE tcgen05.mma (M = 128 windows, N = 128 = 4 window positions x 32 channels, K = 16) per tile;
+//             every TMEM lane (= epilogue thread) then holds all four conv values of its pool window for all
+//             channels: ReLU + max-pool + arg-max nibble need no cross-lane traffic at all.
+//   backward  E[(pos, oc), (a,b)] = sum_windows G[window][(pos, oc)] * patch[window][a][b]
+//             G = pooled gradient routed to its arg-max position and masked by ReLU' (the nibble), so
+//             dW[oc][r][s] = sum_pos E[(pos,oc)][(dy+r, dx+s)], and a constant-one 17th patch column gives
+//             db[oc] = sum_pos E[(pos,oc)][16].  Nothing of the 28x28x32 activation gradient is materialised.
+//
+// The operand tiles are written by builder warps with ordinary stores in the UMMA swizzled layouts
+// (no TMA: the rows are gathered 4x4 patches) and published to the async proxy with fence.proxy.async.
+//
+// Replaces: conv2d_cpu / conv2d_backward_cpu for the first layer (src/layers/CPU_kernels/Conv2D.cpp:83-146, :150-240),
+// Layer_Conv2D.forward/backward incl. np.pad and the bias gradient (src/layers/Conv_wrapepr.py:73-115), Activation_ReLU
+// (src/activations/Relu.py:7-14) and Layer_MaxPooling2D 2x2/2 forward/backward (maxpooling_backend.cpp:24-133, :145-238).
+#include "nm_common.cuh"
+#include "nm_tc_common.cuh"
+#include "nm_tc_host.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int OC = 32;
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// byte offset of (row, byte-in-row) inside a tile of 64-byte / 128-byte rows in the SWIZZLE_64B / SWIZZLE_128B layout
+// (16-byte chunk index XOR address bits [7,9) / [7,10)); the tile base is 1024-byte aligned.
+__device__ __forceinline__ uint32_t sw64(uint32_t row, uint32_t byte) { const uint32_t o = row * 64 + byte; return o ^ (((o >> 7) & 3) << 4); }
+__device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t byte) { const uint32_t o = row * 128 + byte; return o ^ (((o >> 7) & 7) << 4); }
+
+struct Conv1Geom { int N, H, W, PH, PW, PHW; long long total; int num_tiles; };
+
+// the 4x4 input patch of pool window g (zero outside the image: the 'same' padding of Conv_wrapepr.py:78-84)
+__device__ __forceinline__ void load_patch(const float* __restrict__ x, const Conv1Geom& G, long long g, float p[16]) {
+    if (g < G.total) {
+        const int n = (int)(g / G.PHW), w = (int)(g - (long long)n * G.PHW), py = w / G.PW, px = w - py * G.PW;
+        const float* img = x + (size_t)n * G.H * G.W;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int yy = 2 * py - 1 + a;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int xx = 2 * px - 1 + b;
+                p[a * 4 + b] = ((unsigned)yy < (unsigned)G.H && (unsigned)xx < (unsigned)G.W) ? __ldg(img + yy * G.W + xx) : 0.f;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) p[i] = 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+constexpr int F_TILE_BYTES = 128 * 64;          // 128 rows x 64 B (K = 16 bf16 used, SWIZZLE_64B)
+constexpr int F_STAGES = 3;
+
+__global__ void __launch_bounds__(416, 1)
+conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ wext, __nv_bfloat16* __restrict__ y_pad,
+                    uint8_t* __restrict__ idx, Conv1Geom G) {
+    constexpr uint64_t TMPL = desc_template(16, 512, LAYOUT_SW64);
+    constexpr uint32_t IDESC = idesc_bf16(128, 128, 0, 0);
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* b_smem = smem;
+    uint8_t* a_smem = smem + F_TILE_BYTES;
+    uint64_t* afull = reinterpret_cast<uint64_t*>(a_smem + F_STAGES * F_TILE_BYTES);
+    uint64_t* aempty = afull + F_STAGES;
+    uint64_t* tfull = aempty + F_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // Wext [128 (pos,oc)][16] bf16 -> B tile
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const int row = i >> 1, c = i & 1;
+        *reinterpret_cast<uint4*>(b_smem + sw64(row, c * 16)) = __ldg(reinterpret_cast<const uint4*>(wext + row * 16 + c * 8));
+    }
+    fence_proxy_async();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < F_STAGES; ++s) { mbar_init(&afull[s], 128); mbar_init(&aempty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, 256);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ============================== builders: one pool window per thread =================
+        const int row = threadIdx.x;
+        float cur[16], nxt[16];
+        int tile = blockIdx.x;
+        load_patch(x, G, (long long)tile * 128 + row, cur);
+        int stage = 0; uint32_t phase = 0;
+        for (; tile < G.num_tiles; tile += gridDim.x) {
+            const int ntile = tile + gridDim.x;
+            if (ntile < G.num_tiles) load_patch(x, G, (long long)ntile * 128 + row, nxt);   // in flight during the stores below
+            mbar_wait(&aempty[stage], phase ^ 1);
+            uint8_t* at = a_smem + stage * F_TILE_BYTES;
+            *reinterpret_cast<uint4*>(at + sw64(row, 0)) = make_uint4(pack_bf16x2(cur[0], cur[1]), pack_bf16x2(cur[2], cur[3]),
+                                                                       pack_bf16x2(cur[4], cur[5]), pack_bf16x2(cur[6], cur[7]));
+            *reinterpret_cast<uint4*>(at + sw64(row, 16)) = make_uint4(pack_bf16x2(cur[8], cur[9]), pack_bf16x2(cur[10], cur[11]),
+                                                                        pack_bf16x2(cur[12], cur[13]), pack_bf16x2(cur[14], cur[15]));
+            fence_proxy_async();
+            mbar_arrive(&afull[stage]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+            if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 4) {
+        // ============================== MMA issuer ===========================================
+        const uint32_t b_base = smem_u32(b_smem);
+        int stage = 0; uint32_t phase = 0; int it = 0;
+        for (int tile = blockIdx.x; tile < G.num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+            mbar_wait(&afull[stage], phase);
+            fence_after_sync();
+            if (elect_one()) {
+                mma_bf16(tmem_base + acc * 128, desc_at(TMPL, smem_u32(a_smem + stage * F_TILE_BYTES)), desc_at(TMPL, b_base), IDESC, 0);
+                mma_commit(&aempty[stage]);
+                mma_commit(&tfull[acc]);
+            }
+            __syncwarp();
+            if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else {
+        // ============================== epilogue: two groups of 4 warps, alternating tiles ====
+        const int grp = (warp - 5) >> 2, q = warp & 3;                     // q = TMEM sub-partition of this warp
+        int it = grp;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < G.num_tiles; tile += 2 * gridDim.x, it += 2) {
+            mbar_wait(&tfull[grp], (it >> 1) & 1);
+            fence_after_sync();
+            const long long g = (long long)tile * 128 + q * 32 + lane;
+            const bool valid = g < G.total;
+            int n = 0, py = 0, px = 0, w = 0;
+            if (valid) { n = (int)(g / G.PHW); w = (int)(g - (long long)n * G.PHW); py = w / G.PW; px = w - py * G.PW; }
+            __nv_bfloat16* yo = y_pad + (((size_t)n * (G.PH + 2) + py + 1) * (G.PW + 2) + px + 1) * OC;
+            uint32_t nibw[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t raw[4][16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 128 + h * 16;
+#pragma unroll
+                for (int pos = 0; pos < 4; ++pos) tmem_ld_x16(taddr + pos * 32, raw[pos]);
+                tmem_ld_wait();
+                if (h == 1) {                                              // accumulator drained: the MMA may overwrite it
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[grp]);
+                }
+                float best[16];
+                uint32_t nl = 0, nh = 0;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    // max-pool of ReLU == ReLU of max-pool; first max of the reference scan (0,0),(0,1),(1,0),(1,1) with its
+                    // strict '>' (maxpooling_backend.cpp:104); an all-non-positive window keeps position 0 like the reference.
+                    float bv = fmaxf(__uint_as_float(raw[0][c]), 0.f); uint32_t bi = 0;
+#pragma unroll
+                    for (int pos = 1; pos < 4; ++pos) {
+                        const float v = __uint_as_float(raw[pos][c]);
+                        if (v > bv) { bv = v; bi = pos; }
+                    }
+                    best[c] = bv;
+                    const uint32_t nb = bi | (bv > 0.f ? 4u : 0u);
+                    if (c < 8) nl |= nb << (4 * c); else nh |= nb << (4 * (c - 8));
+                }
+                nibw[2 * h] = nl; nibw[2 * h + 1] = nh;
+                if (valid) {
+                    uint4* dst = reinterpret_cast<uint4*>(yo + h * 16);
+                    dst[0] = make_uint4(pack_bf16x2(best[0], best[1]), pack_bf16x2(best[2], best[3]),
+                                        pack_bf16x2(best[4], best[5]), pack_bf16x2(best[6], best[7]));
+                    dst[1] = make_uint4(pack_bf16x2(best[8], best[9]), pack_bf16x2(best[10], best[11]),
+                                        pack_bf16x2(best[12], best[13]), pack_bf16x2(best[14], best[15]));
+                }
+            }
+            if (valid)
+                *reinterpret_cast<uint4*>(idx + ((size_t)n * G.PHW + w) * (OC / 2)) = make_uint4(nibw[0], nibw[1], nibw[2], nibw[3]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, 256);
+}
+
+// Wext[(dy,dx,oc)][a*4+b] = W[oc][a-dy][b-dx] inside the 3x3 support, else 0
+__global__ void pack_conv1_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wext) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 128 * 16) return;
+    const int row = i >> 4, k = i & 15, pos = row >> 5, oc = row & 31, a = k >> 2, b = k & 3;
+    const int r = a - (pos >> 1), s = b - (pos & 1);
+    const float v = ((unsigned)r < 3u && (unsigned)s < 3u) ? w[oc * 9 + r * 3 + s] : 0.f;
+    wext[i] = __float2bfloat16(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+constexpr int B_G_BYTES = 2 * 128 * 128;        // G: two SW128 column blocks [(pos>>1)] of [128 windows][64 (pos&1, oc)] bf16
+constexpr int B_P_BYTES = 128 * 64;             // P: [128 windows][32 = 16 patch + 1 ones + 15 zero] bf16, SW64
+constexpr int B_STAGE = B_G_BYTES + B_P_BYTES;  // 40 KB
+constexpr int B_STAGES = 3;
+constexpr int B_MAX_GRID = 148;
+
+__global__ void __launch_bounds__(288, 1)
+conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dp_grid, const uint8_t* __restrict__ idx,
+                    float* __restrict__ partial, Conv1Geom G) {
+    constexpr uint64_t TMPL_A = desc_template(16, 1024, LAYOUT_SW128);     // MN-major: SBO = 8 k-rows of 128 B
+    constexpr uint64_t TMPL_B = desc_template(16, 512, LAYOUT_SW64);       //           SBO = 8 k-rows of 64 B
+    constexpr uint32_t IDESC = idesc_bf16(64, 32, 1, 1);
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* afull = reinterpret_cast<uint64_t*>(smem + B_STAGES * B_STAGE);
+    uint64_t* aempty = afull + B_STAGES;
+    uint64_t* done = aempty + B_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // constant half of every P row: column 16 = 1 (bias gradient), columns 17..31 = 0
+    for (int i = threadIdx.x; i < B_STAGES * 128; i += blockDim.x) {
+        uint8_t* pt = smem + (i / 128) * B_STAGE + B_G_BYTES;
+        const int row = i % 128;
+        *reinterpret_cast<uint4*>(pt + sw64(row, 32)) = make_uint4(0x00003F80u, 0u, 0u, 0u);   // bf16(1.0) = 0x3F80
+        *reinterpret_cast<uint4*>(pt + sw64(row, 48)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < B_STAGES; ++s) { mbar_init(&afull[s], 256); mbar_init(&aempty[s], 1); }
+        mbar_init(done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 64);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const bool has_work = (int)blockIdx.x < G.num_tiles;
+
+    if (warp < 8) {
+        // ============================== builders: (window, half of the channels) per thread ==
+        const int row = threadIdx.x & 127, hh = threadIdx.x >> 7;
+        uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0, nd0 = d0, nd1 = d0;
+        uint2 nb = make_uint2(0, 0), nnb = nb;
+        float cur[16], nxt[16];
+        auto fetch = [&](int tile, uint4& a0, uint4& a1, uint2& nn, float p[16]) {
+            const long long g = (long long)tile * 128 + row;
+            a0 = make_uint4(0, 0, 0, 0); a1 = a0; nn = make_uint2(0, 0);
+            if (g < G.total) {
+                const int n = (int)(g / G.PHW), w = (int)(g - (long long)n * G.PHW), py = w / G.PW, px = w - py * G.PW;
+                const uint4* src = reinterpret_cast<const uint4*>(dp_grid + (((size_t)n * (G.PH + 2) + py) * (G.PW + 2) + px) * OC + hh * 16);
+                a0 = __ldg(src); a1 = __ldg(src + 1);
+                nn = __ldg(reinterpret_cast<const uint2*>(idx + ((size_t)n * G.PHW + w) * (OC / 2) + hh * 8));
+            }
+            if (hh == 0) load_patch(x, G, g, p);
+        };
+        int tile = blockIdx.x;
+        if (has_work) fetch(tile, d0, d1, nb, cur);
+        int stage = 0; uint32_t phase = 0;
+        for (; tile < G.num_tiles; tile += gridDim.x) {
+            const int ntile = tile + gridDim.x;
+            if (ntile < G.num_tiles) fetch(ntile, nd0, nd1, nnb, nxt);
+            mbar_wait(&aempty[stage], phase ^ 1);
+            uint8_t* gt = smem + stage * B_STAGE;
+            const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};   // 16 channels as bf16 pairs
+            uint32_t out[4][8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t nw = j < 4 ? nb.x : nb.y;
+                const uint32_t n0 = (nw >> (8 * (j & 3))) & 7u, n1 = (nw >> (8 * (j & 3) + 4)) & 7u;   // position | relu << 2
+                const uint32_t lo = dw[j] & 0xFFFFu, hi = dw[j] & 0xFFFF0000u;
+#pragma unroll
+                for (int pos = 0; pos < 4; ++pos)
+                    out[pos][j] = (n0 == (4u | pos) ? lo : 0u) | (n1 == (4u | pos) ? hi : 0u);   // arg-max routing + ReLU mask
+            }
+#pragma unroll
+            for (int pos = 0; pos < 4; ++pos) {
+                uint8_t* blk = gt + (pos >> 1) * (128 * 128);
+                const uint32_t base = (pos & 1) * 64 + hh * 32;
+                *reinterpret_cast<uint4*>(blk + sw128(row, base)) = make_uint4(out[pos][0], out[pos][1], out[pos][2], out[pos][3]);
+                *reinterpret_cast<uint4*>(blk + sw128(row, base + 16)) = make_uint4(out[pos][4], out[pos][5], out[pos][6], out[pos][7]);
+            }
+            if (hh == 0) {
+                uint8_t* pt = gt + B_G_BYTES;
+                *reinterpret_cast<uint4*>(pt + sw64(row, 0)) = make_uint4(pack_bf16x2(cur[0], cur[1]), pack_bf16x2(cur[2], cur[3]),
+                                                                           pack_bf16x2(cur[4], cur[5]), pack_bf16x2(cur[6], cur[7]));
+                *reinterpret_cast<uint4*>(pt + sw64(row, 16)) = make_uint4(pack_bf16x2(cur[8], cur[9]), pack_bf16x2(cur[10], cur[11]),
+                                                                            pack_bf16x2(cur[12], cur[13]), pack_bf16x2(cur[14], cur[15]));
+            }
+            fence_proxy_async();
+            mbar_arrive(&afull[stage]);
+            d0 = nd0; d1 = nd1; nb = nnb;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+            if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+        }
+        // ============================== epilogue: E -> one FP32 partial per CTA ==============
+        if (warp < 4) {
+            if (has_work) { mbar_wait(done, 0); fence_after_sync(); }
+            // M = 64 accumulator rows sit in TMEM lanes (m % 16) + 32 * (m / 16): lanes 0..15 of each sub-partition
+            const int q = warp, m = 16 * q + lane;
+#pragma unroll
+            for (int mh = 0; mh < 2; ++mh) {
+                uint32_t raw[32];
+                if (has_work) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + mh * 32;
+                    tmem_ld_x16(taddr, raw);
+                    tmem_ld_x16(taddr + 16, raw + 16);
+                    tmem_ld_wait();
+                }
+                if (lane < 16) {
+                    float4* dst = reinterpret_cast<float4*>(partial + ((size_t)blockIdx.x * 128 + mh * 64 + m) * 32);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        dst[j / 4] = has_work ? make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]),
+                                                            __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    } else {
+        // ============================== MMA issuer ===========================================
+        int stage = 0; uint32_t phase = 0; uint32_t first = 1;
+        for (int tile = blockIdx.x; tile < G.num_tiles; tile += gridDim.x) {
+            mbar_wait(&afull[stage], phase);
+            fence_after_sync();
+            if (elect_one()) {
+                const uint32_t g_base = smem_u32(smem + stage * B_STAGE), p_base = g_base + B_G_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint64_t bdesc = desc_at(TMPL_B, p_base + ks * 16 * 64);
+#pragma unroll
+                    for (int mh = 0; mh < 2; ++mh)
+                        mma_bf16(tmem_base + mh * 32, desc_at(TMPL_A, g_base + mh * (128 * 128) + ks * 16 * 128), bdesc, IDESC,
+                                 !(first && ks == 0));
+                }
+                mma_commit(&aempty[stage]);
+            }
+            __syncwarp();
+            first = 0;
+            if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (has_work && elect_one()) mma_commit(done);
+        __syncwarp();
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, 64);
+}
+
+// dW[oc][r][s] = sum_cta sum_pos E[cta][(pos,oc)][(dy+r)*4 + dx+s],  db[oc] = sum_cta sum_pos E[cta][(pos,oc)][16]
+// 32 outputs x 8 slices of the CTA range per block, slices combined in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+conv1_tc_bwd_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db, int n_cta) {
+    __shared__ float red[8][32];
+    const int total = OC * 10;
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+    const int per = (n_cta + 7) / 8, c0 = slice * per, c1 = min(n_cta, c0 + per);
+    float s = 0.f;
+    if (i < total) {
+        const int oc = i / 10, t = i % 10, r = t / 3, sx = t % 3;
+        for (int c = c0; c < c1; ++c) {
+            float v[4];
+#pragma unroll
+            for (int pos = 0; pos < 4; ++pos) {
+                const int col = t < 9 ? ((pos >> 1) + r) * 4 + (pos & 1) + sx : 16;
+                v[pos] = __ldg(partial + ((size_t)c * 128 + pos * 32 + oc) * 32 + col);
+            }
+            s += (v[0] + v[1]) + (v[2] + v[3]);
+        }
+    }
+    red[slice][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (slice == 0 && i < total) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a += red[k][threadIdx.x];
+        const int oc = i / 10, t = i % 10;
+        if (t < 9) dw[oc * 9 + t] = a; else db[oc] = a;
+    }
+}
+
+int geom(Conv1Geom* g, int N, int H, int W) {
+    g->N = N; g->H = H; g->W = W; g->PH = H / 2; g->PW = W / 2; g->PHW = g->PH * g->PW;
+    g->total = (long long)N * g->PHW;
+    g->num_tiles = (int)((g->total + 127) / 128);
+    return NM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nm_tc_pack_conv1_weights_bf16(const float* w, void* w_ext, int OCn, void* stream) {
+    NM_REQUIRE(w && w_ext, "null pointer");
+    if (OCn != OC) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_pack_conv1_weights_bf16: only OC=32 is instantiated");
+    pack_conv1_weights_kernel<<<8, 256, 0, nm::S(stream)>>>(w, static_cast<__nv_bfloat16*>(w_ext));
+    return nm::launched("pack_conv1_weights");
+}
+
+int nm_tc_conv1_fwd_pool_bf16(const float* x, const void* w_ext, void* y_pad, void* idx, int N, int H, int W, int OCn, void* stream) {
+    NM_REQUIRE(x && w_ext && y_pad && idx, "null pointer");
+    NM_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "bad dimensions");
+    if (OCn != OC) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_fwd_pool_bf16: only OC=32 is instantiated");
+    Conv1Geom g; geom(&g, N, H, W);
+    const size_t smem = (size_t)(1 + F_STAGES) * F_TILE_BYTES + 256;
+    static bool attr = false;
+    if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv1_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+    const int grid = g.num_tiles < sm_count() ? g.num_tiles : sm_count();
+    conv1_tc_fwd_kernel<<<grid, 416, smem, nm::S(stream)>>>(x, static_cast<const __nv_bfloat16*>(w_ext), static_cast<__nv_bfloat16*>(y_pad),
+                                                           static_cast<uint8_t*>(idx), g);
+    return nm::launched("conv1_tc_fwd");
+}
+
+size_t nm_tc_conv1_bwd_workspace(int OCn) { (void)OCn; return (size_t)B_MAX_GRID * 128 * 32 * sizeof(float); }
+
+int nm_tc_conv1_bwd_bf16(const float* x, const void* dp_grid, const void* idx, float* dw, float* db,
+                         void* workspace, size_t workspace_bytes, int N, int H, int W, int OCn, void* stream) {
+    NM_REQUIRE(x && dp_grid && idx && dw && db && workspace, "null pointer");
+    NM_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "bad dimensions");
+    if (OCn != OC) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_bwd_bf16: only OC=32 is instantiated");
+    Conv1Geom g; geom(&g, N, H, W);
+    int grid = sm_count() < B_MAX_GRID ? sm_count() : B_MAX_GRID;
+    if (g.num_tiles < grid) grid = g.num_tiles;
+    NM_REQUIRE(workspace_bytes >= (size_t)grid * 128 * 32 * sizeof(float), "workspace too small");
+    const size_t smem = (size_t)B_STAGES * B_STAGE + 256;
+    static bool attr = false;
+    if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv1_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+    conv1_tc_bwd_kernel<<<grid, 288, smem, nm::S(stream)>>>(x, static_cast<const __nv_bfloat16*>(dp_grid), static_cast<const uint8_t*>(idx),
+                                                           static_cast<float*>(workspace), g);
+    int rc = nm::launched("conv1_tc_bwd");
+    if (rc) return rc;
+    conv1_tc_bwd_reduce_kernel<<<nm_cdiv(OC * 10, 32), 256, 0, nm::S(stream)>>>(static_cast<const float*>(workspace), dw, db, grid);
+    return nm::launched("conv1_tc_bwd_reduce");
+}
+
+}  // extern "C"

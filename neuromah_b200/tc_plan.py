@@ -96,6 +96,7 @@ class TcCnnPlan:
         self.scratch = Scratch()
         self.w2f = DeviceArray((64, 9, 32), np.uint16)
         self.w2d = DeviceArray((32, 9, 64), np.uint16)
+        self.w1e = DeviceArray((128, 16), np.uint16)          # conv1 weights expanded over the 4 pool-window positions
         self.w3p = None
         self.launches_per_step = 0
 
@@ -133,6 +134,7 @@ class TcCnnPlan:
     def pack_weights(self):
         """Refresh the bf16 / permuted operand copies from the FP32 master weights in the arena."""
         s = stream()
+        lib.nm_tc_pack_conv1_weights_bf16(self.c1.weights.p, self.w1e.p, 32, s)
         lib.nm_tc_pack_conv_weights_bf16(self.c2.weights.p, self.w2f.p, self.w2d.p, 64, 32, s)
         if self.w3p is not None:
             lib.nm_tc_pack_dense_weights(self.de.weights.p, self.w3p.p, self.w3hl.p, self.K, self.n_out, 49, 64, s)
@@ -146,7 +148,7 @@ class TcCnnPlan:
         s = stream()
         self.x = x
         self.pack_weights()          # master weights may have changed (optimizer, set_parameters, FedAvg)
-        _timed('tc_conv1_fwd_pool', lib.nm_tc_conv1_fwd_pool_bf16, x.p, self.c1.weights.p, self.act1_pad.p, self.idx1.p, B, 28, 28, 32, s)
+        _timed('tc_conv1_fwd_pool', lib.nm_tc_conv1_fwd_pool_bf16, x.p, self.w1e.p, self.act1_pad.p, self.idx1.p, B, 28, 28, 32, s)
         _timed('tc_conv2_fprop_pool', lib.nm_tc_conv3x3_fprop_pool_bf16, self.act1_pad.p, self.w2f.p, self.act2.p, self.idx2.p, B, 14, 14, 32, 64, 0, s)
         lab = labels if labels is not None else self.dummy_labels
         _timed('tc_dense_softmax_ce', lib.nm_tc_dense_softmax_ce_bf16, self.act2.p, self.w3hl.p, self.de.biases.p, lab.p,

@@ -231,8 +231,8 @@ def test_tc_dense_bwd_unpool(B):
     dy = DeviceArray.zeros((B, 2 * PH + 2, 2 * PW + 2, Cc), np.uint16)
     dbias = DeviceArray.zeros((Cc,))
     ws = DeviceArray.zeros((lib.nm_tc_dense_bwd_unpool_workspace(Cc),), np.uint8)
-    lib.nm_tc_dense_bwd_unpool_bf16(DeviceArray.from_numpy(dl).p, wp.p, DeviceArray.from_numpy(idx).p, dy.p, dbias.p,
-                                    ws.p, ws.nbytes, B, PH, PW, Cc, n_out, s)
+    dld, idxd = DeviceArray.from_numpy(dl), DeviceArray.from_numpy(idx)     # keep the device buffers alive across the launch
+    lib.nm_tc_dense_bwd_unpool_bf16(dld.p, wp.p, idxd.p, dy.p, dbias.p, ws.p, ws.nbytes, B, PH, PW, Cc, n_out, s)
     dflat = dl.astype(np.float64) @ w.astype(np.float64).T                    # (B, K) in (c,h,w) order
     dpool = dflat.reshape(B, Cc, PH, PW).transpose(0, 2, 3, 1)                # -> (B, PH, PW, C)
     live = (nib >> 2).astype(bool)
@@ -244,3 +244,66 @@ def test_tc_dense_bwd_unpool(B):
     np.testing.assert_allclose(got, ref, rtol=2 ** -7, atol=1e-12)
     assert not got[:, 0].any() and not got[:, -1].any() and not got[:, :, 0].any() and not got[:, :, -1].any()
     np.testing.assert_allclose(dbias.numpy(), np.where(live, dpool, 0.0).sum(axis=(0, 1, 2)), rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------ tcgen05 conv1 (C_in = 1) ----
+@pytest.mark.parametrize("n,integer", [(1, True), (37, True), (300, False)])
+def test_tc_conv1_forward_backward(n, integer):
+    """First conv (1->32, 3x3 same, ReLU) + 2x2 pool on tensor cores via the 4x4-patch formulation, fwd and bwd."""
+    from neuromah_b200._lib import lib
+    from neuromah_b200.device import DeviceArray, stream
+    rng = np.random.default_rng(90 + n)
+    if integer:
+        x = rng.integers(-3, 4, (n, 1, 28, 28)).astype(np.float32)
+        w = rng.integers(-2, 3, (32, 1, 3, 3)).astype(np.float32)
+    else:
+        x = bf16_round(rng.random((n, 1, 28, 28), dtype=np.float32))
+        w = bf16_round((rng.standard_normal((32, 1, 3, 3)) * 0.3).astype(np.float32))
+    s = stream()
+    xd, wd = DeviceArray.from_numpy(x), DeviceArray.from_numpy(w)
+    we = DeviceArray.zeros((128, 16), np.uint16)
+    lib.nm_tc_pack_conv1_weights_bf16(wd.p, we.p, 32, s)
+    y = DeviceArray.zeros((n, 16, 16, 32), np.uint16)
+    idx = DeviceArray.zeros((n, 14, 14, 16), np.uint8)
+    lib.nm_tc_conv1_fwd_pool_bf16(xd.p, we.p, y.p, idx.p, n, 28, 28, 32, s)
+    conv, _ = R.conv_layer_forward(x, w, None, padding="same", relu=True, dtype=np.float64)
+    pooled, pidx = R.maxpool2d_forward_cpu(conv.astype(np.float32), 2, 2, 2, 2, "valid")
+    yn = from_bf16_bits(y.numpy())
+    got = yn[:, 1:-1, 1:-1, :].transpose(0, 3, 1, 2)
+    assert not yn[:, 0].any() and not yn[:, -1].any() and not yn[:, :, 0].any() and not yn[:, :, -1].any()
+    nib = unpack_nibbles(idx.numpy()).transpose(0, 3, 1, 2)
+    exp_pos = (pidx[..., 0] % 2) * 2 + (pidx[..., 1] % 2)
+    if integer:
+        np.testing.assert_array_equal(got, bf16_round(pooled))
+        np.testing.assert_array_equal(nib & 3, exp_pos)
+        np.testing.assert_array_equal(nib >> 2, (pooled > 0).astype(np.uint8))
+    else:
+        np.testing.assert_allclose(got, pooled, rtol=2 ** -7, atol=1e-3)
+        assert np.mean((nib & 3) != exp_pos) < 2e-3                           # near-ties only
+
+    # backward: gradient of the pooled output on the un-shifted grid, routed by the kernel's own nibbles
+    dp = (rng.integers(-2, 3, (n, 32, 14, 14)) if integer else bf16_round(rng.standard_normal((n, 32, 14, 14)))).astype(np.float32)
+    grid = np.zeros((n, 16, 16, 32), np.float32)
+    grid[:, :14, :14, :] = dp.transpose(0, 2, 3, 1)
+    grid[:, 14:, :, :] = 7.0                                                  # don't-care rows/cols must be ignored
+    grid[:, :, 14:, :] = 7.0
+    dw, db = DeviceArray.zeros((32, 1, 3, 3)), DeviceArray.zeros((32, 1))
+    ws = DeviceArray.zeros((lib.nm_tc_conv1_bwd_workspace(32),), np.uint8)
+    gd = DeviceArray.from_numpy(to_bf16_bits(grid))
+    lib.nm_tc_conv1_bwd_bf16(xd.p, gd.p, idx.p, dw.p, db.p, ws.p, ws.nbytes, n, 28, 28, 32, s)
+    pos = nib & 3
+    live = (nib >> 2).astype(bool)
+    dconv = np.zeros((n, 32, 28, 28))
+    for p4 in range(4):
+        dconv[:, :, (p4 >> 1)::2, (p4 & 1)::2] = np.where(live & (pos == p4), dp, 0.0)
+    _, dw_ref, db_ref = R.conv_layer_backward(x, w, None, dconv.astype(np.float32), padding="same", relu=False, mode="wired",
+                                              dtype=np.float64)
+    if integer:
+        np.testing.assert_array_equal(dw.numpy(), dw_ref.astype(np.float32))
+        np.testing.assert_array_equal(db.numpy().ravel(), db_ref.astype(np.float32).ravel())
+    else:
+        np.testing.assert_allclose(dw.numpy(), dw_ref, rtol=1e-4, atol=1e-3 * np.abs(dw_ref).max())
+        np.testing.assert_allclose(db.numpy().ravel(), db_ref.ravel(), rtol=1e-4, atol=1e-3 * np.abs(db_ref).max())
+    dw2 = DeviceArray.zeros((32, 1, 3, 3))                                    # deterministic
+    lib.nm_tc_conv1_bwd_bf16(xd.p, gd.p, idx.p, dw2.p, db.p, ws.p, ws.nbytes, n, 28, 28, 32, s)
+    np.testing.assert_array_equal(dw.numpy(), dw2.numpy())
