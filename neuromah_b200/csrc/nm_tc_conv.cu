@@ -14,6 +14,7 @@
 #include "nm_common.cuh"
 #include "nm_tc_common.cuh"
 #include "nm_tc_host.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -228,7 +229,7 @@ struct WgradTcParams {
     float* partial;                      // [gridDim.x][COUT][9*CIN]
 };
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, bool FOLD>
 __global__ void __launch_bounds__(256, 1)
 conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, WgradTcParams p) {
     static_assert(COUT == 64 && CIN == 32, "instantiated for the MNIST conv2 shape");
@@ -236,6 +237,11 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     constexpr uint64_t TMPL_A = desc_template(16, 8 * A_ROWB, LAYOUT_SW128);   // MN-major: SBO = 8 k-rows
     constexpr uint64_t TMPL_B = desc_template(16, 8 * B_ROWB, LAYOUT_SW64);
     constexpr uint32_t IDESC = idesc_bf16(COUT, CIN, 1, 1);        // M = 64, N = 32, both MN-major
+    // FOLD: the three s-taps of a filter row become three N-chunks of ONE MMA (N = 96): for an MN-major operand
+    // the leading byte offset is the distance between 32-channel chunks, and 64 B is exactly one pixel row, so
+    // chunk j reads the rows shifted by j pixels.  24 MMAs of 48 cycles per k-block instead of 72 of 24.
+    constexpr uint64_t TMPL_B3 = desc_template(B_ROWB, 8 * B_ROWB, LAYOUT_SW64);
+    constexpr uint32_t IDESC3 = idesc_bf16(COUT, 3 * CIN, 1, 1);
     constexpr int A_BYTES = TILE_M * A_ROWB;                        // 16 KB
     constexpr uint32_t TMEM_COLS = 512;                             // 9 * 32 = 288 columns used
 
@@ -284,10 +290,18 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
 #pragma unroll
                 for (int ks = 0; ks < TILE_M / 16; ++ks) {
                     const uint64_t adesc = desc_at(TMPL_A, a_base + ks * 16 * A_ROWB);
+                    if constexpr (FOLD) {
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const uint32_t shift = (uint32_t)((tap / 3) * p.Wp + (tap % 3) + ks * 16) * B_ROWB;
-                        mma_bf16(tmem_base + tap * CIN, adesc, desc_at(TMPL_B, x_base + shift), IDESC, !(first && ks == 0));
+                        for (int r = 0; r < 3; ++r) {
+                            const uint32_t shift = (uint32_t)(r * p.Wp + ks * 16) * B_ROWB;
+                            mma_bf16(tmem_base + r * 3 * CIN, adesc, desc_at(TMPL_B3, x_base + shift), IDESC3, !(first && ks == 0));
+                        }
+                    } else {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint32_t shift = (uint32_t)((tap / 3) * p.Wp + (tap % 3) + ks * 16) * B_ROWB;
+                            mma_bf16(tmem_base + tap * CIN, adesc, desc_at(TMPL_B, x_base + shift), IDESC, !(first && ks == 0));
+                        }
                     }
                 }
                 mma_commit(&empty[stage]);
@@ -456,13 +470,16 @@ int nm_tc_conv3x3_wgrad_bf16(const void* x_pad, const void* dy_pad, float* dw, v
     rc = make_map_2d(&mx, x_pad, 32, (uint64_t)p.rows_total, 64, 32, (uint32_t)p.x_rows, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
     size_t smem = (size_t)p.n_stages * (TILE_M * 128 + p.x_stage_bytes) + 256;
-    auto kern = conv3x3_wgrad_tc_kernel<32, 64>;
+    static int fold = -1;
+    if (fold < 0) { const char* e = getenv("NM_TC_WGRAD_FOLD"); fold = e ? atoi(e) : 1; }
     static bool attr_set = false;
     if (!attr_set) {
-        NM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        NM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<32, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        NM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<32, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    kern<<<grid, 256, smem, nm::S(stream)>>>(mdy, mx, p);
+    if (fold) conv3x3_wgrad_tc_kernel<32, 64, true><<<grid, 256, smem, nm::S(stream)>>>(mdy, mx, p);
+    else conv3x3_wgrad_tc_kernel<32, 64, false><<<grid, 256, smem, nm::S(stream)>>>(mdy, mx, p);
     rc = nm::launched("conv3x3_wgrad_tc");
     if (rc) return rc;
     int total = OC * 9 * C;

@@ -38,23 +38,30 @@ __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t byte) { const u
 
 struct Conv1Geom { int N, H, W, PH, PW, PHW; long long total; int num_tiles; };
 
-// the 4x4 input patch of pool window g (zero outside the image: the 'same' padding of Conv_wrapepr.py:78-84)
-__device__ __forceinline__ void load_patch(const float* __restrict__ x, const Conv1Geom& G, long long g, float p[16]) {
-    if (g < G.total) {
-        const int n = (int)(g / G.PHW), w = (int)(g - (long long)n * G.PHW), py = w / G.PW, px = w - py * G.PW;
-        const float* img = x + (size_t)n * G.H * G.W;
+// Images [n0, n1] touched by the 128 windows of a tile; the bulk-copy producer stages them (contiguous in x).
+struct TileSpan { long long g0, g1; int n0, n1; };
+__device__ __forceinline__ TileSpan tile_span(const Conv1Geom& G, int tile) {
+    TileSpan t;
+    t.g0 = (long long)tile * 128;
+    t.g1 = t.g0 + 127 < G.total - 1 ? t.g0 + 127 : G.total - 1;
+    t.n0 = (int)(t.g0 / G.PHW);
+    t.n1 = (int)(t.g1 / G.PHW);
+    return t;
+}
+
+// the 4x4 input patch of pool window (n, py, px) from the staged images (zero outside the image: the 'same'
+// padding of Conv_wrapepr.py:78-84)
+__device__ __forceinline__ void load_patch(const float* __restrict__ xs, const Conv1Geom& G, bool valid, int n_local, int py, int px,
+                                           float p[16]) {
+    const float* img = xs + n_local * G.H * G.W;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int yy = 2 * py - 1 + a;
+    for (int a = 0; a < 4; ++a) {
+        const int yy = 2 * py - 1 + a;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int xx = 2 * px - 1 + b;
-                p[a * 4 + b] = ((unsigned)yy < (unsigned)G.H && (unsigned)xx < (unsigned)G.W) ? __ldg(img + yy * G.W + xx) : 0.f;
-            }
+        for (int b = 0; b < 4; ++b) {
+            const int xx = 2 * px - 1 + b;
+            p[a * 4 + b] = (valid && (unsigned)yy < (unsigned)G.H && (unsigned)xx < (unsigned)G.W) ? img[yy * G.W + xx] : 0.f;
         }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) p[i] = 0.f;
     }
 }
 
@@ -62,19 +69,24 @@ __device__ __forceinline__ void load_patch(const float* __restrict__ x, const Co
 // forward
 // ---------------------------------------------------------------------------------------------
 constexpr int F_TILE_BYTES = 128 * 64;          // 128 rows x 64 B (K = 16 bf16 used, SWIZZLE_64B)
-constexpr int F_STAGES = 3;
+constexpr int F_STAGES = 3;                     // A-tile ring (builders -> MMA)
+constexpr int F_XSTAGES = 6;                    // staged-image ring (bulk-copy producer -> builders): hides the HBM latency
+constexpr int F_THREADS = 448;                  // warps 0-3 builders, 4 MMA, 5-12 epilogue (2 groups), 13 bulk-copy producer
 
-__global__ void __launch_bounds__(416, 1)
+__global__ void __launch_bounds__(F_THREADS, 1)
 conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ wext, __nv_bfloat16* __restrict__ y_pad,
-                    uint8_t* __restrict__ idx, Conv1Geom G) {
+                    uint8_t* __restrict__ idx, Conv1Geom G, int x_stage_bytes) {
     constexpr uint64_t TMPL = desc_template(16, 512, LAYOUT_SW64);
     constexpr uint32_t IDESC = idesc_bf16(128, 128, 0, 0);
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* b_smem = smem;
     uint8_t* a_smem = smem + F_TILE_BYTES;
-    uint64_t* afull = reinterpret_cast<uint64_t*>(a_smem + F_STAGES * F_TILE_BYTES);
+    uint8_t* x_smem = a_smem + F_STAGES * F_TILE_BYTES;
+    uint64_t* afull = reinterpret_cast<uint64_t*>(x_smem + (size_t)F_XSTAGES * x_stage_bytes);
     uint64_t* aempty = afull + F_STAGES;
-    uint64_t* tfull = aempty + F_STAGES;
+    uint64_t* xfull = aempty + F_STAGES;
+    uint64_t* xempty = xfull + F_XSTAGES;
+    uint64_t* tfull = xempty + F_XSTAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -87,6 +99,7 @@ conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
     fence_proxy_async();
     if (threadIdx.x == 0) {
         for (int s = 0; s < F_STAGES; ++s) { mbar_init(&afull[s], 128); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < F_XSTAGES; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 128); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
         mbar_fence_init();
     }
@@ -96,27 +109,43 @@ conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp == 13) {
+        // ============================== bulk-copy producer: the images a tile touches =========
+        if (lane == 0) {
+            int xs = 0; uint32_t xphase = 0;
+            for (int tile = blockIdx.x; tile < G.num_tiles; tile += gridDim.x) {
+                const TileSpan t = tile_span(G, tile);
+                const uint32_t bytes = (uint32_t)(t.n1 - t.n0 + 1) * G.H * G.W * 4u;
+                mbar_wait(&xempty[xs], xphase ^ 1);
+                mbar_expect_tx(&xfull[xs], bytes);
+                bulk_load(x_smem + (size_t)xs * x_stage_bytes, x + (size_t)t.n0 * G.H * G.W, bytes, &xfull[xs]);
+                if (++xs == F_XSTAGES) { xs = 0; xphase ^= 1; }
+            }
+        }
+    } else if (warp < 4) {
         // ============================== builders: one pool window per thread =================
         const int row = threadIdx.x;
-        float cur[16], nxt[16];
-        int tile = blockIdx.x;
-        load_patch(x, G, (long long)tile * 128 + row, cur);
-        int stage = 0; uint32_t phase = 0;
-        for (; tile < G.num_tiles; tile += gridDim.x) {
-            const int ntile = tile + gridDim.x;
-            if (ntile < G.num_tiles) load_patch(x, G, (long long)ntile * 128 + row, nxt);   // in flight during the stores below
+        int stage = 0; uint32_t phase = 0; int xs = 0; uint32_t xphase = 0;
+        for (int tile = blockIdx.x; tile < G.num_tiles; tile += gridDim.x) {
+            const TileSpan t = tile_span(G, tile);
+            const long long g = t.g0 + row;
+            const bool valid = g < G.total;
+            int n = t.n0, py = 0, px = 0;
+            if (valid) { n = (int)(g / G.PHW); const int w = (int)(g - (long long)n * G.PHW); py = w / G.PW; px = w - py * G.PW; }
+            float p[16];
+            mbar_wait(&xfull[xs], xphase);
+            load_patch(reinterpret_cast<const float*>(x_smem + (size_t)xs * x_stage_bytes), G, valid, n - t.n0, py, px, p);
+            mbar_arrive(&xempty[xs]);                         // the patch is in registers: the image slot may be refilled
             mbar_wait(&aempty[stage], phase ^ 1);
             uint8_t* at = a_smem + stage * F_TILE_BYTES;
-            *reinterpret_cast<uint4*>(at + sw64(row, 0)) = make_uint4(pack_bf16x2(cur[0], cur[1]), pack_bf16x2(cur[2], cur[3]),
-                                                                       pack_bf16x2(cur[4], cur[5]), pack_bf16x2(cur[6], cur[7]));
-            *reinterpret_cast<uint4*>(at + sw64(row, 16)) = make_uint4(pack_bf16x2(cur[8], cur[9]), pack_bf16x2(cur[10], cur[11]),
-                                                                        pack_bf16x2(cur[12], cur[13]), pack_bf16x2(cur[14], cur[15]));
+            *reinterpret_cast<uint4*>(at + sw64(row, 0)) = make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]),
+                                                                       pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+            *reinterpret_cast<uint4*>(at + sw64(row, 16)) = make_uint4(pack_bf16x2(p[8], p[9]), pack_bf16x2(p[10], p[11]),
+                                                                        pack_bf16x2(p[12], p[13]), pack_bf16x2(p[14], p[15]));
             fence_proxy_async();
             mbar_arrive(&afull[stage]);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
             if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+            if (++xs == F_XSTAGES) { xs = 0; xphase ^= 1; }
         }
     } else if (warp == 4) {
         // ============================== MMA issuer ===========================================
@@ -140,13 +169,13 @@ conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
         const int grp = (warp - 5) >> 2, q = warp & 3;                     // q = TMEM sub-partition of this warp
         int it = grp;
         for (int tile = blockIdx.x + grp * gridDim.x; tile < G.num_tiles; tile += 2 * gridDim.x, it += 2) {
-            mbar_wait(&tfull[grp], (it >> 1) & 1);
-            fence_after_sync();
             const long long g = (long long)tile * 128 + q * 32 + lane;
             const bool valid = g < G.total;
             int n = 0, py = 0, px = 0, w = 0;
             if (valid) { n = (int)(g / G.PHW); w = (int)(g - (long long)n * G.PHW); py = w / G.PW; px = w - py * G.PW; }
             __nv_bfloat16* yo = y_pad + (((size_t)n * (G.PH + 2) + py + 1) * (G.PW + 2) + px + 1) * OC;
+            mbar_wait(&tfull[grp], (it >> 1) & 1);
+            fence_after_sync();
             uint32_t nibw[4];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -210,21 +239,30 @@ __global__ void pack_conv1_weights_kernel(const float* __restrict__ w, __nv_bflo
 constexpr int B_G_BYTES = 2 * 128 * 128;        // G: two SW128 column blocks [(pos>>1)] of [128 windows][64 (pos&1, oc)] bf16
 constexpr int B_P_BYTES = 128 * 64;             // P: [128 windows][32 = 16 patch + 1 ones + 15 zero] bf16, SW64
 constexpr int B_STAGE = B_G_BYTES + B_P_BYTES;  // 40 KB
-constexpr int B_STAGES = 3;
+constexpr int B_STAGES = 2;                     // operand ring (builders -> MMA)
+constexpr int B_LSTAGES = 4;                    // staged-input ring (bulk-copy producer -> builders)
+constexpr int B_IDX_BYTES = 128 * (OC / 2);     // 2 KB of nibbles per tile
 constexpr int B_MAX_GRID = 148;
+constexpr int B_THREADS = 320;                  // warps 0-7 builders (0-3 also the epilogue), 8 MMA, 9 bulk-copy producer
 
-__global__ void __launch_bounds__(288, 1)
+struct Conv1BwdSmem { int x_bytes, dp_bytes, lstage_bytes; };   // per load stage: [x images | dp rows | nibbles]
+
+__global__ void __launch_bounds__(B_THREADS, 1)
 conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dp_grid, const uint8_t* __restrict__ idx,
-                    float* __restrict__ partial, Conv1Geom G) {
+                    float* __restrict__ partial, Conv1Geom G, Conv1BwdSmem L) {
     constexpr uint64_t TMPL_A = desc_template(16, 1024, LAYOUT_SW128);     // MN-major: SBO = 8 k-rows of 128 B
     constexpr uint64_t TMPL_B = desc_template(16, 512, LAYOUT_SW64);       //           SBO = 8 k-rows of 64 B
     constexpr uint32_t IDESC = idesc_bf16(64, 32, 1, 1);
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* afull = reinterpret_cast<uint64_t*>(smem + B_STAGES * B_STAGE);
+    uint8_t* l_smem = smem + B_STAGES * B_STAGE;
+    uint64_t* afull = reinterpret_cast<uint64_t*>(l_smem + (size_t)B_LSTAGES * L.lstage_bytes);
     uint64_t* aempty = afull + B_STAGES;
-    uint64_t* done = aempty + B_STAGES;
+    uint64_t* lfull = aempty + B_STAGES;
+    uint64_t* lempty = lfull + B_LSTAGES;
+    uint64_t* done = lempty + B_LSTAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row_bytes = (G.PW + 2) * OC * 2;                              // one row of the dP grid
 
     // constant half of every P row: column 16 = 1 (bias gradient), columns 17..31 = 0
     for (int i = threadIdx.x; i < B_STAGES * 128; i += blockDim.x) {
@@ -236,6 +274,7 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
     fence_proxy_async();
     if (threadIdx.x == 0) {
         for (int s = 0; s < B_STAGES; ++s) { mbar_init(&afull[s], 256); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < B_LSTAGES; ++s) { mbar_init(&lfull[s], 1); mbar_init(&lempty[s], 256); }
         mbar_init(done, 1);
         mbar_fence_init();
     }
@@ -246,31 +285,51 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
     const uint32_t tmem_base = *tmem_slot;
     const bool has_work = (int)blockIdx.x < G.num_tiles;
 
-    if (warp < 8) {
+    if (warp == 9) {
+        // ============================== bulk-copy producer ===================================
+        // per tile: the images it touches (contiguous in x), the dP grid rows from its first to its last window
+        // (contiguous, incl. the don't-care halo rows when the tile crosses an image boundary) and its 2 KB of nibbles
+        if (lane == 0) {
+            int ls = 0; uint32_t lphase = 0;
+            for (int tile = blockIdx.x; tile < G.num_tiles; tile += gridDim.x) {
+                const TileSpan t = tile_span(G, tile);
+                const int w0 = (int)(t.g0 - (long long)t.n0 * G.PHW), w1 = (int)(t.g1 - (long long)t.n1 * G.PHW);
+                const int r0 = t.n0 * (G.PH + 2) + w0 / G.PW, r1 = t.n1 * (G.PH + 2) + w1 / G.PW;
+                const uint32_t xb = (uint32_t)(t.n1 - t.n0 + 1) * G.H * G.W * 4u;
+                const uint32_t db = (uint32_t)(r1 - r0 + 1) * row_bytes;
+                const uint32_t ib = (uint32_t)(t.g1 - t.g0 + 1) * (OC / 2);
+                uint8_t* st = l_smem + (size_t)ls * L.lstage_bytes;
+                mbar_wait(&lempty[ls], lphase ^ 1);
+                mbar_expect_tx(&lfull[ls], xb + db + ib);
+                bulk_load(st, x + (size_t)t.n0 * G.H * G.W, xb, &lfull[ls]);
+                bulk_load(st + L.x_bytes, reinterpret_cast<const uint8_t*>(dp_grid) + (size_t)r0 * row_bytes, db, &lfull[ls]);
+                bulk_load(st + L.x_bytes + L.dp_bytes, idx + (size_t)t.g0 * (OC / 2), ib, &lfull[ls]);
+                if (++ls == B_LSTAGES) { ls = 0; lphase ^= 1; }
+            }
+        }
+    } else if (warp < 8) {
         // ============================== builders: (window, half of the channels) per thread ==
         const int row = threadIdx.x & 127, hh = threadIdx.x >> 7;
-        uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0, nd0 = d0, nd1 = d0;
-        uint2 nb = make_uint2(0, 0), nnb = nb;
-        float cur[16], nxt[16];
-        auto fetch = [&](int tile, uint4& a0, uint4& a1, uint2& nn, float p[16]) {
-            const long long g = (long long)tile * 128 + row;
-            a0 = make_uint4(0, 0, 0, 0); a1 = a0; nn = make_uint2(0, 0);
-            if (g < G.total) {
-                const int n = (int)(g / G.PHW), w = (int)(g - (long long)n * G.PHW), py = w / G.PW, px = w - py * G.PW;
-                const uint4* src = reinterpret_cast<const uint4*>(dp_grid + (((size_t)n * (G.PH + 2) + py) * (G.PW + 2) + px) * OC + hh * 16);
-                a0 = __ldg(src); a1 = __ldg(src + 1);
-                nn = __ldg(reinterpret_cast<const uint2*>(idx + ((size_t)n * G.PHW + w) * (OC / 2) + hh * 8));
+        int stage = 0; uint32_t phase = 0; int ls = 0; uint32_t lphase = 0;
+        for (int tile = blockIdx.x; tile < G.num_tiles; tile += gridDim.x) {
+            const TileSpan t = tile_span(G, tile);
+            const long long g = t.g0 + row;
+            const bool valid = g < G.total;
+            int n = t.n0, py = 0, px = 0;
+            if (valid) { n = (int)(g / G.PHW); const int w = (int)(g - (long long)n * G.PHW); py = w / G.PW; px = w - py * G.PW; }
+            const int w0 = (int)(t.g0 - (long long)t.n0 * G.PHW), r0 = t.n0 * (G.PH + 2) + w0 / G.PW;
+            const uint8_t* st = l_smem + (size_t)ls * L.lstage_bytes;
+            uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+            uint2 nb = make_uint2(0, 0);
+            float p[16];
+            mbar_wait(&lfull[ls], lphase);
+            if (valid) {
+                const uint4* src = reinterpret_cast<const uint4*>(st + L.x_bytes + (size_t)(n * (G.PH + 2) + py - r0) * row_bytes + px * (OC * 2) + hh * 32);
+                d0 = src[0]; d1 = src[1];
+                nb = *reinterpret_cast<const uint2*>(st + L.x_bytes + L.dp_bytes + row * (OC / 2) + hh * 8);
             }
-            if (hh == 0) load_patch(x, G, g, p);
-        };
-        int tile = blockIdx.x;
-        if (has_work) fetch(tile, d0, d1, nb, cur);
-        int stage = 0; uint32_t phase = 0;
-        for (; tile < G.num_tiles; tile += gridDim.x) {
-            const int ntile = tile + gridDim.x;
-            if (ntile < G.num_tiles) fetch(ntile, nd0, nd1, nnb, nxt);
-            mbar_wait(&aempty[stage], phase ^ 1);
-            uint8_t* gt = smem + stage * B_STAGE;
+            if (hh == 0) load_patch(reinterpret_cast<const float*>(st), G, valid, n - t.n0, py, px, p);
+            mbar_arrive(&lempty[ls]);                         // everything is in registers: the slot may be refilled
             const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};   // 16 channels as bf16 pairs
             uint32_t out[4][8];
 #pragma unroll
@@ -282,6 +341,8 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
                 for (int pos = 0; pos < 4; ++pos)
                     out[pos][j] = (n0 == (4u | pos) ? lo : 0u) | (n1 == (4u | pos) ? hi : 0u);   // arg-max routing + ReLU mask
             }
+            mbar_wait(&aempty[stage], phase ^ 1);
+            uint8_t* gt = smem + stage * B_STAGE;
 #pragma unroll
             for (int pos = 0; pos < 4; ++pos) {
                 uint8_t* blk = gt + (pos >> 1) * (128 * 128);
@@ -291,17 +352,15 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
             }
             if (hh == 0) {
                 uint8_t* pt = gt + B_G_BYTES;
-                *reinterpret_cast<uint4*>(pt + sw64(row, 0)) = make_uint4(pack_bf16x2(cur[0], cur[1]), pack_bf16x2(cur[2], cur[3]),
-                                                                           pack_bf16x2(cur[4], cur[5]), pack_bf16x2(cur[6], cur[7]));
-                *reinterpret_cast<uint4*>(pt + sw64(row, 16)) = make_uint4(pack_bf16x2(cur[8], cur[9]), pack_bf16x2(cur[10], cur[11]),
-                                                                            pack_bf16x2(cur[12], cur[13]), pack_bf16x2(cur[14], cur[15]));
+                *reinterpret_cast<uint4*>(pt + sw64(row, 0)) = make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]),
+                                                                           pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+                *reinterpret_cast<uint4*>(pt + sw64(row, 16)) = make_uint4(pack_bf16x2(p[8], p[9]), pack_bf16x2(p[10], p[11]),
+                                                                            pack_bf16x2(p[12], p[13]), pack_bf16x2(p[14], p[15]));
             }
             fence_proxy_async();
             mbar_arrive(&afull[stage]);
-            d0 = nd0; d1 = nd1; nb = nnb;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
             if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+            if (++ls == B_LSTAGES) { ls = 0; lphase ^= 1; }
         }
         // ============================== epilogue: E -> one FP32 partial per CTA ==============
         if (warp < 4) {
@@ -412,12 +471,15 @@ int nm_tc_conv1_fwd_pool_bf16(const float* x, const void* w_ext, void* y_pad, vo
     NM_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "bad dimensions");
     if (OCn != OC) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_fwd_pool_bf16: only OC=32 is instantiated");
     Conv1Geom g; geom(&g, N, H, W);
-    const size_t smem = (size_t)(1 + F_STAGES) * F_TILE_BYTES + 256;
+    NM_REQUIRE(g.PHW >= 128, "image too small: a 128-window tile must touch at most two images");
+    const int x_stage = (2 * H * W * 4 + 127) & ~127;
+    const size_t smem = (size_t)(1 + F_STAGES) * F_TILE_BYTES + (size_t)F_XSTAGES * x_stage + 256;
+    if (smem > 200 * 1024) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_fwd_pool_bf16: image too large for the staged-image ring");
     static bool attr = false;
-    if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv1_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+    if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv1_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
     const int grid = g.num_tiles < sm_count() ? g.num_tiles : sm_count();
-    conv1_tc_fwd_kernel<<<grid, 416, smem, nm::S(stream)>>>(x, static_cast<const __nv_bfloat16*>(w_ext), static_cast<__nv_bfloat16*>(y_pad),
-                                                           static_cast<uint8_t*>(idx), g);
+    conv1_tc_fwd_kernel<<<grid, F_THREADS, smem, nm::S(stream)>>>(x, static_cast<const __nv_bfloat16*>(w_ext), static_cast<__nv_bfloat16*>(y_pad),
+                                                                 static_cast<uint8_t*>(idx), g, x_stage);
     return nm::launched("conv1_tc_fwd");
 }
 
@@ -432,11 +494,18 @@ int nm_tc_conv1_bwd_bf16(const float* x, const void* dp_grid, const void* idx, f
     int grid = sm_count() < B_MAX_GRID ? sm_count() : B_MAX_GRID;
     if (g.num_tiles < grid) grid = g.num_tiles;
     NM_REQUIRE(workspace_bytes >= (size_t)grid * 128 * 32 * sizeof(float), "workspace too small");
-    const size_t smem = (size_t)B_STAGES * B_STAGE + 256;
+    NM_REQUIRE(g.PHW >= 128, "image too small: a 128-window tile must touch at most two images");
+    Conv1BwdSmem L;
+    L.x_bytes = (2 * H * W * 4 + 127) & ~127;
+    const int max_rows = (128 + g.PW - 1) / g.PW + 1 + 2;          // pooled rows a tile can span + the 2 halo rows at an image boundary
+    L.dp_bytes = max_rows * (g.PW + 2) * OC * 2;
+    L.lstage_bytes = L.x_bytes + L.dp_bytes + B_IDX_BYTES;
+    const size_t smem = (size_t)B_STAGES * B_STAGE + (size_t)B_LSTAGES * L.lstage_bytes + 256;
+    if (smem > 220 * 1024) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_bwd_bf16: image too large for the staged-input ring");
     static bool attr = false;
-    if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv1_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
-    conv1_tc_bwd_kernel<<<grid, 288, smem, nm::S(stream)>>>(x, static_cast<const __nv_bfloat16*>(dp_grid), static_cast<const uint8_t*>(idx),
-                                                           static_cast<float*>(workspace), g);
+    if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv1_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
+    conv1_tc_bwd_kernel<<<grid, B_THREADS, smem, nm::S(stream)>>>(x, static_cast<const __nv_bfloat16*>(dp_grid), static_cast<const uint8_t*>(idx),
+                                                                 static_cast<float*>(workspace), g, L);
     int rc = nm::launched("conv1_tc_bwd");
     if (rc) return rc;
     conv1_tc_bwd_reduce_kernel<<<nm_cdiv(OC * 10, 32), 256, 0, nm::S(stream)>>>(static_cast<const float*>(workspace), dw, db, grid);
