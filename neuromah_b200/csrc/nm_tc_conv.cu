@@ -36,7 +36,13 @@ struct ConvTcParams {
 // ---------------------------------------------------------------------------------------------
 // fprop / dgrad:  D[128 pixels, NOUT] = sum_{tap} A[pixel + shift(tap), 0:CIN] * B[tap][NOUT, CIN]^T
 // ---------------------------------------------------------------------------------------------
-template <int CIN, int NOUT, int EPI>
+// FOLD (needs Wp == 16, plain-store epilogue): the three s-taps of a filter row are three N-chunks of ONE MMA
+// (N = 3*NOUT, the B blocks of taps 3r..3r+2 are contiguous rows), all reading the A rows shifted by r*Wp only;
+// the s-shift is applied to the accumulator instead: out[p] = E[p][0] + E[p+1][1] + E[p+2][2], two warp shuffles
+// per value (a warp holds two complete 16-pixel grid rows and the last two pixels of a row are halo, so the shift
+// never crosses a warp).  The MMA is bound by the 128 B/cycle read of its 4 KB A slice, so tripling N is free:
+// 12 MMAs of 56 cycles per tile instead of 36 of 45 (profiles/r01_mma_rate.txt).
+template <int CIN, int NOUT, int EPI, bool FOLD>
 __global__ void __launch_bounds__(256, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvTcParams p) {
     constexpr int ROWB = CIN * 2;                                   // bytes per pixel row: 64 (SW64) or 128 (SW128)
@@ -47,8 +53,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     constexpr int B_TAP_BYTES = NOUT * ROWB;
     constexpr int B_BYTES = 9 * B_TAP_BYTES;
     static_assert(B_BYTES % 1024 == 0, "weight block must keep the A stages 1024-aligned");
-    constexpr uint32_t TMEM_COLS = 2 * NOUT < 32 ? 32 : 2 * NOUT;   // two accumulators; 64 or 128: powers of two
-    constexpr uint32_t IDESC = idesc_bf16(TILE_M, NOUT, 0, 0);
+    static_assert(!FOLD || EPI == 0, "tap folding is implemented for the plain-store epilogue");
+    constexpr int NACC = FOLD ? 3 * NOUT : NOUT;                    // accumulator columns per buffer
+    constexpr uint32_t TMEM_COLS = 2 * NACC <= 32 ? 32 : 2 * NACC <= 64 ? 64 : 2 * NACC <= 128 ? 128 : 2 * NACC <= 256 ? 256 : 512;
+    constexpr uint32_t IDESC = idesc_bf16(TILE_M, NACC, 0, 0);
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* b_smem = smem;
@@ -102,14 +110,25 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             fence_after_sync();
             if (elect_one()) {
                 const uint32_t a_base = smem_u32(a_smem + (size_t)stage * p.a_stage_bytes);
-                const uint32_t d_addr = tmem_base + acc * NOUT;
+                const uint32_t d_addr = tmem_base + acc * NACC;
+                if constexpr (FOLD) {
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
-                    const uint32_t shift = (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * ROWB;
+                    for (int r = 0; r < 3; ++r) {
+                        const uint32_t shift = (uint32_t)(r * p.Wp) * ROWB;
 #pragma unroll
-                    for (int kk = 0; kk < KSTEPS; ++kk)
-                        mma_bf16(d_addr, desc_at(TMPL, a_base + shift + kk * 32),
-                                 desc_at(TMPL, b_base + tap * B_TAP_BYTES + kk * 32), IDESC, (tap | kk) != 0);
+                        for (int kk = 0; kk < KSTEPS; ++kk)
+                            mma_bf16(d_addr, desc_at(TMPL, a_base + shift + kk * 32),
+                                     desc_at(TMPL, b_base + 3 * r * B_TAP_BYTES + kk * 32), IDESC, (r | kk) != 0);
+                    }
+                } else {
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t shift = (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * ROWB;
+#pragma unroll
+                        for (int kk = 0; kk < KSTEPS; ++kk)
+                            mma_bf16(d_addr, desc_at(TMPL, a_base + shift + kk * 32),
+                                     desc_at(TMPL, b_base + tap * B_TAP_BYTES + kk * 32), IDESC, (tap | kk) != 0);
+                    }
                 }
                 mma_commit(&empty[stage]);          // A stage reusable once these MMAs have read it
                 mma_commit(&tfull[acc]);            // accumulator ready for the epilogue
@@ -125,14 +144,33 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             mbar_wait(&tfull[acc], acc_phase);
             fence_after_sync();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NOUT;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NACC;
             uint32_t raw[NOUT];
+            if constexpr (FOLD) {
+                uint32_t e1[NOUT], e2[NOUT];
 #pragma unroll
-            for (int c = 0; c < NOUT; c += 16) tmem_ld_x16(taddr + c, raw + c);
-            tmem_ld_wait();
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator drained: MMA may overwrite it
+                for (int c = 0; c < NOUT; c += 16) {
+                    tmem_ld_x16(taddr + c, raw + c);
+                    tmem_ld_x16(taddr + NOUT + c, e1 + c);
+                    tmem_ld_x16(taddr + 2 * NOUT + c, e2 + c);
+                }
+                tmem_ld_wait();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+#pragma unroll
+                for (int c = 0; c < NOUT; ++c)
+                    raw[c] = __float_as_uint(__uint_as_float(raw[c]) +
+                                             (__uint_as_float(__shfl_down_sync(0xffffffffu, e1[c], 1)) +
+                                              __uint_as_float(__shfl_down_sync(0xffffffffu, e2[c], 2))));
+            } else {
+#pragma unroll
+                for (int c = 0; c < NOUT; c += 16) tmem_ld_x16(taddr + c, raw + c);
+                tmem_ld_wait();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator drained: MMA may overwrite it
+            }
             acc ^= 1; if (acc == 0) acc_phase ^= 1;
 
             if constexpr (EPI == 0) {
@@ -375,7 +413,7 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, __nv_bfloa
     if (wd) wd[((size_t)c * 9 + (8 - tap)) * OC + oc] = v;
 }
 
-template <int CIN, int NOUT, int EPI>
+template <int CIN, int NOUT, int EPI, bool FOLD>
 int launch_conv(const void* a, const void* b, ConvTcParams p, int N, cudaStream_t st) {
     constexpr int ROWB = CIN * 2;
     CUtensorMap ma, mb;
@@ -387,7 +425,7 @@ int launch_conv(const void* a, const void* b, ConvTcParams p, int N, cudaStream_
     p.a_stage_bytes = ((uint32_t)p.a_rows * ROWB + 1023u) & ~1023u;
     p.n_stages = 6;
     size_t smem = 9 * NOUT * ROWB + (size_t)p.n_stages * p.a_stage_bytes + 256;
-    auto kern = conv3x3_tc_kernel<CIN, NOUT, EPI>;
+    auto kern = conv3x3_tc_kernel<CIN, NOUT, EPI, FOLD>;
     static bool attr_set = false;
     if (!attr_set) {
         NM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -424,7 +462,7 @@ int nm_tc_conv3x3_fprop_pool_bf16(const void* x_pad, const void* w_packed, void*
     p.a_rows = TILE_M + 2 * p.Wp + 2;
     p.out = y; p.idx = static_cast<uint8_t*>(idx);
     p.oHp = out_padded ? H / 2 + 2 : H / 2; p.oWp = out_padded ? W / 2 + 2 : W / 2; p.ooff = out_padded ? 1 : 0;
-    return launch_conv<32, 64, 1>(x_pad, w_packed, p, N, nm::S(stream));
+    return launch_conv<32, 64, 1, false>(x_pad, w_packed, p, N, nm::S(stream));
 }
 
 int nm_tc_conv3x3_dgrad_bf16(const void* dy_pad, const void* w_packed_dgrad, void* dx_grid,
@@ -440,7 +478,10 @@ int nm_tc_conv3x3_dgrad_bf16(const void* dy_pad, const void* w_packed_dgrad, voi
     p.num_tiles = (p.rows_total + TILE_M - 1) / TILE_M;
     p.a_rows = TILE_M + 2 * p.Wp + 2;
     p.out = dx_grid;
-    return launch_conv<64, 32, 0>(dy_pad, w_packed_dgrad, p, N, nm::S(stream));
+    static int fold = -1;
+    if (fold < 0) { const char* e = getenv("NM_TC_DGRAD_FOLD"); fold = e ? atoi(e) : 1; }
+    if (fold && p.Wp == 16) return launch_conv<64, 32, 0, true>(dy_pad, w_packed_dgrad, p, N, nm::S(stream));
+    return launch_conv<64, 32, 0, false>(dy_pad, w_packed_dgrad, p, N, nm::S(stream));
 }
 
 size_t nm_tc_conv3x3_wgrad_workspace(int C, int OC) {

@@ -36,16 +36,16 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ uint32_t sw64(uint32_t row, uint32_t byte) { const uint32_t o = row * 64 + byte; return o ^ (((o >> 7) & 3) << 4); }
 __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t byte) { const uint32_t o = row * 128 + byte; return o ^ (((o >> 7) & 7) << 4); }
 
-struct Conv1Geom { int N, H, W, PH, PW, PHW; long long total; int num_tiles; };
+struct Conv1Geom { int N, H, W, PH, PW, PHW; unsigned total; int num_tiles; };   // total pool windows < 2^31
 
 // Images [n0, n1] touched by the 128 windows of a tile; the bulk-copy producer stages them (contiguous in x).
-struct TileSpan { long long g0, g1; int n0, n1; };
+struct TileSpan { unsigned g0, g1; int n0, n1; };
 __device__ __forceinline__ TileSpan tile_span(const Conv1Geom& G, int tile) {
     TileSpan t;
-    t.g0 = (long long)tile * 128;
-    t.g1 = t.g0 + 127 < G.total - 1 ? t.g0 + 127 : G.total - 1;
-    t.n0 = (int)(t.g0 / G.PHW);
-    t.n1 = (int)(t.g1 / G.PHW);
+    t.g0 = (unsigned)tile * 128u;
+    t.g1 = min(t.g0 + 127u, G.total - 1u);
+    t.n0 = (int)(t.g0 / (unsigned)G.PHW);
+    t.n1 = t.n0 + ((t.g1 - (unsigned)t.n0 * G.PHW) >= (unsigned)G.PHW ? 1 : 0);     // a tile touches at most two images
     return t;
 }
 
@@ -128,10 +128,14 @@ conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
         int stage = 0; uint32_t phase = 0; int xs = 0; uint32_t xphase = 0;
         for (int tile = blockIdx.x; tile < G.num_tiles; tile += gridDim.x) {
             const TileSpan t = tile_span(G, tile);
-            const long long g = t.g0 + row;
+            const unsigned g = t.g0 + row;
             const bool valid = g < G.total;
             int n = t.n0, py = 0, px = 0;
-            if (valid) { n = (int)(g / G.PHW); const int w = (int)(g - (long long)n * G.PHW); py = w / G.PW; px = w - py * G.PW; }
+            if (valid) {
+                unsigned w = g - (unsigned)t.n0 * G.PHW;
+                if (w >= (unsigned)G.PHW) { w -= G.PHW; ++n; }
+                py = (int)(w / (unsigned)G.PW); px = (int)w - py * G.PW;
+            }
             float p[16];
             mbar_wait(&xfull[xs], xphase);
             load_patch(reinterpret_cast<const float*>(x_smem + (size_t)xs * x_stage_bytes), G, valid, n - t.n0, py, px, p);
@@ -169,10 +173,10 @@ conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
         const int grp = (warp - 5) >> 2, q = warp & 3;                     // q = TMEM sub-partition of this warp
         int it = grp;
         for (int tile = blockIdx.x + grp * gridDim.x; tile < G.num_tiles; tile += 2 * gridDim.x, it += 2) {
-            const long long g = (long long)tile * 128 + q * 32 + lane;
+            const unsigned g = (unsigned)tile * 128u + q * 32 + lane;
             const bool valid = g < G.total;
             int n = 0, py = 0, px = 0, w = 0;
-            if (valid) { n = (int)(g / G.PHW); w = (int)(g - (long long)n * G.PHW); py = w / G.PW; px = w - py * G.PW; }
+            if (valid) { n = (int)(g / (unsigned)G.PHW); w = (int)(g - (unsigned)n * G.PHW); py = w / G.PW; px = w - py * G.PW; }
             __nv_bfloat16* yo = y_pad + (((size_t)n * (G.PH + 2) + py + 1) * (G.PW + 2) + px + 1) * OC;
             mbar_wait(&tfull[grp], (it >> 1) & 1);
             fence_after_sync();
@@ -255,7 +259,8 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
     constexpr uint32_t IDESC = idesc_bf16(64, 32, 1, 1);
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* l_smem = smem + B_STAGES * B_STAGE;
-    uint64_t* afull = reinterpret_cast<uint64_t*>(l_smem + (size_t)B_LSTAGES * L.lstage_bytes);
+    uint4* lut = reinterpret_cast<uint4*>(l_smem + (size_t)B_LSTAGES * L.lstage_bytes);     // 256 x 4 PRMT selectors
+    uint64_t* afull = reinterpret_cast<uint64_t*>(lut + 256);
     uint64_t* aempty = afull + B_STAGES;
     uint64_t* lfull = aempty + B_STAGES;
     uint64_t* lempty = lfull + B_LSTAGES;
@@ -270,6 +275,14 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
         const int row = i % 128;
         *reinterpret_cast<uint4*>(pt + sw64(row, 32)) = make_uint4(0x00003F80u, 0u, 0u, 0u);   // bf16(1.0) = 0x3F80
         *reinterpret_cast<uint4*>(pt + sw64(row, 48)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    // selector for window position pos: keep a channel's 16 bits where its nibble == (relu bit | pos), else zero
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) {
+        uint32_t sel[4];
+#pragma unroll
+        for (int pos = 0; pos < 4; ++pos)
+            sel[pos] = (((b & 7) == (4 | pos)) ? 0x0010u : 0x0044u) | ((((b >> 4) & 7) == (4 | pos)) ? 0x3200u : 0x4400u);
+        lut[b] = make_uint4(sel[0], sel[1], sel[2], sel[3]);
     }
     fence_proxy_async();
     if (threadIdx.x == 0) {
@@ -293,7 +306,7 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
             int ls = 0; uint32_t lphase = 0;
             for (int tile = blockIdx.x; tile < G.num_tiles; tile += gridDim.x) {
                 const TileSpan t = tile_span(G, tile);
-                const int w0 = (int)(t.g0 - (long long)t.n0 * G.PHW), w1 = (int)(t.g1 - (long long)t.n1 * G.PHW);
+                const int w0 = (int)(t.g0 - (unsigned)t.n0 * G.PHW), w1 = (int)(t.g1 - (unsigned)t.n1 * G.PHW);
                 const int r0 = t.n0 * (G.PH + 2) + w0 / G.PW, r1 = t.n1 * (G.PH + 2) + w1 / G.PW;
                 const uint32_t xb = (uint32_t)(t.n1 - t.n0 + 1) * G.H * G.W * 4u;
                 const uint32_t db = (uint32_t)(r1 - r0 + 1) * row_bytes;
@@ -313,11 +326,15 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
         int stage = 0; uint32_t phase = 0; int ls = 0; uint32_t lphase = 0;
         for (int tile = blockIdx.x; tile < G.num_tiles; tile += gridDim.x) {
             const TileSpan t = tile_span(G, tile);
-            const long long g = t.g0 + row;
+            const unsigned g = t.g0 + row;
             const bool valid = g < G.total;
             int n = t.n0, py = 0, px = 0;
-            if (valid) { n = (int)(g / G.PHW); const int w = (int)(g - (long long)n * G.PHW); py = w / G.PW; px = w - py * G.PW; }
-            const int w0 = (int)(t.g0 - (long long)t.n0 * G.PHW), r0 = t.n0 * (G.PH + 2) + w0 / G.PW;
+            if (valid) {
+                unsigned w = g - (unsigned)t.n0 * G.PHW;
+                if (w >= (unsigned)G.PHW) { w -= G.PHW; ++n; }
+                py = (int)(w / (unsigned)G.PW); px = (int)w - py * G.PW;
+            }
+            const int w0 = (int)(t.g0 - (unsigned)t.n0 * G.PHW), r0 = t.n0 * (G.PH + 2) + w0 / G.PW;
             const uint8_t* st = l_smem + (size_t)ls * L.lstage_bytes;
             uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
             uint2 nb = make_uint2(0, 0);
@@ -334,12 +351,14 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
             uint32_t out[4][8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const uint32_t nw = j < 4 ? nb.x : nb.y;
-                const uint32_t n0 = (nw >> (8 * (j & 3))) & 7u, n1 = (nw >> (8 * (j & 3) + 4)) & 7u;   // position | relu << 2
-                const uint32_t lo = dw[j] & 0xFFFFu, hi = dw[j] & 0xFFFF0000u;
-#pragma unroll
-                for (int pos = 0; pos < 4; ++pos)
-                    out[pos][j] = (n0 == (4u | pos) ? lo : 0u) | (n1 == (4u | pos) ? hi : 0u);   // arg-max routing + ReLU mask
+                // arg-max routing + ReLU mask of two channels = four byte permutes whose selectors come from a 256-entry
+                // table indexed by the channels' nibble byte
+                const uint32_t byte = ((j < 4 ? nb.x : nb.y) >> (8 * (j & 3))) & 0xFFu;
+                const uint4 sel = lut[byte];
+                out[0][j] = __byte_perm(dw[j], 0u, sel.x);
+                out[1][j] = __byte_perm(dw[j], 0u, sel.y);
+                out[2][j] = __byte_perm(dw[j], 0u, sel.z);
+                out[3][j] = __byte_perm(dw[j], 0u, sel.w);
             }
             mbar_wait(&aempty[stage], phase ^ 1);
             uint8_t* gt = smem + stage * B_STAGE;
@@ -450,8 +469,9 @@ conv1_tc_bwd_reduce_kernel(const float* __restrict__ partial, float* __restrict_
 
 int geom(Conv1Geom* g, int N, int H, int W) {
     g->N = N; g->H = H; g->W = W; g->PH = H / 2; g->PW = W / 2; g->PHW = g->PH * g->PW;
-    g->total = (long long)N * g->PHW;
-    g->num_tiles = (int)((g->total + 127) / 128);
+    if ((long long)N * g->PHW > 0x7FFFFF00LL) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "conv1: more than 2^31 pool windows");
+    g->total = (unsigned)N * (unsigned)g->PHW;
+    g->num_tiles = (int)((g->total + 127u) / 128u);
     return NM_OK;
 }
 
@@ -470,7 +490,8 @@ int nm_tc_conv1_fwd_pool_bf16(const float* x, const void* w_ext, void* y_pad, vo
     NM_REQUIRE(x && w_ext && y_pad && idx, "null pointer");
     NM_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "bad dimensions");
     if (OCn != OC) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_fwd_pool_bf16: only OC=32 is instantiated");
-    Conv1Geom g; geom(&g, N, H, W);
+    Conv1Geom g;
+    { int rc = geom(&g, N, H, W); if (rc) return rc; }
     NM_REQUIRE(g.PHW >= 128, "image too small: a 128-window tile must touch at most two images");
     const int x_stage = (2 * H * W * 4 + 127) & ~127;
     const size_t smem = (size_t)(1 + F_STAGES) * F_TILE_BYTES + (size_t)F_XSTAGES * x_stage + 256;
@@ -490,7 +511,8 @@ int nm_tc_conv1_bwd_bf16(const float* x, const void* dp_grid, const void* idx, f
     NM_REQUIRE(x && dp_grid && idx && dw && db && workspace, "null pointer");
     NM_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "bad dimensions");
     if (OCn != OC) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_bwd_bf16: only OC=32 is instantiated");
-    Conv1Geom g; geom(&g, N, H, W);
+    Conv1Geom g;
+    { int rc = geom(&g, N, H, W); if (rc) return rc; }
     int grid = sm_count() < B_MAX_GRID ? sm_count() : B_MAX_GRID;
     if (g.num_tiles < grid) grid = g.num_tiles;
     NM_REQUIRE(workspace_bytes >= (size_t)grid * 128 * 32 * sizeof(float), "workspace too small");
@@ -500,7 +522,7 @@ int nm_tc_conv1_bwd_bf16(const float* x, const void* dp_grid, const void* idx, f
     const int max_rows = (128 + g.PW - 1) / g.PW + 1 + 2;          // pooled rows a tile can span + the 2 halo rows at an image boundary
     L.dp_bytes = max_rows * (g.PW + 2) * OC * 2;
     L.lstage_bytes = L.x_bytes + L.dp_bytes + B_IDX_BYTES;
-    const size_t smem = (size_t)B_STAGES * B_STAGE + (size_t)B_LSTAGES * L.lstage_bytes + 256;
+    const size_t smem = (size_t)B_STAGES * B_STAGE + (size_t)B_LSTAGES * L.lstage_bytes + 256 * 16 + 256;
     if (smem > 220 * 1024) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_bwd_bf16: image too large for the staged-input ring");
     static bool attr = false;
     if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv1_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
