@@ -31,6 +31,8 @@ struct ConvTcParams {
     void* out;                         // EPI 0: bf16 [rows_total][NOUT];  EPI 1: pooled bf16 NHWC
     uint8_t* idx;                      // EPI 1: one nibble per pooled element: argmax (2 bits) | (value>0) << 2
     int oHp, oWp, ooff;                // EPI 1: pooled output geometry (padded for a following conv, or dense)
+    long long* trace;                  // timing experiments only: CTA 0 records clock64() per tile and role
+    int debug;                         // timing experiments only (NM_TC_DEBUG): 1 = no shuffles, 2 = no stores, 4 = no MMA
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -43,7 +45,7 @@ struct ConvTcParams {
 // never crosses a warp).  The MMA is bound by the 128 B/cycle read of its 4 KB A slice, so tripling N is free:
 // 12 MMAs of 56 cycles per tile instead of 36 of 45 (profiles/r01_mma_rate.txt).
 template <int CIN, int NOUT, int EPI, bool FOLD>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvTcParams p) {
     constexpr int ROWB = CIN * 2;                                   // bytes per pixel row: 64 (SW64) or 128 (SW128)
     static_assert(ROWB == 64 || ROWB == 128, "CIN must be 32 or 64");
@@ -55,7 +57,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     static_assert(B_BYTES % 1024 == 0, "weight block must keep the A stages 1024-aligned");
     static_assert(!FOLD || EPI == 0, "tap folding is implemented for the plain-store epilogue");
     constexpr int NACC = FOLD ? 3 * NOUT : NOUT;                    // accumulator columns per buffer
-    constexpr uint32_t TMEM_COLS = 2 * NACC <= 32 ? 32 : 2 * NACC <= 64 ? 64 : 2 * NACC <= 128 ? 128 : 2 * NACC <= 256 ? 256 : 512;
+    // Four accumulator buffers: the hand-off chain commit -> epilogue wake-up -> tcgen05.ld -> arrive -> MMA wake-up is about
+    // as long as one tile's MMAs, so with two buffers the tensor pipe idled between tiles (measured: MMA time added on top of
+    // the load time instead of hiding under it).
+    constexpr int NBUF = 4;
+    constexpr uint32_t TMEM_COLS = NBUF * NACC <= 32 ? 32 : NBUF * NACC <= 64 ? 64 : NBUF * NACC <= 128 ? 128 : NBUF * NACC <= 256 ? 256 : 512;
+    static_assert(NBUF * NACC <= 512, "accumulators exceed TMEM");
     constexpr uint32_t IDESC = idesc_bf16(TILE_M, NACC, 0, 0);
 
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -65,15 +72,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint64_t* full = bars;
     uint64_t* empty = bars + p.n_stages;
     uint64_t* tfull = empty + p.n_stages;
-    uint64_t* tempty = tfull + 2;
-    uint64_t* bfull = tempty + 2;
+    uint64_t* tempty = tfull + NBUF;
+    uint64_t* bfull = tempty + NBUF;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < NBUF; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
         mbar_init(bfull, 1);
         mbar_fence_init();
     }
@@ -91,25 +98,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 mbar_wait(&empty[stage], phase ^ 1);
+                if (p.trace && blockIdx.x == 0) p.trace[(tile / gridDim.x) * 8 + 0] = clock64();
                 mbar_expect_tx(&full[stage], (uint32_t)p.a_rows * ROWB);
                 tma_load_2d(a_smem + (size_t)stage * p.a_stage_bytes, &map_a, 0, tile * TILE_M, &full[stage]);
                 if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        // ============================== MMA issuer ================================
+    } else if (warp == 1 || warp == 3) {
+        // ============================== MMA issuers (two warps, alternating tiles) =================
         // The whole warp runs the loop converged and ONE elected lane issues: under `if (lane == 0)` the
         // compiler wraps every UTCHMMA in an ELECT/BRA.U.ANY retry loop fed by R2UR moves (~50 cycles per MMA,
         // measured with scratch/mma_rate.cu); converged + elect.sync issues one every few cycles.
+        // UTCHMMA issue is back-pressured by the tensor pipe (a per-tile trace showed issue time == execution
+        // time), so one issuer leaves the pipe idle while it waits on the next tile's mbarriers (~500 cycles
+        // per tile); a second warp does those waits while the first one's MMAs run.
         mbar_wait(bfull, 0);
-        const uint32_t b_base = smem_u32(b_smem);
-        int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int mw = warp >> 1;                                        // 0 or 1
+        const uint64_t b_desc0 = desc_at(TMPL, smem_u32(b_smem));
+        int it = mw;
+        for (int tile = blockIdx.x + mw * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
+            const int stage = it % p.n_stages, acc = it % NBUF;
+            const uint32_t phase = (it / p.n_stages) & 1, acc_phase = (it / NBUF) & 1;
             mbar_wait(&tempty[acc], acc_phase ^ 1);
+            if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[(tile / gridDim.x) * 8 + 1] = clock64();
             mbar_wait(&full[stage], phase);
+            if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[(tile / gridDim.x) * 8 + 2] = clock64();
             fence_after_sync();
             if (elect_one()) {
-                const uint32_t a_base = smem_u32(a_smem + (size_t)stage * p.a_stage_bytes);
+                // descriptor = template | (address >> 4): advancing the address is one add on the low word
+                const uint64_t a_desc0 = desc_at(TMPL, smem_u32(a_smem + (size_t)stage * p.a_stage_bytes));
                 const uint32_t d_addr = tmem_base + acc * NACC;
                 if constexpr (FOLD) {
 #pragma unroll
@@ -117,8 +134,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         const uint32_t shift = (uint32_t)(r * p.Wp) * ROWB;
 #pragma unroll
                         for (int kk = 0; kk < KSTEPS; ++kk)
-                            mma_bf16(d_addr, desc_at(TMPL, a_base + shift + kk * 32),
-                                     desc_at(TMPL, b_base + 3 * r * B_TAP_BYTES + kk * 32), IDESC, (r | kk) != 0);
+                            mma_bf16(d_addr, a_desc0 + ((shift + kk * 32) >> 4), b_desc0 + ((3 * r * B_TAP_BYTES + kk * 32) >> 4),
+                                     IDESC, (r | kk) != 0);
                     }
                 } else {
 #pragma unroll
@@ -126,23 +143,24 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         const uint32_t shift = (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * ROWB;
 #pragma unroll
                         for (int kk = 0; kk < KSTEPS; ++kk)
-                            mma_bf16(d_addr, desc_at(TMPL, a_base + shift + kk * 32),
-                                     desc_at(TMPL, b_base + tap * B_TAP_BYTES + kk * 32), IDESC, (tap | kk) != 0);
+                            mma_bf16(d_addr, a_desc0 + ((shift + kk * 32) >> 4), b_desc0 + ((tap * B_TAP_BYTES + kk * 32) >> 4),
+                                     IDESC, (tap | kk) != 0);
                     }
                 }
                 mma_commit(&empty[stage]);          // A stage reusable once these MMAs have read it
                 mma_commit(&tfull[acc]);            // accumulator ready for the epilogue
             }
             __syncwarp();
-            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
-            acc ^= 1; if (acc == 0) acc_phase ^= 1;
+            if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[(tile / gridDim.x) * 8 + 3] = clock64();
         }
     } else if (warp >= 4) {
-        // ============================== epilogue (4 warps) ========================
+        // ============================== epilogue (two groups of 4 warps, alternating tiles) ==========
         const int q = warp & 3;                       // TMEM sub-partition = lanes [32q, 32q+32)
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int grp = (warp - 4) >> 2;
+        int acc = grp; uint32_t acc_phase = 0;        // NBUF is even: a buffer always belongs to the same group
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x) {
             mbar_wait(&tfull[acc], acc_phase);
+            if (p.trace && blockIdx.x == 0 && lane == 0 && q == 0) p.trace[(tile / gridDim.x) * 8 + 4] = clock64();
             fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NACC;
             uint32_t raw[NOUT];
@@ -158,11 +176,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (p.debug & 1) {
+#pragma unroll
+                    for (int c = 0; c < NOUT; ++c)
+                        raw[c] = __float_as_uint(__uint_as_float(raw[c]) + (__uint_as_float(e1[c]) + __uint_as_float(e2[c])));
+                } else {
 #pragma unroll
                 for (int c = 0; c < NOUT; ++c)
                     raw[c] = __float_as_uint(__uint_as_float(raw[c]) +
                                              (__uint_as_float(__shfl_down_sync(0xffffffffu, e1[c], 1)) +
                                               __uint_as_float(__shfl_down_sync(0xffffffffu, e2[c], 2))));
+                }
             } else {
 #pragma unroll
                 for (int c = 0; c < NOUT; c += 16) tmem_ld_x16(taddr + c, raw + c);
@@ -171,12 +195,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator drained: MMA may overwrite it
             }
-            acc ^= 1; if (acc == 0) acc_phase ^= 1;
+            acc += 2; if (acc >= NBUF) { acc -= NBUF; acc_phase ^= 1; }
+            if (p.trace && blockIdx.x == 0 && lane == 0 && q == 0) p.trace[(tile / gridDim.x) * 8 + 5] = clock64();
 
             if constexpr (EPI == 0) {
                 // plain bf16 store of the [pixel][NOUT] row (dgrad)
                 const long long row = (long long)tile * TILE_M + q * 32 + lane;
-                if (row < p.rows_total) {
+                if (row < p.rows_total && !(p.debug & 2)) {
                     uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row * NOUT);
 #pragma unroll
                     for (int c = 0; c < NOUT; c += 8) {
@@ -194,6 +219,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 // leave lane (dy,dx) owning channels [ (NOUT/2)*dx + (NOUT/4)*dy, +NOUT/4 ) of its window.
                 static_assert(EPI == 0 || NOUT % 4 == 0, "pool epilogue needs NOUT % 4 == 0");
                 constexpr int HALF = NOUT / 2, QUART = NOUT / 4;
+                if (p.debug & 1) continue;
                 const int dx = lane & 1, dy = (lane >> 4) & 1;
                 float h[HALF];
                 uint32_t hsel = 0;
@@ -224,7 +250,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const int tiles_per_img = (p.Hp * p.Wp) / TILE_M;
                 const int n = tile / tiles_per_img;
                 const int py = ((tile % tiles_per_img) * (TILE_M / 16)) / 2 + q, px = (lane & 15) >> 1;
-                if (py < p.H / 2 && px < p.W / 2) {
+                if (py < p.H / 2 && px < p.W / 2 && !(p.debug & 2)) {
                     const int cbase = HALF * dx + QUART * dy;
                     __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) +
                         (((size_t)n * p.oHp + py + p.ooff) * p.oWp + px + p.ooff) * NOUT + cbase;
@@ -423,22 +449,31 @@ int launch_conv(const void* a, const void* b, ConvTcParams p, int N, cudaStream_
     rc = make_map_2d(&mb, b, 9 * CIN, NOUT, 9 * ROWB, CIN, NOUT, sw);
     if (rc) return rc;
     p.a_stage_bytes = ((uint32_t)p.a_rows * ROWB + 1023u) & ~1023u;
-    p.n_stages = 6;
-    size_t smem = 9 * NOUT * ROWB + (size_t)p.n_stages * p.a_stage_bytes + 256;
+    {   // as many A stages as fit: the tile period is (load latency + MMA time) / stages when few tiles are in flight
+        static int forced = -1;
+        if (forced < 0) { const char* e = getenv("NM_TC_CONV_STAGES"); forced = e ? atoi(e) : 0; }
+        int fit = (int)((215 * 1024 - 9 * NOUT * ROWB) / p.a_stage_bytes);
+        p.n_stages = forced > 0 ? forced : (fit > 12 ? 12 : fit);
+    }
+    size_t smem = 9 * NOUT * ROWB + (size_t)p.n_stages * p.a_stage_bytes + 512;   // + mbarriers
     auto kern = conv3x3_tc_kernel<CIN, NOUT, EPI, FOLD>;
     static bool attr_set = false;
     if (!attr_set) {
-        NM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        NM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
     }
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    kern<<<grid, 256, smem, st>>>(ma, mb, p);
+    kern<<<grid, 384, smem, st>>>(ma, mb, p);
     return nm::launched("conv3x3_tc");
 }
 
 }  // namespace
 
 extern "C" {
+
+static long long* g_conv_trace = nullptr;
+/* timing experiments only: CTA 0 of the next conv3x3 launches records clock64() per tile into buf[tiles][8] */
+int nm_tc_debug_set_trace(void* buf) { g_conv_trace = static_cast<long long*>(buf); return NM_OK; }
 
 int nm_tc_pack_conv_weights_bf16(const float* w_oihw, void* w_fprop, void* w_dgrad, int OC, int C, void* stream) {
     NM_REQUIRE(w_oihw && (w_fprop || w_dgrad), "null pointer");
@@ -462,6 +497,8 @@ int nm_tc_conv3x3_fprop_pool_bf16(const void* x_pad, const void* w_packed, void*
     p.a_rows = TILE_M + 2 * p.Wp + 2;
     p.out = y; p.idx = static_cast<uint8_t*>(idx);
     p.oHp = out_padded ? H / 2 + 2 : H / 2; p.oWp = out_padded ? W / 2 + 2 : W / 2; p.ooff = out_padded ? 1 : 0;
+    { const char* e = getenv("NM_TC_DEBUG_FPROP"); p.debug = e ? atoi(e) : 0; }
+    p.trace = g_conv_trace;
     return launch_conv<32, 64, 1, false>(x_pad, w_packed, p, N, nm::S(stream));
 }
 
@@ -480,6 +517,8 @@ int nm_tc_conv3x3_dgrad_bf16(const void* dy_pad, const void* w_packed_dgrad, voi
     p.out = dx_grid;
     static int fold = -1;
     if (fold < 0) { const char* e = getenv("NM_TC_DGRAD_FOLD"); fold = e ? atoi(e) : 1; }
+    { const char* e = getenv("NM_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
+    p.trace = g_conv_trace;
     if (fold && p.Wp == 16) return launch_conv<64, 32, 0, true>(dy_pad, w_packed_dgrad, p, N, nm::S(stream));
     return launch_conv<64, 32, 0, false>(dy_pad, w_packed_dgrad, p, N, nm::S(stream));
 }
@@ -501,7 +540,12 @@ int nm_tc_conv3x3_wgrad_bf16(const void* x_pad, const void* dy_pad, float* dw, v
     p.num_kblocks = (p.rows_total + TILE_M - 1) / TILE_M;
     p.x_rows = TILE_M + 2 * p.Wp + 2;
     p.x_stage_bytes = ((uint32_t)p.x_rows * 64 + 1023u) & ~1023u;
-    p.n_stages = 4;
+    {
+        static int forced = -1;
+        if (forced < 0) { const char* e = getenv("NM_TC_WGRAD_STAGES"); forced = e ? atoi(e) : 0; }
+        int fit = (int)((216 * 1024) / (TILE_M * 128 + p.x_stage_bytes));
+        p.n_stages = forced > 0 ? forced : (fit > 10 ? 10 : fit);
+    }
     int grid = p.num_kblocks < sm_count() ? p.num_kblocks : sm_count();
     NM_REQUIRE(workspace_bytes >= (size_t)grid * OC * 9 * C * sizeof(float), "workspace too small");
     p.partial = static_cast<float*>(workspace);
@@ -515,8 +559,8 @@ int nm_tc_conv3x3_wgrad_bf16(const void* x_pad, const void* dy_pad, float* dw, v
     if (fold < 0) { const char* e = getenv("NM_TC_WGRAD_FOLD"); fold = e ? atoi(e) : 1; }
     static bool attr_set = false;
     if (!attr_set) {
-        NM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<32, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        NM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<32, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        NM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<32, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        NM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<32, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
     }
     if (fold) conv3x3_wgrad_tc_kernel<32, 64, true><<<grid, 256, smem, nm::S(stream)>>>(mdy, mx, p);
