@@ -484,24 +484,6 @@ int nm_tc_pack_conv_weights_bf16(const float* w_oihw, void* w_fprop, void* w_dgr
     return nm::launched("pack_conv_weights");
 }
 
-int nm_tc_conv3x3_fprop_pool_bf16(const void* x_pad, const void* w_packed, void* y, void* idx,
-                                  int N, int H, int W, int C, int OC, int out_padded, void* stream) {
-    NM_REQUIRE(x_pad && w_packed && y && idx, "null pointer");
-    NM_REQUIRE(N > 0, "bad batch");
-    if (!(C == 32 && OC == 64 && H == 14 && W == 14))
-        return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv3x3_fprop_pool_bf16: only C=32, OC=64, 14x14 is instantiated");
-    ConvTcParams p{};
-    p.Hp = H + 2; p.Wp = W + 2; p.H = H; p.W = W;
-    p.rows_total = N * p.Hp * p.Wp;
-    p.num_tiles = (p.rows_total + TILE_M - 1) / TILE_M;
-    p.a_rows = TILE_M + 2 * p.Wp + 2;
-    p.out = y; p.idx = static_cast<uint8_t*>(idx);
-    p.oHp = out_padded ? H / 2 + 2 : H / 2; p.oWp = out_padded ? W / 2 + 2 : W / 2; p.ooff = out_padded ? 1 : 0;
-    { const char* e = getenv("NM_TC_DEBUG_FPROP"); p.debug = e ? atoi(e) : 0; }
-    p.trace = g_conv_trace;
-    return launch_conv<32, 64, 1, false>(x_pad, w_packed, p, N, nm::S(stream));
-}
-
 int nm_tc_conv3x3_dgrad_bf16(const void* dy_pad, const void* w_packed_dgrad, void* dx_grid,
                              int N, int H, int W, int C, int OC, void* stream) {
     NM_REQUIRE(dy_pad && w_packed_dgrad && dx_grid, "null pointer");

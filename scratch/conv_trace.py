@@ -6,7 +6,7 @@ from neuromah_b200._lib import lib, _Lib
 from neuromah_b200.device import DeviceArray, stream
 device.init(0)
 dll = lib.load()
-dll.nm_tc_debug_set_trace.argtypes = [C.c_void_p]
+dll.nm_tc_debug_set_trace.argtypes = [C.c_void_p]; dll.nm_tc_debug_set_trace_pool.argtypes = [C.c_void_p]
 n = 4096
 rng = np.random.default_rng(0)
 which = sys.argv[1]
@@ -25,10 +25,10 @@ else:
 for _ in range(20):
     call()
 device.synchronize()
-dll.nm_tc_debug_set_trace(trace.p)
+(dll.nm_tc_debug_set_trace if which == 'dgrad' else dll.nm_tc_debug_set_trace_pool)(C.c_void_p(trace.ptr))
 call()
 device.synchronize()
-dll.nm_tc_debug_set_trace(None)
+(dll.nm_tc_debug_set_trace if which == 'dgrad' else dll.nm_tc_debug_set_trace_pool)(None)
 t = trace.numpy()
 t0 = t[0, 0]
 names = ["prod_issue", "mma_tempty", "mma_full", "mma_issued", "epi_tfull", "epi_done"]
