@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libneuromah_b200.so")
+LIB_PATH = os.environ.get("NM_LIB_PATH") or os.path.join(_HERE, "libneuromah_b200.so")
 
 NM_OK, NM_ERR_BAD_ARG, NM_ERR_CUDA, NM_ERR_NCCL, NM_ERR_OOM, NM_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 

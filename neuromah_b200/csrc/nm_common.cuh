@@ -45,4 +45,12 @@ inline int launched(const char* name, int n = 1) {
         if (!(cond)) return nm::fail(NM_ERR_BAD_ARG, "%s: %s", __func__, msg); \
     } while (0)
 
+// Timing experiments only (scratch/ablate.py): -DNM_ABLATE=<bits> builds a variant library with parts of some kernels
+// switched off at COMPILE time; the product build (NM_ABLATE undefined) contains none of it.
+#ifdef NM_ABLATE
+#define NM_DBG(bit) (((NM_ABLATE) >> (bit)) & 1)
+#else
+#define NM_DBG(bit) 0
+#endif
+
 static inline unsigned nm_cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }

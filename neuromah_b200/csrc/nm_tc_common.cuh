@@ -66,6 +66,12 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
                  : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+
 // ---- UMMA descriptors -------------------------------------------------------------------------
 // smem matrix descriptor without the start address (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
 //   [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4, [46,48) version = 1,

@@ -343,38 +343,42 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
             }
         }
     } else if (warp == 1) {
-        // converged warp, one elected lane issues (see conv3x3_tc_kernel)
-        int stage = 0; uint32_t phase = 0; uint32_t first = 1;
-        for (int kb = blockIdx.x; kb < p.num_kblocks; kb += gridDim.x) {
-            mbar_wait(&full[stage], phase);
-            fence_after_sync();
-            if (elect_one()) {
-                const uint32_t a_base = smem_u32(smem + (size_t)stage * stage_bytes);
-                const uint32_t x_base = a_base + A_BYTES;
+        // One elected lane issues everything.  UTCHMMA issue is back-pressured by the tensor pipe, so the wait for the
+        // NEXT k-block's data is done before the last MMAs of the current one are issued: it hides under queued MMAs
+        // instead of leaving the pipe idle for an mbarrier round trip per k-block.
+        if (elect_one()) {
+            int it = 0;
+            if ((int)blockIdx.x < p.num_kblocks) mbar_wait(&full[0], 0);
+            for (int kb = blockIdx.x; kb < p.num_kblocks; kb += gridDim.x, ++it) {
+                const int stage = it % p.n_stages;
+                fence_after_sync();
+                const uint64_t a_desc0 = desc_at(TMPL_A, smem_u32(smem + (size_t)stage * stage_bytes));
+                const uint64_t x_desc0 = desc_at(FOLD ? TMPL_B3 : TMPL_B, smem_u32(smem + (size_t)stage * stage_bytes) + A_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < TILE_M / 16; ++ks) {
-                    const uint64_t adesc = desc_at(TMPL_A, a_base + ks * 16 * A_ROWB);
+                    if (ks == TILE_M / 16 - 1 && kb + (int)gridDim.x < p.num_kblocks) {
+                        const int nit = it + 1;
+                        mbar_wait(&full[nit % p.n_stages], (nit / p.n_stages) & 1);
+                    }
+                    const uint64_t adesc = a_desc0 + ((ks * 16 * A_ROWB) >> 4);
                     if constexpr (FOLD) {
 #pragma unroll
                         for (int r = 0; r < 3; ++r) {
                             const uint32_t shift = (uint32_t)(r * p.Wp + ks * 16) * B_ROWB;
-                            mma_bf16(tmem_base + r * 3 * CIN, adesc, desc_at(TMPL_B3, x_base + shift), IDESC3, !(first && ks == 0));
+                            mma_bf16(tmem_base + r * 3 * CIN, adesc, x_desc0 + (shift >> 4), IDESC3, !(it == 0 && ks == 0));
                         }
                     } else {
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
                             const uint32_t shift = (uint32_t)((tap / 3) * p.Wp + (tap % 3) + ks * 16) * B_ROWB;
-                            mma_bf16(tmem_base + tap * CIN, adesc, desc_at(TMPL_B, x_base + shift), IDESC, !(first && ks == 0));
+                            mma_bf16(tmem_base + tap * CIN, adesc, x_desc0 + (shift >> 4), IDESC, !(it == 0 && ks == 0));
                         }
                     }
                 }
                 mma_commit(&empty[stage]);
             }
-            __syncwarp();
-            first = 0;
-            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+            mma_commit(done);
         }
-        if (elect_one()) mma_commit(done);
         __syncwarp();
     } else if (warp >= 4) {
         const int q = warp & 3;

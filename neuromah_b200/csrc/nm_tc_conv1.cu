@@ -24,6 +24,14 @@
 #include "nm_tc_common.cuh"
 #include "nm_tc_host.cuh"
 
+#ifdef NM_ABLATE   // timing experiments only: CTA 0 records clock64() per tile and role
+#define NM_TRACE(G, tile, slot) do { if ((G).trace && blockIdx.x == 0) (G).trace[((tile) / gridDim.x) * 8 + (slot)] = clock64(); } while (0)
+static long long* g_conv1_trace = nullptr;
+extern "C" int nm_tc_debug_set_trace_conv1(void* buf) { g_conv1_trace = static_cast<long long*>(buf); return 0; }
+#else
+#define NM_TRACE(G, tile, slot) do { } while (0)
+#endif
+
 namespace {
 
 using namespace tc;
@@ -36,7 +44,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ uint32_t sw64(uint32_t row, uint32_t byte) { const uint32_t o = row * 64 + byte; return o ^ (((o >> 7) & 3) << 4); }
 __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t byte) { const uint32_t o = row * 128 + byte; return o ^ (((o >> 7) & 7) << 4); }
 
-struct Conv1Geom { int N, H, W, PH, PW, PHW; unsigned total; int num_tiles; };   // total pool windows < 2^31
+struct Conv1Geom { int N, H, W, PH, PW, PHW; unsigned total; int num_tiles; long long* trace; };   // total pool windows < 2^31
 
 // Images [n0, n1] touched by the 128 windows of a tile; the bulk-copy producer stages them (contiguous in x).
 struct TileSpan { unsigned g0, g1; int n0, n1; };
@@ -69,9 +77,11 @@ __device__ __forceinline__ void load_patch(const float* __restrict__ xs, const C
 // forward
 // ---------------------------------------------------------------------------------------------
 constexpr int F_TILE_BYTES = 128 * 64;          // 128 rows x 64 B (K = 16 bf16 used, SWIZZLE_64B)
-constexpr int F_STAGES = 3;                     // A-tile ring (builders -> MMA)
+constexpr int F_STAGES = 4;                     // A-tile ring (builders -> MMA)
+constexpr int F_NBUF = 4;                       // TMEM accumulators (4 x 128 columns): the MMA runs two tiles ahead of each epilogue
+                                                // group, which hides the ~900-cycle mbarrier hand-off chain seen in the role trace
 constexpr int F_XSTAGES = 6;                    // staged-image ring (bulk-copy producer -> builders): hides the HBM latency
-constexpr int F_THREADS = 448;                  // warps 0-3 builders, 4 MMA, 5-12 epilogue (2 groups), 13 bulk-copy producer
+constexpr int F_THREADS = 832;                  // warps 0-7 builders (2 groups), 8 MMA, 9-24 epilogue (4 groups), 25 bulk-copy producer
 
 __global__ void __launch_bounds__(F_THREADS, 1)
 conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ wext, __nv_bfloat16* __restrict__ y_pad,
@@ -87,8 +97,8 @@ conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
     uint64_t* xfull = aempty + F_STAGES;
     uint64_t* xempty = xfull + F_XSTAGES;
     uint64_t* tfull = xempty + F_XSTAGES;
-    uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* tempty = tfull + F_NBUF;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + F_NBUF);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // Wext [128 (pos,oc)][16] bf16 -> B tile
@@ -98,18 +108,20 @@ conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
     }
     fence_proxy_async();
     if (threadIdx.x == 0) {
-        for (int s = 0; s < F_STAGES; ++s) { mbar_init(&afull[s], 128); mbar_init(&aempty[s], 1); }
-        for (int s = 0; s < F_XSTAGES; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 128); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        // builder barriers count WARPS: 128 per-thread mbarrier arrivals per tile serialise on one shared-memory word and
+        // were the whole pipeline's critical path (ablation: 29 us with the epilogue math and stores switched off)
+        for (int s = 0; s < F_STAGES; ++s) { mbar_init(&afull[s], 4); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < F_XSTAGES; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 4); }
+        for (int a = 0; a < F_NBUF; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         mbar_fence_init();
     }
-    if (warp == 4) tmem_alloc(tmem_slot, 256);
+    if (warp == 8) tmem_alloc(tmem_slot, F_NBUF * 128);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 13) {
+    if (warp == 25) {
         // ============================== bulk-copy producer: the images a tile touches =========
         if (lane == 0) {
             int xs = 0; uint32_t xphase = 0;
@@ -122,11 +134,14 @@ conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
                 if (++xs == F_XSTAGES) { xs = 0; xphase ^= 1; }
             }
         }
-    } else if (warp < 4) {
+    } else if (warp < 8) {
         // ============================== builders: one pool window per thread =================
-        const int row = threadIdx.x;
-        int stage = 0; uint32_t phase = 0; int xs = 0; uint32_t xphase = 0;
-        for (int tile = blockIdx.x; tile < G.num_tiles; tile += gridDim.x) {
+        // two groups of 4 warps alternate tiles (a tile's build is a chain of mbarrier / shared-memory round trips)
+        const int bg = warp >> 2, row = threadIdx.x & 127;
+        int it = bg;
+        for (int tile = blockIdx.x + bg * gridDim.x; tile < G.num_tiles; tile += 2 * gridDim.x, it += 2) {
+            const int stage = it % F_STAGES, xs = it % F_XSTAGES;
+            const uint32_t phase = (it / F_STAGES) & 1, xphase = (it / F_XSTAGES) & 1;
             const TileSpan t = tile_span(G, tile);
             const unsigned g = t.g0 + row;
             const bool valid = g < G.total;
@@ -137,28 +152,33 @@ conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
                 py = (int)(w / (unsigned)G.PW); px = (int)w - py * G.PW;
             }
             float p[16];
+            if (row == 0) NM_TRACE(G, tile, 0);
             mbar_wait(&xfull[xs], xphase);
+            if (row == 0) NM_TRACE(G, tile, 1);
             load_patch(reinterpret_cast<const float*>(x_smem + (size_t)xs * x_stage_bytes), G, valid, n - t.n0, py, px, p);
-            mbar_arrive(&xempty[xs]);                         // the patch is in registers: the image slot may be refilled
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&xempty[xs]);          // the patches are in registers: the image slot may be refilled
             mbar_wait(&aempty[stage], phase ^ 1);
+            if (row == 0) NM_TRACE(G, tile, 2);
             uint8_t* at = a_smem + stage * F_TILE_BYTES;
             *reinterpret_cast<uint4*>(at + sw64(row, 0)) = make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]),
                                                                        pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
             *reinterpret_cast<uint4*>(at + sw64(row, 16)) = make_uint4(pack_bf16x2(p[8], p[9]), pack_bf16x2(p[10], p[11]),
                                                                         pack_bf16x2(p[12], p[13]), pack_bf16x2(p[14], p[15]));
             fence_proxy_async();
-            mbar_arrive(&afull[stage]);
-            if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
-            if (++xs == F_XSTAGES) { xs = 0; xphase ^= 1; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&afull[stage]);
+            if (row == 0) NM_TRACE(G, tile, 3);
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ============================== MMA issuer ===========================================
         const uint32_t b_base = smem_u32(b_smem);
         int stage = 0; uint32_t phase = 0; int it = 0;
         for (int tile = blockIdx.x; tile < G.num_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+            const int acc = it % F_NBUF;
+            mbar_wait(&tempty[acc], ((it / F_NBUF) & 1) ^ 1);
             mbar_wait(&afull[stage], phase);
+            if (lane == 0) NM_TRACE(G, tile, 4);
             fence_after_sync();
             if (elect_one()) {
                 mma_bf16(tmem_base + acc * 128, desc_at(TMPL, smem_u32(a_smem + stage * F_TILE_BYTES)), desc_at(TMPL, b_base), IDESC, 0);
@@ -168,9 +188,12 @@ conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
             __syncwarp();
             if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
         }
-    } else {
-        // ============================== epilogue: two groups of 4 warps, alternating tiles ====
-        const int grp = (warp - 5) >> 2, q = warp & 3;                     // q = TMEM sub-partition of this warp
+    } else if (warp < 25) {
+        // ============================== epilogue: four groups of 4 warps ======================
+        // group = (tile parity, channel half); a thread owns 16 channels of its pool window, in two chunks of 8.  More,
+        // lighter warps: the per-window work is a few hundred dependent ALU instructions, and with two 4-warp groups the
+        // issue slots sat idle on latency (role trace: ~2400 cycles per tile and group).
+        const int g4 = (warp - 9) >> 2, grp = g4 & 1, half = g4 >> 1, q = warp & 3;   // q = TMEM sub-partition of this warp
         int it = grp;
         for (int tile = blockIdx.x + grp * gridDim.x; tile < G.num_tiles; tile += 2 * gridDim.x, it += 2) {
             const unsigned g = (unsigned)tile * 128u + q * 32 + lane;
@@ -178,53 +201,51 @@ conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
             int n = 0, py = 0, px = 0, w = 0;
             if (valid) { n = (int)(g / (unsigned)G.PHW); w = (int)(g - (unsigned)n * G.PHW); py = w / G.PW; px = w - py * G.PW; }
             __nv_bfloat16* yo = y_pad + (((size_t)n * (G.PH + 2) + py + 1) * (G.PW + 2) + px + 1) * OC;
-            mbar_wait(&tfull[grp], (it >> 1) & 1);
+            uint32_t* io = reinterpret_cast<uint32_t*>(idx + ((size_t)n * G.PHW + w) * (OC / 2));
+            const int acc = it % F_NBUF;                                   // F_NBUF is even: buffers {grp, grp + 2} belong to this parity
+            mbar_wait(&tfull[acc], (it / F_NBUF) & 1);
+            if (lane == 0 && q == 0 && half == 0) NM_TRACE(G, tile, 5);
             fence_after_sync();
-            uint32_t nibw[4];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t raw[4][16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 128 + h * 16;
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int chunk = half * 2 + h2;                           // channels [8*chunk, 8*chunk + 8)
+                uint32_t raw[4][8];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + chunk * 8;
 #pragma unroll
-                for (int pos = 0; pos < 4; ++pos) tmem_ld_x16(taddr + pos * 32, raw[pos]);
+                for (int pos = 0; pos < 4; ++pos) tmem_ld_x8(taddr + pos * 32, raw[pos]);
                 tmem_ld_wait();
-                if (h == 1) {                                              // accumulator drained: the MMA may overwrite it
+                if (h2 == 1) {                                             // this group's columns are drained
                     fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[grp]);
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
                 }
-                float best[16];
-                uint32_t nl = 0, nh = 0;
+                float best[8];
+                uint32_t nibs = 0;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
+                for (int c = 0; c < 8; ++c) {
                     // max-pool of ReLU == ReLU of max-pool; first max of the reference scan (0,0),(0,1),(1,0),(1,1) with its
                     // strict '>' (maxpooling_backend.cpp:104); an all-non-positive window keeps position 0 like the reference.
                     float bv = fmaxf(__uint_as_float(raw[0][c]), 0.f); uint32_t bi = 0;
 #pragma unroll
-                    for (int pos = 1; pos < 4; ++pos) {
+                    for (int pos = 1; pos < (NM_DBG(2) ? 1 : 4); ++pos) {
                         const float v = __uint_as_float(raw[pos][c]);
                         if (v > bv) { bv = v; bi = pos; }
                     }
                     best[c] = bv;
-                    const uint32_t nb = bi | (bv > 0.f ? 4u : 0u);
-                    if (c < 8) nl |= nb << (4 * c); else nh |= nb << (4 * (c - 8));
+                    nibs |= (bi | (bv > 0.f ? 4u : 0u)) << (4 * c);
                 }
-                nibw[2 * h] = nl; nibw[2 * h + 1] = nh;
-                if (valid) {
-                    uint4* dst = reinterpret_cast<uint4*>(yo + h * 16);
-                    dst[0] = make_uint4(pack_bf16x2(best[0], best[1]), pack_bf16x2(best[2], best[3]),
-                                        pack_bf16x2(best[4], best[5]), pack_bf16x2(best[6], best[7]));
-                    dst[1] = make_uint4(pack_bf16x2(best[8], best[9]), pack_bf16x2(best[10], best[11]),
-                                        pack_bf16x2(best[12], best[13]), pack_bf16x2(best[14], best[15]));
+                if (valid && !NM_DBG(3)) {
+                    *reinterpret_cast<uint4*>(yo + chunk * 8) = make_uint4(pack_bf16x2(best[0], best[1]), pack_bf16x2(best[2], best[3]),
+                                                                            pack_bf16x2(best[4], best[5]), pack_bf16x2(best[6], best[7]));
+                    io[chunk] = nibs;
                 }
             }
-            if (valid)
-                *reinterpret_cast<uint4*>(idx + ((size_t)n * G.PHW + w) * (OC / 2)) = make_uint4(nibw[0], nibw[1], nibw[2], nibw[3]);
+            if (lane == 0 && q == 0 && half == 0) NM_TRACE(G, tile, 6);
         }
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, 256);
+    if (warp == 8) tmem_dealloc(tmem_base, F_NBUF * 128);
 }
 
 // Wext[(dy,dx,oc)][a*4+b] = W[oc][a-dy][b-dx] inside the 3x3 support, else 0
@@ -244,10 +265,10 @@ constexpr int B_G_BYTES = 2 * 128 * 128;        // G: two SW128 column blocks [(
 constexpr int B_P_BYTES = 128 * 64;             // P: [128 windows][32 = 16 patch + 1 ones + 15 zero] bf16, SW64
 constexpr int B_STAGE = B_G_BYTES + B_P_BYTES;  // 40 KB
 constexpr int B_STAGES = 2;                     // operand ring (builders -> MMA)
-constexpr int B_LSTAGES = 4;                    // staged-input ring (bulk-copy producer -> builders)
+constexpr int B_LSTAGES = 6;                    // staged-input ring (bulk-copy producer -> builders)
 constexpr int B_IDX_BYTES = 128 * (OC / 2);     // 2 KB of nibbles per tile
 constexpr int B_MAX_GRID = 148;
-constexpr int B_THREADS = 320;                  // warps 0-7 builders (0-3 also the epilogue), 8 MMA, 9 bulk-copy producer
+constexpr int B_THREADS = 576;                  // warps 0-15 builders in two groups alternating tiles (0-3 also the epilogue), 16 MMA, 17 bulk-copy producer
 
 struct Conv1BwdSmem { int x_bytes, dp_bytes, lstage_bytes; };   // per load stage: [x images | dp rows | nibbles]
 
@@ -286,19 +307,19 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
     }
     fence_proxy_async();
     if (threadIdx.x == 0) {
-        for (int s = 0; s < B_STAGES; ++s) { mbar_init(&afull[s], 256); mbar_init(&aempty[s], 1); }
-        for (int s = 0; s < B_LSTAGES; ++s) { mbar_init(&lfull[s], 1); mbar_init(&lempty[s], 256); }
+        for (int s = 0; s < B_STAGES; ++s) { mbar_init(&afull[s], 8); mbar_init(&aempty[s], 1); }      // one arrival per builder warp
+        for (int s = 0; s < B_LSTAGES; ++s) { mbar_init(&lfull[s], 1); mbar_init(&lempty[s], 8); }
         mbar_init(done, 1);
         mbar_fence_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, 64);
+    if (warp == 16) tmem_alloc(tmem_slot, 64);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     const bool has_work = (int)blockIdx.x < G.num_tiles;
 
-    if (warp == 9) {
+    if (warp == 17) {
         // ============================== bulk-copy producer ===================================
         // per tile: the images it touches (contiguous in x), the dP grid rows from its first to its last window
         // (contiguous, incl. the don't-care halo rows when the tile crosses an image boundary) and its 2 KB of nibbles
@@ -313,6 +334,7 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
                 const uint32_t ib = (uint32_t)(t.g1 - t.g0 + 1) * (OC / 2);
                 uint8_t* st = l_smem + (size_t)ls * L.lstage_bytes;
                 mbar_wait(&lempty[ls], lphase ^ 1);
+                NM_TRACE(G, tile, 0);
                 mbar_expect_tx(&lfull[ls], xb + db + ib);
                 bulk_load(st, x + (size_t)t.n0 * G.H * G.W, xb, &lfull[ls]);
                 bulk_load(st + L.x_bytes, reinterpret_cast<const uint8_t*>(dp_grid) + (size_t)r0 * row_bytes, db, &lfull[ls]);
@@ -320,11 +342,16 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
                 if (++ls == B_LSTAGES) { ls = 0; lphase ^= 1; }
             }
         }
-    } else if (warp < 8) {
+    } else if (warp < 16) {
         // ============================== builders: (window, half of the channels) per thread ==
-        const int row = threadIdx.x & 127, hh = threadIdx.x >> 7;
-        int stage = 0; uint32_t phase = 0; int ls = 0; uint32_t lphase = 0;
-        for (int tile = blockIdx.x; tile < G.num_tiles; tile += gridDim.x) {
+        // two groups of 8 warps alternate tiles (group g owns operand stage g): a tile's build is a chain of dependent
+        // shared-memory round trips, so one group alone left the issue slots mostly idle
+        const int grp = warp >> 3, row = threadIdx.x & 127, hh = (threadIdx.x >> 7) & 1;
+        const int stage = grp;
+        int it = grp;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < G.num_tiles; tile += 2 * gridDim.x, it += 2) {
+            const int ls = it % B_LSTAGES;
+            const uint32_t phase = (it >> 1) & 1, lphase = (it / B_LSTAGES) & 1;
             const TileSpan t = tile_span(G, tile);
             const unsigned g = t.g0 + row;
             const bool valid = g < G.total;
@@ -339,14 +366,17 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
             uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
             uint2 nb = make_uint2(0, 0);
             float p[16];
+            if ((threadIdx.x & 255) == 0) NM_TRACE(G, tile, 1);
             mbar_wait(&lfull[ls], lphase);
+            if ((threadIdx.x & 255) == 0) NM_TRACE(G, tile, 2);
             if (valid) {
                 const uint4* src = reinterpret_cast<const uint4*>(st + L.x_bytes + (size_t)(n * (G.PH + 2) + py - r0) * row_bytes + px * (OC * 2) + hh * 32);
                 d0 = src[0]; d1 = src[1];
                 nb = *reinterpret_cast<const uint2*>(st + L.x_bytes + L.dp_bytes + row * (OC / 2) + hh * 8);
             }
             if (hh == 0) load_patch(reinterpret_cast<const float*>(st), G, valid, n - t.n0, py, px, p);
-            mbar_arrive(&lempty[ls]);                         // everything is in registers: the slot may be refilled
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&lempty[ls]);          // everything is in registers: the slot may be refilled
             const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};   // 16 channels as bf16 pairs
             uint32_t out[4][8];
 #pragma unroll
@@ -354,16 +384,17 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
                 // arg-max routing + ReLU mask of two channels = four byte permutes whose selectors come from a 256-entry
                 // table indexed by the channels' nibble byte
                 const uint32_t byte = ((j < 4 ? nb.x : nb.y) >> (8 * (j & 3))) & 0xFFu;
-                const uint4 sel = lut[byte];
+                const uint4 sel = NM_DBG(4) ? make_uint4(byte, byte, byte, byte) : lut[byte];
                 out[0][j] = __byte_perm(dw[j], 0u, sel.x);
                 out[1][j] = __byte_perm(dw[j], 0u, sel.y);
                 out[2][j] = __byte_perm(dw[j], 0u, sel.z);
                 out[3][j] = __byte_perm(dw[j], 0u, sel.w);
             }
             mbar_wait(&aempty[stage], phase ^ 1);
+            if ((threadIdx.x & 255) == 0) NM_TRACE(G, tile, 3);
             uint8_t* gt = smem + stage * B_STAGE;
 #pragma unroll
-            for (int pos = 0; pos < 4; ++pos) {
+            for (int pos = 0; pos < (NM_DBG(5) ? 1 : 4); ++pos) {
                 uint8_t* blk = gt + (pos >> 1) * (128 * 128);
                 const uint32_t base = (pos & 1) * 64 + hh * 32;
                 *reinterpret_cast<uint4*>(blk + sw128(row, base)) = make_uint4(out[pos][0], out[pos][1], out[pos][2], out[pos][3]);
@@ -377,9 +408,9 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
                                                                             pack_bf16x2(p[12], p[13]), pack_bf16x2(p[14], p[15]));
             }
             fence_proxy_async();
-            mbar_arrive(&afull[stage]);
-            if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
-            if (++ls == B_LSTAGES) { ls = 0; lphase ^= 1; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&afull[stage]);
+            if ((threadIdx.x & 255) == 0) NM_TRACE(G, tile, 4);
         }
         // ============================== epilogue: E -> one FP32 partial per CTA ==============
         if (warp < 4) {
@@ -410,11 +441,12 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
         int stage = 0; uint32_t phase = 0; uint32_t first = 1;
         for (int tile = blockIdx.x; tile < G.num_tiles; tile += gridDim.x) {
             mbar_wait(&afull[stage], phase);
+            if (lane == 0) NM_TRACE(G, tile, 5);
             fence_after_sync();
             if (elect_one()) {
                 const uint32_t g_base = smem_u32(smem + stage * B_STAGE), p_base = g_base + B_G_BYTES;
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
+                for (int ks = 0; ks < (NM_DBG(6) ? 1 : 8); ++ks) {
                     const uint64_t bdesc = desc_at(TMPL_B, p_base + ks * 16 * 64);
 #pragma unroll
                     for (int mh = 0; mh < 2; ++mh)
@@ -424,6 +456,7 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
                 mma_commit(&aempty[stage]);
             }
             __syncwarp();
+            if (lane == 0) NM_TRACE(G, tile, 6);
             first = 0;
             if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -432,7 +465,7 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 64);
+    if (warp == 16) tmem_dealloc(tmem_base, 64);
 }
 
 // dW[oc][r][s] = sum_cta sum_pos E[cta][(pos,oc)][(dy+r)*4 + dx+s],  db[oc] = sum_cta sum_pos E[cta][(pos,oc)][16]
@@ -472,6 +505,10 @@ int geom(Conv1Geom* g, int N, int H, int W) {
     if ((long long)N * g->PHW > 0x7FFFFF00LL) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "conv1: more than 2^31 pool windows");
     g->total = (unsigned)N * (unsigned)g->PHW;
     g->num_tiles = (int)((g->total + 127u) / 128u);
+    g->trace = nullptr;
+#ifdef NM_ABLATE
+    g->trace = g_conv1_trace;
+#endif
     return NM_OK;
 }
 

@@ -45,39 +45,51 @@ dense_bwd_unpool_kernel(const float* __restrict__ dlogits, const float* __restri
 #pragma unroll
     for (int c = 0; c < 8; ++c) bsum[c] = 0.f;
     const uint32_t* idx32 = reinterpret_cast<const uint32_t*>(idx);
+    // dlogits of the next DLC images of this CTA are staged in shared memory once per chunk: read per image from global
+    // memory they were a dependent L2 round trip at the top of every iteration (28% of the stall samples)
+    constexpr int DLC = 32;
+    __shared__ float dls[DLC][NO];
     int n = blockIdx.x;
     uint32_t nibs_next = (active && n < B) ? __ldg(idx32 + (size_t)n * items + item) : 0u;
-    for (; n < B; n += gridDim.x) {
-        const uint32_t nibs = nibs_next;
-        const int nn = n + gridDim.x;
-        if (active && nn < B) nibs_next = __ldg(idx32 + (size_t)nn * items + item);
-        if (!active) continue;
-        float d[8];
+    for (int n0 = blockIdx.x; n0 < B; n0 += DLC * gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < DLC * NO; i += blockDim.x) {
+            const int k = i / NO, j = i % NO, nn = n0 + k * gridDim.x;
+            dls[k][j] = (nn < B && j < n_out) ? __ldg(dlogits + (size_t)nn * n_out + j) : 0.f;
+        }
+        __syncthreads();
+        for (int k = 0; k < DLC && n < B; ++k, n += gridDim.x) {
+            const uint32_t nibs = nibs_next;
+            const int nn = n + gridDim.x;
+            if (active && nn < B) nibs_next = __ldg(idx32 + (size_t)nn * items + item);
+            if (!active) continue;
+            float d[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) d[c] = 0.f;
+            for (int c = 0; c < 8; ++c) d[c] = 0.f;
 #pragma unroll
-        for (int j = 0; j < NO; ++j) {
-            if (j < n_out) {
-                const float sdl = __ldg(dlogits + (size_t)n * n_out + j);     // same address for the whole CTA: broadcast
+            for (int j = 0; j < NO; ++j) {
+                if (NM_DBG(0)) break;
+                const float sdl = dls[k][j];                                  // same address for the whole CTA: broadcast
 #pragma unroll
                 for (int c = 0; c < 8; ++c) d[c] = fmaf(sdl, wv[j][c], d[c]);
             }
-        }
-        float v[4][8];
+            float v[4][8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const uint32_t nb = (nibs >> (4 * c)) & 0xF;
-            const float val = (nb & 4) ? d[c] : 0.f;                 // ReLU mask
-            bsum[c] += val;
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t nb = (nibs >> (4 * c)) & 0xF;
+                const float val = (nb & 4) ? d[c] : 0.f;                 // ReLU mask
+                bsum[c] += val;
 #pragma unroll
-            for (int pos = 0; pos < 4; ++pos) v[pos][c] = ((nb & 3) == (uint32_t)pos) ? val : 0.f;   // arg-max routing
-        }
+                for (int pos = 0; pos < 4; ++pos) v[pos][c] = ((nb & 3) == (uint32_t)pos) ? val : 0.f;   // arg-max routing
+            }
 #pragma unroll
-        for (int pos = 0; pos < 4; ++pos) {
-            const int Y = 2 * py + (pos >> 1) + 1, X = 2 * px + (pos & 1) + 1;
-            uint4 o = make_uint4(pack2(v[pos][0], v[pos][1]), pack2(v[pos][2], v[pos][3]),
-                                 pack2(v[pos][4], v[pos][5]), pack2(v[pos][6], v[pos][7]));
-            *reinterpret_cast<uint4*>(dy_pad + (((size_t)n * H2 + Y) * W2 + X) * C + g * 8) = o;
+            for (int pos = 0; pos < 4; ++pos) {
+                const int Y = 2 * py + (pos >> 1) + 1, X = 2 * px + (pos & 1) + 1;
+                uint4 o = make_uint4(pack2(v[pos][0], v[pos][1]), pack2(v[pos][2], v[pos][3]),
+                                     pack2(v[pos][4], v[pos][5]), pack2(v[pos][6], v[pos][7]));
+                if (!NM_DBG(1)) *reinterpret_cast<uint4*>(dy_pad + (((size_t)n * H2 + Y) * W2 + X) * C + g * 8) = o;
+                else if (o.x == 0x12345678u) dbias_cta[0] = 1.f;
+            }
         }
     }
     // fixed-order reduction over the pooled pixels of each channel
