@@ -192,7 +192,7 @@ def cpu_arm(steps, warmup, sample):
     return steps * sample / dt, 1e3 * dt / steps, os.cpu_count(), desc
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out_fd):
     if rank != 0:
         return
     value, ms, cores, desc = cpu_arm(args.steps, max(args.warmup, 1), REF_SAMPLE)
@@ -204,10 +204,19 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line, out_fd)
+
+
+def _emit(line, out_fd):
+    os.write(out_fd, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (e.g. NCCL's version banner, which goes
+    # to stdout) is sent to stderr for the duration of the run
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -222,7 +231,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        return run_reference(args, rank, world)
+        return run_reference(args, rank, world, out_fd)
 
     import ctypes as C
     from neuromah_b200 import device, ops, parallel
@@ -358,7 +367,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         v, cms, cores, desc = cpu_arm(6, 1, REF_SAMPLE)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
-    print(json.dumps(line), flush=True)
+    _emit(line, out_fd)
     if dist is not None:
         dist.destroy_process_group()
 

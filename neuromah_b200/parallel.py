@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 from ._lib import lib
-from .device import stream
+from .device import new_event, new_stream, stream
 
 
 def shard_bounds(n: int, rank: int, world: int):
@@ -58,6 +58,7 @@ class Communicator:
     def __init__(self, rank: int, world: int, unique_id: bytes | None = None):
         self.rank, self.world = rank, world
         self.handle = None
+        self.comm_stream = None          # side stream for all-reduces overlapped with the rest of backward
         if world == 1:
             return
         lib.nm_comm_load(find_libnccl().encode())
@@ -90,6 +91,25 @@ class Communicator:
 
     def allreduce_grads(self, arena):
         self.allreduce(arena.grads, arena.total)
+
+    def allreduce_async(self, arr, offset: int, count: int):
+        """SUM all-reduce of ``arr[offset : offset + count]`` (floats) on the communication stream, ordered after
+        everything enqueued on the compute stream so far; the compute stream keeps going.  ``wait()`` joins."""
+        if self.world == 1 or count <= 0:
+            return
+        if self.comm_stream is None:
+            self.comm_stream = new_stream()
+            self._ready, self._done = new_event(), new_event()
+        lib.nm_event_record(self._ready, stream())
+        lib.nm_stream_wait_event(self.comm_stream, self._ready)
+        lib.nm_comm_allreduce_sum_f32(self.handle, C.c_void_p(arr.ptr + 4 * offset), count, self.comm_stream)
+
+    def wait(self):
+        """Make the compute stream wait for every all-reduce issued with ``allreduce_async``."""
+        if self.world == 1 or self.comm_stream is None:
+            return
+        lib.nm_event_record(self._done, self.comm_stream)
+        lib.nm_stream_wait_event(stream(), self._done)
 
     def broadcast(self, arr, root=0, count=None):
         if self.world == 1:

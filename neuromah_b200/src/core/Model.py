@@ -141,13 +141,15 @@ class Model:
             gb = self.softmax_classifier_output.grad_batch
             output = self.plan.forward(as_device(batch_X), labels, accum=self._accum,
                                        inv_batch=None if gb is None else 1.0 / gb)
-            self.plan.backward(gb)
+            self.plan.backward(gb, comm=self.comm)
+            if self.comm is not None:
+                self.comm.wait()
         else:
             output = self.forward(batch_X, training=True)
             self._device_loss_acc(output, labels)
             self.backward(output, labels)
-        if self.comm is not None:
-            self.comm.allreduce_grads(self.arena)
+            if self.comm is not None:
+                self.comm.allreduce_grads(self.arena)
         self._optimizer_step()
         return output
 

@@ -165,7 +165,10 @@ class TcCnnPlan:
         self.model.softmax_classifier_output.dinputs = self.dlogits[0:B]
         return out
 
-    def backward(self, grad_batch=None):
+    def backward(self, grad_batch=None, comm=None):
+        """``comm``: data-parallel communicator.  The gradient slab is all-reduced in two buckets on the communication
+        stream: everything but the first conv's gradients as soon as conv2's wgrad has been enqueued (it then overlaps
+        conv2 dgrad + the whole conv1 backward), the first conv's 320 floats after the last kernel."""
         B = self.x.shape[0]
         s = stream()
         scale = 1.0 / (B if grad_batch is None else grad_batch)
@@ -178,6 +181,18 @@ class TcCnnPlan:
                                         self.c2.bias_gradients.p, self.ws.p, self.ws.nbytes, B, 7, 7, 64, self.n_out, s)
         _timed('tc_conv2_wgrad', lib.nm_tc_conv3x3_wgrad_bf16, self.act1_pad.p, self.dy2_pad.p, self.c2.weight_gradients.p, self.ws.p, self.ws.nbytes,
                                      B, 14, 14, 32, 64, s)
+        if comm is not None:
+            lo = self._first_conv_floats()
+            comm.allreduce_async(self.model.arena.grads, lo, self.model.arena.total - lo)
         _timed('tc_conv2_dgrad', lib.nm_tc_conv3x3_dgrad_bf16, self.dy2_pad.p, self.w2d.p, self.dp1.p, B, 14, 14, 32, 64, s)
         _timed('tc_conv1_bwd', lib.nm_tc_conv1_bwd_bf16, self.x.p, self.dp1.p, self.idx1.p, self.c1.weight_gradients.p, self.c1.bias_gradients.p,
                                  self.ws.p, self.ws.nbytes, B, 28, 28, 32, s)
+        if comm is not None:
+            comm.allreduce_async(self.model.arena.grads, 0, self._first_conv_floats())
+
+    def _first_conv_floats(self):
+        """Length (floats, padded) of the first conv's slice at the start of the arena slabs."""
+        for layer, _, off, _, _ in self.model.arena.table:
+            if layer is not self.c1:
+                return off
+        return self.model.arena.total
