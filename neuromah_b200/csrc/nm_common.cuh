@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstring>
 #include <atomic>
+#include <utility>
 #include "../../include/neuromah_b200.h"
 
 namespace nm {
@@ -44,6 +45,31 @@ inline int launched(const char* name, int n = 1) {
     do {                                                                \
         if (!(cond)) return nm::fail(NM_ERR_BAD_ARG, "%s: %s", __func__, msg); \
     } while (0)
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------
+// The kernels of a training step are launched with programmatic stream serialization: a kernel's CTAs may be
+// scheduled, and run their prologue (mbarrier init, TMEM allocation, tensor-map prefetch, shared-memory tables),
+// while the previous kernel in the stream is still draining.  Contract: pdl_trigger() first thing (lets the NEXT
+// kernel be scheduled as early as the hardware allows), pdl_wait() before the first access to global memory
+// (it returns once every prerequisite grid has completed and its writes are visible).
+namespace nm {
+template <typename... KArgs, typename... Args>
+inline int launch_pdl(const char* name, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    if (e != cudaSuccess) { cudaGetLastError(); return cuda_fail(e, name); }
+    return launched(name);
+}
+}  // namespace nm
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // Timing experiments only (scratch/ablate.py): -DNM_ABLATE=<bits> builds a variant library with parts of some kernels
 // switched off at COMPILE time; the product build (NM_ABLATE undefined) contains none of it.

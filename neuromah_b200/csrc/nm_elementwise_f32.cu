@@ -192,6 +192,8 @@ template <bool DEV>
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, AdamHP hp, const nm_adam_state* __restrict__ ds,
                             int n_apply) {
+    pdl_trigger();
+    pdl_wait();
     if (DEV) { hp.lr = ds->lr; hp.b1 = ds->beta1; hp.b2 = ds->beta2; hp.eps = ds->eps; hp.bc1 = ds->bc1; hp.bc2 = ds->bc2; }
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4, stride = (size_t)gridDim.x * blockDim.x * 4;
     const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
@@ -338,8 +340,8 @@ int nm_adam_step_f32(float* param, const float* grad, float* m, float* v, size_t
     NM_REQUIRE(n_apply >= 1, "n_apply must be >= 1");
     if (!n) return NM_OK;
     AdamHP hp{lr, beta1, beta2, eps, bc1, bc2};
-    adam_kernel<false><<<ew_blocks(n, 256, 4), 256, 0, nm::S(stream)>>>(param, grad, m, v, n, hp, nullptr, n_apply);
-    return nm::launched("adam_step_f32");
+    return nm::launch_pdl("adam_step", adam_kernel<false>, dim3(ew_blocks(n, 256, 4)), dim3(256), 0, nm::S(stream),
+                          param, grad, m, v, n, hp, (const nm_adam_state*)nullptr, n_apply);
 }
 
 int nm_adam_state_init(nm_adam_state* dev_state, float lr, float decay, float beta1,
@@ -354,8 +356,8 @@ int nm_adam_step_dev_f32(float* param, const float* grad, float* m, float* v, si
     NM_REQUIRE(param && grad && m && v && dev_state, "null pointer");
     NM_REQUIRE(n_apply >= 1, "n_apply must be >= 1");
     if (!n) return NM_OK;
-    adam_kernel<true><<<ew_blocks(n, 256, 4), 256, 0, nm::S(stream)>>>(param, grad, m, v, n, AdamHP{}, dev_state, n_apply);
-    return nm::launched("adam_step_dev_f32");
+    return nm::launch_pdl("adam_step_dev", adam_kernel<true>, dim3(ew_blocks(n, 256, 4)), dim3(256), 0, nm::S(stream),
+                          param, grad, m, v, n, AdamHP{}, dev_state, n_apply);
 }
 
 int nm_adam_advance_f32(nm_adam_state* dev_state, void* stream) {

@@ -1,4 +1,4 @@
-// bf16 tensor-core 3x3 'same' convolution for sm_100a: fprop (+ReLU +2x2 max-pool epilogue), dgrad, wgrad.
+// bf16 tensor-core 3x3 'same' convolution for sm_100a: dgrad and wgrad (fprop + ReLU + pool: nm_tc_conv_pool.cu).
 //
 // Implicit GEMM with NO im2col anywhere -- not in HBM, not in shared memory, not in the TMA:
 // activations live in HBM as zero-haloed NHWC bf16 [N, Hp=H+2, Wp=W+2, C].  For an M-tile of 128
@@ -16,6 +16,12 @@
 #include "nm_tc_host.cuh"
 #include <cstdlib>
 
+#ifdef NM_ABLATE   // timing experiments only
+#define NM_TRACE(P, tile, slot) do { if ((P).trace && blockIdx.x == 0) (P).trace[((tile) / gridDim.x) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define NM_TRACE(P, tile, slot) do { } while (0)
+#endif
+
 namespace {
 
 using namespace tc;
@@ -28,15 +34,12 @@ struct ConvTcParams {
     int a_rows;                        // 128 + 2*Wp + 2
     uint32_t a_stage_bytes;            // a_rows * row bytes, rounded up to 1024
     int n_stages;
-    void* out;                         // EPI 0: bf16 [rows_total][NOUT];  EPI 1: pooled bf16 NHWC
-    uint8_t* idx;                      // EPI 1: one nibble per pooled element: argmax (2 bits) | (value>0) << 2
-    int oHp, oWp, ooff;                // EPI 1: pooled output geometry (padded for a following conv, or dense)
-    long long* trace;                  // timing experiments only: CTA 0 records clock64() per tile and role
-    int debug;                         // timing experiments only (NM_TC_DEBUG): 1 = no shuffles, 2 = no stores, 4 = no MMA
+    void* out;                         // bf16 [rows_total][NOUT]
+    long long* trace;                  // timing experiments only (NM_ABLATE builds): CTA 0 records clock64() per tile and role
 };
 
 // ---------------------------------------------------------------------------------------------
-// fprop / dgrad:  D[128 pixels, NOUT] = sum_{tap} A[pixel + shift(tap), 0:CIN] * B[tap][NOUT, CIN]^T
+// dgrad (a correlation with the flipped, transposed filter):  D[128 pixels, NOUT] = sum_{tap} A[pixel + shift(tap), 0:CIN] * B[tap][NOUT, CIN]^T
 // ---------------------------------------------------------------------------------------------
 // FOLD (needs Wp == 16, plain-store epilogue): the three s-taps of a filter row are three N-chunks of ONE MMA
 // (N = 3*NOUT, the B blocks of taps 3r..3r+2 are contiguous rows), all reading the A rows shifted by r*Wp only;
@@ -44,7 +47,7 @@ struct ConvTcParams {
 // per value (a warp holds two complete 16-pixel grid rows and the last two pixels of a row are halo, so the shift
 // never crosses a warp).  The MMA is bound by the 128 B/cycle read of its 4 KB A slice, so tripling N is free:
 // 12 MMAs of 56 cycles per tile instead of 36 of 45 (profiles/r01_mma_rate.txt).
-template <int CIN, int NOUT, int EPI, bool FOLD>
+template <int CIN, int NOUT, bool FOLD>
 __global__ void __launch_bounds__(384, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvTcParams p) {
     constexpr int ROWB = CIN * 2;                                   // bytes per pixel row: 64 (SW64) or 128 (SW128)
@@ -55,7 +58,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     constexpr int B_TAP_BYTES = NOUT * ROWB;
     constexpr int B_BYTES = 9 * B_TAP_BYTES;
     static_assert(B_BYTES % 1024 == 0, "weight block must keep the A stages 1024-aligned");
-    static_assert(!FOLD || EPI == 0, "tap folding is implemented for the plain-store epilogue");
     constexpr int NACC = FOLD ? 3 * NOUT : NOUT;                    // accumulator columns per buffer
     // Four accumulator buffers: the hand-off chain commit -> epilogue wake-up -> tcgen05.ld -> arrive -> MMA wake-up is about
     // as long as one tile's MMAs, so with two buffers the tensor pipe idled between tiles (measured: MMA time added on top of
@@ -77,6 +79,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -89,6 +92,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
@@ -98,7 +102,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 mbar_wait(&empty[stage], phase ^ 1);
-                if (p.trace && blockIdx.x == 0) p.trace[(tile / gridDim.x) * 8 + 0] = clock64();
+                NM_TRACE(p, tile, 0);
                 mbar_expect_tx(&full[stage], (uint32_t)p.a_rows * ROWB);
                 tma_load_2d(a_smem + (size_t)stage * p.a_stage_bytes, &map_a, 0, tile * TILE_M, &full[stage]);
                 if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
@@ -120,9 +124,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int stage = it % p.n_stages, acc = it % NBUF;
             const uint32_t phase = (it / p.n_stages) & 1, acc_phase = (it / NBUF) & 1;
             mbar_wait(&tempty[acc], acc_phase ^ 1);
-            if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[(tile / gridDim.x) * 8 + 1] = clock64();
+            if (lane == 0) NM_TRACE(p, tile, 1);
             mbar_wait(&full[stage], phase);
-            if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[(tile / gridDim.x) * 8 + 2] = clock64();
+            if (lane == 0) NM_TRACE(p, tile, 2);
             fence_after_sync();
             if (elect_one()) {
                 // descriptor = template | (address >> 4): advancing the address is one add on the low word
@@ -151,7 +155,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 mma_commit(&tfull[acc]);            // accumulator ready for the epilogue
             }
             __syncwarp();
-            if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[(tile / gridDim.x) * 8 + 3] = clock64();
+            if (lane == 0) NM_TRACE(p, tile, 3);
         }
     } else if (warp >= 4) {
         // ============================== epilogue (two groups of 4 warps, alternating tiles) ==========
@@ -160,7 +164,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         int acc = grp; uint32_t acc_phase = 0;        // NBUF is even: a buffer always belongs to the same group
         for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x) {
             mbar_wait(&tfull[acc], acc_phase);
-            if (p.trace && blockIdx.x == 0 && lane == 0 && q == 0) p.trace[(tile / gridDim.x) * 8 + 4] = clock64();
+            if (lane == 0 && q == 0) NM_TRACE(p, tile, 4);
             fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NACC;
             uint32_t raw[NOUT];
@@ -176,17 +180,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[acc]);
-                if (p.debug & 1) {
-#pragma unroll
-                    for (int c = 0; c < NOUT; ++c)
-                        raw[c] = __float_as_uint(__uint_as_float(raw[c]) + (__uint_as_float(e1[c]) + __uint_as_float(e2[c])));
-                } else {
 #pragma unroll
                 for (int c = 0; c < NOUT; ++c)
                     raw[c] = __float_as_uint(__uint_as_float(raw[c]) +
                                              (__uint_as_float(__shfl_down_sync(0xffffffffu, e1[c], 1)) +
                                               __uint_as_float(__shfl_down_sync(0xffffffffu, e2[c], 2))));
-                }
             } else {
 #pragma unroll
                 for (int c = 0; c < NOUT; c += 16) tmem_ld_x16(taddr + c, raw + c);
@@ -196,12 +194,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator drained: MMA may overwrite it
             }
             acc += 2; if (acc >= NBUF) { acc -= NBUF; acc_phase ^= 1; }
-            if (p.trace && blockIdx.x == 0 && lane == 0 && q == 0) p.trace[(tile / gridDim.x) * 8 + 5] = clock64();
+            if (lane == 0 && q == 0) NM_TRACE(p, tile, 5);
 
-            if constexpr (EPI == 0) {
+            {
                 // plain bf16 store of the [pixel][NOUT] row (dgrad)
                 const long long row = (long long)tile * TILE_M + q * 32 + lane;
-                if (row < p.rows_total && !(p.debug & 2)) {
+                if (row < p.rows_total) {
                     uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row * NOUT);
 #pragma unroll
                     for (int c = 0; c < NOUT; c += 8) {
@@ -212,65 +210,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         o.w = pack_bf16x2(__uint_as_float(raw[c + 6]), __uint_as_float(raw[c + 7]));
                         dst[c / 8] = o;
                     }
-                }
-            } else {
-                // ReLU + 2x2/2 max-pool + arg-max nibble.  Wp == 16: a warp holds grid rows (2q, 2q+1) of the
-                // tile, lane = 16*dy + x, so a pool window is lanes {l, l^1, l^16, l^17}.  Two exchange stages
-                // leave lane (dy,dx) owning channels [ (NOUT/2)*dx + (NOUT/4)*dy, +NOUT/4 ) of its window.
-                static_assert(EPI == 0 || NOUT % 4 == 0, "pool epilogue needs NOUT % 4 == 0");
-                constexpr int HALF = NOUT / 2, QUART = NOUT / 4;
-                if (p.debug & 1) continue;
-                const int dx = lane & 1, dy = (lane >> 4) & 1;
-                float h[HALF];
-                uint32_t hsel = 0;
-#pragma unroll
-                for (int j = 0; j < HALF; ++j) {
-                    float lo = fmaxf(__uint_as_float(raw[j]), 0.f), hi = fmaxf(__uint_as_float(raw[HALF + j]), 0.f);
-                    float mine = dx ? hi : lo, send = dx ? lo : hi;
-                    float r = __shfl_xor_sync(0xffffffffu, send, 1);
-                    float left = dx ? r : mine, right = dx ? mine : r;     // scan order: (.,0) then (.,1)
-                    bool s = right > left;                                 // strict '>' keeps the first max
-                    h[j] = s ? right : left;
-                    hsel |= (uint32_t)s << j;
-                }
-                const uint32_t osel = __shfl_xor_sync(0xffffffffu, hsel, 16);
-                const uint32_t mysel = dy ? (hsel >> QUART) : hsel, othsel = dy ? (osel >> QUART) : osel;
-                float best[QUART];
-                uint32_t nib[QUART];
-#pragma unroll
-                for (int j = 0; j < QUART; ++j) {
-                    float mine = dy ? h[QUART + j] : h[j], send = dy ? h[j] : h[QUART + j];
-                    float r = __shfl_xor_sync(0xffffffffu, send, 16);
-                    float top = dy ? r : mine, bot = dy ? mine : r;        // scan order: row 0 then row 1
-                    uint32_t tsel = ((dy ? othsel : mysel) >> j) & 1u, bsel = ((dy ? mysel : othsel) >> j) & 1u;
-                    bool s = bot > top;
-                    best[j] = s ? bot : top;
-                    nib[j] = (s ? (2u | bsel) : tsel) | (best[j] > 0.f ? 4u : 0u);
-                }
-                const int tiles_per_img = (p.Hp * p.Wp) / TILE_M;
-                const int n = tile / tiles_per_img;
-                const int py = ((tile % tiles_per_img) * (TILE_M / 16)) / 2 + q, px = (lane & 15) >> 1;
-                if (py < p.H / 2 && px < p.W / 2 && !(p.debug & 2)) {
-                    const int cbase = HALF * dx + QUART * dy;
-                    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) +
-                        (((size_t)n * p.oHp + py + p.ooff) * p.oWp + px + p.ooff) * NOUT + cbase;
-                    uint32_t packed[QUART / 2];
-#pragma unroll
-                    for (int j = 0; j < QUART; j += 2) packed[j / 2] = pack_bf16x2(best[j], best[j + 1]);
-#pragma unroll
-                    for (int j = 0; j < QUART / 2; j += 4)
-                        *reinterpret_cast<uint4*>(o + 2 * j) = make_uint4(packed[j], packed[j + 1], packed[j + 2], packed[j + 3]);
-                    uint8_t* ip = p.idx + (((size_t)n * (p.H / 2) + py) * (p.W / 2) + px) * (NOUT / 2) + cbase / 2;
-                    uint32_t w[QUART / 8];
-#pragma unroll
-                    for (int j = 0; j < QUART; j += 8) {
-                        uint32_t x = 0;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) x |= nib[j + k] << (4 * k);
-                        w[j / 8] = x;
-                    }
-                    if constexpr (QUART == 16) *reinterpret_cast<uint2*>(ip) = make_uint2(w[0], w[1]);
-                    else *reinterpret_cast<uint32_t*>(ip) = w[0];
                 }
             }
         }
@@ -318,6 +257,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_dy); tma_prefetch_desc(&map_x); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -329,6 +269,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -409,6 +350,8 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                                            int n_cta, int COUT, int CIN) {
     __shared__ float red[4][64];
+    pdl_trigger();
+    pdl_wait();
     const int total = COUT * 9 * CIN;
     const int i = blockIdx.x * 64 + (threadIdx.x & 63), slice = threadIdx.x >> 6;
     const int per = (n_cta + 3) / 4, k0 = slice * per, k1 = min(n_cta, k0 + per);
@@ -435,6 +378,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 // OIHW f32 -> bf16 [OC][tap][C] (fprop B operand) and [C][tap'][OC] with tap' = 8 - tap (dgrad B operand)
 __global__ void pack_conv_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
                                          __nv_bfloat16* __restrict__ wd, int OC, int C) {
+    pdl_trigger();
+    pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= OC * C * 9) return;
     int oc = i / (C * 9), rem = i - oc * C * 9, c = rem / 9, tap = rem - c * 9;
@@ -443,7 +388,7 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, __nv_bfloa
     if (wd) wd[((size_t)c * 9 + (8 - tap)) * OC + oc] = v;
 }
 
-template <int CIN, int NOUT, int EPI, bool FOLD>
+template <int CIN, int NOUT, bool FOLD>
 int launch_conv(const void* a, const void* b, ConvTcParams p, int N, cudaStream_t st) {
     constexpr int ROWB = CIN * 2;
     CUtensorMap ma, mb;
@@ -460,32 +405,32 @@ int launch_conv(const void* a, const void* b, ConvTcParams p, int N, cudaStream_
         p.n_stages = forced > 0 ? forced : (fit > 12 ? 12 : fit);
     }
     size_t smem = 9 * NOUT * ROWB + (size_t)p.n_stages * p.a_stage_bytes + 512;   // + mbarriers
-    auto kern = conv3x3_tc_kernel<CIN, NOUT, EPI, FOLD>;
+    auto kern = conv3x3_tc_kernel<CIN, NOUT, FOLD>;
     static bool attr_set = false;
     if (!attr_set) {
         NM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
     }
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    kern<<<grid, 384, smem, st>>>(ma, mb, p);
-    return nm::launched("conv3x3_tc");
+    return nm::launch_pdl("conv3x3_tc", kern, dim3(grid), dim3(384), smem, st, ma, mb, p);
 }
 
 }  // namespace
 
 extern "C" {
 
+#ifdef NM_ABLATE
 static long long* g_conv_trace = nullptr;
 /* timing experiments only: CTA 0 of the next conv3x3 launches records clock64() per tile into buf[tiles][8] */
 int nm_tc_debug_set_trace(void* buf) { g_conv_trace = static_cast<long long*>(buf); return NM_OK; }
+#endif
 
 int nm_tc_pack_conv_weights_bf16(const float* w_oihw, void* w_fprop, void* w_dgrad, int OC, int C, void* stream) {
     NM_REQUIRE(w_oihw && (w_fprop || w_dgrad), "null pointer");
     NM_REQUIRE(OC > 0 && C > 0, "bad dimensions");
     int total = OC * C * 9;
-    pack_conv_weights_kernel<<<nm_cdiv(total, 256), 256, 0, nm::S(stream)>>>(
-        w_oihw, static_cast<__nv_bfloat16*>(w_fprop), static_cast<__nv_bfloat16*>(w_dgrad), OC, C);
-    return nm::launched("pack_conv_weights");
+    return nm::launch_pdl("pack_conv_weights", pack_conv_weights_kernel, dim3(nm_cdiv(total, 256)), dim3(256), 0, nm::S(stream),
+                          w_oihw, static_cast<__nv_bfloat16*>(w_fprop), static_cast<__nv_bfloat16*>(w_dgrad), OC, C);
 }
 
 int nm_tc_conv3x3_dgrad_bf16(const void* dy_pad, const void* w_packed_dgrad, void* dx_grid,
@@ -503,10 +448,11 @@ int nm_tc_conv3x3_dgrad_bf16(const void* dy_pad, const void* w_packed_dgrad, voi
     p.out = dx_grid;
     static int fold = -1;
     if (fold < 0) { const char* e = getenv("NM_TC_DGRAD_FOLD"); fold = e ? atoi(e) : 1; }
-    { const char* e = getenv("NM_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
+#ifdef NM_ABLATE
     p.trace = g_conv_trace;
-    if (fold && p.Wp == 16) return launch_conv<64, 32, 0, true>(dy_pad, w_packed_dgrad, p, N, nm::S(stream));
-    return launch_conv<64, 32, 0, false>(dy_pad, w_packed_dgrad, p, N, nm::S(stream));
+#endif
+    if (fold && p.Wp == 16) return launch_conv<64, 32, true>(dy_pad, w_packed_dgrad, p, N, nm::S(stream));
+    return launch_conv<64, 32, false>(dy_pad, w_packed_dgrad, p, N, nm::S(stream));
 }
 
 size_t nm_tc_conv3x3_wgrad_workspace(int C, int OC) {
@@ -549,13 +495,12 @@ int nm_tc_conv3x3_wgrad_bf16(const void* x_pad, const void* dy_pad, float* dw, v
         NM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<32, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
     }
-    if (fold) conv3x3_wgrad_tc_kernel<32, 64, true><<<grid, 256, smem, nm::S(stream)>>>(mdy, mx, p);
-    else conv3x3_wgrad_tc_kernel<32, 64, false><<<grid, 256, smem, nm::S(stream)>>>(mdy, mx, p);
-    rc = nm::launched("conv3x3_wgrad_tc");
+    rc = fold ? nm::launch_pdl("conv3x3_wgrad_tc", conv3x3_wgrad_tc_kernel<32, 64, true>, dim3(grid), dim3(256), smem, nm::S(stream), mdy, mx, p)
+              : nm::launch_pdl("conv3x3_wgrad_tc", conv3x3_wgrad_tc_kernel<32, 64, false>, dim3(grid), dim3(256), smem, nm::S(stream), mdy, mx, p);
     if (rc) return rc;
     int total = OC * 9 * C;
-    wgrad_reduce_kernel<<<nm_cdiv(total, 64), 256, 0, nm::S(stream)>>>(p.partial, dw, grid, OC, C);
-    return nm::launched("wgrad_reduce");
+    return nm::launch_pdl("wgrad_reduce", wgrad_reduce_kernel, dim3(nm_cdiv(total, 64)), dim3(256), 0, nm::S(stream),
+                          (const float*)p.partial, dw, grid, OC, C);
 }
 
 }  // extern "C"

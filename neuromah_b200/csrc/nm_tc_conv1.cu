@@ -101,21 +101,22 @@ conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + F_NBUF);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // Wext [128 (pos,oc)][16] bf16 -> B tile
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        const int row = i >> 1, c = i & 1;
-        *reinterpret_cast<uint4*>(b_smem + sw64(row, c * 16)) = __ldg(reinterpret_cast<const uint4*>(wext + row * 16 + c * 8));
-    }
-    fence_proxy_async();
+    pdl_trigger();
     if (threadIdx.x == 0) {
-        // builder barriers count WARPS: 128 per-thread mbarrier arrivals per tile serialise on one shared-memory word and
-        // were the whole pipeline's critical path (ablation: 29 us with the epilogue math and stores switched off)
+        // builder barriers count WARPS: 128 per-thread mbarrier arrivals per tile would serialise on one shared-memory word
         for (int s = 0; s < F_STAGES; ++s) { mbar_init(&afull[s], 4); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < F_XSTAGES; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 4); }
         for (int a = 0; a < F_NBUF; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         mbar_fence_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, F_NBUF * 128);
+    pdl_wait();
+    // Wext [128 (pos,oc)][16] bf16 -> B tile
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const int row = i >> 1, c = i & 1;
+        *reinterpret_cast<uint4*>(b_smem + sw64(row, c * 16)) = __ldg(reinterpret_cast<const uint4*>(wext + row * 16 + c * 8));
+    }
+    fence_proxy_async();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -250,6 +251,8 @@ conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
 
 // Wext[(dy,dx,oc)][a*4+b] = W[oc][a-dy][b-dx] inside the 3x3 support, else 0
 __global__ void pack_conv1_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wext) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 128 * 16) return;
     const int row = i >> 4, k = i & 15, pos = row >> 5, oc = row & 31, a = k >> 2, b = k & 3;
@@ -289,6 +292,7 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row_bytes = (G.PW + 2) * OC * 2;                              // one row of the dP grid
+    pdl_trigger();
 
     // constant half of every P row: column 16 = 1 (bias gradient), columns 17..31 = 0
     for (int i = threadIdx.x; i < B_STAGES * 128; i += blockDim.x) {
@@ -318,6 +322,7 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     const bool has_work = (int)blockIdx.x < G.num_tiles;
+    pdl_wait();
 
     if (warp == 17) {
         // ============================== bulk-copy producer ===================================
@@ -473,6 +478,8 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
 __global__ void __launch_bounds__(256)
 conv1_tc_bwd_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db, int n_cta) {
     __shared__ float red[8][32];
+    pdl_trigger();
+    pdl_wait();
     const int total = OC * 10;
     const int i = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
     const int per = (n_cta + 7) / 8, c0 = slice * per, c1 = min(n_cta, c0 + per);
@@ -519,8 +526,7 @@ extern "C" {
 int nm_tc_pack_conv1_weights_bf16(const float* w, void* w_ext, int OCn, void* stream) {
     NM_REQUIRE(w && w_ext, "null pointer");
     if (OCn != OC) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_pack_conv1_weights_bf16: only OC=32 is instantiated");
-    pack_conv1_weights_kernel<<<8, 256, 0, nm::S(stream)>>>(w, static_cast<__nv_bfloat16*>(w_ext));
-    return nm::launched("pack_conv1_weights");
+    return nm::launch_pdl("pack_conv1_weights", pack_conv1_weights_kernel, dim3(8), dim3(256), 0, nm::S(stream), w, static_cast<__nv_bfloat16*>(w_ext));
 }
 
 int nm_tc_conv1_fwd_pool_bf16(const float* x, const void* w_ext, void* y_pad, void* idx, int N, int H, int W, int OCn, void* stream) {
@@ -536,9 +542,8 @@ int nm_tc_conv1_fwd_pool_bf16(const float* x, const void* w_ext, void* y_pad, vo
     static bool attr = false;
     if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv1_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
     const int grid = g.num_tiles < sm_count() ? g.num_tiles : sm_count();
-    conv1_tc_fwd_kernel<<<grid, F_THREADS, smem, nm::S(stream)>>>(x, static_cast<const __nv_bfloat16*>(w_ext), static_cast<__nv_bfloat16*>(y_pad),
-                                                                 static_cast<uint8_t*>(idx), g, x_stage);
-    return nm::launched("conv1_tc_fwd");
+    return nm::launch_pdl("conv1_tc_fwd", conv1_tc_fwd_kernel, dim3(grid), dim3(F_THREADS), smem, nm::S(stream), x,
+                          static_cast<const __nv_bfloat16*>(w_ext), static_cast<__nv_bfloat16*>(y_pad), static_cast<uint8_t*>(idx), g, x_stage);
 }
 
 size_t nm_tc_conv1_bwd_workspace(int OCn) { (void)OCn; return (size_t)B_MAX_GRID * 128 * 32 * sizeof(float); }
@@ -563,12 +568,11 @@ int nm_tc_conv1_bwd_bf16(const float* x, const void* dp_grid, const void* idx, f
     if (smem > 220 * 1024) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_bwd_bf16: image too large for the staged-input ring");
     static bool attr = false;
     if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv1_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
-    conv1_tc_bwd_kernel<<<grid, B_THREADS, smem, nm::S(stream)>>>(x, static_cast<const __nv_bfloat16*>(dp_grid), static_cast<const uint8_t*>(idx),
-                                                                 static_cast<float*>(workspace), g, L);
-    int rc = nm::launched("conv1_tc_bwd");
+    int rc = nm::launch_pdl("conv1_tc_bwd", conv1_tc_bwd_kernel, dim3(grid), dim3(B_THREADS), smem, nm::S(stream), x,
+                            static_cast<const __nv_bfloat16*>(dp_grid), static_cast<const uint8_t*>(idx), static_cast<float*>(workspace), g, L);
     if (rc) return rc;
-    conv1_tc_bwd_reduce_kernel<<<nm_cdiv(OC * 10, 32), 256, 0, nm::S(stream)>>>(static_cast<const float*>(workspace), dw, db, grid);
-    return nm::launched("conv1_tc_bwd_reduce");
+    return nm::launch_pdl("conv1_tc_bwd_reduce", conv1_tc_bwd_reduce_kernel, dim3(nm_cdiv(OC * 10, 32)), dim3(256), 0, nm::S(stream),
+                          static_cast<const float*>(workspace), dw, db, grid);
 }
 
 }  // extern "C"

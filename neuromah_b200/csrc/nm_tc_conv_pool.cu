@@ -20,6 +20,12 @@
 #include "nm_tc_common.cuh"
 #include "nm_tc_host.cuh"
 
+#ifdef NM_ABLATE   // timing experiments only
+#define NM_TRACE(P, tile, slot) do { if ((P).trace && blockIdx.x == 0) (P).trace[((tile) / gridDim.x) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define NM_TRACE(P, tile, slot) do { } while (0)
+#endif
+
 namespace {
 
 using namespace tc;
@@ -58,6 +64,7 @@ conv3x3_pool_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     uint64_t* bfull = tempty + NBUF;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w); }
     if (warp == 1 && lane == 0) {
@@ -71,6 +78,7 @@ conv3x3_pool_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
@@ -81,7 +89,7 @@ conv3x3_pool_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 mbar_wait(&empty[stage], phase ^ 1);
-                if (p.trace && blockIdx.x == 0) p.trace[(tile / gridDim.x) * 8 + 0] = clock64();
+                NM_TRACE(p, tile, 0);
                 mbar_expect_tx(&full[stage], STAGE_BYTES);
                 // two boxes of 144 pair-rows (a TMA box dimension is at most 256); rows past the tensor read as zero
                 tma_load_2d(a_smem + stage * STAGE_BYTES, &map_x, 0, tile * 256, &full[stage]);
@@ -137,7 +145,7 @@ conv3x3_pool_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                 }
                 mma_commit(&empty[stage]);
                 mma_commit(&tfull[acc]);
-                if (p.trace && blockIdx.x == 0) p.trace[(tile / gridDim.x) * 8 + 3] = clock64();
+                NM_TRACE(p, tile, 3);
             }
         }
         __syncwarp();
@@ -154,7 +162,7 @@ conv3x3_pool_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             __nv_bfloat16* yo = p.out + (((size_t)n * p.oHp + py + p.ooff) * p.oWp + px + p.ooff) * COUT;
             uint32_t* io = reinterpret_cast<uint32_t*>(p.idx + (((size_t)n * 7 + py) * 7 + px) * (COUT / 2));
             mbar_wait(&tfull[grp], (it / NBUF) & 1);
-            if (p.trace && blockIdx.x == 0 && lane == 0 && q == 0 && half == 0) p.trace[(tile / gridDim.x) * 8 + 4] = clock64();
+            if (lane == 0 && q == 0 && half == 0) NM_TRACE(p, tile, 4);
             fence_after_sync();
 #pragma unroll
             for (int hh = 0; hh < COUT / 32; ++hh) {
@@ -168,7 +176,7 @@ conv3x3_pool_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                     fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[grp]);
-                    if (p.trace && blockIdx.x == 0 && lane == 0 && q == 0 && half == 0) p.trace[(tile / gridDim.x) * 8 + 5] = clock64();
+                    if (lane == 0 && q == 0 && half == 0) NM_TRACE(p, tile, 5);
                 }
                 float best[16];
                 uint32_t nl = 0, nh = 0;
@@ -206,9 +214,11 @@ conv3x3_pool_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
 
 extern "C" {
 
+#ifdef NM_ABLATE
 static long long* g_pool_trace = nullptr;
 /* timing experiments only */
 int nm_tc_debug_set_trace_pool(void* buf) { g_pool_trace = static_cast<long long*>(buf); return NM_OK; }
+#endif
 
 int nm_tc_conv3x3_fprop_pool_bf16(const void* x_pad, const void* w_packed, void* y, void* idx,
                                   int N, int H, int W, int C, int OC, int out_padded, void* stream) {
@@ -219,7 +229,9 @@ int nm_tc_conv3x3_fprop_pool_bf16(const void* x_pad, const void* w_packed, void*
     PoolConvParams p{};
     p.N = N; p.num_tiles = (N + 1) / 2;
     p.out = static_cast<__nv_bfloat16*>(y); p.idx = static_cast<uint8_t*>(idx);
+#ifdef NM_ABLATE
     p.trace = g_pool_trace;
+#endif
     p.oHp = out_padded ? 9 : 7; p.oWp = p.oHp; p.ooff = out_padded ? 1 : 0;
     // x_pad [N,16,16,32] bf16 as rows of pixel pairs: [N*128][64]
     CUtensorMap mx, mw;
@@ -231,8 +243,7 @@ int nm_tc_conv3x3_fprop_pool_bf16(const void* x_pad, const void* w_packed, void*
     static bool attr = false;
     if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv3x3_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    conv3x3_pool_tc_kernel<<<grid, THREADS, smem, nm::S(stream)>>>(mx, mw, p);
-    return nm::launched("conv3x3_pool_tc");
+    return nm::launch_pdl("conv3x3_pool_tc", conv3x3_pool_tc_kernel, dim3(grid), dim3(THREADS), smem, nm::S(stream), mx, mw, p);
 }
 
 }  // extern "C"

@@ -43,6 +43,7 @@ dense_head_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb0 = blockIdx.y * p.per_split, kb1 = min(p.kblocks, kb0 + p.per_split);
+    pdl_trigger();
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w); }
     if (warp == 1 && lane == 0) {
@@ -55,6 +56,7 @@ dense_head_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -119,6 +121,8 @@ dense_head_finalize_kernel(const float* __restrict__ partial, int n_split, const
                            __nv_bfloat16* __restrict__ dl_hilo, float* __restrict__ sample_loss, int32_t* __restrict__ correct,
                            double* __restrict__ block_part, unsigned* __restrict__ counter, double* __restrict__ accum,
                            int B, int n_out, float inv_batch) {
+    pdl_trigger();
+    pdl_wait();
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     float loss = 0.f, corr = 0.f;
     if (row < B) {
@@ -201,6 +205,8 @@ dense_head_finalize_kernel(const float* __restrict__ partial, int n_split, const
 //   whl  bf16 [32][K]      rows [0,16) = hi, [16,32) = lo, rows >= n_out zero          (may be NULL)
 __global__ void pack_dense_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, __nv_bfloat16* __restrict__ whl,
                                           int K, int n_out, int HW, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= K * kNO) return;
     const int j = i / K, k = i % K, hw = k / C, ch = k % C;
@@ -215,6 +221,8 @@ __global__ void pack_dense_weights_kernel(const float* __restrict__ w, float* __
 
 // f32 dlogits [B][n_out] -> bf16 hi/lo [B][32] (public-API backward after a label-free forward)
 __global__ void pack_dlogits_kernel(const float* __restrict__ dl, __nv_bfloat16* __restrict__ hilo, int B, int n_out) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * kNO) return;
     const int row = i / kNO, j = i % kNO;
@@ -244,6 +252,7 @@ dense_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rb0 = blockIdx.y * p.per_split, rb1 = min(p.rblocks, rb0 + p.per_split);
+    pdl_trigger();
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_dl); }
     if (warp == 1 && lane == 0) {
@@ -256,6 +265,7 @@ dense_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -318,6 +328,8 @@ __global__ void __launch_bounds__(256)
 dense_wgrad_finish_kernel(const float* __restrict__ partial, int n_split, const float* __restrict__ dlogits,
                           const float* __restrict__ w, float* __restrict__ dw, float* __restrict__ db,
                           int B, int K, int n_out, int HW, int C, float scale, float l1, float l2, int dw_blocks) {
+    pdl_trigger();
+    pdl_wait();
     if ((int)blockIdx.x < dw_blocks) {
         const int i = blockIdx.x * blockDim.x + threadIdx.x;
         if (i >= K * kNO) return;
@@ -372,16 +384,15 @@ extern "C" {
 int nm_tc_pack_dense_weights(const float* w, float* w_packed, void* w_hilo, int K, int n_out, int HW, int C, void* stream) {
     NM_REQUIRE(w && (w_packed || w_hilo), "null pointer");
     NM_REQUIRE(K > 0 && n_out > 0 && n_out <= kNO && HW > 0 && C > 0 && HW * C == K, "bad dimensions");
-    pack_dense_weights_kernel<<<nm_cdiv((size_t)K * kNO, 256), 256, 0, nm::S(stream)>>>(
-        w, w_packed, static_cast<__nv_bfloat16*>(w_hilo), K, n_out, HW, C);
-    return nm::launched("pack_dense_weights");
+    return nm::launch_pdl("pack_dense_weights", pack_dense_weights_kernel, dim3(nm_cdiv((size_t)K * kNO, 256)), dim3(256), 0, nm::S(stream),
+                          w, w_packed, static_cast<__nv_bfloat16*>(w_hilo), K, n_out, HW, C);
 }
 
 int nm_tc_pack_dlogits_bf16(const float* dlogits, void* dl_hilo, int B, int n_out, void* stream) {
     NM_REQUIRE(dlogits && dl_hilo, "null pointer");
     NM_REQUIRE(B > 0 && n_out > 0 && n_out <= kNO, "bad dimensions");
-    pack_dlogits_kernel<<<nm_cdiv((size_t)B * kNO, 256), 256, 0, nm::S(stream)>>>(dlogits, static_cast<__nv_bfloat16*>(dl_hilo), B, n_out);
-    return nm::launched("pack_dlogits");
+    return nm::launch_pdl("pack_dlogits", pack_dlogits_kernel, dim3(nm_cdiv((size_t)B * kNO, 256)), dim3(256), 0, nm::S(stream),
+                          dlogits, static_cast<__nv_bfloat16*>(dl_hilo), B, n_out);
 }
 
 size_t nm_tc_dense_softmax_ce_workspace(int B, int K) {
@@ -415,13 +426,11 @@ int nm_tc_dense_softmax_ce_bf16(const void* x, const void* w_hilo, const float* 
     const size_t smem = (size_t)FWD_STAGES * FWD_STAGE + 256;
     static bool attr = false;
     if (!attr) { NM_CUDA(cudaFuncSetAttribute(dense_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-    dense_head_tc_kernel<<<dim3(mtiles, splits), 192, smem, nm::S(stream)>>>(mx, mw, p);
-    rc = nm::launched("dense_head_tc");
+    rc = nm::launch_pdl("dense_head_tc", dense_head_tc_kernel, dim3(mtiles, splits), dim3(192), smem, nm::S(stream), mx, mw, p);
     if (rc) return rc;
-    dense_head_finalize_kernel<<<mtiles, 128, 0, nm::S(stream)>>>(p.partial, splits, bias, labels, probs, dlogits,
-                                                                 static_cast<__nv_bfloat16*>(dl_hilo), sample_loss, correct,
-                                                                 block_part, counter, accum, B, n_out, inv_batch);
-    return nm::launched("dense_head_finalize");
+    return nm::launch_pdl("dense_head_finalize", dense_head_finalize_kernel, dim3(mtiles), dim3(128), 0, nm::S(stream),
+                          (const float*)p.partial, splits, bias, labels, probs, dlogits, static_cast<__nv_bfloat16*>(dl_hilo),
+                          sample_loss, correct, block_part, counter, accum, B, n_out, inv_batch);
 }
 
 size_t nm_tc_dense_wgrad_workspace(int B, int K) {
@@ -449,13 +458,11 @@ int nm_tc_dense_wgrad_bf16(const void* x, const void* dl_hilo, const float* dlog
     const size_t smem = (size_t)WG_STAGES * WG_STAGE + 256;
     static bool attr = false;
     if (!attr) { NM_CUDA(cudaFuncSetAttribute(dense_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-    dense_wgrad_tc_kernel<<<dim3((K + 63) / 64, splits), 192, smem, nm::S(stream)>>>(mx, mdl, p);
-    rc = nm::launched("dense_wgrad_tc");
+    rc = nm::launch_pdl("dense_wgrad_tc", dense_wgrad_tc_kernel, dim3((K + 63) / 64, splits), dim3(192), smem, nm::S(stream), mx, mdl, p);
     if (rc) return rc;
     const int dw_blocks = nm_cdiv((size_t)K * kNO, 256);
-    dense_wgrad_finish_kernel<<<dw_blocks + n_out, 256, 0, nm::S(stream)>>>(p.partial, splits, dlogits, w, dw, db, B, K, n_out,
-                                                                            HW, C, scale, l1, l2, dw_blocks);
-    return nm::launched("dense_wgrad_finish");
+    return nm::launch_pdl("dense_wgrad_finish", dense_wgrad_finish_kernel, dim3(dw_blocks + n_out), dim3(256), 0, nm::S(stream),
+                          (const float*)p.partial, splits, dlogits, w, dw, db, B, K, n_out, HW, C, scale, l1, l2, dw_blocks);
 }
 
 }  // extern "C"

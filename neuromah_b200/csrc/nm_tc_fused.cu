@@ -25,6 +25,8 @@ dense_bwd_unpool_kernel(const float* __restrict__ dlogits, const float* __restri
                         __nv_bfloat16* __restrict__ dy_pad, float* __restrict__ dbias_cta, int B, int PH, int PW, int C,
                         int n_out) {
     extern __shared__ float red[];                       // [items][8] for the bias-gradient reduction
+    pdl_trigger();
+    pdl_wait();
     const int K = PH * PW * C, G = C / 8, items = PH * PW * G;
     const int item = threadIdx.x;
     const bool active = item < items;
@@ -109,6 +111,8 @@ dense_bwd_unpool_kernel(const float* __restrict__ dlogits, const float* __restri
 // out[c] = sum_n in[n][c], fixed-shape tree -> deterministic
 __global__ void column_sum_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int C) {
     __shared__ float red[256];
+    pdl_trigger();
+    pdl_wait();
     const int c = blockIdx.x;
     float s = 0.f;
     for (int n = threadIdx.x; n < N; n += 256) s += in[(size_t)n * C + c];
@@ -140,14 +144,12 @@ int nm_tc_dense_bwd_unpool_bf16(const float* dlogits, const float* w_packed, con
     const uint8_t* ip = static_cast<const uint8_t*>(idx);
     __nv_bfloat16* dyp = static_cast<__nv_bfloat16*>(dy_pad);
     float* part = static_cast<float*>(workspace);
-    if (n_out <= 10)     // the [n_out x 8] weight slice lives in registers: instantiate the common head width exactly
-        dense_bwd_unpool_kernel<10><<<grid, 416, smem, nm::S(stream)>>>(dlogits, w_packed, ip, dyp, part, B, PH, PW, C, n_out);
-    else
-        dense_bwd_unpool_kernel<kNO><<<grid, 416, smem, nm::S(stream)>>>(dlogits, w_packed, ip, dyp, part, B, PH, PW, C, n_out);
-    int rc = nm::launched("dense_bwd_unpool");
+    // the [n_out x 8] weight slice lives in registers: instantiate the common head width exactly
+    int rc = n_out <= 10
+        ? nm::launch_pdl("dense_bwd_unpool", dense_bwd_unpool_kernel<10>, dim3(grid), dim3(416), smem, nm::S(stream), dlogits, w_packed, ip, dyp, part, B, PH, PW, C, n_out)
+        : nm::launch_pdl("dense_bwd_unpool", dense_bwd_unpool_kernel<kNO>, dim3(grid), dim3(416), smem, nm::S(stream), dlogits, w_packed, ip, dyp, part, B, PH, PW, C, n_out);
     if (rc) return rc;
-    column_sum_kernel<<<C, 256, 0, nm::S(stream)>>>(static_cast<const float*>(workspace), dbias, grid, C);
-    return nm::launched("column_sum");
+    return nm::launch_pdl("column_sum", column_sum_kernel, dim3(C), dim3(256), 0, nm::S(stream), (const float*)part, dbias, grid, C);
 }
 
 }  // extern "C"
