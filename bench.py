@@ -62,6 +62,7 @@ def kernel_work(name, b):
     table = {
         # bf16 plan: activations bf16 NHWC with halo (256 grid pixels / image for the 14x14 maps)
         "tc_conv2_fprop_pool": (c2, b * (256 * 64 + 49 * 128 + 49 * 32) + 64 * 288 * 2),
+        "tc_conv2_bwd": (2 * c2, b * (256 * 128 + 256 * 64 + 256 * 64) + 64 * 288 * 6),
         "tc_conv2_dgrad": (c2, b * (256 * 128 + 256 * 64) + 64 * 288 * 2),
         "tc_conv2_wgrad": (c2, b * (256 * 128 + 256 * 64) + 64 * 288 * 4),
         "tc_conv1_fwd_pool": (c1, b * (784 * 4 + 196 * 64 + 196 * 16)),

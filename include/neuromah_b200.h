@@ -203,6 +203,11 @@ int nm_tc_conv3x3_dgrad_bf16(const void* dy_pad, const void* w_packed_dgrad, voi
 size_t nm_tc_conv3x3_wgrad_workspace(int C, int OC);
 int nm_tc_conv3x3_wgrad_bf16(const void* x_pad, const void* dy_pad, float* dw, void* workspace, size_t workspace_bytes,
                              int N, int H, int W, int C, int OC, void* stream);
+/* dgrad AND wgrad of the 3x3 conv in one pass over dY (the same shared-memory dY tile is the K-major operand of the
+ * dgrad MMAs and the MN-major operand of the wgrad MMAs).  Same inputs/outputs as the two calls above. */
+size_t nm_tc_conv3x3_bwd_workspace(int C, int OC);
+int nm_tc_conv3x3_bwd_bf16(const void* x_pad, const void* dy_pad, const void* w_packed_dgrad, float* dw, void* dx_grid,
+                           void* workspace, size_t workspace_bytes, int N, int H, int W, int C, int OC, void* stream);
 
 /* First conv of the net (C_in = 1, 3x3 'same', ReLU, no bias) + MaxPooling2D(2,2) on tcgen05: the 4x4 input patch of a
  * pool window is the K = 16 dimension and the weights are expanded to Wext[(window position, oc)][4x4] (zero outside the

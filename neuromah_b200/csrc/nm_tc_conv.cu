@@ -344,6 +344,186 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused backward of the 3x3 conv: dgrad AND wgrad from ONE pass over dY.
+//   dX[p, c]      = sum_{tap} dY[p + shift(tap), :] . Wd[tap][c, :]          (K-major A = dY tile, tap-folded N = 96)
+//   dW[oc, tap,c] = sum_p dY[p, oc] * X[p + shift(tap) - (Wp+1), c]          (MN-major A = the SAME dY tile)
+// The dY tile (128 pixels + halo, 128-byte rows, SWIZZLE_128B) is read by the dgrad MMAs as a K-major operand and by
+// the wgrad MMAs as an MN-major one -- the shared-memory image is identical, only the instruction descriptor differs --
+// so dY (the largest tensor of the backward pass) crosses L2 once instead of twice and one kernel prologue/tail
+// disappears.  TMEM: nine wgrad accumulators (288 columns, resident for the CTA's whole pixel range) + two dgrad
+// accumulators of 96 columns.  Wp == 16, C = 32, OC = 64.
+// ---------------------------------------------------------------------------------------------
+struct ConvBwdParams {
+    int num_tiles, rows_total;
+    void* dx;                            // bf16 [rows_total][32]  (un-shifted grid)
+    float* partial;                      // [gridDim.x][64][288]
+};
+
+constexpr int BW_C = 32, BW_OC = 64, BW_WP = 16;
+constexpr int BW_ROWS = TILE_M + 2 * BW_WP + 2;                       // 162
+constexpr int BW_DY_BYTES = ((BW_ROWS * 128 + 1023) / 1024) * 1024;   // 21 KB
+constexpr int BW_X_BYTES = ((BW_ROWS * 64 + 1023) / 1024) * 1024;     // 11 KB
+constexpr int BW_STAGE = BW_DY_BYTES + BW_X_BYTES;                    // 32 KB
+constexpr int BW_W_BYTES = 9 * BW_C * 128;                            // 36 KB: dgrad weights [tap][c][oc]
+constexpr int BW_STAGES = 5;
+constexpr int BW_DACC = 3 * BW_C;                                     // 96 dgrad accumulator columns per buffer
+
+__global__ void __launch_bounds__(384, 1)
+conv3x3_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                      const __grid_constant__ CUtensorMap map_w, ConvBwdParams p) {
+    constexpr uint64_t TMPL_128 = desc_template(16, 1024, LAYOUT_SW128);        // dY (K-major or MN-major) and Wd
+    constexpr uint64_t TMPL_X3 = desc_template(64, 512, LAYOUT_SW64);           // X, MN-major, three 32-channel chunks one pixel apart
+    constexpr uint32_t IDESC_D = idesc_bf16(TILE_M, BW_DACC, 0, 0);             // dgrad: M = 128 pixels, N = 96
+    constexpr uint32_t IDESC_W = idesc_bf16(BW_OC, 3 * BW_C, 1, 1);             // wgrad: M = 64 oc, N = 96, both MN-major
+    constexpr uint32_t WCOLS = 9 * BW_C;                                        // 288
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* w_smem = smem;
+    uint8_t* st_smem = smem + BW_W_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(st_smem + BW_STAGES * BW_STAGE);
+    uint64_t* empty = full + BW_STAGES;
+    uint64_t* tfull = empty + BW_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* wfull = tempty + 2;
+    uint64_t* done = wfull + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_dy); tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < BW_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        mbar_init(wfull, 1);
+        mbar_init(done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            mbar_expect_tx(wfull, BW_W_BYTES);
+            for (int tap = 0; tap < 9; ++tap) tma_load_2d(w_smem + tap * (BW_C * 128), &map_w, tap * BW_OC, 0, wfull);
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* st = st_smem + (size_t)stage * BW_STAGE;
+                mbar_expect_tx(&full[stage], BW_ROWS * 128 + BW_ROWS * 64);
+                tma_load_2d(st, &map_dy, 0, tile * TILE_M, &full[stage]);
+                tma_load_2d(st + BW_DY_BYTES, &map_x, 0, tile * TILE_M - (BW_WP + 1), &full[stage]);   // OOB rows read as 0
+                if (++stage == BW_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ================================
+        mbar_wait(wfull, 0);
+        if (elect_one()) {
+            const uint64_t w_desc0 = desc_at(TMPL_128, smem_u32(w_smem));
+            int it = 0;
+            if ((int)blockIdx.x < p.num_tiles) mbar_wait(&full[0], 0);          // tempty[0]: fresh barrier, nothing to wait for
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int stage = it % BW_STAGES, acc = it & 1;
+                fence_after_sync();
+                const uint32_t st = smem_u32(st_smem + (size_t)stage * BW_STAGE);
+                const uint64_t dy_desc0 = desc_at(TMPL_128, st);
+                const uint64_t x_desc0 = desc_at(TMPL_X3, st + BW_DY_BYTES);
+                // ---- dgrad: three filter rows x four k-steps, N = 96 (the three s-taps), accumulator buffer `acc`
+                const uint32_t d_addr = tmem_base + WCOLS + acc * BW_DACC;
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int kk = 0; kk < BW_OC / 16; ++kk)
+                        mma_bf16(d_addr, dy_desc0 + ((r * BW_WP * 128 + kk * 32) >> 4), w_desc0 + ((3 * r * BW_C * 128 + kk * 32) >> 4),
+                                 IDESC_D, (r | kk) != 0);
+                mma_commit(&tfull[acc]);
+                // ---- wgrad: eight k-steps of 16 pixels x three filter rows, N = 96, accumulators resident
+#pragma unroll
+                for (int ks = 0; ks < TILE_M / 16; ++ks) {
+                    if (ks == TILE_M / 16 - 1 && tile + (int)gridDim.x < p.num_tiles) {
+                        // next tile: its dgrad accumulator must be drained and its data must have landed; done here the
+                        // waits hide under the MMAs still queued
+                        const int nit = it + 1;
+                        mbar_wait(&tempty[nit & 1], ((nit >> 1) & 1) ^ 1);
+                        mbar_wait(&full[nit % BW_STAGES], (nit / BW_STAGES) & 1);
+                    }
+                    const uint64_t adesc = dy_desc0 + ((ks * 16 * 128) >> 4);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+                        mma_bf16(tmem_base + r * 3 * BW_C, adesc, x_desc0 + (((r * BW_WP + ks * 16) * 64) >> 4), IDESC_W,
+                                 !(it == 0 && ks == 0));
+                }
+                mma_commit(&empty[stage]);
+            }
+            mma_commit(done);
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ============================== dgrad epilogue: two groups of 4 warps, alternating tiles ======
+        const int q = warp & 3, grp = (warp - 4) >> 2;
+        int it = grp;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
+            mbar_wait(&tfull[grp], (it >> 1) & 1);
+            fence_after_sync();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + WCOLS + grp * BW_DACC;
+            uint32_t e0[BW_C], e1[BW_C], e2[BW_C];
+#pragma unroll
+            for (int c = 0; c < BW_C; c += 16) {
+                tmem_ld_x16(taddr + c, e0 + c);
+                tmem_ld_x16(taddr + BW_C + c, e1 + c);
+                tmem_ld_x16(taddr + 2 * BW_C + c, e2 + c);
+            }
+            tmem_ld_wait();
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[grp]);
+            // out[p] = E[p][s=0] + E[p+1][s=1] + E[p+2][s=2]: a warp holds two complete 16-pixel grid rows whose last two
+            // pixels are halo, so the shift never crosses the warp
+#pragma unroll
+            for (int c = 0; c < BW_C; ++c)
+                e0[c] = __float_as_uint(__uint_as_float(e0[c]) + (__uint_as_float(__shfl_down_sync(0xffffffffu, e1[c], 1)) +
+                                                                 __uint_as_float(__shfl_down_sync(0xffffffffu, e2[c], 2))));
+            const long long row = (long long)tile * TILE_M + q * 32 + lane;
+            if (row < p.rows_total) {
+                uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.dx) + row * BW_C);
+#pragma unroll
+                for (int c = 0; c < BW_C; c += 8)
+                    dst[c / 8] = make_uint4(pack_bf16x2(__uint_as_float(e0[c + 0]), __uint_as_float(e0[c + 1])),
+                                            pack_bf16x2(__uint_as_float(e0[c + 2]), __uint_as_float(e0[c + 3])),
+                                            pack_bf16x2(__uint_as_float(e0[c + 4]), __uint_as_float(e0[c + 5])),
+                                            pack_bf16x2(__uint_as_float(e0[c + 6]), __uint_as_float(e0[c + 7])));
+            }
+        }
+        // ============================== wgrad epilogue: nine [64 x 32] accumulators -> one FP32 partial per CTA ===
+        if (warp < 8) {
+            const bool has_work = (int)blockIdx.x < p.num_tiles;
+            if (has_work) { mbar_wait(done, 0); fence_after_sync(); }
+            // M = 64 accumulator rows sit in lanes (m%16) + 32*(m/16): lanes 0..15 of each sub-partition
+            float* dst = p.partial + ((size_t)blockIdx.x * BW_OC + 16 * q + lane) * WCOLS;
+            for (int c = 0; c < (int)WCOLS; c += 16) {
+                uint32_t raw[16];
+                if (has_work) { tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + c, raw); tmem_ld_wait(); }
+                if (lane < 16) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(dst + c + j) = has_work
+                            ? make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 // dw[oc][c][r][s] = sum_cta partial[cta][oc][(r*3+s)*CIN + c]      (fixed order => deterministic)
 // 64 consecutive outputs per block (coalesced 256-byte rows), 4 slices of the CTA range per output, combined in
 // a fixed order through shared memory.
@@ -499,6 +679,41 @@ int nm_tc_conv3x3_wgrad_bf16(const void* x_pad, const void* dy_pad, float* dw, v
               : nm::launch_pdl("conv3x3_wgrad_tc", conv3x3_wgrad_tc_kernel<32, 64, false>, dim3(grid), dim3(256), smem, nm::S(stream), mdy, mx, p);
     if (rc) return rc;
     int total = OC * 9 * C;
+    return nm::launch_pdl("wgrad_reduce", wgrad_reduce_kernel, dim3(nm_cdiv(total, 64)), dim3(256), 0, nm::S(stream),
+                          (const float*)p.partial, dw, grid, OC, C);
+}
+
+size_t nm_tc_conv3x3_bwd_workspace(int C, int OC) { return (size_t)sm_count() * OC * 9 * C * sizeof(float); }
+
+int nm_tc_conv3x3_bwd_bf16(const void* x_pad, const void* dy_pad, const void* w_packed_dgrad, float* dw, void* dx_grid,
+                           void* workspace, size_t workspace_bytes, int N, int H, int W, int C, int OC, void* stream) {
+    NM_REQUIRE(x_pad && dy_pad && w_packed_dgrad && dw && dx_grid && workspace, "null pointer");
+    NM_REQUIRE(N > 0, "bad batch");
+    if (!(C == BW_C && OC == BW_OC && W + 2 == BW_WP))
+        return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv3x3_bwd_bf16: only C=32, OC=64, W=14 is instantiated");
+    ConvBwdParams p{};
+    p.rows_total = N * (H + 2) * BW_WP;
+    p.num_tiles = (p.rows_total + TILE_M - 1) / TILE_M;
+    p.dx = dx_grid;
+    p.partial = static_cast<float*>(workspace);
+    const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    NM_REQUIRE(workspace_bytes >= (size_t)grid * OC * 9 * C * sizeof(float), "workspace too small");
+    CUtensorMap mdy, mx, mw;
+    int rc = make_map_2d(&mdy, dy_pad, BW_OC, (uint64_t)p.rows_total, 128, BW_OC, BW_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map_2d(&mx, x_pad, BW_C, (uint64_t)p.rows_total, 64, BW_C, BW_ROWS, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    rc = make_map_2d(&mw, w_packed_dgrad, 9 * BW_OC, BW_C, 9 * 128, BW_OC, BW_C, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    const size_t smem = (size_t)BW_W_BYTES + (size_t)BW_STAGES * BW_STAGE + 512;
+    static bool attr_set = false;
+    if (!attr_set) {
+        NM_CUDA(cudaFuncSetAttribute(conv3x3_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set = true;
+    }
+    rc = nm::launch_pdl("conv3x3_bwd_tc", conv3x3_bwd_tc_kernel, dim3(grid), dim3(384), smem, nm::S(stream), mdy, mx, mw, p);
+    if (rc) return rc;
+    const int total = OC * 9 * C;
     return nm::launch_pdl("wgrad_reduce", wgrad_reduce_kernel, dim3(nm_cdiv(total, 64)), dim3(256), 0, nm::S(stream),
                           (const float*)p.partial, dw, grid, OC, C);
 }

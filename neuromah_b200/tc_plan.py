@@ -126,7 +126,7 @@ class TcCnnPlan:
         self.dl_hilo = z((B, 32), np.uint16)                 # dlogits as bf16 hi | lo (tcgen05 Dense wgrad operand)
         self.w3p = DeviceArray((self.n_out, K), np.float32)
         self.w3hl = z((32, K), np.uint16)                    # Dense weights as bf16 hi | lo rows (tcgen05 Dense fprop operand)
-        ws = max(lib.nm_tc_conv3x3_wgrad_workspace(32, 64), lib.nm_tc_conv1_bwd_workspace(32),
+        ws = max(lib.nm_tc_conv3x3_wgrad_workspace(32, 64), lib.nm_tc_conv3x3_bwd_workspace(32, 64), lib.nm_tc_conv1_bwd_workspace(32),
                  lib.nm_tc_dense_wgrad_workspace(B, K), lib.nm_tc_dense_bwd_unpool_workspace(64))
         self.ws = DeviceArray((ws,), np.uint8)
         self.ws_head = z((lib.nm_tc_dense_softmax_ce_workspace(B, K),), np.uint8)   # zero-filled once (ticket counter)
@@ -179,12 +179,12 @@ class TcCnnPlan:
                                    float(self.de.weight_regularizer_l1), float(self.de.weight_regularizer_l2), s)
         _timed('tc_dense_bwd_unpool', lib.nm_tc_dense_bwd_unpool_bf16, self.dlogits.p, self.w3p.p, self.idx2.p, self.dy2_pad.p,
                                         self.c2.bias_gradients.p, self.ws.p, self.ws.nbytes, B, 7, 7, 64, self.n_out, s)
-        _timed('tc_conv2_wgrad', lib.nm_tc_conv3x3_wgrad_bf16, self.act1_pad.p, self.dy2_pad.p, self.c2.weight_gradients.p, self.ws.p, self.ws.nbytes,
-                                     B, 14, 14, 32, 64, s)
+        # conv2 dgrad + wgrad in one pass over dY2
+        _timed('tc_conv2_bwd', lib.nm_tc_conv3x3_bwd_bf16, self.act1_pad.p, self.dy2_pad.p, self.w2d.p, self.c2.weight_gradients.p,
+               self.dp1.p, self.ws.p, self.ws.nbytes, B, 14, 14, 32, 64, s)
         if comm is not None:
             lo = self._first_conv_floats()
             comm.allreduce_async(self.model.arena.grads, lo, self.model.arena.total - lo)
-        _timed('tc_conv2_dgrad', lib.nm_tc_conv3x3_dgrad_bf16, self.dy2_pad.p, self.w2d.p, self.dp1.p, B, 14, 14, 32, 64, s)
         _timed('tc_conv1_bwd', lib.nm_tc_conv1_bwd_bf16, self.x.p, self.dp1.p, self.idx1.p, self.c1.weight_gradients.p, self.c1.bias_gradients.p,
                                  self.ws.p, self.ws.nbytes, B, 28, 28, 32, s)
         if comm is not None:

@@ -128,6 +128,32 @@ def test_tc_conv_wgrad(n, integer):
     np.testing.assert_array_equal(dw.numpy(), dw2.numpy())
 
 
+@pytest.mark.parametrize("n,integer", [(2, True), (300, True), (41, False)])
+def test_tc_conv_fused_backward(n, integer):
+    """dgrad + wgrad from one pass over dY (nm_tc_conv3x3_bwd_bf16) equals the two separate kernels' references."""
+    from neuromah_b200._lib import lib
+    from neuromah_b200.device import DeviceArray, stream
+    rng, x, w = _setup(n, 40 + n, integer)
+    _, wg = _pack(w)
+    dy = (rng.integers(-2, 3, (n, 64, 14, 14)) if integer else bf16_round(rng.standard_normal((n, 64, 14, 14)))).astype(np.float32)
+    xp, dyp = DeviceArray.from_numpy(pad_nhwc(x)), DeviceArray.from_numpy(pad_nhwc(dy))
+    dw = DeviceArray.zeros((64, 32, 3, 3))
+    dx = DeviceArray.zeros((n, 16, 16, 32), np.uint16)
+    ws = DeviceArray((lib.nm_tc_conv3x3_bwd_workspace(32, 64),), np.uint8)
+    lib.nm_tc_conv3x3_bwd_bf16(xp.p, dyp.p, wg.p, dw.p, dx.p, ws.p, ws.nbytes, n, 14, 14, 32, 64, stream())
+    dx_ref, dw_ref, _ = R.conv_layer_backward(x, w, None, dy, padding="same", relu=False, mode="wired", dtype=np.float64)
+    got = from_bf16_bits(dx.numpy())[:, :14, :14, :].transpose(0, 3, 1, 2)
+    if integer:
+        np.testing.assert_array_equal(got, bf16_round(dx_ref.astype(np.float32)))
+        np.testing.assert_array_equal(dw.numpy(), dw_ref.astype(np.float32))
+    else:
+        np.testing.assert_allclose(got, dx_ref, rtol=2 ** -7, atol=2e-2)
+        np.testing.assert_allclose(dw.numpy(), dw_ref, rtol=1e-4, atol=1e-2)
+    dw2 = DeviceArray.zeros((64, 32, 3, 3))                        # deterministic: bitwise repeatable
+    lib.nm_tc_conv3x3_bwd_bf16(xp.p, dyp.p, wg.p, dw2.p, dx.p, ws.p, ws.nbytes, n, 14, 14, 32, 64, stream())
+    np.testing.assert_array_equal(dw.numpy(), dw2.numpy())
+
+
 # ------------------------------------------------------------------ tcgen05 Dense head ----
 def _dense_case(B, K, n_out, hw, c, seed, integer):
     rng = np.random.default_rng(seed)
