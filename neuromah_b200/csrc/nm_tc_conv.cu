@@ -375,8 +375,14 @@ conv3x3_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
     constexpr uint64_t TMPL_128 = desc_template(16, 1024, LAYOUT_SW128);        // dY (K-major or MN-major) and Wd
     constexpr uint64_t TMPL_X3 = desc_template(64, 512, LAYOUT_SW64);           // X, MN-major, three 32-channel chunks one pixel apart
     constexpr uint32_t IDESC_D = idesc_bf16(TILE_M, BW_DACC, 0, 0);             // dgrad: M = 128 pixels, N = 96
-    constexpr uint32_t IDESC_W = idesc_bf16(BW_OC, 3 * BW_C, 1, 1);             // wgrad: M = 64 oc, N = 96, both MN-major
-    constexpr uint32_t WCOLS = 9 * BW_C;                                        // 288
+    // wgrad: filter rows r = 1 and r = 0 share ONE M = 128 MMA: the second 64-oc chunk of the MN-major A operand is the dY
+    // tile shifted by one grid row (leading byte offset = Wp rows), which pairs it with the filter row above; its pixel
+    // range is shifted by Wp too, but the tiles of all CTAs still cover every pixel exactly once (the first Wp rows of
+    // the tensor are halo).  Row r = 2 is a separate M = 64 MMA.  Per 16 pixels: 56 + 48 cycles instead of 3 x 48.
+    constexpr uint64_t TMPL_DY2 = desc_template(BW_WP * 128, 1024, LAYOUT_SW128);
+    constexpr uint32_t IDESC_W2 = idesc_bf16(2 * BW_OC, 3 * BW_C, 1, 1);        // M = 128 = (row pair, oc), N = 96, both MN-major
+    constexpr uint32_t IDESC_W1 = idesc_bf16(BW_OC, 3 * BW_C, 1, 1);            // M = 64 oc
+    constexpr uint32_t WCOLS = 2 * 3 * BW_C;                                    // 192: [0,96) rows {1,0}, [96,192) row 2
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_smem = smem;
@@ -433,6 +439,7 @@ conv3x3_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
                 fence_after_sync();
                 const uint32_t st = smem_u32(st_smem + (size_t)stage * BW_STAGE);
                 const uint64_t dy_desc0 = desc_at(TMPL_128, st);
+                const uint64_t dy_desc2 = desc_at(TMPL_DY2, st);
                 const uint64_t x_desc0 = desc_at(TMPL_X3, st + BW_DY_BYTES);
                 // ---- dgrad: three filter rows x four k-steps, N = 96 (the three s-taps), accumulator buffer `acc`
                 const uint32_t d_addr = tmem_base + WCOLS + acc * BW_DACC;
@@ -453,11 +460,10 @@ conv3x3_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
                         mbar_wait(&tempty[nit & 1], ((nit >> 1) & 1) ^ 1);
                         mbar_wait(&full[nit % BW_STAGES], (nit / BW_STAGES) & 1);
                     }
-                    const uint64_t adesc = dy_desc0 + ((ks * 16 * 128) >> 4);
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)
-                        mma_bf16(tmem_base + r * 3 * BW_C, adesc, x_desc0 + (((r * BW_WP + ks * 16) * 64) >> 4), IDESC_W,
-                                 !(it == 0 && ks == 0));
+                    mma_bf16(tmem_base, dy_desc2 + ((ks * 16 * 128) >> 4), x_desc0 + (((1 * BW_WP + ks * 16) * 64) >> 4), IDESC_W2,
+                             !(it == 0 && ks == 0));
+                    mma_bf16(tmem_base + 3 * BW_C, dy_desc0 + ((ks * 16 * 128) >> 4), x_desc0 + (((2 * BW_WP + ks * 16) * 64) >> 4), IDESC_W1,
+                             !(it == 0 && ks == 0));
                 }
                 mma_commit(&empty[stage]);
             }
@@ -500,21 +506,38 @@ conv3x3_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
                                             pack_bf16x2(__uint_as_float(e0[c + 6]), __uint_as_float(e0[c + 7])));
             }
         }
-        // ============================== wgrad epilogue: nine [64 x 32] accumulators -> one FP32 partial per CTA ===
+        // ============================== wgrad epilogue: accumulators -> one FP32 partial [64][288] per CTA ===
         if (warp < 8) {
             const bool has_work = (int)blockIdx.x < p.num_tiles;
             if (has_work) { mbar_wait(done, 0); fence_after_sync(); }
-            // M = 64 accumulator rows sit in lanes (m%16) + 32*(m/16): lanes 0..15 of each sub-partition
-            float* dst = p.partial + ((size_t)blockIdx.x * BW_OC + 16 * q + lane) * WCOLS;
-            for (int c = 0; c < (int)WCOLS; c += 16) {
-                uint32_t raw[16];
-                if (has_work) { tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + c, raw); tmem_ld_wait(); }
-                if (lane < 16) {
+            float* part = p.partial + (size_t)blockIdx.x * BW_OC * (9 * BW_C);
+            // M = 128 accumulator (columns [0,96)): lane L = 64*j + oc holds filter row r = 1 - j
+            {
+                const int L = q * 32 + lane, j = L >> 6, oc = L & 63;
+                float* dst = part + (size_t)oc * (9 * BW_C) + (1 - j) * 3 * BW_C;
+                for (int c = 0; c < 3 * BW_C; c += 16) {
+                    uint32_t raw[16];
+                    if (has_work) { tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + c, raw); tmem_ld_wait(); }
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(dst + c + j) = has_work
-                            ? make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]))
+                    for (int jj = 0; jj < 16; jj += 4)
+                        *reinterpret_cast<float4*>(dst + c + jj) = has_work
+                            ? make_float4(__uint_as_float(raw[jj]), __uint_as_float(raw[jj + 1]), __uint_as_float(raw[jj + 2]), __uint_as_float(raw[jj + 3]))
                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            // M = 64 accumulator (columns [96,192)), filter row 2: rows sit in lanes (m%16) + 32*(m/16), lanes 0..15 of each sub-partition
+            {
+                float* dst = part + (size_t)(16 * q + lane) * (9 * BW_C) + 2 * 3 * BW_C;
+                for (int c = 0; c < 3 * BW_C; c += 16) {
+                    uint32_t raw[16];
+                    if (has_work) { tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + 3 * BW_C + c, raw); tmem_ld_wait(); }
+                    if (lane < 16) {
+#pragma unroll
+                        for (int jj = 0; jj < 16; jj += 4)
+                            *reinterpret_cast<float4*>(dst + c + jj) = has_work
+                                ? make_float4(__uint_as_float(raw[jj]), __uint_as_float(raw[jj + 1]), __uint_as_float(raw[jj + 2]), __uint_as_float(raw[jj + 3]))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
             }
         }
