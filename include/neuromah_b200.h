@@ -228,6 +228,9 @@ int nm_tc_conv1_bwd_bf16(const float* x, const void* dp_grid, const void* idx, f
  *   w_hilo  bf16 [32][K]: rows [0,16) = bf16(w), rows [16,32) = bf16(w - bf16(w)), classes >= n_out zero
  *           (tcgen05 B operand; the hi/lo pair keeps ~16 mantissa bits of the weights; may be NULL) */
 int nm_tc_pack_dense_weights(const float* w, float* w_packed, void* w_hilo, int K, int n_out, int HW, int C, void* stream);
+/* The three packs of the CNN plan (conv1 Wext, conv2 fprop/dgrad operands, Dense packed + hi/lo) in ONE launch. */
+int nm_tc_pack_cnn_weights_bf16(const float* w1, void* w1_ext, const float* w2, void* w2_fprop, void* w2_dgrad, int OC2, int C2,
+                                const float* w3, float* w3_packed, void* w3_hilo, int K, int n_out, int HW, int C3, void* stream);
 /* f32 dlogits [B][n_out] -> bf16 hi/lo [B][32] (only needed when dlogits did not come from nm_tc_dense_softmax_ce_bf16) */
 int nm_tc_pack_dlogits_bf16(const float* dlogits, void* dl_hilo, int B, int n_out, void* stream);
 /* Layer_Dense.forward + Activation_Softmax + CCE losses + accuracy flags + fused gradient (p-onehot)*inv_batch

@@ -84,6 +84,7 @@ _SIGS = {
     "nm_tc_conv1_bwd_workspace": (_sz, [_i]),
     "nm_tc_conv1_bwd_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp]),
     "nm_tc_pack_dense_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "nm_tc_pack_cnn_weights_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "nm_tc_pack_dlogits_bf16": (_i, [_vp, _vp, _i, _i, _vp]),
     "nm_tc_dense_softmax_ce_workspace": (_sz, [_i, _i]),
     "nm_tc_dense_softmax_ce_bf16": (_i, [_vp] * 11 + [_sz, _i, _i, _i, _f, _vp]),

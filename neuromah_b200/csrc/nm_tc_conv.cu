@@ -14,6 +14,7 @@
 #include "nm_common.cuh"
 #include "nm_tc_common.cuh"
 #include "nm_tc_host.cuh"
+#include "nm_tc_pack.cuh"
 #include <cstdlib>
 
 #ifdef NM_ABLATE   // timing experiments only
@@ -584,11 +585,7 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, __nv_bfloa
     pdl_trigger();
     pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= OC * C * 9) return;
-    int oc = i / (C * 9), rem = i - oc * C * 9, c = rem / 9, tap = rem - c * 9;
-    __nv_bfloat16 v = __float2bfloat16(w[i]);
-    if (wf) wf[((size_t)oc * 9 + tap) * C + c] = v;
-    if (wd) wd[((size_t)c * 9 + (8 - tap)) * OC + oc] = v;
+    if (i < OC * C * 9) tcpack::conv3x3_elem(i, w, wf, wd, OC, C);
 }
 
 template <int CIN, int NOUT, bool FOLD>

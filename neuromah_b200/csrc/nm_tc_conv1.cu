@@ -23,6 +23,7 @@
 #include "nm_common.cuh"
 #include "nm_tc_common.cuh"
 #include "nm_tc_host.cuh"
+#include "nm_tc_pack.cuh"
 
 #ifdef NM_ABLATE   // timing experiments only: CTA 0 records clock64() per tile and role
 #define NM_TRACE(G, tile, slot) do { if ((G).trace && blockIdx.x == 0) (G).trace[((tile) / gridDim.x) * 8 + (slot)] = clock64(); } while (0)
@@ -254,11 +255,7 @@ __global__ void pack_conv1_weights_kernel(const float* __restrict__ w, __nv_bflo
     pdl_trigger();
     pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 128 * 16) return;
-    const int row = i >> 4, k = i & 15, pos = row >> 5, oc = row & 31, a = k >> 2, b = k & 3;
-    const int r = a - (pos >> 1), s = b - (pos & 1);
-    const float v = ((unsigned)r < 3u && (unsigned)s < 3u) ? w[oc * 9 + r * 3 + s] : 0.f;
-    wext[i] = __float2bfloat16(v);
+    if (i < 128 * 16) tcpack::conv1_elem(i, w, wext);
 }
 
 // ---------------------------------------------------------------------------------------------

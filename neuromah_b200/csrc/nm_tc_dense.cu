@@ -15,6 +15,7 @@
 #include "nm_common.cuh"
 #include "nm_tc_common.cuh"
 #include "nm_tc_host.cuh"
+#include "nm_tc_pack.cuh"
 
 namespace {
 
@@ -208,15 +209,7 @@ __global__ void pack_dense_weights_kernel(const float* __restrict__ w, float* __
     pdl_trigger();
     pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= K * kNO) return;
-    const int j = i / K, k = i % K, hw = k / C, ch = k % C;
-    const float v = j < n_out ? w[(size_t)(ch * HW + hw) * n_out + j] : 0.f;
-    if (wp && j < n_out) wp[i] = v;
-    if (whl) {
-        const __nv_bfloat16 h = __float2bfloat16(v);
-        whl[(size_t)j * K + k] = h;
-        whl[(size_t)(kNO + j) * K + k] = __float2bfloat16(v - __bfloat162float(h));
-    }
+    if (i < K * kNO) tcpack::dense_elem(i, w, wp, whl, K, n_out, HW, C);
 }
 
 // f32 dlogits [B][n_out] -> bf16 hi/lo [B][32] (public-API backward after a label-free forward)

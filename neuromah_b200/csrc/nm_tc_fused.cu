@@ -22,8 +22,8 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 template <int NO>
 __global__ void __launch_bounds__(416, 1)
 dense_bwd_unpool_kernel(const float* __restrict__ dlogits, const float* __restrict__ wp, const uint8_t* __restrict__ idx,
-                        __nv_bfloat16* __restrict__ dy_pad, float* __restrict__ dbias_cta, int B, int PH, int PW, int C,
-                        int n_out) {
+                        __nv_bfloat16* __restrict__ dy_pad, float* __restrict__ dbias_cta, float* __restrict__ dbias,
+                        unsigned* __restrict__ ticket, int B, int PH, int PW, int C, int n_out) {
     extern __shared__ float red[];                       // [items][8] for the bias-gradient reduction
     pdl_trigger();
     pdl_wait();
@@ -106,20 +106,21 @@ dense_bwd_unpool_kernel(const float* __restrict__ dlogits, const float* __restri
         for (int p2 = 0; p2 < PH * PW; ++p2) s += red[(p2 * G + gg) * 8 + c];
         dbias_cta[(size_t)blockIdx.x * C + threadIdx.x] = s;
     }
-}
-
-// out[c] = sum_n in[n][c], fixed-shape tree -> deterministic
-__global__ void column_sum_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int C) {
-    __shared__ float red[256];
-    pdl_trigger();
-    pdl_wait();
-    const int c = blockIdx.x;
-    float s = 0.f;
-    for (int n = threadIdx.x; n < N; n += 256) s += in[(size_t)n * C + c];
-    red[threadIdx.x] = s;
+    // the last CTA to finish sums the per-CTA partials in CTA order (deterministic) -- no separate reduction launch
+    __shared__ bool last;
+    __threadfence();
     __syncthreads();
-    for (int o = 128; o; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
-    if (threadIdx.x == 0) out[c] = red[0];
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        if ((int)threadIdx.x < C) {
+            float s = 0.f;
+            for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(dbias_cta + (size_t)b * C + threadIdx.x);
+            dbias[threadIdx.x] = s;
+        }
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
 }
 
 constexpr int kNO = 16;
@@ -145,11 +146,11 @@ int nm_tc_dense_bwd_unpool_bf16(const float* dlogits, const float* w_packed, con
     __nv_bfloat16* dyp = static_cast<__nv_bfloat16*>(dy_pad);
     float* part = static_cast<float*>(workspace);
     // the [n_out x 8] weight slice lives in registers: instantiate the common head width exactly
-    int rc = n_out <= 10
-        ? nm::launch_pdl("dense_bwd_unpool", dense_bwd_unpool_kernel<10>, dim3(grid), dim3(416), smem, nm::S(stream), dlogits, w_packed, ip, dyp, part, B, PH, PW, C, n_out)
-        : nm::launch_pdl("dense_bwd_unpool", dense_bwd_unpool_kernel<kNO>, dim3(grid), dim3(416), smem, nm::S(stream), dlogits, w_packed, ip, dyp, part, B, PH, PW, C, n_out);
-    if (rc) return rc;
-    return nm::launch_pdl("column_sum", column_sum_kernel, dim3(C), dim3(256), 0, nm::S(stream), (const float*)part, dbias, grid, C);
+    static unsigned* ticket = nullptr;             // last-block ticket, left at zero by every launch (one device per process)
+    if (!ticket) { NM_CUDA(cudaMalloc(&ticket, sizeof(unsigned))); NM_CUDA(cudaMemset(ticket, 0, sizeof(unsigned))); }
+    return n_out <= 10
+        ? nm::launch_pdl("dense_bwd_unpool", dense_bwd_unpool_kernel<10>, dim3(grid), dim3(416), smem, nm::S(stream), dlogits, w_packed, ip, dyp, part, dbias, ticket, B, PH, PW, C, n_out)
+        : nm::launch_pdl("dense_bwd_unpool", dense_bwd_unpool_kernel<kNO>, dim3(grid), dim3(416), smem, nm::S(stream), dlogits, w_packed, ip, dyp, part, dbias, ticket, B, PH, PW, C, n_out);
 }
 
 }  // extern "C"

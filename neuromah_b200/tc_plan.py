@@ -134,10 +134,12 @@ class TcCnnPlan:
     def pack_weights(self):
         """Refresh the bf16 / permuted operand copies from the FP32 master weights in the arena."""
         s = stream()
-        lib.nm_tc_pack_conv1_weights_bf16(self.c1.weights.p, self.w1e.p, 32, s)
-        lib.nm_tc_pack_conv_weights_bf16(self.c2.weights.p, self.w2f.p, self.w2d.p, 64, 32, s)
         if self.w3p is not None:
-            lib.nm_tc_pack_dense_weights(self.de.weights.p, self.w3p.p, self.w3hl.p, self.K, self.n_out, 49, 64, s)
+            lib.nm_tc_pack_cnn_weights_bf16(self.c1.weights.p, self.w1e.p, self.c2.weights.p, self.w2f.p, self.w2d.p, 64, 32,
+                                            self.de.weights.p, self.w3p.p, self.w3hl.p, self.K, self.n_out, 49, 64, s)
+        else:
+            lib.nm_tc_pack_conv1_weights_bf16(self.c1.weights.p, self.w1e.p, 32, s)
+            lib.nm_tc_pack_conv_weights_bf16(self.c2.weights.p, self.w2f.p, self.w2d.p, 64, 32, s)
 
     # ------------------------------------------------------------------ passes ----
     def forward(self, x: DeviceArray, labels=None, accum=None, inv_batch=None):
