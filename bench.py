@@ -282,16 +282,19 @@ def main():
     n_dev = min(n_host, 8)
     x_dev = device.DeviceArray.from_numpy(host_x.array[:n_dev * B])
     y_dev = device.DeviceArray.from_numpy(labels[:n_dev * B])
+    x_b = [x_dev[i * B:(i + 1) * B] for i in range(n_dev)]      # stable views: the step's CUDA graph is keyed by pointer
+    y_b = [y_dev[i * B:(i + 1) * B] for i in range(n_dev)]
+    for s in range(2 * n_dev):                                  # untimed priming: every batch once eagerly, once captured
+        model.train_step(x_b[s % n_dev], y_b[s % n_dev])
     for s in range(W):
-        model.train_step(x_dev[(s % n_dev) * B:(s % n_dev + 1) * B], y_dev[(s % n_dev) * B:(s % n_dev + 1) * B])
+        model.train_step(x_b[s % n_dev], y_b[s % n_dev])
     e0, e1 = device.new_event(), device.new_event()
     barrier()
     launches0 = device.launch_count()
     t_wall0 = time.time()
     lib.nm_event_record(e0, device.stream())
     for s in range(K):
-        i = s % n_dev
-        model.train_step(x_dev[i * B:(i + 1) * B], y_dev[i * B:(i + 1) * B])
+        model.train_step(x_b[s % n_dev], y_b[s % n_dev])
     lib.nm_event_record(e1, device.stream())
     device.synchronize()
     t_wall1 = time.time()
@@ -311,8 +314,7 @@ def main():
     ops.timers = ops.KernelTimers()
     lib.nm_event_record(e0, device.stream())
     for s in range(K2):
-        i = s % n_dev
-        model.train_step(x_dev[i * B:(i + 1) * B], y_dev[i * B:(i + 1) * B])
+        model.train_step(x_b[s % n_dev], y_b[s % n_dev])
     lib.nm_event_record(e1, device.stream())
     device.synchronize()
     lib.nm_event_elapsed_ms(e0, e1, C.byref(ms))
@@ -323,7 +325,7 @@ def main():
     # ---------------- end-to-end leg: Model.train from pinned host memory ------------------------
     # K steps = (K // n_host) epochs over the n_host pinned batches + one partial pass; every step copies its
     # batch host->device and reads the running loss/accuracy sums back (16 bytes)
-    n_warm = min(W, n_host)
+    n_warm = min(max(W, 4), n_host)       # >= 4 steps: both feeder slots are seen twice, i.e. their step graphs are captured
     model.train(host_x.array[:n_warm * B], labels[:n_warm * B], epochs=1, batch_size=B, verbose=0, stream_batches=True)
     full, rem = divmod(K, n_host)
     h2d = d2h = 0

@@ -1,6 +1,8 @@
 // Device / memory / stream / event / graph plumbing of the C ABI (include/neuromah_b200.h).
 #include "nm_common.cuh"
 #include <cuda_profiler_api.h>
+#include <mutex>
+#include <unordered_map>
 
 namespace nm {
 thread_local char g_err[512] = "";
@@ -97,8 +99,14 @@ int nm_stream_wait_event(void* stream, void* event) {
     return NM_OK;
 }
 
+// kernels captured per graph, so that nm_launch_count() also counts launches replayed from a graph
+static std::mutex g_graph_mu;
+static std::unordered_map<void*, unsigned long long> g_graph_kernels;
+static thread_local unsigned long long g_capture_start = 0;
+
 int nm_graph_begin(void* stream) {
     NM_CUDA(cudaStreamBeginCapture(nm::S(stream), cudaStreamCaptureModeThreadLocal));
+    g_capture_start = nm::g_launches.load();
     return NM_OK;
 }
 int nm_graph_end(void* stream, void** graph_exec) {
@@ -110,14 +118,25 @@ int nm_graph_end(void* stream, void** graph_exec) {
     cudaGraphDestroy(g);
     if (e != cudaSuccess) return nm::cuda_fail(e, "cudaGraphInstantiate");
     *graph_exec = ge;
+    const unsigned long long captured = nm::g_launches.load() - g_capture_start;
+    nm::g_launches.fetch_sub(captured);           // captured, not executed: they count when the graph is launched
+    std::lock_guard<std::mutex> lk(g_graph_mu);
+    g_graph_kernels[ge] = captured;
     return NM_OK;
 }
 int nm_graph_launch(void* graph_exec, void* stream) {
     NM_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, nm::S(stream)));
+    std::lock_guard<std::mutex> lk(g_graph_mu);
+    auto it = g_graph_kernels.find(graph_exec);
+    if (it != g_graph_kernels.end()) nm::g_launches.fetch_add(it->second);
     return NM_OK;
 }
 int nm_graph_destroy(void* graph_exec) {
-    if (graph_exec) NM_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    if (graph_exec) {
+        NM_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+        std::lock_guard<std::mutex> lk(g_graph_mu);
+        g_graph_kernels.erase(graph_exec);
+    }
     return NM_OK;
 }
 

@@ -223,8 +223,11 @@ __global__ void adam_state_init_kernel(nm_adam_state* s, float lr, float decay, 
 
 // post_update_params (Adam.py:103-107) + next step's pre_update_params (:41-47), on the device
 __global__ void adam_advance_kernel(nm_adam_state* s) {
+    pdl_trigger();
+    pdl_wait();
     s->iterations += 1;
-    s->beta1_pow *= (double)s->beta1; s->beta2_pow *= (double)s->beta2;
+    s->beta1_pow = pow((double)s->beta1, (double)(s->iterations + 1));      // same formula as the host (Adam.py:94-95),
+    s->beta2_pow = pow((double)s->beta2, (double)(s->iterations + 1));      // not a running product: no drift between the paths
     s->bc1 = (float)(1.0 - s->beta1_pow); s->bc2 = (float)(1.0 - s->beta2_pow);
     if (s->decay != 0.f) s->lr = (float)((double)s->base_lr * (1.0 / (1.0 + (double)s->decay * (double)s->iterations)));
 }
@@ -362,8 +365,7 @@ int nm_adam_step_dev_f32(float* param, const float* grad, float* m, float* v, si
 
 int nm_adam_advance_f32(nm_adam_state* dev_state, void* stream) {
     NM_REQUIRE(dev_state, "null pointer");
-    adam_advance_kernel<<<1, 1, 0, nm::S(stream)>>>(dev_state);
-    return nm::launched("adam_advance");
+    return nm::launch_pdl("adam_advance", adam_advance_kernel, dim3(1), dim3(1), 0, nm::S(stream), dev_state);
 }
 
 int nm_sgd_step_f32(float* param, const float* grad, float* mom, size_t n,

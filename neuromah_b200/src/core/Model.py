@@ -134,9 +134,53 @@ class Model:
         """Accumulate sum of CCE losses and #correct for this batch on the device."""
         ops.softmax_ce(output, labels, want_grad=False, accum=self._accum, holder=self)
 
+    # ------------------------------------------------------------ CUDA-graph replay of the fused step ----
+    graph_steps = True          # replay the tensor-core plan's training step from a CUDA graph when possible
+
+    def _graph_train_step(self, x, labels):
+        """The whole step (re-pack, forward, loss sums, backward, Adam, on-device advance) as ONE graph launch.
+        A graph is captured per (input pointer, label pointer, batch) the second time that triple is seen -- the
+        streamed feeder alternates between two device slots, so two graphs serve a whole epoch."""
+        opt = self.optimizer
+        key = (x.ptr, labels.ptr, x.shape[0], self.softmax_classifier_output.grad_batch)
+        graphs = self.__dict__.setdefault("_graphs", {})
+        seen = self.__dict__.setdefault("_graph_seen", set())
+        g = graphs.get(key)
+        if g is None and (key not in seen or x.shape[0] > self.plan.B):
+            seen.add(key)
+            return None                                    # first sighting (buffers, lazy allocations): run eagerly
+        if g is None and len(graphs) >= 16:                # bounded cache: drop the oldest graph
+            lib.nm_graph_destroy(graphs.pop(next(iter(graphs))))
+        dev_state = opt.sync_device_state()
+        n_apply = next(iter(set(self._n_apply.values())))
+        if g is None:
+            gb = self.softmax_classifier_output.grad_batch
+            g = C.c_void_p()
+            lib.nm_graph_begin(stream())
+            try:
+                self.plan.forward(x, labels, accum=self._accum, inv_batch=None if gb is None else 1.0 / gb)
+                self.plan.backward(gb)
+                opt.update_arena_dev(self.arena, n_apply=n_apply)
+            finally:
+                lib.nm_graph_end(stream(), C.byref(g))
+            graphs[key] = g
+        lib.nm_graph_launch(g, stream())
+        opt.host_advance()
+        return self.plan.probs[0:x.shape[0]]
+
+    def _graph_ok(self):
+        opt = self.optimizer
+        return (self.graph_steps and self.plan is not None and self.comm is None and ops.timers is None
+                and hasattr(opt, "update_arena_dev") and len(set(self._n_apply.values())) == 1
+                and getattr(self.plan, "B", 0) > 0)
+
     def train_step(self, batch_X, batch_y):
         """One step of Model.train's loop body with device-side loss/accuracy sums."""
         labels = labels_to_device(batch_y)
+        if self._graph_ok() and isinstance(batch_X, DeviceArray):
+            out = self._graph_train_step(batch_X, labels)
+            if out is not None:
+                return out
         if self.plan is not None:
             gb = self.softmax_classifier_output.grad_batch
             output = self.plan.forward(as_device(batch_X), labels, accum=self._accum,
@@ -172,7 +216,7 @@ class Model:
         if not self._fast_path_ok():
             return self._train_generic(X, y, epochs=epochs, batch_size=batch_size, verbose=verbose,
                                        validation_data=validation_data)
-        feeder = _BatchFeeder(X, _host_labels(y), bs, stream_batches)
+        feeder = _BatchFeeder(X, _host_labels(y), bs, stream_batches, cache=self.__dict__.setdefault("_feeder_cache", {}))
         self.h2d_bytes = self.d2h_bytes = 0
         ring = PinnedBuffer((64, 2), np.float64) if feeder.stream else None
         for epoch in range(1, epochs + 1):
@@ -372,7 +416,7 @@ class _BatchFeeder:
                                staged through two pinned buffers first.
     """
 
-    def __init__(self, X, labels_host, bs, stream_batches):
+    def __init__(self, X, labels_host, bs, stream_batches, cache=None):
         self.bs, self.n = bs, len(X)
         self.stream = bool(stream_batches) and not isinstance(X, DeviceArray)
         self.h2d_bytes = 0
@@ -385,13 +429,23 @@ class _BatchFeeder:
             self.X = self.X.astype(np.float32)
         self.labels_host = np.ascontiguousarray(labels_host, dtype=np.int32)
         shape = (bs,) + self.X.shape[1:]
-        self.dev = [DeviceArray(shape, np.float32) for _ in range(2)]
-        self.dev_lab = [DeviceArray((bs,), np.int32) for _ in range(2)]
-        self.pin_lab = [PinnedBuffer((bs,), np.int32) for _ in range(2)]
-        self.pin_x = None
-        self.copy_stream = new_stream()
-        self.uploaded = [new_event() for _ in range(2)]
-        self.consumed = [new_event() for _ in range(2)]
+        # the two device slots, their pinned label staging, the copy stream and the events persist across train() calls
+        # (same pointers => the CUDA graphs captured for them stay valid)
+        res = None if cache is None else cache.get(shape)
+        if res is None:
+            res = dict(dev=[DeviceArray(shape, np.float32) for _ in range(2)],
+                       dev_lab=[DeviceArray((bs,), np.int32) for _ in range(2)],
+                       pin_lab=[PinnedBuffer((bs,), np.int32) for _ in range(2)],
+                       copy_stream=new_stream(), uploaded=[new_event() for _ in range(2)],
+                       consumed=[new_event() for _ in range(2)], pin_x=None)
+            if cache is not None:
+                cache[shape] = res
+        else:
+            synchronize()                                  # a previous pass may still be reading the slots
+        self._res = res
+        self.dev, self.dev_lab, self.pin_lab = res["dev"], res["dev_lab"], res["pin_lab"]
+        self.pin_x = res["pin_x"]
+        self.copy_stream, self.uploaded, self.consumed = res["copy_stream"], res["uploaded"], res["consumed"]
         self.issued = -1          # last step (of the current pass) whose upload has been enqueued
         self.uploads = 0          # uploads ever enqueued; slot = uploads & 1
         self.slot_of = {}
@@ -411,7 +465,7 @@ class _BatchFeeder:
         addr = pinned_address(src)
         if addr is None:                              # pageable: stage through pinned memory
             if self.pin_x is None:
-                self.pin_x = [PinnedBuffer((self.bs,) + self.X.shape[1:], np.float32) for _ in range(2)]
+                self.pin_x = self._res["pin_x"] = [PinnedBuffer((self.bs,) + self.X.shape[1:], np.float32) for _ in range(2)]
             self.pin_x[slot].array[:rows] = src
             addr = self.pin_x[slot].ptr
         xb = self.dev[slot][0:rows]

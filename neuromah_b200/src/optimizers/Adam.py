@@ -67,6 +67,38 @@ class Optimizer_Adam:
     def update_arena(self, arena, n_apply=1):
         ops.adam_step(arena.params, arena.grads, arena.state[0], arena.state[1], n_apply=n_apply, **self._hp())
 
+    # -- graph-capturable variant: hyper-parameters live in a device struct advanced on the device ----------
+    def _host_snapshot(self):
+        return (self.learning_rate, self.decay, self.beta_1, self.beta_2, self.epsilon, self.iterations)
+
+    def sync_device_state(self):
+        """(Re)initialise the device-side nm_adam_state from the host attributes if they changed behind its back."""
+        import ctypes as C
+        from ..._lib import lib
+        from ...device import stream
+        if getattr(self, "_dev_state", None) is None:
+            self._dev_state = DeviceArray.zeros((64,), np.uint8)          # sizeof(nm_adam_state) = 56
+            self._dev_snapshot = None
+        if self._dev_snapshot != self._host_snapshot():
+            lib.nm_adam_state_init(self._dev_state.p, float(self.learning_rate), float(self.decay), float(self.beta_1),
+                                   float(self.beta_2), float(self.epsilon), C.c_longlong(int(self.iterations)), stream())
+        return self._dev_state
+
+    def update_arena_dev(self, arena, n_apply=1):
+        """One Adam launch + the on-device advance of (iterations, bias corrections, decayed lr): no host values are
+        baked into the launches, so the pair can be replayed from a CUDA graph."""
+        from ..._lib import lib
+        from ...device import stream
+        lib.nm_adam_step_dev_f32(arena.params.p, arena.grads.p, arena.state[0].p, arena.state[1].p, arena.total,
+                                 self._dev_state.p, n_apply, stream())
+        lib.nm_adam_advance_f32(self._dev_state.p, stream())
+
+    def host_advance(self):
+        """Host mirror of the on-device advance (keeps ``iterations`` / ``current_learning_rate`` readable)."""
+        self.pre_update_params()          # the rate the step just used (Adam.py:41-47 runs before the update)
+        self.iterations += 1
+        self._dev_snapshot = self._host_snapshot()
+
     def post_update_params(self):
         self.iterations += 1
 
