@@ -388,12 +388,13 @@ int nm_tc_pack_dlogits_bf16(const float* dlogits, void* dl_hilo, int B, int n_ou
                           dlogits, static_cast<__nv_bfloat16*>(dl_hilo), B, n_out);
 }
 
+// Workspace layout: [0,256) last-block ticket (persists, always left at zero) | per-block loss/accuracy sums | split-K
+// partials.  The size is an upper bound that also covers every SMALLER batch (a validation pass through the same buffers):
+// splits * B <= sm_count * 128 whenever the K range is split, else B.
 size_t nm_tc_dense_softmax_ce_workspace(int B, int K) {
     if (B <= 0 || K <= 0) return 0;
-    int per;
-    const int splits = fwd_split(B, K, &per);
-    const int blocks = (B + 127) / 128;
-    return align256((size_t)splits * B * kNO * sizeof(float)) + align256((size_t)blocks * 2 * sizeof(double)) + 256;
+    const size_t blocks = (size_t)(B + 127) / 128;
+    return 256 + align256(blocks * 2 * sizeof(double)) + align256(((size_t)sm_count() * 128 + (size_t)B) * kNO * sizeof(float));
 }
 
 int nm_tc_dense_softmax_ce_bf16(const void* x, const void* w_hilo, const float* bias, const int32_t* labels,
@@ -402,15 +403,15 @@ int nm_tc_dense_softmax_ce_bf16(const void* x, const void* w_hilo, const float* 
     NM_REQUIRE(x && w_hilo && bias && labels && probs && dlogits && sample_loss && correct && workspace, "null pointer");
     NM_REQUIRE(B > 0 && K > 0 && K % 8 == 0 && n_out > 0, "bad dimensions");
     if (n_out > kNO) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_dense_softmax_ce_bf16: needs n_out <= 16");
-    NM_REQUIRE(workspace_bytes >= nm_tc_dense_softmax_ce_workspace(B, K), "workspace too small");
     DenseFwdParams p{};
     p.B = B; p.kblocks = (K + FWD_BK - 1) / FWD_BK;
     const int splits = fwd_split(B, K, &p.per_split);
     const int mtiles = (B + 127) / 128;
     uint8_t* ws = static_cast<uint8_t*>(workspace);
-    p.partial = reinterpret_cast<float*>(ws);
-    double* block_part = reinterpret_cast<double*>(ws + align256((size_t)splits * B * kNO * sizeof(float)));
-    unsigned* counter = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(block_part) + align256((size_t)mtiles * 2 * sizeof(double)));
+    unsigned* counter = reinterpret_cast<unsigned*>(ws);
+    double* block_part = reinterpret_cast<double*>(ws + 256);
+    p.partial = reinterpret_cast<float*>(ws + 256 + align256((size_t)mtiles * 2 * sizeof(double)));
+    NM_REQUIRE(workspace_bytes >= 256 + align256((size_t)mtiles * 2 * sizeof(double)) + (size_t)splits * B * kNO * sizeof(float), "workspace too small");
     CUtensorMap mx, mw;
     int rc = make_map_2d(&mx, x, (uint64_t)K, (uint64_t)B, (uint64_t)K * 2, FWD_BK, 128, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;

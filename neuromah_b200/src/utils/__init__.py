@@ -1,1 +1,2 @@
 from ..initializers.Initializer import CustomInitializer, HeInitializer, XavierInitializer, RandomNormalInitializer
+from .TensorMonitor import TensorMonitor

@@ -118,3 +118,32 @@ def test_federated_average_host_mirror():
     from neuromah_b200.Federated import federated_average
     out = federated_average([[1.0, 2.0], [3.0, 6.0]], [100, 300])
     assert out == [2.5, 5.0]
+
+
+def test_tensor_monitor_json_shape(tmp_path):
+    """TensorMonitor keeps the reference's hooks and JSON layout (src/utils/TensorMonitor.py:7-136)."""
+    import json
+    import types
+    from neuromah_b200.src.utils import TensorMonitor
+    Layer_Conv2D = type("Layer_Conv2D", (), {})
+    layer = Layer_Conv2D()
+    layer.__dict__.update(weights=np.arange(12.0).reshape(3, 4), biases=np.zeros((1, 4)),
+                          weight_gradients=np.ones((3, 4)), bias_gradients=np.ones((1, 4)), kernel_size=(3, 3))
+    model = types.SimpleNamespace(layers=[layer, object()], optimizer=types.SimpleNamespace(learning_rate=0.1),
+                                  loss=object(), accuracy=object())
+    tm = TensorMonitor(log_dir=str(tmp_path))
+    tm.start_run(model)
+    tm.start_epoch(1)
+    tm.log_scalar("loss/epoch_training", 0.5)
+    tm.log_layer_parameters(layer)
+    tm.end_epoch()
+    tm.save_logs()
+    log = json.load(open(tm.log_file_path))
+    assert set(log) == {"metadata", "epochs"}
+    assert log["metadata"]["layers"][0]["name"] == "Layer_Conv2D"
+    assert log["metadata"]["layers"][0]["config"]["weights"] == {"shape": [3, 4], "dtype": "float64"}
+    ep = log["epochs"][0]
+    assert ep["epoch"] == 1 and ep["metrics"]["scalars"]["loss/epoch_training"] == 0.5 and ep["time_elapsed"] >= 0
+    hist = ep["parameters"]["histograms"]
+    assert set(hist) == {"Layer_Conv2D/weights", "Layer_Conv2D/dweights", "Layer_Conv2D/biases", "Layer_Conv2D/dbiases"}
+    assert sum(hist["Layer_Conv2D/weights"]["histogram"]) == 12 and len(hist["Layer_Conv2D/weights"]["bin_edges"]) == 11

@@ -250,3 +250,30 @@ def test_save_and_load_parameters_roundtrip(tmp_path):
     m1.save_parameters(path)
     m2.load_parameters(path)
     np.testing.assert_array_equal(m1.arena.host_params(), m2.arena.host_params())
+
+
+def test_vgg_style_stack_per_step_parity():
+    """BASELINE.json config 4 (VGG-style Conv2D stack on CIFAR-shaped 32x32x3 data, He init), reduced in width so the
+    NumPy oracle finishes in seconds: C(3->8) C(8->8) P C(8->16) C(16->16) P Flatten Dense(1024->10) Softmax, FP32-exact
+    kernels, per-step outputs / gradients / post-Adam weights within the north-star tolerance."""
+    spec = []
+    ic = 3
+    for oc in (8, 16):
+        spec += [{"kind": "conv", "ic": ic, "oc": oc, "k": 3, "padding": "same", "relu": True},
+                 {"kind": "conv", "ic": oc, "oc": oc, "k": 3, "padding": "same", "relu": True},
+                 {"kind": "pool", "size": 2, "stride": 2, "padding": "valid"}]
+        ic = oc
+    spec += [{"kind": "flatten"}, {"kind": "dense", "n_in": 16 * 8 * 8, "n_out": 10, "relu": False}, {"kind": "softmax"}]
+    params = ref_net.init_params(spec, np.random.RandomState(31), init="he")
+    model = build(spec, params, learning_rate=0.001)
+    net = ref_net.RefNet(spec, params)
+    x, y = synth(32, 3 * 48, (3, 32, 32))
+    for s in range(3):
+        _resync_oracle(net, model)
+        xb, yb = x[s * 48:(s + 1) * 48], y[s * 48:(s + 1) * 48]
+        out = model.train_step(xb, yb)
+        ref = net.step(xb, yb)
+        np.testing.assert_allclose(np.asarray(out), ref["output"], rtol=1e-4, atol=1e-5)
+        g_ref = net.flat("grads")
+        np.testing.assert_allclose(model.arena.host_grads(), g_ref, rtol=1e-4, atol=1e-5 * max(1.0, np.abs(g_ref).max()))
+        np.testing.assert_allclose(model.arena.host_params(), net.flat(), rtol=1e-4, atol=1e-5)

@@ -172,3 +172,23 @@ def test_tc_graph_replay_matches_eager_steps():
     np.testing.assert_allclose(p1, p0, rtol=1e-4, atol=2e-5)
     np.testing.assert_allclose(l1, l0, rtol=1e-5)
     assert abs(c0 - c1) <= 1
+
+
+def test_tc_train_api_with_smaller_validation_batches(tmp_path):
+    """Model.train in bf16 mode with validation data of a different size, a TensorMonitor and a partial last batch:
+    the plan's buffers / workspaces sized for the training batch must serve every smaller batch too."""
+    from neuromah_b200.src.utils import TensorMonitor
+    spec = ref_net.mnist_cnn_spec()
+    params = ref_net.init_params(spec, np.random.RandomState(13), init="he")
+    model = build(spec, params, mode="bf16", learning_rate=0.002)
+    model.tensorMonitor = TensorMonitor(log_dir=str(tmp_path))
+    model.tensorMonitor.start_run(model)
+    x, y = synth_learnable(14, 5 * 256 + 100)                 # 6 steps, the last one partial
+    xv, yv = synth_learnable(15, 96)
+    model.train(x, y, epochs=3, batch_size=256, verbose=0, validation_data=(xv, yv))
+    assert model.last_epoch["acc"] > 0.9
+    res = model.evaluate(xv, yv, batch_size=32, verbose=0)
+    assert res["acc"] > 0.9
+    import json
+    log = json.load(open(model.tensorMonitor.log_file_path))
+    assert len(log["epochs"]) == 3 and "Layer_Conv2D/dweights" in log["epochs"][0]["parameters"]["histograms"]
