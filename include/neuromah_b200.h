@@ -208,6 +208,12 @@ int nm_tc_conv3x3_wgrad_bf16(const void* x_pad, const void* dy_pad, float* dw, v
 size_t nm_tc_conv3x3_bwd_workspace(int C, int OC);
 int nm_tc_conv3x3_bwd_bf16(const void* x_pad, const void* dy_pad, const void* w_packed_dgrad, float* dw, void* dx_grid,
                            void* workspace, size_t workspace_bytes, int N, int H, int W, int C, int OC, void* stream);
+/* The same, with dY never materialised: it is rebuilt per tile in shared memory from the ReLU-masked gradient of the
+ * POOLED conv output (dpool bf16 [N][H/2*W/2][OC], nm_tc_dense_bwd_pool_bf16) and the pool arg-max nibbles
+ * (idx [N][H/2*W/2][OC/2]) -- MaxPooling2D.backward's routing is one byte permute per two channels. */
+int nm_tc_conv3x3_bwd_pool_bf16(const void* x_pad, const void* dpool, const void* idx, const void* w_packed_dgrad, float* dw,
+                                void* dx_grid, void* workspace, size_t workspace_bytes, int N, int H, int W, int C, int OC,
+                                void* stream);
 
 /* First conv of the net (C_in = 1, 3x3 'same', ReLU, no bias) + MaxPooling2D(2,2) on tcgen05: the 4x4 input patch of a
  * pool window is the K = 16 dimension and the weights are expanded to Wext[(window position, oc)][4x4] (zero outside the
@@ -249,6 +255,10 @@ int nm_tc_dense_softmax_ce_bf16(const void* x, const void* w_hilo, const float* 
  * (Relu.py:12-14) -> the last conv's dY, bf16 [B,2PH+2,2PW+2,C] (interior); dbias[C] = sum of dY
  * (Conv_wrapepr.py:107-109).  One thread per (pooled pixel, 8 channels): PH*PW*C/8 <= 416. */
 size_t nm_tc_dense_bwd_unpool_workspace(int C);
+/* ... or only up to the pooled tensor: dpool bf16 [B][PH*PW][C] = ReLU-masked Dense dinputs (no arg-max routing). */
+int nm_tc_dense_bwd_pool_bf16(const float* dlogits, const float* w_packed, const void* idx, void* dpool,
+                              float* dbias, void* workspace, size_t workspace_bytes,
+                              int B, int PH, int PW, int C, int n_out, void* stream);
 int nm_tc_dense_bwd_unpool_bf16(const float* dlogits, const float* w_packed, const void* idx, void* dy_pad,
                                 float* dbias, void* workspace, size_t workspace_bytes,
                                 int B, int PH, int PW, int C, int n_out, void* stream);

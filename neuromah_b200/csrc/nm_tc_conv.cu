@@ -359,7 +359,16 @@ struct ConvBwdParams {
     int num_tiles, rows_total;
     void* dx;                            // bf16 [rows_total][32]  (un-shifted grid)
     float* partial;                      // [gridDim.x][64][288]
+    // BUILD variant: dY is never in HBM.  It is rebuilt per tile in shared memory from the ReLU-masked gradient of the
+    // POOLED tensor (bf16 [N][PH*PW][64]) and the pool arg-max nibbles ([N][PH*PW][32 bytes]); the arg-max routing of
+    // MaxPooling2D.backward (maxpooling_backend.cpp:145-238) is one byte permute per two channels.
+    const __nv_bfloat16* dpool;
+    const uint8_t* idx;
+    int N, H, W;                         // conv output (= dY) size H x W, pooled (H/2) x (W/2)
 };
+
+__device__ __forceinline__ uint32_t bw_sw128(uint32_t row, uint32_t byte) { const uint32_t o = row * 128 + byte; return o ^ (((o >> 7) & 7) << 4); }
+__device__ __forceinline__ void bw_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 constexpr int BW_C = 32, BW_OC = 64, BW_WP = 16;
 constexpr int BW_ROWS = TILE_M + 2 * BW_WP + 2;                       // 162
@@ -370,7 +379,8 @@ constexpr int BW_W_BYTES = 9 * BW_C * 128;                            // 36 KB: 
 constexpr int BW_STAGES = 5;
 constexpr int BW_DACC = 3 * BW_C;                                     // 96 dgrad accumulator columns per buffer
 
-__global__ void __launch_bounds__(384, 1)
+template <bool BUILD>
+__global__ void __launch_bounds__(BUILD ? 640 : 384, 1)
 conv3x3_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                       const __grid_constant__ CUtensorMap map_w, ConvBwdParams p) {
     constexpr uint64_t TMPL_128 = desc_template(16, 1024, LAYOUT_SW128);        // dY (K-major or MN-major) and Wd
@@ -388,7 +398,8 @@ conv3x3_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_smem = smem;
     uint8_t* st_smem = smem + BW_W_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(st_smem + BW_STAGES * BW_STAGE);
+    uint32_t* lut = reinterpret_cast<uint32_t*>(st_smem + BW_STAGES * BW_STAGE);     // BUILD: [4 positions][256] PRMT selectors
+    uint64_t* full = reinterpret_cast<uint64_t*>(lut + (BUILD ? 4 * 256 : 0));
     uint64_t* empty = full + BW_STAGES;
     uint64_t* tfull = empty + BW_STAGES;
     uint64_t* tempty = tfull + 2;
@@ -398,9 +409,18 @@ conv3x3_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_trigger();
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_dy); tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w); }
+    if (warp == 0 && lane == 0) { if (!BUILD) tma_prefetch_desc(&map_dy); tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w); }
+    if constexpr (BUILD) {
+        // selector for window position pos: keep a channel's 16 bits where its nibble's position bits == pos, else zero
+        // (the ReLU mask is already applied to dpool)
+        for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) {
+            const int pos = i >> 8, b = i & 255;
+            lut[i] = (((b & 3) == pos) ? 0x0010u : 0x0044u) | ((((b >> 4) & 3) == pos) ? 0x3200u : 0x4400u);
+        }
+    }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < BW_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        // BUILD: a stage is full when the X tile has landed (TMA tx bytes) AND the four builder warps have written dY
+        for (int s = 0; s < BW_STAGES; ++s) { mbar_init(&full[s], BUILD ? 5 : 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
         mbar_init(wfull, 1);
         mbar_init(done, 1);
@@ -422,8 +442,8 @@ conv3x3_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* st = st_smem + (size_t)stage * BW_STAGE;
-                mbar_expect_tx(&full[stage], BW_ROWS * 128 + BW_ROWS * 64);
-                tma_load_2d(st, &map_dy, 0, tile * TILE_M, &full[stage]);
+                mbar_expect_tx(&full[stage], (BUILD ? 0 : BW_ROWS * 128) + BW_ROWS * 64);
+                if (!BUILD) tma_load_2d(st, &map_dy, 0, tile * TILE_M, &full[stage]);
                 tma_load_2d(st + BW_DY_BYTES, &map_x, 0, tile * TILE_M - (BW_WP + 1), &full[stage]);   // OOB rows read as 0
                 if (++stage == BW_STAGES) { stage = 0; phase ^= 1; }
             }
@@ -471,6 +491,61 @@ conv3x3_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
             mma_commit(done);
         }
         __syncwarp();
+    } else if (BUILD && warp >= 12) {
+        // ============================== dY builders: two groups of 4 warps, alternating tiles =========
+        // item = (grid pixel row of the tile, half of the 64 channels); 162 rows incl. the halo the filter taps reach.
+        const int bg = (warp - 12) >> 2, t = threadIdx.x & 127;
+        const int PH = p.H / 2, PW = p.W / 2, Hp = p.H + 2;
+        int it = bg;
+        for (int tile = blockIdx.x + bg * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
+            const int stage = it % BW_STAGES;
+            uint4 d[3][4], nb[3];
+            int posv[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {                   // issue every load of the tile first: one memory round trip
+                const int item = t + 128 * k, row = item >> 1, half = item & 1;
+                posv[k] = -1;
+                if (row < BW_ROWS) {
+                    const unsigned R = (unsigned)tile * TILE_M + row;                 // < 2^31: rows_total is an int
+                    const int n = (int)(R / (unsigned)(Hp * BW_WP)), rem = (int)(R - (unsigned)n * (Hp * BW_WP)), Y = rem / BW_WP, X = rem % BW_WP;
+                    if (n < p.N && Y >= 1 && Y <= p.H && X >= 1 && X <= p.W && !NM_DBG(8)) {
+                        const int py = (Y - 1) >> 1, px = (X - 1) >> 1;
+                        posv[k] = ((Y - 1) & 1) * 2 + ((X - 1) & 1);
+                        const size_t pix = ((size_t)n * PH + py) * PW + px;
+                        const uint4* src = reinterpret_cast<const uint4*>(p.dpool + pix * BW_OC + half * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) d[k][j] = __ldg(src + j);
+                        nb[k] = __ldg(reinterpret_cast<const uint4*>(p.idx + pix * (BW_OC / 2) + half * 16));
+                    }
+                }
+            }
+            mbar_wait(&empty[stage], ((it / BW_STAGES) & 1) ^ 1);
+            uint8_t* dyt = st_smem + (size_t)stage * BW_STAGE;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int item = t + 128 * k, row = item >> 1, half = item & 1;
+                if (row >= BW_ROWS) continue;
+                uint32_t out[16];
+                if (posv[k] >= 0) {
+                    const uint32_t* sel = lut + posv[k] * 256;
+                    const uint32_t dw[16] = {d[k][0].x, d[k][0].y, d[k][0].z, d[k][0].w, d[k][1].x, d[k][1].y, d[k][1].z, d[k][1].w,
+                                             d[k][2].x, d[k][2].y, d[k][2].z, d[k][2].w, d[k][3].x, d[k][3].y, d[k][3].z, d[k][3].w};
+                    const uint32_t nw[4] = {nb[k].x, nb[k].y, nb[k].z, nb[k].w};
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        out[j] = NM_DBG(9) ? dw[j] ^ nw[j >> 2] : __byte_perm(dw[j], 0u, sel[(nw[j >> 2] >> (8 * (j & 3))) & 0xFFu]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) out[j] = 0u;    // halo pixel (or past the last image)
+                }
+#pragma unroll
+                for (int j = 0; j < (NM_DBG(10) ? 1 : 4); ++j)
+                    *reinterpret_cast<uint4*>(dyt + bw_sw128(row, half * 64 + j * 16)) = make_uint4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+            }
+            bw_fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);
+        }
     } else if (warp >= 4) {
         // ============================== dgrad epilogue: two groups of 4 warps, alternating tiles ======
         const int q = warp & 3, grp = (warp - 4) >> 2;
@@ -479,32 +554,34 @@ conv3x3_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
             mbar_wait(&tfull[grp], (it >> 1) & 1);
             fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + WCOLS + grp * BW_DACC;
-            uint32_t e0[BW_C], e1[BW_C], e2[BW_C];
-#pragma unroll
-            for (int c = 0; c < BW_C; c += 16) {
-                tmem_ld_x16(taddr + c, e0 + c);
-                tmem_ld_x16(taddr + BW_C + c, e1 + c);
-                tmem_ld_x16(taddr + 2 * BW_C + c, e2 + c);
-            }
-            tmem_ld_wait();
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[grp]);
-            // out[p] = E[p][s=0] + E[p+1][s=1] + E[p+2][s=2]: a warp holds two complete 16-pixel grid rows whose last two
-            // pixels are halo, so the shift never crosses the warp
-#pragma unroll
-            for (int c = 0; c < BW_C; ++c)
-                e0[c] = __float_as_uint(__uint_as_float(e0[c]) + (__uint_as_float(__shfl_down_sync(0xffffffffu, e1[c], 1)) +
-                                                                 __uint_as_float(__shfl_down_sync(0xffffffffu, e2[c], 2))));
             const long long row = (long long)tile * TILE_M + q * 32 + lane;
-            if (row < p.rows_total) {
-                uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.dx) + row * BW_C);
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.dx) + row * BW_C);
+            // out[p] = E[p][s=0] + E[p+1][s=1] + E[p+2][s=2]: a warp holds two complete 16-pixel grid rows whose last two
+            // pixels are halo, so the shift never crosses the warp.  Two halves of 16 channels keep the register count low.
 #pragma unroll
-                for (int c = 0; c < BW_C; c += 8)
-                    dst[c / 8] = make_uint4(pack_bf16x2(__uint_as_float(e0[c + 0]), __uint_as_float(e0[c + 1])),
-                                            pack_bf16x2(__uint_as_float(e0[c + 2]), __uint_as_float(e0[c + 3])),
-                                            pack_bf16x2(__uint_as_float(e0[c + 4]), __uint_as_float(e0[c + 5])),
-                                            pack_bf16x2(__uint_as_float(e0[c + 6]), __uint_as_float(e0[c + 7])));
+            for (int h = 0; h < 2; ++h) {
+                uint32_t e0[16], e1[16], e2[16];
+                tmem_ld_x16(taddr + h * 16, e0);
+                tmem_ld_x16(taddr + BW_C + h * 16, e1);
+                tmem_ld_x16(taddr + 2 * BW_C + h * 16, e2);
+                tmem_ld_wait();
+                if (h == 1) {
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[grp]);
+                }
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    e0[c] = __float_as_uint(__uint_as_float(e0[c]) + (__uint_as_float(__shfl_down_sync(0xffffffffu, e1[c], 1)) +
+                                                                     __uint_as_float(__shfl_down_sync(0xffffffffu, e2[c], 2))));
+                if (row < p.rows_total) {
+#pragma unroll
+                    for (int c = 0; c < 16; c += 8)
+                        dst[h * 2 + c / 8] = make_uint4(pack_bf16x2(__uint_as_float(e0[c + 0]), __uint_as_float(e0[c + 1])),
+                                                        pack_bf16x2(__uint_as_float(e0[c + 2]), __uint_as_float(e0[c + 3])),
+                                                        pack_bf16x2(__uint_as_float(e0[c + 4]), __uint_as_float(e0[c + 5])),
+                                                        pack_bf16x2(__uint_as_float(e0[c + 6]), __uint_as_float(e0[c + 7])));
+                }
             }
         }
         // ============================== wgrad epilogue: accumulators -> one FP32 partial [64][288] per CTA ===
@@ -705,37 +782,59 @@ int nm_tc_conv3x3_wgrad_bf16(const void* x_pad, const void* dy_pad, float* dw, v
 
 size_t nm_tc_conv3x3_bwd_workspace(int C, int OC) { return (size_t)sm_count() * OC * 9 * C * sizeof(float); }
 
-int nm_tc_conv3x3_bwd_bf16(const void* x_pad, const void* dy_pad, const void* w_packed_dgrad, float* dw, void* dx_grid,
-                           void* workspace, size_t workspace_bytes, int N, int H, int W, int C, int OC, void* stream) {
-    NM_REQUIRE(x_pad && dy_pad && w_packed_dgrad && dw && dx_grid && workspace, "null pointer");
-    NM_REQUIRE(N > 0, "bad batch");
+static int launch_conv_bwd(bool build, const void* x_pad, const void* dy_pad, const void* dpool, const void* idx,
+                           const void* w_packed_dgrad, float* dw, void* dx_grid, void* workspace, size_t workspace_bytes,
+                           int N, int H, int W, int C, int OC, void* stream) {
+    NM_REQUIRE(x_pad && w_packed_dgrad && dw && dx_grid && workspace, "null pointer");
+    NM_REQUIRE(N > 0 && H > 0 && H % 2 == 0, "bad dimensions");
     if (!(C == BW_C && OC == BW_OC && W + 2 == BW_WP))
-        return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv3x3_bwd_bf16: only C=32, OC=64, W=14 is instantiated");
+        return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv3x3_bwd_*: only C=32, OC=64, W=14 is instantiated");
     ConvBwdParams p{};
     p.rows_total = N * (H + 2) * BW_WP;
     p.num_tiles = (p.rows_total + TILE_M - 1) / TILE_M;
     p.dx = dx_grid;
     p.partial = static_cast<float*>(workspace);
+    p.dpool = static_cast<const __nv_bfloat16*>(dpool);
+    p.idx = static_cast<const uint8_t*>(idx);
+    p.N = N; p.H = H; p.W = W;
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     NM_REQUIRE(workspace_bytes >= (size_t)grid * OC * 9 * C * sizeof(float), "workspace too small");
     CUtensorMap mdy, mx, mw;
-    int rc = make_map_2d(&mdy, dy_pad, BW_OC, (uint64_t)p.rows_total, 128, BW_OC, BW_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = make_map_2d(&mx, x_pad, BW_C, (uint64_t)p.rows_total, 64, BW_C, BW_ROWS, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
-    rc = make_map_2d(&mx, x_pad, BW_C, (uint64_t)p.rows_total, 64, BW_C, BW_ROWS, CU_TENSOR_MAP_SWIZZLE_64B);
-    if (rc) return rc;
+    mdy = mx;                                        // unused by the BUILD variant
+    if (!build) {
+        rc = make_map_2d(&mdy, dy_pad, BW_OC, (uint64_t)p.rows_total, 128, BW_OC, BW_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
     rc = make_map_2d(&mw, w_packed_dgrad, 9 * BW_OC, BW_C, 9 * 128, BW_OC, BW_C, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    const size_t smem = (size_t)BW_W_BYTES + (size_t)BW_STAGES * BW_STAGE + 512;
+    const size_t smem = (size_t)BW_W_BYTES + (size_t)BW_STAGES * BW_STAGE + (build ? 4 * 256 * 4 : 0) + 512;
     static bool attr_set = false;
     if (!attr_set) {
-        NM_CUDA(cudaFuncSetAttribute(conv3x3_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        NM_CUDA(cudaFuncSetAttribute(conv3x3_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        NM_CUDA(cudaFuncSetAttribute(conv3x3_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
     }
-    rc = nm::launch_pdl("conv3x3_bwd_tc", conv3x3_bwd_tc_kernel, dim3(grid), dim3(384), smem, nm::S(stream), mdy, mx, mw, p);
+    rc = build ? nm::launch_pdl("conv3x3_bwd_tc", conv3x3_bwd_tc_kernel<true>, dim3(grid), dim3(640), smem, nm::S(stream), mdy, mx, mw, p)
+               : nm::launch_pdl("conv3x3_bwd_tc", conv3x3_bwd_tc_kernel<false>, dim3(grid), dim3(384), smem, nm::S(stream), mdy, mx, mw, p);
     if (rc) return rc;
     const int total = OC * 9 * C;
     return nm::launch_pdl("wgrad_reduce", wgrad_reduce_kernel, dim3(nm_cdiv(total, 64)), dim3(256), 0, nm::S(stream),
                           (const float*)p.partial, dw, grid, OC, C);
+}
+
+int nm_tc_conv3x3_bwd_bf16(const void* x_pad, const void* dy_pad, const void* w_packed_dgrad, float* dw, void* dx_grid,
+                           void* workspace, size_t workspace_bytes, int N, int H, int W, int C, int OC, void* stream) {
+    NM_REQUIRE(dy_pad, "null pointer");
+    return launch_conv_bwd(false, x_pad, dy_pad, nullptr, nullptr, w_packed_dgrad, dw, dx_grid, workspace, workspace_bytes, N, H, W, C, OC, stream);
+}
+
+int nm_tc_conv3x3_bwd_pool_bf16(const void* x_pad, const void* dpool, const void* idx, const void* w_packed_dgrad, float* dw,
+                                void* dx_grid, void* workspace, size_t workspace_bytes, int N, int H, int W, int C, int OC,
+                                void* stream) {
+    NM_REQUIRE(dpool && idx, "null pointer");
+    return launch_conv_bwd(true, x_pad, nullptr, dpool, idx, w_packed_dgrad, dw, dx_grid, workspace, workspace_bytes, N, H, W, C, OC, stream);
 }
 
 }  // extern "C"

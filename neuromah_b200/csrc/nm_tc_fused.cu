@@ -19,7 +19,10 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 // per image (the per-image version re-read 125 KB x 4096 images from L2 and sat at 10% of HBM).
 // The next image's nibbles are prefetched while the current one is routed and stored.
 // ------------------------------------------------------------------------------------------------
-template <int NO>
+// POOLED = true: only the ReLU-masked gradient of the POOLED tensor is written (bf16 [B, PH*PW, C]); the routing to the
+// arg-max position is left to the consumer (nm_tc_conv3x3_bwd_pool_bf16 builds the dY tile in shared memory from it),
+// which removes the 4x larger dY tensor and its HBM round trip.
+template <int NO, bool POOLED>
 __global__ void __launch_bounds__(416, 1)
 dense_bwd_unpool_kernel(const float* __restrict__ dlogits, const float* __restrict__ wp, const uint8_t* __restrict__ idx,
                         __nv_bfloat16* __restrict__ dy_pad, float* __restrict__ dbias_cta, float* __restrict__ dbias,
@@ -75,6 +78,16 @@ dense_bwd_unpool_kernel(const float* __restrict__ dlogits, const float* __restri
 #pragma unroll
                 for (int c = 0; c < 8; ++c) d[c] = fmaf(sdl, wv[j][c], d[c]);
             }
+            if constexpr (POOLED) {
+                float val[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    val[c] = ((nibs >> (4 * c)) & 4u) ? d[c] : 0.f;          // ReLU mask
+                    bsum[c] += val[c];
+                }
+                *reinterpret_cast<uint4*>(dy_pad + ((size_t)n * items + item) * 8) =
+                    make_uint4(pack2(val[0], val[1]), pack2(val[2], val[3]), pack2(val[4], val[5]), pack2(val[6], val[7]));
+            } else {
             float v[4][8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -91,6 +104,7 @@ dense_bwd_unpool_kernel(const float* __restrict__ dlogits, const float* __restri
                                      pack2(v[pos][4], v[pos][5]), pack2(v[pos][6], v[pos][7]));
                 if (!NM_DBG(1)) *reinterpret_cast<uint4*>(dy_pad + (((size_t)n * H2 + Y) * W2 + X) * C + g * 8) = o;
                 else if (o.x == 0x12345678u) dbias_cta[0] = 1.f;
+            }
             }
         }
     }
@@ -131,26 +145,40 @@ extern "C" {
 
 size_t nm_tc_dense_bwd_unpool_workspace(int C) { return (size_t)148 * 2 * C * sizeof(float); }
 
-int nm_tc_dense_bwd_unpool_bf16(const float* dlogits, const float* w_packed, const void* idx, void* dy_pad,
-                                float* dbias, void* workspace, size_t workspace_bytes,
-                                int B, int PH, int PW, int C, int n_out, void* stream) {
-    NM_REQUIRE(dlogits && w_packed && idx && dy_pad && dbias && workspace, "null pointer");
+static int launch_dense_bwd(bool pooled, const float* dlogits, const float* w_packed, const void* idx, void* out,
+                            float* dbias, void* workspace, size_t workspace_bytes,
+                            int B, int PH, int PW, int C, int n_out, void* stream) {
+    NM_REQUIRE(dlogits && w_packed && idx && out && dbias && workspace, "null pointer");
     NM_REQUIRE(B > 0 && PH > 0 && PW > 0 && C % 8 == 0 && n_out > 0 && n_out <= kNO, "bad dimensions");
     const int items = PH * PW * (C / 8);
     if (items > 416 || C > 416)
-        return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_dense_bwd_unpool_bf16: needs PH*PW*C/8 <= 416 (one thread per item)");
+        return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_dense_bwd_*: needs PH*PW*C/8 <= 416 (one thread per item)");
     int grid = B < 148 ? B : 148;
     NM_REQUIRE(workspace_bytes >= (size_t)grid * C * sizeof(float), "workspace too small");
     const size_t smem = (size_t)items * 8 * sizeof(float);
     const uint8_t* ip = static_cast<const uint8_t*>(idx);
-    __nv_bfloat16* dyp = static_cast<__nv_bfloat16*>(dy_pad);
+    __nv_bfloat16* op = static_cast<__nv_bfloat16*>(out);
     float* part = static_cast<float*>(workspace);
-    // the [n_out x 8] weight slice lives in registers: instantiate the common head width exactly
     static unsigned* ticket = nullptr;             // last-block ticket, left at zero by every launch (one device per process)
     if (!ticket) { NM_CUDA(cudaMalloc(&ticket, sizeof(unsigned))); NM_CUDA(cudaMemset(ticket, 0, sizeof(unsigned))); }
-    return n_out <= 10
-        ? nm::launch_pdl("dense_bwd_unpool", dense_bwd_unpool_kernel<10>, dim3(grid), dim3(416), smem, nm::S(stream), dlogits, w_packed, ip, dyp, part, dbias, ticket, B, PH, PW, C, n_out)
-        : nm::launch_pdl("dense_bwd_unpool", dense_bwd_unpool_kernel<kNO>, dim3(grid), dim3(416), smem, nm::S(stream), dlogits, w_packed, ip, dyp, part, dbias, ticket, B, PH, PW, C, n_out);
+    // the [n_out x 8] weight slice lives in registers: instantiate the common head width exactly
+#define NM_LAUNCH_DB(NO_, P_) nm::launch_pdl("dense_bwd_unpool", dense_bwd_unpool_kernel<NO_, P_>, dim3(grid), dim3(416), smem, nm::S(stream), \
+                                            dlogits, w_packed, ip, op, part, dbias, ticket, B, PH, PW, C, n_out)
+    if (pooled) return n_out <= 10 ? NM_LAUNCH_DB(10, true) : NM_LAUNCH_DB(kNO, true);
+    return n_out <= 10 ? NM_LAUNCH_DB(10, false) : NM_LAUNCH_DB(kNO, false);
+#undef NM_LAUNCH_DB
+}
+
+int nm_tc_dense_bwd_unpool_bf16(const float* dlogits, const float* w_packed, const void* idx, void* dy_pad,
+                                float* dbias, void* workspace, size_t workspace_bytes,
+                                int B, int PH, int PW, int C, int n_out, void* stream) {
+    return launch_dense_bwd(false, dlogits, w_packed, idx, dy_pad, dbias, workspace, workspace_bytes, B, PH, PW, C, n_out, stream);
+}
+
+int nm_tc_dense_bwd_pool_bf16(const float* dlogits, const float* w_packed, const void* idx, void* dpool,
+                              float* dbias, void* workspace, size_t workspace_bytes,
+                              int B, int PH, int PW, int C, int n_out, void* stream) {
+    return launch_dense_bwd(true, dlogits, w_packed, idx, dpool, dbias, workspace, workspace_bytes, B, PH, PW, C, n_out, stream);
 }
 
 }  // extern "C"

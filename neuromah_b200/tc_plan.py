@@ -179,9 +179,12 @@ class TcCnnPlan:
         _timed('tc_dense_wgrad', lib.nm_tc_dense_wgrad_bf16, self.act2.p, self.dl_hilo.p, self.dlogits.p, self.de.weights.p, self.de.dweights.p, self.de.dbiases.p,
                                    self.ws.p, self.ws.nbytes, B, self.K, self.n_out, 49, 64, float(scale),
                                    float(self.de.weight_regularizer_l1), float(self.de.weight_regularizer_l2), s)
+        # Dense dgrad + pool backward + ReLU' -> conv2's dY (+ conv2 bias gradient), then conv2 dgrad + wgrad in one pass
+        # over dY.  (nm_tc_dense_bwd_pool_bf16 + nm_tc_conv3x3_bwd_pool_bf16 keep dY out of HBM altogether by rebuilding
+        # the tile in shared memory, but measured slower: 23 + 100 us against 38 + 73 us -- the builder warps' generic
+        # shared-memory stores starve behind the tensor core's operand reads, which saturate the 128 B/cycle port.)
         _timed('tc_dense_bwd_unpool', lib.nm_tc_dense_bwd_unpool_bf16, self.dlogits.p, self.w3p.p, self.idx2.p, self.dy2_pad.p,
                                         self.c2.bias_gradients.p, self.ws.p, self.ws.nbytes, B, 7, 7, 64, self.n_out, s)
-        # conv2 dgrad + wgrad in one pass over dY2
         _timed('tc_conv2_bwd', lib.nm_tc_conv3x3_bwd_bf16, self.act1_pad.p, self.dy2_pad.p, self.w2d.p, self.c2.weight_gradients.p,
                self.dp1.p, self.ws.p, self.ws.nbytes, B, 14, 14, 32, 64, s)
         if comm is not None:

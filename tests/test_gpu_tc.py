@@ -154,6 +154,39 @@ def test_tc_conv_fused_backward(n, integer):
     np.testing.assert_array_equal(dw.numpy(), dw2.numpy())
 
 
+@pytest.mark.parametrize("n,integer", [(1, True), (67, True), (300, False)])
+def test_tc_conv_fused_backward_from_pooled_gradient(n, integer):
+    """nm_tc_conv3x3_bwd_pool_bf16: dY is rebuilt in shared memory from the pooled gradient + arg-max nibbles
+    (MaxPooling2D.backward routing, maxpooling_backend.cpp:145-238) and never exists in HBM."""
+    from neuromah_b200._lib import lib
+    from neuromah_b200.device import DeviceArray, stream
+    rng, x, w = _setup(n, 60 + n, integer)
+    _, wg = _pack(w)
+    nib = rng.integers(0, 4, (n, 7, 7, 64)).astype(np.uint8) | (rng.integers(0, 2, (n, 7, 7, 64)).astype(np.uint8) << 2)
+    idx = (nib[..., 0::2] | (nib[..., 1::2] << 4)).astype(np.uint8)
+    live = (nib >> 2).astype(bool)
+    dp = (rng.integers(-2, 3, (n, 7, 7, 64)) if integer else bf16_round(rng.standard_normal((n, 7, 7, 64)))).astype(np.float32)
+    dp = np.where(live, dp, 0.0).astype(np.float32)                 # the producer applies the ReLU mask
+    dy = np.zeros((n, 14, 14, 64), np.float32)
+    for pos in range(4):
+        dy[:, (pos >> 1)::2, (pos & 1)::2, :] = np.where((nib & 3) == pos, dp, 0.0)
+    dy = dy.transpose(0, 3, 1, 2).copy()
+    xp = DeviceArray.from_numpy(pad_nhwc(x))
+    dpd, idxd = DeviceArray.from_numpy(to_bf16_bits(dp)), DeviceArray.from_numpy(idx)
+    dw = DeviceArray.zeros((64, 32, 3, 3))
+    dx = DeviceArray.zeros((n, 16, 16, 32), np.uint16)
+    ws = DeviceArray((lib.nm_tc_conv3x3_bwd_workspace(32, 64),), np.uint8)
+    lib.nm_tc_conv3x3_bwd_pool_bf16(xp.p, dpd.p, idxd.p, wg.p, dw.p, dx.p, ws.p, ws.nbytes, n, 14, 14, 32, 64, stream())
+    dx_ref, dw_ref, _ = R.conv_layer_backward(x, w, None, dy, padding="same", relu=False, mode="wired", dtype=np.float64)
+    got = from_bf16_bits(dx.numpy())[:, :14, :14, :].transpose(0, 3, 1, 2)
+    if integer:
+        np.testing.assert_array_equal(got, bf16_round(dx_ref.astype(np.float32)))
+        np.testing.assert_array_equal(dw.numpy(), dw_ref.astype(np.float32))
+    else:
+        np.testing.assert_allclose(got, dx_ref, rtol=2 ** -7, atol=2e-2)
+        np.testing.assert_allclose(dw.numpy(), dw_ref, rtol=1e-4, atol=1e-2)
+
+
 # ------------------------------------------------------------------ tcgen05 Dense head ----
 def _dense_case(B, K, n_out, hw, c, seed, integer):
     rng = np.random.default_rng(seed)
@@ -270,6 +303,12 @@ def test_tc_dense_bwd_unpool(B):
     np.testing.assert_allclose(got, ref, rtol=2 ** -7, atol=1e-12)
     assert not got[:, 0].any() and not got[:, -1].any() and not got[:, :, 0].any() and not got[:, :, -1].any()
     np.testing.assert_allclose(dbias.numpy(), np.where(live, dpool, 0.0).sum(axis=(0, 1, 2)), rtol=1e-4, atol=1e-6)
+    # pooled variant: ReLU-masked gradient of the pooled tensor only (the routing is left to the conv backward kernel)
+    dpl = DeviceArray.zeros((B, PH * PW, Cc), np.uint16)
+    dbias2 = DeviceArray.zeros((Cc,))
+    lib.nm_tc_dense_bwd_pool_bf16(dld.p, wp.p, idxd.p, dpl.p, dbias2.p, ws.p, ws.nbytes, B, PH, PW, Cc, n_out, s)
+    np.testing.assert_allclose(from_bf16_bits(dpl.numpy()).reshape(B, PH, PW, Cc), np.where(live, dpool, 0.0), rtol=2 ** -7, atol=1e-12)
+    np.testing.assert_array_equal(dbias2.numpy(), dbias.numpy())
 
 
 # ------------------------------------------------------------------ tcgen05 conv1 (C_in = 1) ----
