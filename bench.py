@@ -227,6 +227,9 @@ def main():
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"],
                     help="bf16 = fused tensor-core plan (tcgen05), fp32 = FP32-exact CUDA-core kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dp", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: gradient exchange -- fused peer-memory all-reduce + Adam kernel, or NCCL all-reduce "
+                         "(auto = peer memory when the GPUs can map each other)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -268,7 +271,7 @@ def main():
     spec, params = cnn_spec_and_params()
     model = build_model(spec, params, mode=None if args.mode == "fp32" else "bf16")
     comm = parallel.Communicator(rank, world)
-    parallel.attach(model, comm, B * world)
+    parallel.attach(model, comm, B * world, peer=None if args.dp == "auto" else args.dp == "peer")
     model.epoch_end_accuracy = False     # time the K training steps only (no Model.py:199 sweep)
 
     # synthetic data: up to 32 distinct host batches per rank in page-locked memory (cycled when K > 32)
@@ -379,6 +382,9 @@ def main():
             "config": {"workload": "MNIST CNN (Conv3x3x32-ReLU-Pool2-Conv3x3x64-ReLU-Pool2-Dense10-Softmax), "
                                    "softmax-CE, Adam x2 per layer (reference quirk Q1)",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "gradient_exchange": ("none (1 GPU)" if world == 1 else
+                                             "fused all-reduce + Adam kernel over NVLink peer memory (nm_dp_*)"
+                                             if comm.peer is not None else "NCCL all-reduce, two buckets on a side stream"),
                        "mode": "bf16 tensor-core plan (bf16 operands, fp32 accumulate, fp32 master weights)"
                                if args.mode == "bf16" else "fp32_exact", "step_tflops": STEP_FLOPS(B * world) / (elapsed_ms / K * 1e-3) / 1e12,
                        "l2": "inputs cycle over 8 distinct batches; the per-step activation working set "

@@ -277,6 +277,26 @@ int nm_comm_destroy(void* comm);
 int nm_comm_allreduce_sum_f32(void* comm, float* buf, size_t n, void* stream);  /* in place */
 int nm_comm_broadcast_f32(void* comm, float* buf, size_t n, int root, void* stream);
 
+/* ---- data-parallel exchange fused with the optimizer, over NVLink peer memory ----
+ * No reference equivalent (the reference is single-process; its one cross-replica operation is the FedAvg mean,
+ * Federated/utils.py:20-23).  Each rank owns a mailbox in its HBM that the peers map through cudaIpc; ONE kernel
+ * pushes the local gradient chunks to every mailbox, waits for the peers' chunks, sums them in rank order (replicas
+ * stay bit-identical) and applies Optimizer_Adam.update_params (Adam.py:86-100) -- the all-reduce and the optimizer
+ * launch of the NCCL path in one launch, CUDA-graph replayable (the step number lives on the device).
+ *   nm_dp_create   allocate the mailbox for slabs of up to max_floats floats (world <= 16)
+ *   nm_dp_export   64-byte cudaIpcMemHandle_t of this rank's mailbox, to be all-gathered by the launcher
+ *   nm_dp_connect  handles = world x 64 bytes in rank order (own entry ignored); maps the peers' mailboxes
+ *   nm_dp_status   timed_out != 0 if a wait for a peer exceeded the timeout (default 20 s); blocking */
+int nm_dp_create(void** dp, int rank, int world, size_t max_floats);
+int nm_dp_export(void* dp, void* handle64);
+int nm_dp_connect(void* dp, const void* handles);
+int nm_dp_set_timeout_ms(void* dp, unsigned ms);
+int nm_dp_allreduce_sum_f32(void* dp, float* buf, size_t n, void* stream);      /* in place, every rank gets the sum */
+int nm_dp_allreduce_adam_dev_f32(void* dp, float* param, float* grad, float* m, float* v, size_t n,
+                                 const nm_adam_state* dev_state, int n_apply, void* stream);
+int nm_dp_status(void* dp, int* timed_out, unsigned* steps_done);
+int nm_dp_destroy(void* dp);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,6 +100,14 @@ _SIGS = {
     "nm_comm_destroy": (_i, [_vp]),
     "nm_comm_allreduce_sum_f32": (_i, [_vp, _vp, _sz, _vp]),
     "nm_comm_broadcast_f32": (_i, [_vp, _vp, _sz, _i, _vp]),
+    "nm_dp_create": (_i, [_pvp, _i, _i, _sz]),
+    "nm_dp_export": (_i, [_vp, _vp]),
+    "nm_dp_connect": (_i, [_vp, _vp]),
+    "nm_dp_set_timeout_ms": (_i, [_vp, C.c_uint]),
+    "nm_dp_allreduce_sum_f32": (_i, [_vp, _vp, _sz, _vp]),
+    "nm_dp_allreduce_adam_dev_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
+    "nm_dp_status": (_i, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_uint)]),
+    "nm_dp_destroy": (_i, [_vp]),
 }
 
 _UNCHECKED = {"nm_last_error", "nm_version", "nm_conv2d_wgrad_f32_workspace", "nm_dense_wgrad_f32_workspace",

@@ -1,0 +1,268 @@
+// Data-parallel gradient exchange fused with the optimizer, over NVLink 5 / NVSwitch peer memory.
+//
+// The reference has no multi-GPU path; its only cross-replica operation is the FedAvg mean
+// (Federated/utils.py:20-23).  Data parallelism here is "SUM the gradient slab over ranks, then Optimizer_Adam"
+// (Adam.py:86-100).  A library all-reduce followed by an optimizer launch costs two dependent launches plus the
+// collective's own latency for a 200 KB slab; this file does both in ONE kernel:
+//
+//   every rank owns a MAILBOX in its HBM: data[2 parities][world][slot] floats + flag[world][chunks] words, exported
+//   to the peers with cudaIpc.  Block b of the kernel
+//     1. PUSHES its 1024-float chunks of the local gradient into slot[rank] of every rank's mailbox (plain 128-bit
+//        stores that travel over NVLink), fences at system scope and publishes flag[rank][chunk] = step number on
+//        every rank,
+//     2. WAITS until the flags of all ranks for its chunks carry this step number,
+//     3. sums the `world` slots in RANK ORDER (every rank computes the identical fp32 sum, so the replicas stay
+//        bit-identical and the result does not depend on timing), writes the sum back to the gradient slab and applies
+//        Adam to its parameters.
+//   Blocks only wait for pushes and every block pushes before it waits, so no rank can block another; the grid is
+//   capped at the SM count so all blocks are resident.  Two parities make the buffers safe without a second handshake:
+//   a rank can only be one step ahead of the slowest peer (it needs that peer's push to finish its own step).
+//   The step number lives on the device and is advanced by the last block, so the launch is CUDA-graph replayable.
+//   A bounded spin (nm_dp_set_timeout_ms) raises a status word instead of hanging the GPU if a peer never arrives.
+#include "nm_common.cuh"
+#include "nm_adam.cuh"
+
+namespace {
+
+constexpr int kMaxWorld = 16;
+constexpr int kChunk = 1024;                 // floats per chunk = 256 threads x float4
+constexpr int kThreads = 256;
+
+struct DpDev {                               // passed to the kernel by value
+    float* mail[kMaxWorld];                  // mailbox data of rank d, mapped into this process
+    uint32_t* flag[kMaxWorld];               // mailbox flags of rank d
+    uint32_t* seq;                           // local: last completed step number
+    uint32_t* ticket;                        // local: blocks finished in the current launch
+    int* status;                             // local: 0 ok, 1 a wait timed out
+    unsigned long long timeout_ns;
+    size_t slot;                             // floats per (parity, rank) slot, multiple of kChunk
+    int max_chunks, rank, world;
+};
+
+struct Dp {
+    DpDev dev{};
+    void* base = nullptr;                    // this rank's mailbox allocation (data | flags)
+    void* peer_base[kMaxWorld] = {};         // cudaIpcOpenMemHandle results (own entry = base)
+    void* local = nullptr;                   // seq | ticket | status
+    size_t data_bytes = 0, flag_bytes = 0, max_floats = 0;
+    bool connected = false;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// MODE 0: all-reduce only (gradient slab <- sum over ranks); MODE 1: + Adam on (p, m, v)
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+dp_allreduce_kernel(DpDev c, float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                    size_t n, const nm_adam_state* __restrict__ ds, int n_apply) {
+    pdl_trigger();
+    pdl_wait();
+    const int tid = threadIdx.x;
+    const uint32_t step = *reinterpret_cast<volatile uint32_t*>(c.seq) + 1u;
+    const size_t par = (size_t)(step & 1u) * c.world;
+    const int nchunks = (int)((n + kChunk - 1) / kChunk);
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                       reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+
+    // 1. push this rank's chunks into slot[rank] of every mailbox (own included), destinations staggered by rank
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const size_t i = (size_t)ch * kChunk + (size_t)tid * 4;
+        float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec && i + 4 <= n) G = *reinterpret_cast<const float4*>(g + i);
+        else {
+            if (i < n) G.x = g[i];
+            if (i + 1 < n) G.y = g[i + 1];
+            if (i + 2 < n) G.z = g[i + 2];
+            if (i + 3 < n) G.w = g[i + 3];
+        }
+        for (int d = 0; d < c.world; ++d) {
+            const int dst = (c.rank + d) % c.world;
+            *reinterpret_cast<float4*>(c.mail[dst] + (par + c.rank) * c.slot + i) = G;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x)
+        if (tid < c.world) st_release_sys(c.flag[(c.rank + tid) % c.world] + (size_t)c.rank * c.max_chunks + ch, step);
+
+    // 2 + 3. wait for every rank's chunk, reduce in rank order, optimizer
+    AdamHP hp{};
+    if (MODE == 1) hp = adam_hp_from(ds);
+    const float* mine = c.mail[c.rank];
+    const uint32_t* my_flag = c.flag[c.rank];
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        if (tid < c.world) {
+            const uint32_t* f = my_flag + (size_t)tid * c.max_chunks + ch;
+            const unsigned long long t0 = global_ns();
+            while ((int32_t)(ld_acquire_sys(f) - step) < 0) {
+                if (global_ns() - t0 > c.timeout_ns) { atomicExch(c.status, 1); break; }
+                __nanosleep(64);
+            }
+        }
+        __syncthreads();
+        const size_t i = (size_t)ch * kChunk + (size_t)tid * 4;
+        float4 G = __ldcg(reinterpret_cast<const float4*>(mine + par * c.slot + i));
+        for (int r = 1; r < c.world; ++r) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(mine + (par + r) * c.slot + i));
+            G.x += t.x; G.y += t.y; G.z += t.z; G.w += t.w;
+        }
+        if (vec && i + 4 <= n) {
+            *reinterpret_cast<float4*>(g + i) = G;
+            if (MODE == 1) {
+                float4 P = *reinterpret_cast<float4*>(p + i), M = *reinterpret_cast<float4*>(m + i),
+                       V = *reinterpret_cast<float4*>(v + i);
+                adam_one(P.x, G.x, M.x, V.x, hp, n_apply); adam_one(P.y, G.y, M.y, V.y, hp, n_apply);
+                adam_one(P.z, G.z, M.z, V.z, hp, n_apply); adam_one(P.w, G.w, M.w, V.w, hp, n_apply);
+                *reinterpret_cast<float4*>(p + i) = P; *reinterpret_cast<float4*>(m + i) = M;
+                *reinterpret_cast<float4*>(v + i) = V;
+            }
+        } else {
+            const float gs[4] = {G.x, G.y, G.z, G.w};
+            for (int u = 0; u < 4; ++u)
+                if (i + u < n) {
+                    g[i + u] = gs[u];
+                    if (MODE == 1) adam_one(p[i + u], gs[u], m[i + u], v[i + u], hp, n_apply);
+                }
+        }
+    }
+
+    // the last block to finish publishes the step number for the next launch (every block has read it by then)
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(c.ticket, 1u) == gridDim.x - 1) {
+            *c.ticket = 0u;
+            *reinterpret_cast<volatile uint32_t*>(c.seq) = step;
+        }
+    }
+}
+
+int launch(Dp* d, int mode, float* p, float* g, float* m, float* v, size_t n, const nm_adam_state* st, int n_apply, void* stream) {
+    if (!d->connected) return nm::fail(NM_ERR_BAD_ARG, "%s%s", "nm_dp: not connected (call nm_dp_connect first)");
+    if (n > d->max_floats) return nm::fail(NM_ERR_BAD_ARG, "%s%s", "nm_dp: slab larger than the mailbox slot");
+    if (!n) return NM_OK;
+    int dev = 0, sms = 0;
+    NM_CUDA(cudaGetDevice(&dev));
+    NM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int nchunks = (int)((n + kChunk - 1) / kChunk);
+    const dim3 grid(nchunks < sms ? nchunks : sms);               // all blocks resident: a waiting block never starves a pusher
+    if (mode == 0)
+        return nm::launch_pdl("dp_allreduce", dp_allreduce_kernel<0>, grid, dim3(kThreads), 0, nm::S(stream), d->dev,
+                              (float*)nullptr, g, (float*)nullptr, (float*)nullptr, n, (const nm_adam_state*)nullptr, 0);
+    return nm::launch_pdl("dp_allreduce_adam", dp_allreduce_kernel<1>, grid, dim3(kThreads), 0, nm::S(stream), d->dev,
+                          p, g, m, v, n, st, n_apply);
+}
+
+}  // namespace
+
+extern "C" {
+
+int nm_dp_create(void** dp, int rank, int world, size_t max_floats) {
+    NM_REQUIRE(dp, "dp is NULL");
+    NM_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world && max_floats > 0, "bad rank/world/size");
+    Dp* d = new Dp();
+    d->max_floats = max_floats;
+    d->dev.rank = rank; d->dev.world = world;
+    d->dev.max_chunks = (int)((max_floats + kChunk - 1) / kChunk);
+    d->dev.slot = (size_t)d->dev.max_chunks * kChunk;
+    d->dev.timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
+    d->data_bytes = 2 * (size_t)world * d->dev.slot * sizeof(float);
+    d->flag_bytes = (((size_t)world * d->dev.max_chunks * sizeof(uint32_t)) + 255) / 256 * 256;
+    cudaError_t e = cudaMalloc(&d->base, d->data_bytes + d->flag_bytes);     // cudaMalloc: cudaIpc cannot export pool memory
+    if (e == cudaSuccess) e = cudaMemset(d->base, 0, d->data_bytes + d->flag_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d->local, 256);
+    if (e == cudaSuccess) e = cudaMemset(d->local, 0, 256);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(d->base); cudaFree(d->local); delete d; return nm::cuda_fail(e, "nm_dp_create"); }
+    d->dev.seq = static_cast<uint32_t*>(d->local);
+    d->dev.ticket = d->dev.seq + 1;
+    d->dev.status = reinterpret_cast<int*>(d->dev.seq + 2);
+    d->peer_base[rank] = d->base;
+    if (world == 1) {
+        d->dev.mail[0] = static_cast<float*>(d->base);
+        d->dev.flag[0] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d->base) + d->data_bytes);
+        d->connected = true;
+    }
+    *dp = d;
+    return NM_OK;
+}
+
+int nm_dp_export(void* dp, void* handle64) {
+    NM_REQUIRE(dp && handle64, "null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    NM_CUDA(cudaIpcGetMemHandle(&h, static_cast<Dp*>(dp)->base));
+    memcpy(handle64, &h, sizeof(h));
+    return NM_OK;
+}
+
+int nm_dp_connect(void* dp, const void* handles) {
+    NM_REQUIRE(dp && handles, "null pointer");
+    Dp* d = static_cast<Dp*>(dp);
+    if (d->connected) return NM_OK;
+    for (int r = 0; r < d->dev.world; ++r) {
+        if (r != d->dev.rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, static_cast<const uint8_t*>(handles) + (size_t)r * sizeof(h), sizeof(h));
+            NM_CUDA(cudaIpcOpenMemHandle(&d->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+        }
+        d->dev.mail[r] = static_cast<float*>(d->peer_base[r]);
+        d->dev.flag[r] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d->peer_base[r]) + d->data_bytes);
+    }
+    d->connected = true;
+    return NM_OK;
+}
+
+int nm_dp_set_timeout_ms(void* dp, unsigned ms) {
+    NM_REQUIRE(dp, "dp is NULL");
+    static_cast<Dp*>(dp)->dev.timeout_ns = (unsigned long long)ms * 1000000ull;
+    return NM_OK;
+}
+
+int nm_dp_allreduce_sum_f32(void* dp, float* buf, size_t n, void* stream) {
+    NM_REQUIRE(dp && buf, "null pointer");
+    return launch(static_cast<Dp*>(dp), 0, nullptr, buf, nullptr, nullptr, n, nullptr, 0, stream);
+}
+
+int nm_dp_allreduce_adam_dev_f32(void* dp, float* param, float* grad, float* m, float* v, size_t n,
+                                 const nm_adam_state* dev_state, int n_apply, void* stream) {
+    NM_REQUIRE(dp && param && grad && m && v && dev_state, "null pointer");
+    NM_REQUIRE(n_apply >= 1, "n_apply must be >= 1");
+    return launch(static_cast<Dp*>(dp), 1, param, grad, m, v, n, dev_state, n_apply, stream);
+}
+
+int nm_dp_status(void* dp, int* timed_out, unsigned* steps_done) {
+    NM_REQUIRE(dp, "dp is NULL");
+    Dp* d = static_cast<Dp*>(dp);
+    uint32_t w[3];
+    NM_CUDA(cudaMemcpy(w, d->local, sizeof(w), cudaMemcpyDeviceToHost));
+    if (timed_out) *timed_out = (int)w[2];
+    if (steps_done) *steps_done = w[0];
+    return NM_OK;
+}
+
+int nm_dp_destroy(void* dp) {
+    if (!dp) return NM_OK;
+    Dp* d = static_cast<Dp*>(dp);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < d->dev.world; ++r)
+        if (r != d->dev.rank && d->peer_base[r]) cudaIpcCloseMemHandle(d->peer_base[r]);
+    cudaFree(d->base);
+    cudaFree(d->local);
+    delete d;
+    return NM_OK;
+}
+
+}  // extern "C"

@@ -2,6 +2,7 @@
 // Adam / SGD over a flat slab.  All are coalesced, 128-bit vectorised where the data
 // allows it, and sized as grid-stride loops over a multiple of the SM count.
 #include "nm_common.cuh"
+#include "nm_adam.cuh"
 #include <cfloat>
 
 namespace {
@@ -177,17 +178,6 @@ __global__ void cce_bwd_kernel(const float* __restrict__ p, const int32_t* __res
 }
 
 // ----------------------------------------------------------- optimizers ---
-struct AdamHP { float lr, b1, b2, eps, bc1, bc2; };
-
-__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamHP& h, int n_apply) {
-    for (int a = 0; a < n_apply; ++a) {
-        m = h.b1 * m + (1.f - h.b1) * g;
-        v = h.b2 * v + (1.f - h.b2) * g * g;
-        float mh = m / h.bc1, vh = v / h.bc2;
-        p -= h.lr * mh / (sqrtf(vh) + h.eps);
-    }
-}
-
 template <bool DEV>
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, AdamHP hp, const nm_adam_state* __restrict__ ds,

@@ -1,4 +1,5 @@
-"""Data-parallel plumbing: one process per GPU, NCCL all-reduce of the gradient slab.
+"""Data-parallel plumbing: one process per GPU; the gradient slab is summed over ranks either by the fused peer-memory
+kernel (nm_dp_*: push over NVLink + rank-ordered sum + Adam in one launch) or by an NCCL all-reduce.
 
 Sharding: rank r owns rows [r*b, (r+1)*b) of every global batch.  The
 softmax-CE gradient and the Dense parameter gradients are divided by the GLOBAL batch
@@ -6,8 +7,8 @@ softmax-CE gradient and the Dense parameter gradients are divided by the GLOBAL 
 a plain SUM all-reduce of the gradient slab reproduces the single-GPU batch-B step exactly.
 
 Bootstrap uses torch.distributed (whatever backend the launcher initialised; gloo works)
-only to ship the 128-byte NCCL unique id; the data path is our own communicator on our
-own stream (nm_comm_*).
+only to ship the 128-byte NCCL unique id and the 64-byte cudaIpc handles of the peer
+mailboxes; the data path is our own kernels / our own communicator on our own stream.
 """
 from __future__ import annotations
 
@@ -58,6 +59,7 @@ class Communicator:
     def __init__(self, rank: int, world: int, unique_id: bytes | None = None):
         self.rank, self.world = rank, world
         self.handle = None
+        self.peer = None                 # nm_dp context: fused all-reduce + Adam over NVLink peer memory
         self.comm_stream = None          # side stream for all-reduces overlapped with the rest of backward
         if world == 1:
             return
@@ -83,6 +85,59 @@ class Communicator:
             t = t.cuda()
         dist.broadcast(t, src=0)
         return bytes(t.cpu().numpy().tobytes())
+
+    def _all_gather_bytes(self, blob: bytes) -> bytes:
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised to exchange the peer-memory handles")
+        t = torch.frombuffer(bytearray(blob), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t)
+        return b"".join(bytes(o.cpu().numpy().tobytes()) for o in out)
+
+    def enable_peer(self, max_floats: int, required: bool = False) -> bool:
+        """Set up the peer-memory mailboxes for gradient slabs of up to ``max_floats`` floats.  Returns False (and
+        leaves the NCCL path in charge) when some pair of GPUs cannot map each other's memory; every rank takes the
+        same decision."""
+        if self.world == 1 or self.peer is not None:
+            return self.peer is not None
+        import torch
+        import torch.distributed as dist
+        h = C.c_void_p()
+        ok, err = 1, ""
+        try:
+            lib.nm_dp_create(C.byref(h), self.rank, self.world, int(max_floats))
+            mine = C.create_string_buffer(64)
+            lib.nm_dp_export(h, mine)
+        except Exception as e:          # noqa: BLE001 -- agreement with the peers comes first
+            ok, err, mine = 0, str(e), C.create_string_buffer(64)
+        handles = self._all_gather_bytes(mine.raw)
+        if ok:
+            try:
+                lib.nm_dp_connect(h, C.create_string_buffer(handles, 64 * self.world))
+            except Exception as e:      # noqa: BLE001
+                ok, err = 0, str(e)
+        flags = self._all_gather_bytes(bytes([ok]))
+        if all(flags):
+            self.peer = h
+            return True
+        if h:
+            lib.nm_dp_destroy(h)
+        if required:
+            raise RuntimeError(f"peer-memory data parallelism unavailable (rank {self.rank}: {err or 'a peer failed'})")
+        return False
+
+    def check(self):
+        """Raise if a peer-memory wait timed out (a rank died or never launched its step); blocking."""
+        if self.peer is None:
+            return
+        bad, done = C.c_int(0), C.c_uint(0)
+        lib.nm_dp_status(self.peer, C.byref(bad), C.byref(done))
+        if bad.value:
+            raise RuntimeError(f"rank {self.rank}: a peer did not deliver its gradients in time (step {done.value})")
 
     def allreduce(self, arr, count=None):
         if self.world == 1:
@@ -117,16 +172,26 @@ class Communicator:
         lib.nm_comm_broadcast_f32(self.handle, arr.p, arr.size if count is None else count, root, stream())
 
     def close(self):
+        if self.peer is not None:
+            lib.nm_dp_destroy(self.peer)
+            self.peer = None
         if self.handle is not None:
             lib.nm_comm_destroy(self.handle)
             self.handle = None
 
 
-def attach(model, comm: Communicator, global_batch: int):
-    """Turn ``model`` into one data-parallel replica: global-batch normalisation + grad all-reduce,
-    and identical initial weights on every rank (broadcast from rank 0)."""
+def attach(model, comm: Communicator, global_batch: int, peer: bool | None = None):
+    """Turn ``model`` into one data-parallel replica: global-batch normalisation + gradient sum over ranks,
+    and identical initial weights on every rank (broadcast from rank 0).  ``peer``: True = require the fused
+    peer-memory exchange, False = NCCL all-reduce, None = peer memory when the GPUs can map each other."""
     model.comm = comm if comm.world > 1 else None
     set_global_batch(model, global_batch)
     if comm.world > 1:
         comm.broadcast(model.arena.params, 0, model.arena.total)
+        if peer is None:
+            peer = os.environ.get("NM_DP_PEER", "1") != "0"
+        if peer:
+            comm.enable_peer(model.arena.total, required=os.environ.get("NM_DP_PEER") == "require")
+        from .device import synchronize
+        synchronize()
     return model

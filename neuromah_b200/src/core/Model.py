@@ -160,7 +160,10 @@ class Model:
             try:
                 self.plan.forward(x, labels, accum=self._accum, inv_batch=None if gb is None else 1.0 / gb)
                 self.plan.backward(gb)
-                opt.update_arena_dev(self.arena, n_apply=n_apply)
+                if self.comm is not None:
+                    opt.update_arena_dp(self.arena, self.comm, n_apply=n_apply)
+                else:
+                    opt.update_arena_dev(self.arena, n_apply=n_apply)
             finally:
                 lib.nm_graph_end(stream(), C.byref(g))
             graphs[key] = g
@@ -170,9 +173,20 @@ class Model:
 
     def _graph_ok(self):
         opt = self.optimizer
-        return (self.graph_steps and self.plan is not None and self.comm is None and ops.timers is None
-                and hasattr(opt, "update_arena_dev") and len(set(self._n_apply.values())) == 1
+        return (self.graph_steps and self.plan is not None and (self.comm is None or self._dp_fused_ok())
+                and ops.timers is None and hasattr(opt, "update_arena_dev") and len(set(self._n_apply.values())) == 1
                 and getattr(self.plan, "B", 0) > 0)
+
+    def _dp_fused_ok(self):
+        """Data parallel with the peer-memory exchange: gradient sum + Adam are one kernel (nm_dp_allreduce_adam)."""
+        return (self.comm is not None and getattr(self.comm, "peer", None) is not None
+                and hasattr(self.optimizer, "update_arena_dp") and len(set(self._n_apply.values())) == 1)
+
+    def _dp_fused_step(self):
+        opt = self.optimizer
+        opt.sync_device_state()
+        opt.update_arena_dp(self.arena, self.comm, n_apply=next(iter(set(self._n_apply.values()))))
+        opt.host_advance()
 
     def train_step(self, batch_X, batch_y):
         """One step of Model.train's loop body with device-side loss/accuracy sums."""
@@ -185,13 +199,20 @@ class Model:
             gb = self.softmax_classifier_output.grad_batch
             output = self.plan.forward(as_device(batch_X), labels, accum=self._accum,
                                        inv_batch=None if gb is None else 1.0 / gb)
-            self.plan.backward(gb, comm=self.comm)
+            fused = self._dp_fused_ok()
+            self.plan.backward(gb, comm=None if fused else self.comm)
+            if fused:
+                self._dp_fused_step()
+                return output
             if self.comm is not None:
                 self.comm.wait()
         else:
             output = self.forward(batch_X, training=True)
             self._device_loss_acc(output, labels)
             self.backward(output, labels)
+            if self._dp_fused_ok():
+                self._dp_fused_step()
+                return output
             if self.comm is not None:
                 self.comm.allreduce_grads(self.arena)
         self._optimizer_step()
@@ -234,6 +255,8 @@ class Model:
                     lib.nm_d2h(C.c_void_p(ring.ptr + 16 * (step % 64)), self._accum.p, 16, stream())
                     self.d2h_bytes += 16
             loss_sum, _ = self._read_accum()
+            if self.comm is not None and getattr(self.comm, "peer", None) is not None:
+                self.comm.check()         # a peer that never delivered its gradients raises here instead of going unnoticed
             self.h2d_bytes = feeder.h2d_bytes
             epoch_time = time.time() - start_time
             self.loss.accumulated_sum, self.loss.accumulated_count = loss_sum, n

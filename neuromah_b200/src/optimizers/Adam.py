@@ -93,6 +93,15 @@ class Optimizer_Adam:
                                  self._dev_state.p, n_apply, stream())
         lib.nm_adam_advance_f32(self._dev_state.p, stream())
 
+    def update_arena_dp(self, arena, comm, n_apply=1):
+        """Data-parallel step: gradient sum over ranks (peer memory over NVLink) + Adam in ONE launch, then the
+        on-device advance.  ``arena.grads`` holds the summed gradient afterwards, as after an in-place all-reduce."""
+        from ..._lib import lib
+        from ...device import stream
+        lib.nm_dp_allreduce_adam_dev_f32(comm.peer, arena.params.p, arena.grads.p, arena.state[0].p, arena.state[1].p,
+                                         arena.total, self._dev_state.p, n_apply, stream())
+        lib.nm_adam_advance_f32(self._dev_state.p, stream())
+
     def host_advance(self):
         """Host mirror of the on-device advance (keeps ``iterations`` / ``current_learning_rate`` readable)."""
         self.pre_update_params()          # the rate the step just used (Adam.py:41-47 runs before the update)
