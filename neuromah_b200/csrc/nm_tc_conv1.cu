@@ -280,8 +280,7 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
     constexpr uint32_t IDESC = idesc_bf16(64, 32, 1, 1);
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* l_smem = smem + B_STAGES * B_STAGE;
-    uint4* lut = reinterpret_cast<uint4*>(l_smem + (size_t)B_LSTAGES * L.lstage_bytes);     // 256 x 4 PRMT selectors
-    uint64_t* afull = reinterpret_cast<uint64_t*>(lut + 256);
+    uint64_t* afull = reinterpret_cast<uint64_t*>(l_smem + (size_t)B_LSTAGES * L.lstage_bytes);
     uint64_t* aempty = afull + B_STAGES;
     uint64_t* lfull = aempty + B_STAGES;
     uint64_t* lempty = lfull + B_LSTAGES;
@@ -297,14 +296,6 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
         const int row = i % 128;
         *reinterpret_cast<uint4*>(pt + sw64(row, 32)) = make_uint4(0x00003F80u, 0u, 0u, 0u);   // bf16(1.0) = 0x3F80
         *reinterpret_cast<uint4*>(pt + sw64(row, 48)) = make_uint4(0u, 0u, 0u, 0u);
-    }
-    // selector for window position pos: keep a channel's 16 bits where its nibble == (relu bit | pos), else zero
-    for (int b = threadIdx.x; b < 256; b += blockDim.x) {
-        uint32_t sel[4];
-#pragma unroll
-        for (int pos = 0; pos < 4; ++pos)
-            sel[pos] = (((b & 7) == (4 | pos)) ? 0x0010u : 0x0044u) | ((((b >> 4) & 7) == (4 | pos)) ? 0x3200u : 0x4400u);
-        lut[b] = make_uint4(sel[0], sel[1], sel[2], sel[3]);
     }
     fence_proxy_async();
     if (threadIdx.x == 0) {
@@ -381,16 +372,26 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
             if (lane == 0) mbar_arrive(&lempty[ls]);          // everything is in registers: the slot may be refilled
             const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};   // 16 channels as bf16 pairs
             uint32_t out[4][8];
+            // arg-max routing + ReLU mask with no table: a nibble is (relu << 2 | position), so for window position pos
+            // the byte (nibble ^ (4 | pos) ^ 0x7F) + 1 has bit 7 set exactly when the nibble matches (values stay below
+            // 0x80: no carries between bytes); PRMT's sign-replicate mode widens those bits to one 16-bit mask per channel.
+            // (A 256-entry selector table in shared memory did the same with one LDS.128 per channel pair, but the
+            // kernel is bound by shared-memory wavefronts and those random 16-byte reads were ~40% of them.)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                // arg-max routing + ReLU mask of two channels = four byte permutes whose selectors come from a 256-entry
-                // table indexed by the channels' nibble byte
-                const uint32_t byte = ((j < 4 ? nb.x : nb.y) >> (8 * (j & 3))) & 0xFFu;
-                const uint4 sel = NM_DBG(4) ? make_uint4(byte, byte, byte, byte) : lut[byte];
-                out[0][j] = __byte_perm(dw[j], 0u, sel.x);
-                out[1][j] = __byte_perm(dw[j], 0u, sel.y);
-                out[2][j] = __byte_perm(dw[j], 0u, sel.z);
-                out[3][j] = __byte_perm(dw[j], 0u, sel.w);
+            for (int wd = 0; wd < 2; ++wd) {
+                const uint32_t nbw = wd ? nb.y : nb.x;
+                const uint32_t lo = nbw & 0x07070707u, hi = (nbw >> 4) & 0x07070707u;      // even / odd channels of 4 pairs
+#pragma unroll
+                for (int pos = 0; pos < 4; ++pos) {
+                    const uint32_t k = (0x04040404u | (0x01010101u * pos)) ^ 0x7F7F7F7Fu;
+                    const uint32_t sl = (lo ^ k) + 0x01010101u, sh = (hi ^ k) + 0x01010101u;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t mask;
+                        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(mask) : "r"(sl), "r"(sh), "r"(0xCC88u + 0x1111u * j));
+                        out[pos][wd * 4 + j] = dw[wd * 4 + j] & mask;
+                    }
+                }
             }
             mbar_wait(&aempty[stage], phase ^ 1);
             if ((threadIdx.x & 255) == 0) NM_TRACE(G, tile, 3);
@@ -561,7 +562,7 @@ int nm_tc_conv1_bwd_bf16(const float* x, const void* dp_grid, const void* idx, f
     const int max_rows = (128 + g.PW - 1) / g.PW + 1 + 2;          // pooled rows a tile can span + the 2 halo rows at an image boundary
     L.dp_bytes = max_rows * (g.PW + 2) * OC * 2;
     L.lstage_bytes = L.x_bytes + L.dp_bytes + B_IDX_BYTES;
-    const size_t smem = (size_t)B_STAGES * B_STAGE + (size_t)B_LSTAGES * L.lstage_bytes + 256 * 16 + 256;
+    const size_t smem = (size_t)B_STAGES * B_STAGE + (size_t)B_LSTAGES * L.lstage_bytes + 256;
     if (smem > 220 * 1024) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_bwd_bf16: image too large for the staged-input ring");
     static bool attr = false;
     if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv1_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
