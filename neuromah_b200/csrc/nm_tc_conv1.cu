@@ -74,6 +74,21 @@ __device__ __forceinline__ void load_patch(const float* __restrict__ xs, const C
     }
 }
 
+// rows a0, a0 + 1 of that patch only (the backward builders split a window's patch between two threads)
+__device__ __forceinline__ void load_patch_rows(const float* __restrict__ xs, const Conv1Geom& G, bool valid, int n_local, int py, int px,
+                                                int a0, float p[8]) {
+    const float* img = xs + n_local * G.H * G.W;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int yy = 2 * py - 1 + a0 + a;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int xx = 2 * px - 1 + b;
+            p[a * 4 + b] = (valid && (unsigned)yy < (unsigned)G.H && (unsigned)xx < (unsigned)G.W) ? img[yy * G.W + xx] : 0.f;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -339,7 +354,12 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
         // ============================== builders: (window, half of the channels) per thread ==
         // two groups of 8 warps alternate tiles (group g owns operand stage g): a tile's build is a chain of dependent
         // shared-memory round trips, so one group alone left the issue slots mostly idle
-        const int grp = warp >> 3, row = threadIdx.x & 127, hh = (threadIdx.x >> 7) & 1;
+        // Thread -> (window row, channel half hh): a warp owns 16 rows x 2 halves, laid out so that every quarter-warp of a
+        // 128-bit shared-memory access touches eight different 16-byte bank groups.  Lane bits: b0 = hh, (b1, b3, b2, b4) =
+        // row bits 0..3 -- a quarter-warp holds rows {r, r+1, r+4, r+5} -- and rows with bit 2 set take the two 16-byte
+        // pieces of their 32 bytes in the opposite order ("flip"), for the staged dP reads as well as the G-tile writes.
+        const int grp = warp >> 3, hh = lane & 1, flip = (lane >> 2) & 1;
+        const int row = (warp & 7) * 16 + (((lane >> 1) & 1) | (((lane >> 3) & 1) << 1) | (flip << 2) | (((lane >> 4) & 1) << 3));
         const int stage = grp;
         int it = grp;
         for (int tile = blockIdx.x + grp * gridDim.x; tile < G.num_tiles; tile += 2 * gridDim.x, it += 2) {
@@ -356,21 +376,21 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
             }
             const int w0 = (int)(t.g0 - (unsigned)t.n0 * G.PHW), r0 = t.n0 * (G.PH + 2) + w0 / G.PW;
             const uint8_t* st = l_smem + (size_t)ls * L.lstage_bytes;
-            uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+            uint4 da = make_uint4(0, 0, 0, 0), db = da;          // pieces `flip` and `flip ^ 1` of this thread's 16 channels
             uint2 nb = make_uint2(0, 0);
-            float p[16];
+            float p[8];
             if ((threadIdx.x & 255) == 0) NM_TRACE(G, tile, 1);
             mbar_wait(&lfull[ls], lphase);
             if ((threadIdx.x & 255) == 0) NM_TRACE(G, tile, 2);
             if (valid) {
                 const uint4* src = reinterpret_cast<const uint4*>(st + L.x_bytes + (size_t)(n * (G.PH + 2) + py - r0) * row_bytes + px * (OC * 2) + hh * 32);
-                d0 = src[0]; d1 = src[1];
+                da = src[flip]; db = src[flip ^ 1];
                 nb = *reinterpret_cast<const uint2*>(st + L.x_bytes + L.dp_bytes + row * (OC / 2) + hh * 8);
             }
-            if (hh == 0) load_patch(reinterpret_cast<const float*>(st), G, valid, n - t.n0, py, px, p);
+            load_patch_rows(reinterpret_cast<const float*>(st), G, valid, n - t.n0, py, px, 2 * hh, p);
             __syncwarp();
             if (lane == 0) mbar_arrive(&lempty[ls]);          // everything is in registers: the slot may be refilled
-            const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};   // 16 channels as bf16 pairs
+            const uint32_t dw[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};   // 16 channels as bf16 pairs, piece order
             uint32_t out[4][8];
             // arg-max routing + ReLU mask with no table: a nibble is (relu << 2 | position), so for window position pos
             // the byte (nibble ^ (4 | pos) ^ 0x7F) + 1 has bit 7 set exactly when the nibble matches (values stay below
@@ -379,7 +399,7 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
             // kernel is bound by shared-memory wavefronts and those random 16-byte reads were ~40% of them.)
 #pragma unroll
             for (int wd = 0; wd < 2; ++wd) {
-                const uint32_t nbw = wd ? nb.y : nb.x;
+                const uint32_t nbw = (wd ^ flip) ? nb.y : nb.x;                              // nibbles of that piece's 8 channels
                 const uint32_t lo = nbw & 0x07070707u, hi = (nbw >> 4) & 0x07070707u;      // even / odd channels of 4 pairs
 #pragma unroll
                 for (int pos = 0; pos < 4; ++pos) {
@@ -397,19 +417,14 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
             if ((threadIdx.x & 255) == 0) NM_TRACE(G, tile, 3);
             uint8_t* gt = smem + stage * B_STAGE;
 #pragma unroll
-            for (int pos = 0; pos < (NM_DBG(5) ? 1 : 4); ++pos) {
+            for (int pos = 0; pos < 4; ++pos) {
                 uint8_t* blk = gt + (pos >> 1) * (128 * 128);
                 const uint32_t base = (pos & 1) * 64 + hh * 32;
-                *reinterpret_cast<uint4*>(blk + sw128(row, base)) = make_uint4(out[pos][0], out[pos][1], out[pos][2], out[pos][3]);
-                *reinterpret_cast<uint4*>(blk + sw128(row, base + 16)) = make_uint4(out[pos][4], out[pos][5], out[pos][6], out[pos][7]);
+                *reinterpret_cast<uint4*>(blk + sw128(row, base + 16 * flip)) = make_uint4(out[pos][0], out[pos][1], out[pos][2], out[pos][3]);
+                *reinterpret_cast<uint4*>(blk + sw128(row, base + 16 * (flip ^ 1))) = make_uint4(out[pos][4], out[pos][5], out[pos][6], out[pos][7]);
             }
-            if (hh == 0) {
-                uint8_t* pt = gt + B_G_BYTES;
-                *reinterpret_cast<uint4*>(pt + sw64(row, 0)) = make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]),
-                                                                           pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
-                *reinterpret_cast<uint4*>(pt + sw64(row, 16)) = make_uint4(pack_bf16x2(p[8], p[9]), pack_bf16x2(p[10], p[11]),
-                                                                            pack_bf16x2(p[12], p[13]), pack_bf16x2(p[14], p[15]));
-            }
+            *reinterpret_cast<uint4*>(gt + B_G_BYTES + sw64(row, 16 * hh)) =                  // patch rows 2hh, 2hh+1 of this window
+                make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&afull[stage]);
