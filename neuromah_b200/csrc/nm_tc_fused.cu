@@ -88,20 +88,23 @@ dense_bwd_unpool_kernel(const float* __restrict__ dlogits, const float* __restri
                 *reinterpret_cast<uint4*>(dy_pad + ((size_t)n * items + item) * 8) =
                     make_uint4(pack2(val[0], val[1]), pack2(val[2], val[3]), pack2(val[4], val[5]), pack2(val[6], val[7]));
             } else {
-            float v[4][8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint32_t nb = (nibs >> (4 * c)) & 0xF;
-                const float val = (nb & 4) ? d[c] : 0.f;                 // ReLU mask
-                bsum[c] += val;
-#pragma unroll
-                for (int pos = 0; pos < 4; ++pos) v[pos][c] = ((nb & 3) == (uint32_t)pos) ? val : 0.f;   // arg-max routing
-            }
+            for (int c = 0; c < 8; ++c) bsum[c] += ((nibs >> (4 * c)) & 4u) ? d[c] : 0.f;   // ReLU mask (bias gradient)
+            // ReLU mask + arg-max routing on the packed bf16 pairs: a nibble is (relu << 2 | position), so the byte
+            // (nibble ^ (4 | pos) ^ 0x7F) + 1 has bit 7 set exactly where the channel is live AND its maximum sat at pos;
+            // PRMT's sign-replicate mode turns those bits into one 16-bit mask per channel (nm_tc_conv1.cu uses the same trick)
+            const uint32_t pw[4] = {pack2(d[0], d[1]), pack2(d[2], d[3]), pack2(d[4], d[5]), pack2(d[6], d[7])};
+            const uint32_t lo = nibs & 0x07070707u, hi = (nibs >> 4) & 0x07070707u;
 #pragma unroll
             for (int pos = 0; pos < 4; ++pos) {
                 const int Y = 2 * py + (pos >> 1) + 1, X = 2 * px + (pos & 1) + 1;
-                uint4 o = make_uint4(pack2(v[pos][0], v[pos][1]), pack2(v[pos][2], v[pos][3]),
-                                     pack2(v[pos][4], v[pos][5]), pack2(v[pos][6], v[pos][7]));
+                const uint32_t kk = (0x04040404u | (0x01010101u * pos)) ^ 0x7F7F7F7Fu;
+                const uint32_t sl = (lo ^ kk) + 0x01010101u, sh = (hi ^ kk) + 0x01010101u;
+                uint32_t m[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m[j]) : "r"(sl), "r"(sh), "r"(0xCC88u + 0x1111u * j));
+                const uint4 o = make_uint4(pw[0] & m[0], pw[1] & m[1], pw[2] & m[2], pw[3] & m[3]);
                 if (!NM_DBG(1)) *reinterpret_cast<uint4*>(dy_pad + (((size_t)n * H2 + Y) * W2 + X) * C + g * 8) = o;
                 else if (o.x == 0x12345678u) dbias_cta[0] = 1.f;
             }
