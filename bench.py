@@ -56,6 +56,11 @@ def cnn_spec_and_params(seed=0):
     return spec, ref_net.init_params(spec, np.random.RandomState(seed))
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at batch 4096, from the committed `ncu --set full` capture
+NCU_TRAFFIC_SOURCE = "profiles/r01d_ncu_full_bf16_step.txt (ncu --set full --clock-control none, batch 4096)"
+NCU_TRAFFIC = {"tc_conv2_bwd": (201.40 + 45.01) * 1e6}
+
+
 def kernel_work(name, b):
     """(algorithmic FLOPs, algorithmic HBM bytes) of one launch of the named operator at batch b."""
     c2, c1 = CONV2_FLOPS(b), CONV1_FLOPS(b)
@@ -369,7 +374,8 @@ def main():
         per_kernel[k] = {"ms": round(ms_k, 5), "tflops": round(f / (ms_k * 1e-3) / 1e12, 2),
                          "gbs": round(nb / (ms_k * 1e-3) / 1e9, 1), "launches_per_step": len(kernel_ms[k]) / K2}
     roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                "frac": achieved / peak, "traffic": None, "avg_ms": avg_ms,
+                "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(top), "traffic_source": NCU_TRAFFIC_SOURCE if top in NCU_TRAFFIC else None,
+                "avg_ms": avg_ms,
                 "algorithmic_flops": flops, "algorithmic_bytes": nbytes,
                 "share_of_step": tot[top] / K2 / step2_ms,
                 "timing": f"CUDA events around every operator in a second timed region of {K2} steps ({step2_ms:.4f} ms/step; "
