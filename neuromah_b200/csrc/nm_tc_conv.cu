@@ -626,33 +626,34 @@ conv3x3_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
 }
 
 // dw[oc][c][r][s] = sum_cta partial[cta][oc][(r*3+s)*CIN + c]      (fixed order => deterministic)
-// 64 consecutive outputs per block (coalesced 256-byte rows), 4 slices of the CTA range per output, combined in
-// a fixed order through shared memory.
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
-                                                           int n_cta, int COUT, int CIN) {
-    __shared__ float red[4][64];
+// 64 consecutive outputs per block (coalesced 256-byte rows), 16 slices of the CTA range per output (<= 10 partials per
+// thread, all loads in flight together: the kernel is latency-, not bandwidth-bound), combined in a fixed order.
+constexpr int WR_SLICES = 16, WR_PER = 10;      // covers up to 160 CTAs
+__global__ void __launch_bounds__(64 * WR_SLICES) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                                                      int n_cta, int COUT, int CIN) {
+    __shared__ float red[WR_SLICES][64];
     pdl_trigger();
     pdl_wait();
     const int total = COUT * 9 * CIN;
     const int i = blockIdx.x * 64 + (threadIdx.x & 63), slice = threadIdx.x >> 6;
-    const int per = (n_cta + 3) / 4, k0 = slice * per, k1 = min(n_cta, k0 + per);
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    float s = 0.f;
     if (i < total) {
-        int k = k0;
-        for (; k + 4 <= k1; k += 4) {
-            s0 += __ldg(partial + (size_t)k * total + i);
-            s1 += __ldg(partial + (size_t)(k + 1) * total + i);
-            s2 += __ldg(partial + (size_t)(k + 2) * total + i);
-            s3 += __ldg(partial + (size_t)(k + 3) * total + i);
+        float v[WR_PER];
+#pragma unroll
+        for (int u = 0; u < WR_PER; ++u) {
+            const int k = slice * WR_PER + u;
+            v[u] = k < n_cta ? __ldg(partial + (size_t)k * total + i) : 0.f;
         }
-        for (; k < k1; ++k) s0 += __ldg(partial + (size_t)k * total + i);
+        s = (((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]))) + (v[8] + v[9]);
     }
-    red[slice][threadIdx.x & 63] = (s0 + s1) + (s2 + s3);
+    red[slice][threadIdx.x & 63] = s;
     __syncthreads();
     if (slice == 0 && i < total) {
-        const float s = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < WR_SLICES; ++k) a += red[k][threadIdx.x];
         const int oc = i / (9 * CIN), rem = i - oc * 9 * CIN, tap = rem / CIN, c = rem - tap * CIN;
-        dw[((size_t)oc * CIN + c) * 9 + tap] = s;
+        dw[((size_t)oc * CIN + c) * 9 + tap] = a;
     }
 }
 
@@ -776,7 +777,8 @@ int nm_tc_conv3x3_wgrad_bf16(const void* x_pad, const void* dy_pad, float* dw, v
               : nm::launch_pdl("conv3x3_wgrad_tc", conv3x3_wgrad_tc_kernel<32, 64, false>, dim3(grid), dim3(256), smem, nm::S(stream), mdy, mx, p);
     if (rc) return rc;
     int total = OC * 9 * C;
-    return nm::launch_pdl("wgrad_reduce", wgrad_reduce_kernel, dim3(nm_cdiv(total, 64)), dim3(256), 0, nm::S(stream),
+    NM_REQUIRE(grid <= WR_SLICES * WR_PER, "more CTAs than the reduction covers");
+    return nm::launch_pdl("wgrad_reduce", wgrad_reduce_kernel, dim3(nm_cdiv(total, 64)), dim3(64 * WR_SLICES), 0, nm::S(stream),
                           (const float*)p.partial, dw, grid, OC, C);
 }
 
@@ -820,7 +822,8 @@ static int launch_conv_bwd(bool build, const void* x_pad, const void* dy_pad, co
                : nm::launch_pdl("conv3x3_bwd_tc", conv3x3_bwd_tc_kernel<false>, dim3(grid), dim3(384), smem, nm::S(stream), mdy, mx, mw, p);
     if (rc) return rc;
     const int total = OC * 9 * C;
-    return nm::launch_pdl("wgrad_reduce", wgrad_reduce_kernel, dim3(nm_cdiv(total, 64)), dim3(256), 0, nm::S(stream),
+    NM_REQUIRE(grid <= WR_SLICES * WR_PER, "more CTAs than the reduction covers");
+    return nm::launch_pdl("wgrad_reduce", wgrad_reduce_kernel, dim3(nm_cdiv(total, 64)), dim3(64 * WR_SLICES), 0, nm::S(stream),
                           (const float*)p.partial, dw, grid, OC, C);
 }
 

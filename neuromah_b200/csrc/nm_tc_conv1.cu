@@ -487,34 +487,38 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
 }
 
 // dW[oc][r][s] = sum_cta sum_pos E[cta][(pos,oc)][(dy+r)*4 + dx+s],  db[oc] = sum_cta sum_pos E[cta][(pos,oc)][16]
-// 32 outputs x 8 slices of the CTA range per block, slices combined in a fixed order (deterministic).
-__global__ void __launch_bounds__(256)
+// 32 outputs x 32 slices of the CTA range per block (<= 5 CTAs per thread, all their loads in flight at once: the kernel
+// is a chain of L2 round trips, not bandwidth), slices combined in a fixed order (deterministic).
+constexpr int R_SLICES = 32, R_PER = (B_MAX_GRID + R_SLICES - 1) / R_SLICES;
+__global__ void __launch_bounds__(32 * R_SLICES)
 conv1_tc_bwd_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db, int n_cta) {
-    __shared__ float red[8][32];
+    __shared__ float red[R_SLICES][32];
     pdl_trigger();
     pdl_wait();
     const int total = OC * 10;
     const int i = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
-    const int per = (n_cta + 7) / 8, c0 = slice * per, c1 = min(n_cta, c0 + per);
     float s = 0.f;
     if (i < total) {
         const int oc = i / 10, t = i % 10, r = t / 3, sx = t % 3;
-        for (int c = c0; c < c1; ++c) {
-            float v[4];
+        float v[R_PER][4];
+#pragma unroll
+        for (int u = 0; u < R_PER; ++u) {
+            const int c = slice * R_PER + u;
 #pragma unroll
             for (int pos = 0; pos < 4; ++pos) {
                 const int col = t < 9 ? ((pos >> 1) + r) * 4 + (pos & 1) + sx : 16;
-                v[pos] = __ldg(partial + ((size_t)c * 128 + pos * 32 + oc) * 32 + col);
+                v[u][pos] = c < n_cta ? __ldg(partial + ((size_t)c * 128 + pos * 32 + oc) * 32 + col) : 0.f;
             }
-            s += (v[0] + v[1]) + (v[2] + v[3]);
         }
+#pragma unroll
+        for (int u = 0; u < R_PER; ++u) s += (v[u][0] + v[u][1]) + (v[u][2] + v[u][3]);
     }
     red[slice][threadIdx.x & 31] = s;
     __syncthreads();
     if (slice == 0 && i < total) {
         float a = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) a += red[k][threadIdx.x];
+        for (int k = 0; k < R_SLICES; ++k) a += red[k][threadIdx.x];
         const int oc = i / 10, t = i % 10;
         if (t < 9) dw[oc * 9 + t] = a; else db[oc] = a;
     }
@@ -584,7 +588,7 @@ int nm_tc_conv1_bwd_bf16(const float* x, const void* dp_grid, const void* idx, f
     int rc = nm::launch_pdl("conv1_tc_bwd", conv1_tc_bwd_kernel, dim3(grid), dim3(B_THREADS), smem, nm::S(stream), x,
                             static_cast<const __nv_bfloat16*>(dp_grid), static_cast<const uint8_t*>(idx), static_cast<float*>(workspace), g, L);
     if (rc) return rc;
-    return nm::launch_pdl("conv1_tc_bwd_reduce", conv1_tc_bwd_reduce_kernel, dim3(nm_cdiv(OC * 10, 32)), dim3(256), 0, nm::S(stream),
+    return nm::launch_pdl("conv1_tc_bwd_reduce", conv1_tc_bwd_reduce_kernel, dim3(nm_cdiv(OC * 10, 32)), dim3(32 * R_SLICES), 0, nm::S(stream),
                           static_cast<const float*>(workspace), dw, db, grid);
 }
 

@@ -130,12 +130,22 @@ dense_head_finalize_kernel(const float* __restrict__ partial, int n_split, const
         float z[kNO];
 #pragma unroll
         for (int j = 0; j < kNO; ++j) z[j] = 0.f;
-        for (int s = 0; s < n_split; ++s) {
-            const float4* src = reinterpret_cast<const float4*>(partial + ((size_t)s * B + row) * kNO);
+        for (int s0 = 0; s0 < n_split; s0 += 4) {                 // four splits' loads in flight together, summed in split order
+            float4 v[4][kNO / 4];
 #pragma unroll
-            for (int j = 0; j < kNO; j += 4) {
-                const float4 v = __ldg(src + j / 4);
-                z[j] += v.x; z[j + 1] += v.y; z[j + 2] += v.z; z[j + 3] += v.w;
+            for (int u = 0; u < 4; ++u) {
+                const float4* src = reinterpret_cast<const float4*>(partial + ((size_t)min(s0 + u, n_split - 1) * B + row) * kNO);
+#pragma unroll
+                for (int j = 0; j < kNO / 4; ++j) v[u][j] = __ldg(src + j);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (s0 + u < n_split) {
+#pragma unroll
+                    for (int j = 0; j < kNO; j += 4) {
+                        z[j] += v[u][j / 4].x; z[j + 1] += v[u][j / 4].y; z[j + 2] += v[u][j / 4].z; z[j + 3] += v[u][j / 4].w;
+                    }
+                }
             }
         }
         float mx = -INFINITY;
