@@ -176,6 +176,22 @@ int nm_adam_advance_f32(nm_adam_state* dev_state, void* stream);   /* post_updat
  * nonfinite (may be NULL): device int set to 1 if any gradient is NaN/Inf (SGD.py:80-83). */
 int nm_sgd_step_f32(float* param, const float* grad, float* mom, size_t n,
                     float lr, float momentum, int n_apply, int32_t* nonfinite, void* stream);
+/* The remaining optimizers, same one-pass 128-bit slab kernel, update applied n_apply times:
+ * Optimizer_RMSprop.update_params (RMSprop.py:103-109): cache = rho cache + (1-rho) g^2; p -= lr g / (sqrt(cache) + eps)
+ * Optimizer_Adagrad.update_params (Adagrad.py): cache += g^2; p -= lr g / (sqrt(cache) + eps)
+ * Optimizer_Nadam.update_params (Nadam.py): bc1 = 1-beta1^(t+1), bc2 = 1-beta2^(t+1) from the host in double;
+ *   m_hat = m/(bc1+eps), v_hat = v/(bc2+eps), p -= lr (beta1 m_hat + (1-beta1) g/(bc1+eps)) / (sqrt(v_hat) + eps) */
+int nm_rmsprop_step_f32(float* param, const float* grad, float* cache, size_t n, float lr, float rho, float eps,
+                        int n_apply, int32_t* nonfinite, void* stream);
+int nm_adagrad_step_f32(float* param, const float* grad, float* cache, size_t n, float lr, float eps,
+                        int n_apply, int32_t* nonfinite, void* stream);
+int nm_nadam_step_f32(float* param, const float* grad, float* m, float* v, size_t n, float lr, float beta1, float beta2,
+                      float eps, float bc1, float bc2, int n_apply, void* stream);
+/* Layer_Dropout.forward (Dropout.py:15-30): mask = Bernoulli(keep)/keep drawn on the device (Philox4x32-10, counter =
+ * (element/4, offset), key = seed), y = x * mask; the mask is kept for backward (Dropout.py:32-40: dx = dy * mask). */
+int nm_dropout_fwd_f32(const float* x, float* y, float* mask, size_t n, float keep, unsigned long long seed,
+                       unsigned long long offset, void* stream);
+int nm_mul_f32(float* y, const float* a, const float* b, size_t n, void* stream);      /* y = a * b elementwise */
 /* y = a*x (+ y if accumulate): FedAvg pre-scale n_i/N (Federated/utils.py:21-22). */
 int nm_scale_f32(float* y, const float* x, size_t n, float a, int accumulate, void* stream);
 

@@ -71,6 +71,11 @@ _SIGS = {
     "nm_adam_step_dev_f32": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
     "nm_adam_advance_f32": (_i, [_vp, _vp]),
     "nm_sgd_step_f32": (_i, [_vp, _vp, _vp, _sz, _f, _f, _i, _vp, _vp]),
+    "nm_rmsprop_step_f32": (_i, [_vp, _vp, _vp, _sz, _f, _f, _f, _i, _vp, _vp]),
+    "nm_adagrad_step_f32": (_i, [_vp, _vp, _vp, _sz, _f, _f, _i, _vp, _vp]),
+    "nm_nadam_step_f32": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _f, _i, _vp]),
+    "nm_dropout_fwd_f32": (_i, [_vp, _vp, _vp, _sz, _f, C.c_ulonglong, C.c_ulonglong, _vp]),
+    "nm_mul_f32": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "nm_scale_f32": (_i, [_vp, _vp, _sz, _f, _i, _vp]),
     "nm_tc_pack_conv_weights_bf16": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "nm_tc_conv3x3_fprop_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -222,25 +222,6 @@ __global__ void adam_advance_kernel(nm_adam_state* s) {
     if (s->decay != 0.f) s->lr = (float)((double)s->base_lr * (1.0 / (1.0 + (double)s->decay * (double)s->iterations)));
 }
 
-__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom,
-                           size_t n, float lr, float mu, int n_apply, int32_t* __restrict__ nonfinite) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-    bool bad = false;
-    for (; i < n; i += stride) {
-        float gv = g[i], pv = p[i];
-        bad |= !isfinite(gv);
-        if (mom) {
-            float mv = mom[i];
-            for (int a = 0; a < n_apply; ++a) { mv = mv * mu + lr * gv; pv -= mv; }
-            mom[i] = mv;
-        } else {
-            for (int a = 0; a < n_apply; ++a) pv += -lr * gv;
-        }
-        p[i] = pv;
-    }
-    if (nonfinite && bad) *nonfinite = 1;
-}
-
 __global__ void scale_kernel(float* __restrict__ y, const float* __restrict__ x, size_t n, float a, int accumulate) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) y[i] = accumulate ? y[i] + a * x[i] : a * x[i];
@@ -356,17 +337,6 @@ int nm_adam_step_dev_f32(float* param, const float* grad, float* m, float* v, si
 int nm_adam_advance_f32(nm_adam_state* dev_state, void* stream) {
     NM_REQUIRE(dev_state, "null pointer");
     return nm::launch_pdl("adam_advance", adam_advance_kernel, dim3(1), dim3(1), 0, nm::S(stream), dev_state);
-}
-
-int nm_sgd_step_f32(float* param, const float* grad, float* mom, size_t n,
-                    float lr, float momentum, int n_apply, int32_t* nonfinite, void* stream) {
-    NM_REQUIRE(param && grad, "null pointer");
-    NM_REQUIRE(n_apply >= 1, "n_apply must be >= 1");
-    NM_REQUIRE(momentum == 0.f || mom, "momentum needs a momentum buffer");
-    if (!n) return NM_OK;
-    sgd_kernel<<<ew_blocks(n, 256, 1), 256, 0, nm::S(stream)>>>(param, grad, momentum != 0.f ? mom : nullptr, n, lr,
-                                                               momentum, n_apply, nonfinite);
-    return nm::launched("sgd_step_f32");
 }
 
 int nm_scale_f32(float* y, const float* x, size_t n, float a, int accumulate, void* stream) {

@@ -354,6 +354,47 @@ def sgd_update(param, grad, mom, *, lr, momentum=0.0):
     return param - lr * grad, mom
 
 
+def rmsprop_update(param, grad, cache, *, lr, rho=0.9, eps=1e-7):
+    """Optimizer_RMSprop.update_params (src/optimizers/RMSprop.py:103-109): cache = rho cache + (1-rho) g^2;
+    param -= lr g / (sqrt(cache) + eps).  NaN/Inf gradients raise ValueError (:93-96)."""
+    if np.any(np.isnan(grad)) or np.any(np.isinf(grad)):
+        raise ValueError("Gradient contains NaN/Inf values.")
+    cache = rho * cache + (1.0 - rho) * grad ** 2
+    return param - lr * grad / (np.sqrt(cache) + eps), cache
+
+
+def adagrad_update(param, grad, cache, *, lr, eps=1e-7):
+    """Optimizer_Adagrad.update_params (src/optimizers/Adagrad.py, last two statements of the loop): cache += g^2;
+    param -= lr g / (sqrt(cache) + eps).  NaN/Inf gradients raise ValueError."""
+    if np.any(np.isnan(grad)) or np.any(np.isinf(grad)):
+        raise ValueError("Gradient contains NaN/Inf values.")
+    cache = cache + grad ** 2
+    return param - lr * grad / (np.sqrt(cache) + eps), cache
+
+
+def nadam_update(param, grad, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, t=0):
+    """Optimizer_Nadam.update_params (src/optimizers/Nadam.py): eps is added to the bias-correction denominators too.
+    ``t`` = optimizer.iterations, not advanced between the duplicate applications of Q1."""
+    m = beta1 * m + (1.0 - beta1) * grad
+    v = beta2 * v + (1.0 - beta2) * grad ** 2
+    b1p = 1.0 - beta1 ** (t + 1)
+    b2p = 1.0 - beta2 ** (t + 1)
+    m_hat = m / (b1p + eps)
+    v_hat = v / (b2p + eps)
+    m_nesterov = beta1 * m_hat + (1.0 - beta1) * grad / (b1p + eps)
+    return param - lr * m_nesterov / (np.sqrt(v_hat) + eps), m, v
+
+
+def dropout_forward(x, mask):
+    """Layer_Dropout.forward in training mode with a given mask = Bernoulli(keep)/keep (src/layers/Dropout.py:27-30)."""
+    return x * mask
+
+
+def dropout_backward(dvalues, mask):
+    """Layer_Dropout.backward (src/layers/Dropout.py:40)."""
+    return dvalues * mask
+
+
 def decayed_lr(lr, decay, iterations):
     """lr / (1 + decay * t), Adam.py:45-47 / SGD.py:52-53."""
     return lr * (1.0 / (1.0 + decay * iterations)) if decay else lr

@@ -126,6 +126,7 @@ class RefNet:
                                               for k, v in p.items()} for p in self.params]
         self.grads = [None] * len(spec)
         self.dinputs = [None] * len(spec)
+        self.dropout_masks = {}         # layer index -> mask for the next training forward (Layer_Dropout.binary_mask)
 
     # -- forward ------------------------------------------------------------
     def forward(self, x, training=True):
@@ -157,6 +158,11 @@ class RefNet:
             elif k == "softmax":
                 self.cache.append((a,))
                 a = R.softmax_forward(a)
+            elif k == "dropout":
+                # Dropout.py:21-30; the mask (Bernoulli(keep)/keep) is supplied by the caller: self.dropout_masks[layer index]
+                mask = self.dropout_masks[len(self.cache)] if training else None
+                self.cache.append((mask,))
+                a = R.dropout_forward(a, mask) if training else a.copy()
             else:
                 raise ValueError(k)
             self.outs.append(a)
@@ -191,6 +197,8 @@ class RefNet:
                 d = dx
             elif k == "flatten":
                 d = d.reshape(c[0])
+            elif k == "dropout":
+                d = R.dropout_backward(d, c[0])
             elif k == "pool":
                 a, idx = c
                 ph, pw = _pair(L["size"])
@@ -226,6 +234,15 @@ class RefNet:
                     elif o["kind"] == "sgd":
                         p[name], m = R.sgd_update(p[name], g, m, lr=self.current_lr,
                                                   momentum=o["momentum"])
+                    # the three below keep per-tensor state here; the reference keys it by the bare parameter name, which
+                    # is the same thing for the single-trainable-layer models it can run them on
+                    elif o["kind"] == "rmsprop":
+                        p[name], m = R.rmsprop_update(p[name], g, m, lr=self.current_lr, rho=o.get("rho", 0.9), eps=o["eps"])
+                    elif o["kind"] == "adagrad":
+                        p[name], m = R.adagrad_update(p[name], g, m, lr=self.current_lr, eps=o["eps"])
+                    elif o["kind"] == "nadam":
+                        p[name], m, v = R.nadam_update(p[name], g, m, v, lr=self.current_lr, beta1=o["beta_1"],
+                                                       beta2=o["beta_2"], eps=o["eps"], t=self.iterations)
                     else:
                         raise ValueError(o["kind"])
                     self.state[i][name] = (m, v)

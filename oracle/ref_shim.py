@@ -99,10 +99,11 @@ def build_model(spec, params, *, optimizer="adam", lr=0.001, momentum=0.0, decay
     """Build a reference ``Model`` from an oracle.ref_net spec with given initial params."""
     load()
     from NeuromahRef.src.core import Model
-    from NeuromahRef.src.layers import Layer_Conv2D, Layer_MaxPooling2D, Layer_Dense, Layer_Flatten
+    from NeuromahRef.src.layers import Layer_Conv2D, Layer_MaxPooling2D, Layer_Dense, Layer_Flatten, Layer_Dropout
     from NeuromahRef.src.activations import Activation_ReLU, Activation_Softmax
     from NeuromahRef.src.losses import Loss_CategoricalCrossentropy
-    from NeuromahRef.src.optimizers import Optimizer_Adam, Optimizer_SGD
+    from NeuromahRef.src.optimizers import (Optimizer_Adam, Optimizer_SGD, Optimizer_RMSprop, Optimizer_Adagrad,
+                                            Optimizer_Nadam)
     from NeuromahRef.src.metrics import Accuracy_Categorical
 
     Conv = wired_conv_class() if conv_backward == "wired" else Layer_Conv2D
@@ -121,14 +122,19 @@ def build_model(spec, params, *, optimizer="adam", lr=0.001, momentum=0.0, decay
                                 weight_regularizer_l1=L.get("l1", 0), weight_regularizer_l2=L.get("l2", 0))
         elif k == "softmax":
             layer = Activation_Softmax()
+        elif k == "dropout":
+            layer = Layer_Dropout(L["rate"])
         else:
             raise ValueError(k)
         if p is not None:
             layer.weights = np.array(p["weights"], dtype=np.float64, copy=True)
             layer.biases = np.array(p["biases"], dtype=np.float64, copy=True)
         model.add(layer)
-    opt = (Optimizer_Adam(learning_rate=lr, decay=decay) if optimizer == "adam"
-           else Optimizer_SGD(learning_rate=lr, decay=decay, momentum=momentum))
+    opt = {"adam": lambda: Optimizer_Adam(learning_rate=lr, decay=decay),
+           "sgd": lambda: Optimizer_SGD(learning_rate=lr, decay=decay, momentum=momentum),
+           "rmsprop": lambda: Optimizer_RMSprop(learning_rate=lr, decay=decay),
+           "adagrad": lambda: Optimizer_Adagrad(learning_rate=lr, decay=decay),
+           "nadam": lambda: Optimizer_Nadam(learning_rate=lr, decay=decay)}[optimizer]()
     model.set(loss=Loss_CategoricalCrossentropy, optimizer=opt, accuracy=Accuracy_Categorical)
     model.finalize()
     model.loss.new_pass()          # Model.train does this at the start of every epoch (:133-134)

@@ -66,6 +66,42 @@ def mlp_sgd():
                         final_params=flat_params(model).astype(np.float32))
 
 
+def single_layer_optimizers():
+    """RMSprop / Adagrad / Nadam keep their state keyed by the bare parameter name (RMSprop.py:99-101), so the reference
+    only runs them on a model with ONE trainable layer: softmax regression 64 -> 10, batch 32, 20 steps, with the
+    duplicate application per step of SURVEY Q1."""
+    spec = [{"kind": "dense", "n_in": 64, "n_out": 10, "relu": False}, {"kind": "softmax"}]
+    out = {}
+    for kind, lr, decay in (("rmsprop", 0.01, 1e-3), ("adagrad", 0.05, 0.0), ("nadam", 0.01, 1e-2)):
+        params = ref_net.init_params(spec, np.random.RandomState(31))
+        model = ref_shim.build_model(spec, params, optimizer=kind, lr=lr, decay=decay)
+        x, y = data(32, 32 * 20, (64,))
+        losses = []
+        for s in range(20):
+            losses.append(ref_shim.train_step(model, x[s * 32:(s + 1) * 32], y[s * 32:(s + 1) * 32])["loss"])
+        out[f"{kind}_losses"] = np.array(losses)
+        out[f"{kind}_params"] = flat_params(model).astype(np.float64)
+    np.savez_compressed(os.path.join(HERE, "optimizers_single_layer_20steps.npz"), **out)
+
+
+def dropout_mlp():
+    """Dense(64->32, ReLU) -> Dropout(0.3) -> Dense(32->10) -> Softmax, Adam, batch 16, 10 steps.  The masks the
+    reference drew (np.random.binomial, Dropout.py:27) are stored so the device layer can replay them (fixed_mask)."""
+    spec = [{"kind": "dense", "n_in": 64, "n_out": 32, "relu": True}, {"kind": "dropout", "rate": 0.3},
+            {"kind": "dense", "n_in": 32, "n_out": 10, "relu": False}, {"kind": "softmax"}]
+    params = ref_net.init_params(spec, np.random.RandomState(41))
+    model = ref_shim.build_model(spec, params, optimizer="adam", lr=0.01)
+    x, y = data(42, 16 * 10, (64,))
+    np.random.seed(123)
+    losses, masks = [], []
+    for s in range(10):
+        losses.append(ref_shim.train_step(model, x[s * 16:(s + 1) * 16], y[s * 16:(s + 1) * 16])["loss"])
+        masks.append(np.array(model.layers[1].binary_mask, dtype=np.float32))
+    infer = model.forward(x[:16], training=False)
+    np.savez_compressed(os.path.join(HERE, "dropout_mlp_10steps.npz"), losses=np.array(losses), masks=np.stack(masks),
+                        final_params=flat_params(model).astype(np.float64), infer=np.asarray(infer, dtype=np.float64))
+
+
 def cnn_small():
     """MNIST CNN of examples/test_Conv2D_MNIST.py:47-53, batch 4, 3 Adam steps, wired conv backward."""
     spec = ref_net.mnist_cnn_spec()
@@ -173,7 +209,7 @@ def ops():
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (mlp_200, mlp_sgd, cnn_small, cnn_stub, cnn_200, ops):
+    for fn in (mlp_200, mlp_sgd, cnn_small, cnn_stub, cnn_200, ops, single_layer_optimizers, dropout_mlp):
         if not only or fn.__name__ in only:
             fn()
     for f in sorted(os.listdir(HERE)):

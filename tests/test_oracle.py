@@ -115,6 +115,36 @@ def test_mlp_sgd_golden():
     np.testing.assert_allclose(net.flat(), g["final_params"], rtol=1e-6, atol=1e-7)
 
 
+@pytest.mark.parametrize("kind,lr,decay,eps", [("rmsprop", 0.01, 1e-3, 1e-7), ("adagrad", 0.05, 0.0, 1e-7), ("nadam", 0.01, 1e-2, 1e-8)])
+def test_single_layer_optimizer_goldens(kind, lr, decay, eps):
+    """RMSprop / Adagrad / Nadam restatements against the unmodified reference (softmax regression, 20 steps, Q1 doubling)."""
+    g = golden("optimizers_single_layer_20steps.npz")
+    spec = [{"kind": "dense", "n_in": 64, "n_out": 10, "relu": False}, {"kind": "softmax"}]
+    net = ref_net.RefNet(spec, ref_net.init_params(spec, np.random.RandomState(31)), optimizer=kind, lr=lr, decay=decay, eps=eps)
+    x, y = synth(32, 32 * 20, (64,))
+    losses = [net.step(x[s * 32:(s + 1) * 32], y[s * 32:(s + 1) * 32])["loss"] for s in range(20)]
+    np.testing.assert_allclose(losses, g[f"{kind}_losses"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(net.flat(), g[f"{kind}_params"], rtol=1e-9, atol=1e-12)
+
+
+def test_dropout_mlp_golden():
+    """Layer_Dropout fwd/bwd restatement with the masks the reference drew (Dropout.py:27), Adam, 10 steps + inference."""
+    g = golden("dropout_mlp_10steps.npz")
+    spec = [{"kind": "dense", "n_in": 64, "n_out": 32, "relu": True}, {"kind": "dropout", "rate": 0.3},
+            {"kind": "dense", "n_in": 32, "n_out": 10, "relu": False}, {"kind": "softmax"}]
+    params = ref_net.init_params(spec, np.random.RandomState(41))
+    net = ref_net.RefNet(spec, params, optimizer="adam", lr=0.01)
+    x, y = synth(42, 16 * 10, (64,))
+    assert set(np.unique(g["masks"])) == {0.0, np.float32(1 / 0.7)}
+    losses = []
+    for s in range(10):
+        net.dropout_masks[1] = g["masks"][s].astype(np.float64)
+        losses.append(net.step(x[s * 16:(s + 1) * 16], y[s * 16:(s + 1) * 16])["loss"])
+    np.testing.assert_allclose(losses, g["losses"], rtol=1e-6, atol=1e-8)       # masks are stored as float32
+    np.testing.assert_allclose(net.flat(), g["final_params"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(net.forward(x[:16], training=False), g["infer"], rtol=1e-5, atol=1e-7)
+
+
 @pytest.mark.parametrize("mode,fixture,steps", [("wired", "cnn_small_3steps.npz", 3), ("stub", "cnn_stub_2steps.npz", 2)])
 def test_cnn_golden(mode, fixture, steps):
     g = golden(fixture)
