@@ -414,6 +414,18 @@ class Model:
         with open(path, "rb") as f:
             self.set_parameters(pickle.load(f))
 
+    def save(self, path):
+        """Whole-model checkpoint (Model.py:396-411): layers + parameters + optimizer state, as a host-side description
+        (see neuromah_b200/checkpoint.py for why it is not a pickle of the live object)."""
+        from ... import checkpoint
+        checkpoint.save(self, path)
+
+    @staticmethod
+    def load(path):
+        """Rebuild and finalize the model stored by ``save`` (Model.py:413-417)."""
+        from ... import checkpoint
+        return checkpoint.load(path)
+
 
 def _host_labels(y):
     """Class ids from sparse labels or one-hot rows (argmax, as the reference's fused gradient does)."""

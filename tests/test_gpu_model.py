@@ -252,6 +252,48 @@ def test_save_and_load_parameters_roundtrip(tmp_path):
     np.testing.assert_array_equal(m1.arena.host_params(), m2.arena.host_params())
 
 
+@pytest.mark.parametrize("case", ["mlp_dropout_rmsprop", "cnn_bf16_adam"])
+def test_save_load_whole_model_resumes_training_identically(tmp_path, case):
+    """Model.save / Model.load (Model.py:396-417): the reloaded model carries parameters, optimizer state and iteration
+    count, so continuing training on both gives the same parameters."""
+    from neuromah_b200.src.core import Model
+    from neuromah_b200.src.layers import Layer_Dense, Layer_Dropout
+    from neuromah_b200.src.activations import Activation_ReLU, Activation_Softmax
+    from neuromah_b200.src.losses import Loss_CategoricalCrossentropy
+    from neuromah_b200.src.optimizers import Optimizer_RMSprop
+    from neuromah_b200.src.metrics import Accuracy_Categorical
+    if case == "mlp_dropout_rmsprop":
+        m1 = Model()
+        for l in (Layer_Dense(20, 16, activation=Activation_ReLU(), weight_regularizer_l2=1e-3), Layer_Dropout(0.25, seed=9),
+                  Layer_Dense(16, 10), Activation_Softmax()):
+            m1.add(l)
+        m1.set(loss=Loss_CategoricalCrossentropy, optimizer=Optimizer_RMSprop(learning_rate=0.01, decay=1e-2),
+               accuracy=Accuracy_Categorical)
+        m1.finalize()
+        x, y = synth(50, 32 * 6, (20,))
+        B = 32
+    else:
+        spec = ref_net.mnist_cnn_spec()
+        m1 = build(spec, ref_net.init_params(spec, np.random.RandomState(12)), mode="bf16", learning_rate=0.002, decay=1e-3)
+        x, y = synth(51, 16 * 6, (1, 28, 28))
+        B = 16
+    for s in range(3):
+        m1.train_step(x[s * B:(s + 1) * B], y[s * B:(s + 1) * B])
+    path = str(tmp_path / "model.pkl")
+    m1.save(path)
+    m2 = Model.load(path)
+    assert m2.mode == m1.mode and m2.optimizer.iterations == 3 and type(m2.optimizer) is type(m1.optimizer)
+    assert [type(l).__name__ for l in m2.layers] == [type(l).__name__ for l in m1.layers]
+    np.testing.assert_array_equal(m1.arena.host_params(), m2.arena.host_params())
+    for a, b in zip(m1.arena.state, m2.arena.state):
+        np.testing.assert_array_equal(np.asarray(a), np.asarray(b))
+    for s in range(3, 6):
+        m1.train_step(x[s * B:(s + 1) * B], y[s * B:(s + 1) * B])
+        m2.train_step(x[s * B:(s + 1) * B], y[s * B:(s + 1) * B])
+    np.testing.assert_allclose(m1.arena.host_params(), m2.arena.host_params(), rtol=1e-6, atol=1e-7)
+    assert m2.optimizer.current_learning_rate == pytest.approx(m1.optimizer.current_learning_rate)
+
+
 def test_vgg_style_stack_per_step_parity():
     """BASELINE.json config 4 (VGG-style Conv2D stack on CIFAR-shaped 32x32x3 data, He init), reduced in width so the
     NumPy oracle finishes in seconds: C(3->8) C(8->8) P C(8->16) C(16->16) P Flatten Dense(1024->10) Softmax, FP32-exact
