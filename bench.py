@@ -176,6 +176,42 @@ class ClockSampler:
                 "samples": len(inside), "window": window, "reasons": reasons}
 
 
+def optimizer_bandwidth(n=1 << 28, reps=10):
+    """the MNIST-CNN parameter slab (0.2 MB) is far too small to say anything about the optimizer
+    kernels' bandwidth, so the same kernels are also timed on a synthetic slab of 2^28 parameters (1 GiB per buffer)."""
+    import ctypes as C
+    from neuromah_b200 import device
+    from neuromah_b200._lib import lib
+    peak = peaks()["hbm_gbs"]
+    bufs = [device.DeviceArray.zeros((n,)) for _ in range(4)]
+    p, g, m, v = bufs
+    lib.nm_memset(g.p, 0x3c, g.nbytes, device.stream())          # small non-zero gradients (0x3c3c3c3c ~ 0.0115)
+    s = device.stream()
+    cases = {
+        "adam_step_f32": (28, lambda: lib.nm_adam_step_f32(p.p, g.p, m.p, v.p, n, 1e-3, 0.9, 0.999, 1e-7, 0.1, 0.001, 2, s)),
+        "sgd_step_f32": (12, lambda: lib.nm_sgd_step_f32(p.p, g.p, None, n, 1e-3, 0.0, 2, None, s)),
+        "sgd_momentum_step_f32": (20, lambda: lib.nm_sgd_step_f32(p.p, g.p, m.p, n, 1e-3, 0.9, 2, None, s)),
+        "rmsprop_step_f32": (20, lambda: lib.nm_rmsprop_step_f32(p.p, g.p, m.p, n, 1e-3, 0.9, 1e-7, 2, None, s)),
+        "nadam_step_f32": (28, lambda: lib.nm_nadam_step_f32(p.p, g.p, m.p, v.p, n, 1e-3, 0.9, 0.999, 1e-8, 0.1, 0.001, 2, s)),
+    }
+    e0, e1 = device.new_event(), device.new_event()
+    out = {"params": n, "peak_gbs": peak, "n_apply": 2}
+    ms = C.c_float()
+    for name, (bpp, call) in cases.items():
+        for _ in range(3):
+            call()
+        lib.nm_event_record(e0, s)
+        for _ in range(reps):
+            call()
+        lib.nm_event_record(e1, s)
+        device.synchronize()
+        lib.nm_event_elapsed_ms(e0, e1, C.byref(ms))
+        gbs = bpp * n / (ms.value / reps * 1e-3) / 1e9
+        out[name] = {"bytes_per_param": bpp, "ms": round(ms.value / reps, 4), "gbs": round(gbs, 1), "frac": round(gbs / peak, 3)}
+    del bufs
+    return out
+
+
 def cpu_arm(steps, warmup, sample):
     """The reference's CPU path as the oracle port (NumPy + the reference's compiled max-pool), all host
     threads NumPy's BLAS will use.  Returns (samples/s, ms_per_step, cores, description)."""
@@ -396,6 +432,8 @@ def main():
                        "l2": "inputs cycle over 8 distinct batches; the per-step activation working set "
                              "(>1 GB) is far larger than the 126 MB L2, so no explicit flush is needed"},
             "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
+    if world == 1:
+        line["hbm_kernels"] = optimizer_bandwidth()
     if world == 1 and not args.no_cpu_baseline:
         v, cms, cores, desc = cpu_arm(6, 1, REF_SAMPLE)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}

@@ -1,12 +1,13 @@
 // The remaining optimizers of the reference as variants of one coalesced, 128-bit vectorised slab kernel
 // (SURVEY.md 8f row 3), and Layer_Dropout.  Each is HBM-bound: one pass over (param, grad, state...) per step,
 // the update applied n_apply times in registers (Model registers every trainable layer twice: Model.py:56-59, :82-83).
-//   Optimizer_SGD      src/optimizers/SGD.py:85-97      12 B/param (16 with momentum)
+//   Optimizer_SGD      src/optimizers/SGD.py:85-97      12 B/param (20 with momentum)
 //   Optimizer_RMSprop  src/optimizers/RMSprop.py:103-109  20 B/param
 //   Optimizer_Adagrad  src/optimizers/Adagrad.py (cache += g^2; p -= lr g / (sqrt(cache) + eps))  20 B/param
 //   Optimizer_Nadam    src/optimizers/Nadam.py (eps added to the bias corrections as well)  28 B/param
 //   Layer_Dropout      src/layers/Dropout.py:15-40: mask = Bernoulli(keep) / keep, drawn with Philox4x32-10 on the device
 #include "nm_common.cuh"
+#include "nm_adam.cuh"      // nm_sqrt_approx: MUFU square root / division keep these kernels HBM-bound (see there)
 
 namespace {
 
@@ -23,16 +24,17 @@ __device__ __forceinline__ void opt_one(float& p, float g, float& s1, float& s2,
             p -= s1;
         } else if (KIND == K_RMSPROP) {
             s1 = h.a * s1 + (1.f - h.a) * g * g;                      // RMSprop.py:103-106
-            p -= h.lr * g / (sqrtf(s1) + h.eps);                      // RMSprop.py:109
+            p -= h.lr * __fdividef(g, nm_sqrt_approx(s1) + h.eps);    // RMSprop.py:109
         } else if (KIND == K_ADAGRAD) {
             s1 += g * g;
-            p -= h.lr * g / (sqrtf(s1) + h.eps);
+            p -= h.lr * __fdividef(g, nm_sqrt_approx(s1) + h.eps);
         } else {
             s1 = h.a * s1 + (1.f - h.a) * g;                          // Nadam: momentums / caches
             s2 = h.b * s2 + (1.f - h.b) * g * g;
-            const float mh = s1 / (h.c1 + h.eps), vh = s2 / (h.c2 + h.eps);      // c1 = 1 - beta1^(t+1), c2 = 1 - beta2^(t+1)
-            const float mn = h.a * mh + (1.f - h.a) * g / (h.c1 + h.eps);
-            p -= h.lr * mn / (sqrtf(vh) + h.eps);
+            const float i1 = __frcp_rn(h.c1 + h.eps), i2 = __frcp_rn(h.c2 + h.eps);   // c1 = 1 - beta1^(t+1), c2 = 1 - beta2^(t+1)
+            const float mh = s1 * i1, vh = s2 * i2;
+            const float mn = h.a * mh + (1.f - h.a) * g * i1;
+            p -= h.lr * __fdividef(mn, nm_sqrt_approx(vh) + h.eps);
         }
     }
 }
