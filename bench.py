@@ -264,7 +264,9 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--batch", type=int, default=BATCH, help="per-GPU batch (weak scaling) or global batch (--scaling strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, BASELINE.json): --batch samples per GPU; strong: --batch is the GLOBAL batch, split N ways")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"],
                     help="bf16 = fused tensor-core plan (tcgen05), fp32 = FP32-exact CUDA-core kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -293,6 +295,10 @@ def main():
         clocks.start()                  # early: nvidia-smi takes a while to produce its first sample
     device.init(local_rank)
     W, K, B = max(args.warmup, 3), args.steps, args.batch
+    if args.scaling == "strong":
+        if B % world:
+            raise SystemExit(f"--scaling strong: global batch {B} is not divisible by {world} GPUs")
+        B //= world
 
     def barrier():
         device.synchronize()
@@ -419,7 +425,7 @@ def main():
                 "peak_source": pk["source"] + (" bf16 dense sustained (cuBLAS)" if bound == "tensor" else " HBM copy"),
                 "kernels": per_kernel}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": "MNIST CNN (Conv3x3x32-ReLU-Pool2-Conv3x3x64-ReLU-Pool2-Dense10-Softmax), "
                                    "softmax-CE, Adam x2 per layer (reference quirk Q1)",

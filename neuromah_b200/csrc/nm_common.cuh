@@ -65,6 +65,22 @@ inline int launch_pdl(const char* name, void (*kernel)(KArgs...), dim3 grid, dim
     if (e != cudaSuccess) { cudaGetLastError(); return cuda_fail(e, name); }
     return launched(name);
 }
+// same, plus a thread-block cluster shape (the CTAs of a cluster are co-scheduled and can read each other's shared memory)
+template <typename... KArgs, typename... Args>
+inline int launch_pdl_cluster(const char* name, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              dim3 cluster, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = cluster.x; attr[1].val.clusterDim.y = cluster.y; attr[1].val.clusterDim.z = cluster.z;
+    cfg.attrs = attr; cfg.numAttrs = 2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    if (e != cudaSuccess) { cudaGetLastError(); return cuda_fail(e, name); }
+    return launched(name);
+}
 }  // namespace nm
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
