@@ -66,6 +66,7 @@ dense_head_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     uint64_t* done = empty + FWD_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
     double* red = reinterpret_cast<double*>(tmem_slot + 2);            // [4 warps][2]
+    int* last_flag = reinterpret_cast<int*>(red + 8);
     float* part = reinterpret_cast<float*>(smem);                      // [128][16] partial logits, reuses stage 0 once the MMAs are done
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int splits = gridDim.y, split = blockIdx.y;                  // cluster = (1, splits, 1): the rank in the cluster is blockIdx.y
@@ -148,12 +149,20 @@ dense_head_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 #pragma unroll
             for (int j = 0; j < kNO; ++j) z[j] = 0.f;
             const uint32_t local = smem_u32(part + lr * kNO);
-            for (int s = 0; s < splits; ++s) {
+            for (int s0 = 0; s0 < splits; s0 += 4) {               // four splits' loads in flight together, summed in split order
+                float4 v[4][kNO / 4];
 #pragma unroll
-                for (int j = 0; j < kNO; j += 4) {
-                    const float4 v = ld_cluster_f4(local + j * 4, (uint32_t)s);
-                    z[j] += v.x; z[j + 1] += v.y; z[j + 2] += v.z; z[j + 3] += v.w;
-                }
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int j = 0; j < kNO / 4; ++j) v[u][j] = ld_cluster_f4(local + j * 16, (uint32_t)min(s0 + u, splits - 1));
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (s0 + u < splits) {
+#pragma unroll
+                        for (int j = 0; j < kNO; j += 4) {
+                            z[j] += v[u][j / 4].x; z[j + 1] += v[u][j / 4].y; z[j + 2] += v[u][j / 4].z; z[j + 3] += v[u][j / 4].w;
+                        }
+                    }
             }
             const int n_out = p.n_out;
             float mx = -INFINITY;
@@ -204,16 +213,25 @@ dense_head_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         for (int o = 16; o; o >>= 1) { l += __shfl_xor_sync(0xffffffffu, l, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
         if (warp >= 2 && lane == 0) { red[(warp - 2) * 2] = l; red[(warp - 2) * 2 + 1] = c; }
         __syncthreads();
+        const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x, n_cta = gridDim.x * gridDim.y;
         if (threadIdx.x == 0) {
-            const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x, n_cta = gridDim.x * gridDim.y;
             p.block_part[2 * cta] = (red[0] + red[2]) + (red[4] + red[6]);
             p.block_part[2 * cta + 1] = (red[1] + red[3]) + (red[5] + red[7]);
             __threadfence();
-            if (atomicAdd(p.counter, 1u) == n_cta - 1) {
-                __threadfence();
-                double tl = 0.0, tc_ = 0.0;
-                for (unsigned b = 0; b < n_cta; ++b) { tl += __ldcg(p.block_part + 2 * b); tc_ += __ldcg(p.block_part + 2 * b + 1); }
-                p.accum[0] += tl; p.accum[1] += tc_;
+            *last_flag = atomicAdd(p.counter, 1u) == n_cta - 1;
+        }
+        __syncthreads();
+        if (*last_flag && warp == 0) {
+            // the last CTA sums every CTA's pair: lane l takes CTAs l, l+32, ... in order, then a fixed shuffle tree
+            // (deterministic), all loads in flight at once; the running sums are bumped with fire-and-forget reductions
+            __threadfence();
+            double tl = 0.0, tc_ = 0.0;
+            for (unsigned b = lane; b < n_cta; b += 32) { tl += __ldcg(p.block_part + 2 * b); tc_ += __ldcg(p.block_part + 2 * b + 1); }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { tl += __shfl_xor_sync(0xffffffffu, tl, o); tc_ += __shfl_xor_sync(0xffffffffu, tc_, o); }
+            if (lane == 0) {
+                atomicAdd(p.accum, tl);                          // one writer per launch, stream-ordered: still deterministic
+                atomicAdd(p.accum + 1, tc_);
                 *p.counter = 0u;
             }
         }
