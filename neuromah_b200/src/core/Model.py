@@ -136,6 +136,7 @@ class Model:
 
     # ------------------------------------------------------------ CUDA-graph replay of the fused step ----
     graph_steps = True          # replay the tensor-core plan's training step from a CUDA graph when possible
+    graph_fork = True           # ... with the Dense wgrad as a sibling branch of the conv backward chain
 
     def _graph_train_step(self, x, labels):
         """The whole step (re-pack, forward, loss sums, backward, Adam, on-device advance) as ONE graph launch.
@@ -159,7 +160,7 @@ class Model:
             lib.nm_graph_begin(stream())
             try:
                 self.plan.forward(x, labels, accum=self._accum, inv_batch=None if gb is None else 1.0 / gb)
-                self.plan.backward(gb)
+                self.plan.backward(gb, fork=self.graph_fork)
                 if self.comm is not None:
                     opt.update_arena_dp(self.arena, self.comm, n_apply=n_apply)
                 else:

@@ -129,6 +129,8 @@ class TcCnnPlan:
         ws = max(lib.nm_tc_conv3x3_wgrad_workspace(32, 64), lib.nm_tc_conv3x3_bwd_workspace(32, 64), lib.nm_tc_conv1_bwd_workspace(32),
                  lib.nm_tc_dense_wgrad_workspace(B, K), lib.nm_tc_dense_bwd_unpool_workspace(64))
         self.ws = DeviceArray((ws,), np.uint8)
+        self.ws_dw = DeviceArray((max(lib.nm_tc_dense_wgrad_workspace(B, K), 256),), np.uint8)   # own workspace: the Dense
+        #                                                     wgrad may run on a side branch next to the conv backward kernels
         self.ws_head = z((lib.nm_tc_dense_softmax_ce_workspace(B, K),), np.uint8)   # zero-filled once (ticket counter)
 
     def pack_weights(self):
@@ -167,18 +169,31 @@ class TcCnnPlan:
         self.model.softmax_classifier_output.dinputs = self.dlogits[0:B]
         return out
 
-    def backward(self, grad_batch=None, comm=None):
+    def backward(self, grad_batch=None, comm=None, fork=False):
         """``comm``: data-parallel communicator.  The gradient slab is all-reduced in two buckets on the communication
         stream: everything but the first conv's gradients as soon as conv2's wgrad has been enqueued (it then overlaps
-        conv2 dgrad + the whole conv1 backward), the first conv's 320 floats after the last kernel."""
+        conv2 dgrad + the whole conv1 backward), the first conv's 320 floats after the last kernel.
+        ``fork``: put the Dense wgrad on a side stream (a sibling branch when the step is captured into a CUDA graph): it
+        only needs the head's outputs, so it fills the SMs that the unpool / conv backward kernels leave idle in their tails
+        instead of sitting on the critical path; the streams join before the optimizer."""
         B = self.x.shape[0]
         s = stream()
         scale = 1.0 / (B if grad_batch is None else grad_batch)
         if not getattr(self, "dl_hilo_valid", False):      # dlogits were written by the public-API backward
             lib.nm_tc_pack_dlogits_bf16(self.dlogits.p, self.dl_hilo.p, B, self.n_out, s)
+        sd = s
+        if fork:
+            if getattr(self, "_side", None) is None:
+                from .device import new_event, new_stream
+                self._side, self._ev_fork, self._ev_join = new_stream(), new_event(), new_event()
+            sd = self._side
+            lib.nm_event_record(self._ev_fork, s)
+            lib.nm_stream_wait_event(sd, self._ev_fork)
         _timed('tc_dense_wgrad', lib.nm_tc_dense_wgrad_bf16, self.act2.p, self.dl_hilo.p, self.dlogits.p, self.de.weights.p, self.de.dweights.p, self.de.dbiases.p,
-                                   self.ws.p, self.ws.nbytes, B, self.K, self.n_out, 49, 64, float(scale),
-                                   float(self.de.weight_regularizer_l1), float(self.de.weight_regularizer_l2), s)
+                                   self.ws_dw.p, self.ws_dw.nbytes, B, self.K, self.n_out, 49, 64, float(scale),
+                                   float(self.de.weight_regularizer_l1), float(self.de.weight_regularizer_l2), sd)
+        if fork:
+            lib.nm_event_record(self._ev_join, sd)
         # Dense dgrad + pool backward + ReLU' -> conv2's dY (+ conv2 bias gradient), then conv2 dgrad + wgrad in one pass
         # over dY.  (nm_tc_dense_bwd_pool_bf16 + nm_tc_conv3x3_bwd_pool_bf16 keep dY out of HBM altogether by rebuilding
         # the tile in shared memory, but measured slower: 23 + 100 us against 38 + 73 us -- the builder warps' generic
@@ -194,6 +209,8 @@ class TcCnnPlan:
                                  self.ws.p, self.ws.nbytes, B, 28, 28, 32, s)
         if comm is not None:
             comm.allreduce_async(self.model.arena.grads, 0, self._first_conv_floats())
+        if fork:
+            lib.nm_stream_wait_event(s, self._ev_join)
 
     def _first_conv_floats(self):
         """Length (floats, padded) of the first conv's slice at the start of the arena slabs."""
