@@ -224,6 +224,9 @@ int nm_tc_conv3x3_wgrad_bf16(const void* x_pad, const void* dy_pad, float* dw, v
 size_t nm_tc_conv3x3_bwd_workspace(int C, int OC);
 int nm_tc_conv3x3_bwd_bf16(const void* x_pad, const void* dy_pad, const void* w_packed_dgrad, float* dw, void* dx_grid,
                            void* workspace, size_t workspace_bytes, int N, int H, int W, int C, int OC, void* stream);
+/* dw == NULL in nm_tc_conv3x3_bwd_*: the per-CTA wgrad partials stay in the workspace and this call reduces them (fixed
+ * order) later -- e.g. on a sibling graph branch while the previous layer's backward already consumes dx_grid. */
+int nm_tc_conv3x3_bwd_reduce_f32(const void* workspace, float* dw, int N, int H, int W, int C, int OC, void* stream);
 /* The same, with dY never materialised: it is rebuilt per tile in shared memory from the ReLU-masked gradient of the
  * POOLED conv output (dpool bf16 [N][H/2*W/2][OC], nm_tc_dense_bwd_pool_bf16) and the pool arg-max nibbles
  * (idx [N][H/2*W/2][OC/2]) -- MaxPooling2D.backward's routing is one byte permute per two channels. */

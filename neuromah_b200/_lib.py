@@ -84,6 +84,7 @@ _SIGS = {
     "nm_tc_conv3x3_wgrad_bf16": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_conv3x3_bwd_workspace": (_sz, [_i, _i]),
     "nm_tc_conv3x3_bwd_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
+    "nm_tc_conv3x3_bwd_reduce_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_conv3x3_bwd_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_dense_bwd_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_pack_conv1_weights_bf16": (_i, [_vp, _vp, _i, _vp]),

@@ -787,7 +787,7 @@ size_t nm_tc_conv3x3_bwd_workspace(int C, int OC) { return (size_t)sm_count() * 
 static int launch_conv_bwd(bool build, const void* x_pad, const void* dy_pad, const void* dpool, const void* idx,
                            const void* w_packed_dgrad, float* dw, void* dx_grid, void* workspace, size_t workspace_bytes,
                            int N, int H, int W, int C, int OC, void* stream) {
-    NM_REQUIRE(x_pad && w_packed_dgrad && dw && dx_grid && workspace, "null pointer");
+    NM_REQUIRE(x_pad && w_packed_dgrad && dx_grid && workspace, "null pointer");      // dw == NULL: leave the per-CTA partials in the workspace
     NM_REQUIRE(N > 0 && H > 0 && H % 2 == 0, "bad dimensions");
     if (!(C == BW_C && OC == BW_OC && W + 2 == BW_WP))
         return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv3x3_bwd_*: only C=32, OC=64, W=14 is instantiated");
@@ -821,10 +821,21 @@ static int launch_conv_bwd(bool build, const void* x_pad, const void* dy_pad, co
     rc = build ? nm::launch_pdl("conv3x3_bwd_tc", conv3x3_bwd_tc_kernel<true>, dim3(grid), dim3(640), smem, nm::S(stream), mdy, mx, mw, p)
                : nm::launch_pdl("conv3x3_bwd_tc", conv3x3_bwd_tc_kernel<false>, dim3(grid), dim3(384), smem, nm::S(stream), mdy, mx, mw, p);
     if (rc) return rc;
+    if (!dw) return NM_OK;
     const int total = OC * 9 * C;
     NM_REQUIRE(grid <= WR_SLICES * WR_PER, "more CTAs than the reduction covers");
     return nm::launch_pdl("wgrad_reduce", wgrad_reduce_kernel, dim3(nm_cdiv(total, 64)), dim3(64 * WR_SLICES), 0, nm::S(stream),
                           (const float*)p.partial, dw, grid, OC, C);
+}
+
+int nm_tc_conv3x3_bwd_reduce_f32(const void* workspace, float* dw, int N, int H, int W, int C, int OC, void* stream) {
+    NM_REQUIRE(workspace && dw, "null pointer");
+    NM_REQUIRE(N > 0 && H > 0 && C == BW_C && OC == BW_OC && W + 2 == BW_WP, "bad dimensions");
+    const int num_tiles = (N * (H + 2) * BW_WP + TILE_M - 1) / TILE_M;
+    const int grid = num_tiles < sm_count() ? num_tiles : sm_count();          // the grid nm_tc_conv3x3_bwd_* launched
+    NM_REQUIRE(grid <= WR_SLICES * WR_PER, "more CTAs than the reduction covers");
+    return nm::launch_pdl("wgrad_reduce", wgrad_reduce_kernel, dim3(nm_cdiv(OC * 9 * C, 64)), dim3(64 * WR_SLICES), 0, nm::S(stream),
+                          static_cast<const float*>(workspace), dw, grid, OC, C);
 }
 
 int nm_tc_conv3x3_bwd_bf16(const void* x_pad, const void* dy_pad, const void* w_packed_dgrad, float* dw, void* dx_grid,

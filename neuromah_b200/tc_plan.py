@@ -129,6 +129,7 @@ class TcCnnPlan:
         ws = max(lib.nm_tc_conv3x3_wgrad_workspace(32, 64), lib.nm_tc_conv3x3_bwd_workspace(32, 64), lib.nm_tc_conv1_bwd_workspace(32),
                  lib.nm_tc_dense_wgrad_workspace(B, K), lib.nm_tc_dense_bwd_unpool_workspace(64))
         self.ws = DeviceArray((ws,), np.uint8)
+        self.ws_c1 = DeviceArray((lib.nm_tc_conv1_bwd_workspace(32),), np.uint8)     # conv1's partials: conv2's may still be being reduced
         self.ws_dw = DeviceArray((max(lib.nm_tc_dense_wgrad_workspace(B, K), 256),), np.uint8)   # own workspace: the Dense
         #                                                     wgrad may run on a side branch next to the conv backward kernels
         self.ws_head = z((lib.nm_tc_dense_softmax_ce_workspace(B, K),), np.uint8)   # zero-filled once (ticket counter)
@@ -185,7 +186,7 @@ class TcCnnPlan:
         if fork:
             if getattr(self, "_side", None) is None:
                 from .device import new_event, new_stream
-                self._side, self._ev_fork, self._ev_join = new_stream(), new_event(), new_event()
+                self._side, self._ev_fork, self._ev_join, self._ev_fork2 = new_stream(), new_event(), new_event(), new_event()
             sd = self._side
             lib.nm_event_record(self._ev_fork, s)
             lib.nm_stream_wait_event(sd, self._ev_fork)
@@ -200,13 +201,22 @@ class TcCnnPlan:
         # shared-memory stores starve behind the tensor core's operand reads, which saturate the 128 B/cycle port.)
         _timed('tc_dense_bwd_unpool', lib.nm_tc_dense_bwd_unpool_bf16, self.dlogits.p, self.w3p.p, self.idx2.p, self.dy2_pad.p,
                                         self.c2.bias_gradients.p, self.ws.p, self.ws.nbytes, B, 7, 7, 64, self.n_out, s)
-        _timed('tc_conv2_bwd', lib.nm_tc_conv3x3_bwd_bf16, self.act1_pad.p, self.dy2_pad.p, self.w2d.p, self.c2.weight_gradients.p,
-               self.dp1.p, self.ws.p, self.ws.nbytes, B, 14, 14, 32, 64, s)
+        if fork and comm is None:
+            # conv2's wgrad partials are reduced on the side branch while conv1's backward already consumes dp1
+            _timed('tc_conv2_bwd', lib.nm_tc_conv3x3_bwd_bf16, self.act1_pad.p, self.dy2_pad.p, self.w2d.p, None,
+                   self.dp1.p, self.ws.p, self.ws.nbytes, B, 14, 14, 32, 64, s)
+            lib.nm_event_record(self._ev_fork2, s)
+            lib.nm_stream_wait_event(sd, self._ev_fork2)
+            lib.nm_tc_conv3x3_bwd_reduce_f32(self.ws.p, self.c2.weight_gradients.p, B, 14, 14, 32, 64, sd)
+            lib.nm_event_record(self._ev_join, sd)
+        else:
+            _timed('tc_conv2_bwd', lib.nm_tc_conv3x3_bwd_bf16, self.act1_pad.p, self.dy2_pad.p, self.w2d.p, self.c2.weight_gradients.p,
+                   self.dp1.p, self.ws.p, self.ws.nbytes, B, 14, 14, 32, 64, s)
         if comm is not None:
             lo = self._first_conv_floats()
             comm.allreduce_async(self.model.arena.grads, lo, self.model.arena.total - lo)
         _timed('tc_conv1_bwd', lib.nm_tc_conv1_bwd_bf16, self.x.p, self.dp1.p, self.idx1.p, self.c1.weight_gradients.p, self.c1.bias_gradients.p,
-                                 self.ws.p, self.ws.nbytes, B, 28, 28, 32, s)
+                                 self.ws_c1.p, self.ws_c1.nbytes, B, 28, 28, 32, s)
         if comm is not None:
             comm.allreduce_async(self.model.arena.grads, 0, self._first_conv_floats())
         if fork:
