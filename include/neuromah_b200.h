@@ -166,12 +166,17 @@ typedef struct nm_adam_state {
     float bc1, bc2, base_lr, decay;
     long long iterations;
     double beta1_pow, beta2_pow;      /* beta^(iterations+1) */
+    unsigned ticket, reserved;        /* last-block ticket of the fused step + advance launch (always left at 0) */
 } nm_adam_state;
 int nm_adam_state_init(nm_adam_state* dev_state, float lr, float decay, float beta1,
                        float beta2, float eps, long long iterations, void* stream);
 int nm_adam_step_dev_f32(float* param, const float* grad, float* m, float* v, size_t n,
                          const nm_adam_state* dev_state, int n_apply, void* stream);
 int nm_adam_advance_f32(nm_adam_state* dev_state, void* stream);   /* post_update_params */
+/* nm_adam_step_dev_f32 + nm_adam_advance_f32 in ONE launch: the last block to finish advances the state (every block has
+ * read the hyper-parameters by then), which takes a 1-thread kernel off the end of every training step. */
+int nm_adam_step_advance_dev_f32(float* param, const float* grad, float* m, float* v, size_t n,
+                                 nm_adam_state* dev_state, int n_apply, void* stream);
 /* Optimizer_SGD.update_params (SGD.py:85-97); mom may be NULL when momentum == 0.
  * nonfinite (may be NULL): device int set to 1 if any gradient is NaN/Inf (SGD.py:80-83). */
 int nm_sgd_step_f32(float* param, const float* grad, float* mom, size_t n,
@@ -312,7 +317,7 @@ int nm_dp_connect(void* dp, const void* handles);
 int nm_dp_set_timeout_ms(void* dp, unsigned ms);
 int nm_dp_allreduce_sum_f32(void* dp, float* buf, size_t n, void* stream);      /* in place, every rank gets the sum */
 int nm_dp_allreduce_adam_dev_f32(void* dp, float* param, float* grad, float* m, float* v, size_t n,
-                                 const nm_adam_state* dev_state, int n_apply, void* stream);
+                                 nm_adam_state* dev_state, int n_apply, int advance, void* stream);   /* advance != 0: + nm_adam_advance_f32 */
 int nm_dp_status(void* dp, int* timed_out, unsigned* steps_done);
 int nm_dp_destroy(void* dp);
 

@@ -70,6 +70,7 @@ _SIGS = {
     "nm_adam_state_init": (_i, [_vp, _f, _f, _f, _f, _f, C.c_longlong, _vp]),
     "nm_adam_step_dev_f32": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
     "nm_adam_advance_f32": (_i, [_vp, _vp]),
+    "nm_adam_step_advance_dev_f32": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
     "nm_sgd_step_f32": (_i, [_vp, _vp, _vp, _sz, _f, _f, _i, _vp, _vp]),
     "nm_rmsprop_step_f32": (_i, [_vp, _vp, _vp, _sz, _f, _f, _f, _i, _vp, _vp]),
     "nm_adagrad_step_f32": (_i, [_vp, _vp, _vp, _sz, _f, _f, _i, _vp, _vp]),
@@ -111,7 +112,7 @@ _SIGS = {
     "nm_dp_connect": (_i, [_vp, _vp]),
     "nm_dp_set_timeout_ms": (_i, [_vp, C.c_uint]),
     "nm_dp_allreduce_sum_f32": (_i, [_vp, _vp, _sz, _vp]),
-    "nm_dp_allreduce_adam_dev_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
+    "nm_dp_allreduce_adam_dev_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _i, _vp]),
     "nm_dp_status": (_i, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_uint)]),
     "nm_dp_destroy": (_i, [_vp]),
 }

@@ -30,3 +30,13 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
         p -= h.lr * __fdividef(mh, nm_sqrt_approx(vh) + h.eps);
     }
 }
+
+// post_update_params (Adam.py:103-107) + the next step's pre_update_params (:41-47), on the device.  Same formula as the
+// host (pow of the iteration count, Adam.py:94-95), not a running product: no drift between the paths.
+__device__ __forceinline__ void adam_state_advance(nm_adam_state* s) {
+    s->iterations += 1;
+    s->beta1_pow = pow((double)s->beta1, (double)(s->iterations + 1));
+    s->beta2_pow = pow((double)s->beta2, (double)(s->iterations + 1));
+    s->bc1 = (float)(1.0 - s->beta1_pow); s->bc2 = (float)(1.0 - s->beta2_pow);
+    if (s->decay != 0.f) s->lr = (float)((double)s->base_lr * (1.0 / (1.0 + (double)s->decay * (double)s->iterations)));
+}

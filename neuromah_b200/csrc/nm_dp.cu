@@ -66,7 +66,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 dp_allreduce_kernel(DpDev c, float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                    size_t n, const nm_adam_state* __restrict__ ds, int n_apply) {
+                    size_t n, nm_adam_state* ds, int n_apply, int advance) {
     pdl_trigger();
     pdl_wait();
     const int tid = threadIdx.x;
@@ -145,11 +145,12 @@ dp_allreduce_kernel(DpDev c, float* __restrict__ p, float* __restrict__ g, float
         if (atomicAdd(c.ticket, 1u) == gridDim.x - 1) {
             *c.ticket = 0u;
             *reinterpret_cast<volatile uint32_t*>(c.seq) = step;
+            if (MODE == 1 && advance) adam_state_advance(ds);      // every block has read the hyper-parameters by now
         }
     }
 }
 
-int launch(Dp* d, int mode, float* p, float* g, float* m, float* v, size_t n, const nm_adam_state* st, int n_apply, void* stream) {
+int launch(Dp* d, int mode, float* p, float* g, float* m, float* v, size_t n, nm_adam_state* st, int n_apply, int advance, void* stream) {
     if (!d->connected) return nm::fail(NM_ERR_BAD_ARG, "%s%s", "nm_dp: not connected (call nm_dp_connect first)");
     if (n > d->max_floats) return nm::fail(NM_ERR_BAD_ARG, "%s%s", "nm_dp: slab larger than the mailbox slot");
     if (!n) return NM_OK;
@@ -160,9 +161,9 @@ int launch(Dp* d, int mode, float* p, float* g, float* m, float* v, size_t n, co
     const dim3 grid(nchunks < sms ? nchunks : sms);               // all blocks resident: a waiting block never starves a pusher
     if (mode == 0)
         return nm::launch_pdl("dp_allreduce", dp_allreduce_kernel<0>, grid, dim3(kThreads), 0, nm::S(stream), d->dev,
-                              (float*)nullptr, g, (float*)nullptr, (float*)nullptr, n, (const nm_adam_state*)nullptr, 0);
+                              (float*)nullptr, g, (float*)nullptr, (float*)nullptr, n, (nm_adam_state*)nullptr, 0, 0);
     return nm::launch_pdl("dp_allreduce_adam", dp_allreduce_kernel<1>, grid, dim3(kThreads), 0, nm::S(stream), d->dev,
-                          p, g, m, v, n, st, n_apply);
+                          p, g, m, v, n, st, n_apply, advance);
 }
 
 }  // namespace
@@ -233,14 +234,14 @@ int nm_dp_set_timeout_ms(void* dp, unsigned ms) {
 
 int nm_dp_allreduce_sum_f32(void* dp, float* buf, size_t n, void* stream) {
     NM_REQUIRE(dp && buf, "null pointer");
-    return launch(static_cast<Dp*>(dp), 0, nullptr, buf, nullptr, nullptr, n, nullptr, 0, stream);
+    return launch(static_cast<Dp*>(dp), 0, nullptr, buf, nullptr, nullptr, n, nullptr, 0, 0, stream);
 }
 
 int nm_dp_allreduce_adam_dev_f32(void* dp, float* param, float* grad, float* m, float* v, size_t n,
-                                 const nm_adam_state* dev_state, int n_apply, void* stream) {
+                                 nm_adam_state* dev_state, int n_apply, int advance, void* stream) {
     NM_REQUIRE(dp && param && grad && m && v && dev_state, "null pointer");
-    NM_REQUIRE(n_apply >= 1, "n_apply must be >= 1");
-    return launch(static_cast<Dp*>(dp), 1, param, grad, m, v, n, dev_state, n_apply, stream);
+    NM_REQUIRE(n_apply >= 1 && n > 0, "n_apply must be >= 1 and n > 0");
+    return launch(static_cast<Dp*>(dp), 1, param, grad, m, v, n, dev_state, n_apply, advance, stream);
 }
 
 int nm_dp_status(void* dp, int* timed_out, unsigned* steps_done) {

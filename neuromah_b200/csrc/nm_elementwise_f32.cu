@@ -180,11 +180,10 @@ __global__ void cce_bwd_kernel(const float* __restrict__ p, const int32_t* __res
 // ----------------------------------------------------------- optimizers ---
 template <bool DEV>
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, size_t n, AdamHP hp, const nm_adam_state* __restrict__ ds,
-                            int n_apply) {
+                            float* __restrict__ v, size_t n, AdamHP hp, nm_adam_state* ds, int n_apply, int advance) {
     pdl_trigger();
     pdl_wait();
-    if (DEV) { hp.lr = ds->lr; hp.b1 = ds->beta1; hp.b2 = ds->beta2; hp.eps = ds->eps; hp.bc1 = ds->bc1; hp.bc2 = ds->bc2; }
+    if (DEV) hp = adam_hp_from(ds);
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4, stride = (size_t)gridDim.x * blockDim.x * 4;
     const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
                        reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
@@ -201,10 +200,19 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
             for (size_t j = i; j < n && j < i + 4; ++j) adam_one(p[j], g[j], m[j], v[j], hp, n_apply);
         }
     }
+    if (DEV && advance) {
+        // every block read the hyper-parameters before it got here, so the last one to arrive may advance them
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(&ds->ticket, 1u) == gridDim.x - 1) {
+            ds->ticket = 0u;
+            adam_state_advance(ds);
+        }
+    }
 }
 
 __global__ void adam_state_init_kernel(nm_adam_state* s, float lr, float decay, float b1, float b2, float eps,
                                        long long it) {
+    s->ticket = 0u; s->reserved = 0u;
     s->base_lr = lr; s->decay = decay; s->beta1 = b1; s->beta2 = b2; s->eps = eps; s->iterations = it;
     s->beta1_pow = pow((double)b1, (double)(it + 1)); s->beta2_pow = pow((double)b2, (double)(it + 1));
     s->bc1 = (float)(1.0 - s->beta1_pow); s->bc2 = (float)(1.0 - s->beta2_pow);
@@ -215,11 +223,7 @@ __global__ void adam_state_init_kernel(nm_adam_state* s, float lr, float decay, 
 __global__ void adam_advance_kernel(nm_adam_state* s) {
     pdl_trigger();
     pdl_wait();
-    s->iterations += 1;
-    s->beta1_pow = pow((double)s->beta1, (double)(s->iterations + 1));      // same formula as the host (Adam.py:94-95),
-    s->beta2_pow = pow((double)s->beta2, (double)(s->iterations + 1));      // not a running product: no drift between the paths
-    s->bc1 = (float)(1.0 - s->beta1_pow); s->bc2 = (float)(1.0 - s->beta2_pow);
-    if (s->decay != 0.f) s->lr = (float)((double)s->base_lr * (1.0 / (1.0 + (double)s->decay * (double)s->iterations)));
+    adam_state_advance(s);
 }
 
 __global__ void scale_kernel(float* __restrict__ y, const float* __restrict__ x, size_t n, float a, int accumulate) {
@@ -315,7 +319,7 @@ int nm_adam_step_f32(float* param, const float* grad, float* m, float* v, size_t
     if (!n) return NM_OK;
     AdamHP hp{lr, beta1, beta2, eps, bc1, bc2};
     return nm::launch_pdl("adam_step", adam_kernel<false>, dim3(ew_blocks(n, 256, 4)), dim3(256), 0, nm::S(stream),
-                          param, grad, m, v, n, hp, (const nm_adam_state*)nullptr, n_apply);
+                          param, grad, m, v, n, hp, (nm_adam_state*)nullptr, n_apply, 0);
 }
 
 int nm_adam_state_init(nm_adam_state* dev_state, float lr, float decay, float beta1,
@@ -331,7 +335,15 @@ int nm_adam_step_dev_f32(float* param, const float* grad, float* m, float* v, si
     NM_REQUIRE(n_apply >= 1, "n_apply must be >= 1");
     if (!n) return NM_OK;
     return nm::launch_pdl("adam_step_dev", adam_kernel<true>, dim3(ew_blocks(n, 256, 4)), dim3(256), 0, nm::S(stream),
-                          param, grad, m, v, n, AdamHP{}, dev_state, n_apply);
+                          param, grad, m, v, n, AdamHP{}, const_cast<nm_adam_state*>(dev_state), n_apply, 0);
+}
+
+int nm_adam_step_advance_dev_f32(float* param, const float* grad, float* m, float* v, size_t n,
+                                 nm_adam_state* dev_state, int n_apply, void* stream) {
+    NM_REQUIRE(param && grad && m && v && dev_state, "null pointer");
+    NM_REQUIRE(n_apply >= 1 && n > 0, "n_apply must be >= 1 and n > 0");
+    return nm::launch_pdl("adam_step_advance_dev", adam_kernel<true>, dim3(ew_blocks(n, 256, 4)), dim3(256), 0, nm::S(stream),
+                          param, grad, m, v, n, AdamHP{}, dev_state, n_apply, 1);
 }
 
 int nm_adam_advance_f32(nm_adam_state* dev_state, void* stream) {

@@ -85,13 +85,12 @@ class Optimizer_Adam:
         return self._dev_state
 
     def update_arena_dev(self, arena, n_apply=1):
-        """One Adam launch + the on-device advance of (iterations, bias corrections, decayed lr): no host values are
-        baked into the launches, so the pair can be replayed from a CUDA graph."""
+        """One launch: Adam over the slab + (last block) the on-device advance of (iterations, bias corrections, decayed
+        lr).  No host values are baked into the launch, so it can be replayed from a CUDA graph."""
         from ..._lib import lib
         from ...device import stream
-        lib.nm_adam_step_dev_f32(arena.params.p, arena.grads.p, arena.state[0].p, arena.state[1].p, arena.total,
-                                 self._dev_state.p, n_apply, stream())
-        lib.nm_adam_advance_f32(self._dev_state.p, stream())
+        lib.nm_adam_step_advance_dev_f32(arena.params.p, arena.grads.p, arena.state[0].p, arena.state[1].p, arena.total,
+                                         self._dev_state.p, n_apply, stream())
 
     def update_arena_dp(self, arena, comm, n_apply=1):
         """Data-parallel step: gradient sum over ranks (peer memory over NVLink) + Adam in ONE launch, then the
@@ -99,8 +98,7 @@ class Optimizer_Adam:
         from ..._lib import lib
         from ...device import stream
         lib.nm_dp_allreduce_adam_dev_f32(comm.peer, arena.params.p, arena.grads.p, arena.state[0].p, arena.state[1].p,
-                                         arena.total, self._dev_state.p, n_apply, stream())
-        lib.nm_adam_advance_f32(self._dev_state.p, stream())
+                                         arena.total, self._dev_state.p, n_apply, 1, stream())
 
     def host_advance(self):
         """Host mirror of the on-device advance (keeps ``iterations`` / ``current_learning_rate`` readable)."""

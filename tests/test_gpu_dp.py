@@ -41,8 +41,7 @@ def test_world1_fused_step_equals_adam_kernel_bitwise(n):
             b[1] = device.DeviceArray.from_numpy(g)
             lib.nm_adam_step_dev_f32(a[0].p, a[1].p, a[2].p, a[3].p, n, st.p, 2, device.stream())
             lib.nm_adam_advance_f32(st.p, device.stream())
-            lib.nm_dp_allreduce_adam_dev_f32(dp, b[0].p, b[1].p, b[2].p, b[3].p, n, st2.p, 2, device.stream())
-            lib.nm_adam_advance_f32(st2.p, device.stream())
+            lib.nm_dp_allreduce_adam_dev_f32(dp, b[0].p, b[1].p, b[2].p, b[3].p, n, st2.p, 2, 1, device.stream())   # advance fused
             device.synchronize()
             for u, v in zip(a, b):
                 assert np.array_equal(u.numpy(), v.numpy())
