@@ -5,20 +5,22 @@
 // (Adam.py:86-100).  A library all-reduce followed by an optimizer launch costs two dependent launches plus the
 // collective's own latency for a 200 KB slab; this file does both in ONE kernel:
 //
-//   every rank owns a MAILBOX in its HBM: data[2 parities][world][slot] floats + flag[world][chunks] words, exported
-//   to the peers with cudaIpc.  Block b of the kernel
-//     1. PUSHES its 1024-float chunks of the local gradient into slot[rank] of every rank's mailbox (plain 128-bit
-//        stores that travel over NVLink), fences at system scope and publishes flag[rank][chunk] = step number on
-//        every rank,
-//     2. WAITS until the flags of all ranks for its chunks carry this step number,
-//     3. sums the `world` slots in RANK ORDER (every rank computes the identical fp32 sum, so the replicas stay
-//        bit-identical and the result does not depend on timing), writes the sum back to the gradient slab and applies
-//        Adam to its parameters.
-//   Blocks only wait for pushes and every block pushes before it waits, so no rank can block another; the grid is
-//   capped at the SM count so all blocks are resident.  Two parities make the buffers safe without a second handshake:
-//   a rank can only be one step ahead of the slowest peer (it needs that peer's push to finish its own step).
-//   The step number lives on the device and is advanced by the last block, so the launch is CUDA-graph replayable.
-//   A bounded spin (nm_dp_set_timeout_ms) raises a status word instead of hanging the GPU if a peer never arrives.
+//   every rank owns a MAILBOX in its HBM, data[2 parities][world][slot] of 8-byte words {gradient float, step tag},
+//   exported to the peers with cudaIpc.  A thread of the kernel owns four parameters:
+//     1. it PUSHES its four local gradients, each packed with the step number into one 8-byte word, into slot[rank] of
+//        every peer's mailbox (8-byte stores over NVLink are single-copy atomic, so a word either carries this step's
+//        tag AND this step's value or neither -- no fence, no separate flag: the low-latency protocol of collective
+//        libraries),
+//     2. it POLLS the same four words of every peer's slot in its own mailbox until their tags show this step,
+//     3. it sums the `world` values in RANK ORDER (own value from the gradient slab; every rank computes the identical
+//        fp32 sum, so the replicas stay bit-identical and the result does not depend on timing), writes the sum back to
+//        the gradient slab and applies Adam to its parameters.
+//   Threads only wait for pushes and push before they wait, so no rank can block another; the grid is capped at the SM
+//   count so all blocks are resident.  Two parities make the buffers safe without a second handshake: a rank can only
+//   be one step ahead of the slowest peer (it needs that peer's push to finish its own step), so a slot is never
+//   overwritten while it may still be read.  The step number lives on the device and is advanced by the last block, so
+//   the launch is CUDA-graph replayable.  A bounded spin (nm_dp_set_timeout_ms) raises a status word instead of hanging
+//   the GPU if a peer never arrives.  Measured at 2 GPUs, 50 186 floats, back-to-back launches: see DESIGN.md section 5.
 #include "nm_common.cuh"
 #include "nm_adam.cuh"
 
@@ -29,32 +31,31 @@ constexpr int kChunk = 1024;                 // floats per chunk = 256 threads x
 constexpr int kThreads = 256;
 
 struct DpDev {                               // passed to the kernel by value
-    float* mail[kMaxWorld];                  // mailbox data of rank d, mapped into this process
-    uint32_t* flag[kMaxWorld];               // mailbox flags of rank d
+    uint2* mail[kMaxWorld];                  // mailbox of rank d ({value, tag} words), mapped into this process
     uint32_t* seq;                           // local: last completed step number
     uint32_t* ticket;                        // local: blocks finished in the current launch
     int* status;                             // local: 0 ok, 1 a wait timed out
     unsigned long long timeout_ns;
-    size_t slot;                             // floats per (parity, rank) slot, multiple of kChunk
-    int max_chunks, rank, world;
+    size_t slot;                             // words per (parity, rank) slot, multiple of kChunk
+    int rank, world;
 };
 
 struct Dp {
     DpDev dev{};
-    void* base = nullptr;                    // this rank's mailbox allocation (data | flags)
+    void* base = nullptr;                    // this rank's mailbox allocation
     void* peer_base[kMaxWorld] = {};         // cudaIpcOpenMemHandle results (own entry = base)
     void* local = nullptr;                   // seq | ticket | status
-    size_t data_bytes = 0, flag_bytes = 0, max_floats = 0;
+    size_t data_bytes = 0, max_floats = 0;
     bool connected = false;
 };
 
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void st_word(uint2* p, float v, uint32_t tag) {          // one single-copy-atomic 8-byte store
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
 }
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ uint4 ld_words(const uint2* p) {                          // two words; each half is self-validating
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
@@ -75,48 +76,44 @@ dp_allreduce_kernel(DpDev c, float* __restrict__ p, float* __restrict__ g, float
     const int nchunks = (int)((n + kChunk - 1) / kChunk);
     const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                        reinterpret_cast<uintptr_t>(v)) & 15) == 0;
-
-    // 1. push this rank's chunks into slot[rank] of every mailbox (own included), destinations staggered by rank
-    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-        const size_t i = (size_t)ch * kChunk + (size_t)tid * 4;
-        float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (vec && i + 4 <= n) G = *reinterpret_cast<const float4*>(g + i);
-        else {
-            if (i < n) G.x = g[i];
-            if (i + 1 < n) G.y = g[i + 1];
-            if (i + 2 < n) G.z = g[i + 2];
-            if (i + 3 < n) G.w = g[i + 3];
-        }
-        for (int d = 0; d < c.world; ++d) {
-            const int dst = (c.rank + d) % c.world;
-            *reinterpret_cast<float4*>(c.mail[dst] + (par + c.rank) * c.slot + i) = G;
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x)
-        if (tid < c.world) st_release_sys(c.flag[(c.rank + tid) % c.world] + (size_t)c.rank * c.max_chunks + ch, step);
-
-    // 2 + 3. wait for every rank's chunk, reduce in rank order, optimizer
     AdamHP hp{};
     if (MODE == 1) hp = adam_hp_from(ds);
-    const float* mine = c.mail[c.rank];
-    const uint32_t* my_flag = c.flag[c.rank];
+    const uint2* mine = c.mail[c.rank];
+
     for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-        if (tid < c.world) {
-            const uint32_t* f = my_flag + (size_t)tid * c.max_chunks + ch;
-            const unsigned long long t0 = global_ns();
-            while ((int32_t)(ld_acquire_sys(f) - step) < 0) {
-                if (global_ns() - t0 > c.timeout_ns) { atomicExch(c.status, 1); break; }
-                __nanosleep(64);
-            }
-        }
-        __syncthreads();
         const size_t i = (size_t)ch * kChunk + (size_t)tid * 4;
-        float4 G = __ldcg(reinterpret_cast<const float4*>(mine + par * c.slot + i));
-        for (int r = 1; r < c.world; ++r) {
-            const float4 t = __ldcg(reinterpret_cast<const float4*>(mine + (par + r) * c.slot + i));
-            G.x += t.x; G.y += t.y; G.z += t.z; G.w += t.w;
+        float4 L = make_float4(0.f, 0.f, 0.f, 0.f);                     // this rank's four gradients (zero past the end)
+        if (vec && i + 4 <= n) L = *reinterpret_cast<const float4*>(g + i);
+        else {
+            if (i < n) L.x = g[i];
+            if (i + 1 < n) L.y = g[i + 1];
+            if (i + 2 < n) L.z = g[i + 2];
+            if (i + 3 < n) L.w = g[i + 3];
+        }
+        // 1. push to every peer (destinations staggered by rank)
+        for (int d = 1; d < c.world; ++d) {
+            uint2* q = c.mail[(c.rank + d) % c.world] + (par + c.rank) * c.slot + i;
+            st_word(q, L.x, step); st_word(q + 1, L.y, step); st_word(q + 2, L.z, step); st_word(q + 3, L.w, step);
+        }
+        // 2 + 3. collect the peers' values in rank order
+        float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < c.world; ++r) {
+            float4 t = L;
+            if (r != c.rank) {
+                const uint2* q = mine + (par + r) * c.slot + i;
+                uint4 a = ld_words(q), b = ld_words(q + 2);
+                if (a.y != step || a.w != step || b.y != step || b.w != step) {
+                    const unsigned long long t0 = global_ns();
+                    unsigned polls = 0;
+                    do {
+                        if ((++polls & 255u) == 0 && global_ns() - t0 > c.timeout_ns) { atomicExch(c.status, 1); break; }
+                        a = ld_words(q); b = ld_words(q + 2);
+                    } while (a.y != step || a.w != step || b.y != step || b.w != step);
+                }
+                t = make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+            }
+            if (r == 0) G = t;
+            else { G.x += t.x; G.y += t.y; G.z += t.z; G.w += t.w; }
         }
         if (vec && i + 4 <= n) {
             *reinterpret_cast<float4*>(g + i) = G;
@@ -140,13 +137,10 @@ dp_allreduce_kernel(DpDev c, float* __restrict__ p, float* __restrict__ g, float
 
     // the last block to finish publishes the step number for the next launch (every block has read it by then)
     __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        if (atomicAdd(c.ticket, 1u) == gridDim.x - 1) {
-            *c.ticket = 0u;
-            *reinterpret_cast<volatile uint32_t*>(c.seq) = step;
-            if (MODE == 1 && advance) adam_state_advance(ds);      // every block has read the hyper-parameters by now
-        }
+    if (tid == 0 && atomicAdd(c.ticket, 1u) == gridDim.x - 1) {
+        *c.ticket = 0u;
+        *reinterpret_cast<volatile uint32_t*>(c.seq) = step;
+        if (MODE == 1 && advance) adam_state_advance(ds);      // every block has read the hyper-parameters by now
     }
 }
 
@@ -176,13 +170,11 @@ int nm_dp_create(void** dp, int rank, int world, size_t max_floats) {
     Dp* d = new Dp();
     d->max_floats = max_floats;
     d->dev.rank = rank; d->dev.world = world;
-    d->dev.max_chunks = (int)((max_floats + kChunk - 1) / kChunk);
-    d->dev.slot = (size_t)d->dev.max_chunks * kChunk;
+    d->dev.slot = (max_floats + kChunk - 1) / kChunk * kChunk;
     d->dev.timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
-    d->data_bytes = 2 * (size_t)world * d->dev.slot * sizeof(float);
-    d->flag_bytes = (((size_t)world * d->dev.max_chunks * sizeof(uint32_t)) + 255) / 256 * 256;
-    cudaError_t e = cudaMalloc(&d->base, d->data_bytes + d->flag_bytes);     // cudaMalloc: cudaIpc cannot export pool memory
-    if (e == cudaSuccess) e = cudaMemset(d->base, 0, d->data_bytes + d->flag_bytes);
+    d->data_bytes = 2 * (size_t)world * d->dev.slot * sizeof(uint2);
+    cudaError_t e = cudaMalloc(&d->base, d->data_bytes);                     // cudaMalloc: cudaIpc cannot export pool memory
+    if (e == cudaSuccess) e = cudaMemset(d->base, 0, d->data_bytes);         // tag 0 = "no step yet" (steps count from 1)
     if (e == cudaSuccess) e = cudaMalloc(&d->local, 256);
     if (e == cudaSuccess) e = cudaMemset(d->local, 0, 256);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -192,8 +184,7 @@ int nm_dp_create(void** dp, int rank, int world, size_t max_floats) {
     d->dev.status = reinterpret_cast<int*>(d->dev.seq + 2);
     d->peer_base[rank] = d->base;
     if (world == 1) {
-        d->dev.mail[0] = static_cast<float*>(d->base);
-        d->dev.flag[0] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d->base) + d->data_bytes);
+        d->dev.mail[0] = static_cast<uint2*>(d->base);
         d->connected = true;
     }
     *dp = d;
@@ -219,8 +210,7 @@ int nm_dp_connect(void* dp, const void* handles) {
             memcpy(&h, static_cast<const uint8_t*>(handles) + (size_t)r * sizeof(h), sizeof(h));
             NM_CUDA(cudaIpcOpenMemHandle(&d->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
         }
-        d->dev.mail[r] = static_cast<float*>(d->peer_base[r]);
-        d->dev.flag[r] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(d->peer_base[r]) + d->data_bytes);
+        d->dev.mail[r] = static_cast<uint2*>(d->peer_base[r]);
     }
     d->connected = true;
     return NM_OK;
