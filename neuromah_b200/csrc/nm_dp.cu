@@ -7,8 +7,8 @@
 //
 //   every rank owns a MAILBOX in its HBM, data[2 parities][world][slot] of 8-byte words {gradient float, step tag},
 //   exported to the peers with cudaIpc.  A thread of the kernel owns four parameters:
-//     1. it PUSHES its four local gradients, each packed with the step number into one 8-byte word, into slot[rank] of
-//        every peer's mailbox (8-byte stores over NVLink are single-copy atomic, so a word either carries this step's
+//     1. it PUSHES its four local gradients, each packed with the step number into one 8-byte word (two words per
+//        coalesced 16-byte store), into slot[rank] of every peer's mailbox (aligned 8-byte halves are single-copy atomic, so a word either carries this step's
 //        tag AND this step's value or neither -- no fence, no separate flag: the low-latency protocol of collective
 //        libraries),
 //     2. it POLLS the same four words of every peer's slot in its own mailbox until their tags show this step,
@@ -49,8 +49,11 @@ struct Dp {
     bool connected = false;
 };
 
-__device__ __forceinline__ void st_word(uint2* p, float v, uint32_t tag) {          // one single-copy-atomic 8-byte store
-    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+// two {value, tag} words in one 16-byte store: each aligned 8-byte half is single-copy atomic, and a warp's 32 stores
+// cover 512 contiguous bytes (full sectors on the NVLink side: 8-byte stores at a 32-byte stride were packet-bound at 8 GPUs)
+__device__ __forceinline__ void st_words(uint2* p, float v0, float v1, uint32_t tag) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(__float_as_uint(v0)), "r"(tag),
+                 "r"(__float_as_uint(v1)), "r"(tag) : "memory");
 }
 __device__ __forceinline__ uint4 ld_words(const uint2* p) {                          // two words; each half is self-validating
     uint4 v;
@@ -64,6 +67,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 
 // MODE 0: all-reduce only (gradient slab <- sum over ranks); MODE 1: + Adam on (p, m, v)
+// A thread owns two pairs of parameters of its 1024-float chunk: floats {2t, 2t+1} and {512 + 2t, 512 + 2t + 1}.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 dp_allreduce_kernel(DpDev c, float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -75,63 +79,72 @@ dp_allreduce_kernel(DpDev c, float* __restrict__ p, float* __restrict__ g, float
     const size_t par = (size_t)(step & 1u) * c.world;
     const int nchunks = (int)((n + kChunk - 1) / kChunk);
     const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
-                       reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+                       reinterpret_cast<uintptr_t>(v)) & 7) == 0;
     AdamHP hp{};
     if (MODE == 1) hp = adam_hp_from(ds);
     const uint2* mine = c.mail[c.rank];
 
     for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-        const size_t i = (size_t)ch * kChunk + (size_t)tid * 4;
-        float4 L = make_float4(0.f, 0.f, 0.f, 0.f);                     // this rank's four gradients (zero past the end)
-        if (vec && i + 4 <= n) L = *reinterpret_cast<const float4*>(g + i);
-        else {
-            if (i < n) L.x = g[i];
-            if (i + 1 < n) L.y = g[i + 1];
-            if (i + 2 < n) L.z = g[i + 2];
-            if (i + 3 < n) L.w = g[i + 3];
+        size_t idx[2];
+        float2 L[2];                                                    // this rank's gradients (zero past the end)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const size_t i = (size_t)ch * kChunk + h * (kChunk / 2) + (size_t)tid * 2;
+            idx[h] = i;
+            L[h] = make_float2(0.f, 0.f);
+            if (vec && i + 2 <= n) L[h] = *reinterpret_cast<const float2*>(g + i);
+            else {
+                if (i < n) L[h].x = g[i];
+                if (i + 1 < n) L[h].y = g[i + 1];
+            }
         }
         // 1. push to every peer (destinations staggered by rank)
         for (int d = 1; d < c.world; ++d) {
-            uint2* q = c.mail[(c.rank + d) % c.world] + (par + c.rank) * c.slot + i;
-            st_word(q, L.x, step); st_word(q + 1, L.y, step); st_word(q + 2, L.z, step); st_word(q + 3, L.w, step);
+            uint2* q = c.mail[(c.rank + d) % c.world] + (par + c.rank) * c.slot;
+            st_words(q + idx[0], L[0].x, L[0].y, step);
+            st_words(q + idx[1], L[1].x, L[1].y, step);
         }
         // 2 + 3. collect the peers' values in rank order
-        float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 G[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         for (int r = 0; r < c.world; ++r) {
-            float4 t = L;
+            float2 t0 = L[0], t1 = L[1];
             if (r != c.rank) {
-                const uint2* q = mine + (par + r) * c.slot + i;
-                uint4 a = ld_words(q), b = ld_words(q + 2);
+                const uint2* q = mine + (par + r) * c.slot;
+                uint4 a = ld_words(q + idx[0]), b = ld_words(q + idx[1]);
                 if (a.y != step || a.w != step || b.y != step || b.w != step) {
-                    const unsigned long long t0 = global_ns();
+                    const unsigned long long t_start = global_ns();
                     unsigned polls = 0;
                     do {
-                        if ((++polls & 255u) == 0 && global_ns() - t0 > c.timeout_ns) { atomicExch(c.status, 1); break; }
-                        a = ld_words(q); b = ld_words(q + 2);
+                        if ((++polls & 255u) == 0 && global_ns() - t_start > c.timeout_ns) { atomicExch(c.status, 1); break; }
+                        a = ld_words(q + idx[0]); b = ld_words(q + idx[1]);
                     } while (a.y != step || a.w != step || b.y != step || b.w != step);
                 }
-                t = make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+                t0 = make_float2(__uint_as_float(a.x), __uint_as_float(a.z));
+                t1 = make_float2(__uint_as_float(b.x), __uint_as_float(b.z));
             }
-            if (r == 0) G = t;
-            else { G.x += t.x; G.y += t.y; G.z += t.z; G.w += t.w; }
+            if (r == 0) { G[0] = t0; G[1] = t1; }
+            else { G[0].x += t0.x; G[0].y += t0.y; G[1].x += t1.x; G[1].y += t1.y; }
         }
-        if (vec && i + 4 <= n) {
-            *reinterpret_cast<float4*>(g + i) = G;
-            if (MODE == 1) {
-                float4 P = *reinterpret_cast<float4*>(p + i), M = *reinterpret_cast<float4*>(m + i),
-                       V = *reinterpret_cast<float4*>(v + i);
-                adam_one(P.x, G.x, M.x, V.x, hp, n_apply); adam_one(P.y, G.y, M.y, V.y, hp, n_apply);
-                adam_one(P.z, G.z, M.z, V.z, hp, n_apply); adam_one(P.w, G.w, M.w, V.w, hp, n_apply);
-                *reinterpret_cast<float4*>(p + i) = P; *reinterpret_cast<float4*>(m + i) = M;
-                *reinterpret_cast<float4*>(v + i) = V;
-            }
-        } else {
-            const float gs[4] = {G.x, G.y, G.z, G.w};
-            for (int u = 0; u < 4; ++u)
-                if (i + u < n) {
-                    g[i + u] = gs[u];
-                    if (MODE == 1) adam_one(p[i + u], gs[u], m[i + u], v[i + u], hp, n_apply);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const size_t i = idx[h];
+            if (vec && i + 2 <= n) {
+                *reinterpret_cast<float2*>(g + i) = G[h];
+                if (MODE == 1) {
+                    float2 P = *reinterpret_cast<float2*>(p + i), M = *reinterpret_cast<float2*>(m + i),
+                           V = *reinterpret_cast<float2*>(v + i);
+                    adam_one(P.x, G[h].x, M.x, V.x, hp, n_apply); adam_one(P.y, G[h].y, M.y, V.y, hp, n_apply);
+                    *reinterpret_cast<float2*>(p + i) = P; *reinterpret_cast<float2*>(m + i) = M;
+                    *reinterpret_cast<float2*>(v + i) = V;
                 }
+            } else {
+                const float gs[2] = {G[h].x, G[h].y};
+                for (int u = 0; u < 2; ++u)
+                    if (i + u < n) {
+                        g[i + u] = gs[u];
+                        if (MODE == 1) adam_one(p[i + u], gs[u], m[i + u], v[i + u], hp, n_apply);
+                    }
+            }
         }
     }
 
