@@ -51,9 +51,28 @@ def peaks():
 
 
 def cnn_spec_and_params(seed=0):
-    from oracle import ref_net          # spec/initial weights only (host-side fixture, not compute)
-    spec = ref_net.mnist_cnn_spec()
-    return spec, ref_net.init_params(spec, np.random.RandomState(seed))
+    """The MNIST CNN of examples/test_Conv2D_MNIST.py:47-53 as a layer list + RandomNormal(0.01) initial weights
+    (Initializer.py:90-98) in the reference's shapes.  Self-contained on purpose: the product arm of the bench does not
+    touch oracle/ (only the CPU arm below does)."""
+    spec = [
+        {"kind": "conv", "ic": 1, "oc": 32, "k": 3, "padding": "same", "relu": True},
+        {"kind": "pool", "size": 2, "stride": 2, "padding": "valid"},
+        {"kind": "conv", "ic": 32, "oc": 64, "k": 3, "padding": "same", "relu": True},
+        {"kind": "pool", "size": 2, "stride": 2, "padding": "valid"},
+        {"kind": "flatten"},
+        {"kind": "dense", "n_in": 64 * 7 * 7, "n_out": 10, "relu": False},
+        {"kind": "softmax"},
+    ]
+    rng = np.random.RandomState(seed)
+    params = []
+    for L in spec:
+        if L["kind"] == "conv":
+            params.append({"weights": rng.randn(L["oc"], L["ic"], L["k"], L["k"]) * 0.01, "biases": np.zeros((L["oc"], 1))})
+        elif L["kind"] == "dense":
+            params.append({"weights": rng.randn(L["n_in"], L["n_out"]) * 0.01, "biases": np.zeros((1, L["n_out"]))})
+        else:
+            params.append(None)
+    return spec, params
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at batch 4096, from the committed `ncu --set full` capture
