@@ -35,6 +35,8 @@ sys.path.insert(0, ROOT)
 METRIC = "train samples/sec (Conv2D MNIST CNN)"
 UNIT = "samples/s"
 BATCH = 4096            # per GPU (BASELINE.json configs[1])
+WORKLOAD = ("MNIST CNN (Conv3x3x32-ReLU-Pool2-Conv3x3x64-ReLU-Pool2-Dense10-Softmax), softmax-CE, "
+            "Adam x2 per layer (reference quirk Q1)")
 REF_SAMPLE = 512        # CPU arm: bounded sample of the batch per step
 CONV2_FLOPS = lambda b: 2.0 * b * 64 * 32 * 9 * 14 * 14      # fprop = dgrad = wgrad  # noqa: E731
 CONV1_FLOPS = lambda b: 2.0 * b * 32 * 1 * 9 * 28 * 28       # noqa: E731
@@ -260,7 +262,8 @@ def run_reference(args, rank, world, out_fd):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32", "data": "synthetic",
-            "config": {"workload": "MNIST CNN (Conv3x3x32-Pool-Conv3x3x64-Pool-Dense10), Adam, batch 4096/GPU",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
+                       "parallelism": f"dp{args.gpus}", "mode": "reference CPU path (rank 0's host cores only)",
                        "per_step_sample": REF_SAMPLE},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -446,8 +449,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": "MNIST CNN (Conv3x3x32-ReLU-Pool2-Conv3x3x64-ReLU-Pool2-Dense10-Softmax), "
-                                   "softmax-CE, Adam x2 per layer (reference quirk Q1)",
+            "config": {"workload": WORKLOAD,
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "gradient_exchange": ("none (1 GPU)" if world == 1 else
                                              "fused all-reduce + Adam kernel over NVLink peer memory (nm_dp_*)"
