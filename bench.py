@@ -38,6 +38,7 @@ BATCH = 4096            # per GPU (BASELINE.json configs[1])
 WORKLOAD = ("MNIST CNN (Conv3x3x32-ReLU-Pool2-Conv3x3x64-ReLU-Pool2-Dense10-Softmax), softmax-CE, "
             "Adam x2 per layer (reference quirk Q1)")
 REF_SAMPLE = 512        # CPU arm: bounded sample of the batch per step
+REF_BUDGET = 100_000    # ... and of the whole --impl reference run: (steps + warmup) * sample <= this many images (~1.5 min on the GPU box's host)
 CONV2_FLOPS = lambda b: 2.0 * b * 64 * 32 * 9 * 14 * 14      # fprop = dgrad = wgrad  # noqa: E731
 CONV1_FLOPS = lambda b: 2.0 * b * 32 * 1 * 9 * 28 * 28       # noqa: E731
 STEP_FLOPS = lambda b: b * 22.767e6                           # BASELINE.md section 3  # noqa: E731
@@ -258,13 +259,15 @@ def cpu_arm(steps, warmup, sample):
 def run_reference(args, rank, world, out_fd):
     if rank != 0:
         return
-    value, ms, cores, desc = cpu_arm(args.steps, max(args.warmup, 1), REF_SAMPLE)
+    warm = max(args.warmup, 1)
+    sample = max(16, min(REF_SAMPLE, REF_BUDGET // (args.steps + warm)))      # K steps must end within a few minutes
+    value, ms, cores, desc = cpu_arm(args.steps, warm, sample)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
                        "parallelism": f"dp{args.gpus}", "mode": "reference CPU path (rank 0's host cores only)",
-                       "per_step_sample": REF_SAMPLE},
+                       "per_step_sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
