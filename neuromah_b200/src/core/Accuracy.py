@@ -1,26 +1,31 @@
-"""Accuracy base class (reference: src/core/Accuracy.py:3-52)."""
+"""Running accuracy over a training / validation pass -- the base class the metrics derive from.
+
+Mirrors the public surface of the reference's src/core/Accuracy.py (``calculate``, ``calculate_accumulated``,
+``new_pass``, ``compare`` and the two ``accumulated_*`` attributes that Model.train reads); predictions and targets
+may be device arrays, the comparison itself is a host-side reduction over B flags.
+"""
 import numpy as np
 
 
 class Accuracy:
     def __init__(self, model):
         self.model = model
-        self.accumulated_sum = 0
-        self.accumulated_count = 0
-
-    def calculate(self, predictions, y):
-        comparisons = self.compare(np.asarray(predictions), np.asarray(y))
-        accuracy = np.mean(comparisons)
-        self.accumulated_sum += np.sum(comparisons)
-        self.accumulated_count += len(comparisons)
-        return accuracy
-
-    def calculate_accumulated(self):
-        return self.accumulated_sum / self.accumulated_count
+        self.new_pass()
 
     def new_pass(self):
-        self.accumulated_sum = 0
-        self.accumulated_count = 0
+        """Start a new pass: forget the hits and the sample count gathered so far."""
+        self.accumulated_sum, self.accumulated_count = 0, 0
 
     def compare(self, predictions, y):
         raise NotImplementedError("Derived classes must implement the 'compare' method.")
+
+    def calculate(self, predictions, y):
+        """Fraction of hits in this batch; also folded into the running totals of the pass."""
+        hits = np.asarray(self.compare(np.asarray(predictions), np.asarray(y)))
+        n_hits, n = hits.sum(), len(hits)
+        self.accumulated_sum += n_hits
+        self.accumulated_count += n
+        return n_hits / n
+
+    def calculate_accumulated(self):
+        return self.accumulated_sum / self.accumulated_count

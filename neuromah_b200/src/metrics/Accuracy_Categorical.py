@@ -1,4 +1,5 @@
-"""Accuracy_Categorical (reference: src/metrics/Accuracy_Categorical.py:4-16)."""
+"""Categorical accuracy (reference: src/metrics/Accuracy_Categorical.py:4-16): a hit is a predicted class id equal to
+the target class id; one-hot targets are reduced with argmax unless ``binary`` is set."""
 import numpy as np
 
 from ..core.Accuracy import Accuracy
@@ -7,12 +8,14 @@ from ..core.Accuracy import Accuracy
 class Accuracy_Categorical(Accuracy):
     def __init__(self, *, binary=False, model):
         super().__init__(model)
-        self.binary = binary
+        self.binary = bool(binary)
 
     def init(self, y):
-        pass
+        """Hook for metrics that must see the targets before training (nothing to prepare for class ids)."""
+        return None
 
     def compare(self, predictions, y):
-        if not self.binary and len(y.shape) == 2:
-            y = np.argmax(y, axis=1)
-        return np.equal(predictions, y)
+        targets = np.asarray(y)
+        if targets.ndim == 2 and not self.binary:
+            targets = targets.argmax(axis=1)
+        return np.asarray(predictions) == targets
