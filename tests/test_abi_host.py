@@ -147,3 +147,58 @@ def test_tensor_monitor_json_shape(tmp_path):
     hist = ep["parameters"]["histograms"]
     assert set(hist) == {"Layer_Conv2D/weights", "Layer_Conv2D/dweights", "Layer_Conv2D/biases", "Layer_Conv2D/dbiases"}
     assert sum(hist["Layer_Conv2D/weights"]["histogram"]) == 12 and len(hist["Layer_Conv2D/weights"]["bin_edges"]) == 11
+
+
+def test_next_row_optimizers_and_dropout_host_side():
+    """SURVEY 8f row 3 on the host: constructor validation, attribute names and defaults as in the reference
+    (src/optimizers/RMSprop.py:21-40, Adagrad.py, Nadam.py; src/layers/Dropout.py:12) -- no device needed."""
+    from neuromah_b200.src.optimizers import Optimizer_Adagrad, Optimizer_Nadam, Optimizer_RMSprop
+    from neuromah_b200.src.layers import Layer_Dropout
+    r = Optimizer_RMSprop()
+    assert (r.learning_rate, r.current_learning_rate, r.decay, r.iterations, r.epsilon, r.rho) == (0.001, 0.001, 0., 0, 1e-7, 0.9)
+    a = Optimizer_Adagrad()
+    assert (a.learning_rate, a.decay, a.epsilon, a.iterations) == (1., 0., 1e-7, 0)
+    n = Optimizer_Nadam()
+    assert (n.learning_rate, n.beta1, n.beta2, n.epsilon) == (1e-3, 0.9, 0.999, 1e-8)
+    for opt in (r, a, n):
+        assert opt.caches == {}
+    for bad in (dict(learning_rate=0), dict(learning_rate="x"), dict(decay=-1), dict(epsilon=0), dict(rho=1.0), dict(rho=-0.1)):
+        with pytest.raises(ValueError):
+            Optimizer_RMSprop(**bad)
+    for bad in (dict(learning_rate=-1.0), dict(decay=-0.5), dict(epsilon=-1e-7)):
+        with pytest.raises(ValueError):
+            Optimizer_Adagrad(**bad)
+    with pytest.raises(TypeError):
+        Optimizer_Nadam(learning_rate="fast")
+    with pytest.raises(TypeError):
+        Optimizer_Nadam(beta1=1)                       # the reference insists on float betas
+    with pytest.raises(ValueError):
+        Optimizer_Nadam(beta2=1.0)
+    with pytest.raises(ValueError):
+        Optimizer_Nadam(epsilon=0.0)
+    # decayed learning rate: lr / (1 + decay * iterations), evaluated in pre_update_params
+    r = Optimizer_RMSprop(learning_rate=0.1, decay=0.5)
+    r.iterations = 4
+    r.pre_update_params()
+    assert r.current_learning_rate == pytest.approx(0.1 / 3.0)
+    r.post_update_params()
+    assert r.iterations == 5
+    # Layer_Dropout keeps the KEEP probability in .rate, like the reference
+    d = Layer_Dropout(0.3)
+    assert d.rate == pytest.approx(0.7) and d.binary_mask is None
+    with pytest.raises(ValueError):
+        Layer_Dropout(1.0)
+    assert Layer_Dropout(0.1).seed != Layer_Dropout(0.1).seed           # distinct default streams per layer
+    for layer_with_no_params in (d,):
+        assert layer_with_no_params.get_parameters() == {}
+
+
+def test_checkpoint_format_is_guarded(tmp_path):
+    """Model.load refuses files that are not neuromah_b200 model checkpoints (host side only)."""
+    import pickle
+    from neuromah_b200 import checkpoint
+    p = tmp_path / "not_a_model.pkl"
+    with open(p, "wb") as f:
+        pickle.dump({"format": "something else"}, f)
+    with pytest.raises(ValueError):
+        checkpoint.load(str(p))
