@@ -17,6 +17,7 @@ finalize() registers every trainable layer twice exactly as the reference does
 is cleared.
 """
 import copy
+import os
 import pickle
 import time
 
@@ -255,6 +256,8 @@ class Model:
                 if ring is not None:      # streamed mode: the step's running loss/accuracy sums go back to the host
                     lib.nm_d2h(C.c_void_p(ring.ptr + 16 * (step % 64)), self._accum.p, 16, stream())
                     self.d2h_bytes += 16
+            if feeder.stream and (self.epoch_end_accuracy or epoch < epochs):
+                feeder.prefetch_next_pass()       # keep the copy engine busy across the end-of-pass synchronisation
             loss_sum, _ = self._read_accum()
             if self.comm is not None and getattr(self.comm, "peer", None) is not None:
                 self.comm.check()         # a peer that never delivered its gradients raises here instead of going unnoticed
@@ -272,6 +275,8 @@ class Model:
                     xb, lb = feeder.batch(step)
                     self._device_loss_acc(self.forward(xb, training=False), lb)
                     feeder.release(step, train_steps)
+                if feeder.stream and epoch < epochs:
+                    feeder.prefetch_next_pass()
                 _, correct = self._read_accum()
             else:
                 correct = float("nan")
@@ -469,48 +474,78 @@ class _BatchFeeder:
         # (same pointers => the CUDA graphs captured for them stay valid)
         res = None if cache is None else cache.get(shape)
         if res is None:
-            res = dict(dev=[DeviceArray(shape, np.float32) for _ in range(2)],
-                       dev_lab=[DeviceArray((bs,), np.int32) for _ in range(2)],
-                       pin_lab=[PinnedBuffer((bs,), np.int32) for _ in range(2)],
-                       copy_stream=new_stream(), uploaded=[new_event() for _ in range(2)],
-                       consumed=[new_event() for _ in range(2)], pin_x=None)
+            ns = self.SLOTS
+            res = dict(dev=[DeviceArray(shape, np.float32) for _ in range(ns)],
+                       dev_lab=[DeviceArray((bs,), np.int32) for _ in range(ns)],
+                       copy_stream=new_stream(), uploaded=[new_event() for _ in range(ns)],
+                       consumed=[new_event() for _ in range(ns)], labels_ready=new_event(), pin_x=None,
+                       pin_labels=None, dev_labels=None)
             if cache is not None:
                 cache[shape] = res
         else:
             synchronize()                                  # a previous pass may still be reading the slots
         self._res = res
-        self.dev, self.dev_lab, self.pin_lab = res["dev"], res["dev_lab"], res["pin_lab"]
+        self.dev, self.dev_lab = res["dev"], res["dev_lab"]
         self.pin_x = res["pin_x"]
         self.copy_stream, self.uploaded, self.consumed = res["copy_stream"], res["uploaded"], res["consumed"]
         self.issued = -1          # last step (of the current pass) whose upload has been enqueued
-        self.uploads = 0          # uploads ever enqueued; slot = uploads & 1
+        self.uploads = 0          # uploads ever enqueued; slot = uploads % SLOTS
         self.slot_of = {}
+        self.prefetched = False   # step 0 of the NEXT pass is already on its way (prefetch_next_pass)
+        # The labels of the whole data set go up in ONE copy (they are 4 bytes per sample); every step then fills its
+        # slot's label buffer with a 16 KB device-to-device copy on the compute stream.  A per-step 16 KB host copy
+        # behind each 12.8 MB image copy cost the copy engine ~7 us of turnaround per step (scratch/e2e_probe3.py).
+        if res["pin_labels"] is None or res["pin_labels"].array.shape[0] < self.n:
+            res["pin_labels"] = PinnedBuffer((self.n,), np.int32)
+            res["dev_labels"] = DeviceArray((self.n,), np.int32)
+        self.pin_labels, self.dev_labels, self.labels_ready = res["pin_labels"], res["dev_labels"], res["labels_ready"]
+        self.pin_labels.array[:self.n] = self.labels_host
+        lib.nm_h2d(self.dev_labels.p, C.c_void_p(self.pin_labels.ptr), 4 * self.n, self.copy_stream)
+        lib.nm_event_record(self.labels_ready, self.copy_stream)
+        self.h2d_bytes += 4 * self.n
+
+    # Device slots (double buffering).  Three slots were measured too (NM_FEED_SLOTS=3): 0.259 ms per step against 0.254
+    # with two on the B200 box, so two it is.
+    SLOTS = int(os.environ.get("NM_FEED_SLOTS", "2"))
 
     def rewind(self):
         """Start a new pass over the data (new epoch / evaluation sweep)."""
-        self.issued = -1
+        if self.prefetched:
+            self.prefetched = False       # step 0 of this pass was enqueued at the end of the previous one
+        else:
+            self.issued = -1
+
+    def prefetch_next_pass(self):
+        """Enqueue the upload of step 0 of the next pass over the same data NOW, so the copy engine keeps going while
+        the host synchronises on the end-of-pass loss read (otherwise every pass boundary drains the pipeline: one
+        copy time, ~0.24 ms, per epoch)."""
+        if self.stream and not self.prefetched:
+            self.issued = -1
+            self._upload(0)
+            self.prefetched = True
 
     def _upload(self, step):
-        slot = self.uploads & 1
+        slot = self.uploads % self.SLOTS
         lo, hi = step * self.bs, min((step + 1) * self.bs, self.n)
         rows = hi - lo
-        if self.uploads >= 2:
-            lib.nm_stream_wait_event(self.copy_stream, self.consumed[slot])   # device slot consumed by step-2
-            lib.nm_event_sync(self.uploaded[slot])                            # pinned staging slot drained
+        if self.uploads >= self.SLOTS:
+            lib.nm_stream_wait_event(self.copy_stream, self.consumed[slot])   # device slot consumed by its previous user
+            if self.pin_x is not None:
+                lib.nm_event_sync(self.uploaded[slot])                        # pinned staging slot drained
         src = self.X[lo:hi]
         addr = pinned_address(src)
         if addr is None:                              # pageable: stage through pinned memory
             if self.pin_x is None:
-                self.pin_x = self._res["pin_x"] = [PinnedBuffer((self.bs,) + self.X.shape[1:], np.float32) for _ in range(2)]
+                self.pin_x = self._res["pin_x"] = [PinnedBuffer((self.bs,) + self.X.shape[1:], np.float32)
+                                                   for _ in range(self.SLOTS)]
+                if self.uploads >= self.SLOTS:
+                    lib.nm_event_sync(self.uploaded[slot])
             self.pin_x[slot].array[:rows] = src
             addr = self.pin_x[slot].ptr
         xb = self.dev[slot][0:rows]
         lib.nm_h2d(xb.p, C.c_void_p(addr), xb.nbytes, self.copy_stream)
-        self.pin_lab[slot].array[:rows] = self.labels_host[lo:hi]
-        lb = self.dev_lab[slot][0:rows]
-        lib.nm_h2d(lb.p, C.c_void_p(self.pin_lab[slot].ptr), lb.nbytes, self.copy_stream)
         lib.nm_event_record(self.uploaded[slot], self.copy_stream)
-        self.h2d_bytes += xb.nbytes + lb.nbytes
+        self.h2d_bytes += xb.nbytes
         self.issued = step
         self.uploads += 1
         self.slot_of[step] = slot
@@ -519,16 +554,20 @@ class _BatchFeeder:
         lo, hi = step * self.bs, min((step + 1) * self.bs, self.n)
         if not self.stream:
             return self.X[lo:hi], self.labels[lo:hi]
-        if self.issued < step:
-            self._upload(step)
+        while self.issued < step:
+            self._upload(self.issued + 1)
         slot = self.slot_of[step]
-        lib.nm_stream_wait_event(stream(), self.uploaded[slot])
-        return self.dev[slot][0:hi - lo], self.dev_lab[slot][0:hi - lo]
+        st = stream()
+        lib.nm_stream_wait_event(st, self.uploaded[slot])
+        lib.nm_stream_wait_event(st, self.labels_ready)
+        lb = self.dev_lab[slot][0:hi - lo]
+        lib.nm_d2d(lb.p, C.c_void_p(self.dev_labels.ptr + 4 * lo), 4 * (hi - lo), st)     # ordered after the slot's last reader
+        return self.dev[slot][0:hi - lo], lb
 
     def release(self, step, n_steps):
-        """Call after step's kernels are enqueued: marks its slot reusable and prefetches step+1."""
+        """Call after step's kernels are enqueued: marks its slot reusable and keeps SLOTS-1 uploads in flight."""
         if not self.stream:
             return
         lib.nm_event_record(self.consumed[self.slot_of[step]], stream())
-        if step + 1 < n_steps and self.issued < step + 1:
-            self._upload(step + 1)
+        while self.issued < min(step + self.SLOTS - 1, n_steps - 1):
+            self._upload(self.issued + 1)
