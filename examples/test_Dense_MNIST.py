@@ -1,8 +1,9 @@
 """BASELINE.json config 1: the 784-128-10 MLP (ReLU, softmax cross-entropy, Adam) on synthetic 28x28 data, batch 128,
-through the reference's API (examples/test_Dense_MNIST.py builds the same kind of stack; its Dropout layers and doubled
-softmax -- SURVEY Q10 -- are left out, as BASELINE.json's config does).
+through the reference's API.  ``--as-written`` builds the stack exactly as the reference's examples/test_Dense_MNIST.py:38-49
+does -- two Dropout layers, a last Dense with an embedded Softmax followed by Activation_Softmax again, loss and
+accuracy passed as instances, batch 32 -- instead of BASELINE.json's clean 784-128-10 config.
 
-    python examples/test_Dense_MNIST.py [--n 25600] [--epochs 2]
+    python examples/test_Dense_MNIST.py [--n 25600] [--epochs 2] [--as-written]
 """
 import argparse
 import os
@@ -14,7 +15,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import neuromah_b200
 neuromah_b200.install_alias()          # `import Neuromah.src...` below resolves to the B200 package
-from Neuromah.src.layers import Layer_Dense
+from Neuromah.src.layers import Layer_Dense, Layer_Dropout
 from Neuromah.src.optimizers import Optimizer_Adam
 from Neuromah.src.losses import Loss_CategoricalCrossentropy
 from Neuromah.src.core import Model
@@ -24,6 +25,7 @@ from Neuromah.src.metrics import Accuracy_Categorical
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=25600)
 ap.add_argument("--epochs", type=int, default=2)
+ap.add_argument("--as-written", action="store_true")
 args = ap.parse_args()
 rng = np.random.default_rng(1)
 labels = rng.integers(0, 10, args.n)
@@ -33,11 +35,23 @@ for k in range(10):
 y = np.eye(10)[labels]
 
 model = Model()
-model.add(Layer_Dense(784, 128, activation=Activation_ReLU()))
-model.add(Layer_Dense(128, 10))
-model.add(Activation_Softmax())
-model.set(loss=Loss_CategoricalCrossentropy, optimizer=Optimizer_Adam(learning_rate=0.001), accuracy=Accuracy_Categorical)
+if args.as_written:
+    model.add(Layer_Dense(n_inputs=784, n_neurons=128, activation=Activation_ReLU()))
+    model.add(Layer_Dropout(rate=0.25))
+    model.add(Layer_Dense(n_inputs=128, n_neurons=64, activation=Activation_ReLU()))
+    model.add(Layer_Dropout(rate=0.25))
+    model.add(Layer_Dense(n_inputs=64, n_neurons=10, activation=Activation_Softmax()))
+    model.add(Activation_Softmax())
+    model.set(loss=Loss_CategoricalCrossentropy(model=model), optimizer=Optimizer_Adam(learning_rate=0.001),
+              accuracy=Accuracy_Categorical(model=model))
+    batch = 32
+else:
+    model.add(Layer_Dense(784, 128, activation=Activation_ReLU()))
+    model.add(Layer_Dense(128, 10))
+    model.add(Activation_Softmax())
+    model.set(loss=Loss_CategoricalCrossentropy, optimizer=Optimizer_Adam(learning_rate=0.001), accuracy=Accuracy_Categorical)
+    batch = 128
 model.finalize()
 t0 = time.perf_counter_ns()
-model.train(X, y, epochs=args.epochs, batch_size=128, validation_data=(X[:1024], y[:1024]))
+model.train(X, y, epochs=args.epochs, batch_size=batch, validation_data=(X[:1024], y[:1024]))
 print(f"Total training time: {time.perf_counter_ns() - t0} ns")

@@ -102,6 +102,44 @@ def dropout_mlp():
                         final_params=flat_params(model).astype(np.float64), infer=np.asarray(infer, dtype=np.float64))
 
 
+def dense_example_stack():
+    """The stack of examples/test_Dense_MNIST.py:38-43 as written (reduced widths): Dense+ReLU, Dropout, Dense+ReLU,
+    Dropout, Dense with an embedded Softmax, then Activation_Softmax again (the doubled softmax), loss and
+    accuracy passed as INSTANCES (:47-49).  Adam, batch 32, 6 steps; the dropout masks are stored for replay."""
+    ref_shim.load()
+    from NeuromahRef.src.core import Model
+    from NeuromahRef.src.layers import Layer_Dense, Layer_Dropout
+    from NeuromahRef.src.activations import Activation_ReLU, Activation_Softmax
+    from NeuromahRef.src.losses import Loss_CategoricalCrossentropy
+    from NeuromahRef.src.optimizers import Optimizer_Adam
+    from NeuromahRef.src.metrics import Accuracy_Categorical
+    rs = np.random.RandomState(61)
+    W = [rs.randn(64, 32) * 0.1, rs.randn(32, 16) * 0.1, rs.randn(16, 10) * 0.1]
+    model = Model()
+    d1 = Layer_Dense(n_inputs=64, n_neurons=32, activation=Activation_ReLU())
+    d2 = Layer_Dense(n_inputs=32, n_neurons=16, activation=Activation_ReLU())
+    d3 = Layer_Dense(n_inputs=16, n_neurons=10, activation=Activation_Softmax())
+    for d, w in zip((d1, d2, d3), W):
+        d.weights = w.copy(); d.biases = np.zeros((1, w.shape[1]))
+    drop1, drop2 = Layer_Dropout(rate=0.25), Layer_Dropout(rate=0.25)
+    for l in (d1, drop1, d2, drop2, d3, Activation_Softmax()):
+        model.add(l)
+    model.set(loss=Loss_CategoricalCrossentropy(model=model), optimizer=Optimizer_Adam(learning_rate=0.01),
+              accuracy=Accuracy_Categorical(model=model))
+    model.finalize()
+    model.loss.new_pass(); model.accuracy.new_pass()
+    x, y = data(62, 32 * 6, (64,))
+    np.random.seed(321)
+    losses, m1, m2 = [], [], []
+    for s in range(6):
+        losses.append(ref_shim.train_step(model, x[s * 32:(s + 1) * 32], y[s * 32:(s + 1) * 32])["loss"])
+        m1.append(np.array(drop1.binary_mask, dtype=np.float32)); m2.append(np.array(drop2.binary_mask, dtype=np.float32))
+    out = model.forward(x[:32], training=False)
+    np.savez_compressed(os.path.join(HERE, "dense_example_stack_6steps.npz"), losses=np.array(losses), masks1=np.stack(m1),
+                        masks2=np.stack(m2), w0=W[0], w1=W[1], w2=W[2], final_params=flat_params(model).astype(np.float64),
+                        infer=np.asarray(out, dtype=np.float64))
+
+
 def cnn_small():
     """MNIST CNN of examples/test_Conv2D_MNIST.py:47-53, batch 4, 3 Adam steps, wired conv backward."""
     spec = ref_net.mnist_cnn_spec()
@@ -209,7 +247,7 @@ def ops():
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (mlp_200, mlp_sgd, cnn_small, cnn_stub, cnn_200, ops, single_layer_optimizers, dropout_mlp):
+    for fn in (mlp_200, mlp_sgd, cnn_small, cnn_stub, cnn_200, ops, single_layer_optimizers, dropout_mlp, dense_example_stack):
         if not only or fn.__name__ in only:
             fn()
     for f in sorted(os.listdir(HERE)):

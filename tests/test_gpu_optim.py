@@ -222,3 +222,38 @@ def test_dropout_device_mask_properties():
         np.testing.assert_array_equal(np.asarray(again.binary_mask), first)   # same seed + call index => same mask
         inf = np.asarray(lay.forward(x, False))
         np.testing.assert_array_equal(inf, x)                                  # inference: copy (Dropout.py:23-25)
+
+
+def test_dense_example_stack_as_written_in_the_reference():
+    """examples/test_Dense_MNIST.py:38-49 call for call (reduced widths): Dropout layers, a Dense with an embedded Softmax
+    followed by Activation_Softmax (the doubled softmax, SURVEY Q10: its Jacobian backward runs on the device), loss and
+    accuracy handed to Model.set as instances.  Goldens from the unmodified reference, dropout masks replayed."""
+    from test_gpu_model import reference_style_step
+    from neuromah_b200.src.core import Model
+    from neuromah_b200.src.layers import Layer_Dense, Layer_Dropout
+    from neuromah_b200.src.activations import Activation_ReLU, Activation_Softmax
+    from neuromah_b200.src.losses import Loss_CategoricalCrossentropy
+    from neuromah_b200.src.optimizers import Optimizer_Adam
+    from neuromah_b200.src.metrics import Accuracy_Categorical
+    g = golden("dense_example_stack_6steps.npz")
+    model = Model()
+    d1 = Layer_Dense(n_inputs=64, n_neurons=32, activation=Activation_ReLU())
+    d2 = Layer_Dense(n_inputs=32, n_neurons=16, activation=Activation_ReLU())
+    d3 = Layer_Dense(n_inputs=16, n_neurons=10, activation=Activation_Softmax())
+    for d, k in zip((d1, d2, d3), ("w0", "w1", "w2")):
+        d.set_parameters(g[k], np.zeros((1, g[k].shape[1])))
+    drop1, drop2 = Layer_Dropout(rate=0.25), Layer_Dropout(rate=0.25)
+    for l in (d1, drop1, d2, drop2, d3, Activation_Softmax()):
+        model.add(l)
+    model.set(loss=Loss_CategoricalCrossentropy(model=model), optimizer=Optimizer_Adam(learning_rate=0.01),
+              accuracy=Accuracy_Categorical(model=model))
+    model.finalize()
+    model.loss.new_pass(); model.accuracy.new_pass()
+    x, y = synth(62, 32 * 6, (64,))
+    losses = []
+    for s in range(6):
+        drop1.fixed_mask, drop2.fixed_mask = g["masks1"][s], g["masks2"][s]
+        losses.append(reference_style_step(model, x[s * 32:(s + 1) * 32], y[s * 32:(s + 1) * 32])[0])
+    np.testing.assert_allclose(losses, g["losses"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(model.arena.host_params(), g["final_params"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(np.asarray(model.forward(x[:32], training=False)), g["infer"], rtol=RTOL, atol=ATOL)
