@@ -239,6 +239,39 @@ int nm_tc_conv3x3_bwd_pool_bf16(const void* x_pad, const void* dpool, const void
                                 void* dx_grid, void* workspace, size_t workspace_bytes, int N, int H, int W, int C, int OC,
                                 void* stream);
 
+/* ---- general-shape 3x3 'same' convolution (streamed filter bank), channel counts padded to multiples of 64 ----
+ * The VGG-style stack of BASELINE.json config 4.  All activation tensors are haloed bf16 NHWC [N,H+2,W+2,Cp]; the
+ * kernels write the halo of their output as zero, so outputs feed the next layer (or its backward) directly. */
+/* OIHW f32 [OC][C][3][3] -> bf16 [OCp][tap][Cp] (fprop operand) and bf16 [Cp][8-tap][OCp] (dgrad operand), padded
+ * channels zero; either destination may be NULL. */
+int nm_tc_pack_conv_weights_gen_bf16(const float* w_oihw, void* w_fprop, void* w_dgrad, int OC, int C, int OCp, int Cp, void* stream);
+/* f32 NCHW [N,C,H,W] -> haloed bf16 NHWC [N,H+2,W+2,Cp] (replaces np.pad, Conv_wrapepr.py:78-84); every element written. */
+int nm_tc_pack_input_nhwc_bf16(const float* x_nchw, void* x_pad, int N, int C, int H, int W, int Cp, void* stream);
+/* y_pad[N,H+2,W+2,Cout] = conv3x3(x_pad[N,H+2,W+2,Cin], w_packed[Cout][9][Cin]) (+ bias[Cout] if not NULL)
+ * (ReLU if relu != 0) (zeroed where relu_mask[N,H+2,W+2,Cout] <= 0, if not NULL).  tcgen05 implicit GEMM, K loop over
+ * (64-channel chunk, tap).  fprop (Conv2D.cpp:83-146 + Conv_wrapepr.py:96-98): w_packed = the fprop operand, relu = 1.
+ * dgrad (Conv2D.cpp:218-222 + col2im, then the ReLU backward of the layer below, Relu.py:12-14): x_pad = dY,
+ * w_packed = the dgrad operand, Cin = OCp, Cout = Cp, relu_mask = that layer's (post-ReLU) output. */
+int nm_tc_conv3x3_gen_bf16(const void* x_pad, const void* w_packed, const float* bias, const void* relu_mask, void* y_pad,
+                           int N, int H, int W, int Cin, int Cout, int relu, void* stream);
+/* wgrad (Conv2D.cpp:207-216: summed over the batch, no normalisation) -> dw f32 OIHW [OC][C][3][3], and, if dbias is
+ * not NULL, the bias gradient sum_{n,h,w} dY -> dbias f32 [OC] (Conv_wrapepr.py:107-109).  Deterministic. */
+size_t nm_tc_conv3x3_wgrad_gen_workspace(int N, int H, int W, int Cp, int OCp);
+int nm_tc_conv3x3_wgrad_gen_bf16(const void* x_pad, const void* dy_pad, float* dw, float* dbias, void* workspace, size_t workspace_bytes,
+                                 int N, int H, int W, int C, int OC, int Cp, int OCp, void* stream);
+
+/* Layer_MaxPooling2D(2, 2).forward (MaxPooling2D.py:37-61, maxpooling_backend.cpp:24-133) on a haloed bf16 NHWC tensor:
+ * x_pad [N,H+2,W+2,C] -> y bf16 [N,H/2,W/2,C] (out_padded = 0) or haloed [N,H/2+2,W/2+2,C] with the halo written as
+ * zero (out_padded = 1); idx nibbles [N,H/2,W/2,C/2] bytes in the format above (first-max position | (max > 0) << 2). */
+int nm_tc_maxpool2x2_fwd_bf16(const void* x_pad, void* y, void* idx, int N, int H, int W, int C, int out_padded, void* stream);
+/* Layer_MaxPooling2D.backward (maxpooling_backend.cpp:145-238) + the ReLU backward of the conv below (Relu.py:12-14):
+ * dpool bf16 [N,H/2,W/2,C] (in_padded = 0) or haloed (in_padded = 1) + idx -> dy_pad bf16 [N,H+2,W+2,C], every element
+ * written (the halo and the non-arg-max positions as zero). */
+int nm_tc_maxpool2x2_bwd_bf16(const void* dpool, const void* idx, void* dy_pad, int N, int H, int W, int C, int in_padded, void* stream);
+/* Layer_Dense dinputs (Dense.py:108) for the tensor-core mode: dx bf16 [B][K] = dlogits f32 [B][n_out] . w_packed
+ * (f32 [n_out][K] from nm_tc_pack_dense_weights, K in (h,w,c) order).  n_out <= 16, K % 8 == 0. */
+int nm_tc_dense_dgrad_bf16(const float* dlogits, const float* w_packed, void* dx, int B, int K, int n_out, void* stream);
+
 /* First conv of the net (C_in = 1, 3x3 'same', ReLU, no bias) + MaxPooling2D(2,2) on tcgen05: the 4x4 input patch of a
  * pool window is the K = 16 dimension and the weights are expanded to Wext[(window position, oc)][4x4] (zero outside the
  * 3x3 support), so one MMA yields all four conv values of a window per TMEM lane and the pool needs no cross-lane traffic.

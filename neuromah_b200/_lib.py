@@ -87,6 +87,14 @@ _SIGS = {
     "nm_tc_conv3x3_bwd_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_conv3x3_bwd_reduce_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_conv3x3_bwd_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
+    "nm_tc_pack_conv_weights_gen_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "nm_tc_pack_input_nhwc_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "nm_tc_conv3x3_gen_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "nm_tc_conv3x3_wgrad_gen_workspace": (_sz, [_i, _i, _i, _i, _i]),
+    "nm_tc_conv3x3_wgrad_gen_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "nm_tc_maxpool2x2_fwd_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "nm_tc_maxpool2x2_bwd_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "nm_tc_dense_dgrad_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "nm_tc_dense_bwd_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_pack_conv1_weights_bf16": (_i, [_vp, _vp, _i, _vp]),
     "nm_tc_conv1_fwd_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -119,7 +127,8 @@ _SIGS = {
 
 _UNCHECKED = {"nm_last_error", "nm_version", "nm_conv2d_wgrad_f32_workspace", "nm_dense_wgrad_f32_workspace",
               "nm_tc_conv3x3_wgrad_workspace", "nm_tc_conv1_bwd_workspace", "nm_tc_dense_wgrad_workspace",
-              "nm_tc_dense_softmax_ce_workspace", "nm_tc_dense_bwd_unpool_workspace", "nm_tc_conv3x3_bwd_workspace"}
+              "nm_tc_dense_softmax_ce_workspace", "nm_tc_dense_bwd_unpool_workspace", "nm_tc_conv3x3_bwd_workspace",
+              "nm_tc_conv3x3_wgrad_gen_workspace"}
 
 
 class NeuromahB200Error(RuntimeError):

@@ -1,0 +1,569 @@
+// General-shape bf16 tensor-core 3x3 'same' convolution for sm_100a (channel counts that are multiples of 64):
+// fprop (+ bias + ReLU), dgrad (+ ReLU' of the layer below) and wgrad (+ bias gradient), for the VGG-style stack of
+// BASELINE.json config 4 (C(3->64) C(64->64) P C(64->128) C(128->128) P C(128->256) C(256->256) P).  The kernels of
+// nm_tc_conv.cu / nm_tc_conv_pool.cu keep the whole filter bank resident in shared memory, which stops at 32 x 64
+// channels; here the filter bank is STREAMED: an implicit GEMM with a K loop over (64-channel chunk, filter tap).
+//
+// Same data layout and the same no-im2col addressing as nm_tc_conv.cu: activations are zero-haloed NHWC bf16
+// [N, Hp = H+2, Wp = W+2, C]; for 256 consecutive pixels of that flattened grid ONE activation tile (256 + 2*Wp + 2 pixel
+// rows of one 64-channel chunk, 128-byte rows, SWIZZLE_128B) lands in shared memory per K chunk, and the nine taps are
+// tcgen05.mma issues whose A-descriptor start address is shifted by (r*Wp + s) rows inside that tile.  The tile is
+// loaded from row (m0 - Wp - 1) -- rows before the tensor read as zero -- so accumulator row p IS grid position m0 + p and
+// the epilogue stores straight into the next layer's haloed tensor (halo positions are written as zero).
+//
+// Replaces: conv2d_cpu / conv2d_backward_cpu (src/layers/CPU_kernels/Conv2D.cpp:83-146, :150-240), the np.pad of
+// Layer_Conv2D.forward (Conv_wrapepr.py:78-84), the embedded ReLU (Conv_wrapepr.py:96-98, Relu.py:7-14) and the
+// bias gradient of Layer_Conv2D.backward (Conv_wrapepr.py:107-109), for the tensor-core mode.
+#include "nm_common.cuh"
+#include "nm_tc_common.cuh"
+#include "nm_tc_host.cuh"
+#include <cstdlib>
+
+namespace {
+
+using namespace tc;
+
+constexpr int G_M = 128;                 // rows of one MMA
+constexpr int G_MSUB = 2;                // MMAs (accumulators) per weight slice: every streamed weight byte feeds 256 pixels
+constexpr int G_TILE_ROWS = G_M * G_MSUB;
+constexpr int G_KC = 64;                 // channels per K chunk = one 128-byte SWIZZLE_128B row
+constexpr int G_ROWB = 128;
+
+struct ConvGenParams {
+    int rows_total, Hp, Wp, H, W;
+    int n_tiles, num_tiles;              // tile = (m_tile, n_tile), n fastest: CTAs that run together share the activation tile in L2
+    int k_chunks, Cin, Cout;
+    int a_boxes, a_box_rows;             // an activation stage = a_boxes TMA boxes of a_box_rows (multiple of 8) rows
+    uint32_t a_stage_bytes;
+    int a_stages, b_stages;
+    __nv_bfloat16* out;                  // [rows_total][Cout], haloed grid
+    const __nv_bfloat16* mask;           // optional [rows_total][Cout]: out = mask > 0 ? acc : 0   (ReLU' of the layer below)
+    const float* bias;                   // optional [Cout]
+    int relu;
+};
+
+// D[256 pixels, NT] = sum_{chunk, tap} A_chunk[pixel + shift(tap), 0:64] * B[tap][n0 : n0+NT, chunk]^T
+template <int NT>
+__global__ void __launch_bounds__(384, 1)
+conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvGenParams p) {
+    constexpr uint64_t TMPL = desc_template(16, 8 * G_ROWB, LAYOUT_SW128);     // K-major, SBO = 8 rows
+    constexpr uint32_t IDESC = idesc_bf16(G_M, NT, 0, 0);
+    constexpr int B_BYTES = NT * G_ROWB;                                      // one (tap, chunk) weight slice
+    constexpr int NACC = G_MSUB * NT;                                         // accumulator columns per buffer
+    constexpr uint32_t TMEM_COLS = 2 * NACC <= 256 ? 256 : 512;
+    static_assert(2 * NACC <= 512, "accumulators exceed TMEM");
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* a_smem = smem;
+    uint8_t* b_smem = smem + (size_t)p.a_stages * p.a_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)p.b_stages * B_BYTES);
+    uint64_t* afull = bars;
+    uint64_t* aempty = afull + p.a_stages;
+    uint64_t* bfull = aempty + p.a_stages;
+    uint64_t* bempty = bfull + p.b_stages;
+    uint64_t* tfull = bempty + p.b_stages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.a_stages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < p.b_stages; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            int a_stage = 0, b_stage = 0; uint32_t a_phase = 0, b_phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * NT;
+                const int row0 = m_tile * G_TILE_ROWS - (p.Wp + 1);                    // negative / past-the-end rows read as zero
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    mbar_wait(&aempty[a_stage], a_phase ^ 1);
+                    mbar_expect_tx(&afull[a_stage], (uint32_t)(p.a_boxes * p.a_box_rows) * G_ROWB);
+                    for (int j = 0; j < p.a_boxes; ++j)
+                        tma_load_2d(a_smem + (size_t)a_stage * p.a_stage_bytes + (size_t)j * p.a_box_rows * G_ROWB, &map_a,
+                                    kc * G_KC, row0 + j * p.a_box_rows, &afull[a_stage]);
+                    if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&bempty[b_stage], b_phase ^ 1);
+                        mbar_expect_tx(&bfull[b_stage], B_BYTES);
+                        tma_load_2d(b_smem + (size_t)b_stage * B_BYTES, &map_b, tap * p.Cin + kc * G_KC, n0, &bfull[b_stage]);
+                        if (++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer (converged warp, one elected lane) ==============================
+        int a_stage = 0, b_stage = 0; uint32_t a_phase = 0, b_phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+            fence_after_sync();
+            const uint32_t d_addr = tmem_base + acc * NACC;
+            for (int kc = 0; kc < p.k_chunks; ++kc) {
+                mbar_wait(&afull[a_stage], a_phase);
+                const uint64_t a_desc0 = desc_at(TMPL, smem_u32(a_smem + (size_t)a_stage * p.a_stage_bytes));
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait(&bfull[b_stage], b_phase);
+                    fence_after_sync();
+                    if (elect_one()) {
+                        const uint64_t b_desc0 = desc_at(TMPL, smem_u32(b_smem + (size_t)b_stage * B_BYTES));
+                        const uint32_t shift = (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * G_ROWB;
+#pragma unroll
+                        for (int kk = 0; kk < G_KC / 16; ++kk)
+#pragma unroll
+                            for (int ms = 0; ms < G_MSUB; ++ms)
+                                mma_bf16(d_addr + ms * NT, a_desc0 + ((shift + ms * G_M * G_ROWB + kk * 32) >> 4),
+                                         b_desc0 + ((kk * 32) >> 4), IDESC, (kc | tap | kk) != 0);
+                        mma_commit(&bempty[b_stage]);                               // weight slice reusable
+                        if (tap == 8) {
+                            mma_commit(&aempty[a_stage]);                           // activation tile reusable
+                            if (kc == p.k_chunks - 1) mma_commit(&tfull[acc]);      // accumulators ready for the epilogue
+                        }
+                    }
+                    __syncwarp();
+                    if (++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
+                }
+                if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ============================== epilogue (two groups of 4 warps, alternating tiles) ==============================
+        const int q = warp & 3;                       // TMEM sub-partition = lanes [32q, 32q+32)
+        const int grp = (warp - 4) >> 2;              // group g drains accumulator buffer g
+        const int plane = p.Hp * p.Wp;
+        int it = grp;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
+            mbar_wait(&tfull[grp], (it >> 1) & 1);
+            fence_after_sync();
+            const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * NT;
+#pragma unroll 1
+            for (int ms = 0; ms < G_MSUB; ++ms) {
+                const long long row = (long long)m_tile * G_TILE_ROWS + ms * G_M + q * 32 + lane;
+                const int rem = (int)(row % plane), hh = rem / p.Wp, ww = rem - hh * p.Wp;
+                const bool in_range = row < p.rows_total;
+                const bool interior = in_range && hh >= 1 && hh <= p.H && ww >= 1 && ww <= p.W;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * NACC + ms * NT;
+                __nv_bfloat16* dst = p.out + row * p.Cout + n0;
+                const __nv_bfloat16* msk = p.mask ? p.mask + row * p.Cout + n0 : nullptr;
+#pragma unroll 1
+                for (int c0 = 0; c0 < NT; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_x16(taddr + c0, v);
+                    tmem_ld_x16(taddr + c0 + 16, v + 16);
+                    tmem_ld_wait();
+                    if (in_range) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            float f[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = interior ? __uint_as_float(v[g * 8 + j]) : 0.f;
+                            if (interior) {
+                                if (p.bias) {
+                                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + g * 8));
+                                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + g * 8 + 4));
+                                    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                                    f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                                }
+                                if (p.relu) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                                }
+                                if (msk) {
+                                    const uint4 m = __ldg(reinterpret_cast<const uint4*>(msk + c0 + g * 8));
+                                    const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const uint32_t h = (mw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;   // bf16 > 0: sign clear, not zero
+                                        if ((h & 0x8000u) || !(h & 0x7FFFu)) f[j] = 0.f;
+                                    }
+                                }
+                            }
+                            uint4 o;
+                            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+                            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+                            *reinterpret_cast<uint4*>(dst + c0 + g * 8) = o;
+                        }
+                    }
+                }
+            }
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[grp]);        // accumulator buffer drained: the MMA warp may overwrite it
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad:  dW[oc, tap, c] = sum_pixels dY[pixel, oc] * X[pixel + shift(tap) - (Wp+1), c]      (both operands MN-major)
+// A CTA owns (MOC output channels) x (32 input channels) x all nine taps -- three accumulators of N = 96, the three
+// s-taps of a filter row folded into N (for an MN-major operand the leading byte offset is the distance between
+// 32-channel chunks, and 64 B is exactly one pixel row of the 32-channel X slice, so chunk j reads the rows shifted
+// by j pixels) -- and every `splits`-th 128-pixel block of the grid; accumulators stay in TMEM for the CTA's whole
+// pixel range; one FP32 partial per CTA and a fixed-order reduction keep the result deterministic.
+// ---------------------------------------------------------------------------------------------
+struct WgradGenParams {
+    int num_kblocks, rows_total, Wp;
+    int x_rows;                          // 128 + 2*Wp + 2
+    uint32_t x_stage_bytes;              // rounded to 1024
+    int n_stages;
+    int splits, c_chunks;                // gridDim.x = splits, gridDim.y = (OCp / MOC) * c_chunks
+    int OCp, Cp;
+    float* partial;                      // [splits][OCp][9][Cp]
+};
+
+template <int MOC>
+__global__ void __launch_bounds__(256, 1)
+conv3x3_wgrad_gen_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, WgradGenParams p) {
+    static_assert(MOC == 64 || MOC == 128, "M = 64 or 128 output channels per CTA");
+    constexpr int CB = 32;                                              // input channels per CTA: 64-byte rows, SWIZZLE_64B
+    constexpr int A_BOX = G_M * 128;                                    // one [128 pixels][64 oc] box, 16 KB
+    constexpr int A_BYTES = (MOC / 64) * A_BOX;
+    // MN-major A: 64-oc chunks A_BOX bytes apart (leading byte offset), 8 pixel rows = 1024 B (stride byte offset)
+    constexpr uint64_t TMPL_A = desc_template(MOC == 128 ? A_BOX : 16, 1024, LAYOUT_SW128);
+    constexpr uint64_t TMPL_B3 = desc_template(CB * 2, 8 * CB * 2, LAYOUT_SW64);
+    constexpr uint32_t IDESC3 = idesc_bf16(MOC, 3 * CB, 1, 1);
+    constexpr uint32_t TMEM_COLS = 512;                                 // 9 * 32 = 288 columns used
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t stage_bytes = A_BYTES + p.x_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + p.n_stages;
+    uint64_t* done = empty + p.n_stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x, item = blockIdx.y;
+    const int oc0 = (item / p.c_chunks) * MOC, c0 = (item % p.c_chunks) * CB;
+    pdl_trigger();
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_dy); tma_prefetch_desc(&map_x); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = split; kb < p.num_kblocks; kb += p.splits) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* st = smem + (size_t)stage * stage_bytes;
+                mbar_expect_tx(&full[stage], A_BYTES + (uint32_t)p.x_rows * CB * 2);
+#pragma unroll
+                for (int j = 0; j < MOC / 64; ++j) tma_load_2d(st + j * A_BOX, &map_dy, oc0 + j * 64, kb * G_M, &full[stage]);
+                tma_load_2d(st + A_BYTES, &map_x, c0, kb * G_M - (p.Wp + 1), &full[stage]);      // OOB rows read as 0
+                if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            int it = 0;
+            for (int kb = split; kb < p.num_kblocks; kb += p.splits, ++it) {
+                const int stage = it % p.n_stages;
+                mbar_wait(&full[stage], (it / p.n_stages) & 1);
+                fence_after_sync();
+                const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint64_t a_desc0 = desc_at(TMPL_A, st);
+                const uint64_t x_desc0 = desc_at(TMPL_B3, st + A_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < G_M / 16; ++ks) {
+                    const uint64_t adesc = a_desc0 + ((ks * 16 * 128) >> 4);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const uint32_t shift = (uint32_t)(r * p.Wp + ks * 16) * (CB * 2);
+                        mma_bf16(tmem_base + r * 3 * CB, adesc, x_desc0 + (shift >> 4), IDESC3, !(it == 0 && ks == 0));
+                    }
+                }
+                mma_commit(&empty[stage]);
+            }
+            mma_commit(done);
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const bool has_work = split < p.num_kblocks;
+        if (has_work) { mbar_wait(done, 0); fence_after_sync(); }
+        // M = 128: accumulator row m is TMEM lane m.  M = 64: rows sit in lanes (m % 16) + 32 * (m / 16).
+        const int m = MOC == 128 ? 32 * q + lane : 16 * q + lane;
+        const bool row_ok = MOC == 128 || lane < 16;
+        float* dst = p.partial + ((size_t)split * p.OCp + oc0 + m) * (size_t)(9 * p.Cp) + c0;
+        for (int c = 0; c < 9 * CB; c += 16) {
+            uint32_t raw[16];
+            if (has_work) { tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + c, raw); tmem_ld_wait(); }
+            if (row_ok) {
+                const int tap = c / CB, ch = c % CB;                    // column = (r*3 + s) * 32 + channel
+                float* d = dst + (size_t)tap * p.Cp + ch;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(d + j) = has_work
+                        ? make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// partial [splits][OCp][9][Cp] -> OIHW [OC][C][3][3], splits summed in a fixed order
+__global__ void wgrad_gen_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits,
+                                        int OC, int C, int OCp, int Cp) {
+    pdl_trigger();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // i = (oc * 9 + tap) * C + c : coalesced reads
+    if (i >= OC * C * 9) return;
+    const int oc = i / (9 * C), rem = i - oc * 9 * C, tap = rem / C, c = rem - tap * C;
+    const size_t src = ((size_t)oc * 9 + tap) * Cp + c, plane = (size_t)OCp * 9 * Cp;
+    float a = 0.f;
+    for (int s = 0; s < splits; ++s) a += __ldg(partial + s * plane + src);
+    dw[((size_t)oc * C + c) * 9 + tap] = a;
+}
+
+// bias gradient: db[oc] = sum over every row of the haloed bf16 gradient [rows][OCp] (halo rows are zero).
+// Stage 1: block b sums rows b, b + gridDim.x, ... (thread = channel pair x row lane); stage 2 sums the blocks in order.
+constexpr int DB_BLOCKS = 296;
+__global__ void __launch_bounds__(1024)
+dbias_partial_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ partial, int rows, int OCp) {
+    __shared__ float2 red[1024];
+    pdl_trigger();
+    pdl_wait();
+    const int pairs = OCp / 2, lanes = 1024 / pairs;            // OCp in {64,128,256,512}: pairs divides 1024
+    const int cp = threadIdx.x % pairs, rl = threadIdx.x / pairs;
+    float2 s = make_float2(0.f, 0.f);
+    if (rl < lanes)
+        for (long long r = (long long)blockIdx.x * lanes + rl; r < rows; r += (long long)gridDim.x * lanes) {
+            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(dy + r * OCp + 2 * cp);
+            s.x += __bfloat162float(v.x); s.y += __bfloat162float(v.y);
+        }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (rl == 0) {
+        for (int k = 1; k < lanes; ++k) { s.x += red[k * pairs + cp].x; s.y += red[k * pairs + cp].y; }
+        partial[(size_t)blockIdx.x * OCp + 2 * cp] = s.x;
+        partial[(size_t)blockIdx.x * OCp + 2 * cp + 1] = s.y;
+    }
+}
+__global__ void dbias_final_kernel(const float* __restrict__ partial, float* __restrict__ db, int blocks, int OC, int OCp) {
+    pdl_trigger();
+    pdl_wait();
+    const int oc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (oc >= OC) return;
+    float a = 0.f;
+    for (int b = 0; b < blocks; ++b) a += partial[(size_t)b * OCp + oc];
+    db[oc] = a;
+}
+
+// OIHW f32 [OC][C][3][3] -> bf16 [OCp][tap][Cp] (fprop B operand) and [Cp][8 - tap][OCp] (dgrad B operand), zero-padded channels
+__global__ void pack_conv_weights_gen_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                             __nv_bfloat16* __restrict__ wd, int OC, int C, int OCp, int Cp) {
+    pdl_trigger();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= OCp * Cp * 9) return;
+    const int oc = i / (Cp * 9), rem = i - oc * Cp * 9, c = rem / 9, tap = rem - c * 9;
+    const __nv_bfloat16 v = __float2bfloat16((oc < OC && c < C) ? w[((size_t)oc * C + c) * 9 + tap] : 0.f);
+    if (wf) wf[((size_t)oc * 9 + tap) * Cp + c] = v;
+    if (wd) wd[((size_t)c * 9 + (8 - tap)) * OCp + oc] = v;
+}
+
+// f32 NCHW [N][C][H][W] -> zero-haloed bf16 NHWC [N][H+2][W+2][Cp]; every element of the destination is written
+__global__ void pack_input_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp,
+                                       int N, int C, int H, int W, int Cp) {
+    pdl_trigger();
+    pdl_wait();
+    const int groups = Cp / 8, Hp = H + 2, Wp = W + 2;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)N * Hp * Wp * groups) return;
+    const int g = (int)(i % groups);
+    long long pix = i / groups;
+    const int ww = (int)(pix % Wp); pix /= Wp;
+    const int hh = (int)(pix % Hp);
+    const int n = (int)(pix / Hp);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        f[j] = (c < C && hh >= 1 && hh <= H && ww >= 1 && ww <= W)
+                   ? __ldg(x + (((size_t)n * C + c) * H + (hh - 1)) * W + (ww - 1)) : 0.f;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+    reinterpret_cast<uint4*>(xp)[i] = o;
+}
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+template <int NT>
+int launch_conv_gen(const void* x_pad, const void* w_packed, ConvGenParams p, cudaStream_t st) {
+    CUtensorMap ma, mb;
+    int rc = make_map_2d(&ma, x_pad, (uint64_t)p.Cin, (uint64_t)p.rows_total, (uint64_t)p.Cin * 2, G_KC, (uint32_t)p.a_box_rows,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map_2d(&mb, w_packed, (uint64_t)9 * p.Cin, (uint64_t)p.Cout, (uint64_t)9 * p.Cin * 2, G_KC, NT, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    constexpr int B_BYTES = NT * G_ROWB;
+    p.a_stages = 2;
+    const int budget = 212 * 1024 - p.a_stages * (int)p.a_stage_bytes;
+    p.b_stages = budget / B_BYTES > 9 ? 9 : budget / B_BYTES;
+    NM_REQUIRE(p.b_stages >= 2, "image too wide for the shared-memory budget");
+    const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * B_BYTES + 512;   // + mbarriers
+    auto kern = conv3x3_gen_kernel<NT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        NM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set = true;
+    }
+    const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    return nm::launch_pdl("conv3x3_gen", kern, dim3(grid), dim3(384), smem, st, ma, mb, p);
+}
+
+struct WgradGenPlan { int moc, items, splits, num_kblocks, rows_total; };
+
+WgradGenPlan wgrad_gen_plan(int N, int H, int W, int Cp, int OCp) {
+    WgradGenPlan g;
+    g.moc = OCp % 128 == 0 ? 128 : 64;
+    g.items = (OCp / g.moc) * (Cp / 32);
+    g.rows_total = N * (H + 2) * (W + 2);
+    g.num_kblocks = (g.rows_total + G_M - 1) / G_M;
+    int s = (2 * sm_count()) / g.items;                 // about two waves: the tail of the first hides under the second
+    if (s < 1) s = 1;
+    if (s > g.num_kblocks) s = g.num_kblocks;
+    if (s > 64) s = 64;
+    g.splits = s;
+    return g;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nm_tc_pack_conv_weights_gen_bf16(const float* w_oihw, void* w_fprop, void* w_dgrad, int OC, int C, int OCp, int Cp, void* stream) {
+    NM_REQUIRE(w_oihw && (w_fprop || w_dgrad), "null pointer");
+    NM_REQUIRE(OC > 0 && C > 0 && OCp >= OC && Cp >= C && OCp % 64 == 0 && Cp % 64 == 0, "padded channel counts must be multiples of 64");
+    const int total = OCp * Cp * 9;
+    return nm::launch_pdl("pack_conv_weights_gen", pack_conv_weights_gen_kernel, dim3(nm_cdiv(total, 256)), dim3(256), 0, nm::S(stream),
+                          w_oihw, static_cast<__nv_bfloat16*>(w_fprop), static_cast<__nv_bfloat16*>(w_dgrad), OC, C, OCp, Cp);
+}
+
+int nm_tc_pack_input_nhwc_bf16(const float* x_nchw, void* x_pad, int N, int C, int H, int W, int Cp, void* stream) {
+    NM_REQUIRE(x_nchw && x_pad, "null pointer");
+    NM_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && Cp >= C && Cp % 8 == 0, "bad dimensions");
+    const long long total = (long long)N * (H + 2) * (W + 2) * (Cp / 8);
+    return nm::launch_pdl("pack_input_nhwc", pack_input_nhwc_kernel, dim3(nm_cdiv((size_t)total, 256)), dim3(256), 0, nm::S(stream),
+                          x_nchw, static_cast<__nv_bfloat16*>(x_pad), N, C, H, W, Cp);
+}
+
+int nm_tc_conv3x3_gen_bf16(const void* x_pad, const void* w_packed, const float* bias, const void* relu_mask, void* y_pad,
+                           int N, int H, int W, int Cin, int Cout, int relu, void* stream) {
+    NM_REQUIRE(x_pad && w_packed && y_pad, "null pointer");
+    NM_REQUIRE(N > 0 && H > 0 && W > 0, "bad dimensions");
+    NM_REQUIRE(Cin > 0 && Cout > 0 && Cin % 64 == 0 && Cout % 64 == 0, "channel counts must be multiples of 64 (pad with zero channels)");
+    ConvGenParams p{};
+    p.Hp = H + 2; p.Wp = W + 2; p.H = H; p.W = W;
+    NM_REQUIRE((long long)N * p.Hp * p.Wp < (1ll << 31) - 1024, "batch too large for 32-bit row coordinates");
+    p.rows_total = N * p.Hp * p.Wp;
+    p.Cin = Cin; p.Cout = Cout;
+    p.k_chunks = Cin / G_KC;
+    const int nt = Cout % 128 == 0 ? 128 : 64;
+    p.n_tiles = Cout / nt;
+    p.num_tiles = ((p.rows_total + G_TILE_ROWS - 1) / G_TILE_ROWS) * p.n_tiles;
+    const int a_rows = G_TILE_ROWS + 2 * p.Wp + 2;
+    p.a_boxes = (a_rows + 255) / 256;
+    p.a_box_rows = round_up((a_rows + p.a_boxes - 1) / p.a_boxes, 8);
+    NM_REQUIRE(p.a_box_rows <= 256, "image too wide");
+    p.a_stage_bytes = (uint32_t)(p.a_boxes * p.a_box_rows) * G_ROWB;
+    p.out = static_cast<__nv_bfloat16*>(y_pad);
+    p.mask = static_cast<const __nv_bfloat16*>(relu_mask);
+    p.bias = bias;
+    p.relu = relu;
+    return nt == 128 ? launch_conv_gen<128>(x_pad, w_packed, p, nm::S(stream)) : launch_conv_gen<64>(x_pad, w_packed, p, nm::S(stream));
+}
+
+size_t nm_tc_conv3x3_wgrad_gen_workspace(int N, int H, int W, int Cp, int OCp) {
+    if (N <= 0 || H <= 0 || W <= 0 || Cp <= 0 || OCp <= 0 || Cp % 64 || OCp % 64) return 0;
+    const WgradGenPlan g = wgrad_gen_plan(N, H, W, Cp, OCp);
+    return (size_t)g.splits * OCp * 9 * Cp * sizeof(float) + (size_t)DB_BLOCKS * OCp * sizeof(float);
+}
+
+int nm_tc_conv3x3_wgrad_gen_bf16(const void* x_pad, const void* dy_pad, float* dw, float* dbias, void* workspace, size_t workspace_bytes,
+                                 int N, int H, int W, int C, int OC, int Cp, int OCp, void* stream) {
+    NM_REQUIRE(x_pad && dy_pad && dw && workspace, "null pointer");
+    NM_REQUIRE(N > 0 && H > 0 && W > 0, "bad dimensions");
+    NM_REQUIRE(C > 0 && OC > 0 && Cp >= C && OCp >= OC && Cp % 64 == 0 && OCp % 64 == 0, "padded channel counts must be multiples of 64");
+    NM_REQUIRE((long long)N * (H + 2) * (W + 2) < (1ll << 31) - 1024, "batch too large for 32-bit row coordinates");
+    const WgradGenPlan g = wgrad_gen_plan(N, H, W, Cp, OCp);
+    NM_REQUIRE(workspace_bytes >= nm_tc_conv3x3_wgrad_gen_workspace(N, H, W, Cp, OCp), "workspace too small");
+    WgradGenParams p{};
+    p.Wp = W + 2;
+    NM_REQUIRE(p.Wp <= 60, "image too wide for one TMA box");
+    p.rows_total = g.rows_total;
+    p.num_kblocks = g.num_kblocks;
+    p.x_rows = G_M + 2 * p.Wp + 2;
+    p.x_stage_bytes = ((uint32_t)p.x_rows * 64 + 1023u) & ~1023u;
+    const int a_bytes = (g.moc / 64) * G_M * 128;
+    {
+        const int fit = (int)((212 * 1024) / (a_bytes + p.x_stage_bytes));
+        p.n_stages = fit > 8 ? 8 : fit;
+    }
+    p.splits = g.splits;
+    p.c_chunks = (C + 31) / 32;                         // all-zero padded input-channel chunks are skipped
+    p.OCp = OCp; p.Cp = Cp;
+    p.partial = static_cast<float*>(workspace);
+    const int items = (OCp / g.moc) * p.c_chunks;
+    CUtensorMap mdy, mx;
+    int rc = make_map_2d(&mdy, dy_pad, (uint64_t)OCp, (uint64_t)p.rows_total, (uint64_t)OCp * 2, 64, G_M, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map_2d(&mx, x_pad, (uint64_t)Cp, (uint64_t)p.rows_total, (uint64_t)Cp * 2, 32, (uint32_t)p.x_rows, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    const size_t smem = (size_t)p.n_stages * (a_bytes + p.x_stage_bytes) + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        NM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_gen_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        NM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_gen_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set = true;
+    }
+    rc = g.moc == 128
+             ? nm::launch_pdl("conv3x3_wgrad_gen", conv3x3_wgrad_gen_kernel<128>, dim3(p.splits, items), dim3(256), smem, nm::S(stream), mdy, mx, p)
+             : nm::launch_pdl("conv3x3_wgrad_gen", conv3x3_wgrad_gen_kernel<64>, dim3(p.splits, items), dim3(256), smem, nm::S(stream), mdy, mx, p);
+    if (rc) return rc;
+    rc = nm::launch_pdl("wgrad_gen_reduce", wgrad_gen_reduce_kernel, dim3(nm_cdiv((size_t)OC * C * 9, 256)), dim3(256), 0, nm::S(stream),
+                        (const float*)p.partial, dw, p.splits, OC, C, OCp, Cp);
+    if (rc || !dbias) return rc;
+    float* dbp = p.partial + (size_t)g.splits * OCp * 9 * Cp;
+    NM_REQUIRE(OCp <= 2048, "bias gradient: too many channels for one block");
+    const int lanes = 1024 / (OCp / 2);
+    int blocks = (p.rows_total + lanes - 1) / lanes;
+    if (blocks > DB_BLOCKS) blocks = DB_BLOCKS;
+    rc = nm::launch_pdl("dbias_partial", dbias_partial_kernel, dim3(blocks), dim3(1024), 0, nm::S(stream),
+                        static_cast<const __nv_bfloat16*>(dy_pad), dbp, p.rows_total, OCp);
+    if (rc) return rc;
+    return nm::launch_pdl("dbias_final", dbias_final_kernel, dim3(nm_cdiv(OC, 128)), dim3(128), 0, nm::S(stream),
+                          (const float*)dbp, dbias, blocks, OC, OCp);
+}
+
+}  // extern "C"

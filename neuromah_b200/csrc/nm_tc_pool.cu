@@ -1,0 +1,146 @@
+// Memory-bound glue kernels of the general bf16 plan (haloed NHWC bf16 activations, see nm_tc_conv_gen.cu):
+// MaxPooling2D(2, 2) forward / backward and the Dense input gradient.  CUDA cores, 128-bit accesses, one thread per
+// (pixel, 8 channels) -- these are HBM-bound (a few bytes per element and no reuse), not GEMM-shaped.
+//
+// Replaces: Layer_MaxPooling2D.forward / backward (src/layers/MaxPooling2D.py:37-84, maxpooling_backend.cpp:24-133,
+// :145-238) together with the ReLU backward of the conv that feeds the pool (Relu.py:12-14), and Layer_Dense's
+// `dinputs = dvalues . W^T` (Dense.py:108), for the tensor-core mode.
+#include "nm_common.cuh"
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int kNO = 16;          // classes the Dense head supports (nm_tc_dense.cu)
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// x_pad [N][H+2][W+2][C] -> y [N][H/2 (+2)][W/2 (+2)][C], idx [N][H/2][W/2][C/2] nibbles:
+// bits 0-1 = position of the FIRST maximum in the reference's row-major window scan (maxpooling_backend.cpp:94-108),
+// bit 2 = (max > 0), i.e. the ReLU mask of the conv below at the element the gradient is routed to.
+__global__ void maxpool2x2_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint32_t* __restrict__ idx,
+                                      int N, int H, int W, int C, int out_padded) {
+    pdl_trigger();
+    pdl_wait();
+    const int G = C / 8, PH = H / 2, PW = W / 2, Wp = W + 2;
+    const int OH = out_padded ? PH + 2 : PH, OW = out_padded ? PW + 2 : PW;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)N * OH * OW * G) return;
+    const int g = (int)(i % G);
+    long long pix = i / G;
+    const int ow = (int)(pix % OW); pix /= OW;
+    const int oh = (int)(pix % OH);
+    const int n = (int)(pix / OH);
+    const int ph = out_padded ? oh - 1 : oh, pw = out_padded ? ow - 1 : ow;
+    if (ph < 0 || ph >= PH || pw < 0 || pw >= PW) { y[i] = make_uint4(0u, 0u, 0u, 0u); return; }     // halo of the output
+    const size_t base = (((size_t)n * (H + 2) + 2 * ph + 1) * Wp + 2 * pw + 1) * G + g;
+    const uint4 v[4] = {__ldg(x + base), __ldg(x + base + G), __ldg(x + base + (size_t)Wp * G), __ldg(x + base + (size_t)Wp * G + G)};
+    const uint32_t* w0 = reinterpret_cast<const uint32_t*>(&v[0]);
+    uint32_t out[4], nib = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {            // 32-bit word k = channels 2k, 2k+1
+        float best[2] = {bf16_lo(w0[k]), bf16_hi(w0[k])};
+        uint32_t pos[2] = {0u, 0u};
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+            const uint32_t wq = reinterpret_cast<const uint32_t*>(&v[q])[k];
+            const float c0 = bf16_lo(wq), c1 = bf16_hi(wq);
+            if (c0 > best[0]) { best[0] = c0; pos[0] = q; }                 // strict: the first maximum wins
+            if (c1 > best[1]) { best[1] = c1; pos[1] = q; }
+        }
+        out[k] = (__float_as_uint(best[0]) >> 16) | (__float_as_uint(best[1]) & 0xFFFF0000u);
+        nib |= (pos[0] | (best[0] > 0.f ? 4u : 0u)) << (8 * k);
+        nib |= (pos[1] | (best[1] > 0.f ? 4u : 0u)) << (8 * k + 4);
+    }
+    y[i] = make_uint4(out[0], out[1], out[2], out[3]);
+    idx[(((size_t)n * PH + ph) * PW + pw) * G + g] = nib;
+}
+
+// dpool [N][H/2 (+2)][W/2 (+2)][C] + idx -> dy_pad [N][H+2][W+2][C]: the pooled gradient goes to the arg-max position
+// of its window if the ReLU mask bit is set, every other element (halo included) is written as zero.
+__global__ void maxpool2x2_bwd_kernel(const uint4* __restrict__ dpool, const uint32_t* __restrict__ idx, uint4* __restrict__ dy,
+                                      int N, int H, int W, int C, int in_padded) {
+    pdl_trigger();
+    pdl_wait();
+    const int G = C / 8, PH = H / 2, PW = W / 2, Hp = H + 2, Wp = W + 2;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)N * Hp * Wp * G) return;
+    const int g = (int)(i % G);
+    long long pix = i / G;
+    const int ww = (int)(pix % Wp); pix /= Wp;
+    const int hh = (int)(pix % Hp);
+    const int n = (int)(pix / Hp);
+    if (hh < 1 || hh > H || ww < 1 || ww > W) { dy[i] = make_uint4(0u, 0u, 0u, 0u); return; }
+    const int ph = (hh - 1) >> 1, pw = (ww - 1) >> 1;
+    const uint32_t me = (uint32_t)(((hh - 1) & 1) * 2 + ((ww - 1) & 1)) | 4u;        // nibble that selects this element
+    const uint32_t nib = __ldg(idx + (((size_t)n * PH + ph) * PW + pw) * G + g);
+    const size_t src = in_padded ? (((size_t)n * (PH + 2) + ph + 1) * (PW + 2) + pw + 1) * G + g
+                                 : (((size_t)n * PH + ph) * PW + pw) * G + g;
+    const uint4 d = __ldg(dpool + src);
+    const uint32_t dv[4] = {d.x, d.y, d.z, d.w};
+    uint32_t out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t lo = ((nib >> (8 * k)) & 7u) == me ? 0x0000FFFFu : 0u;
+        const uint32_t hi = ((nib >> (8 * k + 4)) & 7u) == me ? 0xFFFF0000u : 0u;
+        out[k] = dv[k] & (lo | hi);
+    }
+    dy[i] = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+// dX[b][k] = sum_j dlogits[b][j] * Wp[j][k]   (Wp = the Dense weights packed as [n_out][K] in the kernels' (h,w,c) order)
+__global__ void dense_dgrad_bf16_kernel(const float* __restrict__ dlogits, const float* __restrict__ wp, uint4* __restrict__ dx,
+                                        int B, int K, int n_out) {
+    pdl_trigger();
+    pdl_wait();
+    const int G = K / 8;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * G) return;
+    const int b = (int)(i / G), g = (int)(i - (long long)b * G);
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < n_out; ++j) {
+        const float d = __ldg(dlogits + (size_t)b * n_out + j);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp + (size_t)j * K + g * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + (size_t)j * K + g * 8 + 4));
+        a[0] = fmaf(d, w0.x, a[0]); a[1] = fmaf(d, w0.y, a[1]); a[2] = fmaf(d, w0.z, a[2]); a[3] = fmaf(d, w0.w, a[3]);
+        a[4] = fmaf(d, w1.x, a[4]); a[5] = fmaf(d, w1.y, a[5]); a[6] = fmaf(d, w1.z, a[6]); a[7] = fmaf(d, w1.w, a[7]);
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 t = __floats2bfloat162_rn(a[2 * k], a[2 * k + 1]);
+        o[k] = *reinterpret_cast<const uint32_t*>(&t);
+    }
+    dx[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+}  // namespace
+
+extern "C" {
+
+int nm_tc_maxpool2x2_fwd_bf16(const void* x_pad, void* y, void* idx, int N, int H, int W, int C, int out_padded, void* stream) {
+    NM_REQUIRE(x_pad && y && idx, "null pointer");
+    NM_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0, "bad dimensions (even H, W; C % 8 == 0)");
+    const long long total = (long long)N * (H / 2 + (out_padded ? 2 : 0)) * (W / 2 + (out_padded ? 2 : 0)) * (C / 8);
+    return nm::launch_pdl("maxpool2x2_fwd", maxpool2x2_fwd_kernel, dim3(nm_cdiv((size_t)total, 256)), dim3(256), 0, nm::S(stream),
+                          static_cast<const uint4*>(x_pad), static_cast<uint4*>(y), static_cast<uint32_t*>(idx), N, H, W, C, out_padded);
+}
+
+int nm_tc_maxpool2x2_bwd_bf16(const void* dpool, const void* idx, void* dy_pad, int N, int H, int W, int C, int in_padded, void* stream) {
+    NM_REQUIRE(dpool && idx && dy_pad, "null pointer");
+    NM_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0, "bad dimensions (even H, W; C % 8 == 0)");
+    const long long total = (long long)N * (H + 2) * (W + 2) * (C / 8);
+    return nm::launch_pdl("maxpool2x2_bwd", maxpool2x2_bwd_kernel, dim3(nm_cdiv((size_t)total, 256)), dim3(256), 0, nm::S(stream),
+                          static_cast<const uint4*>(dpool), static_cast<const uint32_t*>(idx), static_cast<uint4*>(dy_pad), N, H, W, C,
+                          in_padded);
+}
+
+int nm_tc_dense_dgrad_bf16(const float* dlogits, const float* w_packed, void* dx, int B, int K, int n_out, void* stream) {
+    NM_REQUIRE(dlogits && w_packed && dx, "null pointer");
+    NM_REQUIRE(B > 0 && K > 0 && K % 8 == 0 && n_out > 0 && n_out <= kNO, "bad dimensions");
+    const long long total = (long long)B * (K / 8);
+    return nm::launch_pdl("dense_dgrad_bf16", dense_dgrad_bf16_kernel, dim3(nm_cdiv((size_t)total, 256)), dim3(256), 0, nm::S(stream),
+                          dlogits, w_packed, static_cast<uint4*>(dx), B, K, n_out);
+}
+
+}  // extern "C"

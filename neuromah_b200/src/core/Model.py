@@ -66,7 +66,8 @@ class Model:
 
     def finalize(self, xp=np, mode=None):
         """``mode``: None / "fp32" = FP32-exact CUDA-core kernels (per-layer launches, reference layouts);
-        "bf16" = fused tensor-core plan (neuromah_b200/tc_plan.py) for the supported layer pattern."""
+        "bf16" = tensor-core plan for the supported layer patterns (neuromah_b200/tc_plan.py: the MNIST CNN;
+        neuromah_b200/tc_plan_gen.py: VGG-style conv stacks)."""
         from ..activations import Activation_Softmax
         from ..losses import Loss_CategoricalCrossentropy
         from ..losses.Activation_Softmax_Loss_CategoricalCrossentropy import \
@@ -106,7 +107,9 @@ class Model:
         self.plan = None
         if self.mode == "bf16":
             from ...tc_plan import TcCnnPlan
-            self.plan = TcCnnPlan(self)
+            from ...tc_plan_gen import TcStackPlan
+            # the MNIST pattern has its own fully fused kernels; any other VGG-style stack takes the general plan
+            self.plan = TcCnnPlan(self) if TcCnnPlan.match(self) or not TcStackPlan.match(self) else TcStackPlan(self)
         elif self.mode != "fp32":
             raise ValueError("mode must be None, 'fp32' or 'bf16'")
         if self.tensorMonitor:

@@ -1,0 +1,221 @@
+"""bf16 tensor-core execution plan for a general VGG-style stack (BASELINE.json config 4):
+
+    ( Conv2D(3x3, same, ReLU) x k  ->  MaxPooling2D(2, 2) ) x m  ->  Flatten  ->  Dense(-> n <= 16)  ->  Softmax
+
+with every conv's out_channels a multiple of 64 (the first conv's in_channels are zero-padded to 64).
+``Model.finalize(mode="bf16")`` picks this plan when the net is not the MNIST pattern of tc_plan.py.
+
+Every contraction runs on tcgen05 tensor cores: the convs through the streamed-filter implicit GEMM of
+nm_tc_conv_gen.cu (fprop + ReLU; dgrad + the ReLU backward of the layer below; wgrad + bias gradient), the Dense head
+through nm_tc_dense.cu (logits + softmax + CE + gradient in one launch; wgrad).  Pool forward / backward and the Dense
+input gradient are HBM-bound CUDA-core kernels (nm_tc_pool.cu).  Activations are bf16 NHWC with a zero halo;
+parameters, gradients and optimizer state stay FP32 in the arena in the reference's layouts, so the optimizers, the
+data-parallel exchange, FedAvg and save/load are shared with the FP32 path.
+Numerics: bf16 operands and stored activations, FP32 accumulation (stated tolerance in tests/test_gpu_vgg_tc_plan.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._lib import lib
+from .device import DeviceArray, stream
+from .tc_plan import Bf16Activation, _timed
+
+
+def _rup(a, b=64):
+    return (a + b - 1) // b * b
+
+
+class TcStackPlan:
+    PATTERN = ("(Conv2D(3x3,same,ReLU, out_channels % 64 == 0) x k -> MaxPooling2D(2,2)) x m -> Flatten -> "
+               "Dense(-> n <= 16) -> Softmax")
+
+    # ------------------------------------------------------------------ pattern ----
+    @staticmethod
+    def parse(model):
+        """-> (blocks, flatten, dense, softmax) with blocks = [([conv, ...], pool), ...], or None."""
+        from .src.layers import Layer_Conv2D, Layer_MaxPooling2D, Layer_Dense, Layer_Flatten
+        from .src.activations import Activation_ReLU, Activation_Softmax
+        L = list(model.layers)
+        if len(L) < 5 or not (isinstance(L[-1], Activation_Softmax) and isinstance(L[-2], Layer_Dense)
+                              and isinstance(L[-3], Layer_Flatten)):
+            return None
+        blocks, convs = [], []
+        for layer in L[:-3]:
+            if isinstance(layer, Layer_Conv2D):
+                oc, _, kh, kw = layer.weights.shape
+                if (kh, kw) != (3, 3) or layer.padding != "same" or type(layer.activation) is not Activation_ReLU or oc % 64:
+                    return None
+                if tuple(np.atleast_1d(layer.stride)) not in ((1,), (1, 1)):
+                    return None
+                convs.append(layer)
+            elif isinstance(layer, Layer_MaxPooling2D):
+                if not convs or layer.pool_size != (2, 2) or layer.strides != (2, 2) or layer.padding != "valid":
+                    return None
+                blocks.append((convs, layer))
+                convs = []
+            else:
+                return None
+        if convs or not blocks:
+            return None
+        de = L[-2]
+        if de.activation is not None or de.weights.shape[1] > 16:
+            return None
+        ic = None
+        for cs, _ in blocks:
+            for c in cs:
+                if ic is not None and c.weights.shape[1] != ic:
+                    return None
+                ic = c.weights.shape[0]
+        return blocks, L[-3], de, L[-1]
+
+    @staticmethod
+    def match(model):
+        return TcStackPlan.parse(model) is not None
+
+    def __init__(self, model):
+        parsed = self.parse(model)
+        if parsed is None:
+            raise ValueError(f"mode='bf16' supports the layer patterns: {self.PATTERN}")
+        if model.softmax_classifier_output is None:
+            raise ValueError("mode='bf16' needs Loss_CategoricalCrossentropy with a final Activation_Softmax")
+        from . import config
+        if config.conv_backward != "wired" or config.conv_bias_in_forward:
+            raise ValueError("mode='bf16' implements the default quirk settings only")
+        self.model = model
+        self.blocks, self.fl, self.de, self.sm = parsed
+        self.convs = [c for cs, _ in self.blocks for c in cs]
+        self.n_out = self.de.weights.shape[1]
+        self.B = 0
+        self.hw = None
+        self.packed = {}
+        for c in self.convs:
+            oc, ic = c.weights.shape[:2]
+            ocp, icp = _rup(oc), _rup(ic)
+            self.packed[id(c)] = (DeviceArray((ocp, 9, icp), np.uint16), DeviceArray((icp, 9, ocp), np.uint16), ocp, icp)
+
+    # ------------------------------------------------------------------ buffers ----
+    def _ensure(self, B, C, H, W):
+        if B <= self.B and (C, H, W) == self.hw:
+            return
+        if C != self.convs[0].weights.shape[1]:
+            raise RuntimeError(f"Input has {C} channels, the first Conv2D expects {self.convs[0].weights.shape[1]}")
+        self.hw, self.B = (C, H, W), B
+        z = DeviceArray.zeros
+        self.x_pad = z((B, H + 2, W + 2, _rup(C)), np.uint16)
+        self.steps = []                     # per block: dict(convs=[(layer, in_buf, act, dy, h, w)], pool=..., ...)
+        cur, h, w = self.x_pad, H, W
+        ws = 256
+        for bi, (cs, pool) in enumerate(self.blocks):
+            if h % 2 or w % 2:
+                raise ValueError("mode='bf16' needs even feature-map sizes at every MaxPooling2D(2, 2)")
+            entries = []
+            for c in cs:
+                _, _, ocp, icp = self.packed[id(c)]
+                act = z((B, h + 2, w + 2, ocp), np.uint16)
+                dy = z((B, h + 2, w + 2, ocp), np.uint16)
+                entries.append(dict(layer=c, inp=cur, act=act, dy=dy, h=h, w=w, ocp=ocp, icp=icp))
+                ws = max(ws, lib.nm_tc_conv3x3_wgrad_gen_workspace(B, h, w, icp, ocp))
+                cur = act
+            last = bi == len(self.blocks) - 1
+            ch = entries[-1]["ocp"]
+            shape = (B, h // 2, w // 2, ch) if last else (B, h // 2 + 2, w // 2 + 2, ch)
+            pooled, dpool = z(shape, np.uint16), z(shape, np.uint16)
+            idx = z((B, h // 2, w // 2, ch // 2), np.uint8)
+            self.steps.append(dict(convs=entries, pool=pool, pooled=pooled, dpool=dpool, idx=idx, h=h, w=w, ch=ch, padded=0 if last else 1))
+            cur, h, w = pooled, h // 2, w // 2
+        self.HW, self.Cl = h * w, self.steps[-1]["ch"]
+        K = self.HW * self.Cl
+        if self.de.weights.shape[0] != K:
+            raise ValueError(f"Dense expects {self.de.weights.shape[0]} inputs, the conv stack produces {K}")
+        self.K = K
+        self.probs = z((B, self.n_out))
+        self.dlogits = z((B, self.n_out))
+        self.losses = z((B,))
+        self.correct = z((B,), np.int32)
+        self.dummy_labels = z((B,), np.int32)
+        self.dl_hilo = z((B, 32), np.uint16)
+        self.w3p = DeviceArray((self.n_out, K), np.float32)
+        self.w3hl = z((32, K), np.uint16)
+        self.ws = DeviceArray((ws,), np.uint8)
+        self.ws_dw = DeviceArray((max(lib.nm_tc_dense_wgrad_workspace(B, K), 256),), np.uint8)
+        self.ws_head = z((lib.nm_tc_dense_softmax_ce_workspace(B, K),), np.uint8)     # zero-filled once (ticket counter)
+
+    def pack_weights(self):
+        """Refresh the bf16 operand copies from the FP32 master weights in the arena."""
+        s = stream()
+        for c in self.convs:
+            wf, wd, ocp, icp = self.packed[id(c)]
+            oc, ic = c.weights.shape[:2]
+            lib.nm_tc_pack_conv_weights_gen_bf16(c.weights.p, wf.p, wd.p, oc, ic, ocp, icp, s)
+        lib.nm_tc_pack_dense_weights(self.de.weights.p, self.w3p.p, self.w3hl.p, self.K, self.n_out, self.HW, self.Cl, s)
+
+    # ------------------------------------------------------------------ passes ----
+    def forward(self, x: DeviceArray, labels=None, accum=None, inv_batch=None):
+        if x.ndim != 4:
+            raise RuntimeError("Input and kernel must be 4D tensors")
+        B, C, H, W = x.shape
+        self._ensure(B, C, H, W)
+        s = stream()
+        self.x = x
+        self.pack_weights()          # master weights may have changed (optimizer, set_parameters, FedAvg)
+        _timed('tc_pack_input', lib.nm_tc_pack_input_nhwc_bf16, x.p, self.x_pad.p, B, C, H, W, self.x_pad.shape[3], s)
+        for st in self.steps:
+            for e in st["convs"]:
+                wf = self.packed[id(e["layer"])][0]
+                _timed('tc_conv_gen_fprop', lib.nm_tc_conv3x3_gen_bf16, e["inp"].p, wf.p, None, None, e["act"].p,
+                       B, e["h"], e["w"], e["icp"], e["ocp"], 1, s)
+                e["layer"].output = Bf16Activation(e["act"], B, 1)
+            _timed('tc_maxpool_fwd', lib.nm_tc_maxpool2x2_fwd_bf16, st["convs"][-1]["act"].p, st["pooled"].p, st["idx"].p,
+                   B, st["h"], st["w"], st["ch"], st["padded"], s)
+            st["pool"].output = Bf16Activation(st["pooled"], B, st["padded"])
+        last = self.steps[-1]
+        lab = labels if labels is not None else self.dummy_labels
+        _timed('tc_dense_softmax_ce', lib.nm_tc_dense_softmax_ce_bf16, last["pooled"].p, self.w3hl.p, self.de.biases.p, lab.p,
+               self.probs.p, self.dlogits.p, self.dl_hilo.p, self.losses.p, self.correct.p,
+               accum.p if accum is not None else None, self.ws_head.p, self.ws_head.nbytes,
+               B, self.K, self.n_out, float(1.0 / B if inv_batch is None else inv_batch), s)
+        self.dl_hilo_valid = labels is not None
+        out = self.probs[0:B]
+        self.fl.output = last["pool"].output
+        self.sm.output = out
+        self.model.softmax_classifier_output.dinputs = self.dlogits[0:B]
+        return out
+
+    def backward(self, grad_batch=None, comm=None, fork=False):
+        """``comm``: data-parallel communicator -- the gradient slab is all-reduced after the last kernel.
+        ``fork`` is accepted for interface parity with TcCnnPlan (the chain is not forked here)."""
+        B = self.x.shape[0]
+        s = stream()
+        scale = 1.0 / (B if grad_batch is None else grad_batch)
+        if not getattr(self, "dl_hilo_valid", False):      # dlogits were written by the public-API backward
+            lib.nm_tc_pack_dlogits_bf16(self.dlogits.p, self.dl_hilo.p, B, self.n_out, s)
+        last = self.steps[-1]
+        _timed('tc_dense_wgrad', lib.nm_tc_dense_wgrad_bf16, last["pooled"].p, self.dl_hilo.p, self.dlogits.p, self.de.weights.p,
+               self.de.dweights.p, self.de.dbiases.p, self.ws_dw.p, self.ws_dw.nbytes, B, self.K, self.n_out, self.HW, self.Cl,
+               float(scale), float(self.de.weight_regularizer_l1), float(self.de.weight_regularizer_l2), s)
+        _timed('tc_dense_dgrad', lib.nm_tc_dense_dgrad_bf16, self.dlogits.p, self.w3p.p, last["dpool"].p, B, self.K, self.n_out, s)
+        first = self.convs[0]
+        for bi in range(len(self.steps) - 1, -1, -1):
+            st = self.steps[bi]
+            cs = st["convs"]
+            # pool backward + ReLU backward of the block's last conv -> its dY
+            _timed('tc_maxpool_bwd', lib.nm_tc_maxpool2x2_bwd_bf16, st["dpool"].p, st["idx"].p, cs[-1]["dy"].p,
+                   B, st["h"], st["w"], st["ch"], st["padded"], s)
+            for j in range(len(cs) - 1, -1, -1):
+                e = cs[j]
+                c = e["layer"]
+                oc, ic = c.weights.shape[:2]
+                _timed('tc_conv_gen_wgrad', lib.nm_tc_conv3x3_wgrad_gen_bf16, e["inp"].p, e["dy"].p, c.weight_gradients.p,
+                       c.bias_gradients.p, self.ws.p, self.ws.nbytes, B, e["h"], e["w"], ic, oc, e["icp"], e["ocp"], s)
+                if c is first:
+                    continue                                # no consumer for the first layer's input gradient
+                wd = self.packed[id(c)][1]
+                if j > 0:       # input = the previous conv's post-ReLU output: dgrad + its ReLU backward -> its dY
+                    dst, mask = cs[j - 1]["dy"], cs[j - 1]["act"]
+                else:           # input = the previous block's pooled tensor: plain dgrad -> its dpool (haloed)
+                    dst, mask = self.steps[bi - 1]["dpool"], None
+                _timed('tc_conv_gen_dgrad', lib.nm_tc_conv3x3_gen_bf16, e["dy"].p, wd.p, None, mask.p if mask is not None else None,
+                       dst.p, B, e["h"], e["w"], e["ocp"], e["icp"], 0, s)
+        if comm is not None:
+            comm.allreduce_async(self.model.arena.grads, 0, self.model.arena.total)
