@@ -30,7 +30,9 @@ def _pack_weights(w):
     ocp, cp = _rup(oc), _rup(c)
     wf = DeviceArray((ocp, 9, cp), np.uint16)
     wd = DeviceArray((cp, 9, ocp), np.uint16)
-    lib.nm_tc_pack_conv_weights_gen_bf16(DeviceArray.from_numpy(w).p, wf.p, wd.p, oc, c, ocp, cp, stream())
+    w_dev = DeviceArray.from_numpy(w)                  # keep the source alive until the (asynchronous) pack has been enqueued
+    lib.nm_tc_pack_conv_weights_gen_bf16(w_dev.p, wf.p, wd.p, oc, c, ocp, cp, stream())
+    wf.numpy()                                         # synchronises: w_dev may go
     return wf, wd, ocp, cp
 
 
@@ -77,7 +79,8 @@ def test_tc_gen_fprop_bias_relu(n, h, w, c, oc, integer):
         np.testing.assert_allclose(gi, ref, rtol=2 ** -7, atol=2e-3)
     # bias switch (config.conv_bias), no ReLU
     b = _data(rng, (oc,), integer)
-    lib.nm_tc_conv3x3_gen_bf16(xp.p, wf.p, DeviceArray.from_numpy(b).p, None, y.p, n, h, w, c, oc, 0, stream())
+    b_dev = DeviceArray.from_numpy(b)
+    lib.nm_tc_conv3x3_gen_bf16(xp.p, wf.p, b_dev.p, None, y.p, n, h, w, c, oc, 0, stream())
     ref2, _ = R.conv_layer_forward(x, wt, None, padding="same", relu=False, dtype=np.float64)
     ref2 = ref2 + b.reshape(1, oc, 1, 1)
     got = y.numpy()
@@ -99,7 +102,8 @@ def test_tc_gen_first_layer_from_nchw_input():
     wt = _data(rng, (oc, c, 3, 3), True, -1, 2)
     wf, _, ocp, cp = _pack_weights(wt)
     xp = DeviceArray.from_numpy(np.full((n, h + 2, w + 2, cp), 0x7FC0, np.uint16))
-    lib.nm_tc_pack_input_nhwc_bf16(DeviceArray.from_numpy(x).p, xp.p, n, c, h, w, cp, stream())
+    x_dev = DeviceArray.from_numpy(x)
+    lib.nm_tc_pack_input_nhwc_bf16(x_dev.p, xp.p, n, c, h, w, cp, stream())
     np.testing.assert_array_equal(xp.numpy(), pad_nhwc(_pad_channels(x, cp)))
     y = DeviceArray.zeros((n, h + 2, w + 2, oc), np.uint16)
     lib.nm_tc_conv3x3_gen_bf16(xp.p, wf.p, None, None, y.p, n, h, w, cp, oc, 1, stream())
