@@ -256,7 +256,7 @@ int nm_tc_conv3x3_gen_bf16(const void* x_pad, const void* w_packed, const float*
                            int N, int H, int W, int Cin, int Cout, int relu, void* stream);
 /* wgrad (Conv2D.cpp:207-216: summed over the batch, no normalisation) -> dw f32 OIHW [OC][C][3][3], and, if dbias is
  * not NULL, the bias gradient sum_{n,h,w} dY -> dbias f32 [OC] (Conv_wrapepr.py:107-109).  Deterministic. */
-size_t nm_tc_conv3x3_wgrad_gen_workspace(int N, int H, int W, int Cp, int OCp);
+size_t nm_tc_conv3x3_wgrad_gen_workspace(int N, int H, int W, int C, int Cp, int OCp);
 int nm_tc_conv3x3_wgrad_gen_bf16(const void* x_pad, const void* dy_pad, float* dw, float* dbias, void* workspace, size_t workspace_bytes,
                                  int N, int H, int W, int C, int OC, int Cp, int OCp, void* stream);
 

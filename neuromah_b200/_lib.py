@@ -90,7 +90,7 @@ _SIGS = {
     "nm_tc_pack_conv_weights_gen_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "nm_tc_pack_input_nhwc_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_conv3x3_gen_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "nm_tc_conv3x3_wgrad_gen_workspace": (_sz, [_i, _i, _i, _i, _i]),
+    "nm_tc_conv3x3_wgrad_gen_workspace": (_sz, [_i, _i, _i, _i, _i, _i]),
     "nm_tc_conv3x3_wgrad_gen_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_maxpool2x2_fwd_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_maxpool2x2_bwd_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

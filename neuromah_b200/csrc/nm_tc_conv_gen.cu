@@ -442,18 +442,19 @@ int launch_conv_gen(const void* x_pad, const void* w_packed, ConvGenParams p, cu
     return nm::launch_pdl("conv3x3_gen", kern, dim3(grid), dim3(384), smem, st, ma, mb, p);
 }
 
-struct WgradGenPlan { int moc, items, splits, num_kblocks, rows_total; };
+struct WgradGenPlan { int moc, c_chunks, items, splits, num_kblocks, rows_total; };
 
-WgradGenPlan wgrad_gen_plan(int N, int H, int W, int Cp, int OCp) {
+WgradGenPlan wgrad_gen_plan(int N, int H, int W, int C, int OCp) {
     WgradGenPlan g;
     g.moc = OCp % 128 == 0 ? 128 : 64;
-    g.items = (OCp / g.moc) * (Cp / 32);
+    g.c_chunks = (C + 31) / 32;                         // all-zero padded input-channel chunks are skipped
+    g.items = (OCp / g.moc) * g.c_chunks;
     g.rows_total = N * (H + 2) * (W + 2);
     g.num_kblocks = (g.rows_total + G_M - 1) / G_M;
     int s = (2 * sm_count()) / g.items;                 // about two waves: the tail of the first hides under the second
+    if (s * g.items > sm_count() && s * g.items < 2 * sm_count()) s = sm_count() / g.items;   // ... or exactly one
     if (s < 1) s = 1;
     if (s > g.num_kblocks) s = g.num_kblocks;
-    if (s > 64) s = 64;
     g.splits = s;
     return g;
 }
@@ -504,9 +505,9 @@ int nm_tc_conv3x3_gen_bf16(const void* x_pad, const void* w_packed, const float*
     return nt == 128 ? launch_conv_gen<128>(x_pad, w_packed, p, nm::S(stream)) : launch_conv_gen<64>(x_pad, w_packed, p, nm::S(stream));
 }
 
-size_t nm_tc_conv3x3_wgrad_gen_workspace(int N, int H, int W, int Cp, int OCp) {
-    if (N <= 0 || H <= 0 || W <= 0 || Cp <= 0 || OCp <= 0 || Cp % 64 || OCp % 64) return 0;
-    const WgradGenPlan g = wgrad_gen_plan(N, H, W, Cp, OCp);
+size_t nm_tc_conv3x3_wgrad_gen_workspace(int N, int H, int W, int C, int Cp, int OCp) {
+    if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cp < C || OCp <= 0 || Cp % 64 || OCp % 64) return 0;
+    const WgradGenPlan g = wgrad_gen_plan(N, H, W, C, OCp);
     return (size_t)g.splits * OCp * 9 * Cp * sizeof(float) + (size_t)DB_BLOCKS * OCp * sizeof(float);
 }
 
@@ -516,8 +517,8 @@ int nm_tc_conv3x3_wgrad_gen_bf16(const void* x_pad, const void* dy_pad, float* d
     NM_REQUIRE(N > 0 && H > 0 && W > 0, "bad dimensions");
     NM_REQUIRE(C > 0 && OC > 0 && Cp >= C && OCp >= OC && Cp % 64 == 0 && OCp % 64 == 0, "padded channel counts must be multiples of 64");
     NM_REQUIRE((long long)N * (H + 2) * (W + 2) < (1ll << 31) - 1024, "batch too large for 32-bit row coordinates");
-    const WgradGenPlan g = wgrad_gen_plan(N, H, W, Cp, OCp);
-    NM_REQUIRE(workspace_bytes >= nm_tc_conv3x3_wgrad_gen_workspace(N, H, W, Cp, OCp), "workspace too small");
+    const WgradGenPlan g = wgrad_gen_plan(N, H, W, C, OCp);
+    NM_REQUIRE(workspace_bytes >= nm_tc_conv3x3_wgrad_gen_workspace(N, H, W, C, Cp, OCp), "workspace too small");
     WgradGenParams p{};
     p.Wp = W + 2;
     NM_REQUIRE(p.Wp <= 60, "image too wide for one TMA box");
@@ -531,10 +532,10 @@ int nm_tc_conv3x3_wgrad_gen_bf16(const void* x_pad, const void* dy_pad, float* d
         p.n_stages = fit > 8 ? 8 : fit;
     }
     p.splits = g.splits;
-    p.c_chunks = (C + 31) / 32;                         // all-zero padded input-channel chunks are skipped
+    p.c_chunks = g.c_chunks;
     p.OCp = OCp; p.Cp = Cp;
     p.partial = static_cast<float*>(workspace);
-    const int items = (OCp / g.moc) * p.c_chunks;
+    const int items = g.items;
     CUtensorMap mdy, mx;
     int rc = make_map_2d(&mdy, dy_pad, (uint64_t)OCp, (uint64_t)p.rows_total, (uint64_t)OCp * 2, 64, G_M, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;

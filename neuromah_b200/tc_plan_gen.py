@@ -115,7 +115,7 @@ class TcStackPlan:
                 act = z((B, h + 2, w + 2, ocp), np.uint16)
                 dy = z((B, h + 2, w + 2, ocp), np.uint16)
                 entries.append(dict(layer=c, inp=cur, act=act, dy=dy, h=h, w=w, ocp=ocp, icp=icp))
-                ws = max(ws, lib.nm_tc_conv3x3_wgrad_gen_workspace(B, h, w, icp, ocp))
+                ws = max(ws, lib.nm_tc_conv3x3_wgrad_gen_workspace(B, h, w, c.weights.shape[1], icp, ocp))
                 cur = act
             last = bi == len(self.blocks) - 1
             ch = entries[-1]["ocp"]

@@ -158,7 +158,7 @@ def test_tc_gen_wgrad_and_bias_gradient(n, h, w, c, oc, integer):
     xp, dyp = DeviceArray.from_numpy(pad_nhwc(_pad_channels(x, cp))), DeviceArray.from_numpy(pad_nhwc(dy))
     dw = DeviceArray.from_numpy(np.full((oc, c, 3, 3), np.nan, np.float32))
     db = DeviceArray.from_numpy(np.full((oc,), np.nan, np.float32))
-    ws = DeviceArray((lib.nm_tc_conv3x3_wgrad_gen_workspace(n, h, w, cp, ocp),), np.uint8)
+    ws = DeviceArray((lib.nm_tc_conv3x3_wgrad_gen_workspace(n, h, w, c, cp, ocp),), np.uint8)
     lib.nm_tc_conv3x3_wgrad_gen_bf16(xp.p, dyp.p, dw.p, db.p, ws.p, ws.nbytes, n, h, w, c, oc, cp, ocp, stream())
     _, ref, refb = R.conv_layer_backward(x, wt, None, dy, padding="same", relu=False, mode="wired", dtype=np.float64)
     if integer:

@@ -1,8 +1,10 @@
 """GPU parity of the general bf16 tensor-core plan (neuromah_b200/tc_plan_gen.py) -- the VGG-style stack of
 BASELINE.json config 4 -- against the oracle's float64 step on identical inputs and state.
 
-Stated tolerance of the mode (bf16 operands and stored activations, FP32 accumulation), the same figures as the MNIST
-plan's tests (tests/test_gpu_tc_model.py): probabilities 2e-3 + 1e-2 |ref|, every gradient tensor <= 3e-2 relative L2.
+Stated tolerance of the mode (bf16 operands, bf16 stored activations AND bf16 stored activation gradients, FP32
+accumulation): probabilities 2e-3 + 1e-2 |ref|; gradient tensors <= 3e-2 relative L2 for the head and the two convs
+below it (the MNIST plan's figure, tests/test_gpu_tc_model.py), <= 6e-2 for deeper convs -- every layer the gradient
+crosses adds one bf16 rounding of dY and the ReLU-mask / arg-max flips of near-ties in the bf16 activations.
 The stack is narrowed / shortened so that the NumPy oracle finishes in seconds; the kernels take the same code paths
 as the full config (K loop over 64-channel chunks, N tiles of 64 and 128, padded first-layer channels)."""
 import numpy as np
@@ -73,10 +75,14 @@ def test_tc_stack_step_gradients_from_identical_state():
         loss_sum, _ = model._read_accum()
         assert abs(loss_sum - r["loss_sum"]) <= 2e-3 * 32
         g, gr = model.arena.host_grads(), net.flat("grads")
-        off = 0
-        for (_, name, _, size, _) in model.arena.table:
-            assert rel_l2(g[off:off + size], gr[off:off + size]) <= 3e-2, (s, name, off)
+        off, errs = 0, []
+        trainable = [l for l in model.layers if hasattr(l, "weights")]
+        for (layer, name, _, size, _) in model.arena.table:
+            depth = len(trainable) - 1 - [id(t) for t in trainable].index(id(layer))      # 0 = the Dense head
+            errs.append((depth, name, rel_l2(g[off:off + size], gr[off:off + size]), 3e-2 if depth <= 2 else 6e-2))
             off += size
+        print("step", s, " ".join(f"{d}:{n[0]}={e:.4f}" for d, n, e, _ in errs))
+        assert all(e <= tol for _, _, e, tol in errs), (s, errs)
     assert model.optimizer.iterations == 3
 
 
@@ -90,3 +96,29 @@ def test_tc_stack_bitwise_deterministic_and_graph_replay():
         m.train(x, y, epochs=3, batch_size=32, verbose=0)
         runs.append(m.arena.host_params().copy())
     np.testing.assert_array_equal(runs[0], runs[1])
+
+
+def test_tc_stack_loss_curve_follows_the_fp32_exact_mode():
+    """40 Adam steps on learnable synthetic data (a fixed random template per class + noise): the bf16 plan's loss curve
+    falls and stays within 5 % of the FP32-exact mode's (itself pinned to the oracle per step in tests/test_gpu_model.py)."""
+    spec = small_vgg_spec()
+    params = ref_net.init_params(spec, np.random.RandomState(11), init="he")
+    rng = np.random.default_rng(21)
+    lab = rng.integers(0, 10, 40 * 32)
+    templ = (np.random.default_rng(4321).random((10, 3, 16, 16), dtype=np.float32) > 0.7).astype(np.float32)
+    x = (0.6 * rng.random((len(lab), 3, 16, 16), dtype=np.float32) + 0.4 * templ[lab]).astype(np.float32)
+    y = np.eye(10)[lab]
+    curves = {}
+    for mode in (None, "bf16"):
+        model = build(spec, params, mode=mode, learning_rate=0.001)
+        losses = []
+        for s in range(40):
+            model._accum.fill_zero()
+            model.train_step(x[s * 32:(s + 1) * 32], y[s * 32:(s + 1) * 32])
+            losses.append(model._read_accum()[0] / 32)
+        curves[mode] = np.array(losses)
+    a, b = curves[None], curves["bf16"]
+    print("fp32 ", np.round(a[::5], 3), "\nbf16 ", np.round(b[::5], 3))
+    assert a[-8:].mean() < 0.95 * a[:4].mean() and b[-8:].mean() < 0.95 * b[:4].mean()     # both learn
+    assert abs(a[:5].mean() - b[:5].mean()) <= 0.02 * a[:5].mean()
+    assert abs(a[-8:].mean() - b[-8:].mean()) <= 0.05 * a[:4].mean()
