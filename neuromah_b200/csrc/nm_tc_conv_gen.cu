@@ -23,9 +23,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int G_M = 128;                 // rows of one MMA
-constexpr int G_MSUB = 2;                // MMAs (accumulators) per weight slice: every streamed weight byte feeds 256 pixels
-constexpr int G_TILE_ROWS = G_M * G_MSUB;
+constexpr int G_M = 128;                 // rows of one MMA; a CTA tile is MSUB of them (MSUB accumulators per weight slice)
 constexpr int G_KC = 64;                 // channels per K chunk = one 128-byte SWIZZLE_128B row
 constexpr int G_ROWB = 128;
 
@@ -36,22 +34,31 @@ struct ConvGenParams {
     int a_boxes, a_box_rows;             // an activation stage = a_boxes TMA boxes of a_box_rows (multiple of 8) rows
     uint32_t a_stage_bytes;
     int a_stages, b_stages;
+    int b_resident;                      // the whole filter bank (9 * k_chunks slices, one N tile) stays in shared memory
     __nv_bfloat16* out;                  // [rows_total][Cout], haloed grid
     const __nv_bfloat16* mask;           // optional [rows_total][Cout]: out = mask > 0 ? acc : 0   (ReLU' of the layer below)
     const float* bias;                   // optional [Cout]
     int relu;
 };
 
-// D[256 pixels, NT] = sum_{chunk, tap} A_chunk[pixel + shift(tap), 0:64] * B[tap][n0 : n0+NT, chunk]^T
-template <int NT>
+// D[MSUB*128 pixels, NT] = sum_{chunk, tap} A_chunk[pixel + shift(tap), 0:64] * B[tap][n0 : n0+NT, chunk]^T
+// Streaming the filter bank costs NT*128 bytes of L2 reads per 4*MSUB MMAs (measured: with MSUB = 2 the conv ran at half
+// its MMA schedule, L2-bound on the weight stream).  Two remedies, chosen on the host:
+//  * MSUB = 4 -- a weight byte feeds 512 pixels; the four accumulators fill TMEM (4 * 128 columns), so the accumulator is
+//    single-buffered and both epilogue groups drain each tile (two sub-tiles each);
+//  * b_resident -- when the whole bank of the CTA's (single) N tile fits next to the activation stages (Cin*Cout <= 64*64
+//    at 32x32), it is loaded once per CTA and never streamed again (MSUB = 2, double-buffered accumulators).
+template <int NT, int MSUB>
 __global__ void __launch_bounds__(384, 1)
 conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvGenParams p) {
     constexpr uint64_t TMPL = desc_template(16, 8 * G_ROWB, LAYOUT_SW128);     // K-major, SBO = 8 rows
     constexpr uint32_t IDESC = idesc_bf16(G_M, NT, 0, 0);
+    constexpr int TILE_ROWS = G_M * MSUB;
     constexpr int B_BYTES = NT * G_ROWB;                                      // one (tap, chunk) weight slice
-    constexpr int NACC = G_MSUB * NT;                                         // accumulator columns per buffer
-    constexpr uint32_t TMEM_COLS = 2 * NACC <= 256 ? 256 : 512;
-    static_assert(2 * NACC <= 512, "accumulators exceed TMEM");
+    constexpr int NACC = MSUB * NT;                                           // accumulator columns per buffer
+    constexpr int NBUF = 2 * NACC <= 512 ? 2 : 1;
+    constexpr uint32_t TMEM_COLS = NBUF * NACC <= 256 ? 256 : 512;
+    static_assert(NBUF * NACC <= 512 && MSUB % 2 == 0, "accumulators exceed TMEM");
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* a_smem = smem;
@@ -71,7 +78,7 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.a_stages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < p.b_stages; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], NBUF == 2 ? 4 : 8); }
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -85,9 +92,14 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // ============================== TMA producer ==============================
         if (lane == 0) {
             int a_stage = 0, b_stage = 0; uint32_t a_phase = 0, b_phase = 0;
+            if (p.b_resident && (int)blockIdx.x < p.num_tiles)
+                for (int j = 0; j < 9 * p.k_chunks; ++j) {                  // slice j = (chunk, tap), loaded once
+                    mbar_expect_tx(&bfull[j], B_BYTES);
+                    tma_load_2d(b_smem + (size_t)j * B_BYTES, &map_b, (j % 9) * p.Cin + (j / 9) * G_KC, 0, &bfull[j]);
+                }
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * NT;
-                const int row0 = m_tile * G_TILE_ROWS - (p.Wp + 1);                    // negative / past-the-end rows read as zero
+                const int row0 = m_tile * TILE_ROWS - (p.Wp + 1);                      // negative / past-the-end rows read as zero
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     mbar_wait(&aempty[a_stage], a_phase ^ 1);
                     mbar_expect_tx(&afull[a_stage], (uint32_t)(p.a_boxes * p.a_box_rows) * G_ROWB);
@@ -95,6 +107,7 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         tma_load_2d(a_smem + (size_t)a_stage * p.a_stage_bytes + (size_t)j * p.a_box_rows * G_ROWB, &map_a,
                                     kc * G_KC, row0 + j * p.a_box_rows, &afull[a_stage]);
                     if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
+                    if (p.b_resident) continue;
                     for (int tap = 0; tap < 9; ++tap) {
                         mbar_wait(&bempty[b_stage], b_phase ^ 1);
                         mbar_expect_tx(&bfull[b_stage], B_BYTES);
@@ -109,68 +122,90 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         int a_stage = 0, b_stage = 0; uint32_t a_phase = 0, b_phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+            const int acc = NBUF == 2 ? (it & 1) : 0;
+            const uint32_t use = NBUF == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;       // how often this buffer has been used
+            mbar_wait(&tempty[acc], (use & 1) ^ 1);
             fence_after_sync();
             const uint32_t d_addr = tmem_base + acc * NACC;
             for (int kc = 0; kc < p.k_chunks; ++kc) {
                 mbar_wait(&afull[a_stage], a_phase);
                 const uint64_t a_desc0 = desc_at(TMPL, smem_u32(a_smem + (size_t)a_stage * p.a_stage_bytes));
                 for (int tap = 0; tap < 9; ++tap) {
-                    mbar_wait(&bfull[b_stage], b_phase);
+                    const int bs = p.b_resident ? kc * 9 + tap : b_stage;
+                    mbar_wait(&bfull[bs], p.b_resident ? 0u : b_phase);            // resident: completes once, stays complete
                     fence_after_sync();
                     if (elect_one()) {
-                        const uint64_t b_desc0 = desc_at(TMPL, smem_u32(b_smem + (size_t)b_stage * B_BYTES));
+                        const uint64_t b_desc0 = desc_at(TMPL, smem_u32(b_smem + (size_t)bs * B_BYTES));
                         const uint32_t shift = (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * G_ROWB;
 #pragma unroll
                         for (int kk = 0; kk < G_KC / 16; ++kk)
 #pragma unroll
-                            for (int ms = 0; ms < G_MSUB; ++ms)
+                            for (int ms = 0; ms < MSUB; ++ms)
                                 mma_bf16(d_addr + ms * NT, a_desc0 + ((shift + ms * G_M * G_ROWB + kk * 32) >> 4),
                                          b_desc0 + ((kk * 32) >> 4), IDESC, (kc | tap | kk) != 0);
-                        mma_commit(&bempty[b_stage]);                               // weight slice reusable
+                        if (!p.b_resident) mma_commit(&bempty[b_stage]);            // weight slice reusable
                         if (tap == 8) {
                             mma_commit(&aempty[a_stage]);                           // activation tile reusable
                             if (kc == p.k_chunks - 1) mma_commit(&tfull[acc]);      // accumulators ready for the epilogue
                         }
                     }
                     __syncwarp();
-                    if (++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
+                    if (!p.b_resident && ++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
                 }
                 if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
-        // ============================== epilogue (two groups of 4 warps, alternating tiles) ==============================
+        // ============================== epilogue (two groups of 4 warps) ==============================
+        // NBUF == 2: group g drains accumulator buffer g, i.e. every second tile, all its sub-tiles.
+        // NBUF == 1: both groups drain every tile, MSUB / 2 sub-tiles each.
         const int q = warp & 3;                       // TMEM sub-partition = lanes [32q, 32q+32)
-        const int grp = (warp - 4) >> 2;              // group g drains accumulator buffer g
+        const int grp = (warp - 4) >> 2;
         const int plane = p.Hp * p.Wp;
-        int it = grp;
-        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
-            mbar_wait(&tfull[grp], (it >> 1) & 1);
+        constexpr int IT_STEP = NBUF == 2 ? 2 : 1;
+        const int acc = NBUF == 2 ? grp : 0;
+        const int ms_lo = NBUF == 2 ? 0 : grp * (MSUB / 2), ms_hi = NBUF == 2 ? MSUB : ms_lo + MSUB / 2;
+        int it = NBUF == 2 ? grp : 0;
+        for (int tile = blockIdx.x + it * gridDim.x; tile < p.num_tiles; tile += IT_STEP * gridDim.x, it += IT_STEP) {
+            const uint32_t use = NBUF == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
+            mbar_wait(&tfull[acc], use & 1);
             fence_after_sync();
             const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * NT;
 #pragma unroll 1
-            for (int ms = 0; ms < G_MSUB; ++ms) {
-                const long long row = (long long)m_tile * G_TILE_ROWS + ms * G_M + q * 32 + lane;
-                const int rem = (int)(row % plane), hh = rem / p.Wp, ww = rem - hh * p.Wp;
+            for (int ms = ms_lo; ms < ms_hi; ++ms) {
+                const int row = m_tile * TILE_ROWS + ms * G_M + q * 32 + lane;        // rows_total < 2^31 (checked on the host)
+                const int rem = row % plane, hh = rem / p.Wp, ww = rem - hh * p.Wp;
                 const bool in_range = row < p.rows_total;
                 const bool interior = in_range && hh >= 1 && hh <= p.H && ww >= 1 && ww <= p.W;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * NACC + ms * NT;
-                __nv_bfloat16* dst = p.out + row * p.Cout + n0;
-                const __nv_bfloat16* msk = p.mask ? p.mask + row * p.Cout + n0 : nullptr;
-#pragma unroll 1
-                for (int c0 = 0; c0 < NT; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld_x16(taddr + c0, v);
-                    tmem_ld_x16(taddr + c0 + 16, v + 16);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NACC + ms * NT;
+                __nv_bfloat16* dst = p.out + (size_t)row * p.Cout + n0;
+                const bool use_mask = p.mask != nullptr && interior;
+                const __nv_bfloat16* msk = p.mask + (size_t)row * p.Cout + n0;
+                // Software pipeline over 32-column chunks: the TMEM load of chunk i+1 and the mask read of chunk i are in
+                // flight while chunk i is converted and stored (measured: with one load -> wait -> store chain per chunk the
+                // epilogue, not the MMAs, set the tile period).
+                uint32_t v[2][32];
+                tmem_ld_x16(taddr, v[0]);
+                tmem_ld_x16(taddr + 16, v[0] + 16);
+#pragma unroll
+                for (int ci = 0; ci < NT / 32; ++ci) {
+                    const int c0 = ci * 32;
+                    uint4 mk[4];
+                    if (use_mask) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) mk[g] = __ldg(reinterpret_cast<const uint4*>(msk + c0 + g * 8));
+                    }
                     tmem_ld_wait();
+                    if (ci + 1 < NT / 32) {
+                        tmem_ld_x16(taddr + c0 + 32, v[(ci + 1) & 1]);
+                        tmem_ld_x16(taddr + c0 + 48, v[(ci + 1) & 1] + 16);
+                    }
                     if (in_range) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             float f[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] = interior ? __uint_as_float(v[g * 8 + j]) : 0.f;
+                            for (int j = 0; j < 8; ++j) f[j] = interior ? __uint_as_float(v[ci & 1][g * 8 + j]) : 0.f;
                             if (interior) {
                                 if (p.bias) {
                                     const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + g * 8));
@@ -182,9 +217,8 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
                                 }
-                                if (msk) {
-                                    const uint4 m = __ldg(reinterpret_cast<const uint4*>(msk + c0 + g * 8));
-                                    const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+                                if (use_mask) {
+                                    const uint32_t mw[4] = {mk[g].x, mk[g].y, mk[g].z, mk[g].w};
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) {
                                         const uint32_t h = (mw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;   // bf16 > 0: sign clear, not zero
@@ -202,7 +236,7 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
             fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[grp]);        // accumulator buffer drained: the MMA warp may overwrite it
+            if (lane == 0) mbar_arrive(&tempty[acc]);        // accumulator buffer drained: the MMA warp may overwrite it
         }
     }
     fence_before_sync();
@@ -223,7 +257,7 @@ struct WgradGenParams {
     int x_rows;                          // 128 + 2*Wp + 2
     uint32_t x_stage_bytes;              // rounded to 1024
     int n_stages;
-    int splits, c_chunks;                // gridDim.x = splits, gridDim.y = (OCp / MOC) * c_chunks
+    int splits, c_chunks;                // gridDim.x = (OCp / MOC) * c_chunks, gridDim.y = splits
     int OCp, Cp;
     float* partial;                      // [splits][OCp][9][Cp]
 };
@@ -250,7 +284,9 @@ conv3x3_wgrad_gen_kernel(const __grid_constant__ CUtensorMap map_dy, const __gri
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int split = blockIdx.x, item = blockIdx.y;
+    // item is the fastest grid index: the CTAs that are resident together walk the SAME pixel blocks (one dY / X slice
+    // each), so a block of dY and X crosses HBM once and is served to the other items from L2
+    const int item = blockIdx.x, split = blockIdx.y;
     const int oc0 = (item / p.c_chunks) * MOC, c0 = (item % p.c_chunks) * CB;
     pdl_trigger();
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_dy); tma_prefetch_desc(&map_x); }
@@ -280,17 +316,23 @@ conv3x3_wgrad_gen_kernel(const __grid_constant__ CUtensorMap map_dy, const __gri
             }
         }
     } else if (warp == 1) {
+        // One elected lane issues everything.  UTCHMMA issue is back-pressured by the tensor pipe, so the wait for the NEXT
+        // k-block's data is done before the last MMAs of the current one are issued: it hides under queued MMAs.
         if (elect_one()) {
             int it = 0;
+            if (split < p.num_kblocks) mbar_wait(&full[0], 0);
             for (int kb = split; kb < p.num_kblocks; kb += p.splits, ++it) {
                 const int stage = it % p.n_stages;
-                mbar_wait(&full[stage], (it / p.n_stages) & 1);
                 fence_after_sync();
                 const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint64_t a_desc0 = desc_at(TMPL_A, st);
                 const uint64_t x_desc0 = desc_at(TMPL_B3, st + A_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < G_M / 16; ++ks) {
+                    if (ks == G_M / 16 - 1 && kb + p.splits < p.num_kblocks) {
+                        const int nit = it + 1;
+                        mbar_wait(&full[nit % p.n_stages], (nit / p.n_stages) & 1);
+                    }
                     const uint64_t adesc = a_desc0 + ((ks * 16 * 128) >> 4);
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
@@ -330,18 +372,31 @@ conv3x3_wgrad_gen_kernel(const __grid_constant__ CUtensorMap map_dy, const __gri
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// partial [splits][OCp][9][Cp] -> OIHW [OC][C][3][3], splits summed in a fixed order
-__global__ void wgrad_gen_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits,
-                                        int OC, int C, int OCp, int Cp) {
+// partial [splits][OCp][9][Cp] -> OIHW [OC][C][3][3].  Block = 64 outputs x 8 slices: slice j sums splits j, j+8, ... in
+// order, the eight slice sums are then added in order -- a fixed summation tree, so the result is bitwise repeatable.
+constexpr int GR_SLICES = 8;
+__global__ void __launch_bounds__(64 * GR_SLICES)
+wgrad_gen_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int OC, int C, int OCp, int Cp) {
+    __shared__ float red[GR_SLICES][64];
     pdl_trigger();
     pdl_wait();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // i = (oc * 9 + tap) * C + c : coalesced reads
-    if (i >= OC * C * 9) return;
-    const int oc = i / (9 * C), rem = i - oc * 9 * C, tap = rem / C, c = rem - tap * C;
-    const size_t src = ((size_t)oc * 9 + tap) * Cp + c, plane = (size_t)OCp * 9 * Cp;
+    const int slice = threadIdx.x >> 6, slices = blockDim.x >> 6;
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);         // i = (oc * 9 + tap) * C + c : coalesced reads
+    const bool ok = i < OC * C * 9;
+    int oc = 0, tap = 0, c = 0;
     float a = 0.f;
-    for (int s = 0; s < splits; ++s) a += __ldg(partial + s * plane + src);
-    dw[((size_t)oc * C + c) * 9 + tap] = a;
+    if (ok) {
+        oc = i / (9 * C); const int rem = i - oc * 9 * C; tap = rem / C; c = rem - tap * C;
+        const size_t src = ((size_t)oc * 9 + tap) * Cp + c, plane = (size_t)OCp * 9 * Cp;
+        for (int s = slice; s < splits; s += slices) a += __ldg(partial + s * plane + src);
+    }
+    red[slice][threadIdx.x & 63] = a;
+    __syncthreads();
+    if (slice == 0 && ok) {
+        float t = 0.f;
+        for (int k = 0; k < slices; ++k) t += red[k][threadIdx.x];
+        dw[((size_t)oc * C + c) * 9 + tap] = t;
+    }
 }
 
 // bias gradient: db[oc] = sum over every row of the haloed bf16 gradient [rows][OCp] (halo rows are zero).
@@ -371,11 +426,13 @@ dbias_partial_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ p
 __global__ void dbias_final_kernel(const float* __restrict__ partial, float* __restrict__ db, int blocks, int OC, int OCp) {
     pdl_trigger();
     pdl_wait();
-    const int oc = blockIdx.x * blockDim.x + threadIdx.x;
+    const int oc = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;      // one warp per channel
     if (oc >= OC) return;
     float a = 0.f;
-    for (int b = 0; b < blocks; ++b) a += partial[(size_t)b * OCp + oc];
-    db[oc] = a;
+    for (int b = lane; b < blocks; b += 32) a += partial[(size_t)b * OCp + oc];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);                   // fixed tree: deterministic
+    if (lane == 0) db[oc] = a;
 }
 
 // OIHW f32 [OC][C][3][3] -> bf16 [OCp][tap][Cp] (fprop B operand) and [Cp][8 - tap][OCp] (dgrad B operand), zero-padded channels
@@ -391,35 +448,50 @@ __global__ void pack_conv_weights_gen_kernel(const float* __restrict__ w, __nv_b
     if (wd) wd[((size_t)c * 9 + (8 - tap)) * OCp + oc] = v;
 }
 
-// f32 NCHW [N][C][H][W] -> zero-haloed bf16 NHWC [N][H+2][W+2][Cp]; every element of the destination is written
+// f32 NCHW [N][C][H][W] -> zero-haloed bf16 NHWC [N][H+2][W+2][Cp]; every element of the destination is written.
+// One thread per grid pixel: reads are coalesced along w, and a thread writes its pixel's own Cp*2 contiguous bytes.
 __global__ void pack_input_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp,
                                        int N, int C, int H, int W, int Cp) {
     pdl_trigger();
     pdl_wait();
     const int groups = Cp / 8, Hp = H + 2, Wp = W + 2;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)N * Hp * Wp * groups) return;
-    const int g = (int)(i % groups);
-    long long pix = i / groups;
-    const int ww = (int)(pix % Wp); pix /= Wp;
-    const int hh = (int)(pix % Hp);
-    const int n = (int)(pix / Hp);
-    float f[8];
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (long long)N * Hp * Wp) return;
+    const int ww = (int)(pix % Wp);
+    const int hh = (int)((pix / Wp) % Hp);
+    const int n = (int)(pix / ((long long)Wp * Hp));
+    const bool interior = hh >= 1 && hh <= H && ww >= 1 && ww <= W;
+    const float* src = x + ((size_t)n * C * H + (hh - 1)) * W + (ww - 1);
+    uint4* dst = reinterpret_cast<uint4*>(xp) + pix * groups;
+    for (int g = 0; g < groups; ++g) {
+        float f[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = g * 8 + j;
-        f[j] = (c < C && hh >= 1 && hh <= H && ww >= 1 && ww <= W)
-                   ? __ldg(x + (((size_t)n * C + c) * H + (hh - 1)) * W + (ww - 1)) : 0.f;
+        for (int j = 0; j < 8; ++j) {
+            const int c = g * 8 + j;
+            f[j] = (interior && c < C) ? __ldg(src + (size_t)c * H * W) : 0.f;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+        dst[g] = o;
     }
-    uint4 o;
-    o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-    reinterpret_cast<uint4*>(xp)[i] = o;
 }
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-template <int NT>
+constexpr int G_SMEM_BUDGET = 212 * 1024;
+
+// activation stage geometry for a tile of msub * 128 pixels
+void conv_gen_tile(ConvGenParams& p, int msub) {
+    const int tile_rows = G_M * msub, a_rows = tile_rows + 2 * p.Wp + 2;
+    p.num_tiles = ((p.rows_total + tile_rows - 1) / tile_rows) * p.n_tiles;
+    p.a_boxes = (a_rows + 255) / 256;
+    p.a_box_rows = round_up((a_rows + p.a_boxes - 1) / p.a_boxes, 8);
+    p.a_stage_bytes = (uint32_t)(p.a_boxes * p.a_box_rows) * G_ROWB;
+}
+
+template <int NT, int MSUB>
 int launch_conv_gen(const void* x_pad, const void* w_packed, ConvGenParams p, cudaStream_t st) {
+    NM_REQUIRE(p.a_box_rows <= 256, "image too wide");
     CUtensorMap ma, mb;
     int rc = make_map_2d(&ma, x_pad, (uint64_t)p.Cin, (uint64_t)p.rows_total, (uint64_t)p.Cin * 2, G_KC, (uint32_t)p.a_box_rows,
                          CU_TENSOR_MAP_SWIZZLE_128B);
@@ -427,12 +499,19 @@ int launch_conv_gen(const void* x_pad, const void* w_packed, ConvGenParams p, cu
     rc = make_map_2d(&mb, w_packed, (uint64_t)9 * p.Cin, (uint64_t)p.Cout, (uint64_t)9 * p.Cin * 2, G_KC, NT, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     constexpr int B_BYTES = NT * G_ROWB;
-    p.a_stages = 2;
-    const int budget = 212 * 1024 - p.a_stages * (int)p.a_stage_bytes;
-    p.b_stages = budget / B_BYTES > 9 ? 9 : budget / B_BYTES;
-    NM_REQUIRE(p.b_stages >= 2, "image too wide for the shared-memory budget");
+    if (p.b_resident) {
+        p.b_stages = 9 * p.k_chunks;
+        p.a_stages = (G_SMEM_BUDGET - p.b_stages * B_BYTES) / (int)p.a_stage_bytes;
+        if (p.a_stages > 4) p.a_stages = 4;
+    } else {
+        p.a_stages = 2;
+        const int budget = G_SMEM_BUDGET - p.a_stages * (int)p.a_stage_bytes;
+        p.b_stages = budget / B_BYTES > 9 ? 9 : budget / B_BYTES;
+    }
+    NM_REQUIRE(p.a_stages >= 2 && p.b_stages >= 2, "image too wide for the shared-memory budget");
+    NM_REQUIRE(2 * (p.a_stages + p.b_stages) + 4 <= 62, "too many pipeline stages for the barrier block");
     const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * B_BYTES + 512;   // + mbarriers
-    auto kern = conv3x3_gen_kernel<NT>;
+    auto kern = conv3x3_gen_kernel<NT, MSUB>;
     static bool attr_set = false;
     if (!attr_set) {
         NM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -474,8 +553,8 @@ int nm_tc_pack_conv_weights_gen_bf16(const float* w_oihw, void* w_fprop, void* w
 int nm_tc_pack_input_nhwc_bf16(const float* x_nchw, void* x_pad, int N, int C, int H, int W, int Cp, void* stream) {
     NM_REQUIRE(x_nchw && x_pad, "null pointer");
     NM_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && Cp >= C && Cp % 8 == 0, "bad dimensions");
-    const long long total = (long long)N * (H + 2) * (W + 2) * (Cp / 8);
-    return nm::launch_pdl("pack_input_nhwc", pack_input_nhwc_kernel, dim3(nm_cdiv((size_t)total, 256)), dim3(256), 0, nm::S(stream),
+    const long long total = (long long)N * (H + 2) * (W + 2);
+    return nm::launch_pdl("pack_input_nhwc", pack_input_nhwc_kernel, dim3(nm_cdiv((size_t)total, 128)), dim3(128), 0, nm::S(stream),
                           x_nchw, static_cast<__nv_bfloat16*>(x_pad), N, C, H, W, Cp);
 }
 
@@ -492,17 +571,21 @@ int nm_tc_conv3x3_gen_bf16(const void* x_pad, const void* w_packed, const float*
     p.k_chunks = Cin / G_KC;
     const int nt = Cout % 128 == 0 ? 128 : 64;
     p.n_tiles = Cout / nt;
-    p.num_tiles = ((p.rows_total + G_TILE_ROWS - 1) / G_TILE_ROWS) * p.n_tiles;
-    const int a_rows = G_TILE_ROWS + 2 * p.Wp + 2;
-    p.a_boxes = (a_rows + 255) / 256;
-    p.a_box_rows = round_up((a_rows + p.a_boxes - 1) / p.a_boxes, 8);
-    NM_REQUIRE(p.a_box_rows <= 256, "image too wide");
-    p.a_stage_bytes = (uint32_t)(p.a_boxes * p.a_box_rows) * G_ROWB;
     p.out = static_cast<__nv_bfloat16*>(y_pad);
     p.mask = static_cast<const __nv_bfloat16*>(relu_mask);
     p.bias = bias;
     p.relu = relu;
-    return nt == 128 ? launch_conv_gen<128>(x_pad, w_packed, p, nm::S(stream)) : launch_conv_gen<64>(x_pad, w_packed, p, nm::S(stream));
+    // Measured on B200 (profiles/r01f_vgg_launches_b1024_v1.csv vs _v2.csv): the streamed MSUB = 2 form is the fastest -- the
+    // single-buffered accumulator of MSUB = 4 exposes the epilogue, and the resident bank is 8-15 % slower than streaming
+    // it from L2.  NM_TC_GEN_MODE=2 selects MSUB = 4, =3 the resident bank where it fits (experiments only).
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("NM_TC_GEN_MODE"); mode = e ? atoi(e) : 1; }
+    conv_gen_tile(p, 2);
+    p.b_resident = mode == 3 && p.n_tiles == 1 && 9 * p.k_chunks * nt * G_ROWB + 2 * (int)p.a_stage_bytes <= G_SMEM_BUDGET;
+    if (mode != 2 || p.b_resident)
+        return nt == 128 ? launch_conv_gen<128, 2>(x_pad, w_packed, p, nm::S(stream)) : launch_conv_gen<64, 2>(x_pad, w_packed, p, nm::S(stream));
+    conv_gen_tile(p, 4);
+    return nt == 128 ? launch_conv_gen<128, 4>(x_pad, w_packed, p, nm::S(stream)) : launch_conv_gen<64, 4>(x_pad, w_packed, p, nm::S(stream));
 }
 
 size_t nm_tc_conv3x3_wgrad_gen_workspace(int N, int H, int W, int C, int Cp, int OCp) {
@@ -549,10 +632,11 @@ int nm_tc_conv3x3_wgrad_gen_bf16(const void* x_pad, const void* dy_pad, float* d
         attr_set = true;
     }
     rc = g.moc == 128
-             ? nm::launch_pdl("conv3x3_wgrad_gen", conv3x3_wgrad_gen_kernel<128>, dim3(p.splits, items), dim3(256), smem, nm::S(stream), mdy, mx, p)
-             : nm::launch_pdl("conv3x3_wgrad_gen", conv3x3_wgrad_gen_kernel<64>, dim3(p.splits, items), dim3(256), smem, nm::S(stream), mdy, mx, p);
+             ? nm::launch_pdl("conv3x3_wgrad_gen", conv3x3_wgrad_gen_kernel<128>, dim3(items, p.splits), dim3(256), smem, nm::S(stream), mdy, mx, p)
+             : nm::launch_pdl("conv3x3_wgrad_gen", conv3x3_wgrad_gen_kernel<64>, dim3(items, p.splits), dim3(256), smem, nm::S(stream), mdy, mx, p);
     if (rc) return rc;
-    rc = nm::launch_pdl("wgrad_gen_reduce", wgrad_gen_reduce_kernel, dim3(nm_cdiv((size_t)OC * C * 9, 256)), dim3(256), 0, nm::S(stream),
+    rc = nm::launch_pdl("wgrad_gen_reduce", wgrad_gen_reduce_kernel, dim3(nm_cdiv((size_t)OC * C * 9, 64)),
+                        dim3(64 * (p.splits >= 64 ? GR_SLICES : p.splits >= 16 ? 2 : 1)), 0, nm::S(stream),
                         (const float*)p.partial, dw, p.splits, OC, C, OCp, Cp);
     if (rc || !dbias) return rc;
     float* dbp = p.partial + (size_t)g.splits * OCp * 9 * Cp;
@@ -563,7 +647,7 @@ int nm_tc_conv3x3_wgrad_gen_bf16(const void* x_pad, const void* dy_pad, float* d
     rc = nm::launch_pdl("dbias_partial", dbias_partial_kernel, dim3(blocks), dim3(1024), 0, nm::S(stream),
                         static_cast<const __nv_bfloat16*>(dy_pad), dbp, p.rows_total, OCp);
     if (rc) return rc;
-    return nm::launch_pdl("dbias_final", dbias_final_kernel, dim3(nm_cdiv(OC, 128)), dim3(128), 0, nm::S(stream),
+    return nm::launch_pdl("dbias_final", dbias_final_kernel, dim3(nm_cdiv((size_t)OC * 32, 256)), dim3(256), 0, nm::S(stream),
                           (const float*)dbp, dbias, blocks, OC, OCp);
 }
 
