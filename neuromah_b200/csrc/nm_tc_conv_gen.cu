@@ -118,43 +118,60 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ============================== MMA issuer (converged warp, one elected lane) ==============================
-        int a_stage = 0, b_stage = 0; uint32_t a_phase = 0, b_phase = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const int acc = NBUF == 2 ? (it & 1) : 0;
-            const uint32_t use = NBUF == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;       // how often this buffer has been used
-            mbar_wait(&tempty[acc], (use & 1) ^ 1);
-            fence_after_sync();
-            const uint32_t d_addr = tmem_base + acc * NACC;
-            for (int kc = 0; kc < p.k_chunks; ++kc) {
-                mbar_wait(&afull[a_stage], a_phase);
-                const uint64_t a_desc0 = desc_at(TMPL, smem_u32(a_smem + (size_t)a_stage * p.a_stage_bytes));
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int bs = p.b_resident ? kc * 9 + tap : b_stage;
-                    mbar_wait(&bfull[bs], p.b_resident ? 0u : b_phase);            // resident: completes once, stays complete
-                    fence_after_sync();
-                    if (elect_one()) {
+        // ============================== MMA issuer (one elected lane runs the whole loop) ==============================
+        // ncu (profiles/r01f_ncu_conv_gen_c4_fprop.txt): with one barrier wait -> issue -> commit round per weight slice the
+        // tensor pipe idled ~350 cycles per slice (58 % active) -- UTCHMMA issue is back-pressured, so when the issuer
+        // returns from the last MMA of a slice only one or two MMAs are still queued, fewer than the wait + descriptor set-up
+        // of the next slice takes.  The wait for the NEXT slice is therefore done before the last two MMAs of the current
+        // one are issued, where it hides under six queued MMAs.
+        if (elect_one()) {
+            const int my_tiles = (int)blockIdx.x < p.num_tiles ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+            const int total_b = my_tiles * p.k_chunks * 9;                  // weight slices this CTA consumes
+            int a_stage = 0, b_stage = 0; uint32_t a_phase = 0, b_phase = 0;
+            int b_done = 0;
+            bool b_ready = false;                                            // bfull of the current slice already waited for
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int acc = NBUF == 2 ? (it & 1) : 0;
+                const uint32_t use = NBUF == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;   // how often this buffer has been used
+                mbar_wait(&tempty[acc], (use & 1) ^ 1);
+                fence_after_sync();
+                const uint32_t d_addr = tmem_base + acc * NACC;
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    mbar_wait(&afull[a_stage], a_phase);
+                    const uint64_t a_desc0 = desc_at(TMPL, smem_u32(a_smem + (size_t)a_stage * p.a_stage_bytes));
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int bs = p.b_resident ? kc * 9 + tap : b_stage;
+                        if (!b_ready) mbar_wait(&bfull[bs], p.b_resident ? 0u : b_phase);   // resident: completes once, stays complete
+                        b_ready = false;
+                        fence_after_sync();
                         const uint64_t b_desc0 = desc_at(TMPL, smem_u32(b_smem + (size_t)bs * B_BYTES));
                         const uint32_t shift = (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * G_ROWB;
 #pragma unroll
                         for (int kk = 0; kk < G_KC / 16; ++kk)
 #pragma unroll
-                            for (int ms = 0; ms < MSUB; ++ms)
+                            for (int ms = 0; ms < MSUB; ++ms) {
+                                if (kk * MSUB + ms == (G_KC / 16) * MSUB - 2 && !p.b_resident && b_done + 1 < total_b) {
+                                    const int nb = b_stage + 1 == p.b_stages ? 0 : b_stage + 1;
+                                    mbar_wait(&bfull[nb], nb == 0 ? b_phase ^ 1 : b_phase);
+                                    b_ready = true;
+                                }
                                 mma_bf16(d_addr + ms * NT, a_desc0 + ((shift + ms * G_M * G_ROWB + kk * 32) >> 4),
                                          b_desc0 + ((kk * 32) >> 4), IDESC, (kc | tap | kk) != 0);
+                            }
                         if (!p.b_resident) mma_commit(&bempty[b_stage]);            // weight slice reusable
                         if (tap == 8) {
                             mma_commit(&aempty[a_stage]);                           // activation tile reusable
                             if (kc == p.k_chunks - 1) mma_commit(&tfull[acc]);      // accumulators ready for the epilogue
                         }
+                        ++b_done;
+                        if (!p.b_resident && ++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
                     }
-                    __syncwarp();
-                    if (!p.b_resident && ++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
+                    if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
                 }
-                if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
             }
         }
+        __syncwarp();
     } else if (warp >= 4) {
         // ============================== epilogue (two groups of 4 warps) ==============================
         // NBUF == 2: group g drains accumulator buffer g, i.e. every second tile, all its sub-tiles.
