@@ -405,7 +405,8 @@ wgrad_gen_reduce_kernel(const float* __restrict__ partial, float* __restrict__ d
     if (ok) {
         oc = i / (9 * C); const int rem = i - oc * 9 * C; tap = rem / C; c = rem - tap * C;
         const size_t src = ((size_t)oc * 9 + tap) * Cp + c, plane = (size_t)OCp * 9 * Cp;
-        for (int s = slice; s < splits; s += slices) a += __ldg(partial + s * plane + src);
+#pragma unroll 4
+        for (int s = slice; s < splits; s += slices) a += __ldg(partial + s * plane + src);        // unrolled: loads in flight together
     }
     red[slice][threadIdx.x & 63] = a;
     __syncthreads();

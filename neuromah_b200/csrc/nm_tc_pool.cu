@@ -24,13 +24,13 @@ __global__ void maxpool2x2_fwd_kernel(const uint4* __restrict__ x, uint4* __rest
     pdl_wait();
     const int G = C / 8, PH = H / 2, PW = W / 2, Wp = W + 2;
     const int OH = out_padded ? PH + 2 : PH, OW = out_padded ? PW + 2 : PW;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)N * OH * OW * G) return;
-    const int g = (int)(i % G);
-    long long pix = i / G;
-    const int ow = (int)(pix % OW); pix /= OW;
-    const int oh = (int)(pix % OH);
-    const int n = (int)(pix / OH);
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;           // element count < 2^31 (checked on the host): 32-bit index math
+    if (i >= (unsigned)N * OH * OW * G) return;
+    const int g = (int)(i % (unsigned)G);
+    unsigned pix = i / (unsigned)G;
+    const int ow = (int)(pix % (unsigned)OW); pix /= (unsigned)OW;
+    const int oh = (int)(pix % (unsigned)OH);
+    const int n = (int)(pix / (unsigned)OH);
     const int ph = out_padded ? oh - 1 : oh, pw = out_padded ? ow - 1 : ow;
     if (ph < 0 || ph >= PH || pw < 0 || pw >= PW) { y[i] = make_uint4(0u, 0u, 0u, 0u); return; }     // halo of the output
     const size_t base = (((size_t)n * (H + 2) + 2 * ph + 1) * Wp + 2 * pw + 1) * G + g;
@@ -63,13 +63,13 @@ __global__ void maxpool2x2_bwd_kernel(const uint4* __restrict__ dpool, const uin
     pdl_trigger();
     pdl_wait();
     const int G = C / 8, PH = H / 2, PW = W / 2, Hp = H + 2, Wp = W + 2;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)N * Hp * Wp * G) return;
-    const int g = (int)(i % G);
-    long long pix = i / G;
-    const int ww = (int)(pix % Wp); pix /= Wp;
-    const int hh = (int)(pix % Hp);
-    const int n = (int)(pix / Hp);
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;           // element count < 2^31 (checked on the host): 32-bit index math
+    if (i >= (unsigned)N * Hp * Wp * G) return;
+    const int g = (int)(i % (unsigned)G);
+    unsigned pix = i / (unsigned)G;
+    const int ww = (int)(pix % (unsigned)Wp); pix /= (unsigned)Wp;
+    const int hh = (int)(pix % (unsigned)Hp);
+    const int n = (int)(pix / (unsigned)Hp);
     if (hh < 1 || hh > H || ww < 1 || ww > W) { dy[i] = make_uint4(0u, 0u, 0u, 0u); return; }
     const int ph = (hh - 1) >> 1, pw = (ww - 1) >> 1;
     const uint32_t me = (uint32_t)(((hh - 1) & 1) * 2 + ((ww - 1) & 1)) | 4u;        // nibble that selects this element
@@ -94,9 +94,9 @@ __global__ void dense_dgrad_bf16_kernel(const float* __restrict__ dlogits, const
     pdl_trigger();
     pdl_wait();
     const int G = K / 8;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)B * G) return;
-    const int b = (int)(i / G), g = (int)(i - (long long)b * G);
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;           // B * K / 8 < 2^31 (checked on the host)
+    if (i >= (unsigned)B * G) return;
+    const int b = (int)(i / (unsigned)G), g = (int)(i - (unsigned)b * G);
     float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int j = 0; j < n_out; ++j) {
         const float d = __ldg(dlogits + (size_t)b * n_out + j);
@@ -122,6 +122,7 @@ int nm_tc_maxpool2x2_fwd_bf16(const void* x_pad, void* y, void* idx, int N, int 
     NM_REQUIRE(x_pad && y && idx, "null pointer");
     NM_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0, "bad dimensions (even H, W; C % 8 == 0)");
     const long long total = (long long)N * (H / 2 + (out_padded ? 2 : 0)) * (W / 2 + (out_padded ? 2 : 0)) * (C / 8);
+    NM_REQUIRE(total < (1ll << 31) - 1024, "tensor too large for 32-bit element indices");
     return nm::launch_pdl("maxpool2x2_fwd", maxpool2x2_fwd_kernel, dim3(nm_cdiv((size_t)total, 256)), dim3(256), 0, nm::S(stream),
                           static_cast<const uint4*>(x_pad), static_cast<uint4*>(y), static_cast<uint32_t*>(idx), N, H, W, C, out_padded);
 }
@@ -130,6 +131,7 @@ int nm_tc_maxpool2x2_bwd_bf16(const void* dpool, const void* idx, void* dy_pad, 
     NM_REQUIRE(dpool && idx && dy_pad, "null pointer");
     NM_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0, "bad dimensions (even H, W; C % 8 == 0)");
     const long long total = (long long)N * (H + 2) * (W + 2) * (C / 8);
+    NM_REQUIRE(total < (1ll << 31) - 1024, "tensor too large for 32-bit element indices");
     return nm::launch_pdl("maxpool2x2_bwd", maxpool2x2_bwd_kernel, dim3(nm_cdiv((size_t)total, 256)), dim3(256), 0, nm::S(stream),
                           static_cast<const uint4*>(dpool), static_cast<const uint32_t*>(idx), static_cast<uint4*>(dy_pad), N, H, W, C,
                           in_padded);
@@ -139,6 +141,7 @@ int nm_tc_dense_dgrad_bf16(const float* dlogits, const float* w_packed, void* dx
     NM_REQUIRE(dlogits && w_packed && dx, "null pointer");
     NM_REQUIRE(B > 0 && K > 0 && K % 8 == 0 && n_out > 0 && n_out <= kNO, "bad dimensions");
     const long long total = (long long)B * (K / 8);
+    NM_REQUIRE(total < (1ll << 31) - 1024, "tensor too large for 32-bit element indices");
     return nm::launch_pdl("dense_dgrad_bf16", dense_dgrad_bf16_kernel, dim3(nm_cdiv((size_t)total, 256)), dim3(256), 0, nm::S(stream),
                           dlogits, w_packed, static_cast<uint4*>(dx), B, K, n_out);
 }
