@@ -147,7 +147,9 @@ class Model:
         A graph is captured per (input pointer, label pointer, batch) the second time that triple is seen -- the
         streamed feeder alternates between two device slots, so two graphs serve a whole epoch."""
         opt = self.optimizer
-        key = (x.ptr, labels.ptr, x.shape[0], self.softmax_classifier_output.grad_batch)
+        # plan.generation changes whenever the plan re-allocates its buffers (a larger batch): graphs captured before
+        # that hold the old device pointers and must never be replayed
+        key = (x.ptr, labels.ptr, x.shape[0], self.softmax_classifier_output.grad_batch, getattr(self.plan, "generation", 0))
         graphs = self.__dict__.setdefault("_graphs", {})
         seen = self.__dict__.setdefault("_graph_seen", set())
         g = graphs.get(key)

@@ -106,6 +106,8 @@ class TcCnnPlan:
             return
         if (H, W) != (28, 28):
             raise ValueError("mode='bf16' is instantiated for 28x28 inputs")
+        # a RE-allocation (larger batch / other input size) makes every captured CUDA graph stale: Model keys its graphs by this
+        self.generation = getattr(self, "generation", 0) + (1 if self.B else 0)
         self.hw, self.B = (H, W), B
         K = 7 * 7 * 64
         if self.de.weights.shape[0] != K:

@@ -100,6 +100,8 @@ class TcStackPlan:
             return
         if C != self.convs[0].weights.shape[1]:
             raise RuntimeError(f"Input has {C} channels, the first Conv2D expects {self.convs[0].weights.shape[1]}")
+        # a RE-allocation (larger batch / other input size) makes every captured CUDA graph stale: Model keys its graphs by this
+        self.generation = getattr(self, "generation", 0) + (1 if self.B else 0)
         self.hw, self.B = (C, H, W), B
         z = DeviceArray.zeros
         self.x_pad = z((B, H + 2, W + 2, _rup(C)), np.uint16)
