@@ -164,6 +164,41 @@ def cnn_small():
     np.savez_compressed(os.path.join(HERE, "cnn_small_3steps.npz"), **out)
 
 
+def vgg_small_spec():
+    """BASELINE.json config 4's stack narrowed 8x so the fixture stays small:
+    C(3->8) C(8->8) P C(8->16) C(16->16) P Flatten Dense(1024->10) Softmax on 32x32x3 inputs."""
+    spec, ic = [], 3
+    for oc in (8, 16):
+        spec += [{"kind": "conv", "ic": ic, "oc": oc, "k": 3, "padding": "same", "relu": True},
+                 {"kind": "conv", "ic": oc, "oc": oc, "k": 3, "padding": "same", "relu": True},
+                 {"kind": "pool", "size": 2, "stride": 2, "padding": "valid"}]
+        ic = oc
+    return spec + [{"kind": "flatten"}, {"kind": "dense", "n_in": 16 * 8 * 8, "n_out": 10, "relu": False}, {"kind": "softmax"}]
+
+
+def vgg_small():
+    """The VGG-style stack through the unmodified reference Python (He-initialised parameters handed in), batch 6,
+    2 Adam steps, wired conv backward: conv -> conv chains (ReLU backward between two convs, dgrad of a non-first conv
+    feeding a conv) that the MNIST CNN never exercises."""
+    spec = vgg_small_spec()
+    params = ref_net.init_params(spec, np.random.RandomState(31), init="he")
+    model = ref_shim.build_model(spec, params, optimizer="adam", lr=0.001, conv_backward="wired")
+    x, y = data(32, 6 * 2, (3, 32, 32))
+    out = {}
+    for s in range(2):
+        r = ref_shim.train_step(model, x[s * 6:(s + 1) * 6], y[s * 6:(s + 1) * 6])
+        out[f"loss{s}"] = r["loss"]
+        if s == 0:
+            out["probs0"] = np.asarray(model.layers[-1].output, dtype=np.float64)
+            g = []
+            for l in trainable(model):
+                p = l.get_parameters()
+                g += [np.ravel(p["weights"][1]), np.ravel(p["biases"][1])]
+            out["grads0"] = np.concatenate(g).astype(np.float64)
+        out[f"params{s}"] = flat_params(model).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "vgg_small_2steps.npz"), **out)
+
+
 def cnn_stub():
     """Same net with the reference's SHIPPED stub conv backward, 2 steps."""
     spec = ref_net.mnist_cnn_spec()
@@ -247,7 +282,7 @@ def ops():
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (mlp_200, mlp_sgd, cnn_small, cnn_stub, cnn_200, ops, single_layer_optimizers, dropout_mlp, dense_example_stack):
+    for fn in (mlp_200, mlp_sgd, cnn_small, vgg_small, cnn_stub, cnn_200, ops, single_layer_optimizers, dropout_mlp, dense_example_stack):
         if not only or fn.__name__ in only:
             fn()
     for f in sorted(os.listdir(HERE)):

@@ -164,6 +164,29 @@ def test_cnn_golden(mode, fixture, steps):
         np.testing.assert_allclose(net.flat(), g["final_params"], rtol=1e-6, atol=1e-7)
 
 
+def test_vgg_small_golden():
+    """The conv -> conv -> pool stack of BASELINE.json config 4 (narrowed 8x): the oracle's step reproduces the run of
+    the unmodified reference Python (tests/golden/make_golden.py::vgg_small) -- losses, step-0 probabilities and
+    gradients, parameters after each of the two Adam steps."""
+    g = golden("vgg_small_2steps.npz")
+    spec, ic = [], 3
+    for oc in (8, 16):
+        spec += [{"kind": "conv", "ic": ic, "oc": oc, "k": 3, "padding": "same", "relu": True},
+                 {"kind": "conv", "ic": oc, "oc": oc, "k": 3, "padding": "same", "relu": True},
+                 {"kind": "pool", "size": 2, "stride": 2, "padding": "valid"}]
+        ic = oc
+    spec += [{"kind": "flatten"}, {"kind": "dense", "n_in": 16 * 8 * 8, "n_out": 10, "relu": False}, {"kind": "softmax"}]
+    net = ref_net.RefNet(spec, ref_net.init_params(spec, np.random.RandomState(31), init="he"))
+    x, y = synth(32, 6 * 2, (3, 32, 32))
+    for s in range(2):
+        r = net.step(x[s * 6:(s + 1) * 6], y[s * 6:(s + 1) * 6])
+        assert abs(r["loss"] - float(g[f"loss{s}"])) < 1e-9
+        if s == 0:
+            np.testing.assert_allclose(r["output"], g["probs0"], rtol=1e-5, atol=1e-7)
+            np.testing.assert_allclose(net.flat("grads"), g["grads0"], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(net.flat(), g[f"params{s}"], rtol=1e-5, atol=1e-6)
+
+
 # -------------------------------------------------------- live reference (here) ----
 def test_oracle_matches_live_reference(have_reference):
     if not have_reference:
