@@ -70,8 +70,9 @@ int nm_event_record(void* event, void* stream);
 int nm_event_sync(void* event);
 int nm_event_elapsed_ms(void* start, void* stop, float* ms);
 int nm_stream_wait_event(void* stream, void* event);
-int nm_graph_begin(void* stream);                        /* stream capture (thread-local mode) */
+int nm_graph_begin(void* stream);                        /* stream capture (relaxed mode) */
 int nm_graph_end(void* stream, void** graph_exec);
+int nm_graph_abort(void* stream);                        /* close a capture whose body failed; discards the partial graph */
 int nm_graph_launch(void* graph_exec, void* stream);
 int nm_graph_destroy(void* graph_exec);
 /* cudaProfilerStart/Stop: bracket the region `ncu --profile-from-start off` captures (profiles/prof_step.py) */

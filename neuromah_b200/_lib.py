@@ -45,6 +45,7 @@ _SIGS = {
     "nm_stream_wait_event": (_i, [_vp, _vp]),
     "nm_graph_begin": (_i, [_vp]),
     "nm_graph_end": (_i, [_vp, _pvp]),
+    "nm_graph_abort": (_i, [_vp]),
     "nm_graph_launch": (_i, [_vp, _vp]),
     "nm_graph_destroy": (_i, [_vp]),
     "nm_profiler_start": (_i, []),

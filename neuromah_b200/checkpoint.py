@@ -73,11 +73,22 @@ _OPT_ATTRS = ("learning_rate", "current_learning_rate", "decay", "iterations", "
               "rho", "momentum_factor", "check_gradients")
 
 
+_QUIRKS = ("duplicate_trainable_registration", "dense_double_batch_division", "conv_bias_in_forward", "conv_backward")
+
+
+def _quirks():
+    """The reference-compatibility switches (neuromah_b200/config.py) the model was finalized under: they change the
+    arithmetic of a step (e.g. how many times the optimizer is applied per step), so a checkpoint carries them."""
+    from . import config
+    return {k: getattr(config, k) for k in _QUIRKS if hasattr(config, k)}
+
+
 def model_state(model):
     opt = model.optimizer
     return {
         "format": FORMAT,
         "mode": getattr(model, "mode", "fp32"),
+        "quirks": _quirks(),
         "layers": [layer_state(l) for l in model.layers],
         "loss": type(model.loss).__name__ if not isinstance(model.loss, type) else model.loss.__name__,
         "accuracy": {"cls": type(model.accuracy).__name__ if not isinstance(model.accuracy, type) else model.accuracy.__name__,
@@ -101,7 +112,16 @@ def model_from_state(st):
         setattr(opt, k, v)
     acc_cls = getattr(metrics, st["accuracy"]["cls"])
     model.set(loss=getattr(losses, st["loss"]), optimizer=opt, accuracy=acc_cls)
-    model.finalize(mode=st["mode"])
+    from . import config
+    saved = {k: getattr(config, k) for k in st.get("quirks", {}) if hasattr(config, k)}
+    try:                                  # finalize under the quirk settings the checkpoint was written with
+        for k, v in st.get("quirks", {}).items():
+            if hasattr(config, k):
+                setattr(config, k, v)
+        model.finalize(mode=st["mode"])
+    finally:
+        for k, v in saved.items():
+            setattr(config, k, v)
     model.accuracy.binary = st["accuracy"].get("binary", False)
     if o["state"]:
         model.arena.ensure_state(len(o["state"]))

@@ -104,9 +104,26 @@ static std::mutex g_graph_mu;
 static std::unordered_map<void*, unsigned long long> g_graph_kernels;
 static thread_local unsigned long long g_capture_start = 0;
 
+// Relaxed mode: a cudaFree / cudaMalloc issued by this thread while the capture is open (a Python finalizer run by the
+// cyclic GC, a lazily created workspace) neither fails nor invalidates the capture -- in thread-local mode it did both
+// (cudaErrorStreamCaptureInvalidated at the next captured launch).  The host side still defers frees (device.py).
 int nm_graph_begin(void* stream) {
-    NM_CUDA(cudaStreamBeginCapture(nm::S(stream), cudaStreamCaptureModeThreadLocal));
+    NM_CUDA(cudaStreamBeginCapture(nm::S(stream), cudaStreamCaptureModeRelaxed));
     g_capture_start = nm::g_launches.load();
+    return NM_OK;
+}
+// Close a capture whose body failed: end it, drop whatever was captured, clear the sticky capture error.
+int nm_graph_abort(void* stream) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(nm::S(stream), &st);
+    if (st != cudaStreamCaptureStatusNone) {
+        cudaGraph_t g = nullptr;
+        cudaStreamEndCapture(nm::S(stream), &g);
+        if (g) cudaGraphDestroy(g);
+    }
+    cudaGetLastError();
+    const unsigned long long captured = nm::g_launches.load() - g_capture_start;
+    nm::g_launches.fetch_sub(captured);
     return NM_OK;
 }
 int nm_graph_end(void* stream, void** graph_exec) {

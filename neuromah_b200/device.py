@@ -9,8 +9,11 @@ process-wide non-blocking stream.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import gc
 import os
+import warnings
 
 import numpy as np
 
@@ -52,23 +55,93 @@ def launch_count() -> int:
     return int(n.value)
 
 
+# ---- releases are never issued while a stream capture is open -------------------------------------------------
+# cudaFree / cudaFreeHost synchronise the device: issued by a finalizer (Python's cyclic GC can run one at any
+# allocation) while a CUDA-graph capture is open on this thread they fail AND invalidate the capture.  While
+# ``graph_capture`` is active every release is queued and drained after cudaStreamEndCapture.
+_capture = {"depth": 0, "device": [], "host": []}
+
+
+def capturing() -> bool:
+    return _capture["depth"] > 0
+
+
+def _release(kind: str, ptr: int):
+    if _capture["depth"] > 0:
+        _capture[kind].append(ptr)
+        return
+    try:
+        (lib.nm_free if kind == "device" else lib.nm_host_free)(C.c_void_p(ptr))
+    except Exception as e:                      # a finalizer cannot raise: make the failure visible instead
+        warnings.warn(f"neuromah_b200: releasing {kind} block 0x{ptr:x} failed: {e}", RuntimeWarning)
+
+
+def drain_deferred_frees():
+    """Release what finalizers queued while a capture was open (no-op inside a capture)."""
+    if _capture["depth"] > 0:
+        return
+    for kind in ("device", "host"):
+        while _capture[kind]:
+            _release(kind, _capture[kind].pop())
+
+
+@contextlib.contextmanager
+def graph_capture(s=None):
+    """Capture the launches issued inside the ``with`` body on stream ``s`` into a CUDA graph.
+
+    ``with graph_capture() as cap: ...`` leaves the instantiated executable graph in ``cap.graph`` (a ``c_void_p``
+    for ``nm_graph_launch``).  Inside the body the cyclic GC is paused and frees are deferred, nothing may allocate
+    device memory.  If the body (or the capture itself) fails, the capture is closed, the partial graph discarded and
+    the ORIGINAL exception propagates -- no kernel of the body has run."""
+    s = stream() if s is None else s
+
+    class _Cap:
+        graph = None
+    cap = _Cap()
+    gc_was_on = gc.isenabled()
+    gc.disable()
+    _capture["depth"] += 1
+    try:
+        lib.nm_graph_begin(s)
+    except BaseException:
+        _capture["depth"] -= 1
+        gc.enable() if gc_was_on else None
+        raise
+    try:
+        yield cap
+    except BaseException:
+        try:                                    # close the (possibly invalidated) capture; its own error is secondary
+            lib.nm_graph_abort(s)
+        except Exception:
+            pass
+        raise
+    else:
+        g = C.c_void_p()
+        lib.nm_graph_end(s, C.byref(g))
+        cap.graph = g
+    finally:
+        _capture["depth"] -= 1
+        if gc_was_on:
+            gc.enable()
+        drain_deferred_frees()
+
+
 class _Block:
     """Owner of one cudaMalloc'd block."""
     __slots__ = ("ptr", "nbytes")
 
     def __init__(self, nbytes: int):
         init()
+        if _capture["depth"] > 0:
+            raise RuntimeError("neuromah_b200: device allocation inside a CUDA-graph capture (allocate before capturing)")
         p = C.c_void_p()
         lib.nm_malloc(C.byref(p), max(int(nbytes), 16))
         self.ptr, self.nbytes = p.value, int(nbytes)
 
     def __del__(self):
-        try:
-            if self.ptr:
-                lib.nm_free(C.c_void_p(self.ptr))
-                self.ptr = None
-        except Exception:
-            pass
+        ptr, self.ptr = self.ptr, None
+        if ptr:
+            _release("device", ptr)
 
 
 _pinned_ranges = []      # (start, end) of live page-locked host blocks
@@ -113,14 +186,11 @@ class PinnedBuffer:
         self.array = np.frombuffer(buf, dtype=self.dtype, count=count).reshape(self.shape)
 
     def __del__(self):
-        try:
-            if self.ptr:
-                self.array = None
-                _pinned_ranges[:] = [r for r in _pinned_ranges if r[0] != self.ptr]
-                lib.nm_host_free(C.c_void_p(self.ptr))
-                self.ptr = None
-        except Exception:
-            pass
+        ptr, self.ptr = getattr(self, "ptr", None), None
+        if ptr:
+            self.array = None
+            _pinned_ranges[:] = [r for r in _pinned_ranges if r[0] != ptr]
+            _release("host", ptr)
 
 
 class DeviceArray:

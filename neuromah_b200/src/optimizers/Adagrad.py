@@ -41,5 +41,11 @@ class Optimizer_Adagrad:
     def update_arena(self, arena, n_apply=1):
         self._step(arena.params, arena.grads, arena.state[0], arena.total, n_apply)
 
+    def check_nonfinite(self):
+        """Arena path: raise the reference's ValueError if the kernel flagged a NaN/Inf gradient since the last check
+        (one device synchronisation: Model.train calls it once per epoch beside the loss read-back)."""
+        if self.check_gradients:
+            self._nf.check("arena")
+
     def post_update_params(self):
         self.iterations += 1

@@ -86,5 +86,11 @@ class Optimizer_SGD:
         ops.sgd_step(arena.params, arena.grads, mom, lr=self.current_learning_rate,
                      momentum=self.momentum_factor, n_apply=n_apply, nonfinite=flag)
 
+    def check_nonfinite(self):
+        """Arena path: the kernel raised the device flag if any gradient of the slab was NaN/Inf (SGD.py:80-83).  Reading
+        it costs a device synchronisation, so Model.train calls this once per epoch beside the loss read-back."""
+        if self.check_gradients and self._flag is not None:
+            self._raise_if_nonfinite("arena")
+
     def post_update_params(self):
         self.iterations += 1

@@ -99,6 +99,9 @@ class TcCnnPlan:
         self.w1e = DeviceArray((128, 16), np.uint16)          # conv1 weights expanded over the 4 pool-window positions
         self.w3p = None
         self.launches_per_step = 0
+        # side branch of the backward pass: created here, never inside a CUDA-graph capture
+        from .device import new_event, new_stream
+        self._side, self._ev_fork, self._ev_join, self._ev_fork2 = new_stream(), new_event(), new_event(), new_event()
 
     # ------------------------------------------------------------------ buffers ----
     def _ensure(self, B, H, W):
@@ -186,9 +189,6 @@ class TcCnnPlan:
             lib.nm_tc_pack_dlogits_bf16(self.dlogits.p, self.dl_hilo.p, B, self.n_out, s)
         sd = s
         if fork:
-            if getattr(self, "_side", None) is None:
-                from .device import new_event, new_stream
-                self._side, self._ev_fork, self._ev_join, self._ev_fork2 = new_stream(), new_event(), new_event(), new_event()
             sd = self._side
             lib.nm_event_record(self._ev_fork, s)
             lib.nm_stream_wait_event(sd, self._ev_fork)
@@ -215,6 +215,8 @@ class TcCnnPlan:
             _timed('tc_conv2_bwd', lib.nm_tc_conv3x3_bwd_bf16, self.act1_pad.p, self.dy2_pad.p, self.w2d.p, self.c2.weight_gradients.p,
                    self.dp1.p, self.ws.p, self.ws.nbytes, B, 14, 14, 32, 64, s)
         if comm is not None:
+            if fork:        # the Dense gradients of this bucket were written on the side branch: join it first
+                lib.nm_stream_wait_event(s, self._ev_join)
             lo = self._first_conv_floats()
             comm.allreduce_async(self.model.arena.grads, lo, self.model.arena.total - lo)
         _timed('tc_conv1_bwd', lib.nm_tc_conv1_bwd_bf16, self.x.p, self.dp1.p, self.idx1.p, self.c1.weight_gradients.p, self.c1.bias_gradients.p,

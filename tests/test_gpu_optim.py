@@ -146,6 +146,25 @@ def test_nonfinite_gradient_raises_value_error():
         Optimizer_Adagrad().update_params(l)
 
 
+@pytest.mark.parametrize("opt_name", ["sgd", "rmsprop", "adagrad"])
+def test_nonfinite_gradient_raises_through_model_train(opt_name):
+    """The arena path Model.train uses (update_arena) keeps the reference's ValueError on NaN/Inf gradients
+    (SGD.py:80-83, RMSprop.py:93-96): the device flag is read once per epoch beside the loss sums."""
+    from neuromah_b200.src.optimizers import Optimizer_SGD, Optimizer_RMSprop, Optimizer_Adagrad
+    from test_gpu_model import build
+    spec = ref_net.mlp_spec(16, 8, 4)
+    model = build(spec, ref_net.init_params(spec, np.random.RandomState(0)), optimizer="sgd", learning_rate=0.1)
+    opt = {"sgd": Optimizer_SGD(learning_rate=0.1), "rmsprop": Optimizer_RMSprop(), "adagrad": Optimizer_Adagrad()}[opt_name]
+    model.optimizer = opt
+    opt.bind_arena(model.arena)
+    x = np.random.default_rng(0).random((32, 16), dtype=np.float32)
+    y = np.eye(4)[np.random.default_rng(1).integers(0, 4, 32)]
+    model.train(x, y, epochs=1, batch_size=16, verbose=0)          # finite gradients: no error
+    x[3, 5] = np.nan
+    with pytest.raises(ValueError, match="Gradient"):
+        model.train(x, y, epochs=1, batch_size=16, verbose=0)
+
+
 def test_constructor_validation_matches_reference():
     from neuromah_b200.src.optimizers import Optimizer_RMSprop, Optimizer_Adagrad, Optimizer_Nadam
     for bad in (dict(learning_rate=0), dict(decay=-1), dict(epsilon=0), dict(rho=1.0)):

@@ -192,3 +192,92 @@ def test_tc_train_api_with_smaller_validation_batches(tmp_path):
     import json
     log = json.load(open(model.tensorMonitor.log_file_path))
     assert len(log["epochs"]) == 3 and "Layer_Conv2D/dweights" in log["epochs"][0]["parameters"]["histograms"]
+
+
+def test_graph_capture_survives_garbage_collection_of_a_dropped_model():
+    """Regression (round-1 driver failure, cudaErrorStreamCaptureInvalidated): a model sits in reference cycles
+    (layer.model <-> model.layers), so the cyclic GC may release its device blocks at ANY allocation -- including in
+    the middle of the capture of another model's training step.  Frees are deferred while a capture is open."""
+    import gc
+    from neuromah_b200 import device
+    from neuromah_b200.device import DeviceArray
+    spec = ref_net.mnist_cnn_spec()
+    params = ref_net.init_params(spec, np.random.RandomState(9), init="he")
+    x, y = synth_learnable(10, 128)
+    xd = DeviceArray.from_numpy(x)
+    yd = DeviceArray.from_numpy(np.argmax(y, axis=1).astype(np.int32))
+    dropped = build(spec, params, mode="bf16")
+    dropped.train_step(xd, yd)
+    model = build(spec, params, mode="bf16")
+    model.train_step(xd, yd)                                  # first sighting: eager
+    del dropped                                               # only the cycle keeps it alive now
+    orig_forward = model.plan.forward
+
+    def forward_with_gc(*a, **k):                             # a GC pass in the middle of the capture
+        assert device.capturing()
+        out = orig_forward(*a, **k)
+        n_before = len(device._capture["device"])
+        gc.collect()
+        assert len(device._capture["device"]) > n_before      # the dropped model's blocks were queued, not freed
+        return out
+    model.plan.forward = forward_with_gc
+    model.train_step(xd, yd)                                  # second sighting: captured + launched
+    model.plan.forward = orig_forward
+    assert len(model._graphs) == 1 and model.graph_steps
+    assert not device._capture["device"] and not device.capturing()      # drained after the capture closed
+    model.train_step(xd, yd)                                  # replay
+    device.synchronize()
+    eager = build(spec, params, mode="bf16")
+    eager.graph_steps = False
+    for _ in range(3):
+        eager.train_step(xd, yd)
+    np.testing.assert_allclose(model.arena.host_params(), eager.arena.host_params(), rtol=1e-4, atol=2e-5)
+
+
+def test_failed_capture_falls_back_to_eager_steps():
+    """A failure inside the captured body closes the capture, disables graph replay for the model and the step runs
+    eagerly -- the model is not left mid-step."""
+    from neuromah_b200.device import DeviceArray
+    spec = ref_net.mnist_cnn_spec()
+    params = ref_net.init_params(spec, np.random.RandomState(9), init="he")
+    x, y = synth_learnable(10, 64)
+    xd = DeviceArray.from_numpy(x)
+    yd = DeviceArray.from_numpy(np.argmax(y, axis=1).astype(np.int32))
+    model = build(spec, params, mode="bf16")
+    model.train_step(xd, yd)
+    orig_backward = model.plan.backward
+    calls = {"n": 0}
+
+    def failing_backward(*a, **k):
+        calls["n"] += 1
+        if calls["n"] == 1:
+            raise RuntimeError("injected failure inside the capture")
+        return orig_backward(*a, **k)
+    model.plan.backward = failing_backward
+    with pytest.warns(RuntimeWarning, match="capture"):
+        model.train_step(xd, yd)
+    assert model.graph_steps is False and model.optimizer.iterations == 2
+    model.plan.backward = orig_backward
+    model.train_step(xd, yd)
+    ref = build(spec, params, mode="bf16")
+    ref.graph_steps = False
+    for _ in range(3):
+        ref.train_step(xd, yd)
+    np.testing.assert_array_equal(model.arena.host_params(), ref.arena.host_params())
+
+
+def test_staged_training_reuses_one_graph_per_batch_shape():
+    """Model.train with the data set staged in HBM: every step's batch is a different pointer, so batches go through one
+    fixed device slot and ONE captured graph serves all full-size steps (+ one for the partial last batch)."""
+    spec = ref_net.mnist_cnn_spec()
+    params = ref_net.init_params(spec, np.random.RandomState(9), init="he")
+    x, y = synth_learnable(16, 20 * 64 + 32)
+    model = build(spec, params, mode="bf16", learning_rate=0.002)
+    model.train(x, y, epochs=2, batch_size=64, verbose=0)
+    assert len(model._graphs) == 2 and len(model._graph_seen) <= 4
+    eager = build(spec, params, mode="bf16", learning_rate=0.002)
+    eager.graph_steps = False
+    eager.train(x, y, epochs=2, batch_size=64, verbose=0)
+    assert model.optimizer.iterations == eager.optimizer.iterations == 42
+    np.testing.assert_allclose(model.arena.host_params(), eager.arena.host_params(), rtol=1e-3, atol=2e-4)
+    assert abs(model.last_epoch["loss"] - eager.last_epoch["loss"]) < 1e-3
