@@ -200,6 +200,10 @@ int nm_dropout_fwd_f32(const float* x, float* y, float* mask, size_t n, float ke
 int nm_mul_f32(float* y, const float* a, const float* b, size_t n, void* stream);      /* y = a * b elementwise */
 /* y = a*x (+ y if accumulate): FedAvg pre-scale n_i/N (Federated/utils.py:21-22). */
 int nm_scale_f32(float* y, const float* x, size_t n, float a, int accumulate, void* stream);
+/* Raw uint8 pixels -> float32: y = float(x) / denom with IEEE division, i.e. the host-side preprocessing
+ * `X.astype(np.float32) / 255.0` of examples/test_Conv2D_MNIST.py:27 moved behind the host->device copy (4x fewer bytes
+ * over PCIe); bit-identical to NumPy.  The bf16 plans take uint8 inputs directly (nm_tc_*_u8_bf16 below). */
+int nm_u8_to_f32_div(const uint8_t* x, float* y, size_t n, float denom, void* stream);
 
 /* ---- bf16 tensor-core path (tcgen05 + TMA + TMEM), see DESIGN.md --------- */
 /* Activations: bf16 NHWC with a one-pixel zero halo, [N, H+2, W+2, C] ("padded grid"); the halo is
@@ -248,6 +252,8 @@ int nm_tc_conv3x3_bwd_pool_bf16(const void* x_pad, const void* dpool, const void
 int nm_tc_pack_conv_weights_gen_bf16(const float* w_oihw, void* w_fprop, void* w_dgrad, int OC, int C, int OCp, int Cp, void* stream);
 /* f32 NCHW [N,C,H,W] -> haloed bf16 NHWC [N,H+2,W+2,Cp] (replaces np.pad, Conv_wrapepr.py:78-84); every element written. */
 int nm_tc_pack_input_nhwc_bf16(const float* x_nchw, void* x_pad, int N, int C, int H, int W, int Cp, void* stream);
+/* ... from raw uint8 pixels, value = float(x) * scale (scale = 1/255: the example scripts' normalisation). */
+int nm_tc_pack_input_nhwc_u8_bf16(const uint8_t* x_nchw, float scale, void* x_pad, int N, int C, int H, int W, int Cp, void* stream);
 /* y_pad[N,H+2,W+2,Cout] = conv3x3(x_pad[N,H+2,W+2,Cin], w_packed[Cout][9][Cin]) (+ bias[Cout] if not NULL)
  * (ReLU if relu != 0) (zeroed where relu_mask[N,H+2,W+2,Cout] <= 0, if not NULL).  tcgen05 implicit GEMM, K loop over
  * (64-channel chunk, tap).  fprop (Conv2D.cpp:83-146 + Conv_wrapepr.py:96-98): w_packed = the fprop operand, relu = 1.
@@ -281,12 +287,18 @@ int nm_tc_pack_conv1_weights_bf16(const float* w, void* w_ext, int OC, void* str
 /* x f32 [N,1,H,W] (rounded to bf16 as the MMA operand) -> y_pad bf16 [N,H/2+2,W/2+2,OC] (interior; the zero halo is
  * never written), idx nibbles [N,H/2,W/2,OC/2].  OC = 32. */
 int nm_tc_conv1_fwd_pool_bf16(const float* x, const void* w_ext, void* y_pad, void* idx, int N, int H, int W, int OC, void* stream);
+/* ... the same from raw uint8 pixels: the operand is bf16(float(x) * scale); with scale = 1/255 that equals
+ * bf16(float32(x) / 255) -- the reference's normalisation -- for all 256 pixel values. */
+int nm_tc_conv1_fwd_pool_u8_bf16(const uint8_t* x, float scale, const void* w_ext, void* y_pad, void* idx, int N, int H, int W, int OC,
+                                 void* stream);
 /* ... and backward: pool backward + ReLU backward (the nibble) + wgrad + bias gradient in one tcgen05 pass
  * (E[(pos,oc)][4x4 patch] accumulated in TMEM, one FP32 partial per CTA, fixed-order reduction).
  * dp_grid = gradient of the pooled output, bf16 on the un-shifted grid [N,H/2+2,W/2+2,OC] (nm_tc_conv3x3_dgrad_bf16). */
 size_t nm_tc_conv1_bwd_workspace(int OC);
 int nm_tc_conv1_bwd_bf16(const float* x, const void* dp_grid, const void* idx, float* dw, float* db,
                          void* workspace, size_t workspace_bytes, int N, int H, int W, int OC, void* stream);
+int nm_tc_conv1_bwd_u8_bf16(const uint8_t* x, float scale, const void* dp_grid, const void* idx, float* dw, float* db,
+                            void* workspace, size_t workspace_bytes, int N, int H, int W, int OC, void* stream);
 /* Dense weights in the reference layout [(c,h,w) rows][n_out] f32 ->
  *   w_packed f32 [n_out][K] with K in the kernels' (h,w,c) order (CUDA-core dgrad; may be NULL)
  *   w_hilo  bf16 [32][K]: rows [0,16) = bf16(w), rows [16,32) = bf16(w - bf16(w)), classes >= n_out zero

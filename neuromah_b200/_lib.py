@@ -79,6 +79,7 @@ _SIGS = {
     "nm_dropout_fwd_f32": (_i, [_vp, _vp, _vp, _sz, _f, C.c_ulonglong, C.c_ulonglong, _vp]),
     "nm_mul_f32": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "nm_scale_f32": (_i, [_vp, _vp, _sz, _f, _i, _vp]),
+    "nm_u8_to_f32_div": (_i, [_vp, _vp, _sz, _f, _vp]),
     "nm_tc_pack_conv_weights_bf16": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "nm_tc_conv3x3_fprop_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_conv3x3_dgrad_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
@@ -99,6 +100,9 @@ _SIGS = {
     "nm_tc_dense_bwd_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_pack_conv1_weights_bf16": (_i, [_vp, _vp, _i, _vp]),
     "nm_tc_conv1_fwd_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "nm_tc_conv1_fwd_pool_u8_bf16": (_i, [_vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "nm_tc_conv1_bwd_u8_bf16": (_i, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp]),
+    "nm_tc_pack_input_nhwc_u8_bf16": (_i, [_vp, _f, _vp, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_conv1_bwd_workspace": (_sz, [_i]),
     "nm_tc_conv1_bwd_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp]),
     "nm_tc_pack_dense_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -231,9 +231,31 @@ __global__ void scale_kernel(float* __restrict__ y, const float* __restrict__ x,
     for (; i < n; i += stride) y[i] = accumulate ? y[i] + a * x[i] : a * x[i];
 }
 
+// raw uint8 pixels -> float32 with the reference's host-side normalisation `X.astype(np.float32) / 255.0`
+// (examples/test_Conv2D_MNIST.py:27): IEEE division, so the result is bit-identical to NumPy's.  4 pixels per thread.
+__global__ void u8_to_f32_div_kernel(const uint8_t* __restrict__ x, float* __restrict__ y, size_t n, float denom) {
+    const size_t n4 = n / 4;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n4; i += stride) {
+        const uchar4 u = reinterpret_cast<const uchar4*>(x)[i];
+        reinterpret_cast<float4*>(y)[i] = make_float4(__fdiv_rn((float)u.x, denom), __fdiv_rn((float)u.y, denom),
+                                                      __fdiv_rn((float)u.z, denom), __fdiv_rn((float)u.w, denom));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) y[n4 * 4 + threadIdx.x] = __fdiv_rn((float)x[n4 * 4 + threadIdx.x], denom);
+}
+
 }  // namespace
 
 extern "C" {
+
+int nm_u8_to_f32_div(const uint8_t* x, float* y, size_t n, float denom, void* stream) {
+    NM_REQUIRE(x && y, "null pointer");
+    NM_REQUIRE(denom != 0.f, "denom must be non-zero");
+    NM_REQUIRE(((uintptr_t)x & 3) == 0 && ((uintptr_t)y & 15) == 0, "x must be 4-byte and y 16-byte aligned");
+    if (!n) return NM_OK;
+    u8_to_f32_div_kernel<<<ew_blocks(n, 256, 4), 256, 0, nm::S(stream)>>>(x, y, n, denom);
+    return nm::launched("u8_to_f32_div");
+}
 
 int nm_relu_fwd_f32(const float* x, float* y, size_t n, void* stream) {
     NM_REQUIRE(x && y, "null pointer");

@@ -58,33 +58,41 @@ __device__ __forceinline__ TileSpan tile_span(const Conv1Geom& G, int tile) {
     return t;
 }
 
+// Input pixels are either FP32 (the reference's `X.astype(float32) / 255`, examples/test_Conv2D_MNIST.py:27, done on the host)
+// or the raw uint8 pixels with that normalisation done here: float(u) * scale.  With scale = 1/255 the product rounds to
+// the same bf16 operand as the reference's float32 division for all 256 pixel values (tests/test_tc_layout_host.py).
+__device__ __forceinline__ float px_val(const float* img, int i, float) { return img[i]; }
+__device__ __forceinline__ float px_val(const uint8_t* img, int i, float scale) { return (float)img[i] * scale; }
+
 // the 4x4 input patch of pool window (n, py, px) from the staged images (zero outside the image: the 'same'
 // padding of Conv_wrapepr.py:78-84)
-__device__ __forceinline__ void load_patch(const float* __restrict__ xs, const Conv1Geom& G, bool valid, int n_local, int py, int px,
+template <typename XT>
+__device__ __forceinline__ void load_patch(const XT* __restrict__ xs, const Conv1Geom& G, float scale, bool valid, int n_local, int py, int px,
                                            float p[16]) {
-    const float* img = xs + n_local * G.H * G.W;
+    const XT* img = xs + n_local * G.H * G.W;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const int yy = 2 * py - 1 + a;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int xx = 2 * px - 1 + b;
-            p[a * 4 + b] = (valid && (unsigned)yy < (unsigned)G.H && (unsigned)xx < (unsigned)G.W) ? img[yy * G.W + xx] : 0.f;
+            p[a * 4 + b] = (valid && (unsigned)yy < (unsigned)G.H && (unsigned)xx < (unsigned)G.W) ? px_val(img, yy * G.W + xx, scale) : 0.f;
         }
     }
 }
 
 // rows a0, a0 + 1 of that patch only (the backward builders split a window's patch between two threads)
-__device__ __forceinline__ void load_patch_rows(const float* __restrict__ xs, const Conv1Geom& G, bool valid, int n_local, int py, int px,
+template <typename XT>
+__device__ __forceinline__ void load_patch_rows(const XT* __restrict__ xs, const Conv1Geom& G, float scale, bool valid, int n_local, int py, int px,
                                                 int a0, float p[8]) {
-    const float* img = xs + n_local * G.H * G.W;
+    const XT* img = xs + n_local * G.H * G.W;
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
         const int yy = 2 * py - 1 + a0 + a;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int xx = 2 * px - 1 + b;
-            p[a * 4 + b] = (valid && (unsigned)yy < (unsigned)G.H && (unsigned)xx < (unsigned)G.W) ? img[yy * G.W + xx] : 0.f;
+            p[a * 4 + b] = (valid && (unsigned)yy < (unsigned)G.H && (unsigned)xx < (unsigned)G.W) ? px_val(img, yy * G.W + xx, scale) : 0.f;
         }
     }
 }
@@ -99,8 +107,9 @@ constexpr int F_NBUF = 4;                       // TMEM accumulators (4 x 128 co
 constexpr int F_XSTAGES = 6;                    // staged-image ring (bulk-copy producer -> builders): hides the HBM latency
 constexpr int F_THREADS = 832;                  // warps 0-7 builders (2 groups), 8 MMA, 9-24 epilogue (4 groups), 25 bulk-copy producer
 
+template <typename XT>
 __global__ void __launch_bounds__(F_THREADS, 1)
-conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ wext, __nv_bfloat16* __restrict__ y_pad,
+conv1_tc_fwd_kernel(const XT* __restrict__ x, float x_scale, const __nv_bfloat16* __restrict__ wext, __nv_bfloat16* __restrict__ y_pad,
                     uint8_t* __restrict__ idx, Conv1Geom G, int x_stage_bytes) {
     constexpr uint64_t TMPL = desc_template(16, 512, LAYOUT_SW64);
     constexpr uint32_t IDESC = idesc_bf16(128, 128, 0, 0);
@@ -144,7 +153,7 @@ conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
             int xs = 0; uint32_t xphase = 0;
             for (int tile = blockIdx.x; tile < G.num_tiles; tile += gridDim.x) {
                 const TileSpan t = tile_span(G, tile);
-                const uint32_t bytes = (uint32_t)(t.n1 - t.n0 + 1) * G.H * G.W * 4u;
+                const uint32_t bytes = (uint32_t)(t.n1 - t.n0 + 1) * G.H * G.W * (uint32_t)sizeof(XT);
                 mbar_wait(&xempty[xs], xphase ^ 1);
                 mbar_expect_tx(&xfull[xs], bytes);
                 bulk_load(x_smem + (size_t)xs * x_stage_bytes, x + (size_t)t.n0 * G.H * G.W, bytes, &xfull[xs]);
@@ -172,7 +181,7 @@ conv1_tc_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
             if (row == 0) NM_TRACE(G, tile, 0);
             mbar_wait(&xfull[xs], xphase);
             if (row == 0) NM_TRACE(G, tile, 1);
-            load_patch(reinterpret_cast<const float*>(x_smem + (size_t)xs * x_stage_bytes), G, valid, n - t.n0, py, px, p);
+            load_patch(reinterpret_cast<const XT*>(x_smem + (size_t)xs * x_stage_bytes), G, x_scale, valid, n - t.n0, py, px, p);
             __syncwarp();
             if (lane == 0) mbar_arrive(&xempty[xs]);          // the patches are in registers: the image slot may be refilled
             mbar_wait(&aempty[stage], phase ^ 1);
@@ -287,8 +296,9 @@ constexpr int B_THREADS = 576;                  // warps 0-15 builders in two gr
 
 struct Conv1BwdSmem { int x_bytes, dp_bytes, lstage_bytes; };   // per load stage: [x images | dp rows | nibbles]
 
+template <typename XT>
 __global__ void __launch_bounds__(B_THREADS, 1)
-conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dp_grid, const uint8_t* __restrict__ idx,
+conv1_tc_bwd_kernel(const XT* __restrict__ x, float x_scale, const __nv_bfloat16* __restrict__ dp_grid, const uint8_t* __restrict__ idx,
                     float* __restrict__ partial, Conv1Geom G, Conv1BwdSmem L) {
     constexpr uint64_t TMPL_A = desc_template(16, 1024, LAYOUT_SW128);     // MN-major: SBO = 8 k-rows of 128 B
     constexpr uint64_t TMPL_B = desc_template(16, 512, LAYOUT_SW64);       //           SBO = 8 k-rows of 64 B
@@ -337,7 +347,7 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
                 const TileSpan t = tile_span(G, tile);
                 const int w0 = (int)(t.g0 - (unsigned)t.n0 * G.PHW), w1 = (int)(t.g1 - (unsigned)t.n1 * G.PHW);
                 const int r0 = t.n0 * (G.PH + 2) + w0 / G.PW, r1 = t.n1 * (G.PH + 2) + w1 / G.PW;
-                const uint32_t xb = (uint32_t)(t.n1 - t.n0 + 1) * G.H * G.W * 4u;
+                const uint32_t xb = (uint32_t)(t.n1 - t.n0 + 1) * G.H * G.W * (uint32_t)sizeof(XT);
                 const uint32_t db = (uint32_t)(r1 - r0 + 1) * row_bytes;
                 const uint32_t ib = (uint32_t)(t.g1 - t.g0 + 1) * (OC / 2);
                 uint8_t* st = l_smem + (size_t)ls * L.lstage_bytes;
@@ -387,7 +397,7 @@ conv1_tc_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
                 da = src[flip]; db = src[flip ^ 1];
                 nb = *reinterpret_cast<const uint2*>(st + L.x_bytes + L.dp_bytes + row * (OC / 2) + hh * 8);
             }
-            load_patch_rows(reinterpret_cast<const float*>(st), G, valid, n - t.n0, py, px, 2 * hh, p);
+            load_patch_rows(reinterpret_cast<const XT*>(st), G, x_scale, valid, n - t.n0, py, px, 2 * hh, p);
             __syncwarp();
             if (lane == 0) mbar_arrive(&lempty[ls]);          // everything is in registers: the slot may be refilled
             const uint32_t dw[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};   // 16 channels as bf16 pairs, piece order
@@ -538,6 +548,54 @@ int geom(Conv1Geom* g, int N, int H, int W) {
 
 }  // namespace
 
+template <typename XT>
+static int conv1_fwd_launch(const XT* x, float scale, const void* w_ext, void* y_pad, void* idx, int N, int H, int W, int OCn, void* stream) {
+    NM_REQUIRE(x && w_ext && y_pad && idx, "null pointer");
+    NM_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "bad dimensions");
+    NM_REQUIRE((H * W * sizeof(XT)) % 16 == 0, "an image must be a multiple of 16 bytes (bulk copies)");
+    if (OCn != OC) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_fwd_pool: only OC=32 is instantiated");
+    Conv1Geom g;
+    { int rc = geom(&g, N, H, W); if (rc) return rc; }
+    NM_REQUIRE(g.PHW >= 128, "image too small: a 128-window tile must touch at most two images");
+    const int x_stage = (2 * H * W * (int)sizeof(XT) + 127) & ~127;
+    const size_t smem = (size_t)(1 + F_STAGES) * F_TILE_BYTES + (size_t)F_XSTAGES * x_stage + 256;
+    if (smem > 200 * 1024) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_fwd_pool: image too large for the staged-image ring");
+    static bool attr = false;
+    if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv1_tc_fwd_kernel<XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    const int grid = g.num_tiles < sm_count() ? g.num_tiles : sm_count();
+    return nm::launch_pdl("conv1_tc_fwd", conv1_tc_fwd_kernel<XT>, dim3(grid), dim3(F_THREADS), smem, nm::S(stream), x, scale,
+                          static_cast<const __nv_bfloat16*>(w_ext), static_cast<__nv_bfloat16*>(y_pad), static_cast<uint8_t*>(idx), g, x_stage);
+}
+
+template <typename XT>
+static int conv1_bwd_launch(const XT* x, float scale, const void* dp_grid, const void* idx, float* dw, float* db,
+                            void* workspace, size_t workspace_bytes, int N, int H, int W, int OCn, void* stream) {
+    NM_REQUIRE(x && dp_grid && idx && dw && db && workspace, "null pointer");
+    NM_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "bad dimensions");
+    NM_REQUIRE((H * W * sizeof(XT)) % 16 == 0, "an image must be a multiple of 16 bytes (bulk copies)");
+    if (OCn != OC) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_bwd: only OC=32 is instantiated");
+    Conv1Geom g;
+    { int rc = geom(&g, N, H, W); if (rc) return rc; }
+    int grid = sm_count() < B_MAX_GRID ? sm_count() : B_MAX_GRID;
+    if (g.num_tiles < grid) grid = g.num_tiles;
+    NM_REQUIRE(workspace_bytes >= (size_t)grid * 128 * 32 * sizeof(float), "workspace too small");
+    NM_REQUIRE(g.PHW >= 128, "image too small: a 128-window tile must touch at most two images");
+    Conv1BwdSmem L;
+    L.x_bytes = (2 * H * W * (int)sizeof(XT) + 127) & ~127;
+    const int max_rows = (128 + g.PW - 1) / g.PW + 1 + 2;          // pooled rows a tile can span + the 2 halo rows at an image boundary
+    L.dp_bytes = max_rows * (g.PW + 2) * OC * 2;
+    L.lstage_bytes = L.x_bytes + L.dp_bytes + B_IDX_BYTES;
+    const size_t smem = (size_t)B_STAGES * B_STAGE + (size_t)B_LSTAGES * L.lstage_bytes + 256;
+    if (smem > 220 * 1024) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_bwd: image too large for the staged-input ring");
+    static bool attr = false;
+    if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv1_tc_bwd_kernel<XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
+    int rc = nm::launch_pdl("conv1_tc_bwd", conv1_tc_bwd_kernel<XT>, dim3(grid), dim3(B_THREADS), smem, nm::S(stream), x, scale,
+                            static_cast<const __nv_bfloat16*>(dp_grid), static_cast<const uint8_t*>(idx), static_cast<float*>(workspace), g, L);
+    if (rc) return rc;
+    return nm::launch_pdl("conv1_tc_bwd_reduce", conv1_tc_bwd_reduce_kernel, dim3(nm_cdiv(OC * 10, 32)), dim3(32 * R_SLICES), 0, nm::S(stream),
+                          static_cast<const float*>(workspace), dw, db, grid);
+}
+
 extern "C" {
 
 int nm_tc_pack_conv1_weights_bf16(const float* w, void* w_ext, int OCn, void* stream) {
@@ -547,49 +605,22 @@ int nm_tc_pack_conv1_weights_bf16(const float* w, void* w_ext, int OCn, void* st
 }
 
 int nm_tc_conv1_fwd_pool_bf16(const float* x, const void* w_ext, void* y_pad, void* idx, int N, int H, int W, int OCn, void* stream) {
-    NM_REQUIRE(x && w_ext && y_pad && idx, "null pointer");
-    NM_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "bad dimensions");
-    if (OCn != OC) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_fwd_pool_bf16: only OC=32 is instantiated");
-    Conv1Geom g;
-    { int rc = geom(&g, N, H, W); if (rc) return rc; }
-    NM_REQUIRE(g.PHW >= 128, "image too small: a 128-window tile must touch at most two images");
-    const int x_stage = (2 * H * W * 4 + 127) & ~127;
-    const size_t smem = (size_t)(1 + F_STAGES) * F_TILE_BYTES + (size_t)F_XSTAGES * x_stage + 256;
-    if (smem > 200 * 1024) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_fwd_pool_bf16: image too large for the staged-image ring");
-    static bool attr = false;
-    if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv1_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-    const int grid = g.num_tiles < sm_count() ? g.num_tiles : sm_count();
-    return nm::launch_pdl("conv1_tc_fwd", conv1_tc_fwd_kernel, dim3(grid), dim3(F_THREADS), smem, nm::S(stream), x,
-                          static_cast<const __nv_bfloat16*>(w_ext), static_cast<__nv_bfloat16*>(y_pad), static_cast<uint8_t*>(idx), g, x_stage);
+    return conv1_fwd_launch<float>(x, 1.f, w_ext, y_pad, idx, N, H, W, OCn, stream);
+}
+int nm_tc_conv1_fwd_pool_u8_bf16(const uint8_t* x, float scale, const void* w_ext, void* y_pad, void* idx, int N, int H, int W, int OCn,
+                                 void* stream) {
+    return conv1_fwd_launch<uint8_t>(x, scale, w_ext, y_pad, idx, N, H, W, OCn, stream);
 }
 
 size_t nm_tc_conv1_bwd_workspace(int OCn) { (void)OCn; return (size_t)B_MAX_GRID * 128 * 32 * sizeof(float); }
 
 int nm_tc_conv1_bwd_bf16(const float* x, const void* dp_grid, const void* idx, float* dw, float* db,
                          void* workspace, size_t workspace_bytes, int N, int H, int W, int OCn, void* stream) {
-    NM_REQUIRE(x && dp_grid && idx && dw && db && workspace, "null pointer");
-    NM_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "bad dimensions");
-    if (OCn != OC) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_bwd_bf16: only OC=32 is instantiated");
-    Conv1Geom g;
-    { int rc = geom(&g, N, H, W); if (rc) return rc; }
-    int grid = sm_count() < B_MAX_GRID ? sm_count() : B_MAX_GRID;
-    if (g.num_tiles < grid) grid = g.num_tiles;
-    NM_REQUIRE(workspace_bytes >= (size_t)grid * 128 * 32 * sizeof(float), "workspace too small");
-    NM_REQUIRE(g.PHW >= 128, "image too small: a 128-window tile must touch at most two images");
-    Conv1BwdSmem L;
-    L.x_bytes = (2 * H * W * 4 + 127) & ~127;
-    const int max_rows = (128 + g.PW - 1) / g.PW + 1 + 2;          // pooled rows a tile can span + the 2 halo rows at an image boundary
-    L.dp_bytes = max_rows * (g.PW + 2) * OC * 2;
-    L.lstage_bytes = L.x_bytes + L.dp_bytes + B_IDX_BYTES;
-    const size_t smem = (size_t)B_STAGES * B_STAGE + (size_t)B_LSTAGES * L.lstage_bytes + 256;
-    if (smem > 220 * 1024) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_bwd_bf16: image too large for the staged-input ring");
-    static bool attr = false;
-    if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv1_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
-    int rc = nm::launch_pdl("conv1_tc_bwd", conv1_tc_bwd_kernel, dim3(grid), dim3(B_THREADS), smem, nm::S(stream), x,
-                            static_cast<const __nv_bfloat16*>(dp_grid), static_cast<const uint8_t*>(idx), static_cast<float*>(workspace), g, L);
-    if (rc) return rc;
-    return nm::launch_pdl("conv1_tc_bwd_reduce", conv1_tc_bwd_reduce_kernel, dim3(nm_cdiv(OC * 10, 32)), dim3(32 * R_SLICES), 0, nm::S(stream),
-                          static_cast<const float*>(workspace), dw, db, grid);
+    return conv1_bwd_launch<float>(x, 1.f, dp_grid, idx, dw, db, workspace, workspace_bytes, N, H, W, OCn, stream);
+}
+int nm_tc_conv1_bwd_u8_bf16(const uint8_t* x, float scale, const void* dp_grid, const void* idx, float* dw, float* db,
+                            void* workspace, size_t workspace_bytes, int N, int H, int W, int OCn, void* stream) {
+    return conv1_bwd_launch<uint8_t>(x, scale, dp_grid, idx, dw, db, workspace, workspace_bytes, N, H, W, OCn, stream);
 }
 
 }  // extern "C"

@@ -468,7 +468,11 @@ __global__ void pack_conv_weights_gen_kernel(const float* __restrict__ w, __nv_b
 
 // f32 NCHW [N][C][H][W] -> zero-haloed bf16 NHWC [N][H+2][W+2][Cp]; every element of the destination is written.
 // One thread per grid pixel: reads are coalesced along w, and a thread writes its pixel's own Cp*2 contiguous bytes.
-__global__ void pack_input_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp,
+__device__ __forceinline__ float in_val(const float* p, float) { return __ldg(p); }
+__device__ __forceinline__ float in_val(const uint8_t* p, float scale) { return (float)__ldg(p) * scale; }   // raw pixels: X / 255 done here
+
+template <typename XT>
+__global__ void pack_input_nhwc_kernel(const XT* __restrict__ x, float x_scale, __nv_bfloat16* __restrict__ xp,
                                        int N, int C, int H, int W, int Cp) {
     pdl_trigger();
     pdl_wait();
@@ -479,14 +483,14 @@ __global__ void pack_input_nhwc_kernel(const float* __restrict__ x, __nv_bfloat1
     const int hh = (int)((pix / Wp) % Hp);
     const int n = (int)(pix / ((long long)Wp * Hp));
     const bool interior = hh >= 1 && hh <= H && ww >= 1 && ww <= W;
-    const float* src = x + ((size_t)n * C * H + (hh - 1)) * W + (ww - 1);
+    const XT* src = x + ((size_t)n * C * H + (hh - 1)) * W + (ww - 1);
     uint4* dst = reinterpret_cast<uint4*>(xp) + pix * groups;
     for (int g = 0; g < groups; ++g) {
         float f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = g * 8 + j;
-            f[j] = (interior && c < C) ? __ldg(src + (size_t)c * H * W) : 0.f;
+            f[j] = (interior && c < C) ? in_val(src + (size_t)c * H * W, x_scale) : 0.f;
         }
         uint4 o;
         o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
@@ -572,8 +576,15 @@ int nm_tc_pack_input_nhwc_bf16(const float* x_nchw, void* x_pad, int N, int C, i
     NM_REQUIRE(x_nchw && x_pad, "null pointer");
     NM_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && Cp >= C && Cp % 8 == 0, "bad dimensions");
     const long long total = (long long)N * (H + 2) * (W + 2);
-    return nm::launch_pdl("pack_input_nhwc", pack_input_nhwc_kernel, dim3(nm_cdiv((size_t)total, 128)), dim3(128), 0, nm::S(stream),
-                          x_nchw, static_cast<__nv_bfloat16*>(x_pad), N, C, H, W, Cp);
+    return nm::launch_pdl("pack_input_nhwc", pack_input_nhwc_kernel<float>, dim3(nm_cdiv((size_t)total, 128)), dim3(128), 0, nm::S(stream),
+                          x_nchw, 1.f, static_cast<__nv_bfloat16*>(x_pad), N, C, H, W, Cp);
+}
+int nm_tc_pack_input_nhwc_u8_bf16(const uint8_t* x_nchw, float scale, void* x_pad, int N, int C, int H, int W, int Cp, void* stream) {
+    NM_REQUIRE(x_nchw && x_pad, "null pointer");
+    NM_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && Cp >= C && Cp % 8 == 0, "bad dimensions");
+    const long long total = (long long)N * (H + 2) * (W + 2);
+    return nm::launch_pdl("pack_input_nhwc_u8", pack_input_nhwc_kernel<uint8_t>, dim3(nm_cdiv((size_t)total, 128)), dim3(128), 0, nm::S(stream),
+                          x_nchw, scale, static_cast<__nv_bfloat16*>(x_pad), N, C, H, W, Cp);
 }
 
 int nm_tc_conv3x3_gen_bf16(const void* x_pad, const void* w_packed, const float* bias, const void* relu_mask, void* y_pad,

@@ -324,6 +324,17 @@ def as_device(x, dtype=np.float32) -> DeviceArray:
     return DeviceArray.from_numpy(np.asarray(x), dtype=dtype)
 
 
+def input_to_device(x) -> DeviceArray:
+    """Model inputs: float32 on the device, except raw ``uint8`` pixels, which stay uint8 (a quarter of the bytes over
+    PCIe) and are normalised on the device -- ``X.astype(np.float32) / 255.0`` of examples/test_Conv2D_MNIST.py:27."""
+    if isinstance(x, DeviceArray):
+        if x.dtype not in (np.dtype(np.float32), np.dtype(np.uint8)):
+            raise TypeError(f"expected a float32 or uint8 DeviceArray, got {x.dtype}")
+        return x
+    a = np.asarray(x)
+    return DeviceArray.from_numpy(a, dtype=np.uint8 if a.dtype == np.uint8 else np.float32)
+
+
 def is_array(x) -> bool:
     return isinstance(x, (np.ndarray, DeviceArray))
 

@@ -83,6 +83,13 @@ def same_padding(k: int):
     return ((k - 1) // 2, (k - 1) // 2) if k % 2 else (k // 2 - 1, k // 2)
 
 
+def u8_to_f32(x: DeviceArray, denom: float, holder=None, name="_xf"):
+    """float32(x) / denom on the device (the reference scripts' host-side `X.astype(np.float32) / 255.0`)."""
+    y = _buf(holder, name, x.shape)
+    lib.nm_u8_to_f32_div(x.p, y.p, x.size, float(denom), stream())
+    return y
+
+
 # ------------------------------------------------------------------ conv ----
 def conv2d_fprop(x: DeviceArray, w: DeviceArray, bias, pads, relu: bool, out=None, holder=None, name="_y"):
     n, c, h, wd = x.shape

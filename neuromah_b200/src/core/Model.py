@@ -28,8 +28,8 @@ from ...arena import ParamArena
 import ctypes as C
 
 from ..._lib import lib
-from ...device import (DeviceArray, PinnedBuffer, as_device, graph_capture, labels_to_device, new_event, new_stream,
-                       pinned_address, stream, synchronize)
+from ...device import (DeviceArray, PinnedBuffer, as_device, graph_capture, input_to_device, labels_to_device, new_event,
+                       new_stream, pinned_address, stream, synchronize)
 from ..layers.Input import Layer_Input
 from ..layers.Conv_wrapepr import Layer_Conv2D
 
@@ -47,6 +47,7 @@ class Model:
         self.arena = None
         self.comm = None                   # data-parallel communicator (neuromah_b200.parallel)
         self.epoch_end_accuracy = True     # Model.py:199-201: forward over the whole X after each epoch
+        self.uint8_denominator = 255.0     # uint8 inputs mean X / 255 (the example scripts' preprocessing, done on the device)
         self.device = device
 
     def add(self, layer):
@@ -112,6 +113,10 @@ class Model:
             self.plan = TcCnnPlan(self) if TcCnnPlan.match(self) or not TcStackPlan.match(self) else TcStackPlan(self)
         elif self.mode != "fp32":
             raise ValueError("mode must be None, 'fp32' or 'bf16'")
+        # raw uint8 pixel batches: normalised on the device by 1 / uint8_denominator (examples/test_Conv2D_MNIST.py:27);
+        # a tensor-core plan reads the bytes itself, the FP32-exact path converts them in Layer_Input
+        self.input_layer.keep_uint8 = self.plan is not None
+        self.input_layer.uint8_denominator = self.uint8_denominator
         if self.tensorMonitor:
             self.tensorMonitor.start_run(self)
 
@@ -212,7 +217,7 @@ class Model:
                 return out
         if self.plan is not None:
             gb = self.softmax_classifier_output.grad_batch
-            output = self.plan.forward(as_device(batch_X), labels, accum=self._accum,
+            output = self.plan.forward(input_to_device(batch_X), labels, accum=self._accum,
                                        inv_batch=None if gb is None else 1.0 / gb)
             fused = self._dp_fused_ok()
             self.plan.backward(gb, comm=None if fused else self.comm)
@@ -479,20 +484,21 @@ class _BatchFeeder:
         self.h2d_bytes = 0
         self._cache = cache
         if not self.stream:
-            self.X = as_device(X)
+            self.X = input_to_device(X)
             self.labels = labels_to_device(labels_host)
             return
         self.X = np.asarray(X)
-        if self.X.dtype != np.float32:
+        if self.X.dtype not in (np.dtype(np.float32), np.dtype(np.uint8)):     # uint8 pixels travel as bytes
             self.X = self.X.astype(np.float32)
+        dt = self.X.dtype
         self.labels_host = np.ascontiguousarray(labels_host, dtype=np.int32)
-        shape = (bs,) + self.X.shape[1:]
+        shape = (bs,) + self.X.shape[1:] + (str(dt),)
         # the two device slots, their pinned label staging, the copy stream and the events persist across train() calls
         # (same pointers => the CUDA graphs captured for them stay valid)
         res = None if cache is None else cache.get(shape)
         if res is None:
             ns = self.SLOTS
-            res = dict(dev=[DeviceArray(shape, np.float32) for _ in range(ns)],
+            res = dict(dev=[DeviceArray(shape[:-1], dt) for _ in range(ns)],
                        dev_lab=[DeviceArray((bs,), np.int32) for _ in range(ns)],
                        copy_stream=new_stream(), uploaded=[new_event() for _ in range(ns)],
                        consumed=[new_event() for _ in range(ns)], labels_ready=new_event(), pin_x=None,
@@ -553,7 +559,7 @@ class _BatchFeeder:
         addr = pinned_address(src)
         if addr is None:                              # pageable: stage through pinned memory
             if self.pin_x is None:
-                self.pin_x = self._res["pin_x"] = [PinnedBuffer((self.bs,) + self.X.shape[1:], np.float32)
+                self.pin_x = self._res["pin_x"] = [PinnedBuffer((self.bs,) + self.X.shape[1:], self.X.dtype)
                                                    for _ in range(self.SLOTS)]
                 if self.uploads >= self.SLOTS:
                     lib.nm_event_sync(self.uploaded[slot])

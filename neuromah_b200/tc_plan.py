@@ -158,7 +158,10 @@ class TcCnnPlan:
         s = stream()
         self.x = x
         self.pack_weights()          # master weights may have changed (optimizer, set_parameters, FedAvg)
-        _timed('tc_conv1_fwd_pool', lib.nm_tc_conv1_fwd_pool_bf16, x.p, self.w1e.p, self.act1_pad.p, self.idx1.p, B, 28, 28, 32, s)
+        if x.dtype == np.uint8:       # raw pixels: normalised by 1 / uint8_denominator inside the patch builder
+            _timed('tc_conv1_fwd_pool', lib.nm_tc_conv1_fwd_pool_u8_bf16, x.p, self._u8_scale(), self.w1e.p, self.act1_pad.p, self.idx1.p, B, 28, 28, 32, s)
+        else:
+            _timed('tc_conv1_fwd_pool', lib.nm_tc_conv1_fwd_pool_bf16, x.p, self.w1e.p, self.act1_pad.p, self.idx1.p, B, 28, 28, 32, s)
         _timed('tc_conv2_fprop_pool', lib.nm_tc_conv3x3_fprop_pool_bf16, self.act1_pad.p, self.w2f.p, self.act2.p, self.idx2.p, B, 14, 14, 32, 64, 0, s)
         lab = labels if labels is not None else self.dummy_labels
         _timed('tc_dense_softmax_ce', lib.nm_tc_dense_softmax_ce_bf16, self.act2.p, self.w3hl.p, self.de.biases.p, lab.p,
@@ -219,12 +222,19 @@ class TcCnnPlan:
                 lib.nm_stream_wait_event(s, self._ev_join)
             lo = self._first_conv_floats()
             comm.allreduce_async(self.model.arena.grads, lo, self.model.arena.total - lo)
-        _timed('tc_conv1_bwd', lib.nm_tc_conv1_bwd_bf16, self.x.p, self.dp1.p, self.idx1.p, self.c1.weight_gradients.p, self.c1.bias_gradients.p,
-                                 self.ws_c1.p, self.ws_c1.nbytes, B, 28, 28, 32, s)
+        if self.x.dtype == np.uint8:
+            _timed('tc_conv1_bwd', lib.nm_tc_conv1_bwd_u8_bf16, self.x.p, self._u8_scale(), self.dp1.p, self.idx1.p, self.c1.weight_gradients.p,
+                   self.c1.bias_gradients.p, self.ws_c1.p, self.ws_c1.nbytes, B, 28, 28, 32, s)
+        else:
+            _timed('tc_conv1_bwd', lib.nm_tc_conv1_bwd_bf16, self.x.p, self.dp1.p, self.idx1.p, self.c1.weight_gradients.p, self.c1.bias_gradients.p,
+                   self.ws_c1.p, self.ws_c1.nbytes, B, 28, 28, 32, s)
         if comm is not None:
             comm.allreduce_async(self.model.arena.grads, 0, self._first_conv_floats())
         if fork:
             lib.nm_stream_wait_event(s, self._ev_join)
+
+    def _u8_scale(self):
+        return float(np.float32(1.0) / np.float32(self.model.uint8_denominator))
 
     def _first_conv_floats(self):
         """Length (floats, padded) of the first conv's slice at the start of the arena slabs."""

@@ -161,7 +161,11 @@ class TcStackPlan:
         s = stream()
         self.x = x
         self.pack_weights()          # master weights may have changed (optimizer, set_parameters, FedAvg)
-        _timed('tc_pack_input', lib.nm_tc_pack_input_nhwc_bf16, x.p, self.x_pad.p, B, C, H, W, self.x_pad.shape[3], s)
+        if x.dtype == np.uint8:       # raw pixels: normalised by 1 / uint8_denominator while packing
+            _timed('tc_pack_input', lib.nm_tc_pack_input_nhwc_u8_bf16, x.p, float(np.float32(1.0) / np.float32(self.model.uint8_denominator)),
+                   self.x_pad.p, B, C, H, W, self.x_pad.shape[3], s)
+        else:
+            _timed('tc_pack_input', lib.nm_tc_pack_input_nhwc_bf16, x.p, self.x_pad.p, B, C, H, W, self.x_pad.shape[3], s)
         for st in self.steps:
             for e in st["convs"]:
                 wf = self.packed[id(e["layer"])][0]

@@ -129,3 +129,19 @@ def test_config4_stack_matches_the_survey_figures():
             fwd += f
             bwd += 2 * f
     assert abs(fwd / 1e6 - 305.61) < 0.01 and abs(bwd / 1e6 - 607.68) < 0.01 and abs((fwd + bwd) / 1e6 - 913.29) < 0.01
+
+
+def test_uint8_pixel_normalisation_is_exact_after_bf16_rounding():
+    """The bf16 plans read raw uint8 pixels and compute float(u) * (1/255) on the device (nm_tc_conv1_*_u8_bf16,
+    nm_tc_pack_input_nhwc_u8_bf16).  The reference's preprocessing is the float32 DIVISION u / 255.0
+    (examples/test_Conv2D_MNIST.py:27); the two differ in the last float32 bit for 126 of the 256 pixel values, but
+    never after rounding to the bf16 MMA operand -- so uint8 input is bit-identical to float32 input in that mode."""
+    u = np.arange(256, dtype=np.float32)
+    div = (u / np.float32(255.0)).astype(np.float32)
+    mul = (u * (np.float32(1.0) / np.float32(255.0))).astype(np.float32)
+
+    def bf16_rn(x):
+        i = x.view(np.uint32).astype(np.uint64)
+        return ((i + 0x7FFF + ((i >> 16) & 1)) >> 16).astype(np.uint16)
+    assert np.sum(div != mul) > 0                      # the float32 values do differ ...
+    np.testing.assert_array_equal(bf16_rn(div), bf16_rn(mul))      # ... the operands never do
