@@ -168,9 +168,11 @@ typedef struct nm_adam_state {
     long long iterations;
     double beta1_pow, beta2_pow;      /* beta^(iterations+1) */
     unsigned ticket, reserved;        /* last-block ticket of the fused step + advance launch (always left at 0) */
+    double base_lr_d, decay_d, beta1_d, beta2_d;   /* the host's float64 hyper-parameters: the bias corrections and the
+                                                      decayed rate are formed in double exactly as Adam.py:41-47, :94-95 */
 } nm_adam_state;
-int nm_adam_state_init(nm_adam_state* dev_state, float lr, float decay, float beta1,
-                       float beta2, float eps, long long iterations, void* stream);
+int nm_adam_state_init(nm_adam_state* dev_state, double lr, double decay, double beta1,
+                       double beta2, float eps, long long iterations, void* stream);
 int nm_adam_step_dev_f32(float* param, const float* grad, float* m, float* v, size_t n,
                          const nm_adam_state* dev_state, int n_apply, void* stream);
 int nm_adam_advance_f32(nm_adam_state* dev_state, void* stream);   /* post_update_params */
@@ -364,6 +366,15 @@ int nm_dp_set_timeout_ms(void* dp, unsigned ms);
 int nm_dp_allreduce_sum_f32(void* dp, float* buf, size_t n, void* stream);      /* in place, every rank gets the sum */
 int nm_dp_allreduce_adam_dev_f32(void* dp, float* param, float* grad, float* m, float* v, size_t n,
                                  nm_adam_state* dev_state, int n_apply, int advance, void* stream);   /* advance != 0: + nm_adam_advance_f32 */
+ /* Exchange overlapped with backward: nm_dp_push_f32 delivers chunks [chunk_lo, chunk_hi) of the gradient slab (chunk =
+ * nm_dp_chunk_floats() floats) to every peer as soon as their producers have been enqueued -- stores only, no waits, meant
+ * for a side stream behind each wgrad -- and nm_dp_collect_adam_dev_f32 is the fused kernel above told that chunks >=
+ * pushed_from_chunk are already on their way: it pushes the rest (the first layer's gradients), collects, sums in rank
+ * order and applies Adam.  All pushes of a step must precede its collect in stream / graph order. */
+int nm_dp_chunk_floats(void);
+int nm_dp_push_f32(void* dp, const float* grad, size_t n, int chunk_lo, int chunk_hi, void* stream);
+int nm_dp_collect_adam_dev_f32(void* dp, float* param, float* grad, float* m, float* v, size_t n,
+                               nm_adam_state* dev_state, int n_apply, int advance, int pushed_from_chunk, void* stream);
 int nm_dp_status(void* dp, int* timed_out, unsigned* steps_done);
 int nm_dp_destroy(void* dp);
 

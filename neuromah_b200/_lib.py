@@ -68,7 +68,7 @@ _SIGS = {
     "nm_softmax_ce_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "nm_cce_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp]),
     "nm_adam_step_f32": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _f, _i, _vp]),
-    "nm_adam_state_init": (_i, [_vp, _f, _f, _f, _f, _f, C.c_longlong, _vp]),
+    "nm_adam_state_init": (_i, [_vp, C.c_double, C.c_double, C.c_double, C.c_double, _f, C.c_longlong, _vp]),
     "nm_adam_step_dev_f32": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
     "nm_adam_advance_f32": (_i, [_vp, _vp]),
     "nm_adam_step_advance_dev_f32": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
@@ -126,11 +126,14 @@ _SIGS = {
     "nm_dp_set_timeout_ms": (_i, [_vp, C.c_uint]),
     "nm_dp_allreduce_sum_f32": (_i, [_vp, _vp, _sz, _vp]),
     "nm_dp_allreduce_adam_dev_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _i, _vp]),
+    "nm_dp_chunk_floats": (_i, []),
+    "nm_dp_push_f32": (_i, [_vp, _vp, _sz, _i, _i, _vp]),
+    "nm_dp_collect_adam_dev_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _i, _i, _vp]),
     "nm_dp_status": (_i, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_uint)]),
     "nm_dp_destroy": (_i, [_vp]),
 }
 
-_UNCHECKED = {"nm_last_error", "nm_version", "nm_conv2d_wgrad_f32_workspace", "nm_dense_wgrad_f32_workspace",
+_UNCHECKED = {"nm_last_error", "nm_version", "nm_dp_chunk_floats", "nm_conv2d_wgrad_f32_workspace", "nm_dense_wgrad_f32_workspace",
               "nm_tc_conv3x3_wgrad_workspace", "nm_tc_conv1_bwd_workspace", "nm_tc_dense_wgrad_workspace",
               "nm_tc_dense_softmax_ce_workspace", "nm_tc_dense_bwd_unpool_workspace", "nm_tc_conv3x3_bwd_workspace",
               "nm_tc_conv3x3_wgrad_gen_workspace"}

@@ -35,8 +35,8 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 // host (pow of the iteration count, Adam.py:94-95), not a running product: no drift between the paths.
 __device__ __forceinline__ void adam_state_advance(nm_adam_state* s) {
     s->iterations += 1;
-    s->beta1_pow = pow((double)s->beta1, (double)(s->iterations + 1));
-    s->beta2_pow = pow((double)s->beta2, (double)(s->iterations + 1));
+    s->beta1_pow = pow(s->beta1_d, (double)(s->iterations + 1));
+    s->beta2_pow = pow(s->beta2_d, (double)(s->iterations + 1));
     s->bc1 = (float)(1.0 - s->beta1_pow); s->bc2 = (float)(1.0 - s->beta2_pow);
-    if (s->decay != 0.f) s->lr = (float)((double)s->base_lr * (1.0 / (1.0 + (double)s->decay * (double)s->iterations)));
+    if (s->decay_d != 0.0) s->lr = (float)(s->base_lr_d * (1.0 / (1.0 + s->decay_d * (double)s->iterations)));
 }

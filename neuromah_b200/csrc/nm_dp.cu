@@ -66,12 +66,40 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
+// Early push: chunks [ch_lo, ch_hi) of the gradient slab go to every peer's mailbox as soon as their producers have run
+// (the backward pass launches this on a side stream behind each wgrad), so the exchange overlaps the rest of backward and
+// the final kernel below finds them delivered.  Same words, same tags, same slots as the in-kernel push; stores only, no waits.
+__global__ void __launch_bounds__(kThreads)
+dp_push_kernel(DpDev c, const float* __restrict__ g, size_t n, int ch_lo, int ch_hi) {
+    pdl_trigger();
+    pdl_wait();
+    const int tid = threadIdx.x;
+    const uint32_t step = *reinterpret_cast<volatile uint32_t*>(c.seq) + 1u;
+    const size_t par = (size_t)(step & 1u) * c.world;
+    const bool vec = (reinterpret_cast<uintptr_t>(g) & 7) == 0;
+    for (int ch = ch_lo + blockIdx.x; ch < ch_hi; ch += gridDim.x) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const size_t i = (size_t)ch * kChunk + h * (kChunk / 2) + (size_t)tid * 2;
+            float2 L = make_float2(0.f, 0.f);
+            if (vec && i + 2 <= n) L = *reinterpret_cast<const float2*>(g + i);
+            else {
+                if (i < n) L.x = g[i];
+                if (i + 1 < n) L.y = g[i + 1];
+            }
+            for (int d = 1; d < c.world; ++d)
+                st_words(c.mail[(c.rank + d) % c.world] + (par + c.rank) * c.slot + i, L.x, L.y, step);
+        }
+    }
+}
+
 // MODE 0: all-reduce only (gradient slab <- sum over ranks); MODE 1: + Adam on (p, m, v)
+// Chunks >= pushed_from were already delivered by dp_push_kernel in this step: they are only collected here.
 // A thread owns two pairs of parameters of its 1024-float chunk: floats {2t, 2t+1} and {512 + 2t, 512 + 2t + 1}.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 dp_allreduce_kernel(DpDev c, float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                    size_t n, nm_adam_state* ds, int n_apply, int advance) {
+                    size_t n, nm_adam_state* ds, int n_apply, int advance, int pushed_from) {
     pdl_trigger();
     pdl_wait();
     const int tid = threadIdx.x;
@@ -98,8 +126,8 @@ dp_allreduce_kernel(DpDev c, float* __restrict__ p, float* __restrict__ g, float
                 if (i + 1 < n) L[h].y = g[i + 1];
             }
         }
-        // 1. push to every peer (destinations staggered by rank)
-        for (int d = 1; d < c.world; ++d) {
+        // 1. push to every peer (destinations staggered by rank) -- unless dp_push_kernel already did
+        for (int d = 1; d < c.world && ch < pushed_from; ++d) {
             uint2* q = c.mail[(c.rank + d) % c.world] + (par + c.rank) * c.slot;
             st_words(q + idx[0], L[0].x, L[0].y, step);
             st_words(q + idx[1], L[1].x, L[1].y, step);
@@ -157,7 +185,8 @@ dp_allreduce_kernel(DpDev c, float* __restrict__ p, float* __restrict__ g, float
     }
 }
 
-int launch(Dp* d, int mode, float* p, float* g, float* m, float* v, size_t n, nm_adam_state* st, int n_apply, int advance, void* stream) {
+int launch(Dp* d, int mode, float* p, float* g, float* m, float* v, size_t n, nm_adam_state* st, int n_apply, int advance, void* stream,
+           int pushed_from = 0x7fffffff) {
     if (!d->connected) return nm::fail(NM_ERR_BAD_ARG, "%s%s", "nm_dp: not connected (call nm_dp_connect first)");
     if (n > d->max_floats) return nm::fail(NM_ERR_BAD_ARG, "%s%s", "nm_dp: slab larger than the mailbox slot");
     if (!n) return NM_OK;
@@ -168,9 +197,9 @@ int launch(Dp* d, int mode, float* p, float* g, float* m, float* v, size_t n, nm
     const dim3 grid(nchunks < sms ? nchunks : sms);               // all blocks resident: a waiting block never starves a pusher
     if (mode == 0)
         return nm::launch_pdl("dp_allreduce", dp_allreduce_kernel<0>, grid, dim3(kThreads), 0, nm::S(stream), d->dev,
-                              (float*)nullptr, g, (float*)nullptr, (float*)nullptr, n, (nm_adam_state*)nullptr, 0, 0);
+                              (float*)nullptr, g, (float*)nullptr, (float*)nullptr, n, (nm_adam_state*)nullptr, 0, 0, pushed_from);
     return nm::launch_pdl("dp_allreduce_adam", dp_allreduce_kernel<1>, grid, dim3(kThreads), 0, nm::S(stream), d->dev,
-                          p, g, m, v, n, st, n_apply, advance);
+                          p, g, m, v, n, st, n_apply, advance, pushed_from);
 }
 
 }  // namespace
@@ -245,6 +274,30 @@ int nm_dp_allreduce_adam_dev_f32(void* dp, float* param, float* grad, float* m, 
     NM_REQUIRE(dp && param && grad && m && v && dev_state, "null pointer");
     NM_REQUIRE(n_apply >= 1 && n > 0, "n_apply must be >= 1 and n > 0");
     return launch(static_cast<Dp*>(dp), 1, param, grad, m, v, n, dev_state, n_apply, advance, stream);
+}
+
+int nm_dp_chunk_floats(void) { return kChunk; }
+
+int nm_dp_push_f32(void* dp, const float* grad, size_t n, int chunk_lo, int chunk_hi, void* stream) {
+    NM_REQUIRE(dp && grad, "null pointer");
+    Dp* d = static_cast<Dp*>(dp);
+    if (!d->connected) return nm::fail(NM_ERR_BAD_ARG, "%s%s", "nm_dp: not connected (call nm_dp_connect first)");
+    if (n > d->max_floats) return nm::fail(NM_ERR_BAD_ARG, "%s%s", "nm_dp: slab larger than the mailbox slot");
+    const int nchunks = (int)((n + kChunk - 1) / kChunk);
+    NM_REQUIRE(chunk_lo >= 0 && chunk_lo <= chunk_hi && chunk_hi <= nchunks, "bad chunk range");
+    if (chunk_lo == chunk_hi || d->dev.world == 1) return NM_OK;
+    int dev = 0, sms = 0;
+    NM_CUDA(cudaGetDevice(&dev));
+    NM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = chunk_hi - chunk_lo < 2 * sms ? chunk_hi - chunk_lo : 2 * sms;
+    return nm::launch_pdl("dp_push", dp_push_kernel, dim3(blocks), dim3(kThreads), 0, nm::S(stream), d->dev, grad, n, chunk_lo, chunk_hi);
+}
+
+int nm_dp_collect_adam_dev_f32(void* dp, float* param, float* grad, float* m, float* v, size_t n,
+                               nm_adam_state* dev_state, int n_apply, int advance, int pushed_from_chunk, void* stream) {
+    NM_REQUIRE(dp && param && grad && m && v && dev_state, "null pointer");
+    NM_REQUIRE(n_apply >= 1 && n > 0 && pushed_from_chunk >= 0, "n_apply must be >= 1, n > 0, pushed_from_chunk >= 0");
+    return launch(static_cast<Dp*>(dp), 1, param, grad, m, v, n, dev_state, n_apply, advance, stream, pushed_from_chunk);
 }
 
 int nm_dp_status(void* dp, int* timed_out, unsigned* steps_done) {

@@ -210,13 +210,14 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
-__global__ void adam_state_init_kernel(nm_adam_state* s, float lr, float decay, float b1, float b2, float eps,
+__global__ void adam_state_init_kernel(nm_adam_state* s, double lr, double decay, double b1, double b2, float eps,
                                        long long it) {
     s->ticket = 0u; s->reserved = 0u;
-    s->base_lr = lr; s->decay = decay; s->beta1 = b1; s->beta2 = b2; s->eps = eps; s->iterations = it;
-    s->beta1_pow = pow((double)b1, (double)(it + 1)); s->beta2_pow = pow((double)b2, (double)(it + 1));
+    s->base_lr_d = lr; s->decay_d = decay; s->beta1_d = b1; s->beta2_d = b2;
+    s->base_lr = (float)lr; s->decay = (float)decay; s->beta1 = (float)b1; s->beta2 = (float)b2; s->eps = eps; s->iterations = it;
+    s->beta1_pow = pow(b1, (double)(it + 1)); s->beta2_pow = pow(b2, (double)(it + 1));
     s->bc1 = (float)(1.0 - s->beta1_pow); s->bc2 = (float)(1.0 - s->beta2_pow);
-    s->lr = decay != 0.f ? (float)((double)lr * (1.0 / (1.0 + (double)decay * (double)it))) : lr;
+    s->lr = decay != 0.0 ? (float)(lr * (1.0 / (1.0 + decay * (double)it))) : (float)lr;
 }
 
 // post_update_params (Adam.py:103-107) + next step's pre_update_params (:41-47), on the device
@@ -344,8 +345,8 @@ int nm_adam_step_f32(float* param, const float* grad, float* m, float* v, size_t
                           param, grad, m, v, n, hp, (nm_adam_state*)nullptr, n_apply, 0);
 }
 
-int nm_adam_state_init(nm_adam_state* dev_state, float lr, float decay, float beta1,
-                       float beta2, float eps, long long iterations, void* stream) {
+int nm_adam_state_init(nm_adam_state* dev_state, double lr, double decay, double beta1,
+                       double beta2, float eps, long long iterations, void* stream) {
     NM_REQUIRE(dev_state, "null pointer");
     adam_state_init_kernel<<<1, 1, 0, nm::S(stream)>>>(dev_state, lr, decay, beta1, beta2, eps, iterations);
     return nm::launched("adam_state_init");

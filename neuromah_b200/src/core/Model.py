@@ -172,9 +172,9 @@ class Model:
             try:
                 with graph_capture(stream()) as cap:
                     self.plan.forward(x, labels, accum=self._accum, inv_batch=None if gb is None else 1.0 / gb)
-                    self.plan.backward(gb, fork=self.graph_fork)
+                    self.plan.backward(gb, fork=self.graph_fork, dp=self.comm)
                     if self.comm is not None:
-                        opt.update_arena_dp(self.arena, self.comm, n_apply=n_apply)
+                        opt.update_arena_dp(self.arena, self.comm, n_apply=n_apply, pushed_from=self.plan.pushed_from)
                     else:
                         opt.update_arena_dev(self.arena, n_apply=n_apply)
             except Exception as e:
@@ -202,10 +202,10 @@ class Model:
         return (self.comm is not None and getattr(self.comm, "peer", None) is not None
                 and hasattr(self.optimizer, "update_arena_dp") and len(set(self._n_apply.values())) == 1)
 
-    def _dp_fused_step(self):
+    def _dp_fused_step(self, pushed_from=None):
         opt = self.optimizer
         opt.sync_device_state()
-        opt.update_arena_dp(self.arena, self.comm, n_apply=next(iter(set(self._n_apply.values()))))
+        opt.update_arena_dp(self.arena, self.comm, n_apply=next(iter(set(self._n_apply.values()))), pushed_from=pushed_from)
         opt.host_advance()
 
     def train_step(self, batch_X, batch_y):
@@ -220,9 +220,9 @@ class Model:
             output = self.plan.forward(input_to_device(batch_X), labels, accum=self._accum,
                                        inv_batch=None if gb is None else 1.0 / gb)
             fused = self._dp_fused_ok()
-            self.plan.backward(gb, comm=None if fused else self.comm)
+            self.plan.backward(gb, comm=None if fused else self.comm, dp=self.comm if fused else None)
             if fused:
-                self._dp_fused_step()
+                self._dp_fused_step(self.plan.pushed_from)
                 return output
             if self.comm is not None:
                 self.comm.wait()

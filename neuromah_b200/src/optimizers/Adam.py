@@ -77,7 +77,7 @@ class Optimizer_Adam:
         from ..._lib import lib
         from ...device import stream
         if getattr(self, "_dev_state", None) is None:
-            self._dev_state = DeviceArray.zeros((64,), np.uint8)          # sizeof(nm_adam_state) = 56
+            self._dev_state = DeviceArray.zeros((128,), np.uint8)         # sizeof(nm_adam_state) = 88
             self._dev_snapshot = None
         if self._dev_snapshot != self._host_snapshot():
             lib.nm_adam_state_init(self._dev_state.p, float(self.learning_rate), float(self.decay), float(self.beta_1),
@@ -92,13 +92,18 @@ class Optimizer_Adam:
         lib.nm_adam_step_advance_dev_f32(arena.params.p, arena.grads.p, arena.state[0].p, arena.state[1].p, arena.total,
                                          self._dev_state.p, n_apply, stream())
 
-    def update_arena_dp(self, arena, comm, n_apply=1):
+    def update_arena_dp(self, arena, comm, n_apply=1, pushed_from=None):
         """Data-parallel step: gradient sum over ranks (peer memory over NVLink) + Adam in ONE launch, then the
-        on-device advance.  ``arena.grads`` holds the summed gradient afterwards, as after an in-place all-reduce."""
+        on-device advance.  ``arena.grads`` holds the summed gradient afterwards, as after an in-place all-reduce.
+        ``pushed_from``: first slab chunk the backward pass already delivered to the peers (nm_dp_push_f32)."""
         from ..._lib import lib
         from ...device import stream
-        lib.nm_dp_allreduce_adam_dev_f32(comm.peer, arena.params.p, arena.grads.p, arena.state[0].p, arena.state[1].p,
-                                         arena.total, self._dev_state.p, n_apply, 1, stream())
+        if pushed_from is None:
+            lib.nm_dp_allreduce_adam_dev_f32(comm.peer, arena.params.p, arena.grads.p, arena.state[0].p, arena.state[1].p,
+                                             arena.total, self._dev_state.p, n_apply, 1, stream())
+        else:
+            lib.nm_dp_collect_adam_dev_f32(comm.peer, arena.params.p, arena.grads.p, arena.state[0].p, arena.state[1].p,
+                                           arena.total, self._dev_state.p, n_apply, 1, int(pushed_from), stream())
 
     def host_advance(self):
         """Host mirror of the on-device advance (keeps ``iterations`` / ``current_learning_rate`` readable)."""

@@ -178,13 +178,18 @@ class TcCnnPlan:
         self.model.softmax_classifier_output.dinputs = self.dlogits[0:B]
         return out
 
-    def backward(self, grad_batch=None, comm=None, fork=False):
+    def backward(self, grad_batch=None, comm=None, fork=False, dp=None):
         """``comm``: data-parallel communicator.  The gradient slab is all-reduced in two buckets on the communication
         stream: everything but the first conv's gradients as soon as conv2's wgrad has been enqueued (it then overlaps
         conv2 dgrad + the whole conv1 backward), the first conv's 320 floats after the last kernel.
         ``fork``: put the Dense wgrad on a side stream (a sibling branch when the step is captured into a CUDA graph): it
         only needs the head's outputs, so it fills the SMs that the unpool / conv backward kernels leave idle in their tails
-        instead of sitting on the critical path; the streams join before the optimizer."""
+        instead of sitting on the critical path; the streams join before the optimizer.
+        ``dp``: communicator with the peer-memory exchange (nm_dp_*): every gradient but the first conv's is PUSHED to the
+        peers as soon as conv2's wgrad has been reduced -- on the side branch when forked -- so the transfer overlaps the
+        whole conv1 backward and the fused collect + Adam kernel finds it delivered; ``self.pushed_from`` tells it which
+        slab chunks are already on their way."""
+        self.pushed_from = None
         B = self.x.shape[0]
         s = stream()
         scale = 1.0 / (B if grad_batch is None else grad_batch)
@@ -213,10 +218,14 @@ class TcCnnPlan:
             lib.nm_event_record(self._ev_fork2, s)
             lib.nm_stream_wait_event(sd, self._ev_fork2)
             lib.nm_tc_conv3x3_bwd_reduce_f32(self.ws.p, self.c2.weight_gradients.p, B, 14, 14, 32, 64, sd)
+            self._early_push(dp, sd)
             lib.nm_event_record(self._ev_join, sd)
         else:
             _timed('tc_conv2_bwd', lib.nm_tc_conv3x3_bwd_bf16, self.act1_pad.p, self.dy2_pad.p, self.w2d.p, self.c2.weight_gradients.p,
                    self.dp1.p, self.ws.p, self.ws.nbytes, B, 14, 14, 32, 64, s)
+            if dp is not None and fork:         # the Dense gradients were written on the side branch
+                lib.nm_stream_wait_event(s, self._ev_join)
+            self._early_push(dp, s)
         if comm is not None:
             if fork:        # the Dense gradients of this bucket were written on the side branch: join it first
                 lib.nm_stream_wait_event(s, self._ev_join)
@@ -232,6 +241,18 @@ class TcCnnPlan:
             comm.allreduce_async(self.model.arena.grads, 0, self._first_conv_floats())
         if fork:
             lib.nm_stream_wait_event(s, self._ev_join)
+
+    def _early_push(self, dp, st):
+        """Deliver every whole slab chunk above the first conv's gradients to the peers now (nm_dp_push_f32)."""
+        if dp is None or getattr(dp, "peer", None) is None:
+            return
+        arena = self.model.arena
+        chunk = lib.nm_dp_chunk_floats()
+        lo = (self._first_conv_floats() + chunk - 1) // chunk
+        hi = (arena.total + chunk - 1) // chunk
+        if lo < hi:
+            lib.nm_dp_push_f32(dp.peer, arena.grads.p, arena.total, lo, hi, st)
+            self.pushed_from = lo
 
     def _u8_scale(self):
         return float(np.float32(1.0) / np.float32(self.model.uint8_denominator))

@@ -93,6 +93,10 @@ class TcStackPlan:
             oc, ic = c.weights.shape[:2]
             ocp, icp = _rup(oc), _rup(ic)
             self.packed[id(c)] = (DeviceArray((ocp, 9, icp), np.uint16), DeviceArray((icp, 9, ocp), np.uint16), ocp, icp)
+        # side stream for the data-parallel early pushes (created here, never inside a CUDA-graph capture)
+        from .device import new_event, new_stream
+        self._side, self._ev_fork, self._ev_join = new_stream(), new_event(), new_event()
+        self.pushed_from = None
 
     # ------------------------------------------------------------------ buffers ----
     def _ensure(self, B, C, H, W):
@@ -188,10 +192,33 @@ class TcStackPlan:
         self.model.softmax_classifier_output.dinputs = self.dlogits[0:B]
         return out
 
-    def backward(self, grad_batch=None, comm=None, fork=False):
-        """``comm``: data-parallel communicator -- the gradient slab is all-reduced after the last kernel.
-        ``fork`` is accepted for interface parity with TcCnnPlan (the chain is not forked here)."""
+    def _push_ready(self, dp, layer, hi_chunk):
+        """All gradients at slab offsets >= ``layer``'s are final: deliver the whole chunks among them that have not been
+        pushed yet to the peers, on the side stream (nm_dp_push_f32: stores over NVLink, no waits), so the exchange
+        overlaps the rest of the backward pass.  Returns the new lower bound of the pushed range."""
+        arena = self.model.arena
+        chunk = lib.nm_dp_chunk_floats()
+        off = min(o for (l, _, o, _, _) in arena.table if l is layer)
+        lo = (off + chunk - 1) // chunk
+        if lo >= hi_chunk:
+            return hi_chunk
+        s = stream()
+        lib.nm_event_record(self._ev_fork, s)
+        lib.nm_stream_wait_event(self._side, self._ev_fork)
+        lib.nm_dp_push_f32(dp.peer, arena.grads.p, arena.total, lo, hi_chunk, self._side)
+        return lo
+
+    def backward(self, grad_batch=None, comm=None, fork=False, dp=None):
+        """``comm``: data-parallel communicator (NCCL path) -- the gradient slab is all-reduced after the last kernel.
+        ``dp``: communicator with the peer-memory exchange: each layer's gradients are pushed to the peers right behind
+        its wgrad (``_push_ready``); ``self.pushed_from`` tells the fused collect + Adam kernel what is left to push.
+        ``fork`` is accepted for interface parity with TcCnnPlan (the compute chain is not forked here)."""
         B = self.x.shape[0]
+        peer = dp is not None and getattr(dp, "peer", None) is not None
+        self.pushed_from = None
+        if peer:
+            chunk = lib.nm_dp_chunk_floats()
+            total_chunks = hi_chunk = (self.model.arena.total + chunk - 1) // chunk
         s = stream()
         scale = 1.0 / (B if grad_batch is None else grad_batch)
         if not getattr(self, "dl_hilo_valid", False):      # dlogits were written by the public-API backward
@@ -200,6 +227,8 @@ class TcStackPlan:
         _timed('tc_dense_wgrad', lib.nm_tc_dense_wgrad_bf16, last["pooled"].p, self.dl_hilo.p, self.dlogits.p, self.de.weights.p,
                self.de.dweights.p, self.de.dbiases.p, self.ws_dw.p, self.ws_dw.nbytes, B, self.K, self.n_out, self.HW, self.Cl,
                float(scale), float(self.de.weight_regularizer_l1), float(self.de.weight_regularizer_l2), s)
+        if peer:
+            hi_chunk = self._push_ready(dp, self.de, hi_chunk)
         _timed('tc_dense_dgrad', lib.nm_tc_dense_dgrad_bf16, self.dlogits.p, self.w3p.p, last["dpool"].p, B, self.K, self.n_out, s)
         first = self.convs[0]
         for bi in range(len(self.steps) - 1, -1, -1):
@@ -216,6 +245,8 @@ class TcStackPlan:
                        c.bias_gradients.p, self.ws.p, self.ws.nbytes, B, e["h"], e["w"], ic, oc, e["icp"], e["ocp"], s)
                 if c is first:
                     continue                                # no consumer for the first layer's input gradient
+                if peer:
+                    hi_chunk = self._push_ready(dp, c, hi_chunk)
                 wd = self.packed[id(c)][1]
                 if j > 0:       # input = the previous conv's post-ReLU output: dgrad + its ReLU backward -> its dY
                     dst, mask = cs[j - 1]["dy"], cs[j - 1]["act"]
@@ -223,5 +254,9 @@ class TcStackPlan:
                     dst, mask = self.steps[bi - 1]["dpool"], None
                 _timed('tc_conv_gen_dgrad', lib.nm_tc_conv3x3_gen_bf16, e["dy"].p, wd.p, None, mask.p if mask is not None else None,
                        dst.p, B, e["h"], e["w"], e["ocp"], e["icp"], 0, s)
+        if peer and hi_chunk < total_chunks:
+            lib.nm_event_record(self._ev_join, self._side)
+            lib.nm_stream_wait_event(s, self._ev_join)
+            self.pushed_from = hi_chunk
         if comm is not None:
             comm.allreduce_async(self.model.arena.grads, 0, self.model.arena.total)

@@ -13,7 +13,7 @@ comm = parallel.Communicator(rank, world)
 n = 50186
 assert comm.enable_peer(n, required=True)
 p, g, m, v = (device.DeviceArray.zeros((n,)) for _ in range(4))
-st = device.DeviceArray.zeros((64,), np.uint8)
+st = device.DeviceArray.zeros((128,), np.uint8)
 lib.nm_adam_state_init(st.p, 1e-3, 0.0, 0.9, 0.999, 1e-7, C.c_longlong(0), device.stream())
 s = device.stream()
 e0, e1 = device.new_event(), device.new_event()

@@ -26,9 +26,9 @@ def test_world1_fused_step_equals_adam_kernel_bitwise(n):
     device.init(0)
     rng = np.random.default_rng(n)
     p0 = rng.standard_normal(n).astype(np.float32)
-    st = device.DeviceArray.zeros((64,), np.uint8)
+    st = device.DeviceArray.zeros((128,), np.uint8)
     lib.nm_adam_state_init(st.p, 1e-3, 1e-4, 0.9, 0.999, 1e-7, C.c_longlong(0), device.stream())
-    st2 = device.DeviceArray.zeros((64,), np.uint8)
+    st2 = device.DeviceArray.zeros((128,), np.uint8)
     lib.nm_adam_state_init(st2.p, 1e-3, 1e-4, 0.9, 0.999, 1e-7, C.c_longlong(0), device.stream())
     a = [device.DeviceArray.from_numpy(p0), None, device.DeviceArray.zeros((n,)), device.DeviceArray.zeros((n,))]
     b = [device.DeviceArray.from_numpy(p0), None, device.DeviceArray.zeros((n,)), device.DeviceArray.zeros((n,))]
