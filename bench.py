@@ -1,56 +1,51 @@
 #!/usr/bin/env python
-"""bench.py -- Conv2D-MNIST-CNN training throughput on N B200s (BASELINE.json metric).
+"""bench.py -- training throughput of the Neuromah hot path on N B200s (BASELINE.json metric).
 
-    python bench.py --gpus 1 --steps 20 --warmup 5
+    python bench.py --gpus 1 --steps 20 --warmup 5                         # configs[1]: MNIST CNN, batch 4096 per GPU
+    python bench.py --workload vgg --steps 20 --warmup 5                   # configs[3]: VGG-style stack, batch 1024 per GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference --gpus 1 --steps K --warmup W     # CPU arm (oracle port)
+    python bench.py --impl reference --gpus 1 --steps K --warmup W         # CPU arm (the reference's NumPy path)
 
 A "step" is one pass of the hot path over one batch: forward, softmax-CE loss sums, backward,
-(gradient-slab all-reduce when N > 1), Adam applied twice per layer.  Workload =
-BASELINE.json configs[1]: the MNIST CNN of examples/test_Conv2D_MNIST.py:47-53 at batch 4096
-per GPU (weak scaling: global batch 4096*N), synthetic MNIST-shaped data, random-init weights.
+(gradient exchange when N > 1), Adam applied twice per layer.  Workloads:
+  mnist (default) = BASELINE.json configs[1]: the CNN of examples/test_Conv2D_MNIST.py:47-53 at batch 4096 per GPU
+  vgg             = BASELINE.json configs[3]: C64 C64 P C128 C128 P C256 C256 P FC10 on 32x32x3 inputs, 1024 per GPU
+weak scaling (global batch = per-GPU batch x N), synthetic data, random-init weights.
 
-One JSON line on stdout (rank 0).  `value` is the device-resident throughput (inputs already in
-HBM), `e2e` the same metric through the public API (Model.train) from page-locked HOST buffers
-with the per-step host->device copies and a per-step device->host read of the running loss
-inside the timed region.  `roofline` describes the dominant kernel (CUDA events on the launch
-stream, inside the timed region), `cpu_baseline` the oracle port timed on this box's host cores.
+One JSON line on stdout (rank 0):
+  value        device-resident throughput (inputs already in HBM), K graph-replayed steps between two CUDA events
+  e2e          the same metric through the public API (Model.train(..., stream_batches=True)) from page-locked HOST
+               buffers: per-step host->device copy of the batch (raw uint8 pixels, normalised on the device -- the
+               example scripts' `X.astype(float32) / 255`) and a per-step device->host read of the running loss sums
+  roofline     the dominant kernel (CUDA events on the launch stream in a second timed region) against the measured peak
+  parity       correctness AT THIS CONFIGURATION, checked after the timed regions: every rank's parameters bit-identical,
+               and the data-parallel step equal to a single-GPU run over the same global batch in virtual shards
+  fp32_exact   (N = 1) the FP32-exact mode's throughput on the same workload
+  cpu_baseline (N = 1) the reference's CPU path timed on this box's host cores on a bounded sample
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
 import time
+import zlib
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "train samples/sec (Conv2D MNIST CNN)"
 UNIT = "samples/s"
-BATCH = 4096            # per GPU (BASELINE.json configs[1])
-WORKLOAD = ("MNIST CNN (Conv3x3x32-ReLU-Pool2-Conv3x3x64-ReLU-Pool2-Dense10-Softmax), softmax-CE, "
-            "Adam x2 per layer (reference quirk Q1)")
-REF_SAMPLE = 512        # CPU arm: bounded sample of the batch per step
-REF_BUDGET = 100_000    # ... and of the whole --impl reference run: (steps + warmup) * sample <= this many images (~1.5 min on the GPU box's host)
-CONV2_FLOPS = lambda b: 2.0 * b * 64 * 32 * 9 * 14 * 14      # fprop = dgrad = wgrad  # noqa: E731
-CONV1_FLOPS = lambda b: 2.0 * b * 32 * 1 * 9 * 28 * 28       # noqa: E731
-STEP_FLOPS = lambda b: b * 22.767e6                           # BASELINE.md section 3  # noqa: E731
 
-
-def peaks():
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        p = json.load(open(path))
-        return {"hbm_gbs": p["hbm_gbs"], "tflops": p["bf16_tflops_sustained"], "tflops_burst": p["bf16_tflops"],
-                "source": "measured"}
-    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "source": "fallback"}
+# ----------------------------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------------------------
 
 
 def cnn_spec_and_params(seed=0):
@@ -66,32 +61,95 @@ def cnn_spec_and_params(seed=0):
         {"kind": "dense", "n_in": 64 * 7 * 7, "n_out": 10, "relu": False},
         {"kind": "softmax"},
     ]
+    return spec, _init(spec, seed, "random_normal")
+
+
+def vgg_spec_and_params(seed=0):
+    """BASELINE.json configs[3] as SURVEY.md 8(d) defines it: all 3x3 'same' + ReLU, He init (Initializer.py:117-128)."""
+    spec, ic = [], 3
+    for oc in (64, 128, 256):
+        spec += [{"kind": "conv", "ic": ic, "oc": oc, "k": 3, "padding": "same", "relu": True},
+                 {"kind": "conv", "ic": oc, "oc": oc, "k": 3, "padding": "same", "relu": True},
+                 {"kind": "pool", "size": 2, "stride": 2, "padding": "valid"}]
+        ic = oc
+    spec += [{"kind": "flatten"}, {"kind": "dense", "n_in": 256 * 4 * 4, "n_out": 10, "relu": False}, {"kind": "softmax"}]
+    return spec, _init(spec, seed, "he")
+
+
+def _init(spec, seed, init):
     rng = np.random.RandomState(seed)
     params = []
     for L in spec:
         if L["kind"] == "conv":
-            params.append({"weights": rng.randn(L["oc"], L["ic"], L["k"], L["k"]) * 0.01, "biases": np.zeros((L["oc"], 1))})
+            shape, fan_in, b = (L["oc"], L["ic"], L["k"], L["k"]), L["ic"] * L["k"] * L["k"], np.zeros((L["oc"], 1))
         elif L["kind"] == "dense":
-            params.append({"weights": rng.randn(L["n_in"], L["n_out"]) * 0.01, "biases": np.zeros((1, L["n_out"]))})
+            shape, fan_in, b = (L["n_in"], L["n_out"]), L["n_in"], np.zeros((1, L["n_out"]))
         else:
             params.append(None)
-    return spec, params
+            continue
+        w = rng.normal(0, np.sqrt(2.0 / fan_in), size=shape) if init == "he" else rng.randn(*shape) * 0.01
+        params.append({"weights": w, "biases": b})
+    return params
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at batch 4096, from the committed `ncu --set full` capture
-NCU_TRAFFIC_SOURCE = "profiles/r01e_ncu_full_bf16_step.txt (ncu --set full --clock-control none, batch 4096)"
-NCU_TRAFFIC = {"tc_conv2_bwd": (201.40 + 45.78) * 1e6}
+WORKLOADS = {
+    "mnist": dict(metric="train samples/sec (Conv2D MNIST CNN)", batch=4096, shape=(1, 28, 28), make=cnn_spec_and_params,
+                  flops_per_sample=22.767e6,          # BASELINE.md section 3 (first-layer dgrad excluded)
+                  desc="MNIST CNN (Conv3x3x32-ReLU-Pool2-Conv3x3x64-ReLU-Pool2-Dense10-Softmax), softmax-CE, "
+                       "Adam x2 per layer (reference quirk Q1)",
+                  cpu_sample=4096, cpu_steps=5, ref_budget=200_000),
+    "vgg": dict(metric="train samples/sec (VGG-style Conv2D stack, CIFAR-10-shaped)", batch=1024, shape=(3, 32, 32),
+                make=vgg_spec_and_params, flops_per_sample=913.29e6,
+                desc="VGG-style stack C64 C64 P C128 C128 P C256 C256 P FC10 (3x3 'same' + ReLU, He init) on 32x32x3, "
+                     "softmax-CE, Adam x2 per layer (reference quirk Q1)",
+                cpu_sample=64, cpu_steps=4, ref_budget=4_000),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p["bf16_tflops_sustained"], "tflops_burst": p["bf16_tflops"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel from the committed `ncu --set full`
+    capture, as summarised in profiles/ncu_traffic.json by profiles/summarize.py (None when there is no capture)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        rec = json.load(open(path)).get(name)
+    except Exception:
+        return None, None
+    if not rec:
+        return None, None
+    return rec["dram_bytes"], f"{rec['source']} ({rec.get('note', 'ncu --set full --clock-control none')})"
+
+
+_TAG = re.compile(r"\[(\d+)->(\d+)@(\d+)\]")
 
 
 def kernel_work(name, b):
-    """(algorithmic FLOPs, algorithmic HBM bytes) of one launch of the named operator at batch b (DESIGN.md)."""
-    c2, c1 = CONV2_FLOPS(b), CONV1_FLOPS(b)
+    """(algorithmic FLOPs, algorithmic HBM bytes) of one launch of the named operator at batch b (DESIGN.md section 4)."""
+    c2 = 2.0 * b * 64 * 32 * 9 * 14 * 14          # conv fprop = dgrad = wgrad = 2 B OC IC kH kW oh ow (SURVEY 8d)
+    c1 = 2.0 * b * 32 * 1 * 9 * 28 * 28
+    m = _TAG.search(name)
+    if m:                                         # general conv kernels, tagged [ic->oc@h]
+        ic, oc, h = int(m.group(1)), int(m.group(2)), int(m.group(3))
+        icp, ocp, grid = -(-ic // 64) * 64, -(-oc // 64) * 64, (h + 2) * (h + 2)
+        flops = 2.0 * b * oc * ic * 9 * h * h
+        if "fprop" in name:
+            return flops, b * grid * 2.0 * (icp + ocp)
+        if "dgrad" in name:
+            return flops, b * grid * 2.0 * (ocp + 2 * icp)          # dY + ReLU mask of the layer below + dX
+        if "wgrad" in name:
+            return flops, b * grid * 2.0 * (icp + ocp)
     table = {
         # bf16 plan: activations bf16 NHWC with halo (256 grid pixels / image for the 14x14 maps)
         "tc_conv2_fprop_pool": (c2, b * (256 * 64 + 49 * 128 + 49 * 32) + 64 * 288 * 2),
         "tc_conv2_bwd": (2 * c2, b * (256 * 128 + 256 * 64 + 256 * 64) + 64 * 288 * 6),
-        "tc_conv2_dgrad": (c2, b * (256 * 128 + 256 * 64) + 64 * 288 * 2),
-        "tc_conv2_wgrad": (c2, b * (256 * 128 + 256 * 64) + 64 * 288 * 4),
         "tc_conv1_fwd_pool": (c1, b * (784 * 4 + 196 * 64 + 196 * 16)),
         "tc_conv1_bwd": (c1 / 4, b * (784 * 4 + 196 * 64 + 196 * 16)),
         "tc_dense_softmax_ce": (2.0 * b * 3136 * 10, b * (3136 * 2 + 100)),
@@ -234,41 +292,55 @@ def optimizer_bandwidth(n=1 << 28, reps=10):
     return out
 
 
-def cpu_arm(steps, warmup, sample):
-    """The reference's CPU path as the oracle port (NumPy + the reference's compiled max-pool), all host
-    threads NumPy's BLAS will use.  Returns (samples/s, ms_per_step, cores, description)."""
-    from oracle import ref_net
-    spec, params = cnn_spec_and_params()
-    net = ref_net.RefNet(spec, params)
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own NumPy path on this box's host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_arm(wl, steps, warmup, sample):
+    """(samples/s, ms_per_step, cores, kind, description).  Where the reference tree is present (the authoring container)
+    the UNMODIFIED reference Python is stepped exactly like Model.train (Model.py:154-174) through oracle/ref_shim.py;
+    on the GPU box (no /root/reference) the oracle port runs the same arithmetic.  Either way conv goes through the NumPy
+    im2col + GEMM restatement of CPU_kernels/Conv2D.cpp (needs Eigen: unbuildable) and max-pool through the reference's
+    own C++ (oracle/_ref) when it was built.  All host threads NumPy's BLAS will use."""
+    from oracle import ref_net, ref_shim
+    spec, params = wl["make"]()
     rng = np.random.default_rng(1)
-    x = rng.random((sample, 1, 28, 28), dtype=np.float32)
+    x = rng.random((sample,) + wl["shape"], dtype=np.float32)
     y = np.eye(10)[rng.integers(0, 10, sample)]
+    if ref_shim.available():
+        model = ref_shim.build_model(spec, params, optimizer="adam", lr=0.001)
+        step = lambda: ref_shim.train_step(model, x, y)      # noqa: E731
+        kind, what = "reference", "the UNMODIFIED reference Python (Model / Dense / ReLU / softmax-CE / Adam) via oracle/ref_shim.py"
+        pool = "the reference's compiled max-pool C++"
+    else:
+        net = ref_net.RefNet(spec, params)
+        step = lambda: net.step(x, y)                        # noqa: E731
+        kind, what = "port", "oracle port: reference Dense/ReLU/softmax-CE/Adam arithmetic in NumPy (float64)"
+        pool = "reference C++ max-pool (oracle/_ref)" if net.pool is not None else "NumPy max-pool"
     for _ in range(warmup):
-        net.step(x, y)
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        net.step(x, y)
+        step()
     dt = time.perf_counter() - t0
-    pool = "reference C++ max-pool (oracle/_ref)" if net.pool is not None else "NumPy max-pool"
-    desc = (f"{steps} steps x {sample} samples of the batch-{BATCH} MNIST-CNN step, oracle port: reference "
-            f"Dense/ReLU/softmax-CE/Adam arithmetic in NumPy (float64), conv = NumPy im2col+GEMM restatement "
-            f"(float32), {pool}")
-    return steps * sample / dt, 1e3 * dt / steps, os.cpu_count(), desc
+    desc = (f"{steps} steps x {sample} samples (the configured batch is {wl['batch']}) of the step of: {wl['desc']}; {what}, "
+            f"conv = NumPy im2col+GEMM restatement of Conv2D.cpp (float32), {pool}")
+    return steps * sample / dt, 1e3 * dt / steps, os.cpu_count(), kind, desc
 
 
-def run_reference(args, rank, world, out_fd):
+def run_reference(args, wl, rank, world, out_fd):
     if rank != 0:
         return
     warm = max(args.warmup, 1)
-    sample = max(16, min(REF_SAMPLE, REF_BUDGET // (args.steps + warm)))      # K steps must end within a few minutes
-    value, ms, cores, desc = cpu_arm(args.steps, warm, sample)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+    sample = max(16, min(wl["batch"], wl["ref_budget"] // (args.steps + warm)))      # K steps must end within a few minutes
+    value, ms, cores, kind, desc = cpu_arm(wl, args.steps, warm, sample)
+    line = {"metric": wl["metric"], "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
+            "config": {"workload": wl["desc"], "batch_per_gpu": args.batch or wl["batch"],
+                       "global_batch": (args.batch or wl["batch"]) * args.gpus,
                        "parallelism": f"dp{args.gpus}", "mode": "reference CPU path (rank 0's host cores only)",
                        "per_step_sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     _emit(line, out_fd)
@@ -278,6 +350,84 @@ def _emit(line, out_fd):
     os.write(out_fd, (json.dumps(line) + "\n").encode())
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# parity at the benchmarked configuration
+# ----------------------------------------------------------------------------------------------------------------
+def parity_check(wl, mode, B, rank, world, comm_factory, dist, peer_arg=None):
+    """One training step at the benchmarked batch on fresh models, after the timed regions:
+      * data parallel (this run's exchange) on rank r's shard of a seeded global batch of B x world samples;
+      * the same global batch on ONE GPU in `world` virtual shards with the global batch as divisor, the
+        gradient slabs summed on the host in float64, then the same Adam step.
+    Reports the per-tensor relative L2 error of the summed gradient, the parameter difference after the update and whether
+    every rank holds bit-identical parameters (crc32 of the slab gathered over the bootstrap group).  At N = 1 the global
+    batch is split into two virtual shards against the un-split step (linearity of the gradient in the batch)."""
+    from neuromah_b200 import device, parallel
+    spec, params = wl["make"](seed=3)
+    shards = max(world, 2)
+    b = B if world > 1 else B // 2
+    rng = np.random.default_rng(777)
+    x = rng.random((shards * b,) + wl["shape"], dtype=np.float32)
+    y = rng.integers(0, 10, shards * b).astype(np.int32)
+    lr = 1e-3
+    # (a) the run's own path
+    m_dp = build_model(spec, params, lr=lr, mode=mode)
+    comm = comm_factory()
+    parallel.attach(m_dp, comm, shards * b, peer=peer_arg)
+    lo, hi = (rank * b, (rank + 1) * b) if world > 1 else (0, shards * b)
+    m_dp.train_step(x[lo:hi], y[lo:hi])
+    device.synchronize()
+    g_dp = m_dp.arena.host_grads().astype(np.float64)
+    p_dp = m_dp.arena.host_params()
+    # (b) virtual shards on this GPU
+    m_v = build_model(spec, params, lr=lr, mode=mode)
+    parallel.set_global_batch(m_v, shards * b)
+    acc = np.zeros(m_v.arena.total, np.float64)
+    for r in range(shards):
+        out = m_v.forward(x[r * b:(r + 1) * b], training=True)
+        m_v.backward(out, y[r * b:(r + 1) * b])
+        acc += m_v.arena.grads.numpy()[:m_v.arena.total]
+    m_v.arena.grads.copy_from(acc.astype(np.float32))
+    m_v._optimizer_step()
+    device.synchronize()
+    g_v = np.concatenate([acc[o:o + s] for _, _, o, s, _ in m_v.arena.table])
+    p_v = m_v.arena.host_params()
+    off, per_tensor = 0, []
+    for (_, _, _, size, _) in m_dp.arena.table:
+        a, r_ = g_dp[off:off + size], g_v[off:off + size]
+        per_tensor.append(float(np.linalg.norm(a - r_) / max(np.linalg.norm(r_), 1e-30)))
+        off += size
+    crc = zlib.crc32(p_dp.tobytes())
+    identical = True
+    if dist is not None:
+        import torch
+        t = torch.tensor([crc], dtype=torch.int64, device="cuda")
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        identical = len({int(o.item()) for o in outs}) == 1
+    dp_abs = float(np.abs(p_dp - p_v).max())
+    init = _flat_init(m_v, params)
+    upd = float(np.linalg.norm((p_dp - p_v).astype(np.float64)) / max(np.linalg.norm((p_v - init).astype(np.float64)), 1e-30))
+    comm.close()
+    grad_tol = 2e-3 if mode == "bf16" else 1e-4          # same addends, different association (+ bf16 re-rounding of partials)
+    ok = identical and max(per_tensor) <= grad_tol and dp_abs <= 2 * (1 + 1.9 / np.sqrt(1.999)) * lr * 1.003
+    return {"ok": bool(ok), "replicas_bit_identical": bool(identical), "ranks": world, "virtual_shards": shards,
+            "batch_per_shard": b, "grad_rel_l2_max": max(per_tensor), "grad_rel_l2_tol": grad_tol,
+            "params_max_abs_diff": dp_abs, "update_rel_l2": upd,
+            "what": ("data-parallel step (this run's gradient exchange) vs one GPU stepping the same global batch in "
+                     "virtual shards" if world > 1 else "un-split step vs two virtual shards with the global batch as divisor")}
+
+
+def _flat_init(model, params):
+    """Initial parameters in arena table order (the update vector is measured against them)."""
+    flat = []
+    trainable = [l for l in model.layers if hasattr(l, "weights")]
+    ps = [p for p in params if p is not None]
+    for layer, p in zip(trainable, ps):
+        flat += [np.asarray(p["weights"], np.float32).ravel(), np.asarray(p["biases"], np.float32).ravel()]
+    return np.concatenate(flat)
+
+
+# ----------------------------------------------------------------------------------------------------------------
 def main():
     # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (e.g. NCCL's version banner, which goes
     # to stdout) is sent to stderr for the duration of the run
@@ -286,24 +436,32 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH, help="per-GPU batch (weak scaling) or global batch (--scaling strong)")
+    ap.add_argument("--workload", default="mnist", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (weak scaling) or global batch (--scaling strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, BASELINE.json): --batch samples per GPU; strong: --batch is the GLOBAL batch, split N ways")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"],
                     help="bf16 = fused tensor-core plan (tcgen05), fp32 = FP32-exact CUDA-core kernels")
+    ap.add_argument("--input", default="u8", choices=["u8", "f32"],
+                    help="host input of the end-to-end leg: raw uint8 pixels normalised on the device, or float32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fp32_exact / hbm_kernels / float32-input e2e sub-records")
     ap.add_argument("--dp", default="auto", choices=["auto", "peer", "nccl"],
                     help="N > 1: gradient exchange -- fused peer-memory all-reduce + Adam kernel, or NCCL all-reduce "
                          "(auto = peer memory when the GPUs can map each other)")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.steps is None:
+        args.steps = 1000 if args.workload == "mnist" else 100
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        return run_reference(args, rank, world, out_fd)
+        return run_reference(args, wl, rank, world, out_fd)
 
     import ctypes as C
     from neuromah_b200 import device, ops, parallel
@@ -319,11 +477,12 @@ def main():
     if rank == 0:                       # rank 0's GPU only: concurrent nvidia-smi pollers contend for the driver lock
         clocks.start()                  # early: nvidia-smi takes a while to produce its first sample
     device.init(local_rank)
-    W, K, B = max(args.warmup, 3), args.steps, args.batch
+    W, K, B = max(args.warmup, 3), args.steps, args.batch or wl["batch"]
     if args.scaling == "strong":
         if B % world:
             raise SystemExit(f"--scaling strong: global batch {B} is not divisible by {world} GPUs")
         B //= world
+    mode = None if args.mode == "fp32" else "bf16"
 
     def barrier():
         device.synchronize()
@@ -340,26 +499,28 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    spec, params = cnn_spec_and_params()
-    model = build_model(spec, params, mode=None if args.mode == "fp32" else "bf16")
+    spec, params = wl["make"]()
+    model = build_model(spec, params, mode=mode)
     comm = parallel.Communicator(rank, world)
-    parallel.attach(model, comm, B * world, peer=None if args.dp == "auto" else args.dp == "peer")
+    peer_arg = None if args.dp == "auto" else args.dp == "peer"
+    parallel.attach(model, comm, B * world, peer=peer_arg)
     model.epoch_end_accuracy = False     # time the K training steps only (no Model.py:199 sweep)
 
-    # synthetic data: up to 32 distinct host batches per rank in page-locked memory (cycled when K > 32)
-    n_host = min(max(K, 1), 32)
+    # synthetic data: up to 32 distinct host batches per rank in page-locked memory (cycled when K > 32).  Raw pixels are
+    # uint8; the float32 copy is the example scripts' host-side normalisation of the same pixels.
+    n_host = min(max(K, 1), 32 if args.workload == "mnist" else 8)
     rng = np.random.default_rng(100 + rank)
-    host_x = device.PinnedBuffer((n_host * B, 1, 28, 28), np.float32)
-    rng.random(out=host_x.array, dtype=np.float32)
+    host_u8 = device.PinnedBuffer((n_host * B,) + wl["shape"], np.uint8)
+    host_u8.array[...] = rng.integers(0, 256, host_u8.array.shape, dtype=np.uint8)
     labels = rng.integers(0, 10, n_host * B).astype(np.int32)
 
-    # ---------------- device-resident leg: inputs already in HBM --------------------------------
+    # ---------------- device-resident leg: inputs already in HBM (float32, as the reference's scripts hold them) ------
     n_dev = min(n_host, 8)
-    x_dev = device.DeviceArray.from_numpy(host_x.array[:n_dev * B])
+    x_dev = device.DeviceArray.from_numpy(host_u8.array[:n_dev * B].astype(np.float32) / 255.0)
     y_dev = device.DeviceArray.from_numpy(labels[:n_dev * B])
     x_b = [x_dev[i * B:(i + 1) * B] for i in range(n_dev)]      # stable views: the step's CUDA graph is keyed by pointer
     y_b = [y_dev[i * B:(i + 1) * B] for i in range(n_dev)]
-    for s in range(2 * n_dev):                                  # untimed priming: every batch once eagerly, once captured
+    for s in range(3 * n_dev):                                  # untimed priming: every batch eagerly, then captured
         model.train_step(x_b[s % n_dev], y_b[s % n_dev])
     for s in range(W):
         model.train_step(x_b[s % n_dev], y_b[s % n_dev])
@@ -379,6 +540,7 @@ def main():
     lib.nm_event_elapsed_ms(e0, e1, C.byref(ms))
     elapsed_ms = max_over_ranks(ms.value)
     value = K * B * world / (elapsed_ms / 1e3)
+    graphs = len(getattr(model, "_graphs", {}))
 
     clock_info = clocks.stop(t_wall0, t_wall1)   # before the end-to-end leg: a polling nvidia-smi stalls host-side syncs
 
@@ -396,32 +558,65 @@ def main():
     step2_ms = ms.value / K2
     kernel_ms = ops.timers.collect()
     ops.timers = None
+    del x_dev, x_b
 
     # ---------------- end-to-end leg: Model.train from pinned host memory ------------------------
     # K steps = (K // n_host) epochs over the n_host pinned batches + one partial pass; every step copies its
     # batch host->device and reads the running loss/accuracy sums back (16 bytes)
-    n_warm = min(max(W, 4), n_host)       # >= 4 steps: both feeder slots are seen twice, i.e. their step graphs are captured
-    model.train(host_x.array[:n_warm * B], labels[:n_warm * B], epochs=1, batch_size=B, verbose=0, stream_batches=True)
-    full, rem = divmod(K, n_host)
-    h2d = d2h = 0
-    barrier()
-    lib.nm_event_record(e0, device.stream())
-    if full:
-        model.train(host_x.array, labels, epochs=full, batch_size=B, verbose=0, stream_batches=True)
-        h2d += model.h2d_bytes; d2h += model.d2h_bytes
-    if rem:
-        model.train(host_x.array[:rem * B], labels[:rem * B], epochs=1, batch_size=B, verbose=0, stream_batches=True)
-        h2d += model.h2d_bytes; d2h += model.d2h_bytes
-    lib.nm_event_record(e1, device.stream())
-    device.synchronize()
-    barrier()
-    lib.nm_event_elapsed_ms(e0, e1, C.byref(ms))
-    e2e_ms = max_over_ranks(ms.value)
-    e2e = {"value": K * B * world / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms / K,
-           "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
-           "api": f"Model.train(X_pinned_host, y, batch_size={B}, stream_batches=True)"}
+    def e2e_leg(host_arr, steps):
+        n_warm = min(max(W, 4), n_host)   # >= 4 steps: both feeder slots are seen twice, i.e. their step graphs are captured
+        for _ in range(2):
+            model.train(host_arr[:n_warm * B], labels[:n_warm * B], epochs=1, batch_size=B, verbose=0, stream_batches=True)
+        full, rem = divmod(steps, n_host)
+        h2d = d2h = 0
+        barrier()
+        lib.nm_event_record(e0, device.stream())
+        if full:
+            model.train(host_arr, labels, epochs=full, batch_size=B, verbose=0, stream_batches=True)
+            h2d += model.h2d_bytes; d2h += model.d2h_bytes
+        if rem:
+            model.train(host_arr[:rem * B], labels[:rem * B], epochs=1, batch_size=B, verbose=0, stream_batches=True)
+            h2d += model.h2d_bytes; d2h += model.d2h_bytes
+        lib.nm_event_record(e1, device.stream())
+        device.synchronize()
+        barrier()
+        lib.nm_event_elapsed_ms(e0, e1, C.byref(ms))
+        t = max_over_ranks(ms.value)
+        return {"value": steps * B * world / (t / 1e3), "unit": UNIT, "ms_per_step": t / steps,
+                "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps}
+
+    host_f32 = None
+    if args.input == "f32" or (world == 1 and not args.no_extras):
+        host_f32 = device.PinnedBuffer(host_u8.array.shape, np.float32)
+        np.divide(host_u8.array, np.float32(255.0), out=host_f32.array, dtype=np.float32)
+    if args.input == "u8":
+        e2e = e2e_leg(host_u8.array, K)
+        e2e["input"] = "raw uint8 pixels in pinned host memory; X / 255 on the device (examples/test_Conv2D_MNIST.py:27)"
+    else:
+        e2e = e2e_leg(host_f32.array, K)
+        e2e["input"] = "float32 pixels in pinned host memory (normalised on the host)"
+    e2e["api"] = f"Model.train(X_pinned_host, y, batch_size={B}, stream_batches=True)"
+    if args.input == "u8" and host_f32 is not None:
+        alt = e2e_leg(host_f32.array, min(K, 200))
+        e2e["float32_host_input"] = {k: alt[k] for k in ("value", "ms_per_step", "h2d_bytes_per_step")}
+    del host_f32
+
+    # ---------------- parity at this configuration (every rank takes part) --------------------------------------
+    parity = None
+    if not args.no_parity:
+        def comm_factory():
+            c = parallel.Communicator(rank, world)
+            return c
+        try:
+            # the check attaches with the same exchange as the timed model
+            parity = parity_check(wl, mode, B, rank, world, comm_factory, dist, peer_arg)
+        except Exception as e:      # a failed check must not lose the measured line; it is reported as such
+            parity = {"ok": False, "error": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     # ---------------- roofline of the dominant kernel ------------------------------------------------
     pk = peaks()
@@ -429,46 +624,82 @@ def main():
     top = max(tot, key=tot.get)
     avg_ms = tot[top] / len(kernel_ms[top])
     flops, nbytes = kernel_work(top, B)
-    t_tensor, t_hbm = flops / (pk["tflops"] * 1e12), nbytes / (pk["hbm_gbs"] * 1e9)
+    # a kernel timed alone in a region far shorter than a second runs at burst clocks: the burst peak is the denominator
+    region_s = step2_ms * K2 / 1e3
+    tf_peak = pk["tflops_burst"] if region_s < 1.0 else pk["tflops"]
+    t_tensor, t_hbm = flops / (tf_peak * 1e12), nbytes / (pk["hbm_gbs"] * 1e9)
     if t_tensor >= t_hbm:
-        achieved, peak, unit, bound = flops / (avg_ms * 1e-3) / 1e12, pk["tflops"], "TFLOP/s", "tensor"
+        achieved, peak, unit, bound = flops / (avg_ms * 1e-3) / 1e12, tf_peak, "TFLOP/s", "tensor"
     else:
         achieved, peak, unit, bound = nbytes / (avg_ms * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s", "hbm"
     per_kernel = {}
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
         f, nb = kernel_work(k, B)
         ms_k = v / len(kernel_ms[k])
-        per_kernel[k] = {"ms": round(ms_k, 5), "tflops": round(f / (ms_k * 1e-3) / 1e12, 2),
-                         "gbs": round(nb / (ms_k * 1e-3) / 1e9, 1), "launches_per_step": len(kernel_ms[k]) / K2}
+        rec = {"ms": round(ms_k, 5), "launches_per_step": len(kernel_ms[k]) / K2}
+        if f:
+            rec["tflops"] = round(f / (ms_k * 1e-3) / 1e12, 2)
+            rec["frac_tensor"] = round(f / (ms_k * 1e-3) / 1e12 / tf_peak, 3)
+        if nb:
+            rec["gbs"] = round(nb / (ms_k * 1e-3) / 1e9, 1)
+            rec["frac_hbm"] = round(nb / (ms_k * 1e-3) / 1e9 / pk["hbm_gbs"], 3)
+        per_kernel[k] = rec
+    traffic, traffic_source = ncu_traffic(top)
     roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(top), "traffic_source": NCU_TRAFFIC_SOURCE if top in NCU_TRAFFIC else None,
-                "avg_ms": avg_ms,
-                "algorithmic_flops": flops, "algorithmic_bytes": nbytes,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
+                "avg_ms": avg_ms, "algorithmic_flops": flops, "algorithmic_bytes": nbytes,
                 "share_of_step": tot[top] / K2 / step2_ms,
-                "timing": f"CUDA events around every operator in a second timed region of {K2} steps ({step2_ms:.4f} ms/step; "
-                          "the headline region carries no per-kernel events)",
-                "peak_source": pk["source"] + (" bf16 dense sustained (cuBLAS)" if bound == "tensor" else " HBM copy"),
+                "timing": f"CUDA events around every operator in a second timed region of {K2} steps ({step2_ms:.4f} ms/step, "
+                          f"{region_s * 1e3:.1f} ms in all; the headline region carries no per-kernel events)",
+                "peak_source": pk["source"] + ((" bf16 dense burst (cuBLAS)" if region_s < 1.0 else " bf16 dense sustained (cuBLAS)")
+                                               if bound == "tensor" else " HBM copy"),
                 "kernels": per_kernel}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+    line = {"metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
+            "config": {"workload": wl["desc"],
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "gradient_exchange": ("none (1 GPU)" if world == 1 else
-                                             "fused all-reduce + Adam kernel over NVLink peer memory (nm_dp_*)"
-                                             if comm.peer is not None else "NCCL all-reduce, two buckets on a side stream"),
+                                             "gradient slab pushed over NVLink peer memory behind each wgrad (overlapping the rest of "
+                                             "backward) + fused collect / rank-ordered sum / Adam kernel (nm_dp_*)"
+                                             if comm.peer is not None else "NCCL all-reduce, buckets on a side stream"),
                        "mode": "bf16 tensor-core plan (bf16 operands, fp32 accumulate, fp32 master weights)"
-                               if args.mode == "bf16" else "fp32_exact", "step_tflops": STEP_FLOPS(B * world) / (elapsed_ms / K * 1e-3) / 1e12,
+                               if args.mode == "bf16" else "fp32_exact",
+                       "step_tflops": wl["flops_per_sample"] * B * world / (elapsed_ms / K * 1e-3) / 1e12,
+                       "cuda_graphs": graphs,
                        "l2": "inputs cycle over 8 distinct batches; the per-step activation working set "
                              "(>1 GB) is far larger than the 126 MB L2, so no explicit flush is needed"},
             "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
-    if world == 1:
+    if parity is not None:
+        line["parity"] = parity
+    if world == 1 and not args.no_extras:
+        # FP32-exact mode (the mode that meets rtol 1e-4 / atol 1e-5 against the NumPy path) on the same workload
+        m32 = build_model(spec, params, mode=None)
+        m32.epoch_end_accuracy = False
+        n32 = 2
+        x32 = device.DeviceArray.from_numpy(host_u8.array[:n32 * B].astype(np.float32) / 255.0)
+        y32 = device.DeviceArray.from_numpy(labels[:n32 * B])
+        for s in range(3):
+            m32.train_step(x32[(s % n32) * B:(s % n32 + 1) * B], y32[(s % n32) * B:(s % n32 + 1) * B])
+        k32 = 10 if args.workload == "mnist" else 4
+        lib.nm_event_record(e0, device.stream())
+        for s in range(k32):
+            m32.train_step(x32[(s % n32) * B:(s % n32 + 1) * B], y32[(s % n32) * B:(s % n32 + 1) * B])
+        lib.nm_event_record(e1, device.stream())
+        device.synchronize()
+        lib.nm_event_elapsed_ms(e0, e1, C.byref(ms))
+        line["fp32_exact"] = {"value": k32 * B / (ms.value / 1e3), "unit": UNIT, "ms_per_step": ms.value / k32, "steps": k32,
+                              "step_tflops": wl["flops_per_sample"] * B / (ms.value / k32 * 1e-3) / 1e12,
+                              "mode": "FP32-exact CUDA-core kernels, reference layouts (Model.finalize()): rtol 1e-4 / atol 1e-5 "
+                                      "against the NumPy path (tests/test_gpu_model.py)"}
+        del m32, x32
         line["hbm_kernels"] = optimizer_bandwidth()
     if world == 1 and not args.no_cpu_baseline:
-        v, cms, cores, desc = cpu_arm(6, 1, REF_SAMPLE)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        v, cms, cores, kind, desc = cpu_arm(wl, wl["cpu_steps"], 1, wl["cpu_sample"])
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
     _emit(line, out_fd)
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -120,7 +120,8 @@ class TcStackPlan:
                 _, _, ocp, icp = self.packed[id(c)]
                 act = z((B, h + 2, w + 2, ocp), np.uint16)
                 dy = z((B, h + 2, w + 2, ocp), np.uint16)
-                entries.append(dict(layer=c, inp=cur, act=act, dy=dy, h=h, w=w, ocp=ocp, icp=icp))
+                entries.append(dict(layer=c, inp=cur, act=act, dy=dy, h=h, w=w, ocp=ocp, icp=icp,
+                                    oc=c.weights.shape[0], ic=c.weights.shape[1]))
                 ws = max(ws, lib.nm_tc_conv3x3_wgrad_gen_workspace(B, h, w, c.weights.shape[1], icp, ocp))
                 cur = act
             last = bi == len(self.blocks) - 1
@@ -173,7 +174,7 @@ class TcStackPlan:
         for st in self.steps:
             for e in st["convs"]:
                 wf = self.packed[id(e["layer"])][0]
-                _timed('tc_conv_gen_fprop', lib.nm_tc_conv3x3_gen_bf16, e["inp"].p, wf.p, None, None, e["act"].p,
+                _timed(f"tc_conv_gen_fprop[{e['ic']}->{e['oc']}@{e['h']}]", lib.nm_tc_conv3x3_gen_bf16, e["inp"].p, wf.p, None, None, e["act"].p,
                        B, e["h"], e["w"], e["icp"], e["ocp"], 1, s)
                 e["layer"].output = Bf16Activation(e["act"], B, 1)
             _timed('tc_maxpool_fwd', lib.nm_tc_maxpool2x2_fwd_bf16, st["convs"][-1]["act"].p, st["pooled"].p, st["idx"].p,
@@ -241,7 +242,7 @@ class TcStackPlan:
                 e = cs[j]
                 c = e["layer"]
                 oc, ic = c.weights.shape[:2]
-                _timed('tc_conv_gen_wgrad', lib.nm_tc_conv3x3_wgrad_gen_bf16, e["inp"].p, e["dy"].p, c.weight_gradients.p,
+                _timed(f"tc_conv_gen_wgrad[{ic}->{oc}@{e['h']}]", lib.nm_tc_conv3x3_wgrad_gen_bf16, e["inp"].p, e["dy"].p, c.weight_gradients.p,
                        c.bias_gradients.p, self.ws.p, self.ws.nbytes, B, e["h"], e["w"], ic, oc, e["icp"], e["ocp"], s)
                 if c is first:
                     continue                                # no consumer for the first layer's input gradient
@@ -252,7 +253,7 @@ class TcStackPlan:
                     dst, mask = cs[j - 1]["dy"], cs[j - 1]["act"]
                 else:           # input = the previous block's pooled tensor: plain dgrad -> its dpool (haloed)
                     dst, mask = self.steps[bi - 1]["dpool"], None
-                _timed('tc_conv_gen_dgrad', lib.nm_tc_conv3x3_gen_bf16, e["dy"].p, wd.p, None, mask.p if mask is not None else None,
+                _timed(f"tc_conv_gen_dgrad[{ic}->{oc}@{e['h']}]", lib.nm_tc_conv3x3_gen_bf16, e["dy"].p, wd.p, None, mask.p if mask is not None else None,
                        dst.p, B, e["h"], e["w"], e["ocp"], e["icp"], 0, s)
         if peer and hi_chunk < total_chunks:
             lib.nm_event_record(self._ev_join, self._side)
