@@ -104,6 +104,10 @@ class Model:
         if hasattr(self.optimizer, "bind_arena"):
             self.optimizer.bind_arena(self.arena)
         self._accum = DeviceArray.zeros((2,), np.float64)        # {sum of losses, #correct}
+        # per-step read-back of the running sums (streamed training): a 16-byte device->host copy that depends only on the
+        # forward pass, issued on its own stream -- a sibling branch of the backward pass when the step is a CUDA graph
+        self._step_readback = None                               # PinnedBuffer while Model.train streams batches
+        self._rb_stream, self._rb_fork, self._rb_join = new_stream(), new_event(), new_event()
         self.mode = mode or "fp32"
         self.plan = None
         if self.mode == "bf16":
@@ -154,7 +158,9 @@ class Model:
         opt = self.optimizer
         # plan.generation changes whenever the plan re-allocates its buffers (a larger batch): graphs captured before
         # that hold the old device pointers and must never be replayed
-        key = (x.ptr, labels.ptr, x.shape[0], self.softmax_classifier_output.grad_batch, getattr(self.plan, "generation", 0))
+        rb = self._step_readback
+        key = (x.ptr, labels.ptr, x.shape[0], self.softmax_classifier_output.grad_batch, getattr(self.plan, "generation", 0),
+               None if rb is None else rb.ptr)
         graphs = self.__dict__.setdefault("_graphs", {})
         seen = self.__dict__.setdefault("_graph_seen", set())
         g = graphs.get(key)
@@ -172,11 +178,13 @@ class Model:
             try:
                 with graph_capture(stream()) as cap:
                     self.plan.forward(x, labels, accum=self._accum, inv_batch=None if gb is None else 1.0 / gb)
+                    self._readback_fork()
                     self.plan.backward(gb, fork=self.graph_fork, dp=self.comm)
                     if self.comm is not None:
                         opt.update_arena_dp(self.arena, self.comm, n_apply=n_apply, pushed_from=self.plan.pushed_from)
                     else:
                         opt.update_arena_dev(self.arena, n_apply=n_apply)
+                    self._readback_join()
             except Exception as e:
                 # nothing of the body has executed: drop graph replay for this model and run the step eagerly
                 import warnings
@@ -188,6 +196,19 @@ class Model:
         lib.nm_graph_launch(g, stream())
         opt.host_advance()
         return self.plan.probs[0:x.shape[0]]
+
+    def _readback_fork(self):
+        """Streamed training: copy the running {loss sum, #correct} to pinned host memory as soon as the forward pass has
+        updated them, on the read-back stream (captured: a sibling branch of the backward chain)."""
+        if self._step_readback is not None:
+            lib.nm_event_record(self._rb_fork, stream())
+            lib.nm_stream_wait_event(self._rb_stream, self._rb_fork)
+            lib.nm_d2h(C.c_void_p(self._step_readback.ptr), self._accum.p, 16, self._rb_stream)
+            lib.nm_event_record(self._rb_join, self._rb_stream)
+
+    def _readback_join(self):
+        if self._step_readback is not None:
+            lib.nm_stream_wait_event(stream(), self._rb_join)
 
     def _graph_capable(self):
         opt = self.optimizer
@@ -219,23 +240,28 @@ class Model:
             gb = self.softmax_classifier_output.grad_batch
             output = self.plan.forward(input_to_device(batch_X), labels, accum=self._accum,
                                        inv_batch=None if gb is None else 1.0 / gb)
+            self._readback_fork()
             fused = self._dp_fused_ok()
             self.plan.backward(gb, comm=None if fused else self.comm, dp=self.comm if fused else None)
             if fused:
                 self._dp_fused_step(self.plan.pushed_from)
+                self._readback_join()
                 return output
             if self.comm is not None:
                 self.comm.wait()
         else:
             output = self.forward(batch_X, training=True)
             self._device_loss_acc(output, labels)
+            self._readback_fork()
             self.backward(output, labels)
             if self._dp_fused_ok():
                 self._dp_fused_step()
+                self._readback_join()
                 return output
             if self.comm is not None:
                 self.comm.allreduce_grads(self.arena)
         self._optimizer_step()
+        self._readback_join()
         return output
 
     def _fast_path_ok(self):
@@ -259,7 +285,10 @@ class Model:
                                        validation_data=validation_data)
         feeder = _BatchFeeder(X, _host_labels(y), bs, stream_batches, cache=self.__dict__.setdefault("_feeder_cache", {}))
         self.h2d_bytes = self.d2h_bytes = 0
-        ring = PinnedBuffer((64, 2), np.float64) if feeder.stream else None
+        # streamed mode: every step's running loss / accuracy sums go back to the host (16 bytes, see _readback_fork)
+        if feeder.stream and self.__dict__.get("_rb_pinned") is None:
+            self._rb_pinned = PinnedBuffer((2,), np.float64)
+        self._step_readback = self._rb_pinned if feeder.stream else None
         for epoch in range(1, epochs + 1):
             start_time = time.time()
             self.loss.new_pass()
@@ -272,8 +301,7 @@ class Model:
             for step in range(train_steps):
                 self.train_step(*feeder.batch(step, fixed))
                 feeder.release(step, train_steps)
-                if ring is not None:      # streamed mode: the step's running loss/accuracy sums go back to the host
-                    lib.nm_d2h(C.c_void_p(ring.ptr + 16 * (step % 64)), self._accum.p, 16, stream())
+                if self._step_readback is not None:
                     self.d2h_bytes += 16
             if feeder.stream and (self.epoch_end_accuracy or epoch < epochs):
                 feeder.prefetch_next_pass()       # keep the copy engine busy across the end-of-pass synchronisation
@@ -318,6 +346,7 @@ class Model:
                                "data_loss": epoch_data_loss}
             if validation_data is not None:
                 self.evaluate(*validation_data, batch_size=batch_size, verbose=verbose)
+        self._step_readback = None
         if self.tensorMonitor:
             self.tensorMonitor.save_logs()
 
@@ -567,6 +596,9 @@ class _BatchFeeder:
             addr = self.pin_x[slot].ptr
         xb = self.dev[slot][0:rows]
         lib.nm_h2d(xb.p, C.c_void_p(addr), xb.nbytes, self.copy_stream)
+        # the slot's labels: a 16 KB device-to-device copy out of the label array that went up once, on the COPY stream (it
+        # is ordered behind that upload there), so the compute stream carries nothing but the step between two events
+        lib.nm_d2d(self.dev_lab[slot].p, C.c_void_p(self.dev_labels.ptr + 4 * lo), 4 * rows, self.copy_stream)
         lib.nm_event_record(self.uploaded[slot], self.copy_stream)
         self.h2d_bytes += xb.nbytes
         self.issued = step
@@ -596,12 +628,8 @@ class _BatchFeeder:
         while self.issued < step:
             self._upload(self.issued + 1)
         slot = self.slot_of[step]
-        st = stream()
-        lib.nm_stream_wait_event(st, self.uploaded[slot])
-        lib.nm_stream_wait_event(st, self.labels_ready)
-        lb = self.dev_lab[slot][0:hi - lo]
-        lib.nm_d2d(lb.p, C.c_void_p(self.dev_labels.ptr + 4 * lo), 4 * (hi - lo), st)     # ordered after the slot's last reader
-        return self.dev[slot][0:hi - lo], lb
+        lib.nm_stream_wait_event(stream(), self.uploaded[slot])
+        return self.dev[slot][0:hi - lo], self.dev_lab[slot][0:hi - lo]
 
     def release(self, step, n_steps):
         """Call after step's kernels are enqueued: marks its slot reusable and keeps SLOTS-1 uploads in flight."""
