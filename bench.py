@@ -103,6 +103,13 @@ WORKLOADS = {
                 desc="VGG-style stack C64 C64 P C128 C128 P C256 C256 P FC10 (3x3 'same' + ReLU, He init) on 32x32x3, "
                      "softmax-CE, Adam x2 per layer (reference quirk Q1)",
                 cpu_sample=64, cpu_steps=4, ref_budget=4_000),
+    # BASELINE.json configs[4]: one FedAvg client per GPU; a "step" of this workload is one ROUND = `local_steps` local
+    # training steps at batch 4096 (no gradient exchange) + federated_average of the weight slab over NCCL
+    "fedavg": dict(metric="train samples/sec (FedAvg rounds, Conv2D MNIST CNN, one client per GPU)", batch=4096, shape=(1, 28, 28),
+                   make=cnn_spec_and_params, flops_per_sample=22.767e6, local_steps=8,
+                   desc="FedAvg round = 8 local steps of the MNIST CNN at batch 4096 per client (Adam x2, state stays local) + "
+                        "federated_average (Federated/utils.py:20-23) of the weight slab as a pre-scaled SUM all-reduce over NCCL",
+                   cpu_sample=4096, cpu_steps=8, ref_budget=200_000),
 }
 
 
@@ -417,6 +424,42 @@ def parity_check(wl, mode, B, rank, world, comm_factory, dist, peer_arg=None):
                      "virtual shards" if world > 1 else "un-split step vs two virtual shards with the global batch as divisor")}
 
 
+def fedavg_parity(model, comm, rank, world, dist, B, E, x, y):
+    """One more round on the timed model: local steps, then the device average; every client's pre-average weights are
+    gathered over the bootstrap group and the reference rule sum_i w_i n_i / N (Federated/utils.py:20-23, equal n_i) is
+    applied on the host in float64.  Every rank must end with that model, bit-identical across ranks."""
+    from neuromah_b200 import device
+    from neuromah_b200.Federated.utils import federated_average, federated_average_device
+    for _ in range(E):
+        model.train_step(x, y)
+    device.synchronize()
+    mine = model.arena.host_params()
+    allw = [mine]
+    if dist is not None:
+        import torch
+        t = torch.from_numpy(mine).cuda()
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        allw = [o.cpu().numpy() for o in outs]
+    ref = np.asarray(federated_average([w.astype(np.float64) for w in allw], [E * B] * world))
+    federated_average_device(model.arena, E * B, E * B * world, comm if world > 1 else None)
+    device.synchronize()
+    got = model.arena.host_params()
+    crc = zlib.crc32(got.tobytes())
+    identical = True
+    if dist is not None:
+        import torch
+        t = torch.tensor([crc], dtype=torch.int64, device="cuda")
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        identical = len({int(o.item()) for o in outs}) == 1
+    err = float(np.abs(got - ref).max())
+    spread = float(max(np.abs(w - allw[0]).max() for w in allw))
+    return {"ok": bool(identical and err <= 1e-6), "replicas_bit_identical": bool(identical), "ranks": world,
+            "max_abs_err_vs_reference_rule": err, "client_weight_spread_before_average": spread,
+            "what": "device FedAvg (pre-scaled SUM all-reduce) vs federated_average() on the gathered client weights"}
+
+
 def _flat_init(model, params):
     """Initial parameters in arena table order (the update vector is measured against them)."""
     flat = []
@@ -456,7 +499,7 @@ def main():
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.steps is None:
-        args.steps = 1000 if args.workload == "mnist" else 100
+        args.steps = {"mnist": 1000, "vgg": 100, "fedavg": 100}[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -503,12 +546,22 @@ def main():
     model = build_model(spec, params, mode=mode)
     comm = parallel.Communicator(rank, world)
     peer_arg = None if args.dp == "auto" else args.dp == "peer"
-    parallel.attach(model, comm, B * world, peer=peer_arg)
+    fed = args.workload == "fedavg"
+    E = wl.get("local_steps", 1)         # training steps per timed "step" (a FedAvg round is E local steps + the average)
+    if fed:                              # clients train independently from the same global model; only weights are exchanged
+        if world > 1:
+            comm.broadcast(model.arena.params, 0, model.arena.total)
+    else:
+        parallel.attach(model, comm, B * world, peer=peer_arg)
     model.epoch_end_accuracy = False     # time the K training steps only (no Model.py:199 sweep)
+    from neuromah_b200.Federated.utils import federated_average_device
+
+    def fed_average():
+        federated_average_device(model.arena, E * B, E * B * world, comm if world > 1 else None)
 
     # synthetic data: up to 32 distinct host batches per rank in page-locked memory (cycled when K > 32).  Raw pixels are
     # uint8; the float32 copy is the example scripts' host-side normalisation of the same pixels.
-    n_host = min(max(K, 1), 32 if args.workload == "mnist" else 8)
+    n_host = min(max(K * E, 1), 8 if args.workload == "vgg" else 32)
     rng = np.random.default_rng(100 + rank)
     host_u8 = device.PinnedBuffer((n_host * B,) + wl["shape"], np.uint8)
     host_u8.array[...] = rng.integers(0, 256, host_u8.array.shape, dtype=np.uint8)
@@ -520,17 +573,23 @@ def main():
     y_dev = device.DeviceArray.from_numpy(labels[:n_dev * B])
     x_b = [x_dev[i * B:(i + 1) * B] for i in range(n_dev)]      # stable views: the step's CUDA graph is keyed by pointer
     y_b = [y_dev[i * B:(i + 1) * B] for i in range(n_dev)]
+    def do_step(s):
+        for j in range(E):
+            model.train_step(x_b[(s * E + j) % n_dev], y_b[(s * E + j) % n_dev])
+        if fed:
+            fed_average()
+
     for s in range(3 * n_dev):                                  # untimed priming: every batch eagerly, then captured
         model.train_step(x_b[s % n_dev], y_b[s % n_dev])
     for s in range(W):
-        model.train_step(x_b[s % n_dev], y_b[s % n_dev])
+        do_step(s)
     e0, e1 = device.new_event(), device.new_event()
     barrier()
     launches0 = device.launch_count()
     t_wall0 = time.time()
     lib.nm_event_record(e0, device.stream())
     for s in range(K):
-        model.train_step(x_b[s % n_dev], y_b[s % n_dev])
+        do_step(s)
     lib.nm_event_record(e1, device.stream())
     device.synchronize()
     t_wall1 = time.time()
@@ -539,7 +598,7 @@ def main():
     ms = C.c_float()
     lib.nm_event_elapsed_ms(e0, e1, C.byref(ms))
     elapsed_ms = max_over_ranks(ms.value)
-    value = K * B * world / (elapsed_ms / 1e3)
+    value = K * E * B * world / (elapsed_ms / 1e3)
     graphs = len(getattr(model, "_graphs", {}))
 
     clock_info = clocks.stop(t_wall0, t_wall1)   # before the end-to-end leg: a polling nvidia-smi stalls host-side syncs
@@ -547,7 +606,7 @@ def main():
     # ---------------- per-kernel pass: the same steps with a CUDA-event pair around every operator ----------
     # (a separate timed region: event records between kernels would serialise the programmatic dependent launches
     #  that the headline region relies on)
-    K2 = min(K, 50)
+    K2 = min(K * E, 50)
     ops.timers = ops.KernelTimers()
     lib.nm_event_record(e0, device.stream())
     for s in range(K2):
@@ -571,6 +630,14 @@ def main():
         h2d = d2h = 0
         barrier()
         lib.nm_event_record(e0, device.stream())
+        if fed:                            # a round = Model.train over the client's E local batches + the weight average
+            for r in range(steps):
+                lo = (r * E) % max(n_host - E + 1, 1)
+                model.train(host_arr[lo * B:(lo + E) * B], labels[lo * B:(lo + E) * B], epochs=1, batch_size=B, verbose=0,
+                            stream_batches=True)
+                fed_average()
+                h2d += model.h2d_bytes; d2h += model.d2h_bytes
+            full = rem = 0
         if full:
             model.train(host_arr, labels, epochs=full, batch_size=B, verbose=0, stream_batches=True)
             h2d += model.h2d_bytes; d2h += model.d2h_bytes
@@ -582,7 +649,7 @@ def main():
         barrier()
         lib.nm_event_elapsed_ms(e0, e1, C.byref(ms))
         t = max_over_ranks(ms.value)
-        return {"value": steps * B * world / (t / 1e3), "unit": UNIT, "ms_per_step": t / steps,
+        return {"value": steps * E * B * world / (t / 1e3), "unit": UNIT, "ms_per_step": t / steps,
                 "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps}
 
     host_f32 = None
@@ -603,13 +670,17 @@ def main():
 
     # ---------------- parity at this configuration (every rank takes part) --------------------------------------
     parity = None
+    if fed:
+        x_par = device.DeviceArray.from_numpy(host_u8.array[:B].astype(np.float32) / 255.0)
+        y_par = device.DeviceArray.from_numpy(labels[:B])
     if not args.no_parity:
         def comm_factory():
             c = parallel.Communicator(rank, world)
             return c
         try:
             # the check attaches with the same exchange as the timed model
-            parity = parity_check(wl, mode, B, rank, world, comm_factory, dist, peer_arg)
+            parity = (fedavg_parity(model, comm, rank, world, dist, B, E, x_par, y_par) if fed else
+                      parity_check(wl, mode, B, rank, world, comm_factory, dist, peer_arg))
         except Exception as e:      # a failed check must not lose the measured line; it is reported as such
             parity = {"ok": False, "error": f"{type(e).__name__}: {e}"}
 
@@ -659,13 +730,14 @@ def main():
             "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": wl["desc"],
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "gradient_exchange": ("none (1 GPU)" if world == 1 else
+                       "gradient_exchange": ("none: clients train independently; weights averaged once per round (NCCL all-reduce of "
+                                             "the pre-scaled slab)" if fed else "none (1 GPU)" if world == 1 else
                                              "gradient slab pushed over NVLink peer memory behind each wgrad (overlapping the rest of "
                                              "backward) + fused collect / rank-ordered sum / Adam kernel (nm_dp_*)"
                                              if comm.peer is not None else "NCCL all-reduce, buckets on a side stream"),
                        "mode": "bf16 tensor-core plan (bf16 operands, fp32 accumulate, fp32 master weights)"
                                if args.mode == "bf16" else "fp32_exact",
-                       "step_tflops": wl["flops_per_sample"] * B * world / (elapsed_ms / K * 1e-3) / 1e12,
+                       "step_tflops": wl["flops_per_sample"] * E * B * world / (elapsed_ms / K * 1e-3) / 1e12,
                        "cuda_graphs": graphs,
                        "l2": "inputs cycle over 8 distinct batches; the per-step activation working set "
                              "(>1 GB) is far larger than the 126 MB L2, so no explicit flush is needed"},

@@ -97,6 +97,14 @@ _SIGS = {
     "nm_tc_maxpool2x2_fwd_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_maxpool2x2_bwd_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_dense_dgrad_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "nm_tc_dense_dgrad_mask_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "nm_tc_to_bf16": (_i, [_vp, _vp, _sz, _vp]),
+    "nm_tc_u8_to_bf16": (_i, [_vp, _f, _vp, _sz, _vp]),
+    "nm_tc_pack_dense_gen_bf16": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "nm_tc_dense_fprop_gen_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "nm_tc_dense_dgrad_gen_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "nm_tc_dense_wgrad_gen_workspace": (_sz, [_i, _i, _i]),
+    "nm_tc_dense_wgrad_gen_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _f, _f, _vp]),
     "nm_tc_dense_bwd_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_pack_conv1_weights_bf16": (_i, [_vp, _vp, _i, _vp]),
     "nm_tc_conv1_fwd_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -136,7 +144,7 @@ _SIGS = {
 _UNCHECKED = {"nm_last_error", "nm_version", "nm_dp_chunk_floats", "nm_conv2d_wgrad_f32_workspace", "nm_dense_wgrad_f32_workspace",
               "nm_tc_conv3x3_wgrad_workspace", "nm_tc_conv1_bwd_workspace", "nm_tc_dense_wgrad_workspace",
               "nm_tc_dense_softmax_ce_workspace", "nm_tc_dense_bwd_unpool_workspace", "nm_tc_conv3x3_bwd_workspace",
-              "nm_tc_conv3x3_wgrad_gen_workspace"}
+              "nm_tc_conv3x3_wgrad_gen_workspace", "nm_tc_dense_wgrad_gen_workspace"}
 
 
 class NeuromahB200Error(RuntimeError):

@@ -24,8 +24,9 @@ namespace {
 using namespace tc;
 
 constexpr int G_M = 128;                 // rows of one MMA; a CTA tile is MSUB of them (MSUB accumulators per weight slice)
-constexpr int G_KC = 64;                 // channels per K chunk = one 128-byte SWIZZLE_128B row
-constexpr int G_ROWB = 128;
+// Channels per K chunk = one swizzled shared-memory row: 64 channels (128-byte rows, SWIZZLE_128B) in general; 32 channels
+// (64-byte rows, SWIZZLE_64B) for a first layer whose few input channels (RGB) are padded to 32 instead of 64 -- half the
+// bytes written by the input pack and read by the first conv's fprop / wgrad.
 
 struct ConvGenParams {
     int rows_total, Hp, Wp, H, W;
@@ -48,10 +49,11 @@ struct ConvGenParams {
 //    single-buffered and both epilogue groups drain each tile (two sub-tiles each);
 //  * b_resident -- when the whole bank of the CTA's (single) N tile fits next to the activation stages (Cin*Cout <= 64*64
 //    at 32x32), it is loaded once per CTA and never streamed again (MSUB = 2, double-buffered accumulators).
-template <int NT, int MSUB>
+template <int NT, int MSUB, int G_KC>
 __global__ void __launch_bounds__(384, 1)
 conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvGenParams p) {
-    constexpr uint64_t TMPL = desc_template(16, 8 * G_ROWB, LAYOUT_SW128);     // K-major, SBO = 8 rows
+    constexpr int G_ROWB = G_KC * 2;
+    constexpr uint64_t TMPL = desc_template(16, 8 * G_ROWB, G_KC == 64 ? LAYOUT_SW128 : LAYOUT_SW64);     // K-major, SBO = 8 rows
     constexpr uint32_t IDESC = idesc_bf16(G_M, NT, 0, 0);
     constexpr int TILE_ROWS = G_M * MSUB;
     constexpr int B_BYTES = NT * G_ROWB;                                      // one (tap, chunk) weight slice
@@ -277,6 +279,7 @@ struct WgradGenParams {
     int splits, c_chunks;                // gridDim.x = (OCp / MOC) * c_chunks, gridDim.y = splits
     int OCp, Cp;
     float* partial;                      // [splits][OCp][9][Cp]
+    float* bias_partial;                 // optional [splits * c_chunks][OCp]: column sums of dY (the bias gradient)
 };
 
 template <int MOC>
@@ -290,11 +293,14 @@ conv3x3_wgrad_gen_kernel(const __grid_constant__ CUtensorMap map_dy, const __gri
     constexpr uint64_t TMPL_A = desc_template(MOC == 128 ? A_BOX : 16, 1024, LAYOUT_SW128);
     constexpr uint64_t TMPL_B3 = desc_template(CB * 2, 8 * CB * 2, LAYOUT_SW64);
     constexpr uint32_t IDESC3 = idesc_bf16(MOC, 3 * CB, 1, 1);
-    constexpr uint32_t TMEM_COLS = 512;                                 // 9 * 32 = 288 columns used
+    constexpr uint32_t IDESC_ONES = idesc_bf16(MOC, CB, 1, 1);
+    constexpr uint32_t TMEM_COLS = 512;                                 // 9 * 32 = 288 columns + 32 for the bias gradient
+    constexpr int ONES_BYTES = G_M * CB * 2;                            // [128 pixels][32] bf16 of 1.0: the "X" of the bias gradient
 
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t stage_bytes = A_BYTES + p.x_stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * stage_bytes);
+    uint8_t* ones = smem + (size_t)p.n_stages * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ones + ONES_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + p.n_stages;
     uint64_t* done = empty + p.n_stages;
@@ -304,8 +310,19 @@ conv3x3_wgrad_gen_kernel(const __grid_constant__ CUtensorMap map_dy, const __gri
     // item is the fastest grid index: the CTAs that are resident together walk the SAME pixel blocks (one dY / X slice
     // each), so a block of dY and X crosses HBM once and is served to the other items from L2
     const int item = blockIdx.x, split = blockIdx.y;
-    const int oc0 = (item / p.c_chunks) * MOC, c0 = (item % p.c_chunks) * CB;
+    const int cq = item % p.c_chunks;
+    const int oc0 = (item / p.c_chunks) * MOC, c0 = cq * CB;
+    // Bias gradient (Conv_wrapepr.py:107-109: sum of dvalues over batch and positions) as one more MMA against a tile of
+    // ones: the CTAs that share (oc block, split) walk the same pixel blocks, CTA `cq` of them takes every c_chunks-th
+    // block, so each block's column sums are formed exactly once and the extra MMA (~24 % of a block's MMA time) is spread
+    // evenly.  dY is not read a second time (the separate column-sum kernels cost 166 us of the 2.08 ms VGG step).
+    const bool want_bias = p.bias_partial != nullptr;
     pdl_trigger();
+    if (want_bias) {
+        for (int i = threadIdx.x; i < ONES_BYTES / 16; i += blockDim.x)
+            reinterpret_cast<uint4*>(ones)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_dy); tma_prefetch_desc(&map_x); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -344,6 +361,8 @@ conv3x3_wgrad_gen_kernel(const __grid_constant__ CUtensorMap map_dy, const __gri
                 const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint64_t a_desc0 = desc_at(TMPL_A, st);
                 const uint64_t x_desc0 = desc_at(TMPL_B3, st + A_BYTES);
+                const uint64_t ones_desc0 = desc_at(TMPL_B3, smem_u32(ones));
+                const bool bias_here = want_bias && (it % p.c_chunks) == cq;
 #pragma unroll
                 for (int ks = 0; ks < G_M / 16; ++ks) {
                     if (ks == G_M / 16 - 1 && kb + p.splits < p.num_kblocks) {
@@ -356,6 +375,8 @@ conv3x3_wgrad_gen_kernel(const __grid_constant__ CUtensorMap map_dy, const __gri
                         const uint32_t shift = (uint32_t)(r * p.Wp + ks * 16) * (CB * 2);
                         mma_bf16(tmem_base + r * 3 * CB, adesc, x_desc0 + (shift >> 4), IDESC3, !(it == 0 && ks == 0));
                     }
+                    if (bias_here)          // first bias block of this CTA is its it == cq
+                        mma_bf16(tmem_base + 9 * CB, adesc, ones_desc0 + ((uint32_t)(ks * 16 * CB * 2) >> 4), IDESC_ONES, !(it == cq && ks == 0));
                 }
                 mma_commit(&empty[stage]);
             }
@@ -382,6 +403,14 @@ conv3x3_wgrad_gen_kernel(const __grid_constant__ CUtensorMap map_dy, const __gri
                         ? make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]))
                         : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        }
+        if (want_bias) {
+            // this CTA formed column sums iff it walked more than cq blocks; all 32 ones-columns hold the same sum
+            const int n_its = split < p.num_kblocks ? (p.num_kblocks - 1 - split) / p.splits + 1 : 0;
+            const bool did = n_its > cq;
+            uint32_t raw[16];
+            if (did) { tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + 9 * CB, raw); tmem_ld_wait(); }
+            if (row_ok) p.bias_partial[((size_t)split * p.c_chunks + cq) * p.OCp + oc0 + m] = did ? __uint_as_float(raw[0]) : 0.f;
         }
     }
     fence_before_sync();
@@ -417,30 +446,8 @@ wgrad_gen_reduce_kernel(const float* __restrict__ partial, float* __restrict__ d
     }
 }
 
-// bias gradient: db[oc] = sum over every row of the haloed bf16 gradient [rows][OCp] (halo rows are zero).
-// Stage 1: block b sums rows b, b + gridDim.x, ... (thread = channel pair x row lane); stage 2 sums the blocks in order.
+// bias gradient, final stage: db[oc] = sum of the per-CTA column sums of dY that the wgrad kernel formed (fixed order).
 constexpr int DB_BLOCKS = 296;
-__global__ void __launch_bounds__(1024)
-dbias_partial_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ partial, int rows, int OCp) {
-    __shared__ float2 red[1024];
-    pdl_trigger();
-    pdl_wait();
-    const int pairs = OCp / 2, lanes = 1024 / pairs;            // OCp in {64,128,256,512}: pairs divides 1024
-    const int cp = threadIdx.x % pairs, rl = threadIdx.x / pairs;
-    float2 s = make_float2(0.f, 0.f);
-    if (rl < lanes)
-        for (long long r = (long long)blockIdx.x * lanes + rl; r < rows; r += (long long)gridDim.x * lanes) {
-            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(dy + r * OCp + 2 * cp);
-            s.x += __bfloat162float(v.x); s.y += __bfloat162float(v.y);
-        }
-    red[threadIdx.x] = s;
-    __syncthreads();
-    if (rl == 0) {
-        for (int k = 1; k < lanes; ++k) { s.x += red[k * pairs + cp].x; s.y += red[k * pairs + cp].y; }
-        partial[(size_t)blockIdx.x * OCp + 2 * cp] = s.x;
-        partial[(size_t)blockIdx.x * OCp + 2 * cp + 1] = s.y;
-    }
-}
 __global__ void dbias_final_kernel(const float* __restrict__ partial, float* __restrict__ db, int blocks, int OC, int OCp) {
     pdl_trigger();
     pdl_wait();
@@ -503,22 +510,23 @@ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 constexpr int G_SMEM_BUDGET = 212 * 1024;
 
 // activation stage geometry for a tile of msub * 128 pixels
-void conv_gen_tile(ConvGenParams& p, int msub) {
+void conv_gen_tile(ConvGenParams& p, int msub, int kc) {
     const int tile_rows = G_M * msub, a_rows = tile_rows + 2 * p.Wp + 2;
     p.num_tiles = ((p.rows_total + tile_rows - 1) / tile_rows) * p.n_tiles;
     p.a_boxes = (a_rows + 255) / 256;
     p.a_box_rows = round_up((a_rows + p.a_boxes - 1) / p.a_boxes, 8);
-    p.a_stage_bytes = (uint32_t)(p.a_boxes * p.a_box_rows) * G_ROWB;
+    p.a_stage_bytes = (uint32_t)round_up(p.a_boxes * p.a_box_rows * kc * 2, 1024);      // swizzled tiles start on 1024-byte boundaries
 }
 
-template <int NT, int MSUB>
+template <int NT, int MSUB, int G_KC>
 int launch_conv_gen(const void* x_pad, const void* w_packed, ConvGenParams p, cudaStream_t st) {
+    constexpr int G_ROWB = G_KC * 2;
+    constexpr CUtensorMapSwizzle SWZ = G_KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     NM_REQUIRE(p.a_box_rows <= 256, "image too wide");
     CUtensorMap ma, mb;
-    int rc = make_map_2d(&ma, x_pad, (uint64_t)p.Cin, (uint64_t)p.rows_total, (uint64_t)p.Cin * 2, G_KC, (uint32_t)p.a_box_rows,
-                         CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = make_map_2d(&ma, x_pad, (uint64_t)p.Cin, (uint64_t)p.rows_total, (uint64_t)p.Cin * 2, G_KC, (uint32_t)p.a_box_rows, SWZ);
     if (rc) return rc;
-    rc = make_map_2d(&mb, w_packed, (uint64_t)9 * p.Cin, (uint64_t)p.Cout, (uint64_t)9 * p.Cin * 2, G_KC, NT, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = make_map_2d(&mb, w_packed, (uint64_t)9 * p.Cin, (uint64_t)p.Cout, (uint64_t)9 * p.Cin * 2, G_KC, NT, SWZ);
     if (rc) return rc;
     constexpr int B_BYTES = NT * G_ROWB;
     if (p.b_resident) {
@@ -533,7 +541,7 @@ int launch_conv_gen(const void* x_pad, const void* w_packed, ConvGenParams p, cu
     NM_REQUIRE(p.a_stages >= 2 && p.b_stages >= 2, "image too wide for the shared-memory budget");
     NM_REQUIRE(2 * (p.a_stages + p.b_stages) + 4 <= 62, "too many pipeline stages for the barrier block");
     const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * B_BYTES + 512;   // + mbarriers
-    auto kern = conv3x3_gen_kernel<NT, MSUB>;
+    auto kern = conv3x3_gen_kernel<NT, MSUB, G_KC>;
     static bool attr_set = false;
     if (!attr_set) {
         NM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -566,7 +574,8 @@ extern "C" {
 
 int nm_tc_pack_conv_weights_gen_bf16(const float* w_oihw, void* w_fprop, void* w_dgrad, int OC, int C, int OCp, int Cp, void* stream) {
     NM_REQUIRE(w_oihw && (w_fprop || w_dgrad), "null pointer");
-    NM_REQUIRE(OC > 0 && C > 0 && OCp >= OC && Cp >= C && OCp % 64 == 0 && Cp % 64 == 0, "padded channel counts must be multiples of 64");
+    NM_REQUIRE(OC > 0 && C > 0 && OCp >= OC && Cp >= C && OCp % 64 == 0 && (Cp % 64 == 0 || Cp == 32),
+               "padded channel counts must be multiples of 64 (input channels: or 32)");
     const int total = OCp * Cp * 9;
     return nm::launch_pdl("pack_conv_weights_gen", pack_conv_weights_gen_kernel, dim3(nm_cdiv(total, 256)), dim3(256), 0, nm::S(stream),
                           w_oihw, static_cast<__nv_bfloat16*>(w_fprop), static_cast<__nv_bfloat16*>(w_dgrad), OC, C, OCp, Cp);
@@ -591,13 +600,15 @@ int nm_tc_conv3x3_gen_bf16(const void* x_pad, const void* w_packed, const float*
                            int N, int H, int W, int Cin, int Cout, int relu, void* stream) {
     NM_REQUIRE(x_pad && w_packed && y_pad, "null pointer");
     NM_REQUIRE(N > 0 && H > 0 && W > 0, "bad dimensions");
-    NM_REQUIRE(Cin > 0 && Cout > 0 && Cin % 64 == 0 && Cout % 64 == 0, "channel counts must be multiples of 64 (pad with zero channels)");
+    NM_REQUIRE(Cin > 0 && Cout > 0 && (Cin % 64 == 0 || Cin == 32) && Cout % 64 == 0,
+               "channel counts must be multiples of 64 (pad with zero channels); Cin = 32 is accepted for a padded first layer");
     ConvGenParams p{};
     p.Hp = H + 2; p.Wp = W + 2; p.H = H; p.W = W;
     NM_REQUIRE((long long)N * p.Hp * p.Wp < (1ll << 31) - 1024, "batch too large for 32-bit row coordinates");
     p.rows_total = N * p.Hp * p.Wp;
     p.Cin = Cin; p.Cout = Cout;
-    p.k_chunks = Cin / G_KC;
+    const int kc = Cin == 32 ? 32 : 64;
+    p.k_chunks = Cin / kc;
     const int nt = Cout % 128 == 0 ? 128 : 64;
     p.n_tiles = Cout / nt;
     p.out = static_cast<__nv_bfloat16*>(y_pad);
@@ -609,16 +620,18 @@ int nm_tc_conv3x3_gen_bf16(const void* x_pad, const void* w_packed, const float*
     // it from L2.  NM_TC_GEN_MODE=2 selects MSUB = 4, =3 the resident bank where it fits (experiments only).
     static int mode = -1;
     if (mode < 0) { const char* e = getenv("NM_TC_GEN_MODE"); mode = e ? atoi(e) : 1; }
-    conv_gen_tile(p, 2);
-    p.b_resident = mode == 3 && p.n_tiles == 1 && 9 * p.k_chunks * nt * G_ROWB + 2 * (int)p.a_stage_bytes <= G_SMEM_BUDGET;
+    conv_gen_tile(p, 2, kc);
+    if (kc == 32)
+        return nt == 128 ? launch_conv_gen<128, 2, 32>(x_pad, w_packed, p, nm::S(stream)) : launch_conv_gen<64, 2, 32>(x_pad, w_packed, p, nm::S(stream));
+    p.b_resident = mode == 3 && p.n_tiles == 1 && 9 * p.k_chunks * nt * 128 + 2 * (int)p.a_stage_bytes <= G_SMEM_BUDGET;
     if (mode != 2 || p.b_resident)
-        return nt == 128 ? launch_conv_gen<128, 2>(x_pad, w_packed, p, nm::S(stream)) : launch_conv_gen<64, 2>(x_pad, w_packed, p, nm::S(stream));
-    conv_gen_tile(p, 4);
-    return nt == 128 ? launch_conv_gen<128, 4>(x_pad, w_packed, p, nm::S(stream)) : launch_conv_gen<64, 4>(x_pad, w_packed, p, nm::S(stream));
+        return nt == 128 ? launch_conv_gen<128, 2, 64>(x_pad, w_packed, p, nm::S(stream)) : launch_conv_gen<64, 2, 64>(x_pad, w_packed, p, nm::S(stream));
+    conv_gen_tile(p, 4, kc);
+    return nt == 128 ? launch_conv_gen<128, 4, 64>(x_pad, w_packed, p, nm::S(stream)) : launch_conv_gen<64, 4, 64>(x_pad, w_packed, p, nm::S(stream));
 }
 
 size_t nm_tc_conv3x3_wgrad_gen_workspace(int N, int H, int W, int C, int Cp, int OCp) {
-    if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cp < C || OCp <= 0 || Cp % 64 || OCp % 64) return 0;
+    if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cp < C || OCp <= 0 || (Cp % 64 && Cp != 32) || OCp % 64) return 0;
     const WgradGenPlan g = wgrad_gen_plan(N, H, W, C, OCp);
     return (size_t)g.splits * OCp * 9 * Cp * sizeof(float) + (size_t)DB_BLOCKS * OCp * sizeof(float);
 }
@@ -627,7 +640,8 @@ int nm_tc_conv3x3_wgrad_gen_bf16(const void* x_pad, const void* dy_pad, float* d
                                  int N, int H, int W, int C, int OC, int Cp, int OCp, void* stream) {
     NM_REQUIRE(x_pad && dy_pad && dw && workspace, "null pointer");
     NM_REQUIRE(N > 0 && H > 0 && W > 0, "bad dimensions");
-    NM_REQUIRE(C > 0 && OC > 0 && Cp >= C && OCp >= OC && Cp % 64 == 0 && OCp % 64 == 0, "padded channel counts must be multiples of 64");
+    NM_REQUIRE(C > 0 && OC > 0 && Cp >= C && OCp >= OC && (Cp % 64 == 0 || Cp == 32) && OCp % 64 == 0,
+               "padded channel counts must be multiples of 64 (input channels: or 32)");
     NM_REQUIRE((long long)N * (H + 2) * (W + 2) < (1ll << 31) - 1024, "batch too large for 32-bit row coordinates");
     const WgradGenPlan g = wgrad_gen_plan(N, H, W, C, OCp);
     NM_REQUIRE(workspace_bytes >= nm_tc_conv3x3_wgrad_gen_workspace(N, H, W, C, Cp, OCp), "workspace too small");
@@ -640,20 +654,22 @@ int nm_tc_conv3x3_wgrad_gen_bf16(const void* x_pad, const void* dy_pad, float* d
     p.x_stage_bytes = ((uint32_t)p.x_rows * 64 + 1023u) & ~1023u;
     const int a_bytes = (g.moc / 64) * G_M * 128;
     {
-        const int fit = (int)((212 * 1024) / (a_bytes + p.x_stage_bytes));
+        const int fit = (int)((212 * 1024 - G_M * 64) / (a_bytes + p.x_stage_bytes));
         p.n_stages = fit > 8 ? 8 : fit;
     }
     p.splits = g.splits;
     p.c_chunks = g.c_chunks;
     p.OCp = OCp; p.Cp = Cp;
     p.partial = static_cast<float*>(workspace);
+    p.bias_partial = dbias ? p.partial + (size_t)g.splits * OCp * 9 * Cp : nullptr;
+    NM_REQUIRE(g.splits * g.c_chunks <= DB_BLOCKS, "bias-gradient partials exceed the workspace");
     const int items = g.items;
     CUtensorMap mdy, mx;
     int rc = make_map_2d(&mdy, dy_pad, (uint64_t)OCp, (uint64_t)p.rows_total, (uint64_t)OCp * 2, 64, G_M, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     rc = make_map_2d(&mx, x_pad, (uint64_t)Cp, (uint64_t)p.rows_total, (uint64_t)Cp * 2, 32, (uint32_t)p.x_rows, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
-    const size_t smem = (size_t)p.n_stages * (a_bytes + p.x_stage_bytes) + 256;
+    const size_t smem = (size_t)p.n_stages * (a_bytes + p.x_stage_bytes) + G_M * 64 + 256;
     static bool attr_set = false;
     if (!attr_set) {
         NM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_gen_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -668,16 +684,9 @@ int nm_tc_conv3x3_wgrad_gen_bf16(const void* x_pad, const void* dy_pad, float* d
                         dim3(64 * (p.splits >= 64 ? GR_SLICES : p.splits >= 16 ? 2 : 1)), 0, nm::S(stream),
                         (const float*)p.partial, dw, p.splits, OC, C, OCp, Cp);
     if (rc || !dbias) return rc;
-    float* dbp = p.partial + (size_t)g.splits * OCp * 9 * Cp;
-    NM_REQUIRE(OCp <= 2048, "bias gradient: too many channels for one block");
-    const int lanes = 1024 / (OCp / 2);
-    int blocks = (p.rows_total + lanes - 1) / lanes;
-    if (blocks > DB_BLOCKS) blocks = DB_BLOCKS;
-    rc = nm::launch_pdl("dbias_partial", dbias_partial_kernel, dim3(blocks), dim3(1024), 0, nm::S(stream),
-                        static_cast<const __nv_bfloat16*>(dy_pad), dbp, p.rows_total, OCp);
-    if (rc) return rc;
+    // column sums of dY were formed inside the wgrad kernel (one partial per CTA): fixed-order final sum
     return nm::launch_pdl("dbias_final", dbias_final_kernel, dim3(nm_cdiv((size_t)OC * 32, 256)), dim3(256), 0, nm::S(stream),
-                          (const float*)dbp, dbias, blocks, OC, OCp);
+                          (const float*)p.bias_partial, dbias, g.splits * g.c_chunks, OC, OCp);
 }
 
 }  // extern "C"

@@ -1,0 +1,429 @@
+// General bf16 tensor-core GEMMs for Layer_Dense (hidden layers of any width) on sm_100a: TMA-fed tcgen05 tiles with
+// FP32 accumulation in TMEM, the layer's elementwise work fused into the epilogue.
+//
+//   fprop  Y[B, n_out]  = X[B, n_in] W[n_in, n_out] + b, ReLU            (Dense.py:79-85)      -> bf16 activations
+//   dgrad  dX[B, n_in]  = dY[B, n_out] W^T, then the ReLU backward of the layer below  (Dense.py:108, Relu.py:12-14)
+//   wgrad  dW[n_in, n_out] = X^T dY / B (+ L1 / L2 terms), db = sum_b dY / B           (Dense.py:96-105)
+//
+// fprop and dgrad are ONE kernel, D[M, N] = A[M, K] B[N, K]^T with both operands K-major: fprop takes the packed bf16 copy
+// W^T [n_out][n_in], dgrad the bf16 copy of W in its own layout [n_in][n_out].  wgrad contracts over the BATCH, so both
+// operands are read MN-major straight from the activation / gradient tensors ([B][features] rows): no transposed copies of
+// anything that changes per step.  Dimensions need not be multiples of the tile: TMA zero-fills out-of-range boxes and the
+// epilogues mask their stores (784 = 12 * 64 + 16 input features run as 13 K chunks).
+//
+// Replaces for the tensor-core mode: np.dot(inputs, weights) + biases and the embedded activation (Dense.py:79-85),
+// np.dot(inputs.T, dvalues) / B, np.sum(dvalues) / B, the regulariser terms and np.dot(dvalues, weights.T)
+// (Dense.py:96-108), Activation_ReLU.forward / backward (Relu.py:7-14).
+#include "nm_common.cuh"
+#include "nm_tc_common.cuh"
+#include "nm_tc_host.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int GM = 128;                  // rows of one MMA / CTA tile
+constexpr int GK = 64;                   // K chunk = one 128-byte SWIZZLE_128B row
+constexpr int G_STAGES = 4;
+
+struct GemmParams {
+    int M, N, K;                         // D[M][N] = sum_k A[M][k] * B[N][k]
+    int k_chunks, n_tiles;
+    __nv_bfloat16* out; int ldo;         // bf16 [M][ldo]
+    const float* bias;                   // optional [N]
+    int relu;
+    const __nv_bfloat16* mask; int ldm;  // optional [M][ldm]: out = mask > 0 ? v : 0   (ReLU' of the layer below)
+};
+
+template <int NT>
+__global__ void __launch_bounds__(256, 1)
+dense_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p) {
+    constexpr uint64_t TMPL = desc_template(16, 8 * 128, LAYOUT_SW128);         // K-major, SBO = 8 rows of 128 B
+    constexpr uint32_t IDESC = idesc_bf16(GM, NT, 0, 0);
+    constexpr int A_BYTES = GM * 128, B_BYTES = NT * 128, STAGE = A_BYTES + B_BYTES;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + G_STAGES * STAGE);
+    uint64_t* empty = full + G_STAGES;
+    uint64_t* tfull = empty + G_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x / p.n_tiles, n0 = (blockIdx.x - m_tile * p.n_tiles) * NT;
+    pdl_trigger();
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < G_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, NT);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kc = 0; kc < p.k_chunks; ++kc) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* st = smem + stage * STAGE;
+                mbar_expect_tx(&full[stage], STAGE);                 // out-of-range parts of a box arrive as zeros, bytes included
+                tma_load_2d(st, &map_a, kc * GK, m_tile * GM, &full[stage]);
+                tma_load_2d(st + A_BYTES, &map_b, kc * GK, n0, &full[stage]);
+                if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kc = 0; kc < p.k_chunks; ++kc) {
+                mbar_wait(&full[stage], phase);
+                fence_after_sync();
+                const uint32_t st = smem_u32(smem + stage * STAGE);
+                const uint64_t a_desc = desc_at(TMPL, st), b_desc = desc_at(TMPL, st + A_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < GK / 16; ++kk)
+                    mma_bf16(tmem_base, a_desc + ((kk * 32) >> 4), b_desc + ((kk * 32) >> 4), IDESC, (kc | kk) != 0);
+                mma_commit(&empty[stage]);
+                if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+            }
+            mma_commit(tfull);
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int row = m_tile * GM + q * 32 + lane;
+        mbar_wait(tfull, 0);
+        fence_after_sync();
+        const bool row_ok = row < p.M;
+        __nv_bfloat16* dst = p.out + (size_t)row * p.ldo + n0;
+        const __nv_bfloat16* msk = p.mask ? p.mask + (size_t)row * p.ldm + n0 : nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+            tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + c0 + 16, v + 16);
+            tmem_ld_wait();
+            if (!row_ok) continue;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int col = n0 + c0 + g * 8;
+                if (col >= p.N) break;                                  // N is a multiple of 8 (checked on the host)
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+                if (p.bias) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+                    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                if (msk) {
+                    const uint4 mk = __ldg(reinterpret_cast<const uint4*>(msk + c0 + g * 8));
+                    const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t h = (mw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;     // bf16 > 0: sign clear, not zero
+                        if ((h & 0x8000u) || !(h & 0x7FFFu)) f[j] = 0.f;
+                    }
+                }
+                *reinterpret_cast<uint4*>(dst + c0 + g * 8) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                                         pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, NT);
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: P[split][f][n] = sum over the split's batch blocks of X[b][f] * dY[b][n]        (both operands MN-major)
+// ---------------------------------------------------------------------------------------------
+struct DenseWgradParams {
+    int F, N;                            // features (n_in), outputs (n_out)
+    int k_blocks, splits, n_tiles;
+    float* partial;                      // [splits][F][N]
+};
+
+template <int NT>
+__global__ void __launch_bounds__(256, 1)
+dense_wgrad_gen_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, DenseWgradParams p) {
+    constexpr int BOX = GM * 128;                                        // one [128 batch rows][64 columns] box, 16 KB
+    constexpr int A_BYTES = 2 * BOX, B_BYTES = (NT / 64) * BOX, STAGE = A_BYTES + B_BYTES;
+    // MN-major: 64-column chunks BOX bytes apart (leading byte offset), 8 batch rows = 1024 B (stride byte offset)
+    constexpr uint64_t TMPL = desc_template(BOX, 1024, LAYOUT_SW128);
+    constexpr uint32_t IDESC = idesc_bf16(GM, NT, 1, 1);
+    constexpr int STAGES = NT == 128 ? 3 : 4;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+    uint64_t* empty = full + STAGES;
+    uint64_t* done = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f_tile = blockIdx.x / p.n_tiles, n0 = (blockIdx.x - f_tile * p.n_tiles) * NT, f0 = f_tile * GM;
+    const int split = blockIdx.y;
+    pdl_trigger();
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_dy); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, NT);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const bool has_work = split < p.k_blocks;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = split; kb < p.k_blocks; kb += p.splits) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* st = smem + stage * STAGE;
+                mbar_expect_tx(&full[stage], STAGE);
+                tma_load_2d(st, &map_x, f0, kb * GM, &full[stage]);
+                tma_load_2d(st + BOX, &map_x, f0 + 64, kb * GM, &full[stage]);
+#pragma unroll
+                for (int j = 0; j < NT / 64; ++j) tma_load_2d(st + A_BYTES + j * BOX, &map_dy, n0 + j * 64, kb * GM, &full[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0; bool first = true;
+            for (int kb = split; kb < p.k_blocks; kb += p.splits) {
+                mbar_wait(&full[stage], phase);
+                fence_after_sync();
+                const uint32_t st = smem_u32(smem + stage * STAGE);
+                const uint64_t a_desc = desc_at(TMPL, st), b_desc = desc_at(TMPL, st + A_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < GM / 16; ++ks)
+                    mma_bf16(tmem_base, a_desc + ((ks * 16 * 128) >> 4), b_desc + ((ks * 16 * 128) >> 4), IDESC, !(first && ks == 0));
+                first = false;
+                mma_commit(&empty[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (has_work) mma_commit(done);
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int f = f0 + q * 32 + lane;
+        if (has_work) { mbar_wait(done, 0); fence_after_sync(); }
+        float* dst = p.partial + ((size_t)split * p.F + f) * p.N + n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+            uint32_t v[16];
+            if (has_work) { tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v); tmem_ld_wait(); }
+            if (f < p.F && n0 + c0 < p.N) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(dst + c0 + j) = has_work
+                        ? make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, NT);
+}
+
+// dW[f][n] = scale * sum_s P[s][f][n] + l1 sign(W) + 2 l2 W      (splits summed in order: bitwise repeatable)
+__global__ void __launch_bounds__(256)
+dense_wgrad_gen_finish_kernel(const float* __restrict__ partial, const float* __restrict__ w, float* __restrict__ dw,
+                              int F, int N, int splits, float scale, float l1, float l2) {
+    pdl_trigger();
+    pdl_wait();
+    const size_t total = (size_t)F * N / 4;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(partial) + (size_t)s * total + i);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
+    if (l1 != 0.f || l2 != 0.f) {
+        const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + i);
+        auto reg = [&](float x) { return l1 * (x > 0.f ? 1.f : x < 0.f ? -1.f : 0.f) + 2.f * l2 * x; };
+        a.x += reg(ww.x); a.y += reg(ww.y); a.z += reg(ww.z); a.w += reg(ww.w);
+    }
+    reinterpret_cast<float4*>(dw)[i] = a;
+}
+
+// db[n] = scale * sum_b dY[b][n] over the bf16 gradient [B][N]: one block per 32 columns, 8 row lanes, fixed tree
+__global__ void __launch_bounds__(256)
+dense_dbias_bf16_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db, int B, int N, float scale) {
+    __shared__ float red[8][32];
+    pdl_trigger();
+    pdl_wait();
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+    float s = 0.f;
+    if (col < N)
+        for (int b = rl; b < B; b += 8) s += __bfloat162float(dy[(size_t)b * N + col]);
+    red[rl][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (rl == 0 && col < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        db[col] = t * scale;
+    }
+}
+
+// float32 (or raw uint8 pixels * scale) -> bf16, 8 elements per thread: the A operand of the first Dense layer
+template <typename XT>
+__global__ void to_bf16_kernel(const XT* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n, float scale) {
+    pdl_trigger();
+    pdl_wait();
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i >= n) return;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = i + j < n ? (float)x[i + j] * scale : 0.f;
+    if (i + 8 <= n)
+        *reinterpret_cast<uint4*>(y + i) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    else
+        for (int j = 0; i + j < n; ++j) y[i + j] = __float2bfloat16(f[j]);
+}
+
+// Dense weights f32 [n_in][n_out] -> bf16 copy in the same layout (dgrad operand) and transposed [n_out][n_in] (fprop operand)
+__global__ void pack_dense_gen_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w_kn, __nv_bfloat16* __restrict__ w_nk,
+                                      int K, int N) {
+    pdl_trigger();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * N) return;
+    const int k = i / N, n = i - k * N;
+    const __nv_bfloat16 v = __float2bfloat16(w[i]);
+    if (w_kn) w_kn[i] = v;
+    if (w_nk) w_nk[(size_t)n * K + k] = v;
+}
+
+template <int NT>
+int launch_gemm(const void* a, const void* b, GemmParams p, cudaStream_t st) {
+    CUtensorMap ma, mb;
+    int rc = make_map_2d(&ma, a, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)p.K * 2, GK, GM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map_2d(&mb, b, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.K * 2, GK, NT, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    const size_t smem = (size_t)G_STAGES * (GM * 128 + NT * 128) + 256;
+    static bool attr = false;
+    if (!attr) { NM_CUDA(cudaFuncSetAttribute(dense_gemm_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    p.n_tiles = (p.N + NT - 1) / NT;
+    const int m_tiles = (p.M + GM - 1) / GM;
+    return nm::launch_pdl("dense_gemm_tc", dense_gemm_tc_kernel<NT>, dim3(m_tiles * p.n_tiles), dim3(256), smem, st, ma, mb, p);
+}
+
+struct DenseWgradPlan { int nt, f_tiles, n_tiles, k_blocks, splits; };
+DenseWgradPlan dense_wgrad_plan(int B, int F, int N) {
+    DenseWgradPlan g;
+    g.nt = N % 128 == 0 ? 128 : 64;
+    g.f_tiles = (F + GM - 1) / GM;
+    g.n_tiles = (N + g.nt - 1) / g.nt;
+    g.k_blocks = (B + GM - 1) / GM;
+    int s = sm_count() / (g.f_tiles * g.n_tiles);
+    if (s < 1) s = 1;
+    if (s > g.k_blocks) s = g.k_blocks;
+    g.splits = s;
+    return g;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nm_tc_to_bf16(const float* x, void* y, size_t n, void* stream) {
+    NM_REQUIRE(x && y, "null pointer");
+    if (!n) return NM_OK;
+    return nm::launch_pdl("to_bf16", to_bf16_kernel<float>, dim3(nm_cdiv(n, 8 * 256)), dim3(256), 0, nm::S(stream), x,
+                          static_cast<__nv_bfloat16*>(y), n, 1.f);
+}
+int nm_tc_u8_to_bf16(const uint8_t* x, float scale, void* y, size_t n, void* stream) {
+    NM_REQUIRE(x && y, "null pointer");
+    if (!n) return NM_OK;
+    return nm::launch_pdl("u8_to_bf16", to_bf16_kernel<uint8_t>, dim3(nm_cdiv(n, 8 * 256)), dim3(256), 0, nm::S(stream), x,
+                          static_cast<__nv_bfloat16*>(y), n, scale);
+}
+
+int nm_tc_pack_dense_gen_bf16(const float* w, void* w_kn, void* w_nk, int n_in, int n_out, void* stream) {
+    NM_REQUIRE(w && (w_kn || w_nk), "null pointer");
+    NM_REQUIRE(n_in > 0 && n_out > 0, "bad dimensions");
+    return nm::launch_pdl("pack_dense_gen", pack_dense_gen_kernel, dim3(nm_cdiv((size_t)n_in * n_out, 256)), dim3(256), 0, nm::S(stream),
+                          w, static_cast<__nv_bfloat16*>(w_kn), static_cast<__nv_bfloat16*>(w_nk), n_in, n_out);
+}
+
+// y[B][n_out] = x[B][n_in] w_nk[n_out][n_in]^T (+ bias) (ReLU)
+int nm_tc_dense_fprop_gen_bf16(const void* x, const void* w_nk, const float* bias, void* y, int B, int n_in, int n_out, int relu,
+                               void* stream) {
+    NM_REQUIRE(x && w_nk && y, "null pointer");
+    NM_REQUIRE(B > 0 && n_in > 0 && n_out > 0 && n_in % 8 == 0 && n_out % 8 == 0, "bad dimensions (n_in, n_out multiples of 8)");
+    GemmParams p{};
+    p.M = B; p.N = n_out; p.K = n_in; p.k_chunks = (n_in + GK - 1) / GK;
+    p.out = static_cast<__nv_bfloat16*>(y); p.ldo = n_out; p.bias = bias; p.relu = relu;
+    return n_out % 128 == 0 ? launch_gemm<128>(x, w_nk, p, nm::S(stream)) : launch_gemm<64>(x, w_nk, p, nm::S(stream));
+}
+
+// dx[B][n_in] = dy[B][n_out] w_kn[n_in][n_out]^T, zeroed where relu_mask[B][n_in] <= 0 (if not NULL)
+int nm_tc_dense_dgrad_gen_bf16(const void* dy, const void* w_kn, const void* relu_mask, void* dx, int B, int n_in, int n_out, void* stream) {
+    NM_REQUIRE(dy && w_kn && dx, "null pointer");
+    NM_REQUIRE(B > 0 && n_in > 0 && n_out > 0 && n_in % 8 == 0 && n_out % 8 == 0, "bad dimensions (n_in, n_out multiples of 8)");
+    GemmParams p{};
+    p.M = B; p.N = n_in; p.K = n_out; p.k_chunks = (n_out + GK - 1) / GK;
+    p.out = static_cast<__nv_bfloat16*>(dx); p.ldo = n_in;
+    p.mask = static_cast<const __nv_bfloat16*>(relu_mask); p.ldm = n_in;
+    return n_in % 128 == 0 ? launch_gemm<128>(dy, w_kn, p, nm::S(stream)) : launch_gemm<64>(dy, w_kn, p, nm::S(stream));
+}
+
+size_t nm_tc_dense_wgrad_gen_workspace(int B, int n_in, int n_out) {
+    if (B <= 0 || n_in <= 0 || n_out <= 0) return 0;
+    const DenseWgradPlan g = dense_wgrad_plan(B, n_in, n_out);
+    return (size_t)g.splits * n_in * n_out * sizeof(float);
+}
+
+// dw[n_in][n_out] = scale * x^T dy (+ l1 sign(w) + 2 l2 w), db[n_out] = scale * sum_b dy      (x, dy bf16 [B][.])
+int nm_tc_dense_wgrad_gen_bf16(const void* x, const void* dy, const float* w, float* dw, float* db, void* workspace, size_t workspace_bytes,
+                               int B, int n_in, int n_out, float scale, float l1, float l2, void* stream) {
+    NM_REQUIRE(x && dy && dw && workspace, "null pointer");
+    NM_REQUIRE(B > 0 && n_in > 0 && n_out > 0 && n_in % 8 == 0 && n_out % 64 == 0, "bad dimensions (n_in % 8, n_out % 64)");
+    NM_REQUIRE(w || (l1 == 0.f && l2 == 0.f), "the regulariser terms need the weights");
+    const DenseWgradPlan g = dense_wgrad_plan(B, n_in, n_out);
+    NM_REQUIRE(workspace_bytes >= nm_tc_dense_wgrad_gen_workspace(B, n_in, n_out), "workspace too small");
+    DenseWgradParams p{};
+    p.F = n_in; p.N = n_out; p.k_blocks = g.k_blocks; p.splits = g.splits; p.n_tiles = g.n_tiles;
+    p.partial = static_cast<float*>(workspace);
+    CUtensorMap mx, mdy;
+    int rc = make_map_2d(&mx, x, (uint64_t)n_in, (uint64_t)B, (uint64_t)n_in * 2, 64, GM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map_2d(&mdy, dy, (uint64_t)n_out, (uint64_t)B, (uint64_t)n_out * 2, 64, GM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    static bool attr = false;
+    if (!attr) {
+        NM_CUDA(cudaFuncSetAttribute(dense_wgrad_gen_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        NM_CUDA(cudaFuncSetAttribute(dense_wgrad_gen_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr = true;
+    }
+    const dim3 grid(g.f_tiles * g.n_tiles, g.splits);
+    if (g.nt == 128)
+        rc = nm::launch_pdl("dense_wgrad_gen_tc", dense_wgrad_gen_tc_kernel<128>, grid, dim3(256), (size_t)3 * (4 * GM * 128) + 256, nm::S(stream), mx, mdy, p);
+    else
+        rc = nm::launch_pdl("dense_wgrad_gen_tc", dense_wgrad_gen_tc_kernel<64>, grid, dim3(256), (size_t)4 * (3 * GM * 128) + 256, nm::S(stream), mx, mdy, p);
+    if (rc) return rc;
+    NM_REQUIRE(((size_t)n_in * n_out) % 4 == 0, "n_in * n_out must be a multiple of 4");
+    rc = nm::launch_pdl("dense_wgrad_gen_finish", dense_wgrad_gen_finish_kernel, dim3(nm_cdiv((size_t)n_in * n_out / 4, 256)), dim3(256), 0,
+                        nm::S(stream), (const float*)p.partial, w, dw, n_in, n_out, g.splits, scale, l1, l2);
+    if (rc || !db) return rc;
+    return nm::launch_pdl("dense_dbias_bf16", dense_dbias_bf16_kernel, dim3(nm_cdiv(n_out, 32)), dim3(256), 0, nm::S(stream),
+                          static_cast<const __nv_bfloat16*>(dy), db, B, n_out, scale);
+}
+
+}  // extern "C"

@@ -68,7 +68,7 @@ class Model:
     def finalize(self, xp=np, mode=None):
         """``mode``: None / "fp32" = FP32-exact CUDA-core kernels (per-layer launches, reference layouts);
         "bf16" = tensor-core plan for the supported layer patterns (neuromah_b200/tc_plan.py: the MNIST CNN;
-        neuromah_b200/tc_plan_gen.py: VGG-style conv stacks)."""
+        neuromah_b200/tc_plan_gen.py: VGG-style conv stacks; neuromah_b200/tc_plan_mlp.py: multi-layer perceptrons)."""
         from ..activations import Activation_Softmax
         from ..losses import Loss_CategoricalCrossentropy
         from ..losses.Activation_Softmax_Loss_CategoricalCrossentropy import \
@@ -113,8 +113,16 @@ class Model:
         if self.mode == "bf16":
             from ...tc_plan import TcCnnPlan
             from ...tc_plan_gen import TcStackPlan
-            # the MNIST pattern has its own fully fused kernels; any other VGG-style stack takes the general plan
-            self.plan = TcCnnPlan(self) if TcCnnPlan.match(self) or not TcStackPlan.match(self) else TcStackPlan(self)
+            from ...tc_plan_mlp import TcMlpPlan
+            # the MNIST pattern has its own fully fused kernels; any other VGG-style stack takes the general conv plan;
+            # Dense-only stacks (the MLP of examples/test_Dense_MNIST.py) the general tcgen05 Dense plan
+            for plan_cls in (TcCnnPlan, TcStackPlan, TcMlpPlan):
+                if plan_cls.match(self):
+                    self.plan = plan_cls(self)
+                    break
+            else:
+                raise ValueError("mode='bf16' supports these layer patterns:\n  " +
+                                 "\n  ".join(c.PATTERN for c in (TcCnnPlan, TcStackPlan, TcMlpPlan)))
         elif self.mode != "fp32":
             raise ValueError("mode must be None, 'fp32' or 'bf16'")
         # raw uint8 pixel batches: normalised on the device by 1 / uint8_denominator (examples/test_Conv2D_MNIST.py:27);

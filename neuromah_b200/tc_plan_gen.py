@@ -26,6 +26,12 @@ def _rup(a, b=64):
     return (a + b - 1) // b * b
 
 
+def _rup_in(c):
+    """Padded INPUT channel count of a conv: multiples of 64; a narrow first layer (RGB) pads to 32 only -- the general
+    conv has a 32-channel K-chunk variant (64-byte rows), which halves the bytes of the input pack and of the first conv."""
+    return 32 if c <= 32 else _rup(c)
+
+
 class TcStackPlan:
     PATTERN = ("(Conv2D(3x3,same,ReLU, out_channels % 64 == 0) x k -> MaxPooling2D(2,2)) x m -> Flatten -> "
                "Dense(-> n <= 16) -> Softmax")
@@ -91,7 +97,7 @@ class TcStackPlan:
         self.packed = {}
         for c in self.convs:
             oc, ic = c.weights.shape[:2]
-            ocp, icp = _rup(oc), _rup(ic)
+            ocp, icp = _rup(oc), _rup_in(ic)
             self.packed[id(c)] = (DeviceArray((ocp, 9, icp), np.uint16), DeviceArray((icp, 9, ocp), np.uint16), ocp, icp)
         # side stream for the data-parallel early pushes (created here, never inside a CUDA-graph capture)
         from .device import new_event, new_stream
@@ -108,7 +114,7 @@ class TcStackPlan:
         self.generation = getattr(self, "generation", 0) + (1 if self.B else 0)
         self.hw, self.B = (C, H, W), B
         z = DeviceArray.zeros
-        self.x_pad = z((B, H + 2, W + 2, _rup(C)), np.uint16)
+        self.x_pad = z((B, H + 2, W + 2, _rup_in(C)), np.uint16)
         self.steps = []                     # per block: dict(convs=[(layer, in_buf, act, dy, h, w)], pool=..., ...)
         cur, h, w = self.x_pad, H, W
         ws = 256

@@ -23,11 +23,11 @@ def _data(rng, shape, integer, lo=-2, hi=3, scale=1.0):
     return bf16_round((rng.standard_normal(shape) * scale).astype(np.float32))
 
 
-def _pack_weights(w):
+def _pack_weights(w, cp=None):
     from neuromah_b200._lib import lib
     from neuromah_b200.device import DeviceArray, stream
     oc, c = w.shape[:2]
-    ocp, cp = _rup(oc), _rup(c)
+    ocp, cp = _rup(oc), (cp or _rup(c))
     wf = DeviceArray((ocp, 9, cp), np.uint16)
     wd = DeviceArray((cp, 9, ocp), np.uint16)
     w_dev = DeviceArray.from_numpy(w)                  # keep the source alive until the (asynchronous) pack has been enqueued
@@ -92,18 +92,24 @@ def test_tc_gen_fprop_bias_relu(n, h, w, c, oc, integer):
         np.testing.assert_allclose(gi, ref2, rtol=2 ** -7, atol=2e-3)
 
 
-def test_tc_gen_first_layer_from_nchw_input():
-    """C(3 -> 64) of the VGG-style stack: f32 NCHW input packed to a haloed, channel-padded bf16 tensor on the device."""
+@pytest.mark.parametrize("cpad,u8", [(64, False), (32, False), (32, True)])
+def test_tc_gen_first_layer_from_nchw_input(cpad, u8):
+    """C(3 -> 64) of the VGG-style stack: f32 (or raw uint8) NCHW input packed to a haloed, channel-padded bf16 tensor on
+    the device; input channels padded to 64 (128-byte K chunks) or to 32 (the 64-byte K-chunk variant the plan uses)."""
     from neuromah_b200._lib import lib
     from neuromah_b200.device import DeviceArray, stream
     rng = np.random.default_rng(7)
     n, c, h, w, oc = 3, 3, 32, 32, 64
-    x = _data(rng, (n, c, h, w), True)
+    x = _data(rng, (n, c, h, w), True, 0, 4)
     wt = _data(rng, (oc, c, 3, 3), True, -1, 2)
-    wf, _, ocp, cp = _pack_weights(wt)
+    wf, _, ocp, cp = _pack_weights(wt, cpad)
     xp = DeviceArray.from_numpy(np.full((n, h + 2, w + 2, cp), 0x7FC0, np.uint16))
-    x_dev = DeviceArray.from_numpy(x)
-    lib.nm_tc_pack_input_nhwc_bf16(x_dev.p, xp.p, n, c, h, w, cp, stream())
+    if u8:
+        x_dev = DeviceArray.from_numpy(x.astype(np.uint8), dtype=np.uint8)
+        lib.nm_tc_pack_input_nhwc_u8_bf16(x_dev.p, 1.0, xp.p, n, c, h, w, cp, stream())
+    else:
+        x_dev = DeviceArray.from_numpy(x)
+        lib.nm_tc_pack_input_nhwc_bf16(x_dev.p, xp.p, n, c, h, w, cp, stream())
     np.testing.assert_array_equal(xp.numpy(), pad_nhwc(_pad_channels(x, cp)))
     y = DeviceArray.zeros((n, h + 2, w + 2, oc), np.uint16)
     lib.nm_tc_conv3x3_gen_bf16(xp.p, wf.p, None, None, y.p, n, h, w, cp, oc, 1, stream())
@@ -145,16 +151,21 @@ def test_tc_gen_dgrad_with_relu_mask(n, h, w, c, oc, integer):
         np.testing.assert_allclose(gi, refm, rtol=2 ** -7, atol=2e-2)
 
 
-@pytest.mark.parametrize("n,h,w,c,oc,integer", [(3, 8, 8, 128, 256, True), (2, 32, 32, 64, 64, True), (3, 32, 32, 3, 64, True),
-                                                (9, 16, 16, 64, 128, True), (5, 8, 8, 256, 256, False)])
-def test_tc_gen_wgrad_and_bias_gradient(n, h, w, c, oc, integer):
+@pytest.mark.parametrize("n,h,w,c,oc,integer,cpad", [(3, 8, 8, 128, 256, True, None), (2, 32, 32, 64, 64, True, None),
+                                                     (3, 32, 32, 3, 64, True, None), (3, 32, 32, 3, 64, True, 32),
+                                                     (9, 16, 16, 64, 128, True, None), (5, 8, 8, 256, 256, False, None),
+                                                     (1, 8, 8, 64, 64, True, None), (40, 16, 16, 3, 128, True, 32)])
+def test_tc_gen_wgrad_and_bias_gradient(n, h, w, c, oc, integer, cpad):
+    """dW and the bias gradient (column sums of dY formed by an extra MMA against a tile of ones inside the wgrad kernel,
+    spread over the CTAs that share a pixel range): bit-exact on integer data for one to eight input-channel chunks,
+    fewer pixel blocks than CTAs sharing them (n = 1), and input channels padded to 32."""
     from neuromah_b200._lib import lib
     from neuromah_b200.device import DeviceArray, stream
     rng = np.random.default_rng(300 + n + c + oc)
     x = _data(rng, (n, c, h, w), integer)
     wt = _data(rng, (oc, c, 3, 3), integer, -1, 2, 0.05)
     dy = _data(rng, (n, oc, h, w), integer)
-    ocp, cp = _rup(oc), _rup(c)
+    ocp, cp = _rup(oc), (cpad or _rup(c))
     xp, dyp = DeviceArray.from_numpy(pad_nhwc(_pad_channels(x, cp))), DeviceArray.from_numpy(pad_nhwc(dy))
     dw = DeviceArray.from_numpy(np.full((oc, c, 3, 3), np.nan, np.float32))
     db = DeviceArray.from_numpy(np.full((oc,), np.nan, np.float32))
