@@ -35,7 +35,6 @@ struct ConvGenParams {
     int a_boxes, a_box_rows;             // an activation stage = a_boxes TMA boxes of a_box_rows (multiple of 8) rows
     uint32_t a_stage_bytes;
     int a_stages, b_stages;
-    int b_resident;                      // the whole filter bank (9 * k_chunks slices, one N tile) stays in shared memory
     __nv_bfloat16* out;                  // [rows_total][Cout], haloed grid
     const __nv_bfloat16* mask;           // optional [rows_total][Cout]: out = mask > 0 ? acc : 0   (ReLU' of the layer below)
     const float* bias;                   // optional [Cout]
@@ -43,15 +42,13 @@ struct ConvGenParams {
 };
 
 // D[MSUB*128 pixels, NT] = sum_{chunk, tap} A_chunk[pixel + shift(tap), 0:64] * B[tap][n0 : n0+NT, chunk]^T
-// Streaming the filter bank costs NT*128 bytes of L2 reads per 4*MSUB MMAs (measured: with MSUB = 2 the conv ran at half
-// its MMA schedule, L2-bound on the weight stream).  Two remedies, chosen on the host:
-//  * MSUB = 4 -- a weight byte feeds 512 pixels; the four accumulators fill TMEM (4 * 128 columns), so the accumulator is
-//    single-buffered and both epilogue groups drain each tile (two sub-tiles each);
-//  * b_resident -- when the whole bank of the CTA's (single) N tile fits next to the activation stages (Cin*Cout <= 64*64
-//    at 32x32), it is loaded once per CTA and never streamed again (MSUB = 2, double-buffered accumulators).
+// MSUB = 2: two M = 128 accumulators share every streamed weight slice; 2 x (2 x NT) TMEM columns double-buffer them against
+// the two epilogue groups.  (Measured and dropped, see DESIGN.md experiment log: MSUB = 4 -- single-buffered accumulators
+// expose the epilogue -- and a shared-memory-resident filter bank -- 8-15 % slower than streaming it from L2.)
 template <int NT, int MSUB, int G_KC>
 __global__ void __launch_bounds__(384, 1)
-conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvGenParams p) {
+conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const __grid_constant__ CUtensorMap map_out, ConvGenParams p) {
     constexpr int G_ROWB = G_KC * 2;
     constexpr uint64_t TMPL = desc_template(16, 8 * G_ROWB, G_KC == 64 ? LAYOUT_SW128 : LAYOUT_SW64);     // K-major, SBO = 8 rows
     constexpr uint32_t IDESC = idesc_bf16(G_M, NT, 0, 0);
@@ -65,7 +62,9 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* a_smem = smem;
     uint8_t* b_smem = smem + (size_t)p.a_stages * p.a_stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)p.b_stages * B_BYTES);
+    // epilogue staging: 32 rows x 32 channels (2 KB, SWIZZLE_64B) per epilogue warp, drained by TMA stores
+    uint8_t* o_smem = b_smem + (size_t)p.b_stages * B_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(o_smem + 8 * 2048);
     uint64_t* afull = bars;
     uint64_t* aempty = afull + p.a_stages;
     uint64_t* bfull = aempty + p.a_stages;
@@ -76,11 +75,11 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_trigger();
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_out); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.a_stages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < p.b_stages; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], NBUF == 2 ? 4 : 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }      // one group of 4 warps per buffer
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -94,11 +93,6 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // ============================== TMA producer ==============================
         if (lane == 0) {
             int a_stage = 0, b_stage = 0; uint32_t a_phase = 0, b_phase = 0;
-            if (p.b_resident && (int)blockIdx.x < p.num_tiles)
-                for (int j = 0; j < 9 * p.k_chunks; ++j) {                  // slice j = (chunk, tap), loaded once
-                    mbar_expect_tx(&bfull[j], B_BYTES);
-                    tma_load_2d(b_smem + (size_t)j * B_BYTES, &map_b, (j % 9) * p.Cin + (j / 9) * G_KC, 0, &bfull[j]);
-                }
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * NT;
                 const int row0 = m_tile * TILE_ROWS - (p.Wp + 1);                      // negative / past-the-end rows read as zero
@@ -109,7 +103,6 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         tma_load_2d(a_smem + (size_t)a_stage * p.a_stage_bytes + (size_t)j * p.a_box_rows * G_ROWB, &map_a,
                                     kc * G_KC, row0 + j * p.a_box_rows, &afull[a_stage]);
                     if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
-                    if (p.b_resident) continue;
                     for (int tap = 0; tap < 9; ++tap) {
                         mbar_wait(&bempty[b_stage], b_phase ^ 1);
                         mbar_expect_tx(&bfull[b_stage], B_BYTES);
@@ -121,55 +114,66 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
     } else if (warp == 1) {
         // ============================== MMA issuer (one elected lane runs the whole loop) ==============================
-        // ncu (profiles/r01f_ncu_conv_gen_c4_fprop.txt): with one barrier wait -> issue -> commit round per weight slice the
-        // tensor pipe idled ~350 cycles per slice (58 % active) -- UTCHMMA issue is back-pressured, so when the issuer
-        // returns from the last MMA of a slice only one or two MMAs are still queued, fewer than the wait + descriptor set-up
-        // of the next slice takes.  The wait for the NEXT slice is therefore done before the last two MMAs of the current
-        // one are issued, where it hides under six queued MMAs.
+        // The issuing thread is INSTRUCTION-bound, not tensor-bound, unless its loop is lean: ncu (profiles/r02k_*) showed
+        // ~130 SASS instructions per (chunk, tap) iteration around 4-8 UTCHMMAs (64-bit descriptor arithmetic, tap / 3 and
+        // tap % 3, parameters re-read from constant memory, R2UR moves) -- ~550 cycles per iteration against 130-510 cycles
+        // of MMA work, i.e. every layer ran at 0.45-0.65 of its MMA schedule and the epilogue warps sat in mbarrier waits.
+        // Now: the nine taps are unrolled, the per-tap row shifts live in registers, descriptors are {constant high word,
+        // 32-bit low word} pairs whose low word takes immediate adds, and the accumulate flag is a compile-time constant
+        // for every MMA but the first of a chunk.
+        // The wait for the NEXT weight slice is issued before the last two MMAs of the current one (UTCHMMA issue is
+        // back-pressured, so it hides under the queued MMAs; r01f: tensor pipe 58 % -> 74 % active).
         if (elect_one()) {
+            constexpr uint32_t DESC_HI = (uint32_t)(TMPL >> 32);
+            constexpr uint32_t DESC_LO = (uint32_t)(TMPL & 0xFFFFFFFFull);
+            auto mk = [](uint32_t lo) -> uint64_t { return ((uint64_t)DESC_HI << 32) | (uint64_t)(DESC_LO | (lo & 0x3FFFu)); };
             const int my_tiles = (int)blockIdx.x < p.num_tiles ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-            const int total_b = my_tiles * p.k_chunks * 9;                  // weight slices this CTA consumes
+            const int k_chunks = p.k_chunks, a_stages = p.a_stages, b_stages = p.b_stages;
+            const uint32_t a_stage16 = p.a_stage_bytes >> 4, a_base16 = smem_u32(a_smem) >> 4, b_base16 = smem_u32(b_smem) >> 4;
+            uint32_t shift16[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) shift16[t] = (uint32_t)(((t / 3) * p.Wp + (t % 3)) * G_ROWB) >> 4;
+            int remaining_b = my_tiles * k_chunks * 9;                       // weight slices this CTA still has to consume
             int a_stage = 0, b_stage = 0; uint32_t a_phase = 0, b_phase = 0;
-            int b_done = 0;
             bool b_ready = false;                                            // bfull of the current slice already waited for
-            int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            for (int it = 0; it < my_tiles; ++it) {
                 const int acc = NBUF == 2 ? (it & 1) : 0;
                 const uint32_t use = NBUF == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;   // how often this buffer has been used
                 mbar_wait(&tempty[acc], (use & 1) ^ 1);
                 fence_after_sync();
                 const uint32_t d_addr = tmem_base + acc * NACC;
-                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                for (int kc = 0; kc < k_chunks; ++kc) {
                     mbar_wait(&afull[a_stage], a_phase);
-                    const uint64_t a_desc0 = desc_at(TMPL, smem_u32(a_smem + (size_t)a_stage * p.a_stage_bytes));
+                    const uint32_t a16 = a_base16 + (uint32_t)a_stage * a_stage16;
+#pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        const int bs = p.b_resident ? kc * 9 + tap : b_stage;
-                        if (!b_ready) mbar_wait(&bfull[bs], p.b_resident ? 0u : b_phase);   // resident: completes once, stays complete
+                        if (!b_ready) mbar_wait(&bfull[b_stage], b_phase);
                         b_ready = false;
                         fence_after_sync();
-                        const uint64_t b_desc0 = desc_at(TMPL, smem_u32(b_smem + (size_t)bs * B_BYTES));
-                        const uint32_t shift = (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * G_ROWB;
+                        const uint32_t b16 = b_base16 + (uint32_t)b_stage * (B_BYTES >> 4);
+                        const uint32_t at16 = a16 + shift16[tap];
+                        --remaining_b;
 #pragma unroll
                         for (int kk = 0; kk < G_KC / 16; ++kk)
 #pragma unroll
                             for (int ms = 0; ms < MSUB; ++ms) {
-                                if (kk * MSUB + ms == (G_KC / 16) * MSUB - 2 && !p.b_resident && b_done + 1 < total_b) {
-                                    const int nb = b_stage + 1 == p.b_stages ? 0 : b_stage + 1;
+                                if (kk * MSUB + ms == (G_KC / 16) * MSUB - 2 && remaining_b > 0) {
+                                    const int nb = b_stage + 1 == b_stages ? 0 : b_stage + 1;
                                     mbar_wait(&bfull[nb], nb == 0 ? b_phase ^ 1 : b_phase);
                                     b_ready = true;
                                 }
-                                mma_bf16(d_addr + ms * NT, a_desc0 + ((shift + ms * G_M * G_ROWB + kk * 32) >> 4),
-                                         b_desc0 + ((kk * 32) >> 4), IDESC, (kc | tap | kk) != 0);
+                                const uint32_t accum = (tap | kk) != 0 ? 1u : (uint32_t)(kc != 0);
+                                mma_bf16(d_addr + ms * NT, mk(at16 + ((ms * G_M * G_ROWB + kk * 32) >> 4)), mk(b16 + ((kk * 32) >> 4)),
+                                         IDESC, accum);
                             }
-                        if (!p.b_resident) mma_commit(&bempty[b_stage]);            // weight slice reusable
+                        mma_commit(&bempty[b_stage]);                               // weight slice reusable
                         if (tap == 8) {
                             mma_commit(&aempty[a_stage]);                           // activation tile reusable
-                            if (kc == p.k_chunks - 1) mma_commit(&tfull[acc]);      // accumulators ready for the epilogue
+                            if (kc == k_chunks - 1) mma_commit(&tfull[acc]);        // accumulators ready for the epilogue
                         }
-                        ++b_done;
-                        if (!p.b_resident && ++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
+                        if (++b_stage == b_stages) { b_stage = 0; b_phase ^= 1; }
                     }
-                    if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
+                    if (++a_stage == a_stages) { a_stage = 0; a_phase ^= 1; }
                 }
             }
         }
@@ -179,14 +183,18 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // NBUF == 2: group g drains accumulator buffer g, i.e. every second tile, all its sub-tiles.
         // NBUF == 1: both groups drain every tile, MSUB / 2 sub-tiles each.
         const int q = warp & 3;                       // TMEM sub-partition = lanes [32q, 32q+32)
+        // Two groups of 4 warps: group g drains accumulator buffer g, i.e. every second tile, both 128-row sub-tiles.
+        // (Four groups -- one per (buffer, sub-tile) -- were measured: no gain, the tile period of the narrow layers is set
+        // by the refill latency of the weight-slice ring, see the host-side stage count.)
+        static_assert(NBUF == 2 && MSUB == 2, "epilogue groups are laid out for two buffers x two sub-tiles");
         const int grp = (warp - 4) >> 2;
         const int plane = p.Hp * p.Wp;
-        constexpr int IT_STEP = NBUF == 2 ? 2 : 1;
-        const int acc = NBUF == 2 ? grp : 0;
-        const int ms_lo = NBUF == 2 ? 0 : grp * (MSUB / 2), ms_hi = NBUF == 2 ? MSUB : ms_lo + MSUB / 2;
-        int it = NBUF == 2 ? grp : 0;
+        constexpr int IT_STEP = 2;
+        const int acc = grp;
+        const int ms_lo = 0, ms_hi = MSUB;
+        int it = acc;
         for (int tile = blockIdx.x + it * gridDim.x; tile < p.num_tiles; tile += IT_STEP * gridDim.x, it += IT_STEP) {
-            const uint32_t use = NBUF == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
+            const uint32_t use = (uint32_t)(it >> 1);
             mbar_wait(&tfull[acc], use & 1);
             fence_after_sync();
             const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * NT;
@@ -197,7 +205,12 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 const bool in_range = row < p.rows_total;
                 const bool interior = in_range && hh >= 1 && hh <= p.H && ww >= 1 && ww <= p.W;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NACC + ms * NT;
-                __nv_bfloat16* dst = p.out + (size_t)row * p.Cout + n0;
+                // Stores go through shared memory and TMA: a thread owns a ROW of the tile, so direct 16-byte global stores
+                // make every warp instruction touch 32 different 128-byte lines with half a sector each (ncu: 303 MB of
+                // L1->L2 write traffic for 151 MB of output).  The warp's 32 rows x 32 channels are staged in the swizzled
+                // layout and leave as one bulk store (UTMASTG) per 32-column chunk.
+                uint8_t* stage = o_smem + (size_t)(warp - 4) * 2048;
+                const int row_base = m_tile * TILE_ROWS + ms * G_M + q * 32;
                 const bool use_mask = p.mask != nullptr && interior;
                 const __nv_bfloat16* msk = p.mask + (size_t)row * p.Cout + n0;
                 // Software pipeline over 32-column chunks: the TMEM load of chunk i+1 and the mask read of chunk i are in
@@ -219,6 +232,8 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         tmem_ld_x16(taddr + c0 + 32, v[(ci + 1) & 1]);
                         tmem_ld_x16(taddr + c0 + 48, v[(ci + 1) & 1] + 16);
                     }
+                    if (lane == 0) tma_store_wait_read();             // the previous bulk store has finished reading the staging buffer
+                    __syncwarp();
                     if (in_range) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
@@ -248,15 +263,20 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                             uint4 o;
                             o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
                             o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-                            *reinterpret_cast<uint4*>(dst + c0 + g * 8) = o;
+                            *reinterpret_cast<uint4*>(stage + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;   // SWIZZLE_64B
                         }
                     }
+                    tma_store_fence();                                // 32 channels staged: hand them to the TMA
+                    __syncwarp();
+                    if (lane == 0 && row_base < p.rows_total)
+                        tma_store_2d(&map_out, stage, n0 + c0, row_base);         // rows past the tensor are clipped
                 }
             }
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);        // accumulator buffer drained: the MMA warp may overwrite it
         }
+        if (lane == 0) tma_store_wait_all();                 // every bulk store of this warp has landed
     }
     fence_before_sync();
     __syncthreads();
@@ -375,8 +395,12 @@ conv3x3_wgrad_gen_kernel(const __grid_constant__ CUtensorMap map_dy, const __gri
                         const uint32_t shift = (uint32_t)(r * p.Wp + ks * 16) * (CB * 2);
                         mma_bf16(tmem_base + r * 3 * CB, adesc, x_desc0 + (shift >> 4), IDESC3, !(it == 0 && ks == 0));
                     }
-                    if (bias_here)          // first bias block of this CTA is its it == cq
-                        mma_bf16(tmem_base + 9 * CB, adesc, ones_desc0 + ((uint32_t)(ks * 16 * CB * 2) >> 4), IDESC_ONES, !(it == cq && ks == 0));
+                }
+                if (bias_here) {            // one branch per block (the issuing thread is instruction-bound); first one: it == cq
+#pragma unroll
+                    for (int ks = 0; ks < G_M / 16; ++ks)
+                        mma_bf16(tmem_base + 9 * CB, a_desc0 + ((ks * 16 * 128) >> 4), ones_desc0 + ((uint32_t)(ks * 16 * CB * 2) >> 4),
+                                 IDESC_ONES, !(it == cq && ks == 0));
                 }
                 mma_commit(&empty[stage]);
             }
@@ -418,31 +442,48 @@ conv3x3_wgrad_gen_kernel(const __grid_constant__ CUtensorMap map_dy, const __gri
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// partial [splits][OCp][9][Cp] -> OIHW [OC][C][3][3].  Block = 64 outputs x 8 slices: slice j sums splits j, j+8, ... in
-// order, the eight slice sums are then added in order -- a fixed summation tree, so the result is bitwise repeatable.
-constexpr int GR_SLICES = 8;
-__global__ void __launch_bounds__(64 * GR_SLICES)
+// partial [splits][OCp][9][Cp] -> OIHW [OC][C][3][3].  A block owns 64 work items x SL slices: slice j sums splits j, j + SL,
+// ... in order, the slice sums are then added in order -- a fixed summation tree, so the result is bitwise repeatable.
+// VEC = 4: a work item is four consecutive input channels (one 16-byte load per split; C % 4 == 0); VEC = 1: one element
+// (the 3-channel first layer).  (The scalar 8-slice version took 131 us per VGG step over the six layers: 4-byte loads and,
+// for the first layer, 27 blocks summing 296 splits.)
+template <int VEC, int SL>
+__global__ void __launch_bounds__(64 * SL)
 wgrad_gen_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int OC, int C, int OCp, int Cp) {
-    __shared__ float red[GR_SLICES][64];
+    __shared__ float red[SL][64][VEC];
     pdl_trigger();
     pdl_wait();
-    const int slice = threadIdx.x >> 6, slices = blockDim.x >> 6;
-    const int i = blockIdx.x * 64 + (threadIdx.x & 63);         // i = (oc * 9 + tap) * C + c : coalesced reads
-    const bool ok = i < OC * C * 9;
+    const int slice = threadIdx.x >> 6, t = threadIdx.x & 63;
+    const int cg = C / VEC;                                      // work items per (oc, tap)
+    const int i = blockIdx.x * 64 + t;                           // i = (oc * 9 + tap) * cg + c / VEC : coalesced reads
+    const bool ok = i < OC * 9 * cg;
     int oc = 0, tap = 0, c = 0;
-    float a = 0.f;
+    float a[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) a[v] = 0.f;
     if (ok) {
-        oc = i / (9 * C); const int rem = i - oc * 9 * C; tap = rem / C; c = rem - tap * C;
+        oc = i / (9 * cg); const int rem = i - oc * 9 * cg; tap = rem / cg; c = (rem - tap * cg) * VEC;
         const size_t src = ((size_t)oc * 9 + tap) * Cp + c, plane = (size_t)OCp * 9 * Cp;
 #pragma unroll 4
-        for (int s = slice; s < splits; s += slices) a += __ldg(partial + s * plane + src);        // unrolled: loads in flight together
+        for (int s = slice; s < splits; s += SL) {               // unrolled: loads in flight together
+            if (VEC == 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(partial + s * plane + src));
+                a[0] += v.x; a[1 % VEC] += v.y; a[2 % VEC] += v.z; a[3 % VEC] += v.w;
+            } else {
+                a[0] += __ldg(partial + s * plane + src);
+            }
+        }
     }
-    red[slice][threadIdx.x & 63] = a;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) red[slice][t][v] = a[v];
     __syncthreads();
     if (slice == 0 && ok) {
-        float t = 0.f;
-        for (int k = 0; k < slices; ++k) t += red[k][threadIdx.x];
-        dw[((size_t)oc * C + c) * 9 + tap] = t;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            float tsum = 0.f;
+            for (int k = 0; k < SL; ++k) tsum += red[k][t][v];
+            dw[((size_t)oc * C + c + v) * 9 + tap] = tsum;
+        }
     }
 }
 
@@ -528,19 +569,23 @@ int launch_conv_gen(const void* x_pad, const void* w_packed, ConvGenParams p, cu
     if (rc) return rc;
     rc = make_map_2d(&mb, w_packed, (uint64_t)9 * p.Cin, (uint64_t)p.Cout, (uint64_t)9 * p.Cin * 2, G_KC, NT, SWZ);
     if (rc) return rc;
+    CUtensorMap mo;
+    rc = make_map_2d(&mo, p.out, (uint64_t)p.Cout, (uint64_t)p.rows_total, (uint64_t)p.Cout * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
     constexpr int B_BYTES = NT * G_ROWB;
-    if (p.b_resident) {
-        p.b_stages = 9 * p.k_chunks;
-        p.a_stages = (G_SMEM_BUDGET - p.b_stages * B_BYTES) / (int)p.a_stage_bytes;
-        if (p.a_stages > 4) p.a_stages = 4;
-    } else {
-        p.a_stages = 2;
-        const int budget = G_SMEM_BUDGET - p.a_stages * (int)p.a_stage_bytes;
-        p.b_stages = budget / B_BYTES > 9 ? 9 : budget / B_BYTES;
+    constexpr int O_BYTES = 8 * 2048;                           // epilogue staging, 2 KB per epilogue warp
+    p.a_stages = 2;
+    {
+        const int budget = G_SMEM_BUDGET - O_BYTES - p.a_stages * (int)p.a_stage_bytes;
+        // The weight-slice ring must cover the refill latency of a slot (MMAs complete -> commit -> producer -> TMA from L2 ->
+        // mbarrier: ~4000 cycles measured) with MMA work: a slice is worth only 190-510 cycles, so the narrow layers (N tile
+        // of 64, one or two K chunks) need far more than one tile's nine slices in flight -- with nine, c1 / c2 ran at the
+        // ring's latency (~4500 cycles per tile) instead of their MMA schedule (1700 / 3500).
+        p.b_stages = budget / B_BYTES > 24 ? 24 : budget / B_BYTES;
     }
     NM_REQUIRE(p.a_stages >= 2 && p.b_stages >= 2, "image too wide for the shared-memory budget");
     NM_REQUIRE(2 * (p.a_stages + p.b_stages) + 4 <= 62, "too many pipeline stages for the barrier block");
-    const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * B_BYTES + 512;   // + mbarriers
+    const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * B_BYTES + O_BYTES + 512;   // + mbarriers
     auto kern = conv3x3_gen_kernel<NT, MSUB, G_KC>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -548,7 +593,7 @@ int launch_conv_gen(const void* x_pad, const void* w_packed, ConvGenParams p, cu
         attr_set = true;
     }
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    return nm::launch_pdl("conv3x3_gen", kern, dim3(grid), dim3(384), smem, st, ma, mb, p);
+    return nm::launch_pdl("conv3x3_gen", kern, dim3(grid), dim3(384), smem, st, ma, mb, mo, p);
 }
 
 struct WgradGenPlan { int moc, c_chunks, items, splits, num_kblocks, rows_total; };
@@ -615,19 +660,10 @@ int nm_tc_conv3x3_gen_bf16(const void* x_pad, const void* w_packed, const float*
     p.mask = static_cast<const __nv_bfloat16*>(relu_mask);
     p.bias = bias;
     p.relu = relu;
-    // Measured on B200 (profiles/r01f_vgg_launches_b1024_v1.csv vs _v2.csv): the streamed MSUB = 2 form is the fastest -- the
-    // single-buffered accumulator of MSUB = 4 exposes the epilogue, and the resident bank is 8-15 % slower than streaming
-    // it from L2.  NM_TC_GEN_MODE=2 selects MSUB = 4, =3 the resident bank where it fits (experiments only).
-    static int mode = -1;
-    if (mode < 0) { const char* e = getenv("NM_TC_GEN_MODE"); mode = e ? atoi(e) : 1; }
     conv_gen_tile(p, 2, kc);
     if (kc == 32)
         return nt == 128 ? launch_conv_gen<128, 2, 32>(x_pad, w_packed, p, nm::S(stream)) : launch_conv_gen<64, 2, 32>(x_pad, w_packed, p, nm::S(stream));
-    p.b_resident = mode == 3 && p.n_tiles == 1 && 9 * p.k_chunks * nt * 128 + 2 * (int)p.a_stage_bytes <= G_SMEM_BUDGET;
-    if (mode != 2 || p.b_resident)
-        return nt == 128 ? launch_conv_gen<128, 2, 64>(x_pad, w_packed, p, nm::S(stream)) : launch_conv_gen<64, 2, 64>(x_pad, w_packed, p, nm::S(stream));
-    conv_gen_tile(p, 4, kc);
-    return nt == 128 ? launch_conv_gen<128, 4, 64>(x_pad, w_packed, p, nm::S(stream)) : launch_conv_gen<64, 4, 64>(x_pad, w_packed, p, nm::S(stream));
+    return nt == 128 ? launch_conv_gen<128, 2, 64>(x_pad, w_packed, p, nm::S(stream)) : launch_conv_gen<64, 2, 64>(x_pad, w_packed, p, nm::S(stream));
 }
 
 size_t nm_tc_conv3x3_wgrad_gen_workspace(int N, int H, int W, int C, int Cp, int OCp) {
@@ -680,9 +716,12 @@ int nm_tc_conv3x3_wgrad_gen_bf16(const void* x_pad, const void* dy_pad, float* d
              ? nm::launch_pdl("conv3x3_wgrad_gen", conv3x3_wgrad_gen_kernel<128>, dim3(items, p.splits), dim3(256), smem, nm::S(stream), mdy, mx, p)
              : nm::launch_pdl("conv3x3_wgrad_gen", conv3x3_wgrad_gen_kernel<64>, dim3(items, p.splits), dim3(256), smem, nm::S(stream), mdy, mx, p);
     if (rc) return rc;
-    rc = nm::launch_pdl("wgrad_gen_reduce", wgrad_gen_reduce_kernel, dim3(nm_cdiv((size_t)OC * C * 9, 64)),
-                        dim3(64 * (p.splits >= 64 ? GR_SLICES : p.splits >= 16 ? 2 : 1)), 0, nm::S(stream),
-                        (const float*)p.partial, dw, p.splits, OC, C, OCp, Cp);
+    if (C % 4 == 0)
+        rc = nm::launch_pdl("wgrad_gen_reduce", wgrad_gen_reduce_kernel<4, 8>, dim3(nm_cdiv((size_t)OC * (C / 4) * 9, 64)), dim3(64 * 8), 0,
+                            nm::S(stream), (const float*)p.partial, dw, p.splits, OC, C, OCp, Cp);
+    else
+        rc = nm::launch_pdl("wgrad_gen_reduce", wgrad_gen_reduce_kernel<1, 16>, dim3(nm_cdiv((size_t)OC * C * 9, 64)), dim3(64 * 16), 0,
+                            nm::S(stream), (const float*)p.partial, dw, p.splits, OC, C, OCp, Cp);
     if (rc || !dbias) return rc;
     // column sums of dY were formed inside the wgrad kernel (one partial per CTA): fixed-order final sum
     return nm::launch_pdl("dbias_final", dbias_final_kernel, dim3(nm_cdiv((size_t)OC * 32, 256)), dim3(256), 0, nm::S(stream),

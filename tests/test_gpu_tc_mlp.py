@@ -140,7 +140,7 @@ def test_tc_mlp_plan_step_gradients_from_identical_state(spec_fn, batch):
         trainable = [l for l in model.layers if hasattr(l, "weights")]
         for (layer, name, _, size, _) in model.arena.table:
             depth = len(trainable) - 1 - [id(t) for t in trainable].index(id(layer))       # 0 = the head
-            errs.append((rel_l2(g[off:off + size], gr[off:off + size]), 3e-2 if depth <= 1 else 6e-2))
+            errs.append((rel_l2(g[off:off + size], gr[off:off + size]), 3e-2 if depth == 0 else 6e-2))
             off += size
         print("step", s, " ".join(f"{e:.4f}" for e, _ in errs))
         assert all(e <= tol for e, tol in errs), errs
