@@ -19,6 +19,14 @@
 #include "nm_tc_host.cuh"
 #include <cstdlib>
 
+#ifdef NM_ABLATE   // timing experiments only: CTA 0 records clock64() per tile and role (scratch/gen_trace.py)
+static long long* g_gen_trace = nullptr;
+extern "C" int nm_tc_debug_set_trace_gen(void* buf) { g_gen_trace = static_cast<long long*>(buf); return 0; }
+#define GEN_TRACE(P, it, slot) do { if ((P).trace && blockIdx.x == 0 && (it) < 48) (P).trace[(it) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define GEN_TRACE(P, it, slot) do { } while (0)
+#endif
+
 namespace {
 
 using namespace tc;
@@ -39,13 +47,19 @@ struct ConvGenParams {
     const __nv_bfloat16* mask;           // optional [rows_total][Cout]: out = mask > 0 ? acc : 0   (ReLU' of the layer below)
     const float* bias;                   // optional [Cout]
     int relu;
+    long long* trace;                    // ablation builds only
 };
 
 // D[MSUB*128 pixels, NT] = sum_{chunk, tap} A_chunk[pixel + shift(tap), 0:64] * B[tap][n0 : n0+NT, chunk]^T
 // MSUB = 2: two M = 128 accumulators share every streamed weight slice; 2 x (2 x NT) TMEM columns double-buffer them against
 // the two epilogue groups.  (Measured and dropped, see DESIGN.md experiment log: MSUB = 4 -- single-buffered accumulators
 // expose the epilogue -- and a shared-memory-resident filter bank -- 8-15 % slower than streaming it from L2.)
-template <int NT, int MSUB, int G_KC>
+// TG = filter taps per weight-ring slot.  Every slot costs one producer round (wait, expect, TMA) and one issuer round
+// (wait, commit) of shared-memory barrier operations in a single thread, ~300 cycles (ablation: with loads, MMAs and epilogue
+// switched off the kernel still took 9 x 300 cycles per tile and chunk).  A tap of an N = 64 tile is worth only 190-380
+// cycles of MMAs, so those layers take a whole filter ROW per slot (TG = 3); N = 128 tiles (510 cycles per tap, 16 KB per
+// slice) keep one tap per slot.
+template <int NT, int MSUB, int G_KC, int TG>
 __global__ void __launch_bounds__(384, 1)
 conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ CUtensorMap map_out, ConvGenParams p) {
@@ -53,7 +67,10 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     constexpr uint64_t TMPL = desc_template(16, 8 * G_ROWB, G_KC == 64 ? LAYOUT_SW128 : LAYOUT_SW64);     // K-major, SBO = 8 rows
     constexpr uint32_t IDESC = idesc_bf16(G_M, NT, 0, 0);
     constexpr int TILE_ROWS = G_M * MSUB;
-    constexpr int B_BYTES = NT * G_ROWB;                                      // one (tap, chunk) weight slice
+    constexpr int B_SLICE = NT * G_ROWB;                                      // one (tap, chunk) weight slice
+    constexpr int B_BYTES = TG * B_SLICE;                                     // one ring slot
+    constexpr int GROUPS = 9 / TG;
+    static_assert(TG == 1 || TG == 3, "a slot holds one tap or one filter row");
     constexpr int NACC = MSUB * NT;                                           // accumulator columns per buffer
     constexpr int NBUF = 2 * NACC <= 512 ? 2 : 1;
     constexpr uint32_t TMEM_COLS = NBUF * NACC <= 256 ? 256 : 512;
@@ -98,15 +115,25 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 const int row0 = m_tile * TILE_ROWS - (p.Wp + 1);                      // negative / past-the-end rows read as zero
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     mbar_wait(&aempty[a_stage], a_phase ^ 1);
+                    if (NM_DBG(19)) mbar_arrive(&afull[a_stage]);
+                    else {
                     mbar_expect_tx(&afull[a_stage], (uint32_t)(p.a_boxes * p.a_box_rows) * G_ROWB);
                     for (int j = 0; j < p.a_boxes; ++j)
                         tma_load_2d(a_smem + (size_t)a_stage * p.a_stage_bytes + (size_t)j * p.a_box_rows * G_ROWB, &map_a,
                                     kc * G_KC, row0 + j * p.a_box_rows, &afull[a_stage]);
+                    }
                     if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
-                    for (int tap = 0; tap < 9; ++tap) {
+                    if (kc == 0) GEN_TRACE(p, tile / (int)gridDim.x, 0);
+                    for (int grp = 0; grp < GROUPS; ++grp) {
                         mbar_wait(&bempty[b_stage], b_phase ^ 1);
+                        if (NM_DBG(18)) mbar_arrive(&bfull[b_stage]);
+                        else {
                         mbar_expect_tx(&bfull[b_stage], B_BYTES);
-                        tma_load_2d(b_smem + (size_t)b_stage * B_BYTES, &map_b, tap * p.Cin + kc * G_KC, n0, &bfull[b_stage]);
+#pragma unroll
+                        for (int t = 0; t < TG; ++t)
+                            tma_load_2d(b_smem + (size_t)b_stage * B_BYTES + t * B_SLICE, &map_b, (grp * TG + t) * p.Cin + kc * G_KC, n0,
+                                        &bfull[b_stage]);
+                        }
                         if (++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
                     }
                 }
@@ -133,43 +160,50 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             uint32_t shift16[9];
 #pragma unroll
             for (int t = 0; t < 9; ++t) shift16[t] = (uint32_t)(((t / 3) * p.Wp + (t % 3)) * G_ROWB) >> 4;
-            int remaining_b = my_tiles * k_chunks * 9;                       // weight slices this CTA still has to consume
+            int remaining_b = my_tiles * k_chunks * GROUPS;                  // weight slots this CTA still has to consume
             int a_stage = 0, b_stage = 0; uint32_t a_phase = 0, b_phase = 0;
-            bool b_ready = false;                                            // bfull of the current slice already waited for
+            bool b_ready = false;                                            // bfull of the current slot already waited for
             for (int it = 0; it < my_tiles; ++it) {
                 const int acc = NBUF == 2 ? (it & 1) : 0;
                 const uint32_t use = NBUF == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;   // how often this buffer has been used
+                GEN_TRACE(p, it, 2);
                 mbar_wait(&tempty[acc], (use & 1) ^ 1);
+                GEN_TRACE(p, it, 3);
                 fence_after_sync();
                 const uint32_t d_addr = tmem_base + acc * NACC;
                 for (int kc = 0; kc < k_chunks; ++kc) {
                     mbar_wait(&afull[a_stage], a_phase);
+                    if (kc == 0) GEN_TRACE(p, it, 4);
                     const uint32_t a16 = a_base16 + (uint32_t)a_stage * a_stage16;
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
+                    for (int grp = 0; grp < GROUPS; ++grp) {
                         if (!b_ready) mbar_wait(&bfull[b_stage], b_phase);
                         b_ready = false;
                         fence_after_sync();
                         const uint32_t b16 = b_base16 + (uint32_t)b_stage * (B_BYTES >> 4);
-                        const uint32_t at16 = a16 + shift16[tap];
                         --remaining_b;
 #pragma unroll
-                        for (int kk = 0; kk < G_KC / 16; ++kk)
+                        for (int t = 0; t < TG; ++t) {
+                            const int tap = grp * TG + t;
+                            const uint32_t at16 = a16 + shift16[tap];
 #pragma unroll
-                            for (int ms = 0; ms < MSUB; ++ms) {
-                                if (kk * MSUB + ms == (G_KC / 16) * MSUB - 2 && remaining_b > 0) {
-                                    const int nb = b_stage + 1 == b_stages ? 0 : b_stage + 1;
-                                    mbar_wait(&bfull[nb], nb == 0 ? b_phase ^ 1 : b_phase);
-                                    b_ready = true;
+                            for (int kk = 0; kk < G_KC / 16; ++kk)
+#pragma unroll
+                                for (int ms = 0; ms < MSUB; ++ms) {
+                                    if (t == TG - 1 && kk * MSUB + ms == (G_KC / 16) * MSUB - 2 && remaining_b > 0) {
+                                        const int nb = b_stage + 1 == b_stages ? 0 : b_stage + 1;
+                                        mbar_wait(&bfull[nb], nb == 0 ? b_phase ^ 1 : b_phase);
+                                        b_ready = true;
+                                    }
+                                    const uint32_t accum = (tap | kk) != 0 ? 1u : (uint32_t)(kc != 0);
+                                    if (!NM_DBG(17)) mma_bf16(d_addr + ms * NT, mk(at16 + ((ms * G_M * G_ROWB + kk * 32) >> 4)),
+                                                              mk(b16 + ((t * B_SLICE + kk * 32) >> 4)), IDESC, accum);
                                 }
-                                const uint32_t accum = (tap | kk) != 0 ? 1u : (uint32_t)(kc != 0);
-                                mma_bf16(d_addr + ms * NT, mk(at16 + ((ms * G_M * G_ROWB + kk * 32) >> 4)), mk(b16 + ((kk * 32) >> 4)),
-                                         IDESC, accum);
-                            }
-                        mma_commit(&bempty[b_stage]);                               // weight slice reusable
-                        if (tap == 8) {
+                        }
+                        mma_commit(&bempty[b_stage]);                               // weight slot reusable
+                        if (grp == GROUPS - 1) {
                             mma_commit(&aempty[a_stage]);                           // activation tile reusable
-                            if (kc == k_chunks - 1) mma_commit(&tfull[acc]);        // accumulators ready for the epilogue
+                            if (kc == k_chunks - 1) { mma_commit(&tfull[acc]); GEN_TRACE(p, it, 5); }   // accumulators ready for the epilogue
                         }
                         if (++b_stage == b_stages) { b_stage = 0; b_phase ^= 1; }
                     }
@@ -195,7 +229,9 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         int it = acc;
         for (int tile = blockIdx.x + it * gridDim.x; tile < p.num_tiles; tile += IT_STEP * gridDim.x, it += IT_STEP) {
             const uint32_t use = (uint32_t)(it >> 1);
+            if (q == 0 && lane == 0) GEN_TRACE(p, it, 6);
             mbar_wait(&tfull[acc], use & 1);
+            if (q == 0 && lane == 0) GEN_TRACE(p, it, 7);
             fence_after_sync();
             const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * NT;
 #pragma unroll 1
@@ -234,7 +270,7 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     }
                     if (lane == 0) tma_store_wait_read();             // the previous bulk store has finished reading the staging buffer
                     __syncwarp();
-                    if (in_range) {
+                    if (in_range && !NM_DBG(16)) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             float f[8];
@@ -268,13 +304,14 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     }
                     tma_store_fence();                                // 32 channels staged: hand them to the TMA
                     __syncwarp();
-                    if (lane == 0 && row_base < p.rows_total)
+                    if (lane == 0 && row_base < p.rows_total && !NM_DBG(16))
                         tma_store_2d(&map_out, stage, n0 + c0, row_base);         // rows past the tensor are clipped
                 }
             }
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);        // accumulator buffer drained: the MMA warp may overwrite it
+            if (q == 0 && lane == 0) GEN_TRACE(p, it, 8);
         }
         if (lane == 0) tma_store_wait_all();                 // every bulk store of this warp has landed
     }
@@ -572,7 +609,8 @@ int launch_conv_gen(const void* x_pad, const void* w_packed, ConvGenParams p, cu
     CUtensorMap mo;
     rc = make_map_2d(&mo, p.out, (uint64_t)p.Cout, (uint64_t)p.rows_total, (uint64_t)p.Cout * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
-    constexpr int B_BYTES = NT * G_ROWB;
+    constexpr int TG = NT == 64 ? 3 : 1;                        // taps per weight-ring slot (see the kernel)
+    constexpr int B_BYTES = TG * NT * G_ROWB;
     constexpr int O_BYTES = 8 * 2048;                           // epilogue staging, 2 KB per epilogue warp
     p.a_stages = 2;
     {
@@ -586,7 +624,7 @@ int launch_conv_gen(const void* x_pad, const void* w_packed, ConvGenParams p, cu
     NM_REQUIRE(p.a_stages >= 2 && p.b_stages >= 2, "image too wide for the shared-memory budget");
     NM_REQUIRE(2 * (p.a_stages + p.b_stages) + 4 <= 62, "too many pipeline stages for the barrier block");
     const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * B_BYTES + O_BYTES + 512;   // + mbarriers
-    auto kern = conv3x3_gen_kernel<NT, MSUB, G_KC>;
+    auto kern = conv3x3_gen_kernel<NT, MSUB, G_KC, TG>;
     static bool attr_set = false;
     if (!attr_set) {
         NM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -660,6 +698,9 @@ int nm_tc_conv3x3_gen_bf16(const void* x_pad, const void* w_packed, const float*
     p.mask = static_cast<const __nv_bfloat16*>(relu_mask);
     p.bias = bias;
     p.relu = relu;
+#ifdef NM_ABLATE
+    p.trace = g_gen_trace;
+#endif
     conv_gen_tile(p, 2, kc);
     if (kc == 32)
         return nt == 128 ? launch_conv_gen<128, 2, 32>(x_pad, w_packed, p, nm::S(stream)) : launch_conv_gen<64, 2, 32>(x_pad, w_packed, p, nm::S(stream));
