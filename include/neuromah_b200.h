@@ -206,6 +206,12 @@ int nm_scale_f32(float* y, const float* x, size_t n, float a, int accumulate, vo
  * `X.astype(np.float32) / 255.0` of examples/test_Conv2D_MNIST.py:27 moved behind the host->device copy (4x fewer bytes
  * over PCIe); bit-identical to NumPy.  The bf16 plans take uint8 inputs directly (nm_tc_*_u8_bf16 below). */
 int nm_u8_to_f32_div(const uint8_t* x, float* y, size_t n, float denom, void* stream);
+/* TensorMonitor.log_histogram (src/utils/TensorMonitor.py:93-104: np.histogram(values.flatten(), bins)) without pulling the
+ * tensor to the host: nm_minmax_f32 leaves {min, max} in out2 (device floats); nm_histogram_f32 counts into `bins` uniform
+ * bins over [first, last] with NumPy's index arithmetic (float64 scaled index + the two edge corrections), so the counts
+ * equal np.histogram's exactly; values outside the range and NaNs are not counted. */
+int nm_minmax_f32(const float* x, size_t n, float* out2, void* stream);
+int nm_histogram_f32(const float* x, size_t n, double first, double last, int bins, unsigned long long* counts, void* stream);
 
 /* ---- bf16 tensor-core path (tcgen05 + TMA + TMEM), see DESIGN.md --------- */
 /* Activations: bf16 NHWC with a one-pixel zero halo, [N, H+2, W+2, C] ("padded grid"); the halo is

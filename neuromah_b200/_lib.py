@@ -80,6 +80,8 @@ _SIGS = {
     "nm_mul_f32": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "nm_scale_f32": (_i, [_vp, _vp, _sz, _f, _i, _vp]),
     "nm_u8_to_f32_div": (_i, [_vp, _vp, _sz, _f, _vp]),
+    "nm_minmax_f32": (_i, [_vp, _sz, _vp, _vp]),
+    "nm_histogram_f32": (_i, [_vp, _sz, C.c_double, C.c_double, _i, _vp, _vp]),
     "nm_tc_pack_conv_weights_bf16": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "nm_tc_conv3x3_fprop_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_conv3x3_dgrad_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

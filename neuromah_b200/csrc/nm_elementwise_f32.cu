@@ -245,9 +245,75 @@ __global__ void u8_to_f32_div_kernel(const uint8_t* __restrict__ x, float* __res
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) y[n4 * 4 + threadIdx.x] = __fdiv_rn((float)x[n4 * 4 + threadIdx.x], denom);
 }
 
+// ---- TensorMonitor.log_histogram (src/utils/TensorMonitor.py:93-104: np.histogram(values.flatten(), bins)) on the device ----
+// pass 1: min / max of the tensor (order-independent, so the block/atomic combination is deterministic)
+__device__ __forceinline__ unsigned f2ord(float f) { const unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float ord2f(unsigned o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o); }
+__global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ x, size_t n, unsigned* __restrict__ out) {
+    __shared__ unsigned smin[8], smax[8];
+    unsigned lo = 0xFFFFFFFFu, hi = 0u;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned o = f2ord(x[i]);
+        lo = min(lo, o); hi = max(hi, o);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, s)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, s)); }
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { lo = min(lo, smin[w]); hi = max(hi, smax[w]); }
+        atomicMin(out, lo); atomicMax(out + 1, hi);
+    }
+}
+__global__ void minmax_finish_kernel(unsigned* out) {                 // ordered keys -> floats, in place
+    const float lo = ord2f(out[0]), hi = ord2f(out[1]);
+    reinterpret_cast<float*>(out)[0] = lo; reinterpret_cast<float*>(out)[1] = hi;
+}
+// pass 2: bin counts with NumPy's own index arithmetic for uniform bins (float64: scaled index, then the two corrections
+// against the linspace edges), integer atomics -- the counts are exact and independent of the order of summation
+__global__ void __launch_bounds__(256)
+histogram_kernel(const float* __restrict__ x, size_t n, double first, double last, int bins, unsigned long long* __restrict__ counts) {
+    extern __shared__ unsigned hist[];
+    for (int b = threadIdx.x; b < bins; b += blockDim.x) hist[b] = 0u;
+    __syncthreads();
+    const double step = (last - first) / bins, norm = bins / (last - first);
+    auto edge = [&](int k) { return k == bins ? last : k * step + first; };      // np.linspace(first, last, bins + 1)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double v = (double)x[i];
+        if (!(v >= first && v <= last)) continue;                                  // outside the range (or NaN): not counted
+        int k = (int)((v - first) * norm);
+        if (k == bins) k = bins - 1;
+        if (v < edge(k)) --k;
+        else if (k != bins - 1 && v >= edge(k + 1)) ++k;
+        atomicAdd(&hist[k], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < bins; b += blockDim.x)
+        if (hist[b]) atomicAdd(&counts[b], (unsigned long long)hist[b]);
+}
+
 }  // namespace
 
 extern "C" {
+
+int nm_minmax_f32(const float* x, size_t n, float* out2, void* stream) {
+    NM_REQUIRE(x && out2 && n > 0, "null pointer or empty tensor");
+    unsigned* o = reinterpret_cast<unsigned*>(out2);
+    const unsigned init[2] = {0xFFFFFFFFu, 0u};
+    NM_CUDA(cudaMemcpyAsync(o, init, sizeof(init), cudaMemcpyHostToDevice, nm::S(stream)));
+    minmax_kernel<<<ew_blocks(n, 256, 8), 256, 0, nm::S(stream)>>>(x, n, o);
+    minmax_finish_kernel<<<1, 1, 0, nm::S(stream)>>>(o);
+    return nm::launched("minmax_f32", 2);
+}
+
+int nm_histogram_f32(const float* x, size_t n, double first, double last, int bins, unsigned long long* counts, void* stream) {
+    NM_REQUIRE(x && counts, "null pointer");
+    NM_REQUIRE(bins > 0 && bins <= 4096 && last > first, "bins must be in [1, 4096] and the range non-empty");
+    NM_CUDA(cudaMemsetAsync(counts, 0, (size_t)bins * sizeof(unsigned long long), nm::S(stream)));
+    if (!n) return NM_OK;
+    histogram_kernel<<<ew_blocks(n, 256, 8), 256, (size_t)bins * sizeof(unsigned), nm::S(stream)>>>(x, n, first, last, bins, counts);
+    return nm::launched("histogram_f32");
+}
 
 int nm_u8_to_f32_div(const uint8_t* x, float* y, size_t n, float denom, void* stream) {
     NM_REQUIRE(x && y, "null pointer");

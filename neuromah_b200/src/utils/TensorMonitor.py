@@ -4,8 +4,10 @@ Same hooks (start_run / start_epoch / log_scalar / log_histogram / log_layer_par
 same file name pattern (``<log_dir>/run-<timestamp>.json``) and the same JSON shape
 (``metadata{start_time, layers, optimizer, loss_function, accuracy_metric, end_time}``, ``epochs[{epoch, time_start,
 metrics{scalars}, parameters{histograms{tag: {histogram, bin_edges}}}, time_end, time_elapsed}]``), so the reference's
-log viewer reads these files.  Parameters live in HBM here: a histogram pulls ONE host copy of the tensor per epoch,
-and the metadata records shapes instead of ``tolist()``-ing every weight into the JSON (TensorMonitor.py:42-44).
+log viewer reads these files.  Parameters live in HBM here: a histogram of a device tensor is computed ON THE DEVICE
+(min/max pass + integer bin counts with NumPy's own index arithmetic, nm_minmax_f32 / nm_histogram_f32: the counts equal
+np.histogram's exactly) and only 2 floats + `bins` counters cross PCIe; the metadata records shapes instead of
+``tolist()``-ing every weight into the JSON (TensorMonitor.py:42-44).
 """
 import json
 import os
@@ -31,6 +33,27 @@ def _describe(obj):
         else:
             out[key] = type(value).__name__
     return out
+
+
+def _on_device(values):
+    from ...device import DeviceArray
+    return isinstance(values, DeviceArray) and values.dtype == np.float32 and values.size > 0
+
+
+def device_histogram(values, bins=10):
+    """np.histogram(values.flatten(), bins) for a float32 DeviceArray, computed on the device (same counts, same edges)."""
+    import ctypes as C
+    from ..._lib import lib
+    from ...device import DeviceArray, stream
+    mm = DeviceArray((2,), np.float32)
+    lib.nm_minmax_f32(values.p, values.size, mm.p, stream())
+    lo, hi = (float(v) for v in mm.numpy())
+    if not (np.isfinite(lo) and np.isfinite(hi)):
+        raise ValueError(f"autodetected range of [{lo}, {hi}] is not finite")          # np.histogram's own error
+    first, last = (lo - 0.5, hi + 0.5) if lo == hi else (lo, hi)                       # numpy widens an empty range
+    counts = DeviceArray((int(bins),), np.uint64)
+    lib.nm_histogram_f32(values.p, values.size, C.c_double(first), C.c_double(last), int(bins), counts.p, stream())
+    return counts.numpy().astype(np.int64), np.linspace(first, last, int(bins) + 1)
 
 
 class TensorMonitor:
@@ -66,7 +89,7 @@ class TensorMonitor:
 
     def log_histogram(self, tag, values, bins=10):
         if self.epoch_data is not None:
-            hist, edges = np.histogram(np.asarray(values).ravel(), bins=bins)
+            hist, edges = device_histogram(values, bins) if _on_device(values) else np.histogram(np.asarray(values).ravel(), bins=bins)
             self.epoch_data['parameters'].setdefault('histograms', {})[tag] = {'histogram': hist.tolist(),
                                                                                 'bin_edges': edges.tolist()}
 

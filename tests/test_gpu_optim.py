@@ -276,3 +276,23 @@ def test_dense_example_stack_as_written_in_the_reference():
     np.testing.assert_allclose(losses, g["losses"], rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(model.arena.host_params(), g["final_params"], rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(np.asarray(model.forward(x[:32], training=False)), g["infer"], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("n,bins", [(288, 10), (50186, 10), (1 << 20, 64), (7, 3)])
+def test_device_histogram_equals_numpy(n, bins):
+    """TensorMonitor.log_histogram on a device tensor (TensorMonitor.py:93-104): counts and edges equal np.histogram's on the
+    float64 values the reference holds its parameters in."""
+    from neuromah_b200.device import DeviceArray
+    from neuromah_b200.src.utils.TensorMonitor import device_histogram
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal(n) * 0.3).astype(np.float32)
+    x[::5] = np.round(x[::5], 1)                                   # repeated values, some exactly on bin edges
+    hist, edges = device_histogram(DeviceArray.from_numpy(x), bins)
+    ref_h, ref_e = np.histogram(x.astype(np.float64), bins=bins)
+    np.testing.assert_array_equal(hist, ref_h)
+    np.testing.assert_array_equal(edges, ref_e)
+    const = DeviceArray.from_numpy(np.full((100,), 0.25, np.float32))
+    h2, e2 = device_histogram(const, 10)
+    r2, re2 = np.histogram(np.full((100,), 0.25, np.float64), bins=10)
+    np.testing.assert_array_equal(h2, r2)
+    np.testing.assert_array_equal(e2, re2)
