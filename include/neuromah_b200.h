@@ -286,9 +286,10 @@ int nm_tc_maxpool2x2_bwd_bf16(const void* dpool, const void* idx, void* dy_pad, 
 /* Layer_Dense dinputs (Dense.py:108) for the tensor-core mode: dx bf16 [B][K] = dlogits f32 [B][n_out] . w_packed
  * (f32 [n_out][K] from nm_tc_pack_dense_weights, K in (h,w,c) order).  n_out <= 16, K % 8 == 0. */
 int nm_tc_dense_dgrad_bf16(const float* dlogits, const float* w_packed, void* dx, int B, int K, int n_out, void* stream);
-/* ... with the ReLU backward of the layer that produced the Dense input (Relu.py:12-14): dx = 0 where relu_mask[B][K] <= 0. */
-int nm_tc_dense_dgrad_mask_bf16(const float* dlogits, const float* w_packed, const void* relu_mask, void* dx, int B, int K, int n_out,
-                                void* stream);
+/* ... with the ReLU backward of the layer that produced the Dense input (Relu.py:12-14): dx = 0 where relu_mask[B][K] <= 0,
+ * dx * mask_scale elsewhere (mask_scale = 1 / keep when a Layer_Dropout sits in between: its surviving elements are > 0). */
+int nm_tc_dense_dgrad_mask_bf16(const float* dlogits, const float* w_packed, const void* relu_mask, float mask_scale, void* dx, int B, int K,
+                                int n_out, void* stream);
 
 /* ---- general tcgen05 Dense layers (hidden layers of an MLP), nm_tc_gemm.cu ----------------------------------------
  * Layer_Dense.forward / backward (Dense.py:79-85, :96-108) + the embedded ReLU (Relu.py:7-14) for any n_in % 8 == 0 and
@@ -296,16 +297,20 @@ int nm_tc_dense_dgrad_mask_bf16(const float* dlogits, const float* w_packed, con
  *   nm_tc_to_bf16 / nm_tc_u8_to_bf16   the first layer's A operand from float32 inputs / raw uint8 pixels * scale
  *   nm_tc_pack_dense_gen_bf16          w f32 [n_in][n_out] -> w_kn bf16 (same layout, dgrad operand), w_nk bf16 [n_out][n_in]
  *                                      (fprop operand); either may be NULL; refreshed after every optimizer step
- *   nm_tc_dense_fprop_gen_bf16         y = x w (+ bias) (ReLU)
- *   nm_tc_dense_dgrad_gen_bf16         dx = dy w^T, zeroed where relu_mask <= 0 (relu_mask may be NULL)
+ *   nm_tc_dense_fprop_gen_bf16         y = x w (+ bias) (ReLU), then a fused Layer_Dropout (Dropout.py:15-30) when drop_keep < 1:
+ *                                      y *= Bernoulli(drop_keep) / drop_keep from the Philox stream of nm_dropout_fwd_f32
+ *                                      (key drop_seed, offset drop_offset + *drop_offset_dev if not NULL)
+ *   nm_tc_dense_dgrad_gen_bf16         dx = dy w^T; with relu_mask: 0 where relu_mask <= 0, x mask_scale elsewhere
  *   nm_tc_dense_wgrad_gen_bf16         dw = scale x^T dy + l1 sign(w) + 2 l2 w, db = scale sum_b dy; both operands are read
  *                                      MN-major straight from x / dy; split over the batch, partials summed in a fixed order */
 int nm_tc_to_bf16(const float* x, void* y, size_t n, void* stream);
 int nm_tc_u8_to_bf16(const uint8_t* x, float scale, void* y, size_t n, void* stream);
 int nm_tc_pack_dense_gen_bf16(const float* w, void* w_kn, void* w_nk, int n_in, int n_out, void* stream);
 int nm_tc_dense_fprop_gen_bf16(const void* x, const void* w_nk, const float* bias, void* y, int B, int n_in, int n_out, int relu,
-                               void* stream);
-int nm_tc_dense_dgrad_gen_bf16(const void* dy, const void* w_kn, const void* relu_mask, void* dx, int B, int n_in, int n_out, void* stream);
+                               float drop_keep, unsigned long long drop_seed, unsigned long long drop_offset,
+                               const long long* drop_offset_dev, void* stream);
+int nm_tc_dense_dgrad_gen_bf16(const void* dy, const void* w_kn, const void* relu_mask, float mask_scale, void* dx, int B, int n_in,
+                               int n_out, void* stream);
 size_t nm_tc_dense_wgrad_gen_workspace(int B, int n_in, int n_out);
 int nm_tc_dense_wgrad_gen_bf16(const void* x, const void* dy, const float* w, float* dw, float* db, void* workspace, size_t workspace_bytes,
                                int B, int n_in, int n_out, float scale, float l1, float l2, void* stream);

@@ -99,12 +99,12 @@ _SIGS = {
     "nm_tc_maxpool2x2_fwd_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_maxpool2x2_bwd_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_dense_dgrad_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
-    "nm_tc_dense_dgrad_mask_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "nm_tc_dense_dgrad_mask_bf16": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp]),
     "nm_tc_to_bf16": (_i, [_vp, _vp, _sz, _vp]),
     "nm_tc_u8_to_bf16": (_i, [_vp, _f, _vp, _sz, _vp]),
     "nm_tc_pack_dense_gen_bf16": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
-    "nm_tc_dense_fprop_gen_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "nm_tc_dense_dgrad_gen_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "nm_tc_dense_fprop_gen_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, C.c_ulonglong, C.c_ulonglong, _vp, _vp]),
+    "nm_tc_dense_dgrad_gen_bf16": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp]),
     "nm_tc_dense_wgrad_gen_workspace": (_sz, [_i, _i, _i]),
     "nm_tc_dense_wgrad_gen_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _f, _f, _vp]),
     "nm_tc_dense_bwd_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),

@@ -7,7 +7,8 @@
 //   Optimizer_Nadam    src/optimizers/Nadam.py (eps added to the bias corrections as well)  28 B/param
 //   Layer_Dropout      src/layers/Dropout.py:15-40: mask = Bernoulli(keep) / keep, drawn with Philox4x32-10 on the device
 #include "nm_common.cuh"
-#include "nm_adam.cuh"      // nm_sqrt_approx: MUFU square root / division keep these kernels HBM-bound (see there)
+#include "nm_adam.cuh"
+#include "nm_philox.cuh"      // nm_sqrt_approx: MUFU square root / division keep these kernels HBM-bound (see there)
 
 namespace {
 
@@ -90,18 +91,6 @@ int launch_opt(const char* name, float* p, const float* g, float* s1, float* s2,
     return nm::launched(name);
 }
 
-// ---- Philox4x32-10 (Salmon et al., SC'11): counter = (element group, stream offset), key = seed ----------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
-    }
-    return ctr;
-}
-
 // y = x * mask, mask = (u < keep) / keep with u uniform in [0,1) from 32 random bits (24 used: exact in fp32)
 __global__ void __launch_bounds__(256)
 dropout_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ mask, size_t n, float keep,
@@ -111,12 +100,10 @@ dropout_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __
     const size_t stride = (size_t)gridDim.x * blockDim.x, groups = (n + 3) / 4;
     const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(mask)) & 15) == 0;
     for (; q < groups; q += stride) {
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
-                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+        const uint32_t kb = dropout_keep4(q, seed, offset, keep);
         float m[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) m[u] = ((float)(rr[u] >> 8) * (1.f / 16777216.f) < keep) ? inv : 0.f;
+        for (int u = 0; u < 4; ++u) m[u] = (kb >> u) & 1u ? inv : 0.f;
         const size_t i = q * 4;
         if (vec && i + 4 <= n) {
             const float4 X = *reinterpret_cast<const float4*>(x + i);

@@ -17,6 +17,7 @@
 #include "nm_common.cuh"
 #include "nm_tc_common.cuh"
 #include "nm_tc_host.cuh"
+#include "nm_philox.cuh"
 
 namespace {
 
@@ -32,8 +33,12 @@ struct GemmParams {
     __nv_bfloat16* out; int ldo;         // bf16 [M][ldo]
     const float* bias;                   // optional [N]
     int relu;
-    const __nv_bfloat16* mask; int ldm;  // optional [M][ldm]: out = mask > 0 ? v : 0   (ReLU' of the layer below)
-};
+    const __nv_bfloat16* mask; int ldm;  // optional [M][ldm]: out = mask > 0 ? v * mask_scale : 0   (ReLU' of the layer below,
+    float mask_scale;                    //   times 1 / keep when a Layer_Dropout sits between the two layers)
+    float drop_keep;                     // < 1: Layer_Dropout fused behind the activation: out *= Bernoulli(keep) / keep
+    unsigned long long drop_seed, drop_offset;      // Philox key / stream offset (same stream as nm_dropout_fwd_f32)
+    const long long* drop_offset_dev;    // optional: added to drop_offset on the device (the optimizer's step counter, so that
+};                                       //   a CUDA-graph replay of the step draws a fresh mask)
 
 template <int NT>
 __global__ void __launch_bounds__(256, 1)
@@ -97,6 +102,7 @@ dense_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         mbar_wait(tfull, 0);
         fence_after_sync();
         const bool row_ok = row < p.M;
+        const unsigned long long drop_dev = p.drop_offset_dev ? (unsigned long long)__ldg(p.drop_offset_dev) : 0ull;
         __nv_bfloat16* dst = p.out + (size_t)row * p.ldo + n0;
         const __nv_bfloat16* msk = p.mask ? p.mask + (size_t)row * p.ldm + n0 : nullptr;
 #pragma unroll 1
@@ -122,13 +128,21 @@ dense_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
                 }
+                if (p.drop_keep < 1.f) {               // Dropout.py:27-30 behind the activation; element index = row * N + col
+                    const unsigned long long e = (unsigned long long)row * p.N + col, off = p.drop_offset + drop_dev;
+                    const uint32_t kb = dropout_keep4(e >> 2, p.drop_seed, off, p.drop_keep) |
+                                        (dropout_keep4((e >> 2) + 1, p.drop_seed, off, p.drop_keep) << 4);
+                    const float inv = 1.f / p.drop_keep;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = (kb >> j) & 1u ? f[j] * inv : 0.f;
+                }
                 if (msk) {
                     const uint4 mk = __ldg(reinterpret_cast<const uint4*>(msk + c0 + g * 8));
                     const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const uint32_t h = (mw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;     // bf16 > 0: sign clear, not zero
-                        if ((h & 0x8000u) || !(h & 0x7FFFu)) f[j] = 0.f;
+                        f[j] = ((h & 0x8000u) || !(h & 0x7FFFu)) ? 0.f : f[j] * p.mask_scale;
                     }
                 }
                 *reinterpret_cast<uint4*>(dst + c0 + g * 8) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
@@ -362,25 +376,29 @@ int nm_tc_pack_dense_gen_bf16(const float* w, void* w_kn, void* w_nk, int n_in, 
                           w, static_cast<__nv_bfloat16*>(w_kn), static_cast<__nv_bfloat16*>(w_nk), n_in, n_out);
 }
 
-// y[B][n_out] = x[B][n_in] w_nk[n_out][n_in]^T (+ bias) (ReLU)
+// y[B][n_out] = x[B][n_in] w_nk[n_out][n_in]^T (+ bias) (ReLU) (x Bernoulli(drop_keep) / drop_keep: a fused Layer_Dropout)
 int nm_tc_dense_fprop_gen_bf16(const void* x, const void* w_nk, const float* bias, void* y, int B, int n_in, int n_out, int relu,
-                               void* stream) {
+                               float drop_keep, unsigned long long drop_seed, unsigned long long drop_offset,
+                               const long long* drop_offset_dev, void* stream) {
     NM_REQUIRE(x && w_nk && y, "null pointer");
     NM_REQUIRE(B > 0 && n_in > 0 && n_out > 0 && n_in % 8 == 0 && n_out % 8 == 0, "bad dimensions (n_in, n_out multiples of 8)");
+    NM_REQUIRE(drop_keep > 0.f && drop_keep <= 1.f, "drop_keep (the KEEP probability) must be in (0, 1]");
     GemmParams p{};
     p.M = B; p.N = n_out; p.K = n_in; p.k_chunks = (n_in + GK - 1) / GK;
     p.out = static_cast<__nv_bfloat16*>(y); p.ldo = n_out; p.bias = bias; p.relu = relu;
+    p.mask_scale = 1.f; p.drop_keep = drop_keep; p.drop_seed = drop_seed; p.drop_offset = drop_offset; p.drop_offset_dev = drop_offset_dev;
     return n_out % 128 == 0 ? launch_gemm<128>(x, w_nk, p, nm::S(stream)) : launch_gemm<64>(x, w_nk, p, nm::S(stream));
 }
 
-// dx[B][n_in] = dy[B][n_out] w_kn[n_in][n_out]^T, zeroed where relu_mask[B][n_in] <= 0 (if not NULL)
-int nm_tc_dense_dgrad_gen_bf16(const void* dy, const void* w_kn, const void* relu_mask, void* dx, int B, int n_in, int n_out, void* stream) {
+// dx[B][n_in] = dy[B][n_out] w_kn[n_in][n_out]^T; where relu_mask[B][n_in] is given: zero where it is <= 0, x mask_scale elsewhere
+int nm_tc_dense_dgrad_gen_bf16(const void* dy, const void* w_kn, const void* relu_mask, float mask_scale, void* dx, int B, int n_in,
+                               int n_out, void* stream) {
     NM_REQUIRE(dy && w_kn && dx, "null pointer");
     NM_REQUIRE(B > 0 && n_in > 0 && n_out > 0 && n_in % 8 == 0 && n_out % 8 == 0, "bad dimensions (n_in, n_out multiples of 8)");
     GemmParams p{};
     p.M = B; p.N = n_in; p.K = n_out; p.k_chunks = (n_out + GK - 1) / GK;
     p.out = static_cast<__nv_bfloat16*>(dx); p.ldo = n_in;
-    p.mask = static_cast<const __nv_bfloat16*>(relu_mask); p.ldm = n_in;
+    p.mask = static_cast<const __nv_bfloat16*>(relu_mask); p.ldm = n_in; p.mask_scale = mask_scale; p.drop_keep = 1.f;
     return n_in % 128 == 0 ? launch_gemm<128>(dy, w_kn, p, nm::S(stream)) : launch_gemm<64>(dy, w_kn, p, nm::S(stream));
 }
 

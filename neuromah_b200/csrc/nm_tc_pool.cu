@@ -90,7 +90,7 @@ __global__ void maxpool2x2_bwd_kernel(const uint4* __restrict__ dpool, const uin
 
 // dX[b][k] = sum_j dlogits[b][j] * Wp[j][k]   (Wp = the Dense weights packed as [n_out][K] in the kernels' (h,w,c) order)
 __global__ void dense_dgrad_bf16_kernel(const float* __restrict__ dlogits, const float* __restrict__ wp, const uint4* __restrict__ mask,
-                                        uint4* __restrict__ dx, int B, int K, int n_out) {
+                                        float mask_scale, uint4* __restrict__ dx, int B, int K, int n_out) {
     pdl_trigger();
     pdl_wait();
     const int G = K / 8;
@@ -111,7 +111,7 @@ __global__ void dense_dgrad_bf16_kernel(const float* __restrict__ dlogits, const
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const uint32_t h = (mw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
-            if ((h & 0x8000u) || !(h & 0x7FFFu)) a[j] = 0.f;
+            a[j] = ((h & 0x8000u) || !(h & 0x7FFFu)) ? 0.f : a[j] * mask_scale;
         }
     }
     uint32_t o[4];
@@ -152,17 +152,17 @@ int nm_tc_dense_dgrad_bf16(const float* dlogits, const float* w_packed, void* dx
     const long long total = (long long)B * (K / 8);
     NM_REQUIRE(total < (1ll << 31) - 1024, "tensor too large for 32-bit element indices");
     return nm::launch_pdl("dense_dgrad_bf16", dense_dgrad_bf16_kernel, dim3(nm_cdiv((size_t)total, 256)), dim3(256), 0, nm::S(stream),
-                          dlogits, w_packed, static_cast<const uint4*>(nullptr), static_cast<uint4*>(dx), B, K, n_out);
+                          dlogits, w_packed, static_cast<const uint4*>(nullptr), 1.f, static_cast<uint4*>(dx), B, K, n_out);
 }
 
-int nm_tc_dense_dgrad_mask_bf16(const float* dlogits, const float* w_packed, const void* relu_mask, void* dx, int B, int K, int n_out,
-                                void* stream) {
+int nm_tc_dense_dgrad_mask_bf16(const float* dlogits, const float* w_packed, const void* relu_mask, float mask_scale, void* dx, int B, int K,
+                                int n_out, void* stream) {
     NM_REQUIRE(dlogits && w_packed && dx, "null pointer");
     NM_REQUIRE(B > 0 && K > 0 && K % 8 == 0 && n_out > 0 && n_out <= kNO, "bad dimensions");
     const long long total = (long long)B * (K / 8);
     NM_REQUIRE(total < (1ll << 31) - 1024, "tensor too large for 32-bit element indices");
     return nm::launch_pdl("dense_dgrad_mask_bf16", dense_dgrad_bf16_kernel, dim3(nm_cdiv((size_t)total, 256)), dim3(256), 0, nm::S(stream),
-                          dlogits, w_packed, static_cast<const uint4*>(relu_mask), static_cast<uint4*>(dx), B, K, n_out);
+                          dlogits, w_packed, static_cast<const uint4*>(relu_mask), mask_scale, static_cast<uint4*>(dx), B, K, n_out);
 }
 
 }  // extern "C"

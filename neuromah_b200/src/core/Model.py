@@ -427,6 +427,8 @@ class Model:
     def forward(self, X, training):
         self.input_layer.forward(X, training)
         if self.plan is not None:
+            if getattr(self.plan, "drops", None):          # a plan with fused Dropout layers needs to know the phase
+                return self.plan.forward(self.input_layer.output, training=training)
             return self.plan.forward(self.input_layer.output)
         for layer in self.layers:
             layer.forward(layer.prev.output, training)

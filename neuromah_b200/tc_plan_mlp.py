@@ -1,10 +1,13 @@
 """bf16 tensor-core execution plan for multi-layer perceptrons (BASELINE.json config 1, examples/test_Dense_MNIST.py):
 
-    Dense(n_in -> h1, ReLU) [-> Dense(h1 -> h2, ReLU) ...] -> Dense(h_k -> n <= 16) -> Softmax
+    Dense(n_in -> h1, ReLU) [-> Dropout] [-> Dense(h1 -> h2, ReLU) [-> Dropout] ...] -> Dense(h_k -> n <= 16) -> Softmax
 
-with n_in % 8 == 0 and every hidden width a multiple of 64.  ``Model.finalize(mode="bf16")`` picks this plan for such
+with n_in % 8 == 0 and every hidden width a multiple of 64 (the stack of examples/test_Dense_MNIST.py:39-44 without its
+doubled softmax).  ``Model.finalize(mode="bf16")`` picks this plan for such
 stacks.  Every Dense contraction runs on tcgen05 tensor cores: hidden layers through the general TMA-fed GEMMs of
-nm_tc_gemm.cu (fprop with bias + ReLU in the epilogue, dgrad with the ReLU backward of the layer below in the epilogue,
+nm_tc_gemm.cu (fprop with bias + ReLU + the Layer_Dropout mask in the epilogue -- the mask is drawn from the same Philox
+stream as the FP32 layer's, keyed by the layer's seed and offset by the optimizer's step count so that a CUDA-graph replay
+draws a fresh one --, dgrad with the ReLU backward of the layer below (and the 1 / keep of a dropout in between) in the epilogue,
 wgrad with both operands read MN-major from the activation / gradient tensors), the last layer through the Dense head of
 nm_tc_dense.cu (logits + softmax + CE + gradient in one launch; hi/lo split weights).  Activations and their gradients
 are bf16 [B][features]; parameters, gradients and optimizer state stay FP32 in the arena in the reference's layouts, so the
@@ -13,6 +16,8 @@ Numerics: bf16 operands and stored activations, FP32 accumulation (stated tolera
 Reference arithmetic: Dense.py:64-108 (incl. the second division by the batch), Relu.py:7-14.
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 
@@ -42,18 +47,25 @@ class Bf16Matrix:
 
 
 class TcMlpPlan:
-    PATTERN = ("Dense(n_in % 8 == 0 -> h % 64 == 0, ReLU) x k (k >= 1) -> Dense(-> n <= 16, no activation) -> Softmax "
-               "(no Dropout layers)")
+    PATTERN = ("(Dense(n_in % 8 == 0 -> h % 64 == 0, ReLU) [-> Dropout]) x k (k >= 1) -> Dense(-> n <= 16, no activation) "
+               "-> Softmax")
 
     @staticmethod
     def parse(model):
-        from .src.layers import Layer_Dense
+        from .src.layers import Layer_Dense, Layer_Dropout
         from .src.activations import Activation_ReLU, Activation_Softmax
         L = list(model.layers)
         if len(L) < 3 or not isinstance(L[-1], Activation_Softmax):
             return None
-        dense = L[:-1]
-        if not all(isinstance(d, Layer_Dense) for d in dense):
+        dense, drops = [], {}
+        for layer in L[:-1]:
+            if isinstance(layer, Layer_Dense):
+                dense.append(layer)
+            elif isinstance(layer, Layer_Dropout) and dense and id(dense[-1]) not in drops and layer.fixed_mask is None:
+                drops[id(dense[-1])] = layer            # a dropout right behind a hidden Dense is fused into its epilogue
+            else:
+                return None
+        if len(dense) < 2 or id(dense[-1]) in drops:
             return None
         hidden, head = dense[:-1], dense[-1]
         if head.activation is not None or head.weights.shape[1] > 16 or head.weights.shape[0] % 8:
@@ -66,7 +78,7 @@ class TcMlpPlan:
             n_prev = n_out
         if head.weights.shape[0] != n_prev:
             return None
-        return hidden, head, L[-1]
+        return hidden, head, L[-1], drops
 
     @staticmethod
     def match(model):
@@ -79,7 +91,7 @@ class TcMlpPlan:
         if model.softmax_classifier_output is None:
             raise ValueError("mode='bf16' needs Loss_CategoricalCrossentropy with a final Activation_Softmax")
         self.model = model
-        self.hidden, self.de, self.sm = parsed
+        self.hidden, self.de, self.sm, self.drops = parsed
         self.n_in = self.hidden[0].weights.shape[0]
         self.K = self.de.weights.shape[0]
         self.n_out = self.de.weights.shape[1]
@@ -126,7 +138,21 @@ class TcMlpPlan:
         lib.nm_tc_pack_dense_weights(self.de.weights.p, self.w3p.p, self.w3hl.p, self.K, self.n_out, 1, self.K, s)
 
     # ------------------------------------------------------------------ passes ----
-    def forward(self, x: DeviceArray, labels=None, accum=None, inv_batch=None):
+    def _dropout_args(self, d, training):
+        """(keep, seed, host offset, device offset pointer) of the Layer_Dropout fused behind hidden layer ``d``.  The stream
+        offset is the optimizer's step count -- read on the DEVICE when the optimizer keeps it there (Adam: the captured
+        step then draws a fresh mask at every replay), from the host attribute otherwise."""
+        drop = self.drops.get(id(d))
+        if drop is None or not training:
+            return 1.0, 0, 0, None
+        opt = self.model.optimizer
+        if hasattr(opt, "sync_device_state"):
+            st = opt.sync_device_state()
+            return float(drop.rate), drop.seed, 0, C.c_void_p(st.ptr + 32)          # nm_adam_state.iterations
+        return float(drop.rate), drop.seed, int(opt.iterations), None
+
+    def forward(self, x: DeviceArray, labels=None, accum=None, inv_batch=None, training=None):
+        training = (labels is not None) if training is None else training
         if x.ndim != 2:
             raise ValueError("The input must be a 2D array (batch, features)")            # Dense.py:73-78
         B = x.shape[0]
@@ -141,10 +167,14 @@ class TcMlpPlan:
         cur = self.x0
         for d, act in zip(self.hidden, self.acts):
             n_in, n_out = d.weights.shape
+            keep, seed, off, off_dev = self._dropout_args(d, training)
             _timed(f"tc_dense_gen_fprop[{n_in}->{n_out}]", lib.nm_tc_dense_fprop_gen_bf16, cur.p, self.packed[id(d)][1].p, d.biases.p, act.p,
-                   B, n_in, n_out, 1, s)
-            d.output = Bf16Matrix(act, B)
+                   B, n_in, n_out, 1, keep, seed, off, off_dev, s)
+            d.output = Bf16Matrix(act, B)         # with a fused dropout: the DROPPED activation (what the next layer reads)
+            if id(d) in self.drops:
+                self.drops[id(d)].output = d.output
             cur = act
+        self._trained_forward = training
         lab = labels if labels is not None else self.dummy_labels
         _timed('tc_dense_softmax_ce', lib.nm_tc_dense_softmax_ce_bf16, cur.p, self.w3hl.p, self.de.biases.p, lab.p,
                self.probs.p, self.dlogits.p, self.dl_hilo.p, self.losses.p, self.correct.p,
@@ -171,7 +201,11 @@ class TcMlpPlan:
                self.de.dweights.p, self.de.dbiases.p, self.ws_dw.p, self.ws_dw.nbytes, B, self.K, self.n_out, 1, self.K,
                float(scale), float(self.de.weight_regularizer_l1), float(self.de.weight_regularizer_l2), s)
         # dX of the head, with the ReLU backward of the last hidden layer -> its dY
-        _timed('tc_dense_dgrad', lib.nm_tc_dense_dgrad_mask_bf16, self.dlogits.p, self.w3p.p, last.p, self.dacts[-1].p, B, self.K, self.n_out, s)
+        def mscale(d):          # surviving elements of a fused dropout carry 1 / keep (Dropout.py:40: dinputs = dvalues * mask)
+            drop = self.drops.get(id(d))
+            return 1.0 / float(drop.rate) if (drop is not None and getattr(self, "_trained_forward", False)) else 1.0
+        _timed('tc_dense_dgrad', lib.nm_tc_dense_dgrad_mask_bf16, self.dlogits.p, self.w3p.p, last.p, mscale(self.hidden[-1]),
+               self.dacts[-1].p, B, self.K, self.n_out, s)
         for i in range(len(self.hidden) - 1, -1, -1):
             d = self.hidden[i]
             n_in, n_out = d.weights.shape
@@ -181,6 +215,6 @@ class TcMlpPlan:
                    float(d.weight_regularizer_l2), s)
             if i > 0:      # dX + the ReLU backward of the layer below -> its dY
                 _timed(f"tc_dense_gen_dgrad[{n_in}->{n_out}]", lib.nm_tc_dense_dgrad_gen_bf16, self.dacts[i].p, self.packed[id(d)][0].p,
-                       self.acts[i - 1].p, self.dacts[i - 1].p, B, n_in, n_out, s)
+                       self.acts[i - 1].p, mscale(self.hidden[i - 1]), self.dacts[i - 1].p, B, n_in, n_out, s)
         if comm is not None:
             comm.allreduce_async(self.model.arena.grads, 0, self.model.arena.total)

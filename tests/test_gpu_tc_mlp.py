@@ -188,3 +188,88 @@ def test_tc_mlp_train_api_graph_replay_uint8_and_determinism():
     eager.train(xu, y, epochs=3, batch_size=128, verbose=0)
     np.testing.assert_allclose(runs[1][0], eager.arena.host_params(), rtol=1e-3, atol=1e-4)
     assert np.isfinite(runs[0][1]) and runs[0][1] < 2.4
+
+
+def _dense_example_model(mode, seeds=(71, 72), lr=0.001):
+    """The stack of examples/test_Dense_MNIST.py:39-44 (Dense+ReLU, Dropout(0.25), Dense+ReLU, Dropout(0.25), Dense, Softmax)
+    with a single softmax."""
+    from neuromah_b200.src.core import Model
+    from neuromah_b200.src.layers import Layer_Dense, Layer_Dropout
+    from neuromah_b200.src.activations import Activation_ReLU, Activation_Softmax
+    from neuromah_b200.src.losses import Loss_CategoricalCrossentropy
+    from neuromah_b200.src.optimizers import Optimizer_Adam
+    from neuromah_b200.src.metrics import Accuracy_Categorical
+    spec = [{"kind": "dense", "n_in": 784, "n_out": 128, "relu": True}, {"kind": "dropout", "rate": 0.25},
+            {"kind": "dense", "n_in": 128, "n_out": 64, "relu": True}, {"kind": "dropout", "rate": 0.25},
+            {"kind": "dense", "n_in": 64, "n_out": 10, "relu": False}, {"kind": "softmax"}]
+    params = ref_net.init_params(spec, np.random.RandomState(17), init="he")
+    model = Model()
+    layers = [Layer_Dense(784, 128, activation=Activation_ReLU()), Layer_Dropout(0.25, seed=seeds[0]),
+              Layer_Dense(128, 64, activation=Activation_ReLU()), Layer_Dropout(0.25, seed=seeds[1]),
+              Layer_Dense(64, 10), Activation_Softmax()]
+    for layer, p in zip(layers, params):
+        if p is not None:
+            layer.set_parameters(p["weights"], p["biases"])
+        model.add(layer)
+    model.set(loss=Loss_CategoricalCrossentropy, optimizer=Optimizer_Adam(learning_rate=lr), accuracy=Accuracy_Categorical)
+    model.finalize(mode=mode)
+    return model, spec, params
+
+
+def _philox_mask(shape, keep, seed, offset):
+    """The mask Layer_Dropout's FP32 kernel draws for (seed, offset): the fused epilogue must draw the same one."""
+    from neuromah_b200._lib import lib
+    from neuromah_b200.device import DeviceArray, stream
+    ones = DeviceArray.from_numpy(np.ones(shape, np.float32))
+    out, mask = DeviceArray(shape, np.float32), DeviceArray(shape, np.float32)
+    lib.nm_dropout_fwd_f32(ones.p, out.p, mask.p, ones.size, float(keep), seed, offset, stream())
+    return mask.numpy().astype(np.float64)
+
+
+def test_tc_mlp_plan_with_fused_dropout_vs_oracle():
+    """Dense example stack in tensor-core mode: the Dropout layers are fused into the Dense epilogues.  Step s draws the mask
+    of Philox stream offset s (the optimizer's step count, read on the device), identical to the FP32 layer's mask for that
+    (seed, offset); with those masks the oracle's step (Dropout.py:21-40) gives the same outputs and gradients."""
+    from neuromah_b200.tc_plan_mlp import TcMlpPlan
+    model, spec, params = _dense_example_model("bf16")
+    assert isinstance(model.plan, TcMlpPlan) and len(model.plan.drops) == 2
+    net = ref_net.RefNet(spec, params)
+    B = 64
+    x, y = synth(81, 3 * B, (784,))
+    for s in range(3):
+        _resync_oracle(net, model)
+        xb, yb = x[s * B:(s + 1) * B], y[s * B:(s + 1) * B]
+        net.dropout_masks = {1: _philox_mask((B, 128), 0.75, 71, s), 3: _philox_mask((B, 64), 0.75, 72, s)}
+        model._accum.fill_zero()
+        out = model.train_step(xb, yb)
+        r = net.step(xb, yb)
+        np.testing.assert_allclose(np.asarray(out), r["output"], rtol=1e-2, atol=2e-3)
+        h1 = np.asarray(model.layers[0].output)                       # the dropped activation
+        assert np.array_equal(h1 == 0, (net.outs[1] == 0)), "dropout pattern differs from the FP32 layer's Philox mask"
+        g, gr = model.arena.host_grads(), net.flat("grads")
+        off, errs = 0, []
+        for (_, name, _, size, _) in model.arena.table:
+            errs.append(rel_l2(g[off:off + size], gr[off:off + size]))
+            off += size
+        print("step", s, " ".join(f"{e:.4f}" for e in errs))
+        assert errs[-1] <= 3e-2 and errs[-2] <= 3e-2 and max(errs) <= 6e-2, errs
+    # inference: dropout is the identity (Dropout.py:23-25)
+    p_eval = np.asarray(model.forward(x[:B], training=False))
+    net.set_flat(model.arena.host_params().astype(np.float64))
+    np.testing.assert_allclose(p_eval, net.forward(x[:B], training=False), rtol=1e-2, atol=2e-3)
+
+
+def test_tc_mlp_dropout_graph_replay_draws_a_fresh_mask_every_step():
+    """Model.train replays ONE captured graph; the dropout offset is the on-device step counter, so the replayed steps equal
+    eager steps (which pass the host's step count) -- a mask baked into the graph would not."""
+    rng = np.random.default_rng(5)
+    x = rng.random((4 * 128, 784), dtype=np.float32)
+    y = np.eye(10)[rng.integers(0, 10, len(x))]
+    runs = []
+    for graph in (True, False):
+        model, _, _ = _dense_example_model("bf16", lr=0.002)
+        model.graph_steps = graph
+        model.train(x, y, epochs=3, batch_size=128, verbose=0)
+        runs.append(model.arena.host_params())
+        assert len(getattr(model, "_graphs", {})) == (1 if graph else 0)
+    np.testing.assert_allclose(runs[0], runs[1], rtol=1e-3, atol=1e-4)
