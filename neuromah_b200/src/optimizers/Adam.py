@@ -82,6 +82,7 @@ class Optimizer_Adam:
         if self._dev_snapshot != self._host_snapshot():
             lib.nm_adam_state_init(self._dev_state.p, float(self.learning_rate), float(self.decay), float(self.beta_1),
                                    float(self.beta_2), float(self.epsilon), C.c_longlong(int(self.iterations)), stream())
+            self._dev_snapshot = self._host_snapshot()      # a second call (e.g. inside a graph capture) must not launch again
         return self._dev_state
 
     def update_arena_dev(self, arena, n_apply=1):
