@@ -76,6 +76,13 @@ def vgg_spec_and_params(seed=0):
     return spec, _init(spec, seed, "he")
 
 
+def mlp_spec_and_params(seed=0):
+    """BASELINE.json configs[0]: the clean 784-128-10 MLP (Dense+ReLU, Dense, Softmax; examples/test_Dense_MNIST.py), RandomNormal init."""
+    spec = [{"kind": "dense", "n_in": 784, "n_out": 128, "relu": True}, {"kind": "dense", "n_in": 128, "n_out": 10, "relu": False},
+            {"kind": "softmax"}]
+    return spec, _init(spec, seed, "random_normal")
+
+
 def _init(spec, seed, init):
     rng = np.random.RandomState(seed)
     params = []
@@ -103,6 +110,11 @@ WORKLOADS = {
                 desc="VGG-style stack C64 C64 P C128 C128 P C256 C256 P FC10 (3x3 'same' + ReLU, He init) on 32x32x3, "
                      "softmax-CE, Adam x2 per layer (reference quirk Q1)",
                 cpu_sample=64, cpu_steps=4, ref_budget=4_000),
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case (launch-bound on a GPU: 0.078 GFLOP per step)
+    "mlp": dict(metric="train samples/sec (Dense MNIST MLP 784-128-10)", batch=128, shape=(784,), make=mlp_spec_and_params,
+                flops_per_sample=0.610e6,
+                desc="MLP 784-128-10 (Dense+ReLU, Dense, Softmax), softmax-CE, Adam x2 per layer (reference quirk Q1), batch 128",
+                cpu_sample=128, cpu_steps=200, ref_budget=400_000),
     # BASELINE.json configs[4]: one FedAvg client per GPU; a "step" of this workload is one ROUND = `local_steps` local
     # training steps at batch 4096 (no gradient exchange) + federated_average of the weight slab over NCCL
     "fedavg": dict(metric="train samples/sec (FedAvg rounds, Conv2D MNIST CNN, one client per GPU)", batch=4096, shape=(1, 28, 28),
@@ -136,12 +148,20 @@ def ncu_traffic(name):
 
 
 _TAG = re.compile(r"\[(\d+)->(\d+)@(\d+)\]")
+_DTAG = re.compile(r"tc_dense_gen_\w+\[(\d+)->(\d+)\]")
 
 
 def kernel_work(name, b):
     """(algorithmic FLOPs, algorithmic HBM bytes) of one launch of the named operator at batch b."""
     c2 = 2.0 * b * 64 * 32 * 9 * 14 * 14          # conv fprop = dgrad = wgrad = 2 B OC IC kH kW oh ow (SURVEY 8d)
     c1 = 2.0 * b * 32 * 1 * 9 * 28 * 28
+    m = _DTAG.search(name)
+    if m:                                         # general Dense GEMMs, tagged [n_in->n_out]: bf16 operands in, bf16 / fp32 out
+        n_in, n_out = int(m.group(1)), int(m.group(2))
+        flops = 2.0 * b * n_in * n_out
+        if "wgrad" in name:
+            return flops, 2.0 * b * (n_in + n_out) + 4.0 * n_in * n_out
+        return flops, 2.0 * b * (n_in + n_out) + 2.0 * n_in * n_out
     m = _TAG.search(name)
     if m:                                         # general conv kernels, tagged [ic->oc@h]
         ic, oc, h = int(m.group(1)), int(m.group(2)), int(m.group(3))
@@ -499,7 +519,7 @@ def main():
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.steps is None:
-        args.steps = {"mnist": 1000, "vgg": 100, "fedavg": 100}[args.workload]
+        args.steps = {"mnist": 1000, "vgg": 100, "fedavg": 100, "mlp": 2000}[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
