@@ -23,6 +23,7 @@
 //   the GPU if a peer never arrives.  Measured at 2 GPUs, 50 186 floats, back-to-back launches: see DESIGN.md section 5.
 #include "nm_common.cuh"
 #include "nm_adam.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -289,7 +290,15 @@ int nm_dp_push_f32(void* dp, const float* grad, size_t n, int chunk_lo, int chun
     int dev = 0, sms = 0;
     NM_CUDA(cudaGetDevice(&dev));
     NM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int blocks = chunk_hi - chunk_lo < 2 * sms ? chunk_hi - chunk_lo : 2 * sms;
+    // Grid size, measured at 8 GPUs (profiles/r02_dp_push_grid.txt): a SMALL slab (MNIST CNN: 49 chunks) is pushed right before
+    // the collect kernel needs it, so it takes a block per chunk (4 blocks: 0.257 ms per step instead of 0.232); a LARGE
+    // range (VGG: up to 577 chunks per layer) only has to land a backward pass later, and a 2-CTAs-per-SM grid took SM time
+    // from the conv kernels it overlaps (1.848 ms per step against 1.821 with 16-64 blocks).  NM_DP_PUSH_BLOCKS overrides.
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("NM_DP_PUSH_BLOCKS"); forced = e ? atoi(e) : 0; }
+    const int chunks = chunk_hi - chunk_lo;
+    int blocks = forced > 0 ? forced : (chunks <= sms ? chunks : 64);
+    if (blocks > chunks) blocks = chunks;
     return nm::launch_pdl("dp_push", dp_push_kernel, dim3(blocks), dim3(kThreads), 0, nm::S(stream), d->dev, grad, n, chunk_lo, chunk_hi);
 }
 

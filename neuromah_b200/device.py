@@ -140,7 +140,7 @@ class _Block:
 
     def __del__(self):
         ptr, self.ptr = self.ptr, None
-        if ptr:
+        if ptr and _release is not None:          # module globals are gone at interpreter shutdown: the driver reclaims the block
             _release("device", ptr)
 
 
@@ -187,7 +187,7 @@ class PinnedBuffer:
 
     def __del__(self):
         ptr, self.ptr = getattr(self, "ptr", None), None
-        if ptr:
+        if ptr and _release is not None and _pinned_ranges is not None:
             self.array = None
             _pinned_ranges[:] = [r for r in _pinned_ranges if r[0] != ptr]
             _release("host", ptr)
