@@ -40,6 +40,8 @@ using namespace tc;
 constexpr int OC = 32;
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ __nv_bfloat162 u2bf(uint32_t u) { return *reinterpret_cast<__nv_bfloat162*>(&u); }
+__device__ __forceinline__ uint32_t bf2u(__nv_bfloat162 b) { return *reinterpret_cast<uint32_t*>(&b); }
 // byte offset of (row, byte-in-row) inside a tile of 64-byte / 128-byte rows in the SWIZZLE_64B / SWIZZLE_128B layout
 // (16-byte chunk index XOR address bits [7,9) / [7,10)); the tile base is 1024-byte aligned.
 __device__ __forceinline__ uint32_t sw64(uint32_t row, uint32_t byte) { const uint32_t o = row * 64 + byte; return o ^ (((o >> 7) & 3) << 4); }
@@ -245,24 +247,34 @@ conv1_tc_fwd_kernel(const XT* __restrict__ x, float x_scale, const __nv_bfloat16
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);
                 }
-                float best[8];
-                uint32_t nibs = 0;
+                // ReLU + 2x2 max-pool + arg-max on PACKED bf16 pairs (two channels per instruction): the kernel is bound by the
+                // half-rate ALU pipe, and the exact-FP32 version cost ~15 ALU instructions per channel (3 x compare / select
+                // value / select index, ReLU, nibble assembly, pack) against ~9 here.  The pooled VALUE is unchanged --
+                // rounding is monotonic, so bf16(max(relu(v))) == max(relu(bf16(v))) bit for bit.  The arg-max follows the
+                // reference's scan (0,0),(0,1),(1,0),(1,1) with its strict '>' (maxpooling_backend.cpp:104: the first maximum
+                // wins) on the bf16-ROUNDED conv values, i.e. two positions that differ only below bf16 resolution count as
+                // a tie -- the values the rest of the tensor-core plan sees.  A window with no positive value keeps position 0
+                // and a cleared ReLU bit, like the reference's pool over the ReLU output.
+                uint32_t outw[4], n4[4];
+                const __nv_bfloat162 zero2 = u2bf(0u);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    // max-pool of ReLU == ReLU of max-pool; first max of the reference scan (0,0),(0,1),(1,0),(1,1) with its
-                    // strict '>' (maxpooling_backend.cpp:104); an all-non-positive window keeps position 0 like the reference.
-                    float bv = fmaxf(__uint_as_float(raw[0][c]), 0.f); uint32_t bi = 0;
-#pragma unroll
-                    for (int pos = 1; pos < (NM_DBG(2) ? 1 : 4); ++pos) {
-                        const float v = __uint_as_float(raw[pos][c]);
-                        if (v > bv) { bv = v; bi = pos; }
-                    }
-                    best[c] = bv;
-                    nibs |= (bi | (bv > 0.f ? 4u : 0u)) << (4 * c);
+                for (int pr = 0; pr < 4; ++pr) {
+                    const __nv_bfloat162 h0 = u2bf(pack_bf16x2(__uint_as_float(raw[0][2 * pr]), __uint_as_float(raw[0][2 * pr + 1]))),
+                                         h1 = u2bf(pack_bf16x2(__uint_as_float(raw[1][2 * pr]), __uint_as_float(raw[1][2 * pr + 1]))),
+                                         h2 = u2bf(pack_bf16x2(__uint_as_float(raw[2][2 * pr]), __uint_as_float(raw[2][2 * pr + 1]))),
+                                         h3 = u2bf(pack_bf16x2(__uint_as_float(raw[3][2 * pr]), __uint_as_float(raw[3][2 * pr + 1])));
+                    const __nv_bfloat162 a = __hmax2(h0, h1), b = __hmax2(h2, h3), m = __hmax2(a, b);
+                    // 0xFFFF per half where the later position is strictly greater: ties keep the earlier one
+                    const uint32_t g01 = __hgt2_mask(h1, h0), g23 = __hgt2_mask(h3, h2), gab = __hgt2_mask(b, a), gp = __hgt2_mask(m, zero2);
+                    outw[pr] = bf2u(__hmax2(m, zero2));
+                    const uint32_t b0 = (gab & g23) | (~gab & g01);              // bit 0 of the winner's position, bit 1 is gab
+                    n4[pr] = (b0 & gp & 0x00010001u) | (gab & gp & 0x00020002u) | (gp & 0x00040004u);   // nibble per half
                 }
+                // n4[pr] holds the nibbles of channels 2pr (bits 0-2) and 2pr+1 (bits 16-18): interleave them into bytes
+                const uint32_t w01 = n4[0] | (n4[1] << 8), w23 = n4[2] | (n4[3] << 8);
+                const uint32_t nibs = ((w01 | (w01 >> 12)) & 0xFFFFu) | (((w23 | (w23 >> 12)) & 0xFFFFu) << 16);
                 if (valid && !NM_DBG(3)) {
-                    *reinterpret_cast<uint4*>(yo + chunk * 8) = make_uint4(pack_bf16x2(best[0], best[1]), pack_bf16x2(best[2], best[3]),
-                                                                            pack_bf16x2(best[4], best[5]), pack_bf16x2(best[6], best[7]));
+                    *reinterpret_cast<uint4*>(yo + chunk * 8) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
                     io[chunk] = nibs;
                 }
             }
