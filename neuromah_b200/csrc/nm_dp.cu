@@ -39,6 +39,10 @@ struct DpDev {                               // passed to the kernel by value
     unsigned long long timeout_ns;
     size_t slot;                             // words per (parity, rank) slot, multiple of kChunk
     int rank, world;
+    // two-phase mode (large slabs, world >= 4): reduce-scatter region [2 parities][world][gslot] followed by the all-gather
+    // region [2 parities][aslot] in every mailbox
+    int two_phase;
+    size_t gslot, aslot;
 };
 
 struct Dp {
@@ -186,6 +190,155 @@ dp_allreduce_kernel(DpDev c, float* __restrict__ p, float* __restrict__ g, float
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Two-phase exchange for LARGE slabs (world >= 4): reduce-scatter + all-gather, O(n) traffic per rank instead of the
+// O(world * n) of the all-to-all push above (VGG-style stack, 4.75 MB slab, 8 GPUs: 66 MB -> 16.6 MB pushed per rank and
+// step).  Chunk c is OWNED by rank c % world.
+//   push      a rank sends its gradients of chunk c only to the owner (same tagged 8-byte words, slot (c / world) of the
+//             reduce-scatter region [parity][source rank]) -- dp_push2_kernel behind each wgrad, the rest by phase 0 below;
+//   phase 1   the owner collects the world - 1 contributions, sums in RANK ORDER (bit-identical on every rank by
+//             construction: only the owner forms the sum), and broadcasts the sum to every peer's all-gather region;
+//   phase 2   every rank picks up the sums of the chunks it does not own.
+// Every rank then holds the full summed gradient (as after an in-place all-reduce) and applies Adam to the whole slab, so
+// parameters AND optimizer state stay replicated (checkpoints need no gather).  Waits only ever depend on pushes that are
+// issued before any wait of the same kernel, so all-resident blocks cannot deadlock; the two-parity argument of the
+// all-to-all protocol carries over (a rank needs every peer's step-s sums to finish step s).
+__device__ __forceinline__ void load_local(const float* __restrict__ g, size_t n, bool vec, size_t i, float2& L) {
+    L = make_float2(0.f, 0.f);
+    if (vec && i + 2 <= n) L = *reinterpret_cast<const float2*>(g + i);
+    else {
+        if (i < n) L.x = g[i];
+        if (i + 1 < n) L.y = g[i + 1];
+    }
+}
+
+__device__ __forceinline__ uint4 poll_words(const uint2* q, uint32_t step, const DpDev& c) {
+    uint4 a = ld_words(q);
+    if (a.y != step || a.w != step) {
+        const unsigned long long t_start = global_ns();
+        unsigned polls = 0;
+        do {
+            if ((++polls & 255u) == 0 && global_ns() - t_start > c.timeout_ns) { atomicExch(c.status, 1); break; }
+            a = ld_words(q);
+        } while (a.y != step || a.w != step);
+    }
+    return a;
+}
+
+// reduce-scatter push of chunks [ch_lo, ch_hi): to the owner only
+__global__ void __launch_bounds__(kThreads)
+dp_push2_kernel(DpDev c, const float* __restrict__ g, size_t n, int ch_lo, int ch_hi) {
+    pdl_trigger();
+    pdl_wait();
+    const int tid = threadIdx.x;
+    const uint32_t step = *reinterpret_cast<volatile uint32_t*>(c.seq) + 1u;
+    const size_t par = (size_t)(step & 1u);
+    const bool vec = (reinterpret_cast<uintptr_t>(g) & 7) == 0;
+    for (int ch = ch_lo + blockIdx.x; ch < ch_hi; ch += gridDim.x) {
+        const int owner = ch % c.world;
+        if (owner == c.rank) continue;
+        uint2* q = c.mail[owner] + (par * c.world + c.rank) * c.gslot + (size_t)(ch / c.world) * kChunk;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const size_t off = h * (kChunk / 2) + (size_t)tid * 2;
+            float2 L;
+            load_local(g, n, vec, (size_t)ch * kChunk + off, L);
+            st_words(q + off, L.x, L.y, step);
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+dp_allreduce2_kernel(DpDev c, float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                     size_t n, nm_adam_state* ds, int n_apply, int advance, int pushed_from) {
+    pdl_trigger();
+    pdl_wait();
+    const int tid = threadIdx.x;
+    const uint32_t step = *reinterpret_cast<volatile uint32_t*>(c.seq) + 1u;
+    const size_t par = (size_t)(step & 1u);
+    const int nchunks = (int)((n + kChunk - 1) / kChunk);
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                       reinterpret_cast<uintptr_t>(v)) & 7) == 0;
+    AdamHP hp{};
+    if (MODE == 1) hp = adam_hp_from(ds);
+    const uint2* my_rs = c.mail[c.rank] + par * c.world * c.gslot;
+    const uint2* my_ag = c.mail[c.rank] + 2 * (size_t)c.world * c.gslot + par * c.aslot;
+
+    auto finish = [&](size_t i, float2 G) {                   // summed gradient -> slab (+ Adam)
+        if (vec && i + 2 <= n) {
+            *reinterpret_cast<float2*>(g + i) = G;
+            if (MODE == 1) {
+                float2 P = *reinterpret_cast<float2*>(p + i), M = *reinterpret_cast<float2*>(m + i), V = *reinterpret_cast<float2*>(v + i);
+                adam_one(P.x, G.x, M.x, V.x, hp, n_apply); adam_one(P.y, G.y, M.y, V.y, hp, n_apply);
+                *reinterpret_cast<float2*>(p + i) = P; *reinterpret_cast<float2*>(m + i) = M; *reinterpret_cast<float2*>(v + i) = V;
+            }
+        } else {
+            const float gs[2] = {G.x, G.y};
+            for (int u = 0; u < 2; ++u)
+                if (i + u < n) {
+                    g[i + u] = gs[u];
+                    if (MODE == 1) adam_one(p[i + u], gs[u], m[i + u], v[i + u], hp, n_apply);
+                }
+        }
+    };
+
+    // phase 0: reduce-scatter push of the chunks the backward pass has not delivered yet (the first layer's)
+    const int lim = pushed_from < nchunks ? pushed_from : nchunks;
+    for (int ch = blockIdx.x; ch < lim; ch += gridDim.x) {
+        const int owner = ch % c.world;
+        if (owner == c.rank) continue;
+        uint2* q = c.mail[owner] + (par * c.world + c.rank) * c.gslot + (size_t)(ch / c.world) * kChunk;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const size_t off = h * (kChunk / 2) + (size_t)tid * 2;
+            float2 L;
+            load_local(g, n, vec, (size_t)ch * kChunk + off, L);
+            st_words(q + off, L.x, L.y, step);
+        }
+    }
+    // phase 1: owned chunks -- collect, sum in rank order, broadcast the sum
+    for (int ch = c.rank + (int)blockIdx.x * c.world; ch < nchunks; ch += (int)gridDim.x * c.world) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const size_t off = h * (kChunk / 2) + (size_t)tid * 2, i = (size_t)ch * kChunk + off;
+            float2 L;
+            load_local(g, n, vec, i, L);
+            float2 G = make_float2(0.f, 0.f);
+            for (int r = 0; r < c.world; ++r) {
+                float2 t = L;
+                if (r != c.rank) {
+                    const uint4 a = poll_words(my_rs + (size_t)r * c.gslot + (size_t)(ch / c.world) * kChunk + off, step, c);
+                    t = make_float2(__uint_as_float(a.x), __uint_as_float(a.z));
+                }
+                if (r == 0) G = t; else { G.x += t.x; G.y += t.y; }
+            }
+            for (int d = 1; d < c.world; ++d) {
+                uint2* q = c.mail[(c.rank + d) % c.world] + 2 * (size_t)c.world * c.gslot + par * c.aslot + i;
+                st_words(q, G.x, G.y, step);
+            }
+            finish(i, G);
+        }
+    }
+    // phase 2: the other ranks' chunks -- pick up their sums
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        if (ch % c.world == c.rank) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const size_t i = (size_t)ch * kChunk + h * (kChunk / 2) + (size_t)tid * 2;
+            const uint4 a = poll_words(my_ag + i, step, c);
+            finish(i, make_float2(__uint_as_float(a.x), __uint_as_float(a.z)));
+        }
+    }
+
+    __syncthreads();
+    if (tid == 0 && atomicAdd(c.ticket, 1u) == gridDim.x - 1) {
+        *c.ticket = 0u;
+        *reinterpret_cast<volatile uint32_t*>(c.seq) = step;
+        if (MODE == 1 && advance) adam_state_advance(ds);
+    }
+}
+
 int launch(Dp* d, int mode, float* p, float* g, float* m, float* v, size_t n, nm_adam_state* st, int n_apply, int advance, void* stream,
            int pushed_from = 0x7fffffff) {
     if (!d->connected) return nm::fail(NM_ERR_BAD_ARG, "%s%s", "nm_dp: not connected (call nm_dp_connect first)");
@@ -196,6 +349,13 @@ int launch(Dp* d, int mode, float* p, float* g, float* m, float* v, size_t n, nm
     NM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int nchunks = (int)((n + kChunk - 1) / kChunk);
     const dim3 grid(nchunks < sms ? nchunks : sms);               // all blocks resident: a waiting block never starves a pusher
+    if (d->dev.two_phase) {
+        if (mode == 0)
+            return nm::launch_pdl("dp_allreduce2", dp_allreduce2_kernel<0>, grid, dim3(kThreads), 0, nm::S(stream), d->dev,
+                                  (float*)nullptr, g, (float*)nullptr, (float*)nullptr, n, (nm_adam_state*)nullptr, 0, 0, pushed_from);
+        return nm::launch_pdl("dp_allreduce2_adam", dp_allreduce2_kernel<1>, grid, dim3(kThreads), 0, nm::S(stream), d->dev,
+                              p, g, m, v, n, st, n_apply, advance, pushed_from);
+    }
     if (mode == 0)
         return nm::launch_pdl("dp_allreduce", dp_allreduce_kernel<0>, grid, dim3(kThreads), 0, nm::S(stream), d->dev,
                               (float*)nullptr, g, (float*)nullptr, (float*)nullptr, n, (nm_adam_state*)nullptr, 0, 0, pushed_from);
@@ -216,6 +376,19 @@ int nm_dp_create(void** dp, int rank, int world, size_t max_floats) {
     d->dev.slot = (max_floats + kChunk - 1) / kChunk * kChunk;
     d->dev.timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
     d->data_bytes = 2 * (size_t)world * d->dev.slot * sizeof(uint2);
+    {
+        // large slabs on >= 4 GPUs take the two-phase (reduce-scatter + all-gather) exchange: O(n) instead of O(world n) bytes
+        // per rank; small slabs stay on the single-hop all-to-all (latency).  NM_DP_TWO_PHASE=0/1 overrides.
+        const char* e = getenv("NM_DP_TWO_PHASE");
+        d->dev.two_phase = e ? atoi(e) != 0 : (world >= 4 && max_floats >= (1u << 18));
+        if (world < 2) d->dev.two_phase = 0;
+        if (d->dev.two_phase) {
+            const size_t nchunks = d->dev.slot / kChunk;
+            d->dev.gslot = (nchunks + world - 1) / world * kChunk;
+            d->dev.aslot = d->dev.slot;
+            d->data_bytes = (2 * (size_t)world * d->dev.gslot + 2 * d->dev.aslot) * sizeof(uint2);
+        }
+    }
     cudaError_t e = cudaMalloc(&d->base, d->data_bytes);                     // cudaMalloc: cudaIpc cannot export pool memory
     if (e == cudaSuccess) e = cudaMemset(d->base, 0, d->data_bytes);         // tag 0 = "no step yet" (steps count from 1)
     if (e == cudaSuccess) e = cudaMalloc(&d->local, 256);
@@ -299,6 +472,8 @@ int nm_dp_push_f32(void* dp, const float* grad, size_t n, int chunk_lo, int chun
     const int chunks = chunk_hi - chunk_lo;
     int blocks = forced > 0 ? forced : (chunks <= sms ? chunks : 64);
     if (blocks > chunks) blocks = chunks;
+    if (d->dev.two_phase)
+        return nm::launch_pdl("dp_push2", dp_push2_kernel, dim3(blocks), dim3(kThreads), 0, nm::S(stream), d->dev, grad, n, chunk_lo, chunk_hi);
     return nm::launch_pdl("dp_push", dp_push_kernel, dim3(blocks), dim3(kThreads), 0, nm::S(stream), d->dev, grad, n, chunk_lo, chunk_hi);
 }
 

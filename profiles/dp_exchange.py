@@ -4,8 +4,10 @@ VGG-style stack's 1 186 378 floats (config 4).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29544 profiles/dp_exchange.py
 
-NVLink bytes are algorithmic: the protocol ships one 8-byte {value, step tag} word per 4-byte gradient to each of the
-world - 1 peers (no acknowledgements, no reads over the link), so a rank pushes 2 * 4 * n * (world - 1) bytes per step."""
+NVLink bytes are algorithmic: the protocol ships 8-byte {value, step tag} words, no acknowledgements, no reads over the
+link.  Small slabs (all-to-all): one word per gradient to each of the world - 1 peers = 8 n (world - 1) bytes per rank and
+step.  Large slabs on >= 4 GPUs (two-phase: reduce-scatter to the chunk owner + all-gather of the owner's sums):
+16 n (world - 1) / world bytes."""
 import ctypes as C
 import os
 import sys
@@ -63,8 +65,9 @@ for name, n, first in (("MNIST CNN slab", 50186, 320), ("VGG-style slab", 118637
     t_nccl = run(lambda: lib.nm_comm_allreduce_sum_f32(comm.handle, g.p, n, s))
     comm.check()
     if rank == 0:
-        pushed = 8 * n * (world - 1)
-        print(f"world {world} | {name}: {n} floats ({4 * n / 1e6:.2f} MB) | fused push+collect+Adam {t_fused:.1f} us | "
+        two_phase = world >= 4 and n >= (1 << 18) if os.environ.get("NM_DP_TWO_PHASE") is None else os.environ["NM_DP_TWO_PHASE"] != "0"
+        pushed = 16 * n * (world - 1) // world if two_phase else 8 * n * (world - 1)
+        print(f"world {world} | {'two-phase (reduce-scatter + all-gather)' if two_phase else 'all-to-all'} | {name}: {n} floats ({4 * n / 1e6:.2f} MB) | fused push+collect+Adam {t_fused:.1f} us | "
               f"early push kernel + collect/Adam kernel (as in the training step, here back to back) {t_split:.1f} us | "
               f"Adam alone {t_adam:.1f} us | NCCL all-reduce alone {t_nccl:.1f} us | NVLink bytes pushed per rank and step "
               f"{pushed / 1e6:.2f} MB ({pushed / 1e3 / max(t_fused, 1e-9):.1f} GB/s per rank while the fused kernel runs)", flush=True)
