@@ -58,7 +58,7 @@ __global__ void maxpool2x2_fwd_kernel(const uint4* __restrict__ x, uint4* __rest
 
 // dpool [N][H/2 (+2)][W/2 (+2)][C] + idx -> dy_pad [N][H+2][W+2][C]: the pooled gradient goes to the arg-max position
 // of its window if the ReLU mask bit is set, every other element (halo included) is written as zero.
-// Grid: blockIdx.y = image row of the haloed gradient (n * Hp + hh), threads along (ww, 8-channel group).  The flat
+// Block = (one image row of (ww, 8-channel group) elements) x (a few rows); blockIdx.x walks the rows n * Hp + hh.  The flat
 // one-thread-per-element index of the first version needed three 32-bit divisions by run-time values per 16-byte store and
 // was INSTRUCTION-bound (block 1 of the VGG stack: 65 us for 198 MB, 0.47 of the HBM bound); here the row split is one
 // division per block and the channel-group split a shift.
@@ -67,11 +67,12 @@ __global__ void maxpool2x2_bwd_kernel(const uint4* __restrict__ dpool, const uin
     pdl_trigger();
     pdl_wait();
     const int G = C / 8, PH = H / 2, PW = W / 2, Hp = H + 2, Wp = W + 2;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;                // (ww, g) within the row
-    if (t >= Wp * G) return;
+    const int t = blockIdx.y * blockDim.x + threadIdx.x;                // (ww, g) within the row
+    const int row = blockIdx.x * blockDim.y + threadIdx.y;              // n * Hp + hh
+    if (t >= Wp * G || row >= N * Hp) return;
     const int ww = g_shift >= 0 ? t >> g_shift : t / G, g = t - ww * G;
-    const int n = blockIdx.y / Hp, hh = blockIdx.y - n * Hp;
-    const size_t i = (size_t)blockIdx.y * Wp * G + t;
+    const int n = row / Hp, hh = row - n * Hp;
+    const size_t i = (size_t)row * Wp * G + t;
     if (hh < 1 || hh > H || ww < 1 || ww > W) { dy[i] = make_uint4(0u, 0u, 0u, 0u); return; }
     const int ph = (hh - 1) >> 1, pw = (ww - 1) >> 1;
     const uint32_t me = (uint32_t)(((hh - 1) & 1) * 2 + ((ww - 1) & 1)) | 4u;        // nibble that selects this element
@@ -142,28 +143,14 @@ int nm_tc_maxpool2x2_bwd_bf16(const void* dpool, const void* idx, void* dy_pad, 
     NM_REQUIRE(dpool && idx && dy_pad, "null pointer");
     NM_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0, "bad dimensions (even H, W; C % 8 == 0)");
     const long long rows = (long long)N * (H + 2);
+    NM_REQUIRE(rows < (1ll << 31) - 1024, "tensor too large for 32-bit row indices");
     const int G = C / 8, per_row = (W + 2) * G;
     int g_shift = -1;
     for (int sft = 0; sft < 16; ++sft) if ((1 << sft) == G) g_shift = sft;                 // G a power of two: shift instead of divide
-    NM_REQUIRE(rows < (1ll << 31), "tensor too large");
-    // blockIdx.y is limited to 65535: fold the excess into z?  rows = N * (H + 2) <= 65535 covers batch 1024 at 32 x 32 only
-    // up to N = 1927, so rows go in gridDim.y when they fit and are split over gridDim.z otherwise
-    if (rows <= 65535)
-        return nm::launch_pdl("maxpool2x2_bwd", maxpool2x2_bwd_kernel, dim3(nm_cdiv((size_t)per_row, 256), (unsigned)rows), dim3(256), 0,
-                              nm::S(stream), static_cast<const uint4*>(dpool), static_cast<const uint32_t*>(idx),
-                              static_cast<uint4*>(dy_pad), N, H, W, C, in_padded, g_shift);
-    // large batches: one launch per slab of whole images
-    const int imgs_per = 65535 / (H + 2);
-    for (int n0 = 0; n0 < N; n0 += imgs_per) {
-        const int nb = N - n0 < imgs_per ? N - n0 : imgs_per;
-        const size_t in_img = (size_t)(in_padded ? (H / 2 + 2) * (W / 2 + 2) : (H / 2) * (W / 2)) * G;
-        int rc = nm::launch_pdl("maxpool2x2_bwd", maxpool2x2_bwd_kernel, dim3(nm_cdiv((size_t)per_row, 256), (unsigned)(nb * (H + 2))), dim3(256), 0,
-                                nm::S(stream), static_cast<const uint4*>(dpool) + (size_t)n0 * in_img,
-                                static_cast<const uint32_t*>(idx) + (size_t)n0 * (H / 2) * (W / 2) * G,
-                                static_cast<uint4*>(dy_pad) + (size_t)n0 * (H + 2) * (W + 2) * G, nb, H, W, C, in_padded, g_shift);
-        if (rc) return rc;
-    }
-    return NM_OK;
+    const int bx = per_row < 1024 ? per_row : 1024, by = 768 / bx > 0 ? 768 / bx : 1;       // a whole row per block where it fits
+    return nm::launch_pdl("maxpool2x2_bwd", maxpool2x2_bwd_kernel, dim3(nm_cdiv((size_t)rows, by), nm_cdiv((size_t)per_row, bx)),
+                          dim3(bx, by), 0, nm::S(stream), static_cast<const uint4*>(dpool), static_cast<const uint32_t*>(idx),
+                          static_cast<uint4*>(dy_pad), N, H, W, C, in_padded, g_shift);
 }
 
 int nm_tc_dense_dgrad_bf16(const float* dlogits, const float* w_packed, void* dx, int B, int K, int n_out, void* stream) {
