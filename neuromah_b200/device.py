@@ -139,7 +139,8 @@ class _Block:
         self.ptr, self.nbytes = p.value, int(nbytes)
 
     def __del__(self):
-        ptr, self.ptr = self.ptr, None
+        ptr = getattr(self, "ptr", None)      # __init__ may have raised before the block existed
+        self.ptr = None
         if ptr and _release is not None:          # module globals are gone at interpreter shutdown: the driver reclaims the block
             _release("device", ptr)
 
