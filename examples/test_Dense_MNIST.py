@@ -25,7 +25,11 @@ from Neuromah.src.metrics import Accuracy_Categorical
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=25600)
 ap.add_argument("--epochs", type=int, default=2)
-ap.add_argument("--as-written", action="store_true")
+ap.add_argument("--as-written", action="store_true",
+                help="the reference script's stack verbatim (Dropout twice, softmax applied twice); FP32-exact mode only")
+ap.add_argument("--dropout", action="store_true", help="the reference script's stack with a single softmax (Dense+ReLU, Dropout, "
+                "Dense+ReLU, Dropout, Dense, Softmax): takes the tensor-core MLP plan in --mode bf16")
+ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16"], help="bf16 = tcgen05 MLP plan (neuromah_b200/tc_plan_mlp.py)")
 args = ap.parse_args()
 rng = np.random.default_rng(1)
 labels = rng.integers(0, 10, args.n)
@@ -45,13 +49,24 @@ if args.as_written:
     model.set(loss=Loss_CategoricalCrossentropy(model=model), optimizer=Optimizer_Adam(learning_rate=0.001),
               accuracy=Accuracy_Categorical(model=model))
     batch = 32
+elif args.dropout:
+    model.add(Layer_Dense(n_inputs=784, n_neurons=128, activation=Activation_ReLU()))
+    model.add(Layer_Dropout(rate=0.25))
+    model.add(Layer_Dense(n_inputs=128, n_neurons=64, activation=Activation_ReLU()))
+    model.add(Layer_Dropout(rate=0.25))
+    model.add(Layer_Dense(n_inputs=64, n_neurons=10))
+    model.add(Activation_Softmax())
+    model.set(loss=Loss_CategoricalCrossentropy, optimizer=Optimizer_Adam(learning_rate=0.001), accuracy=Accuracy_Categorical)
+    batch = 128
 else:
     model.add(Layer_Dense(784, 128, activation=Activation_ReLU()))
     model.add(Layer_Dense(128, 10))
     model.add(Activation_Softmax())
     model.set(loss=Loss_CategoricalCrossentropy, optimizer=Optimizer_Adam(learning_rate=0.001), accuracy=Accuracy_Categorical)
     batch = 128
-model.finalize()
+if args.as_written and args.mode == "bf16":
+    raise SystemExit("--as-written (softmax applied twice) runs in FP32-exact mode only; use --dropout --mode bf16")
+model.finalize(mode=None if args.mode == "fp32" else "bf16")
 t0 = time.perf_counter_ns()
 model.train(X, y, epochs=args.epochs, batch_size=batch, validation_data=(X[:1024], y[:1024]))
 print(f"Total training time: {time.perf_counter_ns() - t0} ns")
