@@ -315,6 +315,30 @@ size_t nm_tc_dense_wgrad_gen_workspace(int B, int n_in, int n_out);
 int nm_tc_dense_wgrad_gen_bf16(const void* x, const void* dy, const float* w, float* dw, float* db, void* workspace, size_t workspace_bytes,
                                int B, int n_in, int n_out, float scale, float l1, float l2, void* stream);
 
+/* ---- FP32-exact Dense layers on the tensor cores (mode "bf16x3"), nm_tc_gemm.cu ------------------------------------
+ * The same three contractions (Dense.py:79-85, :96-108) with every operand carried as THREE bf16 planes h + m + l
+ * (h = bf16(v), m = bf16(v - h), l = bf16(v - h - m): 24 mantissa bits) and the six plane pairs above 2^-24 accumulated
+ * in one FP32 TMEM tile, smallest first; the epilogues split their FP32 results back into planes.  Meets the FP32-exact
+ * tolerance of the CUDA-core kernels (rtol 1e-4 / atol 1e-5 against the NumPy path).  A "x3" matrix is three bf16
+ * [rows][cols] planes `*_plane` elements apart (multiple of 8, >= rows * cols); weight planes are rows * cols apart.
+ *   nm_tc_split3_f32 / nm_tc_split3_u8   float32 (optionally through a ReLU mask: 0 where relu_mask <= 0, x mask_scale
+ *                                        elsewhere) / raw uint8 pixels divided by denom -> planes
+ *   nm_tc_pack_dense_gen_x3              w f32 [n_in][n_out] -> w_kn3 [3][n_in][n_out], w_nk3 [3][n_out][n_in]
+ *   nm_tc_dense_fprop_gen_x3             as nm_tc_dense_fprop_gen_bf16; y_f32 (optional) also receives the FP32 result
+ *   nm_tc_dense_dgrad_gen_x3             relu_mask = the h plane of the activation below
+ *   nm_tc_dense_wgrad_gen_x3             workspace: nm_tc_dense_wgrad_gen_workspace */
+int nm_tc_split3_f32(const float* x, const void* relu_mask, float mask_scale, void* planes, size_t n, size_t plane_stride, void* stream);
+int nm_tc_split3_u8(const uint8_t* x, float denom, void* planes, size_t n, size_t plane_stride, void* stream);
+int nm_tc_pack_dense_gen_x3(const float* w, void* w_kn3, void* w_nk3, int n_in, int n_out, void* stream);
+int nm_tc_dense_fprop_gen_x3(const void* x3, size_t x_plane, const void* w_nk3, const float* bias, void* y3, size_t y_plane, float* y_f32,
+                             int B, int n_in, int n_out, int relu, float drop_keep, unsigned long long drop_seed,
+                             unsigned long long drop_offset, const long long* drop_offset_dev, void* stream);
+int nm_tc_dense_dgrad_gen_x3(const void* dy3, size_t dy_plane, const void* w_kn3, const void* relu_mask, float mask_scale, void* dx3,
+                             size_t dx_plane, int B, int n_in, int n_out, void* stream);
+int nm_tc_dense_wgrad_gen_x3(const void* x3, size_t x_plane, const void* dy3, size_t dy_plane, const float* w, float* dw, float* db,
+                             void* workspace, size_t workspace_bytes, int B, int n_in, int n_out, float scale, float l1, float l2,
+                             void* stream);
+
 /* First conv of the net (C_in = 1, 3x3 'same', ReLU, no bias) + MaxPooling2D(2,2) on tcgen05: the 4x4 input patch of a
  * pool window is the K = 16 dimension and the weights are expanded to Wext[(window position, oc)][4x4] (zero outside the
  * 3x3 support), so one MMA yields all four conv values of a window per TMEM lane and the pool needs no cross-lane traffic.

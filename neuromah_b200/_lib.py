@@ -106,6 +106,12 @@ _SIGS = {
     "nm_tc_dense_fprop_gen_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, C.c_ulonglong, C.c_ulonglong, _vp, _vp]),
     "nm_tc_dense_dgrad_gen_bf16": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp]),
     "nm_tc_dense_wgrad_gen_workspace": (_sz, [_i, _i, _i]),
+    "nm_tc_split3_f32": (_i, [_vp, _vp, _f, _vp, _sz, _sz, _vp]),
+    "nm_tc_split3_u8": (_i, [_vp, _f, _vp, _sz, _sz, _vp]),
+    "nm_tc_pack_dense_gen_x3": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "nm_tc_dense_fprop_gen_x3": (_i, [_vp, _sz, _vp, _vp, _vp, _sz, _vp, _i, _i, _i, _i, _f, C.c_ulonglong, C.c_ulonglong, _vp, _vp]),
+    "nm_tc_dense_dgrad_gen_x3": (_i, [_vp, _sz, _vp, _vp, _f, _vp, _sz, _i, _i, _i, _vp]),
+    "nm_tc_dense_wgrad_gen_x3": (_i, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _f, _f, _vp]),
     "nm_tc_dense_wgrad_gen_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _f, _f, _vp]),
     "nm_tc_dense_bwd_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_pack_conv1_weights_bf16": (_i, [_vp, _vp, _i, _vp]),

@@ -68,7 +68,9 @@ class Model:
     def finalize(self, xp=np, mode=None):
         """``mode``: None / "fp32" = FP32-exact CUDA-core kernels (per-layer launches, reference layouts);
         "bf16" = tensor-core plan for the supported layer patterns (neuromah_b200/tc_plan.py: the MNIST CNN;
-        neuromah_b200/tc_plan_gen.py: VGG-style conv stacks; neuromah_b200/tc_plan_mlp.py: multi-layer perceptrons)."""
+        neuromah_b200/tc_plan_gen.py: VGG-style conv stacks; neuromah_b200/tc_plan_mlp.py: multi-layer perceptrons);
+        "bf16x3" = FP32-exact on the tensor cores (three bf16 planes per operand, six products per contraction):
+        multi-layer perceptrons only (tc_plan_mlp.py), same tolerance against the NumPy path as "fp32"."""
         from ..activations import Activation_Softmax
         from ..losses import Loss_CategoricalCrossentropy
         from ..losses.Activation_Softmax_Loss_CategoricalCrossentropy import \
@@ -123,8 +125,11 @@ class Model:
             else:
                 raise ValueError("mode='bf16' supports these layer patterns:\n  " +
                                  "\n  ".join(c.PATTERN for c in (TcCnnPlan, TcStackPlan, TcMlpPlan)))
+        elif self.mode == "bf16x3":
+            from ...tc_plan_mlp import TcMlpPlan
+            self.plan = TcMlpPlan(self, split=True)        # raises with the supported pattern when the stack is not an MLP
         elif self.mode != "fp32":
-            raise ValueError("mode must be None, 'fp32' or 'bf16'")
+            raise ValueError("mode must be None, 'fp32', 'bf16' or 'bf16x3'")
         # raw uint8 pixel batches: normalised on the device by 1 / uint8_denominator (examples/test_Conv2D_MNIST.py:27);
         # a tensor-core plan reads the bytes itself, the FP32-exact path converts them in Layer_Input
         self.input_layer.keep_uint8 = self.plan is not None

@@ -14,6 +14,11 @@ are bf16 [B][features]; parameters, gradients and optimizer state stay FP32 in t
 optimizers, the data-parallel exchange, FedAvg and save/load are shared with the FP32 path.
 Numerics: bf16 operands and stored activations, FP32 accumulation (stated tolerance in tests/test_gpu_tc_mlp.py).
 Reference arithmetic: Dense.py:64-108 (incl. the second division by the batch), Relu.py:7-14.
+
+``Model.finalize(mode="bf16x3")`` runs the same plan FP32-EXACT on the tensor cores: every hidden-layer operand is three
+bf16 planes h + m + l (24 mantissa bits) and each contraction the six plane-pair products above 2^-24 in one FP32 TMEM
+accumulator (nm_tc_dense_*_gen_x3); the narrow head (K x n_out <= 16) runs on the FP32 CUDA-core kernels.  Tolerance: the
+FP32-exact one, rtol 1e-4 / atol 1e-5 against the NumPy path.
 """
 from __future__ import annotations
 
@@ -40,6 +45,27 @@ class Bf16Matrix:
 
     def numpy(self):
         return bf16_bits_to_f32(self.buf.numpy()[:self.n])
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+
+class Split3Matrix:
+    """Host-convertible view of an activation kept as three bf16 planes [3][B][features]: h + m + l in float32."""
+
+    def __init__(self, buf: DeviceArray, n):
+        self.buf, self.n = buf, n
+        self.shape = (n, buf.shape[2])
+        self.dtype = np.dtype(np.float32)
+        self.ndim = 2
+
+    def __len__(self):
+        return self.n
+
+    def numpy(self):
+        planes = bf16_bits_to_f32(self.buf.numpy()[:, :self.n])
+        return (planes[2] + planes[1]) + planes[0]
 
     def __array__(self, dtype=None, copy=None):
         a = self.numpy()
@@ -84,24 +110,28 @@ class TcMlpPlan:
     def match(model):
         return TcMlpPlan.parse(model) is not None
 
-    def __init__(self, model):
+    def __init__(self, model, split=False):
         parsed = self.parse(model)
+        mode = "bf16x3" if split else "bf16"
         if parsed is None:
-            raise ValueError(f"mode='bf16' supports the layer pattern: {self.PATTERN}")
+            raise ValueError(f"mode='{mode}' supports the layer pattern: {self.PATTERN}")
         if model.softmax_classifier_output is None:
-            raise ValueError("mode='bf16' needs Loss_CategoricalCrossentropy with a final Activation_Softmax")
+            raise ValueError(f"mode='{mode}' needs Loss_CategoricalCrossentropy with a final Activation_Softmax")
         self.model = model
+        self.split = bool(split)          # FP32-exact: three bf16 planes per operand
         self.hidden, self.de, self.sm, self.drops = parsed
         self.n_in = self.hidden[0].weights.shape[0]
         self.K = self.de.weights.shape[0]
         self.n_out = self.de.weights.shape[1]
         self.B = 0
         self.packed = {}
+        pl = (3,) if self.split else ()
         for d in self.hidden:
             n_in, n_out = d.weights.shape
-            self.packed[id(d)] = (DeviceArray((n_in, n_out), np.uint16), DeviceArray((n_out, n_in), np.uint16))
-        self.w3p = DeviceArray((self.n_out, self.K), np.float32)
-        self.w3hl = DeviceArray.zeros((32, self.K), np.uint16)
+            self.packed[id(d)] = (DeviceArray(pl + (n_in, n_out), np.uint16), DeviceArray(pl + (n_out, n_in), np.uint16))
+        if not self.split:
+            self.w3p = DeviceArray((self.n_out, self.K), np.float32)
+            self.w3hl = DeviceArray.zeros((32, self.K), np.uint16)
         self._side, self._ev_fork, self._ev_join = new_stream(), new_event(), new_event()
         self.pushed_from = None
 
@@ -115,9 +145,10 @@ class TcMlpPlan:
         self.generation = getattr(self, "generation", 0) + (1 if self.B else 0)
         self.B = B
         z = DeviceArray.zeros
-        self.x0 = z((B, self.n_in), np.uint16)
-        self.acts = [z((B, d.weights.shape[1]), np.uint16) for d in self.hidden]
-        self.dacts = [z((B, d.weights.shape[1]), np.uint16) for d in self.hidden]
+        pl = (3,) if self.split else ()
+        self.x0 = z(pl + (B, self.n_in), np.uint16)
+        self.acts = [z(pl + (B, d.weights.shape[1]), np.uint16) for d in self.hidden]
+        self.dacts = [z(pl + (B, d.weights.shape[1]), np.uint16) for d in self.hidden]
         self.probs = z((B, self.n_out))
         self.dlogits = z((B, self.n_out))
         self.losses = z((B,))
@@ -126,16 +157,24 @@ class TcMlpPlan:
         self.dl_hilo = z((B, 32), np.uint16)
         ws = max(lib.nm_tc_dense_wgrad_gen_workspace(B, *d.weights.shape) for d in self.hidden)
         self.ws = DeviceArray((max(ws, 256),), np.uint8)
+        if self.split:        # the head on the FP32 CUDA-core kernels: FP32 copy of its input, logits, dX
+            self.last_f32 = z((B, self.K))
+            self.logits = z((B, self.n_out))
+            self.dx_head = z((B, self.K))
+            self.ws_dw = DeviceArray((max(lib.nm_dense_wgrad_f32_workspace(B, self.K, self.n_out), 256),), np.uint8)
+            return
         self.ws_dw = DeviceArray((max(lib.nm_tc_dense_wgrad_workspace(B, self.K), 256),), np.uint8)
         self.ws_head = z((lib.nm_tc_dense_softmax_ce_workspace(B, self.K),), np.uint8)     # zero-filled once (ticket counter)
 
     def pack_weights(self):
         """Refresh the bf16 operand copies from the FP32 master weights in the arena."""
         s = stream()
+        pack = lib.nm_tc_pack_dense_gen_x3 if self.split else lib.nm_tc_pack_dense_gen_bf16
         for d in self.hidden:
             w_kn, w_nk = self.packed[id(d)]
-            lib.nm_tc_pack_dense_gen_bf16(d.weights.p, w_kn.p, w_nk.p, d.weights.shape[0], d.weights.shape[1], s)
-        lib.nm_tc_pack_dense_weights(self.de.weights.p, self.w3p.p, self.w3hl.p, self.K, self.n_out, 1, self.K, s)
+            pack(d.weights.p, w_kn.p, w_nk.p, d.weights.shape[0], d.weights.shape[1], s)
+        if not self.split:
+            lib.nm_tc_pack_dense_weights(self.de.weights.p, self.w3p.p, self.w3hl.p, self.K, self.n_out, 1, self.K, s)
 
     # ------------------------------------------------------------------ passes ----
     def _dropout_args(self, d, training):
@@ -160,6 +199,8 @@ class TcMlpPlan:
         s = stream()
         self.x = x
         self.pack_weights()          # master weights may have changed (optimizer, set_parameters, FedAvg)
+        if self.split:
+            return self._forward_x3(x, labels, accum, inv_batch, training)
         if x.dtype == np.uint8:
             lib.nm_tc_u8_to_bf16(x.p, float(np.float32(1.0) / np.float32(self.model.uint8_denominator)), self.x0.p, x.size, s)
         else:
@@ -186,6 +227,69 @@ class TcMlpPlan:
         self.model.softmax_classifier_output.dinputs = self.dlogits[0:B]
         return out
 
+    def _forward_x3(self, x, labels, accum, inv_batch, training):
+        """FP32-exact forward: hidden layers on planes (nm_tc_dense_fprop_gen_x3), the head on the FP32 CUDA-core kernels."""
+        B = x.shape[0]
+        s = stream()
+        cap = self.B                                   # rows of a plane (the buffers' capacity)
+        if x.dtype == np.uint8:                        # the division Layer_Input's FP32 path performs
+            lib.nm_tc_split3_u8(x.p, float(self.model.uint8_denominator), self.x0.p, x.size, cap * self.n_in, s)
+        else:
+            lib.nm_tc_split3_f32(x.p, None, 1.0, self.x0.p, x.size, cap * self.n_in, s)
+        cur, cur_n = self.x0, self.n_in
+        for i, (d, act) in enumerate(zip(self.hidden, self.acts)):
+            n_in, n_out = d.weights.shape
+            keep, seed, off, off_dev = self._dropout_args(d, training)
+            last = i == len(self.hidden) - 1
+            _timed(f"tc_dense_gen_fprop_x3[{n_in}->{n_out}]", lib.nm_tc_dense_fprop_gen_x3, cur.p, cap * cur_n, self.packed[id(d)][1].p,
+                   d.biases.p, act.p, cap * n_out, self.last_f32.p if last else None, B, n_in, n_out, 1, keep, seed, off, off_dev, s)
+            d.output = Split3Matrix(act, B)
+            if id(d) in self.drops:
+                self.drops[id(d)].output = d.output
+            cur, cur_n = act, n_out
+        self._trained_forward = training
+        lib.nm_dense_fprop_f32(self.last_f32.p, self.de.weights.p, self.de.biases.p, self.logits.p, B, self.K, self.n_out, 0, s)
+        lib.nm_softmax_fwd_f32(self.logits.p, self.probs.p, B, self.n_out, s)
+        if labels is not None:
+            lib.nm_softmax_ce_f32(self.probs.p, labels.p, self.dlogits.p, self.losses.p, self.correct.p,
+                                  accum.p if accum is not None else None, B, self.n_out,
+                                  float(1.0 / B if inv_batch is None else inv_batch), s)
+        self.dl_hilo_valid = True                      # no hi/lo copy in this mode: the backward reads dlogits itself
+        self.de.output = self.logits[0:B]
+        out = self.probs[0:B]
+        self.sm.output = out
+        self.model.softmax_classifier_output.dinputs = self.dlogits[0:B]
+        return out
+
+    def _backward_x3(self, grad_batch, comm):
+        B = self.x.shape[0]
+        s = stream()
+        cap = self.B
+        scale = 1.0 / (B if grad_batch is None else grad_batch)
+
+        def mscale(d):
+            drop = self.drops.get(id(d))
+            return 1.0 / float(drop.rate) if (drop is not None and getattr(self, "_trained_forward", False)) else 1.0
+        de = self.de
+        lib.nm_dense_wgrad_f32(self.last_f32.p, self.dlogits.p, de.weights.p, de.dweights.p, de.dbiases.p, self.ws_dw.p, self.ws_dw.nbytes,
+                               B, self.K, self.n_out, float(scale), float(de.weight_regularizer_l1), float(de.weight_regularizer_l2), s)
+        lib.nm_dense_dgrad_f32(self.dlogits.p, de.weights.p, self.dx_head.p, B, self.K, self.n_out, s)
+        # ReLU backward of the last hidden layer (and 1 / keep of a dropout behind it) while splitting into planes
+        lib.nm_tc_split3_f32(self.dx_head.p, self.acts[-1].p, mscale(self.hidden[-1]), self.dacts[-1].p, B * self.K, cap * self.K, s)
+        for i in range(len(self.hidden) - 1, -1, -1):
+            d = self.hidden[i]
+            n_in, n_out = d.weights.shape
+            x_in = self.acts[i - 1] if i > 0 else self.x0
+            _timed(f"tc_dense_gen_wgrad_x3[{n_in}->{n_out}]", lib.nm_tc_dense_wgrad_gen_x3, x_in.p, cap * n_in, self.dacts[i].p, cap * n_out,
+                   d.weights.p, d.dweights.p, d.dbiases.p, self.ws.p, self.ws.nbytes, B, n_in, n_out, float(scale),
+                   float(d.weight_regularizer_l1), float(d.weight_regularizer_l2), s)
+            if i > 0:
+                _timed(f"tc_dense_gen_dgrad_x3[{n_in}->{n_out}]", lib.nm_tc_dense_dgrad_gen_x3, self.dacts[i].p, cap * n_out,
+                       self.packed[id(d)][0].p, self.acts[i - 1].p, mscale(self.hidden[i - 1]), self.dacts[i - 1].p, cap * n_in,
+                       B, n_in, n_out, s)
+        if comm is not None:
+            comm.allreduce_async(self.model.arena.grads, 0, self.model.arena.total)
+
     def backward(self, grad_batch=None, comm=None, fork=False, dp=None):
         """``comm``: data-parallel communicator (NCCL path) -- the gradient slab is all-reduced after the last kernel.
         ``dp`` / ``fork`` are accepted for interface parity with the conv plans (the fused peer exchange pushes the whole
@@ -193,6 +297,8 @@ class TcMlpPlan:
         B = self.x.shape[0]
         s = stream()
         self.pushed_from = None
+        if self.split:
+            return self._backward_x3(grad_batch, comm)
         scale = 1.0 / (B if grad_batch is None else grad_batch)
         if not getattr(self, "dl_hilo_valid", False):      # dlogits were written by the public-API backward
             lib.nm_tc_pack_dlogits_bf16(self.dlogits.p, self.dl_hilo.p, B, self.n_out, s)
