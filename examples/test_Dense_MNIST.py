@@ -29,7 +29,8 @@ ap.add_argument("--as-written", action="store_true",
                 help="the reference script's stack verbatim (Dropout twice, softmax applied twice); FP32-exact mode only")
 ap.add_argument("--dropout", action="store_true", help="the reference script's stack with a single softmax (Dense+ReLU, Dropout, "
                 "Dense+ReLU, Dropout, Dense, Softmax): takes the tensor-core MLP plan in --mode bf16")
-ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16"], help="bf16 = tcgen05 MLP plan (neuromah_b200/tc_plan_mlp.py)")
+ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16", "bf16x3"],
+                help="bf16 = tcgen05 MLP plan (neuromah_b200/tc_plan_mlp.py); bf16x3 = the same plan FP32-exact on the tensor cores")
 args = ap.parse_args()
 rng = np.random.default_rng(1)
 labels = rng.integers(0, 10, args.n)
@@ -64,9 +65,9 @@ else:
     model.add(Activation_Softmax())
     model.set(loss=Loss_CategoricalCrossentropy, optimizer=Optimizer_Adam(learning_rate=0.001), accuracy=Accuracy_Categorical)
     batch = 128
-if args.as_written and args.mode == "bf16":
+if args.as_written and args.mode != "fp32":
     raise SystemExit("--as-written (softmax applied twice) runs in FP32-exact mode only; use --dropout --mode bf16")
-model.finalize(mode=None if args.mode == "fp32" else "bf16")
+model.finalize(mode=None if args.mode == "fp32" else args.mode)
 t0 = time.perf_counter_ns()
 model.train(X, y, epochs=args.epochs, batch_size=batch, validation_data=(X[:1024], y[:1024]))
 print(f"Total training time: {time.perf_counter_ns() - t0} ns")
