@@ -36,10 +36,11 @@ class Bf16Activation:
     """Host-convertible view of an internal bf16 NHWC (optionally haloed) activation: np.asarray(view)
     yields the reference's float32 NCHW tensor."""
 
-    def __init__(self, buf: DeviceArray, n, halo):
+    def __init__(self, buf: DeviceArray, n, halo, channels=None):
         self.buf, self.n, self.halo = buf, n, halo
         _, hp, wp, c = buf.shape
-        self.shape = (n, c, hp - 2 * halo, wp - 2 * halo)
+        self.channels = c if channels is None else channels       # the layer's own channels (the buffer may be zero-padded)
+        self.shape = (n, self.channels, hp - 2 * halo, wp - 2 * halo)
         self.dtype = np.dtype(np.float32)
         self.ndim = 4
 
@@ -50,7 +51,7 @@ class Bf16Activation:
         a = bf16_bits_to_f32(self.buf.numpy()[:self.n])
         if self.halo:
             a = a[:, self.halo:-self.halo, self.halo:-self.halo, :]
-        return np.ascontiguousarray(a.transpose(0, 3, 1, 2))
+        return np.ascontiguousarray(a[..., :self.channels].transpose(0, 3, 1, 2))
 
     def __array__(self, dtype=None, copy=None):
         a = self.numpy()

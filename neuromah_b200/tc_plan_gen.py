@@ -2,7 +2,9 @@
 
     ( Conv2D(3x3, same, ReLU) x k  ->  MaxPooling2D(2, 2) ) x m  ->  Flatten  ->  Dense(-> n <= 16)  ->  Softmax
 
-with every conv's out_channels a multiple of 64 (the first conv's in_channels are zero-padded to 64).
+The last conv's out_channels must be a multiple of 64 (the Dense head reads its pooled output unpadded); every other conv may
+have ANY width: its filters are zero-padded to the next multiple of 64 (the padded channels stay zero through ReLU, pool,
+dgrad and are never written to the parameter gradients), the first conv's in_channels to 32 or a multiple of 64.
 ``Model.finalize(mode="bf16")`` picks this plan when the net is not the MNIST pattern of tc_plan.py.
 
 Every contraction runs on tcgen05 tensor cores: the convs through the streamed-filter implicit GEMM of
@@ -33,8 +35,8 @@ def _rup_in(c):
 
 
 class TcStackPlan:
-    PATTERN = ("(Conv2D(3x3,same,ReLU, out_channels % 64 == 0) x k -> MaxPooling2D(2,2)) x m -> Flatten -> "
-               "Dense(-> n <= 16) -> Softmax")
+    PATTERN = ("(Conv2D(3x3,same,ReLU) x k -> MaxPooling2D(2,2)) x m -> Flatten -> Dense(-> n <= 16) -> Softmax "
+               "(out_channels of the last conv % 64 == 0)")
 
     # ------------------------------------------------------------------ pattern ----
     @staticmethod
@@ -50,7 +52,7 @@ class TcStackPlan:
         for layer in L[:-3]:
             if isinstance(layer, Layer_Conv2D):
                 oc, _, kh, kw = layer.weights.shape
-                if (kh, kw) != (3, 3) or layer.padding != "same" or type(layer.activation) is not Activation_ReLU or oc % 64:
+                if (kh, kw) != (3, 3) or layer.padding != "same" or type(layer.activation) is not Activation_ReLU:
                     return None
                 if tuple(np.atleast_1d(layer.stride)) not in ((1,), (1, 1)):
                     return None
@@ -62,7 +64,7 @@ class TcStackPlan:
                 convs = []
             else:
                 return None
-        if convs or not blocks:
+        if convs or not blocks or blocks[-1][0][-1].weights.shape[0] % 64:
             return None
         de = L[-2]
         if de.activation is not None or de.weights.shape[1] > 16:
@@ -95,9 +97,12 @@ class TcStackPlan:
         self.B = 0
         self.hw = None
         self.packed = {}
+        prev_ocp = None
         for c in self.convs:
             oc, ic = c.weights.shape[:2]
-            ocp, icp = _rup(oc), _rup_in(ic)
+            # a conv reads the PADDED channels of the tensor below it (zero weights for the padding)
+            ocp, icp = _rup(oc), (_rup_in(ic) if prev_ocp is None else prev_ocp)
+            prev_ocp = ocp
             self.packed[id(c)] = (DeviceArray((ocp, 9, icp), np.uint16), DeviceArray((icp, 9, ocp), np.uint16), ocp, icp)
         # side stream for the data-parallel early pushes (created here, never inside a CUDA-graph capture)
         from .device import new_event, new_stream
@@ -182,10 +187,10 @@ class TcStackPlan:
                 wf = self.packed[id(e["layer"])][0]
                 _timed(f"tc_conv_gen_fprop[{e['ic']}->{e['oc']}@{e['h']}]", lib.nm_tc_conv3x3_gen_bf16, e["inp"].p, wf.p, None, None, e["act"].p,
                        B, e["h"], e["w"], e["icp"], e["ocp"], 1, s)
-                e["layer"].output = Bf16Activation(e["act"], B, 1)
+                e["layer"].output = Bf16Activation(e["act"], B, 1, e["oc"])
             _timed('tc_maxpool_fwd', lib.nm_tc_maxpool2x2_fwd_bf16, st["convs"][-1]["act"].p, st["pooled"].p, st["idx"].p,
                    B, st["h"], st["w"], st["ch"], st["padded"], s)
-            st["pool"].output = Bf16Activation(st["pooled"], B, st["padded"])
+            st["pool"].output = Bf16Activation(st["pooled"], B, st["padded"], st["convs"][-1]["oc"])
         last = self.steps[-1]
         lab = labels if labels is not None else self.dummy_labels
         _timed('tc_dense_softmax_ce', lib.nm_tc_dense_softmax_ce_bf16, last["pooled"].p, self.w3hl.p, self.de.biases.p, lab.p,

@@ -39,9 +39,58 @@ def test_tc_stack_plan_is_selected_and_rejects_other_nets():
     model = build(spec, ref_net.init_params(spec, np.random.RandomState(1), init="he"), mode="bf16")
     assert isinstance(model.plan, TcStackPlan)
     bad = small_vgg_spec()
-    bad[0]["oc"] = bad[1]["ic"] = 48                  # out_channels not a multiple of 64
+    bad[4]["oc"] = 96                                 # the LAST conv feeds the Dense head unpadded: multiple of 64 required
+    bad[7]["n_in"] = 96 * 16
     with pytest.raises(ValueError):
         build(bad, ref_net.init_params(bad, np.random.RandomState(1), init="he"), mode="bf16")
+
+
+def narrow_spec(hw=16):
+    """C(3->24) C(24->40) P C(40->64) P Flatten Dense(->10) Softmax: widths that are NOT multiples of 64 below the last conv
+    (zero-padded to 64 channels inside the plan) -- the small-CNN shapes the round-1 review found rejected."""
+    return [{"kind": "conv", "ic": 3, "oc": 24, "k": 3, "padding": "same", "relu": True},
+            {"kind": "conv", "ic": 24, "oc": 40, "k": 3, "padding": "same", "relu": True},
+            {"kind": "pool", "size": 2, "stride": 2, "padding": "valid"},
+            {"kind": "conv", "ic": 40, "oc": 64, "k": 3, "padding": "same", "relu": True},
+            {"kind": "pool", "size": 2, "stride": 2, "padding": "valid"},
+            {"kind": "flatten"}, {"kind": "dense", "n_in": 64 * (hw // 4) ** 2, "n_out": 10, "relu": False}, {"kind": "softmax"}]
+
+
+def test_tc_stack_narrow_channels_are_zero_padded():
+    """Forward activations (reported with the layer's own channel count), per-tensor gradients and a graph-replayed run for
+    a stack whose conv widths are 24 / 40 / 64."""
+    from neuromah_b200.tc_plan_gen import TcStackPlan
+    spec = narrow_spec()
+    params = ref_net.init_params(spec, np.random.RandomState(13), init="he")
+    model = build(spec, params, mode="bf16", learning_rate=0.001)
+    assert isinstance(model.plan, TcStackPlan)
+    net = ref_net.RefNet(spec, params)
+    x, y = synth(14, 3 * 32, (3, 16, 16))
+    for s in range(3):
+        _resync_oracle(net, model)
+        xb, yb = x[s * 32:(s + 1) * 32], y[s * 32:(s + 1) * 32]
+        model._accum.fill_zero()
+        out = model.train_step(xb, yb)
+        r = net.step(xb, yb)
+        np.testing.assert_allclose(np.asarray(out), r["output"], rtol=1e-2, atol=2e-3)
+        for li in range(5):
+            a, ref = np.asarray(model.layers[li].output), net.outs[li]
+            assert a.shape == ref.shape, (li, a.shape, ref.shape)
+            assert np.abs(a - ref).max() <= 2e-2 * np.abs(ref).max(), li
+        g, gr = model.arena.host_grads(), net.flat("grads")
+        off, errs = 0, []
+        for (_, name, _, size, _) in model.arena.table:
+            errs.append(rel_l2(g[off:off + size], gr[off:off + size]))
+            off += size
+        print("step", s, " ".join(f"{e:.4f}" for e in errs))
+        assert max(errs) <= 6e-2 and errs[-1] <= 3e-2, errs
+    runs = []
+    for _ in range(2):
+        m = build(spec, params, mode="bf16")
+        m.train(x, y, epochs=3, batch_size=32, verbose=0)
+        assert len(m._graphs) >= 1
+        runs.append(m.arena.host_params().copy())
+    np.testing.assert_array_equal(runs[0], runs[1])
 
 
 def test_tc_stack_forward_activations_and_probs():
