@@ -339,6 +339,30 @@ int nm_tc_dense_wgrad_gen_x3(const void* x3, size_t x_plane, const void* dy3, si
                              void* workspace, size_t workspace_bytes, int B, int n_in, int n_out, float scale, float l1, float l2,
                              void* stream);
 
+/* ---- FP32-exact conv stacks on the tensor cores (mode "bf16x3"), nm_tc_conv_gen.cu / nm_tc_pool.cu -------------------
+ * The general conv kernels above on three bf16 planes per tensor (see the Dense "x3" block): same layouts per plane
+ * (zero-haloed NHWC, packed weights), planes `*_plane` elements apart (weights: OCp * 9 * Cp), six plane-pair passes per
+ * contraction into one TMEM accumulator, FP32 results split back into planes in the epilogue.
+ *   nm_tc_pack_conv_weights_gen_x3 / nm_tc_pack_input_nhwc_x3 / _u8_x3   planes of the packed weights / the haloed input
+ *                                      (uint8 pixels are DIVIDED by denom, the FP32 path's division)
+ *   nm_tc_conv3x3_gen_x3               fprop (+ bias + ReLU) or dgrad (+ ReLU mask = h plane of the activation below)
+ *   nm_tc_conv3x3_wgrad_gen_x3         dW, db (workspace: nm_tc_conv3x3_wgrad_gen_workspace)
+ *   nm_tc_maxpool2x2_fwd_x3            window maximum of the exact FP32 values (l + m) + h, first maximum wins; idx as in
+ *                                      nm_tc_maxpool2x2_fwd_bf16 (the backward is nm_tc_maxpool2x2_bwd_bf16 once per plane)
+ *   nm_tc_merge3_nhwc_to_nchw_f32      planes [3][N][HW][C] -> float32 [N][C * HW] in Flatten's order (input of the FP32 head)
+ *   nm_tc_split3_nchw_to_nhwc          float32 [N][C * HW] -> planes [3][N][HW][C] (the head's input gradient) */
+int nm_tc_pack_conv_weights_gen_x3(const float* w_oihw, void* w_fprop3, void* w_dgrad3, int OC, int C, int OCp, int Cp, void* stream);
+int nm_tc_pack_input_nhwc_x3(const float* x_nchw, void* x_pad3, size_t plane, int N, int C, int H, int W, int Cp, void* stream);
+int nm_tc_pack_input_nhwc_u8_x3(const uint8_t* x_nchw, float denom, void* x_pad3, size_t plane, int N, int C, int H, int W, int Cp, void* stream);
+int nm_tc_conv3x3_gen_x3(const void* x_pad3, size_t x_plane, const void* w_packed3, const float* bias, const void* relu_mask, void* y_pad3,
+                         size_t y_plane, int N, int H, int W, int Cin, int Cout, int relu, void* stream);
+int nm_tc_conv3x3_wgrad_gen_x3(const void* x_pad3, size_t x_plane, const void* dy_pad3, size_t dy_plane, float* dw, float* dbias,
+                               void* workspace, size_t workspace_bytes, int N, int H, int W, int C, int OC, int Cp, int OCp, void* stream);
+int nm_tc_maxpool2x2_fwd_x3(const void* x_pad3, size_t x_plane, void* y3, size_t y_plane, void* idx, int N, int H, int W, int C, int out_padded,
+                            void* stream);
+int nm_tc_merge3_nhwc_to_nchw_f32(const void* planes, size_t plane_stride, float* out, int N, int HW, int C, void* stream);
+int nm_tc_split3_nchw_to_nhwc(const float* x, void* planes, size_t plane_stride, int N, int HW, int C, void* stream);
+
 /* First conv of the net (C_in = 1, 3x3 'same', ReLU, no bias) + MaxPooling2D(2,2) on tcgen05: the 4x4 input patch of a
  * pool window is the K = 16 dimension and the weights are expanded to Wext[(window position, oc)][4x4] (zero outside the
  * 3x3 support), so one MMA yields all four conv values of a window per TMEM lane and the pool needs no cross-lane traffic.

@@ -123,4 +123,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// ---- FP32-exact mode on bf16 tensor cores ("bf16x3"): v = h + m + l with h = bf16(v), m = bf16(v - h), l = bf16(v - h - m) --
+// 24 mantissa bits; a product is the six plane pairs whose weight is above 2^-24, smallest first:
+// pass pr takes plane split_plane_a(pr) of the first operand and split_plane_b(pr) of the second: (l,h) (h,l) (m,m) (m,h) (h,m) (h,h)
+__host__ __device__ __forceinline__ int split_plane_a(int pr) { return (0x001102 >> (4 * pr)) & 0xF; }
+__host__ __device__ __forceinline__ int split_plane_b(int pr) { return (0x010120 >> (4 * pr)) & 0xF; }
+// h and m come back as bf16-representable floats, l as the FP32 remainder (exact; rounded when it is stored as bf16)
+__device__ __forceinline__ void split3(float v, float& h, float& m, float& l) {
+    h = __bfloat162float(__float2bfloat16(v));
+    const float r = v - h;
+    m = __bfloat162float(__float2bfloat16(r));
+    l = r - m;
+}
+
 }  // namespace tc

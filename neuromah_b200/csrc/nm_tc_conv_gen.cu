@@ -59,10 +59,17 @@ struct ConvGenParams {
 // switched off the kernel still took 9 x 300 cycles per tile and chunk).  A tap of an N = 64 tile is worth only 190-380
 // cycles of MMAs, so those layers take a whole filter ROW per slot (TG = 3); N = 128 tiles (510 cycles per tap, 16 KB per
 // slice) keep one tap per slot.
-template <int NT, int MSUB, int G_KC, int TG>
+// SPLIT ("bf16x3", FP32-exact): activations, weights and outputs are three bf16 planes each (one tensor map per plane); the
+// K loop runs six times over the chunks with the plane pair of the pass (nm_tc_common.cuh), all into the same accumulators,
+// and the epilogue splits the FP32 result back into planes (three staged bulk stores per 32-column chunk).
+template <bool SPLIT> struct MapSet { CUtensorMap m[SPLIT ? 3 : 1]; };
+
+template <int NT, int MSUB, int G_KC, int TG, bool SPLIT>
 __global__ void __launch_bounds__(384, 1)
-conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                   const __grid_constant__ CUtensorMap map_out, ConvGenParams p) {
+conv3x3_gen_kernel(const __grid_constant__ MapSet<SPLIT> maps_a, const __grid_constant__ MapSet<SPLIT> maps_b,
+                   const __grid_constant__ MapSet<SPLIT> maps_out, ConvGenParams p) {
+    constexpr int PASSES = SPLIT ? 6 : 1, NPL = SPLIT ? 3 : 1;
+    constexpr int O_WARP = NPL * 2048;                                        // epilogue staging per warp: 2 KB per plane
     constexpr int G_ROWB = G_KC * 2;
     constexpr uint64_t TMPL = desc_template(16, 8 * G_ROWB, G_KC == 64 ? LAYOUT_SW128 : LAYOUT_SW64);     // K-major, SBO = 8 rows
     constexpr uint32_t IDESC = idesc_bf16(G_M, NT, 0, 0);
@@ -81,7 +88,7 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     uint8_t* b_smem = smem + (size_t)p.a_stages * p.a_stage_bytes;
     // epilogue staging: 32 rows x 32 channels (2 KB, SWIZZLE_64B) per epilogue warp, drained by TMA stores
     uint8_t* o_smem = b_smem + (size_t)p.b_stages * B_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(o_smem + 8 * 2048);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(o_smem + 8 * O_WARP);
     uint64_t* afull = bars;
     uint64_t* aempty = afull + p.a_stages;
     uint64_t* bfull = aempty + p.a_stages;
@@ -92,7 +99,10 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_trigger();
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_out); }
+    if (warp == 0 && lane == 0) {
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl) { tma_prefetch_desc(&maps_a.m[pl]); tma_prefetch_desc(&maps_b.m[pl]); tma_prefetch_desc(&maps_out.m[pl]); }
+    }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.a_stages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < p.b_stages; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
@@ -113,17 +123,21 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * NT;
                 const int row0 = m_tile * TILE_ROWS - (p.Wp + 1);                      // negative / past-the-end rows read as zero
-                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                for (int kcv = 0; kcv < PASSES * p.k_chunks; ++kcv) {
+                    int pass = 0, kc = kcv;
+                    if constexpr (SPLIT) { pass = kcv / p.k_chunks; kc = kcv - pass * p.k_chunks; }
+                    const CUtensorMap* map_a = &maps_a.m[SPLIT ? split_plane_a(pass) : 0];
+                    const CUtensorMap* map_b = &maps_b.m[SPLIT ? split_plane_b(pass) : 0];
                     mbar_wait(&aempty[a_stage], a_phase ^ 1);
                     if (NM_DBG(19)) mbar_arrive(&afull[a_stage]);
                     else {
                     mbar_expect_tx(&afull[a_stage], (uint32_t)(p.a_boxes * p.a_box_rows) * G_ROWB);
                     for (int j = 0; j < p.a_boxes; ++j)
-                        tma_load_2d(a_smem + (size_t)a_stage * p.a_stage_bytes + (size_t)j * p.a_box_rows * G_ROWB, &map_a,
+                        tma_load_2d(a_smem + (size_t)a_stage * p.a_stage_bytes + (size_t)j * p.a_box_rows * G_ROWB, map_a,
                                     kc * G_KC, row0 + j * p.a_box_rows, &afull[a_stage]);
                     }
                     if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
-                    if (kc == 0) GEN_TRACE(p, tile / (int)gridDim.x, 0);
+                    if (kcv == 0) GEN_TRACE(p, tile / (int)gridDim.x, 0);
                     for (int grp = 0; grp < GROUPS; ++grp) {
                         mbar_wait(&bempty[b_stage], b_phase ^ 1);
                         if (NM_DBG(18)) mbar_arrive(&bfull[b_stage]);
@@ -131,7 +145,7 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         mbar_expect_tx(&bfull[b_stage], B_BYTES);
 #pragma unroll
                         for (int t = 0; t < TG; ++t)
-                            tma_load_2d(b_smem + (size_t)b_stage * B_BYTES + t * B_SLICE, &map_b, (grp * TG + t) * p.Cin + kc * G_KC, n0,
+                            tma_load_2d(b_smem + (size_t)b_stage * B_BYTES + t * B_SLICE, map_b, (grp * TG + t) * p.Cin + kc * G_KC, n0,
                                         &bfull[b_stage]);
                         }
                         if (++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
@@ -155,7 +169,7 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             constexpr uint32_t DESC_LO = (uint32_t)(TMPL & 0xFFFFFFFFull);
             auto mk = [](uint32_t lo) -> uint64_t { return ((uint64_t)DESC_HI << 32) | (uint64_t)(DESC_LO | (lo & 0x3FFFu)); };
             const int my_tiles = (int)blockIdx.x < p.num_tiles ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-            const int k_chunks = p.k_chunks, a_stages = p.a_stages, b_stages = p.b_stages;
+            const int k_chunks = PASSES * p.k_chunks, a_stages = p.a_stages, b_stages = p.b_stages;   // SPLIT: six passes, one accumulator
             const uint32_t a_stage16 = p.a_stage_bytes >> 4, a_base16 = smem_u32(a_smem) >> 4, b_base16 = smem_u32(b_smem) >> 4;
             uint32_t shift16[9];
 #pragma unroll
@@ -245,7 +259,7 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 // make every warp instruction touch 32 different 128-byte lines with half a sector each (ncu: 303 MB of
                 // L1->L2 write traffic for 151 MB of output).  The warp's 32 rows x 32 channels are staged in the swizzled
                 // layout and leave as one bulk store (UTMASTG) per 32-column chunk.
-                uint8_t* stage = o_smem + (size_t)(warp - 4) * 2048;
+                uint8_t* stage = o_smem + (size_t)(warp - 4) * O_WARP;
                 const int row_base = m_tile * TILE_ROWS + ms * G_M + q * 32;
                 const bool use_mask = p.mask != nullptr && interior;
                 const __nv_bfloat16* msk = p.mask + (size_t)row * p.Cout + n0;
@@ -296,16 +310,32 @@ conv3x3_gen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                                     }
                                 }
                             }
-                            uint4 o;
-                            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-                            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-                            *reinterpret_cast<uint4*>(stage + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;   // SWIZZLE_64B
+                            uint8_t* dst = stage + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4);                   // SWIZZLE_64B
+                            if constexpr (SPLIT) {
+                                float h[8], m[8], l[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) split3(f[j], h[j], m[j], l[j]);
+                                *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]),
+                                                                            pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+                                *reinterpret_cast<uint4*>(dst + 2048) = make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]),
+                                                                                   pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
+                                *reinterpret_cast<uint4*>(dst + 4096) = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]),
+                                                                                   pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+                            } else {
+                                uint4 o;
+                                o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+                                o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+                                *reinterpret_cast<uint4*>(dst) = o;
+                            }
                         }
                     }
                     tma_store_fence();                                // 32 channels staged: hand them to the TMA
                     __syncwarp();
-                    if (lane == 0 && row_base < p.rows_total && !NM_DBG(16))
-                        tma_store_2d(&map_out, stage, n0 + c0, row_base);         // rows past the tensor are clipped
+                    if (lane == 0 && row_base < p.rows_total && !NM_DBG(16)) {
+#pragma unroll
+                        for (int pl = 0; pl < NPL; ++pl)
+                            tma_store_2d(&maps_out.m[pl], stage + pl * 2048, n0 + c0, row_base);     // rows past the tensor are clipped
+                    }
                 }
             }
             fence_before_sync();
@@ -339,10 +369,13 @@ struct WgradGenParams {
     float* bias_partial;                 // optional [splits * c_chunks][OCp]: column sums of dY (the bias gradient)
 };
 
-template <int MOC>
+// SPLIT ("bf16x3"): dY and X are three bf16 planes each; the CTA walks its pixel blocks six times, once per plane pair, into
+// the same accumulators.  The dY plane of passes 0, 1, 2 is l, h, m: the bias-gradient MMAs run in exactly those passes.
+template <int MOC, bool SPLIT>
 __global__ void __launch_bounds__(256, 1)
-conv3x3_wgrad_gen_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, WgradGenParams p) {
+conv3x3_wgrad_gen_kernel(const __grid_constant__ MapSet<SPLIT> maps_dy, const __grid_constant__ MapSet<SPLIT> maps_x, WgradGenParams p) {
     static_assert(MOC == 64 || MOC == 128, "M = 64 or 128 output channels per CTA");
+    constexpr int PASSES = SPLIT ? 6 : 1, NPL = SPLIT ? 3 : 1;
     constexpr int CB = 32;                                              // input channels per CTA: 64-byte rows, SWIZZLE_64B
     constexpr int A_BOX = G_M * 128;                                    // one [128 pixels][64 oc] box, 16 KB
     constexpr int A_BYTES = (MOC / 64) * A_BOX;
@@ -380,7 +413,10 @@ conv3x3_wgrad_gen_kernel(const __grid_constant__ CUtensorMap map_dy, const __gri
             reinterpret_cast<uint4*>(ones)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_dy); tma_prefetch_desc(&map_x); }
+    if (warp == 0 && lane == 0) {
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl) { tma_prefetch_desc(&maps_dy.m[pl]); tma_prefetch_desc(&maps_x.m[pl]); }
+    }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(done, 1);
@@ -396,33 +432,39 @@ conv3x3_wgrad_gen_kernel(const __grid_constant__ CUtensorMap map_dy, const __gri
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int kb = split; kb < p.num_kblocks; kb += p.splits) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                uint8_t* st = smem + (size_t)stage * stage_bytes;
-                mbar_expect_tx(&full[stage], A_BYTES + (uint32_t)p.x_rows * CB * 2);
+            for (int pass = 0; pass < PASSES; ++pass) {
+                const CUtensorMap* map_dy = &maps_dy.m[SPLIT ? split_plane_a(pass) : 0];
+                const CUtensorMap* map_x = &maps_x.m[SPLIT ? split_plane_b(pass) : 0];
+                for (int kb = split; kb < p.num_kblocks; kb += p.splits) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* st = smem + (size_t)stage * stage_bytes;
+                    mbar_expect_tx(&full[stage], A_BYTES + (uint32_t)p.x_rows * CB * 2);
 #pragma unroll
-                for (int j = 0; j < MOC / 64; ++j) tma_load_2d(st + j * A_BOX, &map_dy, oc0 + j * 64, kb * G_M, &full[stage]);
-                tma_load_2d(st + A_BYTES, &map_x, c0, kb * G_M - (p.Wp + 1), &full[stage]);      // OOB rows read as 0
-                if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                    for (int j = 0; j < MOC / 64; ++j) tma_load_2d(st + j * A_BOX, map_dy, oc0 + j * 64, kb * G_M, &full[stage]);
+                    tma_load_2d(st + A_BYTES, map_x, c0, kb * G_M - (p.Wp + 1), &full[stage]);      // OOB rows read as 0
+                    if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
         // One elected lane issues everything.  UTCHMMA issue is back-pressured by the tensor pipe, so the wait for the NEXT
         // k-block's data is done before the last MMAs of the current one are issued: it hides under queued MMAs.
         if (elect_one()) {
-            int it = 0;
-            if (split < p.num_kblocks) mbar_wait(&full[0], 0);
-            for (int kb = split; kb < p.num_kblocks; kb += p.splits, ++it) {
+            const int its_pass = split < p.num_kblocks ? (p.num_kblocks - 1 - split) / p.splits + 1 : 0;    // blocks per pass
+            const int total = PASSES * its_pass;
+            if (total > 0) mbar_wait(&full[0], 0);
+            for (int it = 0; it < total; ++it) {
                 const int stage = it % p.n_stages;
+                const int pass = SPLIT ? it / its_pass : 0, bi = SPLIT ? it - pass * its_pass : it;
                 fence_after_sync();
                 const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint64_t a_desc0 = desc_at(TMPL_A, st);
                 const uint64_t x_desc0 = desc_at(TMPL_B3, st + A_BYTES);
                 const uint64_t ones_desc0 = desc_at(TMPL_B3, smem_u32(ones));
-                const bool bias_here = want_bias && (it % p.c_chunks) == cq;
+                const bool bias_here = want_bias && (bi % p.c_chunks) == cq && pass < 3;
 #pragma unroll
                 for (int ks = 0; ks < G_M / 16; ++ks) {
-                    if (ks == G_M / 16 - 1 && kb + p.splits < p.num_kblocks) {
+                    if (ks == G_M / 16 - 1 && it + 1 < total) {
                         const int nit = it + 1;
                         mbar_wait(&full[nit % p.n_stages], (nit / p.n_stages) & 1);
                     }
@@ -583,7 +625,69 @@ __global__ void pack_input_nhwc_kernel(const XT* __restrict__ x, float x_scale, 
     }
 }
 
+// the same two packs as three bf16 planes h, m, l (FP32-exact mode); weight planes are OCp * 9 * Cp elements apart
+__global__ void pack_conv_weights_gen_x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                                __nv_bfloat16* __restrict__ wd, int OC, int C, int OCp, int Cp) {
+    pdl_trigger();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= OCp * Cp * 9) return;
+    const int oc = i / (Cp * 9), rem = i - oc * Cp * 9, c = rem / 9, tap = rem - c * 9;
+    float v[3];
+    split3((oc < OC && c < C) ? w[((size_t)oc * C + c) * 9 + tap] : 0.f, v[0], v[1], v[2]);
+    const size_t plane = (size_t)OCp * 9 * Cp;
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+        const __nv_bfloat16 b = __float2bfloat16(v[pl]);
+        if (wf) wf[pl * plane + ((size_t)oc * 9 + tap) * Cp + c] = b;
+        if (wd) wd[pl * plane + ((size_t)c * 9 + (8 - tap)) * OCp + oc] = b;
+    }
+}
+
+// raw uint8 pixels are DIVIDED by denom here (the IEEE division of the FP32 path, nm_u8_to_f32_div)
+__device__ __forceinline__ float in_val_div(const float* p, float) { return __ldg(p); }
+__device__ __forceinline__ float in_val_div(const uint8_t* p, float denom) { return (float)__ldg(p) / denom; }
+
+template <typename XT>
+__global__ void pack_input_nhwc_x3_kernel(const XT* __restrict__ x, float denom, __nv_bfloat16* __restrict__ xp, size_t plane,
+                                          int N, int C, int H, int W, int Cp) {
+    pdl_trigger();
+    pdl_wait();
+    const int groups = Cp / 8, Hp = H + 2, Wp = W + 2;
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (long long)N * Hp * Wp) return;
+    const int ww = (int)(pix % Wp);
+    const int hh = (int)((pix / Wp) % Hp);
+    const int n = (int)(pix / ((long long)Wp * Hp));
+    const bool interior = hh >= 1 && hh <= H && ww >= 1 && ww <= W;
+    const XT* src = x + ((size_t)n * C * H + (hh - 1)) * W + (ww - 1);
+    for (int g = 0; g < groups; ++g) {
+        float h[8], m[8], l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = g * 8 + j;
+            split3((interior && c < C) ? in_val_div(src + (size_t)c * H * W, denom) : 0.f, h[j], m[j], l[j]);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(xp) + pix * groups + g;
+        dst[0] = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+        dst[plane / 8] = make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
+        dst[2 * (plane / 8)] = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+    }
+}
+
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// tensor maps of the planes of a bf16 [rows][inner] matrix (`plane` elements apart)
+template <bool SPLIT>
+int make_mapset(MapSet<SPLIT>* m, const void* base, size_t plane, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows,
+                CUtensorMapSwizzle swz) {
+    for (int pl = 0; pl < (SPLIT ? 3 : 1); ++pl) {
+        const int rc = make_map_2d(&m->m[pl], static_cast<const __nv_bfloat16*>(base) + (size_t)pl * plane, inner, rows, inner * 2,
+                                   box_inner, box_rows, swz);
+        if (rc) return rc;
+    }
+    return NM_OK;
+}
 
 constexpr int G_SMEM_BUDGET = 212 * 1024;
 
@@ -596,22 +700,21 @@ void conv_gen_tile(ConvGenParams& p, int msub, int kc) {
     p.a_stage_bytes = (uint32_t)round_up(p.a_boxes * p.a_box_rows * kc * 2, 1024);      // swizzled tiles start on 1024-byte boundaries
 }
 
-template <int NT, int MSUB, int G_KC>
-int launch_conv_gen(const void* x_pad, const void* w_packed, ConvGenParams p, cudaStream_t st) {
+template <int NT, int MSUB, int G_KC, bool SPLIT>
+int launch_conv_gen(const void* x_pad, size_t x_plane, const void* w_packed, size_t y_plane, ConvGenParams p, cudaStream_t st) {
     constexpr int G_ROWB = G_KC * 2;
     constexpr CUtensorMapSwizzle SWZ = G_KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     NM_REQUIRE(p.a_box_rows <= 256, "image too wide");
-    CUtensorMap ma, mb;
-    int rc = make_map_2d(&ma, x_pad, (uint64_t)p.Cin, (uint64_t)p.rows_total, (uint64_t)p.Cin * 2, G_KC, (uint32_t)p.a_box_rows, SWZ);
+    MapSet<SPLIT> ma, mb, mo;
+    int rc = make_mapset<SPLIT>(&ma, x_pad, x_plane, (uint64_t)p.Cin, (uint64_t)p.rows_total, G_KC, (uint32_t)p.a_box_rows, SWZ);
     if (rc) return rc;
-    rc = make_map_2d(&mb, w_packed, (uint64_t)9 * p.Cin, (uint64_t)p.Cout, (uint64_t)9 * p.Cin * 2, G_KC, NT, SWZ);
+    rc = make_mapset<SPLIT>(&mb, w_packed, (size_t)p.Cout * 9 * p.Cin, (uint64_t)9 * p.Cin, (uint64_t)p.Cout, G_KC, NT, SWZ);
     if (rc) return rc;
-    CUtensorMap mo;
-    rc = make_map_2d(&mo, p.out, (uint64_t)p.Cout, (uint64_t)p.rows_total, (uint64_t)p.Cout * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    rc = make_mapset<SPLIT>(&mo, p.out, y_plane, (uint64_t)p.Cout, (uint64_t)p.rows_total, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
     constexpr int TG = NT == 64 ? 3 : 1;                        // taps per weight-ring slot (see the kernel)
     constexpr int B_BYTES = TG * NT * G_ROWB;
-    constexpr int O_BYTES = 8 * 2048;                           // epilogue staging, 2 KB per epilogue warp
+    constexpr int O_BYTES = 8 * (SPLIT ? 3 : 1) * 2048;         // epilogue staging, 2 KB per epilogue warp and plane
     p.a_stages = 2;
     {
         const int budget = G_SMEM_BUDGET - O_BYTES - p.a_stages * (int)p.a_stage_bytes;
@@ -624,14 +727,14 @@ int launch_conv_gen(const void* x_pad, const void* w_packed, ConvGenParams p, cu
     NM_REQUIRE(p.a_stages >= 2 && p.b_stages >= 2, "image too wide for the shared-memory budget");
     NM_REQUIRE(2 * (p.a_stages + p.b_stages) + 4 <= 62, "too many pipeline stages for the barrier block");
     const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * B_BYTES + O_BYTES + 512;   // + mbarriers
-    auto kern = conv3x3_gen_kernel<NT, MSUB, G_KC, TG>;
+    auto kern = conv3x3_gen_kernel<NT, MSUB, G_KC, TG, SPLIT>;
     static bool attr_set = false;
     if (!attr_set) {
         NM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
     }
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    return nm::launch_pdl("conv3x3_gen", kern, dim3(grid), dim3(384), smem, st, ma, mb, mo, p);
+    return nm::launch_pdl(SPLIT ? "conv3x3_gen_x3" : "conv3x3_gen", kern, dim3(grid), dim3(384), smem, st, ma, mb, mo, p);
 }
 
 struct WgradGenPlan { int moc, c_chunks, items, splits, num_kblocks, rows_total; };
@@ -649,6 +752,102 @@ WgradGenPlan wgrad_gen_plan(int N, int H, int W, int C, int OCp) {
     if (s > g.num_kblocks) s = g.num_kblocks;
     g.splits = s;
     return g;
+}
+
+size_t wgrad_gen_workspace(int N, int H, int W, int C, int Cp, int OCp) {
+    if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cp < C || OCp <= 0 || (Cp % 64 && Cp != 32) || OCp % 64) return 0;
+    const WgradGenPlan g = wgrad_gen_plan(N, H, W, C, OCp);
+    return (size_t)g.splits * OCp * 9 * Cp * sizeof(float) + (size_t)DB_BLOCKS * OCp * sizeof(float);
+}
+
+template <bool SPLIT>
+int conv_gen(const void* x_pad, size_t x_plane, const void* w_packed, const float* bias, const void* relu_mask, void* y_pad, size_t y_plane,
+             int N, int H, int W, int Cin, int Cout, int relu, cudaStream_t st) {
+    NM_REQUIRE(x_pad && w_packed && y_pad, "null pointer");
+    NM_REQUIRE(N > 0 && H > 0 && W > 0, "bad dimensions");
+    NM_REQUIRE(Cin > 0 && Cout > 0 && (Cin % 64 == 0 || Cin == 32) && Cout % 64 == 0,
+               "channel counts must be multiples of 64 (pad with zero channels); Cin = 32 is accepted for a padded first layer");
+    ConvGenParams p{};
+    p.Hp = H + 2; p.Wp = W + 2; p.H = H; p.W = W;
+    NM_REQUIRE((long long)N * p.Hp * p.Wp < (1ll << 31) - 1024, "batch too large for 32-bit row coordinates");
+    p.rows_total = N * p.Hp * p.Wp;
+    p.Cin = Cin; p.Cout = Cout;
+    const int kc = Cin == 32 ? 32 : 64;
+    p.k_chunks = Cin / kc;
+    const int nt = Cout % 128 == 0 ? 128 : 64;
+    p.n_tiles = Cout / nt;
+    p.out = static_cast<__nv_bfloat16*>(y_pad);
+    p.mask = static_cast<const __nv_bfloat16*>(relu_mask);
+    p.bias = bias;
+    p.relu = relu;
+#ifdef NM_ABLATE
+    p.trace = g_gen_trace;
+#endif
+    conv_gen_tile(p, 2, kc);
+    if (kc == 32)
+        return nt == 128 ? launch_conv_gen<128, 2, 32, SPLIT>(x_pad, x_plane, w_packed, y_plane, p, st)
+                         : launch_conv_gen<64, 2, 32, SPLIT>(x_pad, x_plane, w_packed, y_plane, p, st);
+    return nt == 128 ? launch_conv_gen<128, 2, 64, SPLIT>(x_pad, x_plane, w_packed, y_plane, p, st)
+                     : launch_conv_gen<64, 2, 64, SPLIT>(x_pad, x_plane, w_packed, y_plane, p, st);
+}
+
+template <int MOC, bool SPLIT>
+int launch_wgrad_gen(const MapSet<SPLIT>& mdy, const MapSet<SPLIT>& mx, const WgradGenParams& p, int items, size_t smem, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        NM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_gen_kernel<MOC, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set = true;
+    }
+    return nm::launch_pdl(SPLIT ? "conv3x3_wgrad_gen_x3" : "conv3x3_wgrad_gen", conv3x3_wgrad_gen_kernel<MOC, SPLIT>, dim3(items, p.splits),
+                          dim3(256), smem, st, mdy, mx, p);
+}
+
+template <bool SPLIT>
+int conv_wgrad_gen(const void* x_pad, size_t x_plane, const void* dy_pad, size_t dy_plane, float* dw, float* dbias, void* workspace,
+                   size_t workspace_bytes, int N, int H, int W, int C, int OC, int Cp, int OCp, cudaStream_t st) {
+    NM_REQUIRE(x_pad && dy_pad && dw && workspace, "null pointer");
+    NM_REQUIRE(N > 0 && H > 0 && W > 0, "bad dimensions");
+    NM_REQUIRE(C > 0 && OC > 0 && Cp >= C && OCp >= OC && (Cp % 64 == 0 || Cp == 32) && OCp % 64 == 0,
+               "padded channel counts must be multiples of 64 (input channels: or 32)");
+    NM_REQUIRE((long long)N * (H + 2) * (W + 2) < (1ll << 31) - 1024, "batch too large for 32-bit row coordinates");
+    const WgradGenPlan g = wgrad_gen_plan(N, H, W, C, OCp);
+    NM_REQUIRE(workspace_bytes >= wgrad_gen_workspace(N, H, W, C, Cp, OCp), "workspace too small");
+    WgradGenParams p{};
+    p.Wp = W + 2;
+    NM_REQUIRE(p.Wp <= 60, "image too wide for one TMA box");
+    p.rows_total = g.rows_total;
+    p.num_kblocks = g.num_kblocks;
+    p.x_rows = G_M + 2 * p.Wp + 2;
+    p.x_stage_bytes = ((uint32_t)p.x_rows * 64 + 1023u) & ~1023u;
+    const int a_bytes = (g.moc / 64) * G_M * 128;
+    {
+        const int fit = (int)((212 * 1024 - G_M * 64) / (a_bytes + p.x_stage_bytes));
+        p.n_stages = fit > 8 ? 8 : fit;
+    }
+    p.splits = g.splits;
+    p.c_chunks = g.c_chunks;
+    p.OCp = OCp; p.Cp = Cp;
+    p.partial = static_cast<float*>(workspace);
+    p.bias_partial = dbias ? p.partial + (size_t)g.splits * OCp * 9 * Cp : nullptr;
+    NM_REQUIRE(g.splits * g.c_chunks <= DB_BLOCKS, "bias-gradient partials exceed the workspace");
+    MapSet<SPLIT> mdy, mx;
+    int rc = make_mapset<SPLIT>(&mdy, dy_pad, dy_plane, (uint64_t)OCp, (uint64_t)p.rows_total, 64, G_M, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_mapset<SPLIT>(&mx, x_pad, x_plane, (uint64_t)Cp, (uint64_t)p.rows_total, 32, (uint32_t)p.x_rows, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    const size_t smem = (size_t)p.n_stages * (a_bytes + p.x_stage_bytes) + G_M * 64 + 256;
+    rc = g.moc == 128 ? launch_wgrad_gen<128, SPLIT>(mdy, mx, p, g.items, smem, st) : launch_wgrad_gen<64, SPLIT>(mdy, mx, p, g.items, smem, st);
+    if (rc) return rc;
+    if (C % 4 == 0)
+        rc = nm::launch_pdl("wgrad_gen_reduce", wgrad_gen_reduce_kernel<4, 8>, dim3(nm_cdiv((size_t)OC * (C / 4) * 9, 64)), dim3(64 * 8), 0,
+                            st, (const float*)p.partial, dw, p.splits, OC, C, OCp, Cp);
+    else
+        rc = nm::launch_pdl("wgrad_gen_reduce", wgrad_gen_reduce_kernel<1, 16>, dim3(nm_cdiv((size_t)OC * C * 9, 64)), dim3(64 * 16), 0,
+                            st, (const float*)p.partial, dw, p.splits, OC, C, OCp, Cp);
+    if (rc || !dbias) return rc;
+    // column sums of dY were formed inside the wgrad kernel (one partial per CTA): fixed-order final sum
+    return nm::launch_pdl("dbias_final", dbias_final_kernel, dim3(nm_cdiv((size_t)OC * 32, 256)), dim3(256), 0, st,
+                          (const float*)p.bias_partial, dbias, g.splits * g.c_chunks, OC, OCp);
 }
 
 }  // namespace
@@ -681,92 +880,58 @@ int nm_tc_pack_input_nhwc_u8_bf16(const uint8_t* x_nchw, float scale, void* x_pa
 
 int nm_tc_conv3x3_gen_bf16(const void* x_pad, const void* w_packed, const float* bias, const void* relu_mask, void* y_pad,
                            int N, int H, int W, int Cin, int Cout, int relu, void* stream) {
-    NM_REQUIRE(x_pad && w_packed && y_pad, "null pointer");
-    NM_REQUIRE(N > 0 && H > 0 && W > 0, "bad dimensions");
-    NM_REQUIRE(Cin > 0 && Cout > 0 && (Cin % 64 == 0 || Cin == 32) && Cout % 64 == 0,
-               "channel counts must be multiples of 64 (pad with zero channels); Cin = 32 is accepted for a padded first layer");
-    ConvGenParams p{};
-    p.Hp = H + 2; p.Wp = W + 2; p.H = H; p.W = W;
-    NM_REQUIRE((long long)N * p.Hp * p.Wp < (1ll << 31) - 1024, "batch too large for 32-bit row coordinates");
-    p.rows_total = N * p.Hp * p.Wp;
-    p.Cin = Cin; p.Cout = Cout;
-    const int kc = Cin == 32 ? 32 : 64;
-    p.k_chunks = Cin / kc;
-    const int nt = Cout % 128 == 0 ? 128 : 64;
-    p.n_tiles = Cout / nt;
-    p.out = static_cast<__nv_bfloat16*>(y_pad);
-    p.mask = static_cast<const __nv_bfloat16*>(relu_mask);
-    p.bias = bias;
-    p.relu = relu;
-#ifdef NM_ABLATE
-    p.trace = g_gen_trace;
-#endif
-    conv_gen_tile(p, 2, kc);
-    if (kc == 32)
-        return nt == 128 ? launch_conv_gen<128, 2, 32>(x_pad, w_packed, p, nm::S(stream)) : launch_conv_gen<64, 2, 32>(x_pad, w_packed, p, nm::S(stream));
-    return nt == 128 ? launch_conv_gen<128, 2, 64>(x_pad, w_packed, p, nm::S(stream)) : launch_conv_gen<64, 2, 64>(x_pad, w_packed, p, nm::S(stream));
+    return conv_gen<false>(x_pad, 0, w_packed, bias, relu_mask, y_pad, 0, N, H, W, Cin, Cout, relu, nm::S(stream));
+}
+// FP32-exact variant: x_pad3 / y_pad3 are three bf16 planes x_plane / y_plane elements apart, w_packed3 the three planes of
+// nm_tc_pack_conv_weights_gen_x3; relu_mask = the h plane of the activation below
+int nm_tc_conv3x3_gen_x3(const void* x_pad3, size_t x_plane, const void* w_packed3, const float* bias, const void* relu_mask, void* y_pad3,
+                         size_t y_plane, int N, int H, int W, int Cin, int Cout, int relu, void* stream) {
+    NM_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "bad dimensions");
+    NM_REQUIRE(x_plane >= (size_t)N * (H + 2) * (W + 2) * Cin && y_plane >= (size_t)N * (H + 2) * (W + 2) * Cout && x_plane % 8 == 0 &&
+               y_plane % 8 == 0, "plane strides must cover a haloed NHWC plane and be multiples of 8 elements");
+    return conv_gen<true>(x_pad3, x_plane, w_packed3, bias, relu_mask, y_pad3, y_plane, N, H, W, Cin, Cout, relu, nm::S(stream));
 }
 
-size_t nm_tc_conv3x3_wgrad_gen_workspace(int N, int H, int W, int C, int Cp, int OCp) {
-    if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cp < C || OCp <= 0 || (Cp % 64 && Cp != 32) || OCp % 64) return 0;
-    const WgradGenPlan g = wgrad_gen_plan(N, H, W, C, OCp);
-    return (size_t)g.splits * OCp * 9 * Cp * sizeof(float) + (size_t)DB_BLOCKS * OCp * sizeof(float);
-}
+size_t nm_tc_conv3x3_wgrad_gen_workspace(int N, int H, int W, int C, int Cp, int OCp) { return wgrad_gen_workspace(N, H, W, C, Cp, OCp); }
 
 int nm_tc_conv3x3_wgrad_gen_bf16(const void* x_pad, const void* dy_pad, float* dw, float* dbias, void* workspace, size_t workspace_bytes,
                                  int N, int H, int W, int C, int OC, int Cp, int OCp, void* stream) {
-    NM_REQUIRE(x_pad && dy_pad && dw && workspace, "null pointer");
-    NM_REQUIRE(N > 0 && H > 0 && W > 0, "bad dimensions");
-    NM_REQUIRE(C > 0 && OC > 0 && Cp >= C && OCp >= OC && (Cp % 64 == 0 || Cp == 32) && OCp % 64 == 0,
+    return conv_wgrad_gen<false>(x_pad, 0, dy_pad, 0, dw, dbias, workspace, workspace_bytes, N, H, W, C, OC, Cp, OCp, nm::S(stream));
+}
+// FP32-exact variant on planes (same workspace size)
+int nm_tc_conv3x3_wgrad_gen_x3(const void* x_pad3, size_t x_plane, const void* dy_pad3, size_t dy_plane, float* dw, float* dbias,
+                               void* workspace, size_t workspace_bytes, int N, int H, int W, int C, int OC, int Cp, int OCp, void* stream) {
+    NM_REQUIRE(N > 0 && H > 0 && W > 0 && Cp > 0 && OCp > 0, "bad dimensions");
+    NM_REQUIRE(x_plane >= (size_t)N * (H + 2) * (W + 2) * Cp && dy_plane >= (size_t)N * (H + 2) * (W + 2) * OCp && x_plane % 8 == 0 &&
+               dy_plane % 8 == 0, "plane strides must cover a haloed NHWC plane and be multiples of 8 elements");
+    return conv_wgrad_gen<true>(x_pad3, x_plane, dy_pad3, dy_plane, dw, dbias, workspace, workspace_bytes, N, H, W, C, OC, Cp, OCp,
+                                nm::S(stream));
+}
+
+int nm_tc_pack_conv_weights_gen_x3(const float* w_oihw, void* w_fprop3, void* w_dgrad3, int OC, int C, int OCp, int Cp, void* stream) {
+    NM_REQUIRE(w_oihw && (w_fprop3 || w_dgrad3), "null pointer");
+    NM_REQUIRE(OC > 0 && C > 0 && OCp >= OC && Cp >= C && OCp % 64 == 0 && (Cp % 64 == 0 || Cp == 32),
                "padded channel counts must be multiples of 64 (input channels: or 32)");
-    NM_REQUIRE((long long)N * (H + 2) * (W + 2) < (1ll << 31) - 1024, "batch too large for 32-bit row coordinates");
-    const WgradGenPlan g = wgrad_gen_plan(N, H, W, C, OCp);
-    NM_REQUIRE(workspace_bytes >= nm_tc_conv3x3_wgrad_gen_workspace(N, H, W, C, Cp, OCp), "workspace too small");
-    WgradGenParams p{};
-    p.Wp = W + 2;
-    NM_REQUIRE(p.Wp <= 60, "image too wide for one TMA box");
-    p.rows_total = g.rows_total;
-    p.num_kblocks = g.num_kblocks;
-    p.x_rows = G_M + 2 * p.Wp + 2;
-    p.x_stage_bytes = ((uint32_t)p.x_rows * 64 + 1023u) & ~1023u;
-    const int a_bytes = (g.moc / 64) * G_M * 128;
-    {
-        const int fit = (int)((212 * 1024 - G_M * 64) / (a_bytes + p.x_stage_bytes));
-        p.n_stages = fit > 8 ? 8 : fit;
-    }
-    p.splits = g.splits;
-    p.c_chunks = g.c_chunks;
-    p.OCp = OCp; p.Cp = Cp;
-    p.partial = static_cast<float*>(workspace);
-    p.bias_partial = dbias ? p.partial + (size_t)g.splits * OCp * 9 * Cp : nullptr;
-    NM_REQUIRE(g.splits * g.c_chunks <= DB_BLOCKS, "bias-gradient partials exceed the workspace");
-    const int items = g.items;
-    CUtensorMap mdy, mx;
-    int rc = make_map_2d(&mdy, dy_pad, (uint64_t)OCp, (uint64_t)p.rows_total, (uint64_t)OCp * 2, 64, G_M, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
-    rc = make_map_2d(&mx, x_pad, (uint64_t)Cp, (uint64_t)p.rows_total, (uint64_t)Cp * 2, 32, (uint32_t)p.x_rows, CU_TENSOR_MAP_SWIZZLE_64B);
-    if (rc) return rc;
-    const size_t smem = (size_t)p.n_stages * (a_bytes + p.x_stage_bytes) + G_M * 64 + 256;
-    static bool attr_set = false;
-    if (!attr_set) {
-        NM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_gen_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        NM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_gen_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
-    }
-    rc = g.moc == 128
-             ? nm::launch_pdl("conv3x3_wgrad_gen", conv3x3_wgrad_gen_kernel<128>, dim3(items, p.splits), dim3(256), smem, nm::S(stream), mdy, mx, p)
-             : nm::launch_pdl("conv3x3_wgrad_gen", conv3x3_wgrad_gen_kernel<64>, dim3(items, p.splits), dim3(256), smem, nm::S(stream), mdy, mx, p);
-    if (rc) return rc;
-    if (C % 4 == 0)
-        rc = nm::launch_pdl("wgrad_gen_reduce", wgrad_gen_reduce_kernel<4, 8>, dim3(nm_cdiv((size_t)OC * (C / 4) * 9, 64)), dim3(64 * 8), 0,
-                            nm::S(stream), (const float*)p.partial, dw, p.splits, OC, C, OCp, Cp);
-    else
-        rc = nm::launch_pdl("wgrad_gen_reduce", wgrad_gen_reduce_kernel<1, 16>, dim3(nm_cdiv((size_t)OC * C * 9, 64)), dim3(64 * 16), 0,
-                            nm::S(stream), (const float*)p.partial, dw, p.splits, OC, C, OCp, Cp);
-    if (rc || !dbias) return rc;
-    // column sums of dY were formed inside the wgrad kernel (one partial per CTA): fixed-order final sum
-    return nm::launch_pdl("dbias_final", dbias_final_kernel, dim3(nm_cdiv((size_t)OC * 32, 256)), dim3(256), 0, nm::S(stream),
-                          (const float*)p.bias_partial, dbias, g.splits * g.c_chunks, OC, OCp);
+    const int total = OCp * Cp * 9;
+    return nm::launch_pdl("pack_conv_weights_gen_x3", pack_conv_weights_gen_x3_kernel, dim3(nm_cdiv(total, 256)), dim3(256), 0, nm::S(stream),
+                          w_oihw, static_cast<__nv_bfloat16*>(w_fprop3), static_cast<__nv_bfloat16*>(w_dgrad3), OC, C, OCp, Cp);
+}
+
+int nm_tc_pack_input_nhwc_x3(const float* x_nchw, void* x_pad3, size_t plane, int N, int C, int H, int W, int Cp, void* stream) {
+    NM_REQUIRE(x_nchw && x_pad3, "null pointer");
+    NM_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && Cp >= C && Cp % 8 == 0, "bad dimensions");
+    const long long total = (long long)N * (H + 2) * (W + 2);
+    NM_REQUIRE(plane >= (size_t)total * Cp && plane % 8 == 0, "plane stride must cover a haloed NHWC plane and be a multiple of 8 elements");
+    return nm::launch_pdl("pack_input_nhwc_x3", pack_input_nhwc_x3_kernel<float>, dim3(nm_cdiv((size_t)total, 128)), dim3(128), 0, nm::S(stream),
+                          x_nchw, 1.f, static_cast<__nv_bfloat16*>(x_pad3), plane, N, C, H, W, Cp);
+}
+int nm_tc_pack_input_nhwc_u8_x3(const uint8_t* x_nchw, float denom, void* x_pad3, size_t plane, int N, int C, int H, int W, int Cp, void* stream) {
+    NM_REQUIRE(x_nchw && x_pad3, "null pointer");
+    NM_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && Cp >= C && Cp % 8 == 0 && denom != 0.f, "bad dimensions");
+    const long long total = (long long)N * (H + 2) * (W + 2);
+    NM_REQUIRE(plane >= (size_t)total * Cp && plane % 8 == 0, "plane stride must cover a haloed NHWC plane and be a multiple of 8 elements");
+    return nm::launch_pdl("pack_input_nhwc_u8_x3", pack_input_nhwc_x3_kernel<uint8_t>, dim3(nm_cdiv((size_t)total, 128)), dim3(128), 0, nm::S(stream),
+                          x_nchw, denom, static_cast<__nv_bfloat16*>(x_pad3), plane, N, C, H, W, Cp);
 }
 
 }  // extern "C"

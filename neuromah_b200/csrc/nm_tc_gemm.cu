@@ -50,17 +50,6 @@ struct GemmParams {
 };                                       //   a CUDA-graph replay of the step draws a fresh mask)
 
 struct Maps3 { CUtensorMap m[3]; };      // one tensor map per plane (bf16 mode: only [0])
-// plane of the A / B operand in pass pr of the split product: (l,h) (h,l) (m,m) (m,h) (h,m) (h,h)
-__device__ __forceinline__ int split_plane_a(int pr) { return (0x001102 >> (4 * pr)) & 0xF; }
-__device__ __forceinline__ int split_plane_b(int pr) { return (0x010120 >> (4 * pr)) & 0xF; }
-// v -> bf16 h, m, l with h + m + l == v to 24 bits (the two subtractions are exact in FP32)
-__device__ __forceinline__ void split3(float v, float& h, float& m, float& l) {
-    h = __bfloat162float(__float2bfloat16(v));
-    const float r = v - h;
-    m = __bfloat162float(__float2bfloat16(r));
-    l = r - m;
-}
-
 template <int NT, bool SPLIT>
 __global__ void __launch_bounds__(256, 1)
 dense_gemm_tc_kernel(const __grid_constant__ Maps3 maps_a, const __grid_constant__ Maps3 maps_b, GemmParams p) {

@@ -91,6 +91,95 @@ __global__ void maxpool2x2_bwd_kernel(const uint4* __restrict__ dpool, const uin
     dy[i] = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
+// FP32-exact mode ("bf16x3"): the activation is three bf16 planes h, m, l (`xplane` / `yplane` uint4 apart).  The window's FP32
+// values (l + m) + h are compared exactly like the FP32 path compares its floats; the winner's three plane words are copied.
+__global__ void maxpool2x2_fwd_x3_kernel(const uint4* __restrict__ x, size_t xplane, uint4* __restrict__ y, size_t yplane,
+                                         uint32_t* __restrict__ idx, int N, int H, int W, int C, int out_padded) {
+    pdl_trigger();
+    pdl_wait();
+    const int G = C / 8, PH = H / 2, PW = W / 2, Wp = W + 2;
+    const int OH = out_padded ? PH + 2 : PH, OW = out_padded ? PW + 2 : PW;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (unsigned)N * OH * OW * G) return;
+    const int g = (int)(i % (unsigned)G);
+    unsigned pix = i / (unsigned)G;
+    const int ow = (int)(pix % (unsigned)OW); pix /= (unsigned)OW;
+    const int oh = (int)(pix % (unsigned)OH);
+    const int n = (int)(pix / (unsigned)OH);
+    const int ph = out_padded ? oh - 1 : oh, pw = out_padded ? ow - 1 : ow;
+    if (ph < 0 || ph >= PH || pw < 0 || pw >= PW) {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        y[i] = z; y[yplane + i] = z; y[2 * yplane + i] = z;
+        return;
+    }
+    const size_t base = (((size_t)n * (H + 2) + 2 * ph + 1) * Wp + 2 * pw + 1) * G + g;
+    const size_t off[4] = {0, (size_t)G, (size_t)Wp * G, (size_t)Wp * G + G};
+    uint32_t w[3][4][4];                                     // [plane][window position][word]
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 v = __ldg(x + pl * xplane + base + off[q]);
+            w[pl][q][0] = v.x; w[pl][q][1] = v.y; w[pl][q][2] = v.z; w[pl][q][3] = v.w;
+        }
+    uint32_t out[3][4], nib = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float best[2]; uint32_t pos[2] = {0u, 0u};
+        best[0] = (bf16_lo(w[2][0][k]) + bf16_lo(w[1][0][k])) + bf16_lo(w[0][0][k]);
+        best[1] = (bf16_hi(w[2][0][k]) + bf16_hi(w[1][0][k])) + bf16_hi(w[0][0][k]);
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+            const float c0 = (bf16_lo(w[2][q][k]) + bf16_lo(w[1][q][k])) + bf16_lo(w[0][q][k]);
+            const float c1 = (bf16_hi(w[2][q][k]) + bf16_hi(w[1][q][k])) + bf16_hi(w[0][q][k]);
+            if (c0 > best[0]) { best[0] = c0; pos[0] = q; }                 // strict: the first maximum wins
+            if (c1 > best[1]) { best[1] = c1; pos[1] = q; }
+        }
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+            uint32_t lo = w[pl][0][k], hi = w[pl][0][k];
+#pragma unroll
+            for (int q = 1; q < 4; ++q) { if (pos[0] == (uint32_t)q) lo = w[pl][q][k]; if (pos[1] == (uint32_t)q) hi = w[pl][q][k]; }
+            out[pl][k] = (lo & 0x0000FFFFu) | (hi & 0xFFFF0000u);
+        }
+        nib |= (pos[0] | (best[0] > 0.f ? 4u : 0u)) << (8 * k);
+        nib |= (pos[1] | (best[1] > 0.f ? 4u : 0u)) << (8 * k + 4);
+    }
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) y[pl * yplane + i] = make_uint4(out[pl][0], out[pl][1], out[pl][2], out[pl][3]);
+    idx[(((size_t)n * PH + ph) * PW + pw) * G + g] = nib;
+}
+
+// planes [3][N][HW][C] (unpadded NHWC) -> float32 [N][C][HW], the reference's Flatten order (Flatten.py:21-53): the input of
+// the FP32 Dense head in the FP32-exact mode
+__global__ void merge3_nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ planes, size_t plane, float* __restrict__ out, int N, int HW, int C) {
+    pdl_trigger();
+    pdl_wait();
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;         // output index: coalesced writes
+    if (i >= (size_t)N * C * HW) return;
+    const int hw = (int)(i % HW);
+    const int c = (int)((i / HW) % C);
+    const size_t n = i / ((size_t)HW * C);
+    const size_t src = (n * HW + hw) * C + c;
+    out[i] = (__bfloat162float(planes[2 * plane + src]) + __bfloat162float(planes[plane + src])) + __bfloat162float(planes[src]);
+}
+
+// float32 [N][C][HW] -> planes [3][N][HW][C]: the Dense head's input gradient back into the conv stack's layout
+__global__ void split3_nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ planes, size_t plane, int N, int HW, int C) {
+    pdl_trigger();
+    pdl_wait();
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;         // destination index
+    if (i >= (size_t)N * C * HW) return;
+    const int c = (int)(i % C);
+    const int hw = (int)((i / C) % HW);
+    const size_t n = i / ((size_t)HW * C);
+    const float v = __ldg(x + (n * C + c) * HW + hw);
+    const __nv_bfloat16 h = __float2bfloat16(v);
+    const float r = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16(r);
+    planes[i] = h; planes[plane + i] = m; planes[2 * plane + i] = __float2bfloat16(r - __bfloat162float(m));
+}
+
 // dX[b][k] = sum_j dlogits[b][j] * Wp[j][k]   (Wp = the Dense weights packed as [n_out][K] in the kernels' (h,w,c) order)
 __global__ void dense_dgrad_bf16_kernel(const float* __restrict__ dlogits, const float* __restrict__ wp, const uint4* __restrict__ mask,
                                         float mask_scale, uint4* __restrict__ dx, int B, int K, int n_out) {
@@ -137,6 +226,35 @@ int nm_tc_maxpool2x2_fwd_bf16(const void* x_pad, void* y, void* idx, int N, int 
     NM_REQUIRE(total < (1ll << 31) - 1024, "tensor too large for 32-bit element indices");
     return nm::launch_pdl("maxpool2x2_fwd", maxpool2x2_fwd_kernel, dim3(nm_cdiv((size_t)total, 256)), dim3(256), 0, nm::S(stream),
                           static_cast<const uint4*>(x_pad), static_cast<uint4*>(y), static_cast<uint32_t*>(idx), N, H, W, C, out_padded);
+}
+
+int nm_tc_maxpool2x2_fwd_x3(const void* x_pad3, size_t x_plane, void* y3, size_t y_plane, void* idx, int N, int H, int W, int C, int out_padded,
+                            void* stream) {
+    NM_REQUIRE(x_pad3 && y3 && idx, "null pointer");
+    NM_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0, "bad dimensions (even H, W; C % 8 == 0)");
+    const long long total = (long long)N * (H / 2 + (out_padded ? 2 : 0)) * (W / 2 + (out_padded ? 2 : 0)) * (C / 8);
+    NM_REQUIRE(total < (1ll << 31) - 1024, "tensor too large for 32-bit element indices");
+    NM_REQUIRE(x_plane >= (size_t)N * (H + 2) * (W + 2) * C && y_plane >= (size_t)total * 8 && x_plane % 8 == 0 && y_plane % 8 == 0,
+               "plane strides must cover a plane and be multiples of 8 elements");
+    return nm::launch_pdl("maxpool2x2_fwd_x3", maxpool2x2_fwd_x3_kernel, dim3(nm_cdiv((size_t)total, 128)), dim3(128), 0, nm::S(stream),
+                          static_cast<const uint4*>(x_pad3), x_plane / 8, static_cast<uint4*>(y3), y_plane / 8, static_cast<uint32_t*>(idx),
+                          N, H, W, C, out_padded);
+}
+
+int nm_tc_merge3_nhwc_to_nchw_f32(const void* planes, size_t plane_stride, float* out, int N, int HW, int C, void* stream) {
+    NM_REQUIRE(planes && out, "null pointer");
+    NM_REQUIRE(N > 0 && HW > 0 && C > 0 && plane_stride >= (size_t)N * HW * C, "bad dimensions");
+    const size_t total = (size_t)N * HW * C;
+    return nm::launch_pdl("merge3_nhwc_to_nchw", merge3_nhwc_to_nchw_kernel, dim3(nm_cdiv(total, 256)), dim3(256), 0, nm::S(stream),
+                          static_cast<const __nv_bfloat16*>(planes), plane_stride, out, N, HW, C);
+}
+
+int nm_tc_split3_nchw_to_nhwc(const float* x, void* planes, size_t plane_stride, int N, int HW, int C, void* stream) {
+    NM_REQUIRE(planes && x, "null pointer");
+    NM_REQUIRE(N > 0 && HW > 0 && C > 0 && plane_stride >= (size_t)N * HW * C, "bad dimensions");
+    const size_t total = (size_t)N * HW * C;
+    return nm::launch_pdl("split3_nchw_to_nhwc", split3_nchw_to_nhwc_kernel, dim3(nm_cdiv(total, 256)), dim3(256), 0, nm::S(stream),
+                          x, static_cast<__nv_bfloat16*>(planes), plane_stride, N, HW, C);
 }
 
 int nm_tc_maxpool2x2_bwd_bf16(const void* dpool, const void* idx, void* dy_pad, int N, int H, int W, int C, int in_padded, void* stream) {
