@@ -349,8 +349,9 @@ int nm_tc_dense_wgrad_gen_x3(const void* x3, size_t x_plane, const void* dy3, si
  *   nm_tc_conv3x3_wgrad_gen_x3         dW, db (workspace: nm_tc_conv3x3_wgrad_gen_workspace)
  *   nm_tc_maxpool2x2_fwd_x3            window maximum of the exact FP32 values (l + m) + h, first maximum wins; idx as in
  *                                      nm_tc_maxpool2x2_fwd_bf16 (the backward is nm_tc_maxpool2x2_bwd_bf16 once per plane)
- *   nm_tc_merge3_nhwc_to_nchw_f32      planes [3][N][HW][C] -> float32 [N][C * HW] in Flatten's order (input of the FP32 head)
- *   nm_tc_split3_nchw_to_nhwc          float32 [N][C * HW] -> planes [3][N][HW][C] (the head's input gradient) */
+ *   nm_tc_merge3_nhwc_to_nchw_f32      planes [3][N][HW][Cp] -> float32 [N][C * HW] in Flatten's order (input of the FP32 head;
+ *                                      C <= Cp: the zero-padded channels of the last conv are dropped)
+ *   nm_tc_split3_nchw_to_nhwc          float32 [N][C * HW] -> planes [3][N][HW][Cp] (the head's input gradient; zeros in the padding) */
 int nm_tc_pack_conv_weights_gen_x3(const float* w_oihw, void* w_fprop3, void* w_dgrad3, int OC, int C, int OCp, int Cp, void* stream);
 int nm_tc_pack_input_nhwc_x3(const float* x_nchw, void* x_pad3, size_t plane, int N, int C, int H, int W, int Cp, void* stream);
 int nm_tc_pack_input_nhwc_u8_x3(const uint8_t* x_nchw, float denom, void* x_pad3, size_t plane, int N, int C, int H, int W, int Cp, void* stream);
@@ -360,8 +361,8 @@ int nm_tc_conv3x3_wgrad_gen_x3(const void* x_pad3, size_t x_plane, const void* d
                                void* workspace, size_t workspace_bytes, int N, int H, int W, int C, int OC, int Cp, int OCp, void* stream);
 int nm_tc_maxpool2x2_fwd_x3(const void* x_pad3, size_t x_plane, void* y3, size_t y_plane, void* idx, int N, int H, int W, int C, int out_padded,
                             void* stream);
-int nm_tc_merge3_nhwc_to_nchw_f32(const void* planes, size_t plane_stride, float* out, int N, int HW, int C, void* stream);
-int nm_tc_split3_nchw_to_nhwc(const float* x, void* planes, size_t plane_stride, int N, int HW, int C, void* stream);
+int nm_tc_merge3_nhwc_to_nchw_f32(const void* planes, size_t plane_stride, float* out, int N, int HW, int C, int Cp, void* stream);
+int nm_tc_split3_nchw_to_nhwc(const float* x, void* planes, size_t plane_stride, int N, int HW, int C, int Cp, void* stream);
 
 /* First conv of the net (C_in = 1, 3x3 'same', ReLU, no bias) + MaxPooling2D(2,2) on tcgen05: the 4x4 input patch of a
  * pool window is the K = 16 dimension and the weights are expanded to Wext[(window position, oc)][4x4] (zero outside the

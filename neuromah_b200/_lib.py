@@ -112,8 +112,8 @@ _SIGS = {
     "nm_tc_conv3x3_gen_x3": (_i, [_vp, _sz, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_conv3x3_wgrad_gen_x3": (_i, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_maxpool2x2_fwd_x3": (_i, [_vp, _sz, _vp, _sz, _vp, _i, _i, _i, _i, _i, _vp]),
-    "nm_tc_merge3_nhwc_to_nchw_f32": (_i, [_vp, _sz, _vp, _i, _i, _i, _vp]),
-    "nm_tc_split3_nchw_to_nhwc": (_i, [_vp, _vp, _sz, _i, _i, _i, _vp]),
+    "nm_tc_merge3_nhwc_to_nchw_f32": (_i, [_vp, _sz, _vp, _i, _i, _i, _i, _vp]),
+    "nm_tc_split3_nchw_to_nhwc": (_i, [_vp, _vp, _sz, _i, _i, _i, _i, _vp]),
     "nm_tc_split3_f32": (_i, [_vp, _vp, _f, _vp, _sz, _sz, _vp]),
     "nm_tc_split3_u8": (_i, [_vp, _f, _vp, _sz, _sz, _vp]),
     "nm_tc_pack_dense_gen_x3": (_i, [_vp, _vp, _vp, _i, _i, _vp]),

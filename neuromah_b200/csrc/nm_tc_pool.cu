@@ -150,9 +150,10 @@ __global__ void maxpool2x2_fwd_x3_kernel(const uint4* __restrict__ x, size_t xpl
     idx[(((size_t)n * PH + ph) * PW + pw) * G + g] = nib;
 }
 
-// planes [3][N][HW][C] (unpadded NHWC) -> float32 [N][C][HW], the reference's Flatten order (Flatten.py:21-53): the input of
-// the FP32 Dense head in the FP32-exact mode
-__global__ void merge3_nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ planes, size_t plane, float* __restrict__ out, int N, int HW, int C) {
+// planes [3][N][HW][Cp] (unpadded NHWC grid, channels possibly zero-padded to Cp) -> float32 [N][C][HW], the reference's Flatten
+// order (Flatten.py:21-53): the input of the FP32 Dense head in the FP32-exact mode
+__global__ void merge3_nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ planes, size_t plane, float* __restrict__ out, int N, int HW, int C,
+                                           int Cp) {
     pdl_trigger();
     pdl_wait();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;         // output index: coalesced writes
@@ -160,20 +161,22 @@ __global__ void merge3_nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ pla
     const int hw = (int)(i % HW);
     const int c = (int)((i / HW) % C);
     const size_t n = i / ((size_t)HW * C);
-    const size_t src = (n * HW + hw) * C + c;
+    const size_t src = (n * HW + hw) * Cp + c;
     out[i] = (__bfloat162float(planes[2 * plane + src]) + __bfloat162float(planes[plane + src])) + __bfloat162float(planes[src]);
 }
 
-// float32 [N][C][HW] -> planes [3][N][HW][C]: the Dense head's input gradient back into the conv stack's layout
-__global__ void split3_nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ planes, size_t plane, int N, int HW, int C) {
+// float32 [N][C][HW] -> planes [3][N][HW][Cp] (zeros in the padded channels): the Dense head's input gradient back into the
+// conv stack's layout
+__global__ void split3_nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ planes, size_t plane, int N, int HW, int C,
+                                           int Cp) {
     pdl_trigger();
     pdl_wait();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;         // destination index
-    if (i >= (size_t)N * C * HW) return;
-    const int c = (int)(i % C);
-    const int hw = (int)((i / C) % HW);
-    const size_t n = i / ((size_t)HW * C);
-    const float v = __ldg(x + (n * C + c) * HW + hw);
+    if (i >= (size_t)N * Cp * HW) return;
+    const int c = (int)(i % Cp);
+    const int hw = (int)((i / Cp) % HW);
+    const size_t n = i / ((size_t)HW * Cp);
+    const float v = c < C ? __ldg(x + (n * C + c) * HW + hw) : 0.f;
     const __nv_bfloat16 h = __float2bfloat16(v);
     const float r = v - __bfloat162float(h);
     const __nv_bfloat16 m = __float2bfloat16(r);
@@ -241,20 +244,20 @@ int nm_tc_maxpool2x2_fwd_x3(const void* x_pad3, size_t x_plane, void* y3, size_t
                           N, H, W, C, out_padded);
 }
 
-int nm_tc_merge3_nhwc_to_nchw_f32(const void* planes, size_t plane_stride, float* out, int N, int HW, int C, void* stream) {
+int nm_tc_merge3_nhwc_to_nchw_f32(const void* planes, size_t plane_stride, float* out, int N, int HW, int C, int Cp, void* stream) {
     NM_REQUIRE(planes && out, "null pointer");
-    NM_REQUIRE(N > 0 && HW > 0 && C > 0 && plane_stride >= (size_t)N * HW * C, "bad dimensions");
+    NM_REQUIRE(N > 0 && HW > 0 && C > 0 && Cp >= C && plane_stride >= (size_t)N * HW * Cp, "bad dimensions");
     const size_t total = (size_t)N * HW * C;
     return nm::launch_pdl("merge3_nhwc_to_nchw", merge3_nhwc_to_nchw_kernel, dim3(nm_cdiv(total, 256)), dim3(256), 0, nm::S(stream),
-                          static_cast<const __nv_bfloat16*>(planes), plane_stride, out, N, HW, C);
+                          static_cast<const __nv_bfloat16*>(planes), plane_stride, out, N, HW, C, Cp);
 }
 
-int nm_tc_split3_nchw_to_nhwc(const float* x, void* planes, size_t plane_stride, int N, int HW, int C, void* stream) {
+int nm_tc_split3_nchw_to_nhwc(const float* x, void* planes, size_t plane_stride, int N, int HW, int C, int Cp, void* stream) {
     NM_REQUIRE(planes && x, "null pointer");
-    NM_REQUIRE(N > 0 && HW > 0 && C > 0 && plane_stride >= (size_t)N * HW * C, "bad dimensions");
-    const size_t total = (size_t)N * HW * C;
+    NM_REQUIRE(N > 0 && HW > 0 && C > 0 && Cp >= C && plane_stride >= (size_t)N * HW * Cp, "bad dimensions");
+    const size_t total = (size_t)N * HW * Cp;
     return nm::launch_pdl("split3_nchw_to_nhwc", split3_nchw_to_nhwc_kernel, dim3(nm_cdiv(total, 256)), dim3(256), 0, nm::S(stream),
-                          x, static_cast<__nv_bfloat16*>(planes), plane_stride, N, HW, C);
+                          x, static_cast<__nv_bfloat16*>(planes), plane_stride, N, HW, C, Cp);
 }
 
 int nm_tc_maxpool2x2_bwd_bf16(const void* dpool, const void* idx, void* dy_pad, int N, int H, int W, int C, int in_padded, void* stream) {

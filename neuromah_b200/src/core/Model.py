@@ -70,7 +70,8 @@ class Model:
         "bf16" = tensor-core plan for the supported layer patterns (neuromah_b200/tc_plan.py: the MNIST CNN;
         neuromah_b200/tc_plan_gen.py: VGG-style conv stacks; neuromah_b200/tc_plan_mlp.py: multi-layer perceptrons);
         "bf16x3" = FP32-exact on the tensor cores (three bf16 planes per operand, six products per contraction):
-        multi-layer perceptrons only (tc_plan_mlp.py), same tolerance against the NumPy path as "fp32"."""
+        conv stacks (tc_plan_gen.py, which covers the MNIST CNN as well) and multi-layer perceptrons (tc_plan_mlp.py),
+        same tolerance against the NumPy path as "fp32"."""
         from ..activations import Activation_Softmax
         from ..losses import Loss_CategoricalCrossentropy
         from ..losses.Activation_Softmax_Loss_CategoricalCrossentropy import \
@@ -126,8 +127,15 @@ class Model:
                 raise ValueError("mode='bf16' supports these layer patterns:\n  " +
                                  "\n  ".join(c.PATTERN for c in (TcCnnPlan, TcStackPlan, TcMlpPlan)))
         elif self.mode == "bf16x3":
+            from ...tc_plan_gen import TcStackPlan
             from ...tc_plan_mlp import TcMlpPlan
-            self.plan = TcMlpPlan(self, split=True)        # raises with the supported pattern when the stack is not an MLP
+            for plan_cls in (TcStackPlan, TcMlpPlan):
+                if plan_cls.match(self, True) if plan_cls is TcStackPlan else plan_cls.match(self):
+                    self.plan = plan_cls(self, split=True)
+                    break
+            else:
+                raise ValueError("mode='bf16x3' supports these layer patterns:\n  " +
+                                 "\n  ".join(c.PATTERN for c in (TcStackPlan, TcMlpPlan)))
         elif self.mode != "fp32":
             raise ValueError("mode must be None, 'fp32', 'bf16' or 'bf16x3'")
         # raw uint8 pixel batches: normalised on the device by 1 / uint8_denominator (examples/test_Conv2D_MNIST.py:27);

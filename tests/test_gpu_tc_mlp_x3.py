@@ -120,8 +120,8 @@ def test_dense_gen_x3_fprop_dgrad_wgrad_fp32_exact(B, n_in, n_out):
     assert np.abs(db.numpy().ravel() - refb).max() <= 2e-6 * max(np.abs(refb).max(), np.abs(dy).max() * np.sqrt(B) * sc)
 
 
-def test_x3_mode_needs_an_mlp():
-    spec = ref_net.mnist_cnn_spec()
+def test_x3_mode_rejects_unsupported_stacks():
+    spec = [{"kind": "dense", "n_in": 20, "n_out": 10, "relu": False}, {"kind": "softmax"}]       # no hidden layer: neither plan
     with pytest.raises(ValueError, match="bf16x3"):
         build(spec, ref_net.init_params(spec, np.random.RandomState(0)), mode="bf16x3")
 

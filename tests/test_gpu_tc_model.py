@@ -97,7 +97,7 @@ def test_tc_bitwise_deterministic():
 
 
 @pytest.mark.parametrize("mode,early_tol,base_tol,slope_tol,tail_tol",
-                         [(None, 2e-4, 5e-3, 0.25, 2e-3), ("bf16", 1e-2, 2e-2, 0.5, 1e-2)])
+                         [(None, 2e-4, 5e-3, 0.25, 2e-3), ("bf16", 1e-2, 2e-2, 0.5, 1e-2), ("bf16x3", 2e-4, 5e-3, 0.25, 2e-3)])
 def test_cnn_200_step_loss_curve_golden(mode, early_tol, base_tol, slope_tol, tail_tol):
     """The reference's own 200-step loss curve (tests/golden/cnn_200steps.npz, learnable synthetic data, batch 64,
     Adam 1e-3 applied twice per layer) against a FREE-RUNNING device run in each mode.  Two float runs of a

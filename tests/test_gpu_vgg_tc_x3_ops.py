@@ -216,12 +216,22 @@ def test_x3_maxpool_forward_backward_and_head_transposes(padded):
         # planes [3][N][HW][C] -> float32 [N][C*HW] (Flatten's order) and back
         hw = (h // 2) * (w // 2)
         flat = DeviceArray.from_numpy(np.full((n, c * hw), np.nan, np.float32))
-        lib.nm_tc_merge3_nhwc_to_nchw_f32(y.p, ys, flat.p, n, hw, c, stream())
+        lib.nm_tc_merge3_nhwc_to_nchw_f32(y.p, ys, flat.p, n, hw, c, c, stream())
         np.testing.assert_array_equal(flat.numpy(), ref.reshape(n, -1).astype(np.float32))
         g = rng.standard_normal((n, c * hw)).astype(np.float32)
         back = DeviceArray.from_numpy(np.full((3, cap, hw, c), NAN, np.uint16))
-        lib.nm_tc_split3_nchw_to_nhwc(DeviceArray.from_numpy(g).p, back.p, cap * hw * c, n, hw, c, stream())
+        lib.nm_tc_split3_nchw_to_nhwc(DeviceArray.from_numpy(g).p, back.p, cap * hw * c, n, hw, c, c, stream())
         gb = back.numpy()
         assert (gb[:, n:] == NAN).all()
         for pl, part in enumerate(split3_host(g.reshape(n, c, hw))):
             np.testing.assert_array_equal(gb[pl, :n], to_bf16_bits(part.transpose(0, 2, 1)))
+        # a last conv narrower than its padded tensor: only the first cr channels are real
+        cr = 40
+        flat2 = DeviceArray.from_numpy(np.full((n, cr * hw), np.nan, np.float32))
+        lib.nm_tc_merge3_nhwc_to_nchw_f32(y.p, ys, flat2.p, n, hw, cr, c, stream())
+        np.testing.assert_array_equal(flat2.numpy(), ref[:, :cr].reshape(n, -1).astype(np.float32))
+        g2 = rng.standard_normal((n, cr * hw)).astype(np.float32)
+        lib.nm_tc_split3_nchw_to_nhwc(DeviceArray.from_numpy(g2).p, back.p, cap * hw * c, n, hw, cr, c, stream())
+        gb = back.numpy()
+        assert not gb[:, :n, :, cr:].any()
+        np.testing.assert_array_equal(gb[0, :n, :, :cr], to_bf16_bits(g2.reshape(n, cr, hw).transpose(0, 2, 1)))
