@@ -21,7 +21,7 @@ One JSON line on stdout (rank 0):
   roofline     the dominant kernel (CUDA events on the launch stream in a second timed region) against the measured peak
   parity       correctness AT THIS CONFIGURATION, checked after the timed regions: every rank's parameters bit-identical,
                and the data-parallel step equal to a single-GPU run over the same global batch in virtual shards
-  fp32_exact   (N = 1) the FP32-exact mode's throughput on the same workload (+ fp32_exact_tensor_core on the MLP: mode "bf16x3")
+  fp32_exact   (N = 1) the FP32-exact mode's throughput on the same workload (+ fp32_exact_tensor_core: mode "bf16x3")
   cpu_baseline (N = 1) the reference's CPU path timed on this box's host cores on a bounded sample
 """
 from __future__ import annotations
@@ -784,13 +784,13 @@ def main():
                               "step_tflops": wl["flops_per_sample"] * B / (ms.value / k32 * 1e-3) / 1e12,
                               "mode": "FP32-exact CUDA-core kernels, reference layouts (Model.finalize()): rtol 1e-4 / atol 1e-5 "
                                       "against the NumPy path (tests/test_gpu_model.py)"}
-        if args.workload == "mlp":
+        if args.workload in ("mlp", "mnist", "vgg"):
             # the same tolerance on the TENSOR cores: three bf16 planes per operand, six products per contraction (mode "bf16x3")
             mx3 = build_model(spec, params, mode="bf16x3")
             mx3.epoch_end_accuracy = False
             for s in range(8):                      # each of the two input slices is seen, then captured, then replayed
                 mx3.train_step(x32[(s % n32) * B:(s % n32 + 1) * B], y32[(s % n32) * B:(s % n32 + 1) * B])
-            kx3 = 200
+            kx3 = 200 if args.workload == "mlp" else 10
             lib.nm_event_record(e0, device.stream())
             for s in range(kx3):
                 mx3.train_step(x32[(s % n32) * B:(s % n32 + 1) * B], y32[(s % n32) * B:(s % n32 + 1) * B])
@@ -800,8 +800,10 @@ def main():
             line["fp32_exact_tensor_core"] = {
                 "value": kx3 * B / (ms.value / 1e3), "unit": UNIT, "ms_per_step": ms.value / kx3, "steps": kx3,
                 "cuda_graphs": len(getattr(mx3, "_graphs", {})),
-                "mode": "Model.finalize(mode='bf16x3'): hidden Dense layers as 3 bf16 planes x 6 tcgen05 products with FP32 accumulation, "
-                        "head on the FP32 CUDA-core kernels; rtol 1e-4 / atol 1e-5 against the NumPy path (tests/test_gpu_tc_mlp_x3.py)"}
+                "step_tflops": wl["flops_per_sample"] * B / (ms.value / kx3 * 1e-3) / 1e12,
+                "mode": "Model.finalize(mode='bf16x3'): every conv / hidden Dense contraction as 3 bf16 planes x 6 tcgen05 products with FP32 "
+                        "accumulation, head on the FP32 CUDA-core kernels; rtol 1e-4 / atol 1e-5 against the NumPy path "
+                        "(tests/test_gpu_tc_mlp_x3.py, tests/test_gpu_vgg_tc_x3_plan.py)"}
             del mx3
         del m32, x32
         line["hbm_kernels"] = optimizer_bandwidth()
