@@ -3,7 +3,7 @@ C(128->128) P C(128->256) C(256->256) P Flatten Dense(4096->10) Softmax, all 3x3
 CIFAR-10-shaped 32x32x3 data, built with the reference's own layer / model API (the building block reads like
 examples/test_Conv2D_MNIST.py:42-63 of the reference, with more layers).
 
-    python examples/test_Conv2D_CIFAR_VGG.py [--mode bf16|fp32] [--n 8192] [--batch 1024] [--epochs 2]
+    python examples/test_Conv2D_CIFAR_VGG.py [--mode bf16|bf16x3|fp32] [--n 8192] [--batch 1024] [--epochs 2]
 
 mode bf16 = the general tensor-core plan (neuromah_b200/tc_plan_gen.py: streamed-filter tcgen05 conv fprop / dgrad /
 wgrad); mode fp32 = the FP32-exact per-layer kernels.
@@ -35,7 +35,8 @@ def synthetic_cifar(n, rng):
 
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+ap.add_argument("--mode", default="bf16", choices=["bf16", "bf16x3", "fp32"],
+                help="bf16 = tensor-core plan; bf16x3 = FP32-exact on the tensor cores (3 bf16 planes per operand); fp32 = FP32-exact CUDA-core kernels")
 ap.add_argument("--n", type=int, default=8192)
 ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--epochs", type=int, default=2)
@@ -59,7 +60,7 @@ model.add(Activation_Softmax())
 model.set(loss=Loss_CategoricalCrossentropy,
           optimizer=Optimizer_Adam(learning_rate=0.001),
           accuracy=Accuracy_Categorical)
-model.finalize(mode=None if args.mode == "fp32" else "bf16")
+model.finalize(mode=None if args.mode == "fp32" else args.mode)
 
 t0 = time.perf_counter()
 model.train(train_images, train_labels_onehot, validation_data=(val_images, val_labels), epochs=args.epochs,

@@ -1,7 +1,7 @@
 """The reference's examples/test_Conv2D_MNIST.py on the B200 path, with synthetic MNIST-shaped data (no TensorFlow,
 no network).  The model-building block is the reference's, call for call (examples/test_Conv2D_MNIST.py:42-63).
 
-    python examples/test_Conv2D_MNIST.py [--mode bf16|fp32] [--n 16384] [--batch 4096] [--epochs 3]
+    python examples/test_Conv2D_MNIST.py [--mode bf16|bf16x3|fp32] [--n 16384] [--batch 4096] [--epochs 3]
 """
 import argparse
 import os
@@ -32,7 +32,8 @@ def synthetic_digits(n, rng):
 
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+ap.add_argument("--mode", default="bf16", choices=["bf16", "bf16x3", "fp32"],
+                help="bf16 = tensor-core plan; bf16x3 = FP32-exact on the tensor cores (3 bf16 planes per operand); fp32 = FP32-exact CUDA-core kernels")
 ap.add_argument("--n", type=int, default=16384)
 ap.add_argument("--batch", type=int, default=4096)
 ap.add_argument("--epochs", type=int, default=3)
@@ -54,7 +55,7 @@ model.set(loss=Loss_CategoricalCrossentropy,
           optimizer=Optimizer_Adam(learning_rate=0.001),
           accuracy=Accuracy_Categorical,
           tensorMonitor=TensorMonitor(log_dir=args.log_dir))
-model.finalize(mode=None if args.mode == "fp32" else "bf16")
+model.finalize(mode=None if args.mode == "fp32" else args.mode)
 
 t0 = time.perf_counter()
 model.train(train_images, train_labels_onehot, validation_data=(val_images, val_labels), epochs=args.epochs,

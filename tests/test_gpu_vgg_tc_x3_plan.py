@@ -113,3 +113,24 @@ def test_x3_stack_train_api_graph_replay_uint8_and_determinism():
     one = build(spec, params, mode="bf16x3", learning_rate=0.001)
     one.train(xu, y, epochs=1, batch_size=32, verbose=0)
     np.testing.assert_allclose(one.arena.host_params(), ref.arena.host_params(), rtol=1e-3, atol=2e-5)
+
+
+def test_x3_virtual_shards_global_batch_rule_and_public_api():
+    """SURVEY 8e in bf16x3 mode through the public forward / backward: G shards with the global batch as divisor sum to the
+    un-split gradient (the data-parallel rule), to FP32 summation order."""
+    from neuromah_b200 import parallel
+    spec = ref_net.mnist_cnn_spec()
+    params = ref_net.init_params(spec, np.random.RandomState(7), init="he")
+    B, G = 256, 4
+    x, y = synth(8, B, (1, 28, 28))
+    full = build(spec, params, mode="bf16x3")
+    out = full.forward(x, training=True); full.backward(out, y)
+    g_full = full.arena.host_grads().astype(np.float64)
+    shard = build(spec, params, mode="bf16x3")
+    parallel.set_global_batch(shard, B)
+    acc = np.zeros_like(g_full)
+    for r in range(G):
+        lo, hi = parallel.shard_bounds(B, r, G)
+        o = shard.forward(x[lo:hi], training=True); shard.backward(o, y[lo:hi])
+        acc += shard.arena.host_grads()
+    assert rel_l2(acc, g_full) <= 2e-6
