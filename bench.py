@@ -152,7 +152,14 @@ _DTAG = re.compile(r"tc_dense_gen_\w+\[(\d+)->(\d+)\]")
 
 
 def kernel_work(name, b):
-    """(algorithmic FLOPs, algorithmic HBM bytes) of one launch of the named operator at batch b."""
+    """(algorithmic FLOPs, algorithmic HBM bytes) of one launch of the named operator at batch b.
+    Operators of the FP32-exact tensor-core mode (names with _x3) move three bf16 planes per tensor: 3 x the bf16 bytes; their
+    FLOPs are counted once (FP32-equivalent), although the tensor cores execute six bf16 products per term."""
+    f, by = _kernel_work(name, b)
+    return (f, 3.0 * by) if "_x3" in name else (f, by)
+
+
+def _kernel_work(name, b):
     c2 = 2.0 * b * 64 * 32 * 9 * 14 * 14          # conv fprop = dgrad = wgrad = 2 B OC IC kH kW oh ow (SURVEY 8d)
     c1 = 2.0 * b * 32 * 1 * 9 * 28 * 28
     m = _DTAG.search(name)
@@ -506,8 +513,9 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (weak scaling) or global batch (--scaling strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, BASELINE.json): --batch samples per GPU; strong: --batch is the GLOBAL batch, split N ways")
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"],
-                    help="bf16 = fused tensor-core plan (tcgen05), fp32 = FP32-exact CUDA-core kernels")
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "bf16x3", "fp32"],
+                    help="bf16 = fused tensor-core plan (tcgen05), bf16x3 = FP32-exact on the tensor cores (3 bf16 planes per operand), "
+                         "fp32 = FP32-exact CUDA-core kernels")
     ap.add_argument("--input", default="u8", choices=["u8", "f32"],
                     help="host input of the end-to-end leg: raw uint8 pixels normalised on the device, or float32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -545,7 +553,7 @@ def main():
         if B % world:
             raise SystemExit(f"--scaling strong: global batch {B} is not divisible by {world} GPUs")
         B //= world
-    mode = None if args.mode == "fp32" else "bf16"
+    mode = None if args.mode == "fp32" else args.mode
 
     def barrier():
         device.synchronize()
@@ -747,7 +755,7 @@ def main():
                 "kernels": per_kernel}
     line = {"metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+            "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (three bf16 planes per operand, FP32-exact)"}.get(args.mode, "f32"), "data": "synthetic",
             "config": {"workload": wl["desc"],
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "gradient_exchange": ("none: clients train independently; weights averaged once per round (NCCL all-reduce of "
@@ -755,8 +763,9 @@ def main():
                                              "gradient slab pushed over NVLink peer memory behind each wgrad (overlapping the rest of "
                                              "backward) + fused collect / rank-ordered sum / Adam kernel (nm_dp_*)"
                                              if comm.peer is not None else "NCCL all-reduce, buckets on a side stream"),
-                       "mode": "bf16 tensor-core plan (bf16 operands, fp32 accumulate, fp32 master weights)"
-                               if args.mode == "bf16" else "fp32_exact",
+                       "mode": {"bf16": "bf16 tensor-core plan (bf16 operands, fp32 accumulate, fp32 master weights)",
+                                "bf16x3": "FP32-exact tensor-core plan (three bf16 planes per operand, six tcgen05 products per contraction, "
+                                          "fp32 accumulate, fp32 master weights)"}.get(args.mode, "fp32_exact"),
                        "step_tflops": wl["flops_per_sample"] * E * B * world / (elapsed_ms / K * 1e-3) / 1e12,
                        "cuda_graphs": graphs,
                        "l2": "inputs cycle over 8 distinct batches; the per-step activation working set "
