@@ -145,3 +145,49 @@ def test_uint8_pixel_normalisation_is_exact_after_bf16_rounding():
         return ((i + 0x7FFF + ((i >> 16) & 1)) >> 16).astype(np.uint16)
     assert np.sum(div != mul) > 0                      # the float32 values do differ ...
     np.testing.assert_array_equal(bf16_rn(div), bf16_rn(mul))      # ... the operands never do
+
+
+# ---------------------------------------------------------------- mode "bf16x3": three bf16 planes, six products ----
+def _bf16(a):
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    return (((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16).astype(np.uint32).view(np.float32)
+
+
+def _split3(a):
+    a = np.ascontiguousarray(a, np.float32)
+    h = _bf16(a)
+    m = _bf16(a - h)
+    return h, m, _bf16(a - h - m)
+
+
+def test_three_plane_split_and_six_products_are_fp32_exact():
+    """The arithmetic contract of the FP32-exact tensor-core mode (nm_tc_common.cuh: split3, split_plane_a / split_plane_b),
+    restated in NumPy: the planes carry 24 mantissa bits, the pass table in the header decodes to the six plane pairs whose
+    weight is above 2^-24 ordered smallest first, their sum with FP32 accumulation matches the float64 product to ~1e-6 of
+    the output scale, and the three dropped pairs are below 2^-23 of it -- while the single bf16 product of mode "bf16" is
+    ~1e-3 off, which is why that mode states a looser tolerance."""
+    import pathlib
+    import re
+    src = (pathlib.Path(__file__).resolve().parents[1] / "neuromah_b200" / "csrc" / "nm_tc_common.cuh").read_text()
+    ta = int(re.search(r"split_plane_a\(int pr\) \{ return \((0x[0-9a-fA-F]+) >>", src).group(1), 16)
+    tb = int(re.search(r"split_plane_b\(int pr\) \{ return \((0x[0-9a-fA-F]+) >>", src).group(1), 16)
+    pairs = [((ta >> (4 * pr)) & 0xF, (tb >> (4 * pr)) & 0xF) for pr in range(6)]
+    assert sorted(pairs) == sorted([(0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (2, 0)])          # every pair with a + b <= 2
+    assert [a + b for a, b in pairs] == sorted((a + b for a, b in pairs), reverse=True)       # smallest products first
+    assert sorted(a for a, _ in pairs[:3]) == [0, 1, 2]      # passes 0-2 see each plane of the first operand once (wgrad's bias MMA)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((64, 784)).astype(np.float32)
+    w = (rng.standard_normal((784, 128)) * 0.05).astype(np.float32)
+    xs, ws = _split3(x), _split3(w)
+    for v, parts in ((x, xs), (w, ws)):
+        assert np.abs((parts[0].astype(np.float64) + parts[1] + parts[2]) - v).max() <= 2.0 ** -24 * np.abs(v).max()
+    ref = x.astype(np.float64) @ w.astype(np.float64)
+    scale = np.abs(ref).max()
+    acc = np.zeros(ref.shape, np.float32)
+    for a, b in pairs:
+        acc = acc + (xs[a] @ ws[b]).astype(np.float32)                                         # FP32 accumulator
+    assert np.abs(acc - ref).max() <= 2e-6 * scale
+    dropped = sum(np.abs(xs[a].astype(np.float64) @ ws[b]) for a, b in ((1, 2), (2, 1), (2, 2)))
+    assert dropped.max() <= 2.0 ** -23 * scale
+    one = (xs[0].astype(np.float64) @ ws[0])
+    assert 1e-4 * scale < np.abs(one - ref).max() < 1e-2 * scale
