@@ -24,9 +24,10 @@
 #include "nm_tc_common.cuh"
 #include "nm_tc_host.cuh"
 #include "nm_tc_pack.cuh"
+#include <cstdlib>
 
 #ifdef NM_ABLATE   // timing experiments only: CTA 0 records clock64() per tile and role
-#define NM_TRACE(G, tile, slot) do { if ((G).trace && blockIdx.x == 0) (G).trace[((tile) / gridDim.x) * 8 + (slot)] = clock64(); } while (0)
+#define NM_TRACE(G, tile, slot) do { if ((G).g.trace && blockIdx.x == 0) (G).g.trace[((tile) / gridDim.x) * 8 + (slot)] = clock64(); } while (0)
 static long long* g_conv1_trace = nullptr;
 extern "C" int nm_tc_debug_set_trace_conv1(void* buf) { g_conv1_trace = static_cast<long long*>(buf); return 0; }
 #else
@@ -49,14 +50,30 @@ __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t byte) { const u
 
 struct Conv1Geom { int N, H, W, PH, PW, PHW; unsigned total; int num_tiles; long long* trace; };   // total pool windows < 2^31
 
+// Geometry as the kernels read it.  HC = 28: H = W = 28 (MNIST, BASELINE configs[1]) known at COMPILE time, so the divisions
+// by the pooled width / image size in the per-tile index math fold into multiply-shifts (ncu: the run-time divisions --
+// I2F / MUFU.RCP / F2I chains -- and their fix-ups were ~15 % of the instructions of these issue-bound kernels);
+// HC = 0: any even H, W from the run-time struct.
+template <int HC> struct GeomView {
+    const Conv1Geom& g;
+    __device__ __forceinline__ int H() const { return HC ? HC : g.H; }
+    __device__ __forceinline__ int W() const { return HC ? HC : g.W; }
+    __device__ __forceinline__ int PH() const { return HC ? HC / 2 : g.PH; }
+    __device__ __forceinline__ int PW() const { return HC ? HC / 2 : g.PW; }
+    __device__ __forceinline__ int PHW() const { return HC ? (HC / 2) * (HC / 2) : g.PHW; }
+    unsigned total;
+    int num_tiles;
+};
+
 // Images [n0, n1] touched by the 128 windows of a tile; the bulk-copy producer stages them (contiguous in x).
 struct TileSpan { unsigned g0, g1; int n0, n1; };
-__device__ __forceinline__ TileSpan tile_span(const Conv1Geom& G, int tile) {
+template <int HC>
+__device__ __forceinline__ TileSpan tile_span(const GeomView<HC>& G, int tile) {
     TileSpan t;
     t.g0 = (unsigned)tile * 128u;
     t.g1 = min(t.g0 + 127u, G.total - 1u);
-    t.n0 = (int)(t.g0 / (unsigned)G.PHW);
-    t.n1 = t.n0 + ((t.g1 - (unsigned)t.n0 * G.PHW) >= (unsigned)G.PHW ? 1 : 0);     // a tile touches at most two images
+    t.n0 = (int)(t.g0 / (unsigned)G.PHW());
+    t.n1 = t.n0 + ((t.g1 - (unsigned)t.n0 * G.PHW()) >= (unsigned)G.PHW() ? 1 : 0);     // a tile touches at most two images
     return t;
 }
 
@@ -68,33 +85,33 @@ __device__ __forceinline__ float px_val(const uint8_t* img, int i, float scale) 
 
 // the 4x4 input patch of pool window (n, py, px) from the staged images (zero outside the image: the 'same'
 // padding of Conv_wrapepr.py:78-84)
-template <typename XT>
-__device__ __forceinline__ void load_patch(const XT* __restrict__ xs, const Conv1Geom& G, float scale, bool valid, int n_local, int py, int px,
+template <typename XT, int HC>
+__device__ __forceinline__ void load_patch(const XT* __restrict__ xs, const GeomView<HC>& G, float scale, bool valid, int n_local, int py, int px,
                                            float p[16]) {
-    const XT* img = xs + n_local * G.H * G.W;
+    const XT* img = xs + n_local * G.H() * G.W();
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const int yy = 2 * py - 1 + a;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int xx = 2 * px - 1 + b;
-            p[a * 4 + b] = (valid && (unsigned)yy < (unsigned)G.H && (unsigned)xx < (unsigned)G.W) ? px_val(img, yy * G.W + xx, scale) : 0.f;
+            p[a * 4 + b] = (valid && (unsigned)yy < (unsigned)G.H() && (unsigned)xx < (unsigned)G.W()) ? px_val(img, yy * G.W() + xx, scale) : 0.f;
         }
     }
 }
 
 // rows a0, a0 + 1 of that patch only (the backward builders split a window's patch between two threads)
-template <typename XT>
-__device__ __forceinline__ void load_patch_rows(const XT* __restrict__ xs, const Conv1Geom& G, float scale, bool valid, int n_local, int py, int px,
+template <typename XT, int HC>
+__device__ __forceinline__ void load_patch_rows(const XT* __restrict__ xs, const GeomView<HC>& G, float scale, bool valid, int n_local, int py, int px,
                                                 int a0, float p[8]) {
-    const XT* img = xs + n_local * G.H * G.W;
+    const XT* img = xs + n_local * G.H() * G.W();
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
         const int yy = 2 * py - 1 + a0 + a;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int xx = 2 * px - 1 + b;
-            p[a * 4 + b] = (valid && (unsigned)yy < (unsigned)G.H && (unsigned)xx < (unsigned)G.W) ? px_val(img, yy * G.W + xx, scale) : 0.f;
+            p[a * 4 + b] = (valid && (unsigned)yy < (unsigned)G.H() && (unsigned)xx < (unsigned)G.W()) ? px_val(img, yy * G.W() + xx, scale) : 0.f;
         }
     }
 }
@@ -109,10 +126,11 @@ constexpr int F_NBUF = 4;                       // TMEM accumulators (4 x 128 co
 constexpr int F_XSTAGES = 6;                    // staged-image ring (bulk-copy producer -> builders): hides the HBM latency
 constexpr int F_THREADS = 832;                  // warps 0-7 builders (2 groups), 8 MMA, 9-24 epilogue (4 groups), 25 bulk-copy producer
 
-template <typename XT>
+template <typename XT, int HC>
 __global__ void __launch_bounds__(F_THREADS, 1)
 conv1_tc_fwd_kernel(const XT* __restrict__ x, float x_scale, const __nv_bfloat16* __restrict__ wext, __nv_bfloat16* __restrict__ y_pad,
-                    uint8_t* __restrict__ idx, Conv1Geom G, int x_stage_bytes) {
+                    uint8_t* __restrict__ idx, Conv1Geom Gp, int x_stage_bytes) {
+    const GeomView<HC> G{Gp, Gp.total, Gp.num_tiles};
     constexpr uint64_t TMPL = desc_template(16, 512, LAYOUT_SW64);
     constexpr uint32_t IDESC = idesc_bf16(128, 128, 0, 0);
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -155,10 +173,10 @@ conv1_tc_fwd_kernel(const XT* __restrict__ x, float x_scale, const __nv_bfloat16
             int xs = 0; uint32_t xphase = 0;
             for (int tile = blockIdx.x; tile < G.num_tiles; tile += gridDim.x) {
                 const TileSpan t = tile_span(G, tile);
-                const uint32_t bytes = (uint32_t)(t.n1 - t.n0 + 1) * G.H * G.W * (uint32_t)sizeof(XT);
+                const uint32_t bytes = (uint32_t)(t.n1 - t.n0 + 1) * G.H() * G.W() * (uint32_t)sizeof(XT);
                 mbar_wait(&xempty[xs], xphase ^ 1);
                 mbar_expect_tx(&xfull[xs], bytes);
-                bulk_load(x_smem + (size_t)xs * x_stage_bytes, x + (size_t)t.n0 * G.H * G.W, bytes, &xfull[xs]);
+                bulk_load(x_smem + (size_t)xs * x_stage_bytes, x + (size_t)t.n0 * G.H() * G.W(), bytes, &xfull[xs]);
                 if (++xs == F_XSTAGES) { xs = 0; xphase ^= 1; }
             }
         }
@@ -175,24 +193,29 @@ conv1_tc_fwd_kernel(const XT* __restrict__ x, float x_scale, const __nv_bfloat16
             const bool valid = g < G.total;
             int n = t.n0, py = 0, px = 0;
             if (valid) {
-                unsigned w = g - (unsigned)t.n0 * G.PHW;
-                if (w >= (unsigned)G.PHW) { w -= G.PHW; ++n; }
-                py = (int)(w / (unsigned)G.PW); px = (int)w - py * G.PW;
+                unsigned w = g - (unsigned)t.n0 * G.PHW();
+                if (w >= (unsigned)G.PHW()) { w -= G.PHW(); ++n; }
+                py = (int)(w / (unsigned)G.PW()); px = (int)w - py * G.PW();
             }
             float p[16];
             if (row == 0) NM_TRACE(G, tile, 0);
             mbar_wait(&xfull[xs], xphase);
             if (row == 0) NM_TRACE(G, tile, 1);
             load_patch(reinterpret_cast<const XT*>(x_smem + (size_t)xs * x_stage_bytes), G, x_scale, valid, n - t.n0, py, px, p);
+            // The slot is handed back only once the pixels are IN REGISTERS: the packed words below consume every load, and
+            // the empty asm makes the arrive depend on them.  Issuing the loads is not enough -- with the arrive right behind
+            // sixteen LDS the bulk copy of a later tile overwrote pixels that had not been read yet (1 launch in 10 at batch
+            // 4096 once the index math got cheaper; never seen with the slower run-time divisions in between).
+            const uint4 plo = make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+            const uint4 phi = make_uint4(pack_bf16x2(p[8], p[9]), pack_bf16x2(p[10], p[11]), pack_bf16x2(p[12], p[13]), pack_bf16x2(p[14], p[15]));
+            asm volatile("" :: "r"(plo.x), "r"(plo.y), "r"(plo.z), "r"(plo.w), "r"(phi.x), "r"(phi.y), "r"(phi.z), "r"(phi.w) : "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&xempty[xs]);          // the patches are in registers: the image slot may be refilled
             mbar_wait(&aempty[stage], phase ^ 1);
             if (row == 0) NM_TRACE(G, tile, 2);
             uint8_t* at = a_smem + stage * F_TILE_BYTES;
-            *reinterpret_cast<uint4*>(at + sw64(row, 0)) = make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]),
-                                                                       pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
-            *reinterpret_cast<uint4*>(at + sw64(row, 16)) = make_uint4(pack_bf16x2(p[8], p[9]), pack_bf16x2(p[10], p[11]),
-                                                                        pack_bf16x2(p[12], p[13]), pack_bf16x2(p[14], p[15]));
+            *reinterpret_cast<uint4*>(at + sw64(row, 0)) = plo;
+            *reinterpret_cast<uint4*>(at + sw64(row, 16)) = phi;
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&afull[stage]);
@@ -227,9 +250,9 @@ conv1_tc_fwd_kernel(const XT* __restrict__ x, float x_scale, const __nv_bfloat16
             const unsigned g = (unsigned)tile * 128u + q * 32 + lane;
             const bool valid = g < G.total;
             int n = 0, py = 0, px = 0, w = 0;
-            if (valid) { n = (int)(g / (unsigned)G.PHW); w = (int)(g - (unsigned)n * G.PHW); py = w / G.PW; px = w - py * G.PW; }
-            __nv_bfloat16* yo = y_pad + (((size_t)n * (G.PH + 2) + py + 1) * (G.PW + 2) + px + 1) * OC;
-            uint32_t* io = reinterpret_cast<uint32_t*>(idx + ((size_t)n * G.PHW + w) * (OC / 2));
+            if (valid) { n = (int)(g / (unsigned)G.PHW()); w = (int)(g - (unsigned)n * G.PHW()); py = w / G.PW(); px = w - py * G.PW(); }
+            __nv_bfloat16* yo = y_pad + (((size_t)n * (G.PH() + 2) + py + 1) * (G.PW() + 2) + px + 1) * OC;
+            uint32_t* io = reinterpret_cast<uint32_t*>(idx + ((size_t)n * G.PHW() + w) * (OC / 2));
             const int acc = it % F_NBUF;                                   // F_NBUF is even: buffers {grp, grp + 2} belong to this parity
             mbar_wait(&tfull[acc], (it / F_NBUF) & 1);
             if (lane == 0 && q == 0 && half == 0) NM_TRACE(G, tile, 5);
@@ -308,10 +331,11 @@ constexpr int B_THREADS = 576;                  // warps 0-15 builders in two gr
 
 struct Conv1BwdSmem { int x_bytes, dp_bytes, lstage_bytes; };   // per load stage: [x images | dp rows | nibbles]
 
-template <typename XT>
+template <typename XT, int HC>
 __global__ void __launch_bounds__(B_THREADS, 1)
 conv1_tc_bwd_kernel(const XT* __restrict__ x, float x_scale, const __nv_bfloat16* __restrict__ dp_grid, const uint8_t* __restrict__ idx,
-                    float* __restrict__ partial, Conv1Geom G, Conv1BwdSmem L) {
+                    float* __restrict__ partial, Conv1Geom Gp, Conv1BwdSmem L) {
+    const GeomView<HC> G{Gp, Gp.total, Gp.num_tiles};
     constexpr uint64_t TMPL_A = desc_template(16, 1024, LAYOUT_SW128);     // MN-major: SBO = 8 k-rows of 128 B
     constexpr uint64_t TMPL_B = desc_template(16, 512, LAYOUT_SW64);       //           SBO = 8 k-rows of 64 B
     constexpr uint32_t IDESC = idesc_bf16(64, 32, 1, 1);
@@ -324,7 +348,7 @@ conv1_tc_bwd_kernel(const XT* __restrict__ x, float x_scale, const __nv_bfloat16
     uint64_t* done = lempty + B_LSTAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row_bytes = (G.PW + 2) * OC * 2;                              // one row of the dP grid
+    const int row_bytes = (G.PW() + 2) * OC * 2;                              // one row of the dP grid
     pdl_trigger();
 
     // constant half of every P row: column 16 = 1 (bias gradient), columns 17..31 = 0
@@ -357,16 +381,16 @@ conv1_tc_bwd_kernel(const XT* __restrict__ x, float x_scale, const __nv_bfloat16
             int ls = 0; uint32_t lphase = 0;
             for (int tile = blockIdx.x; tile < G.num_tiles; tile += gridDim.x) {
                 const TileSpan t = tile_span(G, tile);
-                const int w0 = (int)(t.g0 - (unsigned)t.n0 * G.PHW), w1 = (int)(t.g1 - (unsigned)t.n1 * G.PHW);
-                const int r0 = t.n0 * (G.PH + 2) + w0 / G.PW, r1 = t.n1 * (G.PH + 2) + w1 / G.PW;
-                const uint32_t xb = (uint32_t)(t.n1 - t.n0 + 1) * G.H * G.W * (uint32_t)sizeof(XT);
+                const int w0 = (int)(t.g0 - (unsigned)t.n0 * G.PHW()), w1 = (int)(t.g1 - (unsigned)t.n1 * G.PHW());
+                const int r0 = t.n0 * (G.PH() + 2) + w0 / G.PW(), r1 = t.n1 * (G.PH() + 2) + w1 / G.PW();
+                const uint32_t xb = (uint32_t)(t.n1 - t.n0 + 1) * G.H() * G.W() * (uint32_t)sizeof(XT);
                 const uint32_t db = (uint32_t)(r1 - r0 + 1) * row_bytes;
                 const uint32_t ib = (uint32_t)(t.g1 - t.g0 + 1) * (OC / 2);
                 uint8_t* st = l_smem + (size_t)ls * L.lstage_bytes;
                 mbar_wait(&lempty[ls], lphase ^ 1);
                 NM_TRACE(G, tile, 0);
                 mbar_expect_tx(&lfull[ls], xb + db + ib);
-                bulk_load(st, x + (size_t)t.n0 * G.H * G.W, xb, &lfull[ls]);
+                bulk_load(st, x + (size_t)t.n0 * G.H() * G.W(), xb, &lfull[ls]);
                 bulk_load(st + L.x_bytes, reinterpret_cast<const uint8_t*>(dp_grid) + (size_t)r0 * row_bytes, db, &lfull[ls]);
                 bulk_load(st + L.x_bytes + L.dp_bytes, idx + (size_t)t.g0 * (OC / 2), ib, &lfull[ls]);
                 if (++ls == B_LSTAGES) { ls = 0; lphase ^= 1; }
@@ -392,11 +416,11 @@ conv1_tc_bwd_kernel(const XT* __restrict__ x, float x_scale, const __nv_bfloat16
             const bool valid = g < G.total;
             int n = t.n0, py = 0, px = 0;
             if (valid) {
-                unsigned w = g - (unsigned)t.n0 * G.PHW;
-                if (w >= (unsigned)G.PHW) { w -= G.PHW; ++n; }
-                py = (int)(w / (unsigned)G.PW); px = (int)w - py * G.PW;
+                unsigned w = g - (unsigned)t.n0 * G.PHW();
+                if (w >= (unsigned)G.PHW()) { w -= G.PHW(); ++n; }
+                py = (int)(w / (unsigned)G.PW()); px = (int)w - py * G.PW();
             }
-            const int w0 = (int)(t.g0 - (unsigned)t.n0 * G.PHW), r0 = t.n0 * (G.PH + 2) + w0 / G.PW;
+            const int w0 = (int)(t.g0 - (unsigned)t.n0 * G.PHW()), r0 = t.n0 * (G.PH() + 2) + w0 / G.PW();
             const uint8_t* st = l_smem + (size_t)ls * L.lstage_bytes;
             uint4 da = make_uint4(0, 0, 0, 0), db = da;          // pieces `flip` and `flip ^ 1` of this thread's 16 channels
             uint2 nb = make_uint2(0, 0);
@@ -405,11 +429,15 @@ conv1_tc_bwd_kernel(const XT* __restrict__ x, float x_scale, const __nv_bfloat16
             mbar_wait(&lfull[ls], lphase);
             if ((threadIdx.x & 255) == 0) NM_TRACE(G, tile, 2);
             if (valid) {
-                const uint4* src = reinterpret_cast<const uint4*>(st + L.x_bytes + (size_t)(n * (G.PH + 2) + py - r0) * row_bytes + px * (OC * 2) + hh * 32);
+                const uint4* src = reinterpret_cast<const uint4*>(st + L.x_bytes + (size_t)(n * (G.PH() + 2) + py - r0) * row_bytes + px * (OC * 2) + hh * 32);
                 da = src[flip]; db = src[flip ^ 1];
                 nb = *reinterpret_cast<const uint2*>(st + L.x_bytes + L.dp_bytes + row * (OC / 2) + hh * 8);
             }
             load_patch_rows(reinterpret_cast<const XT*>(st), G, x_scale, valid, n - t.n0, py, px, 2 * hh, p);
+            // hand the slot back only once every staged value is in registers (see the forward builder)
+            const uint4 pk = make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+            asm volatile("" :: "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w), "r"(da.x), "r"(da.y), "r"(da.z), "r"(da.w),
+                               "r"(db.x), "r"(db.y), "r"(db.z), "r"(db.w), "r"(nb.x), "r"(nb.y) : "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&lempty[ls]);          // everything is in registers: the slot may be refilled
             const uint32_t dw[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};   // 16 channels as bf16 pairs, piece order
@@ -445,8 +473,7 @@ conv1_tc_bwd_kernel(const XT* __restrict__ x, float x_scale, const __nv_bfloat16
                 *reinterpret_cast<uint4*>(blk + sw128(row, base + 16 * flip)) = make_uint4(out[pos][0], out[pos][1], out[pos][2], out[pos][3]);
                 *reinterpret_cast<uint4*>(blk + sw128(row, base + 16 * (flip ^ 1))) = make_uint4(out[pos][4], out[pos][5], out[pos][6], out[pos][7]);
             }
-            *reinterpret_cast<uint4*>(gt + B_G_BYTES + sw64(row, 16 * hh)) =                  // patch rows 2hh, 2hh+1 of this window
-                make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+            *reinterpret_cast<uint4*>(gt + B_G_BYTES + sw64(row, 16 * hh)) = pk;              // patch rows 2hh, 2hh+1 of this window
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&afull[stage]);
@@ -573,9 +600,16 @@ static int conv1_fwd_launch(const XT* x, float scale, const void* w_ext, void* y
     const size_t smem = (size_t)(1 + F_STAGES) * F_TILE_BYTES + (size_t)F_XSTAGES * x_stage + 256;
     if (smem > 200 * 1024) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_fwd_pool: image too large for the staged-image ring");
     static bool attr = false;
-    if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv1_tc_fwd_kernel<XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    if (!attr) {
+        NM_CUDA(cudaFuncSetAttribute(conv1_tc_fwd_kernel<XT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        NM_CUDA(cudaFuncSetAttribute(conv1_tc_fwd_kernel<XT, 28>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
     const int grid = g.num_tiles < sm_count() ? g.num_tiles : sm_count();
-    return nm::launch_pdl("conv1_tc_fwd", conv1_tc_fwd_kernel<XT>, dim3(grid), dim3(F_THREADS), smem, nm::S(stream), x, scale,
+    if (H == 28 && W == 28 && !getenv("NM_CONV1_GENERIC"))      // MNIST geometry: compile-time index math (the variable: A/B debugging)
+        return nm::launch_pdl("conv1_tc_fwd", conv1_tc_fwd_kernel<XT, 28>, dim3(grid), dim3(F_THREADS), smem, nm::S(stream), x, scale,
+                              static_cast<const __nv_bfloat16*>(w_ext), static_cast<__nv_bfloat16*>(y_pad), static_cast<uint8_t*>(idx), g, x_stage);
+    return nm::launch_pdl("conv1_tc_fwd", conv1_tc_fwd_kernel<XT, 0>, dim3(grid), dim3(F_THREADS), smem, nm::S(stream), x, scale,
                           static_cast<const __nv_bfloat16*>(w_ext), static_cast<__nv_bfloat16*>(y_pad), static_cast<uint8_t*>(idx), g, x_stage);
 }
 
@@ -600,9 +634,16 @@ static int conv1_bwd_launch(const XT* x, float scale, const void* dp_grid, const
     const size_t smem = (size_t)B_STAGES * B_STAGE + (size_t)B_LSTAGES * L.lstage_bytes + 256;
     if (smem > 220 * 1024) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_bwd: image too large for the staged-input ring");
     static bool attr = false;
-    if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv1_tc_bwd_kernel<XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
-    int rc = nm::launch_pdl("conv1_tc_bwd", conv1_tc_bwd_kernel<XT>, dim3(grid), dim3(B_THREADS), smem, nm::S(stream), x, scale,
-                            static_cast<const __nv_bfloat16*>(dp_grid), static_cast<const uint8_t*>(idx), static_cast<float*>(workspace), g, L);
+    if (!attr) {
+        NM_CUDA(cudaFuncSetAttribute(conv1_tc_bwd_kernel<XT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        NM_CUDA(cudaFuncSetAttribute(conv1_tc_bwd_kernel<XT, 28>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr = true;
+    }
+    int rc = (H == 28 && W == 28 && !getenv("NM_CONV1_GENERIC"))
+        ? nm::launch_pdl("conv1_tc_bwd", conv1_tc_bwd_kernel<XT, 28>, dim3(grid), dim3(B_THREADS), smem, nm::S(stream), x, scale,
+                         static_cast<const __nv_bfloat16*>(dp_grid), static_cast<const uint8_t*>(idx), static_cast<float*>(workspace), g, L)
+        : nm::launch_pdl("conv1_tc_bwd", conv1_tc_bwd_kernel<XT, 0>, dim3(grid), dim3(B_THREADS), smem, nm::S(stream), x, scale,
+                         static_cast<const __nv_bfloat16*>(dp_grid), static_cast<const uint8_t*>(idx), static_cast<float*>(workspace), g, L);
     if (rc) return rc;
     return nm::launch_pdl("conv1_tc_bwd_reduce", conv1_tc_bwd_reduce_kernel, dim3(nm_cdiv(OC * 10, 32)), dim3(32 * R_SLICES), 0, nm::S(stream),
                           static_cast<const float*>(workspace), dw, db, grid);

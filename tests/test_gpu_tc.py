@@ -379,3 +379,36 @@ def test_tc_conv1_forward_backward(n, integer):
     dw2 = DeviceArray.zeros((32, 1, 3, 3))                                    # deterministic
     lib.nm_tc_conv1_bwd_bf16(xd.p, gd.p, idx.p, dw2.p, db.p, ws.p, ws.nbytes, n, 28, 28, 32, s)
     np.testing.assert_array_equal(dw.numpy(), dw2.numpy())
+
+
+def test_conv1_kernels_are_repeatable_at_batch_4096():
+    """Regression (round 2): the conv1 builders handed their staged-input slot back (mbarrier arrive) right behind the
+    shared-memory loads that read it; the arrive can overtake loads that have been issued but have not returned, and the
+    bulk copy of a later tile then overwrote pixels still to be read -- about one launch in ten at batch 4096 produced
+    ~30 wrong pool windows once the index math in between got cheaper.  The slot is now released only after the loaded
+    values have been consumed into registers.  Many launches into fresh NaN-filled outputs must agree bit for bit."""
+    from neuromah_b200._lib import lib
+    from neuromah_b200.device import DeviceArray, stream
+    n = 4096
+    rng = np.random.default_rng(0)
+    x = rng.random((n, 1, 28, 28), dtype=np.float32)
+    w = (rng.standard_normal((32, 1, 3, 3)) * 0.3).astype(np.float32)
+    wext = DeviceArray((128, 16), np.uint16)
+    lib.nm_tc_pack_conv1_weights_bf16(DeviceArray.from_numpy(w).p, wext.p, 32, stream())
+    xd = DeviceArray.from_numpy(x)
+    dp = DeviceArray.from_numpy(to_bf16_bits(rng.standard_normal((n, 16, 16, 32)).astype(np.float32)))
+    ws = DeviceArray((lib.nm_tc_conv1_bwd_workspace(32),), np.uint8)
+    good = None
+    for rep in range(24):
+        y = DeviceArray.from_numpy(np.full((n, 16, 16, 32), 0x7FC0, np.uint16))
+        idx = DeviceArray.from_numpy(np.full((n, 14, 14, 16), 0xEE, np.uint8))
+        lib.nm_tc_conv1_fwd_pool_bf16(xd.p, wext.p, y.p, idx.p, n, 28, 28, 32, stream())
+        dw, db = DeviceArray.zeros((32, 1, 3, 3)), DeviceArray.zeros((32,))
+        lib.nm_tc_conv1_bwd_bf16(xd.p, dp.p, idx.p, dw.p, db.p, ws.p, ws.nbytes, n, 28, 28, 32, stream())
+        got = (y.numpy()[:, 1:15, 1:15].copy(), idx.numpy().copy(), dw.numpy().copy(), db.numpy().copy())
+        if good is None:
+            good = got
+            assert not (good[0] == 0x7FC0).any() and not (good[1] == 0xEE).any()      # every window was written
+        else:
+            for a, b, what in zip(got, good, ("y", "idx", "dw", "db")):
+                np.testing.assert_array_equal(a, b, err_msg=f"launch {rep}: {what}")
