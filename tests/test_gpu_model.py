@@ -252,7 +252,7 @@ def test_save_and_load_parameters_roundtrip(tmp_path):
     np.testing.assert_array_equal(m1.arena.host_params(), m2.arena.host_params())
 
 
-@pytest.mark.parametrize("case", ["mlp_dropout_rmsprop", "cnn_bf16_adam"])
+@pytest.mark.parametrize("case", ["mlp_dropout_rmsprop", "cnn_bf16_adam", "cnn_bf16x3_adam"])
 def test_save_load_whole_model_resumes_training_identically(tmp_path, case):
     """Model.save / Model.load (Model.py:396-417): the reloaded model carries parameters, optimizer state and iteration
     count, so continuing training on both gives the same parameters."""
@@ -274,7 +274,8 @@ def test_save_load_whole_model_resumes_training_identically(tmp_path, case):
         B = 32
     else:
         spec = ref_net.mnist_cnn_spec()
-        m1 = build(spec, ref_net.init_params(spec, np.random.RandomState(12)), mode="bf16", learning_rate=0.002, decay=1e-3)
+        m1 = build(spec, ref_net.init_params(spec, np.random.RandomState(12)), mode="bf16x3" if "x3" in case else "bf16",
+                   learning_rate=0.002, decay=1e-3)
         x, y = synth(51, 16 * 6, (1, 28, 28))
         B = 16
     for s in range(3):
