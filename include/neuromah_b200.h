@@ -376,6 +376,13 @@ int nm_tc_conv1_fwd_pool_bf16(const float* x, const void* w_ext, void* y_pad, vo
  * bf16(float32(x) / 255) -- the reference's normalisation -- for all 256 pixel values. */
 int nm_tc_conv1_fwd_pool_u8_bf16(const uint8_t* x, float scale, const void* w_ext, void* y_pad, void* idx, int N, int H, int W, int OC,
                                  void* stream);
+/* The same forward with the step's weight re-pack folded in (one launch less on the critical path of every training step):
+ * the B operand is built from the FP32 conv1 weights w1 directly, and two spare warps per CTA refresh the packed copies of
+ * conv2's and the Dense head's weights exactly as nm_tc_pack_cnn_weights_bf16 does.  x: float32, or raw uint8 pixels
+ * (x_is_u8 != 0) normalised by u8_scale. */
+int nm_tc_conv1_fwd_pool_pack_bf16(const void* x, int x_is_u8, float u8_scale, const float* w1, void* y_pad, void* idx, int N, int H, int W,
+                                   int OC, const float* w2, void* w2_fprop, void* w2_dgrad, int OC2, int C2,
+                                   const float* w3, float* w3_packed, void* w3_hilo, int K, int n_out, int HW, int C3, void* stream);
 /* ... and backward: pool backward + ReLU backward (the nibble) + wgrad + bias gradient in one tcgen05 pass
  * (E[(pos,oc)][4x4 patch] accumulated in TMEM, one FP32 partial per CTA, fixed-order reduction).
  * dp_grid = gradient of the pooled output, bf16 on the un-shifted grid [N,H/2+2,W/2+2,OC] (nm_tc_conv3x3_dgrad_bf16). */

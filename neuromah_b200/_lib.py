@@ -125,6 +125,7 @@ _SIGS = {
     "nm_tc_pack_conv1_weights_bf16": (_i, [_vp, _vp, _i, _vp]),
     "nm_tc_conv1_fwd_pool_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "nm_tc_conv1_fwd_pool_u8_bf16": (_i, [_vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "nm_tc_conv1_fwd_pool_pack_bf16": (_i, [_vp, _i, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "nm_tc_conv1_bwd_u8_bf16": (_i, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp]),
     "nm_tc_pack_input_nhwc_u8_bf16": (_i, [_vp, _f, _vp, _i, _i, _i, _i, _i, _vp]),
     "nm_tc_conv1_bwd_workspace": (_sz, [_i]),

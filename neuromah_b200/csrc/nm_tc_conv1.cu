@@ -126,10 +126,21 @@ constexpr int F_NBUF = 4;                       // TMEM accumulators (4 x 128 co
 constexpr int F_XSTAGES = 6;                    // staged-image ring (bulk-copy producer -> builders): hides the HBM latency
 constexpr int F_THREADS = 832;                  // warps 0-7 builders (2 groups), 8 MMA, 9-24 epilogue (4 groups), 25 bulk-copy producer
 
-template <typename XT, int HC>
-__global__ void __launch_bounds__(F_THREADS, 1)
+// PACK: the step's weight re-pack rides in this kernel instead of a launch of its own in front of it (~4 us of every step's
+// critical path): the B tile is built from the FP32 conv1 weights directly, and two spare warps refresh the packed copies of
+// conv2's and the Dense head's weights (69 k elements over the grid) while the first tiles are computed.  Their consumers are
+// later kernels of the stream; their previous readers belong to the step before.
+struct Conv1Pack {
+    const float* w1;                                                     // conv1 [32][1][3][3]
+    const float* w2; __nv_bfloat16* wf; __nv_bfloat16* wd; int OC2, C2;  // conv2 OIHW -> fprop / dgrad operands
+    const float* w3; float* wp; __nv_bfloat16* whl; int K, n_out, HW, C3;    // Dense (c,h,w) rows -> packed FP32 + hi/lo
+};
+constexpr int F_PACK_WARPS = 2;
+
+template <typename XT, int HC, bool PACK>
+__global__ void __launch_bounds__(F_THREADS + (PACK ? 32 * F_PACK_WARPS : 0), 1)
 conv1_tc_fwd_kernel(const XT* __restrict__ x, float x_scale, const __nv_bfloat16* __restrict__ wext, __nv_bfloat16* __restrict__ y_pad,
-                    uint8_t* __restrict__ idx, Conv1Geom Gp, int x_stage_bytes) {
+                    uint8_t* __restrict__ idx, Conv1Geom Gp, int x_stage_bytes, Conv1Pack pk) {
     const GeomView<HC> G{Gp, Gp.total, Gp.num_tiles};
     constexpr uint64_t TMPL = desc_template(16, 512, LAYOUT_SW64);
     constexpr uint32_t IDESC = idesc_bf16(128, 128, 0, 0);
@@ -159,7 +170,15 @@ conv1_tc_fwd_kernel(const XT* __restrict__ x, float x_scale, const __nv_bfloat16
     // Wext [128 (pos,oc)][16] bf16 -> B tile
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         const int row = i >> 1, c = i & 1;
-        *reinterpret_cast<uint4*>(b_smem + sw64(row, c * 16)) = __ldg(reinterpret_cast<const uint4*>(wext + row * 16 + c * 8));
+        if constexpr (PACK) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = tcpack::conv1_value(row * 16 + c * 8 + j, pk.w1);
+            *reinterpret_cast<uint4*>(b_smem + sw64(row, c * 16)) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        } else {
+            *reinterpret_cast<uint4*>(b_smem + sw64(row, c * 16)) = __ldg(reinterpret_cast<const uint4*>(wext + row * 16 + c * 8));
+        }
     }
     fence_proxy_async();
     fence_before_sync();
@@ -303,6 +322,11 @@ conv1_tc_fwd_kernel(const XT* __restrict__ x, float x_scale, const __nv_bfloat16
             }
             if (lane == 0 && q == 0 && half == 0) NM_TRACE(G, tile, 6);
         }
+    } else if (PACK && warp >= 26) {
+        // ============================== weight re-pack for the later kernels of the step ========
+        const int t = blockIdx.x * (32 * F_PACK_WARPS) + ((int)threadIdx.x - 26 * 32), T = gridDim.x * (32 * F_PACK_WARPS);
+        for (int i = t; i < pk.OC2 * pk.C2 * 9; i += T) tcpack::conv3x3_elem(i, pk.w2, pk.wf, pk.wd, pk.OC2, pk.C2);
+        for (int i = t; i < pk.K * 16; i += T) tcpack::dense_elem(i, pk.w3, pk.wp, pk.whl, pk.K, pk.n_out, pk.HW, pk.C3);
     }
     fence_before_sync();
     __syncthreads();
@@ -587,9 +611,21 @@ int geom(Conv1Geom* g, int N, int H, int W) {
 
 }  // namespace
 
+template <typename XT, int HC, bool PACK>
+static int conv1_fwd_launch_k(const XT* x, float scale, const void* w_ext, void* y_pad, void* idx, const Conv1Geom& g, int x_stage, size_t smem,
+                              const Conv1Pack& pk, void* stream) {
+    static bool attr = false;
+    if (!attr) { NM_CUDA(cudaFuncSetAttribute(conv1_tc_fwd_kernel<XT, HC, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    const int grid = g.num_tiles < sm_count() ? g.num_tiles : sm_count();
+    return nm::launch_pdl(PACK ? "conv1_tc_fwd_pack" : "conv1_tc_fwd", conv1_tc_fwd_kernel<XT, HC, PACK>, dim3(grid),
+                          dim3(F_THREADS + (PACK ? 32 * F_PACK_WARPS : 0)), smem, nm::S(stream), x, scale,
+                          static_cast<const __nv_bfloat16*>(w_ext), static_cast<__nv_bfloat16*>(y_pad), static_cast<uint8_t*>(idx), g, x_stage, pk);
+}
+
 template <typename XT>
-static int conv1_fwd_launch(const XT* x, float scale, const void* w_ext, void* y_pad, void* idx, int N, int H, int W, int OCn, void* stream) {
-    NM_REQUIRE(x && w_ext && y_pad && idx, "null pointer");
+static int conv1_fwd_launch(const XT* x, float scale, const void* w_ext, void* y_pad, void* idx, int N, int H, int W, int OCn, void* stream,
+                            const Conv1Pack* pack = nullptr) {
+    NM_REQUIRE(x && (w_ext || pack) && y_pad && idx, "null pointer");
     NM_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "bad dimensions");
     NM_REQUIRE((H * W * sizeof(XT)) % 16 == 0, "an image must be a multiple of 16 bytes (bulk copies)");
     if (OCn != OC) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_fwd_pool: only OC=32 is instantiated");
@@ -599,18 +635,13 @@ static int conv1_fwd_launch(const XT* x, float scale, const void* w_ext, void* y
     const int x_stage = (2 * H * W * (int)sizeof(XT) + 127) & ~127;
     const size_t smem = (size_t)(1 + F_STAGES) * F_TILE_BYTES + (size_t)F_XSTAGES * x_stage + 256;
     if (smem > 200 * 1024) return nm::fail(NM_ERR_UNSUPPORTED, "%s%s", "nm_tc_conv1_fwd_pool: image too large for the staged-image ring");
-    static bool attr = false;
-    if (!attr) {
-        NM_CUDA(cudaFuncSetAttribute(conv1_tc_fwd_kernel<XT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        NM_CUDA(cudaFuncSetAttribute(conv1_tc_fwd_kernel<XT, 28>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
-    }
-    const int grid = g.num_tiles < sm_count() ? g.num_tiles : sm_count();
-    if (H == 28 && W == 28 && !getenv("NM_CONV1_GENERIC"))      // MNIST geometry: compile-time index math (the variable: A/B debugging)
-        return nm::launch_pdl("conv1_tc_fwd", conv1_tc_fwd_kernel<XT, 28>, dim3(grid), dim3(F_THREADS), smem, nm::S(stream), x, scale,
-                              static_cast<const __nv_bfloat16*>(w_ext), static_cast<__nv_bfloat16*>(y_pad), static_cast<uint8_t*>(idx), g, x_stage);
-    return nm::launch_pdl("conv1_tc_fwd", conv1_tc_fwd_kernel<XT, 0>, dim3(grid), dim3(F_THREADS), smem, nm::S(stream), x, scale,
-                          static_cast<const __nv_bfloat16*>(w_ext), static_cast<__nv_bfloat16*>(y_pad), static_cast<uint8_t*>(idx), g, x_stage);
+    const bool k28 = H == 28 && W == 28 && !getenv("NM_CONV1_GENERIC");      // MNIST geometry: compile-time index math (the variable: A/B debugging)
+    const Conv1Pack none{};
+    if (pack)
+        return k28 ? conv1_fwd_launch_k<XT, 28, true>(x, scale, w_ext, y_pad, idx, g, x_stage, smem, *pack, stream)
+                   : conv1_fwd_launch_k<XT, 0, true>(x, scale, w_ext, y_pad, idx, g, x_stage, smem, *pack, stream);
+    return k28 ? conv1_fwd_launch_k<XT, 28, false>(x, scale, w_ext, y_pad, idx, g, x_stage, smem, none, stream)
+               : conv1_fwd_launch_k<XT, 0, false>(x, scale, w_ext, y_pad, idx, g, x_stage, smem, none, stream);
 }
 
 template <typename XT>
@@ -663,6 +694,20 @@ int nm_tc_conv1_fwd_pool_bf16(const float* x, const void* w_ext, void* y_pad, vo
 int nm_tc_conv1_fwd_pool_u8_bf16(const uint8_t* x, float scale, const void* w_ext, void* y_pad, void* idx, int N, int H, int W, int OCn,
                                  void* stream) {
     return conv1_fwd_launch<uint8_t>(x, scale, w_ext, y_pad, idx, N, H, W, OCn, stream);
+}
+
+// conv1 forward + the step's weight re-pack in ONE launch (x: float32, or raw uint8 pixels * u8_scale when x_is_u8): the B tile
+// comes from the FP32 conv1 weights w1, and the packed copies of conv2's (w2 -> w2_fprop / w2_dgrad) and the Dense head's
+// (w3 -> w3_packed / w3_hilo) weights are refreshed as by nm_tc_pack_cnn_weights_bf16
+int nm_tc_conv1_fwd_pool_pack_bf16(const void* x, int x_is_u8, float u8_scale, const float* w1, void* y_pad, void* idx, int N, int H, int W, int OCn,
+                                   const float* w2, void* w2_fprop, void* w2_dgrad, int OC2, int C2,
+                                   const float* w3, float* w3_packed, void* w3_hilo, int K, int n_out, int HW, int C3, void* stream) {
+    NM_REQUIRE(w1 && w2 && (w2_fprop || w2_dgrad) && w3 && (w3_packed || w3_hilo), "null pointer");
+    NM_REQUIRE(OC2 > 0 && C2 > 0 && K > 0 && n_out > 0 && n_out <= 16 && HW * C3 == K, "bad dimensions");
+    const Conv1Pack pk{w1, w2, static_cast<__nv_bfloat16*>(w2_fprop), static_cast<__nv_bfloat16*>(w2_dgrad), OC2, C2,
+                       w3, w3_packed, static_cast<__nv_bfloat16*>(w3_hilo), K, n_out, HW, C3};
+    if (x_is_u8) return conv1_fwd_launch<uint8_t>(static_cast<const uint8_t*>(x), u8_scale, nullptr, y_pad, idx, N, H, W, OCn, stream, &pk);
+    return conv1_fwd_launch<float>(static_cast<const float*>(x), 1.f, nullptr, y_pad, idx, N, H, W, OCn, stream, &pk);
 }
 
 size_t nm_tc_conv1_bwd_workspace(int OCn) { (void)OCn; return (size_t)B_MAX_GRID * 128 * 32 * sizeof(float); }

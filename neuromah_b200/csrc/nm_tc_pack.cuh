@@ -7,11 +7,13 @@
 namespace tcpack {
 
 // conv1 [OC=32][1][3][3] -> Wext[(dy,dx,oc)][a*4+b] = W[oc][a-dy][b-dx] inside the 3x3 support, else 0   (i < 128*16)
-__device__ __forceinline__ void conv1_elem(int i, const float* __restrict__ w, __nv_bfloat16* __restrict__ wext) {
+__device__ __forceinline__ float conv1_value(int i, const float* __restrict__ w) {
     const int row = i >> 4, k = i & 15, pos = row >> 5, oc = row & 31, a = k >> 2, b = k & 3;
     const int r = a - (pos >> 1), s = b - (pos & 1);
-    const float v = ((unsigned)r < 3u && (unsigned)s < 3u) ? w[oc * 9 + r * 3 + s] : 0.f;
-    wext[i] = __float2bfloat16(v);
+    return ((unsigned)r < 3u && (unsigned)s < 3u) ? w[oc * 9 + r * 3 + s] : 0.f;
+}
+__device__ __forceinline__ void conv1_elem(int i, const float* __restrict__ w, __nv_bfloat16* __restrict__ wext) {
+    wext[i] = __float2bfloat16(conv1_value(i, w));
 }
 
 // OIHW f32 -> bf16 [OC][tap][C] (fprop B operand) and [C][8-tap][OC] (dgrad B operand)                    (i < OC*C*9)

@@ -59,6 +59,7 @@ class Bf16Activation:
 
 
 class TcCnnPlan:
+    fused_pack = True       # weight re-pack inside the conv1 forward kernel (False: the separate nm_tc_pack_cnn_weights_bf16 launch)
     PATTERN = "Conv2D(1->32,3x3,same,ReLU) Pool(2,2) Conv2D(32->64,3x3,same,ReLU) Pool(2,2) Flatten Dense(->n<=16) Softmax"
 
     @staticmethod
@@ -158,11 +159,20 @@ class TcCnnPlan:
         self._ensure(B, x.shape[2], x.shape[3])
         s = stream()
         self.x = x
-        self.pack_weights()          # master weights may have changed (optimizer, set_parameters, FedAvg)
-        if x.dtype == np.uint8:       # raw pixels: normalised by 1 / uint8_denominator inside the patch builder
-            _timed('tc_conv1_fwd_pool', lib.nm_tc_conv1_fwd_pool_u8_bf16, x.p, self._u8_scale(), self.w1e.p, self.act1_pad.p, self.idx1.p, B, 28, 28, 32, s)
+        # The master weights may have changed (optimizer, set_parameters, FedAvg): every packed operand copy is refreshed
+        # per forward pass -- inside the conv1 kernel (its B tile comes from the FP32 weights, two spare warps re-pack conv2's
+        # and the Dense head's), which takes the separate pack launch off the critical path of the step.
+        u8 = x.dtype == np.uint8       # raw pixels: normalised by 1 / uint8_denominator inside the patch builder
+        if self.fused_pack and self.w3p is not None:
+            _timed('tc_conv1_fwd_pool', lib.nm_tc_conv1_fwd_pool_pack_bf16, x.p, int(u8), self._u8_scale() if u8 else 1.0, self.c1.weights.p,
+                   self.act1_pad.p, self.idx1.p, B, 28, 28, 32, self.c2.weights.p, self.w2f.p, self.w2d.p, 64, 32,
+                   self.de.weights.p, self.w3p.p, self.w3hl.p, self.K, self.n_out, 49, 64, s)
         else:
-            _timed('tc_conv1_fwd_pool', lib.nm_tc_conv1_fwd_pool_bf16, x.p, self.w1e.p, self.act1_pad.p, self.idx1.p, B, 28, 28, 32, s)
+            self.pack_weights()
+            if u8:
+                _timed('tc_conv1_fwd_pool', lib.nm_tc_conv1_fwd_pool_u8_bf16, x.p, self._u8_scale(), self.w1e.p, self.act1_pad.p, self.idx1.p, B, 28, 28, 32, s)
+            else:
+                _timed('tc_conv1_fwd_pool', lib.nm_tc_conv1_fwd_pool_bf16, x.p, self.w1e.p, self.act1_pad.p, self.idx1.p, B, 28, 28, 32, s)
         _timed('tc_conv2_fprop_pool', lib.nm_tc_conv3x3_fprop_pool_bf16, self.act1_pad.p, self.w2f.p, self.act2.p, self.idx2.p, B, 14, 14, 32, 64, 0, s)
         lab = labels if labels is not None else self.dummy_labels
         _timed('tc_dense_softmax_ce', lib.nm_tc_dense_softmax_ce_bf16, self.act2.p, self.w3hl.p, self.de.biases.p, lab.p,

@@ -313,3 +313,26 @@ def test_uint8_pixel_input_equals_host_normalised_float_input(mode):
     # already replays a graph; the two paths share kernels and double-precision hyper-parameter formulas
     np.testing.assert_allclose(runs["u8_stream"][0], runs["f32"][0], rtol=1e-4, atol=2e-5)
     assert abs(runs["u8_stream"][1] - runs["f32"][1]) < 1e-4
+
+
+def test_fused_weight_repack_equals_the_separate_pack_launch():
+    """The conv1 forward kernel re-packs the step's operand copies itself (TcCnnPlan.fused_pack): same packed tensors, same
+    training run bit for bit as with the separate nm_tc_pack_cnn_weights_bf16 launch, float32 and uint8 inputs."""
+    from neuromah_b200.tc_plan import TcCnnPlan
+    spec = ref_net.mnist_cnn_spec()
+    params = ref_net.init_params(spec, np.random.RandomState(4), init="he")
+    rng = np.random.default_rng(6)
+    xu = rng.integers(0, 256, (3 * 256, 1, 28, 28)).astype(np.uint8)
+    y = np.eye(10)[rng.integers(0, 10, len(xu))]
+    for xin in (xu.astype(np.float32) / np.float32(255.0), xu):
+        runs = []
+        for fused in (True, False):
+            TcCnnPlan.fused_pack = fused
+            try:
+                m = build(spec, params, mode="bf16", learning_rate=0.002)
+                m.train(xin, y, epochs=2, batch_size=256, verbose=0)
+            finally:
+                TcCnnPlan.fused_pack = True
+            runs.append((m.arena.host_params(), m.plan.w2f.numpy(), m.plan.w2d.numpy(), m.plan.w3hl.numpy(), m.plan.w3p.numpy()))
+        for a, b in zip(*runs):
+            np.testing.assert_array_equal(a, b)
