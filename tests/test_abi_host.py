@@ -202,3 +202,53 @@ def test_checkpoint_format_is_guarded(tmp_path):
         pickle.dump({"format": "something else"}, f)
     with pytest.raises(ValueError):
         checkpoint.load(str(p))
+
+
+def _header_prototypes():
+    """name -> (return kind, [argument kinds]) parsed from include/neuromah_b200.h; kinds: ptr, int, uint, float, double,
+    size_t, llong, ullong."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(neuromah_b200.__file__)))
+    text = open(os.path.join(root, "include", "neuromah_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+
+    def kind(decl):
+        d = " ".join(decl.replace("const", " ").split())
+        if "*" in d:
+            return "ptr"
+        words = d.split()
+        words = words[:-1] if len(words) > 1 and words[-1] not in ("int", "long", "float", "double", "size_t", "unsigned") else words
+        t = " ".join(words)
+        return {"int": "int", "unsigned": "uint", "unsigned int": "uint", "float": "float", "double": "double", "size_t": "size_t",
+                "long long": "llong", "unsigned long long": "ullong"}[t]
+    out = {}
+    for m in re.finditer(r"([A-Za-z_][\w \*]*?)\b(nm_\w+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        arglist = [] if args in ("", "void") else [kind(a) for a in args.split(",")]
+        out[name] = ("ptr" if "*" in ret else kind(ret + " x"), arglist)
+    return out
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/neuromah_b200.h against the hand-written ctypes table: same argument count, and the same
+    kind of C type in every position (a drifted signature corrupts the call silently)."""
+    import ctypes as C
+    protos = _header_prototypes()
+    assert set(protos) == set(_SIGS)
+
+    def ckind(t):
+        if t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return "ptr"
+        return {C.c_int: "int", C.c_uint: "uint", C.c_float: "float", C.c_double: "double", C.c_size_t: "size_t",
+                C.c_longlong: "llong", C.c_ulonglong: "ullong"}[t]
+    bad = []
+    same = {"size_t": "u64", "ullong": "u64", "llong": "i64"}        # ctypes aliases the 64-bit integer types on LP64
+    norm = lambda k: same.get(k, k)
+    for name, (ret, args) in protos.items():
+        res, argtypes = _SIGS[name]
+        got = (norm(ckind(res)), [norm(ckind(a)) for a in argtypes])
+        ret, args = norm(ret), [norm(a) for a in args]
+        if got != (ret, args):
+            bad.append((name, (ret, args), got))
+    assert not bad, bad
