@@ -71,7 +71,7 @@ def _rup_in(c):
 
 class TcStackPlan:
     PATTERN = ("(Conv2D(3x3,same,ReLU) x k -> MaxPooling2D(2,2)) x m -> Flatten -> Dense(-> n <= 16) -> Softmax "
-               "(out_channels of the last conv % 64 == 0)")
+               "(mode 'bf16': out_channels of the last conv % 64 == 0; any width in mode 'bf16x3')")
 
     # ------------------------------------------------------------------ pattern ----
     @staticmethod
