@@ -753,6 +753,11 @@ def main():
                 "peak_source": pk["source"] + ((" bf16 dense burst (cuBLAS)" if region_s < 1.0 else " bf16 dense sustained (cuBLAS)")
                                                if bound == "tensor" else " HBM copy"),
                 "kernels": per_kernel}
+    if world > 1 and not fed:
+        # the instrumented pass is eager: the exchange's push kernel (side stream, behind conv2's wgrad) then shares the SMs
+        # with whichever kernel the compute stream runs next, and that kernel's event pair absorbs the wait
+        roofline["note"] = ("per-kernel times at N > 1 are taken while the gradient push runs beside the backward kernels "
+                            "(tc_conv1_bwd's event pair absorbs the contention); the N = 1 line has the kernels timed alone")
     line = {"metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (three bf16 planes per operand, FP32-exact)"}.get(args.mode, "f32"), "data": "synthetic",
