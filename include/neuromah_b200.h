@@ -152,6 +152,28 @@ int nm_softmax_ce_f32(const float* probs, const int32_t* labels, float* dlogits,
 int nm_cce_bwd_f32(const float* probs, const int32_t* labels, float* dx,
                    int B, int n, float inv_batch, void* stream);
 
+/* Activation_Sigmoid.forward / backward (src/activations/Sigmoid.py:5-10): y = 1 / (1 + exp(-x));
+ * dx = dy * (1 - out) * out with `out` the forward output. */
+int nm_sigmoid_fwd_f32(const float* x, float* y, size_t n, void* stream);
+int nm_sigmoid_bwd_f32(const float* dy, const float* out, float* dx, size_t n, void* stream);
+
+/* The element-wise losses of src/losses: Loss_MeanSquaredError (MSE.py:10-28), Loss_MeanAbsoluteError
+ * (MAE.py:11-28), Loss_BinaryCrossentropy (binary_crossentropy.py:9-33).  pred / target are [B, D]
+ * (every non-batch dimension flattened into D).
+ * forward: sample_loss[b] = mean over D of (t - p)^2 | |t - p| | -(t log p' + (1 - t) log(1 - p')),
+ *          p' = clip(p, 1e-7, 1 - 1e-7); one warp per sample, fixed reduction order.
+ * backward: dx = -2 (t - p) / D | sign(t - p) / D (the reference's sign, MAE.py:23) |
+ *          -(t / p' - (1 - t) / (1 - p')) / D.  As in the reference the gradient is divided by the
+ *          outputs per sample only (prod(shape) / samples), NOT by the batch: Layer_Dense.backward
+ *          applies the 1 / batch (Dense.py:96-98). */
+#define NM_LOSS_MSE 0
+#define NM_LOSS_MAE 1
+#define NM_LOSS_BCE 2
+int nm_loss_fwd_f32(int kind, const float* pred, const float* target, float* sample_loss,
+                    int B, int D, void* stream);
+int nm_loss_bwd_f32(int kind, const float* pred, const float* target, float* dx,
+                    int B, int D, void* stream);
+
 /* ---- optimizers over a flat FP32 slab ------------------------------------ */
 /* Optimizer_Adam.update_params (Adam.py:86-100) applied n_apply times in registers
  * with the same t (Model registers every trainable layer twice: Model.py:56-59,:82-83).

@@ -67,6 +67,10 @@ _SIGS = {
     "nm_softmax_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "nm_softmax_ce_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "nm_cce_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp]),
+    "nm_sigmoid_fwd_f32": (_i, [_vp, _vp, _sz, _vp]),
+    "nm_sigmoid_bwd_f32": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "nm_loss_fwd_f32": (_i, [_i, _vp, _vp, _vp, _i, _i, _vp]),
+    "nm_loss_bwd_f32": (_i, [_i, _vp, _vp, _vp, _i, _i, _vp]),
     "nm_adam_step_f32": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _f, _i, _vp]),
     "nm_adam_state_init": (_i, [_vp, C.c_double, C.c_double, C.c_double, C.c_double, _f, C.c_longlong, _vp]),
     "nm_adam_step_dev_f32": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),

@@ -236,6 +236,47 @@ def cce_bwd(probs: DeviceArray, labels: DeviceArray, holder=None):
     return dx
 
 
+# ------------------------------------------------ sigmoid / element-wise losses ----
+def sigmoid_fwd(x: DeviceArray, holder=None, name="_y"):
+    y = _buf(holder, name, x.shape)
+    lib.nm_sigmoid_fwd_f32(x.p, y.p, x.size, stream())
+    return y
+
+
+def sigmoid_bwd(dy: DeviceArray, out: DeviceArray, holder=None, name="_dx"):
+    dx = _buf(holder, name, dy.shape)
+    lib.nm_sigmoid_bwd_f32(dy.p, out.p, dx.p, dy.size, stream())
+    return dx
+
+
+LOSS_MSE, LOSS_MAE, LOSS_BCE = 0, 1, 2        # NM_LOSS_* of include/neuromah_b200.h
+
+
+def _loss_dims(pred: DeviceArray, target: DeviceArray):
+    if pred.ndim < 2:
+        raise ValueError("loss inputs must be (batch, ...) arrays")
+    if target.shape != pred.shape:
+        raise ValueError(f"operands could not be broadcast together with shapes {target.shape} {pred.shape}")
+    bsz = pred.shape[0]
+    return bsz, pred.size // bsz
+
+
+def loss_fwd(kind: int, pred: DeviceArray, target: DeviceArray, holder=None):
+    """Per-sample mean over the non-batch dimensions of the MSE / MAE / BCE terms."""
+    bsz, d = _loss_dims(pred, target)
+    losses = _buf(holder, "_sample_losses", (bsz,))
+    lib.nm_loss_fwd_f32(kind, pred.p, target.p, losses.p, bsz, d, stream())
+    return losses
+
+
+def loss_bwd(kind: int, pred: DeviceArray, target: DeviceArray, holder=None):
+    """Gradient of the per-sample mean with respect to the predictions (divided by the outputs per sample only)."""
+    bsz, d = _loss_dims(pred, target)
+    dx = _buf(holder, "_dx", pred.shape)
+    lib.nm_loss_bwd_f32(kind, pred.p, target.p, dx.p, bsz, d, stream())
+    return dx
+
+
 # ------------------------------------------------------------- optimizers ----
 def adam_step(p: DeviceArray, g: DeviceArray, m: DeviceArray, v: DeviceArray, *, lr, beta_1, beta_2, eps, t,
               n_apply=1, count=None):

@@ -22,10 +22,9 @@ class Accuracy:
     def calculate(self, predictions, y):
         """Fraction of hits in this batch; also folded into the running totals of the pass."""
         hits = np.asarray(self.compare(np.asarray(predictions), np.asarray(y)))
-        n_hits, n = hits.sum(), len(hits)
-        self.accumulated_sum += n_hits
-        self.accumulated_count += n
-        return n_hits / n
+        self.accumulated_sum += hits.sum()
+        self.accumulated_count += len(hits)        # samples, also when a sample has several outputs (Accuracy.py:22)
+        return hits.mean()                         # over every compared element (Accuracy.py:20)
 
     def calculate_accumulated(self):
         return self.accumulated_sum / self.accumulated_count

@@ -252,6 +252,8 @@ class Model:
 
     def train_step(self, batch_X, batch_y):
         """One step of Model.train's loop body with device-side loss/accuracy sums."""
+        if not self._fast_path_ok():
+            return self._generic_step(batch_X, batch_y)
         labels = labels_to_device(batch_y)
         if self._graph_ok() and isinstance(batch_X, DeviceArray):
             out = self._graph_train_step(batch_X, labels)
@@ -371,6 +373,21 @@ class Model:
         if self.tensorMonitor:
             self.tensorMonitor.save_logs()
 
+    def _generic_step(self, batch_X, batch_y):
+        """Model.py:154-174 for ANY loss / output activation (MSE, MAE, binary cross-entropy, a softmax without the
+        fused gradient, ...): the layers, the loss and its gradient run on the device, the per-sample losses and the
+        predictions are reduced on the host as the reference does."""
+        output = self.forward(batch_X, training=True)
+        losses = self.loss.calculate(output, batch_y, include_regularization=True)
+        predictions = self.output_layer_activation.predictions(output)
+        acc = self.accuracy.calculate(predictions, batch_y)
+        self.last_step = {"loss": float(losses["data_loss"]), "acc": float(acc)}
+        self.backward(output, batch_y)
+        if self.comm is not None:
+            self.comm.allreduce_grads(self.arena)
+        self._optimizer_step()
+        return output
+
     def _train_generic(self, X, y, *, epochs, batch_size, verbose, validation_data):
         """The reference's loop verbatim in structure (any loss / last layer); host-side sums."""
         train_steps = self._steps(len(X), batch_size)
@@ -380,15 +397,7 @@ class Model:
             self.accuracy.new_pass()
             for step in range(train_steps):
                 sl = slice(None) if batch_size is None else slice(step * batch_size, (step + 1) * batch_size)
-                batch_X, batch_y = X[sl], y[sl]
-                output = self.forward(batch_X, training=True)
-                self.loss.calculate(output, batch_y, include_regularization=True)
-                predictions = self.output_layer_activation.predictions(output)
-                self.accuracy.calculate(predictions, batch_y)
-                self.backward(output, batch_y)
-                if self.comm is not None:
-                    self.comm.allreduce_grads(self.arena)
-                self._optimizer_step()
+                self._generic_step(X[sl], y[sl])
             epoch_time = time.time() - start_time
             losses = self.loss.calculate_accumulated(include_regularization=True)
             output = self.forward(X, training=False)

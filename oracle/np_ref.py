@@ -317,6 +317,71 @@ def accuracy_categorical(probs, y_true):
     return float(np.mean(np.argmax(probs, axis=1) == y_true))
 
 
+def sigmoid_forward(x):
+    """src/activations/Sigmoid.py:5-7."""
+    return 1 / (1 + np.exp(-x))
+
+
+def sigmoid_backward(out, dvalues):
+    """dvalues * (1 - out) * out on the forward OUTPUT, src/activations/Sigmoid.py:9-10."""
+    return dvalues * (1 - out) * out
+
+
+def sigmoid_predictions(out):
+    """Threshold at 0.5, src/activations/Sigmoid.py:12-14."""
+    return (out > 0.5) * 1
+
+
+def _per_sample_mean(terms):
+    return np.mean(terms, axis=tuple(range(1, terms.ndim)))
+
+
+def mse_forward(y_pred, y_true):
+    """Per-sample mean of (y - p)^2 over the non-batch axes, src/losses/MSE.py:10-14."""
+    return _per_sample_mean((y_true - y_pred) ** 2)
+
+
+def mse_backward(dvalues, y_true):
+    """-2 (y - p) / (prod(shape) / samples): NOT divided by the batch, src/losses/MSE.py:17-28."""
+    return -2 * (y_true - dvalues) / (np.prod(dvalues.shape) / len(dvalues))
+
+
+def mae_forward(y_pred, y_true):
+    """Per-sample mean of |y - p|, src/losses/MAE.py:11-14."""
+    return _per_sample_mean(np.abs(y_true - y_pred))
+
+
+def mae_backward(dvalues, y_true):
+    """sign(y - p) / (prod(shape) / samples) -- the reference's sign, as shipped, src/losses/MAE.py:17-28."""
+    return np.sign(y_true - dvalues) / (np.prod(dvalues.shape) / len(dvalues))
+
+
+def bce_forward(y_pred, y_true):
+    """Per-sample mean of -(y log p + (1 - y) log(1 - p)), p clipped to [1e-7, 1 - 1e-7],
+    src/losses/binary_crossentropy.py:9-18."""
+    p = np.clip(y_pred, 1e-7, 1 - 1e-7)
+    return _per_sample_mean(-(y_true * np.log(p) + (1 - y_true) * np.log(1 - p)))
+
+
+def bce_backward(dvalues, y_true):
+    """-(y / p - (1 - y) / (1 - p)) / (prod(shape) / samples) on the clipped predictions,
+    src/losses/binary_crossentropy.py:20-33."""
+    p = np.clip(dvalues, 1e-7, 1 - 1e-7)
+    return -(y_true / p - (1 - y_true) / (1 - p)) / (np.prod(dvalues.shape) / len(dvalues))
+
+
+def accuracy_regression_precision(y):
+    """std(y) / 250, src/metrics/Accuracy_Regression.py:10-12."""
+    return np.std(y) / 250
+
+
+def accuracy_elementwise(hits):
+    """Accuracy.calculate (src/core/Accuracy.py:19-23): the batch value is the mean over EVERY compared element,
+    the running sum counts elements but the running count counts samples."""
+    hits = np.asarray(hits)
+    return float(np.mean(hits)), float(np.sum(hits)), len(hits)
+
+
 # ----------------------------------------------------------------------------
 # Optimizers
 # ----------------------------------------------------------------------------

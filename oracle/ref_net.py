@@ -20,6 +20,8 @@ Layer specs (dicts):
   {"kind": "dense", "n_in":, "n_out":, "relu": bool, "l1": 0.0, "l2": 0.0}
   {"kind": "softmax"}                (must be last; fused softmax-CE backward,
                                       Model.py:106-109, :339-356)
+  {"kind": "sigmoid"} / {"kind": "linear"}   (last, with ``loss="bce" | "mse" | "mae"``: the generic
+                                      loss.backward path, Model.py:362-366)
 """
 from __future__ import annotations
 
@@ -109,8 +111,10 @@ class RefNet:
     def __init__(self, spec, params, *, optimizer="adam", lr=0.001, decay=0.0,
                  eps=1e-7, beta_1=0.9, beta_2=0.999, momentum=0.0,
                  n_apply=2, conv_backward="wired", conv_bias=False,
-                 first_layer_dinputs=True, use_ref_pool=True):
+                 first_layer_dinputs=True, use_ref_pool=True, loss="cce"):
         self.spec = spec
+        self.loss = loss                # "cce" (fused with a final softmax) | "mse" | "mae" | "bce" (generic path, Model.py:362-366)
+        self.precision = None           # Accuracy_Regression.precision, set by init_accuracy(y)
         self.params = [None if p is None else {k: np.array(v, dtype=np.float64, copy=True)
                                                for k, v in p.items()} for p in params]
         self.opt = dict(kind=optimizer, lr=lr, decay=decay, eps=eps, beta_1=beta_1,
@@ -158,6 +162,11 @@ class RefNet:
             elif k == "softmax":
                 self.cache.append((a,))
                 a = R.softmax_forward(a)
+            elif k == "sigmoid":
+                self.cache.append((a,))
+                a = R.sigmoid_forward(a)
+            elif k == "linear":
+                self.cache.append((a,))                 # Activation_Linear.forward: output = inputs (Linear.py:5-7)
             elif k == "dropout":
                 # Dropout.py:21-30; the mask (Bernoulli(keep)/keep) is supplied by the caller: self.dropout_masks[layer index]
                 mask = self.dropout_masks[len(self.cache)] if training else None
@@ -172,8 +181,15 @@ class RefNet:
     # -- backward -----------------------------------------------------------
     def backward(self, output, y, *, global_batch=None):
         spec = self.spec
-        assert spec[-1]["kind"] == "softmax", "fused softmax-CE path only"
-        d = R.softmax_cce_backward(output, y, batch=global_batch)      # Model.py:339-348
+        last = spec[-1]["kind"]
+        if self.loss == "cce":
+            assert last == "softmax", "fused softmax-CE path only"
+            d = R.softmax_cce_backward(output, y, batch=global_batch)  # Model.py:339-348
+        else:
+            # generic path (Model.py:362-366): loss.backward, then every layer in reverse -- the output activation first
+            assert global_batch is None and last in ("sigmoid", "linear")
+            d = {"mse": R.mse_backward, "mae": R.mae_backward, "bce": R.bce_backward}[self.loss](output, y)
+            d = R.sigmoid_backward(output, d) if last == "sigmoid" else d.copy()
         self.dinputs[len(spec) - 1] = d
         for i in range(len(spec) - 2, -1, -1):                         # Model.py:353-354
             L, p, c = spec[i], self.params[i], self.cache[i]
@@ -251,13 +267,26 @@ class RefNet:
     # -- one Model.train step -------------------------------------------------
     def step(self, x, y, *, global_batch=None, update=True):
         out = self.forward(x, training=True)
-        losses = R.cce_forward(out, y)
+        if self.loss == "cce":
+            losses = R.cce_forward(out, y)
+            acc = R.accuracy_categorical(out, y)
+        else:
+            losses = {"mse": R.mse_forward, "mae": R.mae_forward, "bce": R.bce_forward}[self.loss](out, y)
+            if self.spec[-1]["kind"] == "sigmoid":          # Accuracy_Categorical(binary=True) on Sigmoid.predictions
+                hits = R.sigmoid_predictions(out) == y
+            else:                                           # Accuracy_Regression on Linear.predictions
+                hits = np.absolute(out - y) < self.precision
+            acc = R.accuracy_elementwise(hits)[0]
         loss = float(np.mean(losses))
-        acc = R.accuracy_categorical(out, y)
         self.backward(out, y, global_batch=global_batch)
         if update:
             self.update()
         return {"loss": loss, "loss_sum": float(np.sum(losses)), "acc": acc, "output": out}
+
+    def init_accuracy(self, y):
+        """Accuracy_Regression.init (Accuracy_Regression.py:10-12); Model.train calls it before the first epoch (:119)."""
+        if self.precision is None:
+            self.precision = R.accuracy_regression_precision(y)
 
     # -- flat views (arena order: per trainable layer, weights then biases) --
     def flat(self, what="params"):

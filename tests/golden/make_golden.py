@@ -280,9 +280,69 @@ def ops():
     np.savez_compressed(os.path.join(HERE, "ops.npz"), **out)
 
 
+def losses_family():
+    """The other output activations / losses of the Model.train step, from the UNMODIFIED reference classes:
+    Activation_Sigmoid / Activation_Linear, Loss_MeanSquaredError / MeanAbsoluteError / BinaryCrossentropy,
+    Accuracy_Regression / Accuracy_Categorical(binary=True).  Per-op vectors on the operands of
+    tests/conftest.py::losses_family_inputs and three small models (conftest.LOSSES_FAMILY_CASES) stepped exactly as
+    Model.train does (batch 32)."""
+    ref_shim.load()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import LOSSES_FAMILY_CASES, losses_family_case, losses_family_inputs
+    from NeuromahRef.src.core import Model
+    from NeuromahRef.src.layers import Layer_Dense
+    from NeuromahRef.src.activations import Activation_ReLU, Activation_Sigmoid, Activation_Linear
+    from NeuromahRef.src.losses import Loss_MeanSquaredError, Loss_MeanAbsoluteError, Loss_BinaryCrossentropy
+    from NeuromahRef.src.optimizers import Optimizer_Adam, Optimizer_SGD
+    from NeuromahRef.src.metrics import Accuracy_Categorical, Accuracy_Regression
+    out = {}
+    v = {k: a.astype(np.float64) for k, a in losses_family_inputs().items()}
+    sg = Activation_Sigmoid()
+    sg.forward(v["x"], training=True)
+    sg.backward(v["dv"])
+    out["sigmoid_out"], out["sigmoid_dx"], out["sigmoid_pred"] = sg.output, sg.dinputs, sg.predictions(sg.output)
+    for name, cls, t in (("mse", Loss_MeanSquaredError, "t_reg"), ("mae", Loss_MeanAbsoluteError, "t_reg"),
+                         ("bce", Loss_BinaryCrossentropy, "t_bin")):
+        loss = cls(model=None)
+        out[f"{name}_fwd"] = loss.forward(v["pred"], v[t])
+        loss.backward(v["pred"], v[t])
+        out[f"{name}_bwd"] = loss.dinputs
+        out[f"{name}_fwd4"] = loss.forward(v["pred4"], v["t4"])
+        loss.backward(v["pred4"], v["t4"])
+        out[f"{name}_bwd4"] = loss.dinputs
+    losses = {"mse": Loss_MeanSquaredError, "mae": Loss_MeanAbsoluteError, "bce": Loss_BinaryCrossentropy}
+    for name, c in LOSSES_FAMILY_CASES.items():
+        w, x, y = losses_family_case(name)
+        model = Model()
+        d1 = Layer_Dense(n_inputs=8, n_neurons=16, activation=Activation_ReLU())
+        d2 = Layer_Dense(n_inputs=16, n_neurons=c["n_out"])
+        for d, wi in zip((d1, d2), w):
+            d.weights = wi.copy(); d.biases = np.zeros((1, wi.shape[1]))
+        for l in (d1, d2, Activation_Sigmoid() if c["act"] == "sigmoid" else Activation_Linear()):
+            model.add(l)
+        opt = Optimizer_Adam(learning_rate=c["lr"]) if c["opt"] == "adam" else Optimizer_SGD(learning_rate=c["lr"])
+        acc = Accuracy_Categorical(binary=True, model=model) if c["acc"] == "binary" else Accuracy_Regression(model=model)
+        model.set(loss=losses[c["loss"]](model=model), optimizer=opt, accuracy=acc)
+        model.finalize()
+        model.accuracy.init(y)                      # Model.train does this first (:119)
+        model.loss.new_pass(); model.accuracy.new_pass()
+        ls, accs = [], []
+        for s in range(c["steps"]):
+            r = ref_shim.train_step(model, x[s * 32:(s + 1) * 32], y[s * 32:(s + 1) * 32])
+            ls.append(r["loss"]); accs.append(r["acc"])
+        out[f"{name}_losses"], out[f"{name}_accs"] = np.array(ls), np.array(accs)
+        out[f"{name}_final_params"] = flat_params(model).astype(np.float64)
+        out[f"{name}_acc_running"] = np.array([model.accuracy.accumulated_sum, model.accuracy.accumulated_count], dtype=np.float64)
+        out[f"{name}_infer"] = np.asarray(model.forward(x[:32], training=False), dtype=np.float64)
+        if c["acc"] == "regression":
+            out[f"{name}_precision"] = np.float64(model.accuracy.precision)
+    np.savez_compressed(os.path.join(HERE, "losses_family.npz"), **out)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (mlp_200, mlp_sgd, cnn_small, vgg_small, cnn_stub, cnn_200, ops, single_layer_optimizers, dropout_mlp, dense_example_stack):
+    for fn in (mlp_200, mlp_sgd, cnn_small, vgg_small, cnn_stub, cnn_200, ops, single_layer_optimizers, dropout_mlp, dense_example_stack,
+               losses_family):
         if not only or fn.__name__ in only:
             fn()
     for f in sorted(os.listdir(HERE)):
