@@ -27,7 +27,7 @@ def _activation(name):
 
 def layer_state(layer):
     from .src.layers import Layer_Conv2D, Layer_Dense, Layer_Dropout, Layer_Flatten, Layer_MaxPooling2D
-    from .src.activations import Activation_ReLU, Activation_Softmax
+    from .src.activations import Activation_Linear, Activation_ReLU, Activation_Sigmoid, Activation_Softmax
     if isinstance(layer, Layer_Dense):
         n_in, n_out = layer.weights.shape
         st = {"cls": "Layer_Dense", "args": dict(n_inputs=int(n_in), n_neurons=int(n_out),
@@ -46,7 +46,7 @@ def layer_state(layer):
         return {"cls": "Layer_Flatten", "args": {}}
     elif isinstance(layer, Layer_Dropout):
         return {"cls": "Layer_Dropout", "args": dict(rate=1 - layer.rate, seed=layer.seed), "calls": layer.calls}
-    elif isinstance(layer, (Activation_ReLU, Activation_Softmax)):
+    elif isinstance(layer, (Activation_ReLU, Activation_Softmax, Activation_Sigmoid, Activation_Linear)):
         return {"cls": type(layer).__name__, "args": {}}
     else:
         raise TypeError(f"Model.save: no checkpoint recipe for {type(layer).__name__}")
@@ -92,7 +92,8 @@ def model_state(model):
         "layers": [layer_state(l) for l in model.layers],
         "loss": type(model.loss).__name__ if not isinstance(model.loss, type) else model.loss.__name__,
         "accuracy": {"cls": type(model.accuracy).__name__ if not isinstance(model.accuracy, type) else model.accuracy.__name__,
-                     "binary": getattr(model.accuracy, "binary", False)},
+                     "binary": getattr(model.accuracy, "binary", False),
+                     "precision": getattr(model.accuracy, "precision", None)},      # Accuracy_Regression: std(y) / 250 of the run
         "optimizer": {"cls": type(opt).__name__, "attrs": {k: getattr(opt, k) for k in _OPT_ATTRS if hasattr(opt, k)},
                       "state": [np.asarray(s) for s in (model.arena.state if model.arena else [])]},
     }
@@ -122,7 +123,10 @@ def model_from_state(st):
     finally:
         for k, v in saved.items():
             setattr(config, k, v)
-    model.accuracy.binary = st["accuracy"].get("binary", False)
+    if hasattr(model.accuracy, "binary"):
+        model.accuracy.binary = st["accuracy"].get("binary", False)
+    if hasattr(model.accuracy, "precision"):
+        model.accuracy.precision = st["accuracy"].get("precision")
     if o["state"]:
         model.arena.ensure_state(len(o["state"]))
         for slab, host in zip(model.arena.state, o["state"]):

@@ -166,3 +166,32 @@ def test_train_evaluate_predict_with_a_regression_head():
     pred = model.predict(x[:40], batch_size=16)
     assert pred.shape == (40, 3)
     close(np.mean((pred - y[:40]) ** 2, axis=1), np.asarray(model.loss.forward(pred.astype(np.float32), y[:40])))
+
+
+@pytest.mark.parametrize("name", ["mse", "bce"])
+def test_save_load_resumes_training_identically(tmp_path, name):
+    """Model.save / Model.load with a Linear / Sigmoid head: layers, loss and metric classes, the regression precision,
+    parameters and optimizer state survive; both models then take the same steps."""
+    from neuromah_b200.src.core import Model
+    m1, c, x, y = _model(name)
+    m1.accuracy.init(y)
+    m1.loss.new_pass(); m1.accuracy.new_pass()
+    for s in range(3):
+        m1.train_step(x[s * 32:(s + 1) * 32], y[s * 32:(s + 1) * 32])
+    path = str(tmp_path / "model.pkl")
+    m1.save(path)
+    m2 = Model.load(path)
+    assert [type(l).__name__ for l in m2.layers] == [type(l).__name__ for l in m1.layers]
+    assert type(m2.loss) is type(m1.loss) and type(m2.accuracy) is type(m1.accuracy)
+    assert m2.optimizer.iterations == 3 and m2.softmax_classifier_output is None
+    if name == "mse":
+        assert m2.accuracy.precision == m1.accuracy.precision
+    else:
+        assert m2.accuracy.binary is True
+    np.testing.assert_array_equal(m1.arena.host_params(), m2.arena.host_params())
+    m2.loss.new_pass(); m2.accuracy.new_pass()
+    for s in range(3, 6):
+        m1.train_step(x[s * 32:(s + 1) * 32], y[s * 32:(s + 1) * 32])
+        m2.train_step(x[s * 32:(s + 1) * 32], y[s * 32:(s + 1) * 32])
+        assert m2.last_step["loss"] == pytest.approx(m1.last_step["loss"], rel=1e-6)
+    np.testing.assert_allclose(m1.arena.host_params(), m2.arena.host_params(), rtol=1e-6, atol=1e-7)
