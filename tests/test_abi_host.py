@@ -112,6 +112,38 @@ def test_alias_makes_reference_imports_resolve():
     from Neuromah.src.core import Model                         # noqa: F401
     from Neuromah.src.activations import Activation_ReLU, Activation_Softmax   # noqa: F401
     from Neuromah.src.metrics import Accuracy_Categorical       # noqa: F401
+    # the rest of the reference's package surface around Model.train (activations/__init__.py:1-4, losses/__init__.py:1-4,
+    # metrics/__init__.py:1-2, core/__init__.py:1-5)
+    from Neuromah.src.activations import Activation_Linear, Activation_Sigmoid
+    from Neuromah.src.losses import Loss_BinaryCrossentropy, Loss_MeanAbsoluteError, Loss_MeanSquaredError  # noqa: F401
+    from Neuromah.src.metrics import Accuracy_Regression
+    from Neuromah.src.core import Accuracy, Activation, Loss
+    assert issubclass(Activation_Sigmoid, Activation) and issubclass(Activation_Linear, Activation)
+    assert issubclass(Loss_MeanSquaredError, Loss) and issubclass(Accuracy_Regression, Accuracy)
+
+
+def test_regression_accuracy_and_element_counting_on_the_host():
+    """Accuracy_Regression (Accuracy_Regression.py:10-17) and Accuracy.calculate (Accuracy.py:19-23) are host arithmetic."""
+    from neuromah_b200.src.metrics import Accuracy_Categorical, Accuracy_Regression
+    y = np.array([[0.0, 1.0], [2.0, 3.0], [4.0, 5.0]])
+    acc = Accuracy_Regression(model=None)
+    acc.init(y)
+    assert acc.precision == np.std(y) / 250
+    acc.init(y * 10)                                   # kept unless reinit
+    assert acc.precision == np.std(y) / 250
+    acc.init(y * 10, reinit=True)
+    assert acc.precision == np.std(y * 10) / 250
+    acc.new_pass()
+    pred = y + np.array([[0.0, 1.0], [0.0, 0.0], [1.0, 0.5]])
+    assert acc.calculate(pred, y) == 0.5               # mean over the six compared elements
+    assert (acc.accumulated_sum, acc.accumulated_count) == (3, 3)      # element hits, but samples counted
+    assert acc.calculate_accumulated() == 1.0
+    binary = Accuracy_Categorical(binary=True, model=None)
+    binary.new_pass()
+    assert binary.calculate(np.array([[1, 0], [1, 1]]), np.array([[1.0, 1.0], [1.0, 1.0]])) == 0.75
+    with pytest.raises(NotImplementedError):
+        from neuromah_b200.src.core import Activation
+        Activation().forward(None, False)
 
 
 def test_federated_average_host_mirror():

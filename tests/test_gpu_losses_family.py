@@ -195,3 +195,26 @@ def test_save_load_resumes_training_identically(tmp_path, name):
         m2.train_step(x[s * 32:(s + 1) * 32], y[s * 32:(s + 1) * 32])
         assert m2.last_step["loss"] == pytest.approx(m1.last_step["loss"], rel=1e-6)
     np.testing.assert_allclose(m1.arena.host_params(), m2.arena.host_params(), rtol=1e-6, atol=1e-7)
+
+
+def test_dense_with_an_embedded_sigmoid():
+    """Layer_Dense(activation=Activation_Sigmoid()) (Dense.py:82-85, :90-93): the embedded activation's forward / backward
+    wrap the GEMMs exactly as in the reference."""
+    from neuromah_b200.src.layers import Layer_Dense
+    from neuromah_b200.src.activations import Activation_Sigmoid
+    rng = np.random.default_rng(17)
+    x = rng.standard_normal((37, 19)).astype(np.float32)
+    w = (rng.standard_normal((19, 11)) * 0.4).astype(np.float32)
+    b = rng.standard_normal((1, 11)).astype(np.float32)
+    dv = rng.standard_normal((37, 11)).astype(np.float32)
+    layer = Layer_Dense(19, 11, activation=Activation_Sigmoid())
+    layer.set_parameters(w, b)
+    layer.forward(x, training=True)
+    x64, w64, b64, dv64 = (a.astype(np.float64) for a in (x, w, b, dv))
+    out = R.sigmoid_forward(R.dense_forward(x64, w64, b64))
+    close(layer.output, out)
+    layer.backward(dv)
+    dx, dw, db = R.dense_backward(x64, w64, R.sigmoid_backward(out, dv64))
+    close(layer.dinputs, dx)
+    close(layer.dweights, dw)
+    close(layer.dbiases, db)
