@@ -122,6 +122,31 @@ def test_alias_makes_reference_imports_resolve():
     assert issubclass(Loss_MeanSquaredError, Loss) and issubclass(Accuracy_Regression, Accuracy)
 
 
+def test_alias_deep_imports_share_module_and_class_identity():
+    """The reference notebook imports classes by their module path (examples/test.ipynb cell 1:
+    `from Neuromah.src.losses.categorical_crossentropy import Loss_CategoricalCrossentropy`,
+    `from Neuromah.src.metrics.Accuracy_Categorical import Accuracy_Categorical`).  Under the alias these must be the
+    SAME objects as the mirror package's -- Model.finalize selects the fused softmax / cross-entropy path with
+    isinstance -- and the names the package __init__s rebind from submodule to class must stay classes."""
+    import sys
+    neuromah_b200.install_alias()
+    from Neuromah.src.losses.categorical_crossentropy import Loss_CategoricalCrossentropy as A
+    from Neuromah.src.metrics.Accuracy_Categorical import Accuracy_Categorical as C
+    from Neuromah.src.core.Model import Model as M
+    import Neuromah.device as dev_alias
+    import neuromah_b200.device as dev_real
+    from neuromah_b200.src.losses import Loss_CategoricalCrossentropy
+    from neuromah_b200.src.metrics import Accuracy_Categorical
+    from neuromah_b200.src.core import Model
+    assert A is Loss_CategoricalCrossentropy and C is Accuracy_Categorical and M is Model
+    assert isinstance(Model, type) and isinstance(Accuracy_Categorical, type)
+    assert dev_alias is dev_real                          # one library stream / launch counter, not a copy per name
+    assert sys.modules["Neuromah.src.layers.Dense"] is sys.modules["neuromah_b200.src.layers.Dense"]
+    assert not any(m.startswith("Neuromah.compat") for m in sys.modules)
+    with pytest.raises(ImportError):
+        import Neuromah.src.layers.RNN                    # noqa: F401  (absent from the reference as well)
+
+
 def test_regression_accuracy_and_element_counting_on_the_host():
     """Accuracy_Regression (Accuracy_Regression.py:10-17) and Accuracy.calculate (Accuracy.py:19-23) are host arithmetic."""
     from neuromah_b200.src.metrics import Accuracy_Categorical, Accuracy_Regression
