@@ -65,6 +65,25 @@ def test_unmodified_reference_layers_bind_the_shim():
             del sys.modules[k]
 
 
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF_ROOT, "tests")), reason="reference tree only in the authoring container")
+def test_reference_own_adam_unit_tests_pass_against_the_mirror():
+    """The reference's tests/optimizers/test_Adam.py, UNMODIFIED, loaded from where it lies and run with `Neuromah`
+    aliased to the mirror package: its module-path import (`from Neuromah.src.optimizers.Adam import Optimizer_Adam`,
+    :4) and its three cases (defaults :13-20, custom values :22-29, ValueError on bad betas :31-35)."""
+    import importlib.util
+    import unittest
+    import neuromah_b200
+    neuromah_b200.install_alias()
+    spec = importlib.util.spec_from_file_location("ref_test_Adam", os.path.join(REF_ROOT, "tests", "optimizers", "test_Adam.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from neuromah_b200.src.optimizers import Optimizer_Adam
+    assert mod.Optimizer_Adam is Optimizer_Adam
+    suite = unittest.defaultTestLoader.loadTestsFromModule(mod)
+    result = unittest.TextTestRunner(stream=open(os.devnull, "w")).run(suite)
+    assert result.testsRun == 3 and result.wasSuccessful(), result.failures + result.errors
+
+
 # ------------------------------------------------------------------ GPU: values through the seam ----
 @pytest.mark.gpu
 def test_shim_maxpool_reference_kats():
