@@ -64,3 +64,28 @@ def test_package_exports_match_the_reference():
         exported = [k for k, v in vars(ref_mod).items() if inspect.isclass(v) and v.__module__.startswith(ref_shim.PKG)]
         missing = [k for k in exported if not hasattr(mod, k) and k != "Layer_RNN"]
         assert not missing, f"src.{sub}: {missing}"
+
+
+@pytest.mark.parametrize("name", ["Optimizer_Adam", "Optimizer_SGD", "Optimizer_RMSprop", "Optimizer_Adagrad", "Optimizer_Nadam"])
+def test_optimizer_constructor_validation_is_the_reference(name):
+    """Differential: every constructor parameter of every optimizer, set to each of 13 good / bad values, gives the same
+    outcome as the unmodified reference -- the same exception type, or an object with the same hyper-parameter
+    attributes (Adam.py:24-35, SGD.py:28-46, RMSprop.py / Adagrad.py / Nadam.py constructors)."""
+    ref_shim.load()
+    ref_cls = getattr(importlib.import_module(f"{ref_shim.PKG}.src.optimizers"), name)
+    cls = getattr(importlib.import_module("neuromah_b200.src.optimizers"), name)
+    attrs = ("learning_rate", "current_learning_rate", "decay", "iterations", "epsilon", "beta_1", "beta_2", "beta1", "beta2",
+             "rho", "momentum", "momentum_factor")
+
+    def outcome(c, kw):
+        try:
+            o = c(**kw)
+        except Exception as e:          # noqa: BLE001 - the exception TYPE is the thing compared
+            return type(e).__name__
+        return {k: getattr(o, k, None) for k in attrs}
+
+    params = [k for k in inspect.signature(ref_cls.__init__).parameters if k != "self"]
+    assert params
+    for p in params:
+        for v in (0, -1, -0.5, 1, 1.0, 1.5, 2, "x", None, True, 0.0, 1e-9, 0.5):
+            assert outcome(cls, {p: v}) == outcome(ref_cls, {p: v}), f"{name}({p}={v!r})"
