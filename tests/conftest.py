@@ -71,6 +71,55 @@ def losses_family_case(name, batch=32):
     return w, x, y
 
 
+# ---- constructor differential (golden/ctor_surface.json): the same constructor calls on the reference and the mirror ----
+# values are Python literals; "@relu" / "@xavier" / "@he" / "@object" stand for Activation_ReLU(), XavierInitializer(),
+# HeInitializer() and a bare object() of whichever package is under test
+CTOR_CASES = (
+    [("Layer_Dense", {"n_inputs": a, "n_neurons": b}) for a, b in
+     [(4, 3), (0, 3), (-1, 3), (2.5, 3), ("4", 3), (None, 3), (4, 0), (4, -2), (4, 1.0), (True, 3)]] +
+    [("Layer_Dense", dict(n_inputs=4, n_neurons=3, **kw)) for kw in
+     [{"weight_initializer": "xavier"}, {"weight_initializer": "HE"}, {"weight_initializer": "glorot"},
+      {"weight_initializer": "@xavier"}, {"weight_initializer": "@object"}, {"weight_initializer": 3},
+      {"activation": "@relu"}, {"weight_regularizer_l1": 0.01, "weight_regularizer_l2": 0.5}]] +
+    [("Layer_Conv2D", dict(in_channels=a, out_channels=b, kernel_size=k)) for a, b, k in
+     [(3, 5, 3), (3, 5, (2, 4)), (0, 5, 3), (3, -1, 3), (3.0, 5, 3), (3, "5", 3), (3, 5, [3, 3]), (3, 5, (3,)), (3, 5, (3, 3, 3)),
+      (3, 5, 2.0), (3, 5, None)]] +
+    [("Layer_Conv2D", dict(in_channels=3, out_channels=5, kernel_size=3, **kw)) for kw in
+     [{"stride": 2}, {"stride": (1, 2)}, {"stride": 0}, {"stride": (1, 0)}, {"stride": -1}, {"stride": 1.5}, {"stride": (1, 1, 1)},
+      {"padding": "same"}, {"padding": "SAME"}, {"padding": "full"}, {"padding": None},
+      {"weight_initializer": "he"}, {"weight_initializer": "Xavier"}, {"weight_initializer": "lecun"},
+      {"weight_initializer": "@he"}, {"weight_initializer": "@object"}, {"weight_initializer": 1.0}, {"activation": "@relu"}]] +
+    [("Layer_MaxPooling2D", kw) for kw in
+     [{"pool_size": 2}, {"pool_size": (2, 3)}, {"pool_size": [2, 2]}, {"pool_size": (2,)}, {"pool_size": 2.0}, {"pool_size": None},
+      {"pool_size": 2, "strides": 1}, {"pool_size": 2, "strides": (1, 2)}, {"pool_size": 2, "strides": [1, 1]},
+      {"pool_size": 2, "strides": 1.0}, {"pool_size": 3, "strides": None, "padding": "same"},
+      {"pool_size": 2, "padding": "full"}, {"pool_size": 2, "padding": "VALID"}]] +
+    [("Layer_Dropout", {"rate": r}) for r in (0.0, 0.1, 0.5, 0.9)] +
+    [("Layer_Flatten", {})]
+)
+
+
+def ctor_outcome(cls, kwargs, ns):
+    """Exception type name, or {attribute: descriptor} of the constructed object: arrays by shape, plain values by value,
+    anything else by type name.  ``ns`` resolves the "@..." tokens to objects of the package under test."""
+    kw = {k: (ns[v[1:]]() if isinstance(v, str) and v.startswith("@") else v) for k, v in kwargs.items()}
+    try:
+        obj = cls(**kw)
+    except Exception as e:          # noqa: BLE001 - the exception TYPE is what is compared
+        return type(e).__name__
+    out = {}
+    for k, v in vars(obj).items():
+        if isinstance(getattr(v, "shape", None), tuple) and hasattr(v, "dtype"):
+            out[k] = ["array", [int(d) for d in v.shape]]
+        elif v is None or isinstance(v, (bool, int, float, str)):
+            out[k] = ["value", v]
+        elif isinstance(v, tuple):
+            out[k] = ["value", list(v)]
+        else:
+            out[k] = ["object", type(v).__name__]
+    return out
+
+
 @pytest.fixture(scope="session")
 def have_reference():
     return os.path.isdir("/root/reference/src")

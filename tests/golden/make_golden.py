@@ -339,10 +339,27 @@ def losses_family():
     np.savez_compressed(os.path.join(HERE, "losses_family.npz"), **out)
 
 
+def ctor_surface():
+    """Constructor differential: every call of tests/conftest.py::CTOR_CASES on the UNMODIFIED reference layer classes --
+    the exception type it raises, or the attributes (names, array shapes, plain values) of the object it builds."""
+    import json
+    ref_shim.load()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import CTOR_CASES, ctor_outcome
+    import NeuromahRef.src.layers as L
+    from NeuromahRef.src.activations import Activation_ReLU
+    from NeuromahRef.src.initializers.Initializer import HeInitializer, XavierInitializer
+    ns = {"relu": Activation_ReLU, "xavier": XavierInitializer, "he": HeInitializer, "object": object}
+    np.random.seed(0)
+    out = [{"cls": c, "kwargs": repr(kw), "outcome": ctor_outcome(getattr(L, c), kw, ns)} for c, kw in CTOR_CASES]
+    with open(os.path.join(HERE, "ctor_surface.json"), "w") as f:
+        json.dump(out, f, indent=0)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     for fn in (mlp_200, mlp_sgd, cnn_small, vgg_small, cnn_stub, cnn_200, ops, single_layer_optimizers, dropout_mlp, dense_example_stack,
-               losses_family):
+               losses_family, ctor_surface):
         if not only or fn.__name__ in only:
             fn()
     for f in sorted(os.listdir(HERE)):

@@ -1,0 +1,46 @@
+"""GPU (the mirror's layers allocate device memory when constructed): constructor differential against the UNMODIFIED
+reference.  tests/golden/ctor_surface.json holds, for every call in conftest.CTOR_CASES, what the reference's layer class
+did -- the exception type, or the attributes of the object it built (names, array shapes, plain values, object type
+names).  The mirror must raise the same type / carry every reference attribute with the same descriptor (it may have
+more: gradient buffers, device handles)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CTOR_CASES, GOLDEN, ctor_outcome
+
+pytestmark = pytest.mark.gpu
+
+
+def _ns():
+    from neuromah_b200.src.activations import Activation_ReLU
+    from neuromah_b200.src.initializers.Initializer import HeInitializer, XavierInitializer
+    return {"relu": Activation_ReLU, "xavier": XavierInitializer, "he": HeInitializer, "object": object}
+
+
+def test_constructor_outcomes_match_the_reference():
+    import neuromah_b200.src.layers as L
+    with open(os.path.join(GOLDEN, "ctor_surface.json")) as f:
+        gold = json.load(f)
+    assert len(gold) == len(CTOR_CASES)
+    ns, problems = _ns(), []
+    np.random.seed(0)
+    for (cls, kw), g in zip(CTOR_CASES, gold):
+        assert g["cls"] == cls and g["kwargs"] == repr(kw), "golden file out of date: re-run make_golden.py ctor_surface"
+        mine, ref = ctor_outcome(getattr(L, cls), kw, ns), g["outcome"]
+        if isinstance(ref, str) or isinstance(mine, str):
+            if mine != ref:
+                problems.append(f"{cls}({kw}): reference {ref if isinstance(ref, str) else 'constructs'}, "
+                                f"mirror {mine if isinstance(mine, str) else 'constructs'}")
+            continue
+        for attr, desc in ref.items():
+            if attr not in mine:
+                problems.append(f"{cls}({kw}): attribute {attr} missing")
+            elif desc[0] == "value" and isinstance(desc[1], float):
+                if not (mine[attr][0] == "value" and mine[attr][1] == pytest.approx(desc[1], rel=1e-12)):
+                    problems.append(f"{cls}({kw}).{attr}: {mine[attr]} vs reference {desc}")
+            elif mine[attr] != desc:
+                problems.append(f"{cls}({kw}).{attr}: {mine[attr]} vs reference {desc}")
+    assert not problems, "\n".join(problems)
