@@ -94,6 +94,9 @@ class Model:
                 self.trainable_layers.append(layer)
         if isinstance(self.loss, type):
             self.loss = self.loss(model=self)
+            # the last layer's `next` is the loss OBJECT whose dinputs the generic backward reads (Model.py:362-366); the
+            # reference leaves the class there (:74 runs before :91), which only the fused softmax path never notices
+            self.layers[-1].next = self.loss
         if isinstance(self.accuracy, type):
             self.accuracy = self.accuracy(model=self)
         if isinstance(self.layers[-1], Activation_Softmax) and isinstance(self.loss, Loss_CategoricalCrossentropy):

@@ -21,7 +21,10 @@ class Layer_Dense:
             raise ValueError("n_inputs must be a positive integer")
         if not isinstance(n_neurons, int) or n_neurons <= 0:
             raise ValueError("n_neurons must be a positive integer")
-        self.weight_initializer = resolve(weight_initializer, ValueError)
+        # anything that is neither None, a name nor an Initializer: TypeError, as the reference actually raises -- its
+        # isinstance test against the Initializer MODULE (Dense.py:3, :49) fails before the ValueError of :52 is reached.
+        # (For the same reason the reference cannot take an Initializer INSTANCE at all; the mirror does.)
+        self.weight_initializer = resolve(weight_initializer, TypeError)
         self.weights = DeviceArray.from_numpy(self.weight_initializer.initialize((n_inputs, n_neurons)), np.float32)
         self.biases = DeviceArray.zeros((1, n_neurons))
         self.dweights = DeviceArray.zeros((n_inputs, n_neurons))

@@ -30,6 +30,12 @@ def test_constructor_outcomes_match_the_reference():
     for (cls, kw), g in zip(CTOR_CASES, gold):
         assert g["cls"] == cls and g["kwargs"] == repr(kw), "golden file out of date: re-run make_golden.py ctor_surface"
         mine, ref = ctor_outcome(getattr(L, cls), kw, ns), g["outcome"]
+        if str(kw.get("weight_initializer")) in ("@xavier", "@he"):
+            # documented extension: the reference tests `isinstance(x, Initializer)` against the Initializer MODULE
+            # (Dense.py:3, :49; Conv_wrapepr.py:5, :56), i.e. raises TypeError for every Initializer instance; the mirror
+            # accepts them
+            assert ref == "TypeError" and isinstance(mine, dict) and mine["weight_initializer"][1] in ("XavierInitializer", "HeInitializer")
+            continue
         if isinstance(ref, str) or isinstance(mine, str):
             if mine != ref:
                 problems.append(f"{cls}({kw}): reference {ref if isinstance(ref, str) else 'constructs'}, "
