@@ -15,12 +15,14 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import neuromah_b200
 neuromah_b200.install_alias()          # `import Neuromah.src...` below resolves to the B200 package
-from Neuromah.src.layers import Layer_Dense, Layer_Dropout
-from Neuromah.src.optimizers import Optimizer_Adam
-from Neuromah.src.losses import Loss_CategoricalCrossentropy
+# the reference script's own import lines (examples/test_Dense_MNIST.py:2-9), module-path imports included
 from Neuromah.src.core import Model
-from Neuromah.src.activations import Activation_ReLU, Activation_Softmax
-from Neuromah.src.metrics import Accuracy_Categorical
+from Neuromah.src.layers import Layer_Dense
+from Neuromah.src.losses.categorical_crossentropy import Loss_CategoricalCrossentropy
+from Neuromah.src.optimizers import Optimizer_Adam
+from Neuromah.src.activations import Activation_Softmax, Activation_ReLU
+from Neuromah.src.metrics.Accuracy_Categorical import Accuracy_Categorical
+from Neuromah.src.layers import Layer_Dropout
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=25600)

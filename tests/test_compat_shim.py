@@ -132,3 +132,39 @@ def test_shim_conv_reference_shape_cases_and_oracle_values():
     assert dx.shape == xp.shape and dw.shape == w.shape
     np.testing.assert_allclose(dx, rdx, rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(dw, rdw, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF_ROOT, "examples")), reason="reference tree only in the authoring container")
+def test_every_neuromah_import_of_the_reference_examples_resolves_to_the_mirror():
+    """Each `from Neuromah... import ...` line of the reference's example scripts and notebook, executed as written with
+    `Neuromah` aliased to the mirror: the names resolve to the mirror's own objects (module-path imports included, e.g.
+    examples/test_Dense_MNIST.py:4, :7).  The only lines that may fail are the federated HTTP client / server ones
+    (`Neuromah.Federated.Client` / `.Auth`: FastAPI / JWT wire path, out of scope -- DESIGN.md section 7)."""
+    import json
+    import re
+    import neuromah_b200
+    neuromah_b200.install_alias()
+    ex = os.path.join(REF_ROOT, "examples")
+    lines = []
+    for name in sorted(os.listdir(ex)):
+        path = os.path.join(ex, name)
+        if name.endswith(".py"):
+            src = open(path, encoding="utf-8").read().splitlines()
+        elif name.endswith(".ipynb"):
+            nb = json.load(open(path, encoding="utf-8"))
+            src = [l for c in nb["cells"] if c["cell_type"] == "code" for l in "".join(c["source"]).splitlines()]
+        else:
+            continue
+        lines += [(name, l.split("#")[0].strip()) for l in src if re.match(r"\s*from\s+Neuromah[.\w]*\s+import\s+\w", l)]
+    assert len(lines) >= 20
+    resolved = 0
+    for name, line in sorted(set(lines)):
+        ns = {}
+        if re.search(r"Neuromah\.Federated\.(Client|Server|Auth)\b", line):
+            continue
+        exec(line, ns)                                        # noqa: S102 - the reference's own import statement
+        for k, v in ns.items():
+            if k != "__builtins__":
+                assert getattr(v, "__module__", "").startswith("neuromah_b200."), f"{name}: {line}: {k} -> {v!r}"
+                resolved += 1
+    assert resolved >= 30
