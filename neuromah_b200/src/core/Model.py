@@ -398,20 +398,32 @@ class Model:
             start_time = time.time()
             self.loss.new_pass()
             self.accuracy.new_pass()
+            if self.tensorMonitor:
+                self.tensorMonitor.start_epoch(epoch)
             for step in range(train_steps):
                 sl = slice(None) if batch_size is None else slice(step * batch_size, (step + 1) * batch_size)
                 self._generic_step(X[sl], y[sl])
             epoch_time = time.time() - start_time
             losses = self.loss.calculate_accumulated(include_regularization=True)
+            epoch_loss = losses['data_loss'] + losses.get('regularization_loss', 0)
             output = self.forward(X, training=False)
             acc = self.accuracy.calculate(self.output_layer_activation.predictions(output), y)
+            if self.tensorMonitor:                      # the same per-epoch hooks as the fused path (Model.py:203-223)
+                self.tensorMonitor.log_scalar("loss/epoch_training", epoch_loss)
+                self.tensorMonitor.log_scalar("accuracy/epoch_training", acc)
+                for layer in self.trainable_layers:
+                    self.tensorMonitor.log_layer_parameters(layer)
+                self.tensorMonitor.end_epoch()
             if verbose:
-                print(f"time: {epoch_time:.2f}s, acc: {acc:.3f}, loss: "
-                      f"{losses['data_loss'] + losses.get('regularization_loss', 0):.3f} ("
+                print(f"time: {epoch_time:.2f}s, acc: {acc:.3f}, loss: {epoch_loss:.3f} ("
                       f"data_loss: {losses['data_loss']:.3f}, reg_loss: {losses.get('regularization_loss', 0):.3f}), "
                       f"lr: {self.optimizer.current_learning_rate:.7f}")
+            self.last_epoch = {"time": epoch_time, "acc": float(acc), "loss": float(epoch_loss),
+                               "data_loss": float(losses['data_loss'])}
             if validation_data is not None:
                 self.evaluate(*validation_data, batch_size=batch_size, verbose=verbose)
+        if self.tensorMonitor:
+            self.tensorMonitor.save_logs()
 
     def evaluate(self, X_val, y_val, *, batch_size=None, verbose=1):
         n = len(X_val)

@@ -218,3 +218,34 @@ def test_dense_with_an_embedded_sigmoid():
     close(layer.dinputs, dx)
     close(layer.dweights, dw)
     close(layer.dbiases, db)
+
+
+def test_tensor_monitor_hooks_on_the_generic_training_loop(tmp_path, capsys):
+    """Model.train with a TensorMonitor and a non-softmax head: the per-epoch hooks of Model.py:203-227 run on the generic
+    loop too (scalars, parameter histograms computed on the device, one JSON file at the end)."""
+    import json
+    from neuromah_b200.src.core import Model
+    from neuromah_b200.src.layers import Layer_Dense
+    from neuromah_b200.src.activations import Activation_ReLU, Activation_Sigmoid
+    from neuromah_b200.src.losses import Loss_BinaryCrossentropy
+    from neuromah_b200.src.optimizers import Optimizer_Adam
+    from neuromah_b200.src.metrics import Accuracy_Categorical
+    from neuromah_b200.src.utils import TensorMonitor
+    _, x, y = losses_family_case("bce")
+    np.random.seed(3)
+    model = Model()
+    for l in (Layer_Dense(8, 16, activation=Activation_ReLU()), Layer_Dense(16, 2), Activation_Sigmoid()):
+        model.add(l)
+    tm = TensorMonitor(log_dir=str(tmp_path))
+    model.set(loss=Loss_BinaryCrossentropy, optimizer=Optimizer_Adam(learning_rate=0.01),     # loss passed as a CLASS
+              accuracy=Accuracy_Categorical(binary=True, model=model), tensorMonitor=tm)
+    model.finalize()
+    model.train(x, y, epochs=2, batch_size=64, verbose=1)
+    assert "data_loss" in capsys.readouterr().out
+    assert model.last_epoch["loss"] > 0 and 0 <= model.last_epoch["acc"] <= 1
+    log = json.load(open(tm.log_file_path))
+    assert log["metadata"]["loss_function"] == "Loss_BinaryCrossentropy" and len(log["epochs"]) == 2
+    ep = log["epochs"][1]
+    assert ep["metrics"]["scalars"]["loss/epoch_training"] == pytest.approx(model.last_epoch["loss"])
+    hist = ep["parameters"]["histograms"]["Layer_Dense/weights"]
+    assert sum(hist["histogram"]) in (8 * 16, 16 * 2) and len(hist["bin_edges"]) == 11
