@@ -757,7 +757,8 @@ def main():
         # the instrumented pass is eager: the exchange's push kernel (side stream, behind conv2's wgrad) then shares the SMs
         # with whichever kernel the compute stream runs next, and that kernel's event pair absorbs the wait
         roofline["note"] = ("per-kernel times at N > 1 are taken while the gradient push runs beside the backward kernels "
-                            "(tc_conv1_bwd's event pair absorbs the contention); the N = 1 line has the kernels timed alone")
+                            "(the event pair of the kernel launched next on the compute stream -- tc_conv1_bwd in the MNIST plan -- absorbs the "
+                            "contention); the N = 1 line has the kernels timed alone")
     line = {"metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (three bf16 planes per operand, FP32-exact)"}.get(args.mode, "f32"), "data": "synthetic",
