@@ -4,7 +4,7 @@ from __future__ import annotations
 import importlib.util
 import os
 
-from .build_ref import target_path
+from .build_ref import conv_target_path, target_path
 
 
 def load_ref_maxpool():
@@ -15,3 +15,16 @@ def load_ref_maxpool():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_ref_conv():
+    """The reference's Conv2D.cpp compiled against oracle/eigen_standin (see build_ref.py): a checker for the conv oracle,
+    correct for one output channel only."""
+    path = conv_target_path()
+    if not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location("_Conv2DBackend_cpp", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
