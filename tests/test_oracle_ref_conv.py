@@ -113,3 +113,38 @@ def test_same_padding_through_the_wrapper_call_pattern():
         assert out.shape == (3, 1, 8, 8)
         ref, _ = R.conv_layer_forward(x, w, np.zeros((1, 1)), padding="same", relu=False)
         np.testing.assert_allclose(out, ref, rtol=RTOL, atol=ATOL)
+
+
+def test_oracle_step_driver_equals_the_reference_model_on_its_own_compiled_kernels():
+    """A one-filter CNN -- Conv(3->1, 3x3, same, ReLU) -> MaxPool 2 -> Flatten -> Dense(16->4) -> Softmax, Adam -- stepped
+    three times by the UNMODIFIED reference Model with BOTH of its own compiled kernels at the `compiled` seam (Conv2D.cpp
+    through the Eigen stand-in, maxpooling_backend.cpp), against the oracle's step driver from the same initial weights.
+    The only non-reference line in the reference run is the wiring of Layer_Conv2D.backward to the backend's own
+    conv2d_backward_cpu (the shipped backward is a stub)."""
+    from oracle import ref_net, ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree only in the authoring container")
+    ref_shim.load()
+    from NeuromahRef.src.layers.compiled import _Conv2DBackend_cpp as seam
+    spec = [{"kind": "conv", "ic": 3, "oc": 1, "k": (3, 3), "padding": "same", "relu": True},
+            {"kind": "pool", "size": (2, 2)}, {"kind": "flatten"},
+            {"kind": "dense", "n_in": 16, "n_out": 4, "relu": False}, {"kind": "softmax"}]
+    rs = np.random.RandomState(21)
+    params = [{"weights": rs.randn(1, 3, 3, 3) * 0.4, "biases": np.zeros((1, 1))}, None, None,
+              {"weights": rs.randn(16, 4) * 0.3, "biases": np.zeros((1, 4))}, None]
+    rng = np.random.default_rng(22)
+    x = rng.random((8 * 3, 3, 8, 8), dtype=np.float32)
+    y = np.eye(4)[rng.integers(0, 4, 8 * 3)]
+    saved = (seam.conv2d_cpu, seam.conv2d_backward_cpu)
+    try:
+        seam.conv2d_cpu, seam.conv2d_backward_cpu = REF.conv2d_cpu, REF.conv2d_backward_cpu
+        model = ref_shim.build_model(spec, params, optimizer="adam", lr=0.01)
+        ref_losses = [ref_shim.train_step(model, x[s * 8:(s + 1) * 8], y[s * 8:(s + 1) * 8])["loss"] for s in range(3)]
+        conv, dense = model.layers[0], model.layers[3]
+        ref_flat = np.concatenate([conv.weights.ravel(), conv.biases.ravel(), dense.weights.ravel(), dense.biases.ravel()])
+    finally:
+        seam.conv2d_cpu, seam.conv2d_backward_cpu = saved
+    net = ref_net.RefNet(spec, params, optimizer="adam", lr=0.01)
+    losses = [net.step(x[s * 8:(s + 1) * 8], y[s * 8:(s + 1) * 8])["loss"] for s in range(3)]
+    np.testing.assert_allclose(losses, ref_losses, rtol=1e-6)
+    np.testing.assert_allclose(net.flat(), ref_flat, rtol=1e-4, atol=1e-6)
